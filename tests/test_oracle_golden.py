@@ -1,0 +1,279 @@
+"""Pin the CPU oracle against every known answer the reference holds for the hot path
+(SURVEY.md §8c).  CPU-only."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import hydromodels_jl_b200 as hm
+from hydromodels_jl_b200 import HydroFlux, Symbols
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+import hydro_oracle as ho  # noqa: E402
+
+EXPHYDRO_DOCS_PARAMS = dict(f=0.0167, Smax=1709.46, Qmax=18.47, Df=2.674, Tmax=0.17, Tmin=-2.09)
+
+
+# -- 1. exact flux KATs: /root/reference/test/base/run_hydro_flux.jl:8-9,22-23,36-41,55-59 ----
+def test_flux_kat_single_output():
+    s = Symbols("a b c", "p1 p2")
+    flux = HydroFlux("c ~ a * p1 + b * p2", symbols=s)
+    assert set(flux.get_input_names()) == {"a", "b"}
+    assert set(flux.get_param_names()) == {"p1", "p2"}
+    assert flux.get_output_names() == ["c"]
+    out = ho.run_flux(flux, np.array([[2.0, 3.0, 1.0], [3.0, 2.0, 2.0]]), {"params": dict(p1=3.0, p2=4.0)})
+    assert np.array_equal(out, np.array([[18.0, 17.0, 11.0]]))
+
+
+def test_flux_kat_two_outputs():
+    s = Symbols("a b c d", "p1 p2")
+    flux = HydroFlux(["c ~ a * p1 + b * p2", "d ~ a + p1 + b + p2"], symbols=s)
+    inp = np.array([[2.0, 3.0], [3.0, 2.0], [4.0, 1.0]]).T
+    out = ho.run_flux(flux, inp, {"params": dict(p1=3.0, p2=4.0)})
+    assert np.array_equal(out, np.array([[18.0, 12.0], [17.0, 12.0], [16.0, 12.0]]).T)
+
+
+def test_flux_kat_multinode_equals_replicated():
+    s = Symbols("a b c d", "p1 p2")
+    flux = HydroFlux(["c ~ a * p1 + b * p2", "d ~ a + p1 + b + p2"], symbols=s, htypes=np.arange(1, 11))
+    inp2 = np.array([[2.0, 3.0], [3.0, 2.0], [4.0, 1.0]]).T
+    out2 = np.array([[18.0, 12.0], [17.0, 12.0], [16.0, 12.0]]).T
+    # 2D fallback of a multi-node flux (`src/flux.jl:193-203`)
+    assert np.array_equal(ho.run_flux(flux, inp2, {"params": dict(p1=3.0, p2=4.0)}), out2)
+    inp3 = np.repeat(inp2[:, None, :], 10, axis=1)
+    out3 = ho.run_flux(flux, inp3, {"params": dict(p1=np.full(10, 3.0), p2=np.full(10, 4.0))})
+    assert np.array_equal(out3, np.repeat(out2[:, None, :], 10, axis=1))
+
+
+# -- 2. exact D8 KATs: /root/reference/test/miscellaneous/run_d8_grid.jl:20-31 -----------------
+def test_d8_regular_grid():
+    positions = [(1, 1), (1, 2), (1, 3), (2, 1), (2, 2), (2, 3), (3, 1), (3, 2), (3, 3)]
+    flwdir = np.array([[1, 4, 8], [1, 4, 4], [1, 1, 2]])
+    res = ho.grid_routing(flwdir, positions, np.ones(9))
+    assert np.array_equal(res, [0.0, 1.0, 0.0, 0.0, 3.0, 0.0, 0.0, 2.0, 2.0])
+
+
+def test_d8_irregular_grid():
+    positions = [(1, 2), (1, 3), (2, 1), (2, 2), (2, 3), (2, 4), (3, 2), (3, 3), (4, 3), (4, 4)]
+    flwdir = np.array([[0, 4, 4, 0], [1, 2, 4, 8], [0, 1, 4, 0], [0, 0, 1, 1]])
+    res = ho.grid_routing(flwdir, positions, np.ones(10))
+    assert np.array_equal(res, [0.0, 0.0, 0.0, 2.0, 1.0, 0.0, 0.0, 4.0, 1.0, 1.0])
+
+
+def test_d8_downstream_table_matches_pad_restatement():
+    """`GridAggregation.downstream()` (what the GPU gather uses) ≡ the literal pad_zeros push."""
+    rng = np.random.default_rng(3)
+    R, C = 7, 9
+    flw = rng.choice([0, 1, 2, 4, 8, 16, 32, 64, 128, 3], size=(R, C))
+    cells = [(r + 1, c + 1) for r in range(R) for c in range(C) if rng.random() < 0.8]
+    ag = hm.build_aggr_func(flw, cells)
+    q = rng.random(len(cells))
+    down = ag.downstream()
+    ref = ho.grid_routing(flw, cells, q)
+    mine = np.zeros(len(cells))
+    for n, d in enumerate(down):
+        if d >= 0:
+            mine[d] += q[n]
+    assert np.allclose(mine, ref, rtol=0, atol=1e-15)
+
+
+# -- 3. ExpHydro on CAMELS 01013500: docs table + NSE/PBIAS ------------------------------------
+def _run_exphydro_docs(golden, min_value):
+    d = golden("exphydro_01013500.npz")
+    model = hm.models.exphydro(docs_variant=True)
+    inp = np.stack([d["temp"], d["lday"], d["prcp"]])
+    out = ho.run_model(model, inp, {"params": EXPHYDRO_DOCS_PARAMS}, hm.HydroConfig(min_value=min_value),
+                       initstates=dict(snowpack=0.0, soilwater=1303.0))
+    return model, d, out
+
+
+def test_exphydro_published_table(golden):
+    """Rows 1-3 and 9999-10000 of the published DataFrame (`docs/src/get_start_en.md:379-387`),
+    6 significant digits as printed."""
+    model, d, out = _run_exphydro_docs(golden, 1e-6)
+    assert model.var_names == ["snowpack", "soilwater", "pet", "snowfall", "rainfall", "melt", "evap",
+                               "baseflow", "surfaceflow", "flow"]
+    table = {
+        0: [0.0, 1305.21, 1.13779, 0.0, 3.1, 0.0, 0.868733, 0.0216058, 0.0, 0.0216058],
+        1: [0.0, 1308.28, 1.51019, 0.0, 4.24, 0.0, 1.15577, 0.0227406, 0.0, 0.0227406],
+        2: [0.0, 1315.03, 1.63204, 0.0, 8.02, 0.0, 1.25547, 0.0254533, 0.0, 0.0254533],
+        9998: [279.712, 1517.91, 0.311022, 1.84, 0.0, -0.0, 0.276171, 0.753699, 0.0, 0.753699],
+        9999: [279.852, 1517.0, 0.176836, 0.14, 0.0, -0.0, 0.156927, 0.742322, 0.0, 0.742322],
+    }
+    for t, row in table.items():
+        # 6 printed digits; the table predates the `max(min_value, ·)` clamp, which
+        # moves an empty snowpack from 0 to 1e-6 and melt from 0 to 5e-7 → absolute floor 2e-6
+        assert np.allclose(out[:, t], row, rtol=6e-6, atol=2e-6), (t, out[:, t], row)
+
+
+def test_exphydro_published_nse_pbias(golden):
+    """NSE 0.7323810502829138 / PBIAS 4.127942033470476 (`docs/src/get_start_en.md:466-468`) —
+    reproduced to ~1 ulp with the clamp effectively off (the docs predate `src/solve.jl:50`)."""
+    model, d, out = _run_exphydro_docs(golden, 1e-300)
+    sim, obs = out[-1], d["flow"]
+    nse = 1 - np.sum((obs - sim) ** 2) / np.sum((obs - obs.mean()) ** 2)
+    pbias = 100 * (sim.sum() - obs.sum()) / obs.sum()
+    assert abs(nse - 0.7323810502829138) < 5e-15
+    assert abs(pbias - 4.127942033470476) < 5e-12
+    # with today's default clamp the same run gives 0.73238100115505… (oracle-derived)
+    _, _, out2 = _run_exphydro_docs(golden, 1e-6)
+    nse2 = 1 - np.sum((obs - out2[-1]) ** 2) / np.sum((obs - obs.mean()) ** 2)
+    assert abs(nse2 - 0.73238100115505) < 1e-13
+    assert abs(-ho.objective("nse", obs, sim) - nse) < 1e-15
+
+
+def test_exphydro_worked_rows(golden):
+    """SURVEY.md Appendix E.1 (default clamp)."""
+    model, d, out = _run_exphydro_docs(golden, 1e-6)
+    r = {n: out[i] for i, n in enumerate(model.var_names)}
+    assert np.allclose(r["pet"][:3], [1.1377949580991165, 1.5101916733737377, 1.632038689244646], rtol=1e-14)
+    assert np.allclose(r["evap"][:3], [0.8687325468241877, 1.155773989704324, 1.2554680791495025], rtol=1e-13)
+    assert np.allclose(r["flow"][:3], [0.021605763395262413, 0.022740582262054335, 0.02545333074333472], rtol=1e-13)
+    assert np.allclose(r["melt"][:3], 5.000025e-07, rtol=1e-6)
+    assert np.allclose(r["flow"][9998:], [0.7536987721818956, 0.7423224815940612], rtol=1e-12)
+
+
+# -- 4. unit hydrograph: GR4J fixture pr -> q9/q1 ---------------------------------------------
+def test_uh_weights_x4_139():
+    g = hm.models.gr4j()
+    uh_slow, uh_fast = g.components[1], g.components[2]
+    w1 = uh_slow.weights({"x4": 1.39})
+    w2 = uh_fast.weights({"x4": 1.39})
+    assert np.allclose(w1, [0.438998462646846, 0.5610015373531541], rtol=1e-14)
+    assert np.allclose(w2, [0.219499231323423, 0.6625584910271335, 0.11794227764944354], rtol=1e-13)
+
+
+def test_uh_reproduces_gr4j_fixture_columns(golden):
+    d = golden("gr4j_sample.npz")
+    g = hm.models.gr4j()
+    uh_slow, uh_fast = g.components[1], g.components[2]
+    p = {"params": dict(x4=1.39)}
+    q9 = ho.run_uh(uh_slow, (0.9 * d["pr"])[None, :], p)[0]
+    q1 = ho.run_uh(uh_fast, (0.1 * d["pr"])[None, :], p)[0]
+    # the third-party run agrees to ~5e-7 absolute (single-precision ordinates on its side; a
+    # wrong UH semantic — un-differenced, un-normalised or unguarded S-curve — is off by >1e-1);
+    # rows before t=4 depend on the third party's warm-up history
+    assert np.allclose(q9[3:], d["q9"][3:], rtol=0, atol=1e-6)
+    assert np.allclose(q1[3:], d["q1"][3:], rtol=0, atol=1e-6)
+
+
+def test_uh_zero_lag_is_identity_and_nonnegative():
+    s = Symbols("x y t", "lag")
+    uh = hm.UnitHydrograph(s.x, s.y, [("lag", "(t / lag)^2.5")], symbols=s)
+    x = np.abs(np.random.default_rng(0).normal(size=(1, 30)))
+    assert np.array_equal(ho.run_uh(uh, x, {"params": dict(lag=0.0)}), x)
+    y = ho.run_uh(uh, x, {"params": dict(lag=3.5)})
+    assert y.shape == (1, 30) and np.all(y >= 0)
+    assert abs(y.sum() - sum(x[0, :30 - k].sum() * w for k, w in enumerate(uh.weights({"lag": 3.5})))) < 1e-12
+
+
+# -- 5. metamorphic: multi-node == replicated single node (run_multi_bucket.jl:79,115,171,190) ---
+@pytest.mark.parametrize("shared", [False, True])
+def test_multinode_equals_replicated_single(golden, shared):
+    d = golden("exphydro_01013500.npz")
+    T, N = 100, 6
+    inp = np.stack([d["temp"][:T], d["lday"][:T], d["prcp"][:T]])
+    single = hm.models.exphydro()
+    ref = ho.run_model(single, inp, {"params": EXPHYDRO_DOCS_PARAMS}, initstates=dict(snowpack=0.0, soilwater=1303.0))
+    ht = np.array([1, 1, 2, 2, 3, 3]) if shared else np.arange(1, N + 1)
+    ntypes = int(ht.max())
+    multi = hm.models.exphydro(htypes=ht)
+    p = {"params": {k: np.full(ntypes, v) for k, v in EXPHYDRO_DOCS_PARAMS.items()}}
+    inp3 = np.repeat(inp[:, None, :], N, axis=1)
+    init = np.concatenate([np.zeros(N), np.full(N, 1303.0)])      # state-major, node-fastest
+    out = ho.run_model(multi, inp3, p, initstates=init)
+    assert out.shape == (10, N, T)
+    for n in range(N):
+        assert np.allclose(out[:, n, :], ref, rtol=0, atol=1e-10)
+    assert np.all(out[:2] >= 1e-6)
+
+
+# -- 6. HydroRoute worked example: SURVEY.md Appendix E.2 (run_hydro_route.jl:5-45) ------------
+def test_route_worked_example():
+    s = Symbols("q q_routed s_river", "lag")
+    flwdir = np.array([[1, 4, 8], [1, 4, 4], [1, 1, 2]])
+    positions = [(i, j) for i in (1, 2, 3) for j in (1, 2, 3)]
+    route = hm.HydroRoute(rfluxes=[HydroFlux("q_routed ~ s_river / (1 + lag)", symbols=s)],
+                          dfluxes=[hm.StateFlux("s_river ~ q - q_routed", symbols=s)],
+                          aggr_func=hm.build_aggr_func(flwdir, positions), htypes=np.arange(1, 10))
+    out = ho.run_route(route, np.ones((1, 9, 20)), {"params": dict(lag=np.full(9, 0.2))})
+    assert out.shape == (2, 9, 20) and np.all(out >= 0)
+    assert np.allclose(out[0, :, 0], 1.0)
+    assert np.allclose(out[0, :, 1], [1.166667, 2.0, 1.166667, 1.166667, 3.666667, 1.166667, 1.166667, 2.833333, 2.833333], atol=1e-6)
+    assert np.allclose(out[0, :, 2], [1.194444, 2.305556, 1.194444, 1.194444, 5.222222, 1.194444, 1.194444, 5.5, 4.805556], atol=1e-6)
+    assert np.allclose(out[1], out[0] / 1.2, rtol=1e-15)
+    assert out[1, 8].mean() > out[1, 0].mean()                    # outlet > source (`:142`)
+
+
+def test_graph_route_matches_grid_route():
+    """`adjacency' * q` with the same topology gives the same result as the D8 push."""
+    flwdir = np.array([[1, 4, 8], [1, 4, 4], [1, 1, 2]])
+    positions = [(i, j) for i in (1, 2, 3) for j in (1, 2, 3)]
+    grid = hm.build_aggr_func(flwdir, positions)
+    down = grid.downstream()
+    edges = [(n + 1, d + 1) for n, d in enumerate(down) if d >= 0]
+    graph = hm.build_aggr_func(9, edges)
+    q = np.random.default_rng(1).random(9)
+    assert np.allclose(ho.aggregate(grid, q), ho.aggregate(graph, q), atol=1e-15)
+
+
+# -- 7. component boundaries matter (F5) and GR4J / HBV / M50 run with the right shapes ---------
+def test_two_bucket_differs_from_single_bucket(golden):
+    d = golden("exphydro_01013500.npz")
+    T = 400
+    inp = np.stack([d["temp"][:T], d["lday"][:T], d["prcp"][:T]])
+    kw = dict(initstates=dict(snowpack=0.0, soilwater=1303.0))
+    a = ho.run_model(hm.models.exphydro(), inp, {"params": EXPHYDRO_DOCS_PARAMS}, **kw)
+    b = ho.run_model(hm.models.exphydro_single_bucket(), inp, {"params": EXPHYDRO_DOCS_PARAMS}, **kw)
+    assert a.shape == b.shape
+    assert np.max(np.abs(a[1] - b[1])) > 1e-3
+
+
+def test_gr4j_runs(golden):
+    d = golden("gr4j_sample.npz")
+    T = 100
+    g = hm.models.gr4j()
+    out = ho.run_model(g, np.stack([d["prec"][:T], d["pet"][:T]]),
+                       {"params": dict(x1=320.11, x2=2.42, x3=69.63, x4=1.39)},
+                       initstates=dict(soilwater=235.97, routingstore=45.47))
+    assert out.shape == (15, T) and np.all(out[:2] >= 0) and np.all(np.isfinite(out))
+    # plausibility against the third-party simulation in the fixture (different numerics)
+    assert abs(out[0, 50] - d["prob"][50]) / d["prob"][50] < 0.05
+
+
+def test_m50_and_hbv_run(golden):
+    d = golden("m50_01013500.npz")
+    T = 200
+    m = hm.models.m50()
+    et_nn, q_nn = hm.models.m50_chains()
+    cols = [d["Prcp"], d["Temp"], d["SnowWater"], d["SoilWater"]]
+    means, stds = [c.mean() for c in cols], [c.std(ddof=1) for c in cols]
+    p = dict(Df=2.674, Tmax=0.17, Tmin=-2.09)
+    for nm, mu, sd in zip(["prcp", "temp", "snowpack", "soilwater"], means, stds):
+        p[f"{nm}_mean"], p[f"{nm}_std"] = mu, sd
+    out = ho.run_model(m, np.stack([d["Prcp"][:T], d["Temp"][:T], d["Lday"][:T]]),
+                       {"params": p, "nns": {"etnn": et_nn.init_params(1), "qnn": q_nn.init_params(2)}},
+                       initstates=dict(snowpack=0.0, soilwater=1303.0))
+    assert out.shape == (12, T) and np.all(np.isfinite(out))
+    h = golden("hbv_sample.npz")
+    hb = hm.models.hbv()
+    hp = dict(TT=0.0, CFMAX=3.0, CFR=0.05, CWH=0.1, LP=0.7, FC=200.0, BETA=0.4, PPERC=0.05, UZL=20.0,
+              k0=0.2, k1=0.03, k2=0.02)
+    out = ho.run_model(hb, np.stack([h["prec"][:T], h["temp"][:T], h["pet"][:T]]), {"params": hp},
+                       initstates=dict(snowpack=0.0, meltwater=0.0, soilwater=100.0, suz=3.0, slz=10.0))
+    assert out.shape == (18, T) and np.all(np.isfinite(out)) and np.all(out[:5] >= 1e-6)
+
+
+# -- 8. objectives -----------------------------------------------------------------------------
+def test_objectives_formulae():
+    rng = np.random.default_rng(5)
+    o, s = rng.random(50) + 0.5, rng.random(50) + 0.5
+    assert abs(ho.mse(o, s) - np.mean((o - s) ** 2)) < 1e-15
+    r = np.corrcoef(o, s)[0, 1]
+    k = 1 - np.sqrt((r - 1) ** 2 + (s.std(ddof=1) / o.std(ddof=1) - 1) ** 2 + (s.mean() / o.mean() - 1) ** 2)
+    assert abs(ho.kge(o, s) - k) < 1e-15
+    assert ho.objective("KGE", o, s, warm_up=11) == -ho.kge(o[10:], s[10:])
+    with pytest.raises(ValueError):
+        ho.objective("rmse", o, s)
