@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — basin-timesteps/s of the fused forward-run stepper (BASELINE.json's metric).
+
+A "step" is ONE pass of the hot path over the whole synthetic batch: the workload's model run
+for all N basins × T time steps (one kernel launch).  Default workload at one GPU: ExpHydro,
+1 M basins × 365 d, FP64, full 10-row output — the configuration the north star quotes its
+target on (≥0.6 of HBM roofline on 1M-basin ExpHydro).  With N GPUs every rank owns its own
+1 M basins (weak scaling; basins are independent, no data-path collective — SURVEY.md §8e).
+
+`value`  : device-resident throughput (forcing and results in HBM; CUDA events; max over ranks).
+`e2e`    : same workload through the public functor `model(input, params, config; initstates)`
+           with pinned HOST buffers (H2D of the forcing + D2H of all rows inside the timed region).
+`roofline`: algorithmic bytes (8·(V + rows) per basin-timestep) ÷ kernel time ÷
+           measured HBM copy bandwidth (MEASURED_PEAKS.json).
+`cpu_baseline` / `--impl reference`: the CPU oracle (a port: the Julia reference cannot run
+           here) timed on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, basins per GPU, steps, description)
+    "exphydro_1M_basins_x_365d": ("exphydro", 1_000_000, 365),
+    "gr4j_uh_100k_basins_x_3650d": ("gr4j", 100_000, 3650),
+    "hbv_100k_basins_x_730d": ("hbv", 100_000, 730),
+    "m50_50k_basins_x_3650d": ("m50", 50_000, 3650),
+    "exphydro_64k_basins_x_365d": ("exphydro", 65_536, 365),
+}
+DEFAULT_WORKLOAD = "exphydro_1M_basins_x_365d"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (recipe's clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+                if self._stop_evt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.15] or [r for _, r in self.rows]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+def build_problem(hm, sy, model_name, n0, N, T):
+    ht = np.arange(1, N + 1)
+    model = getattr(hm.models, model_name)(htypes=ht)
+    p = {"params": sy.parameters(model_name, n0, n0 + N)}
+    if model_name == "m50":
+        et, q = hm.models.m50_chains()
+        p["nns"] = {"etnn": et.init_params(1) * 0.5, "qnn": q.init_params(2) * 0.5}
+    init = {k: np.full(N, v) for k, v in sy.INIT[model_name].items()}
+    return model, p, init
+
+
+def device_forcing(torch, model_name, N, T, seed):
+    """Synthetic forcing generated ON the device, layout [T][N][V] (= Julia input[V,N,T])."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    t = torch.arange(1, T + 1, device="cuda", dtype=torch.float64).view(T, 1)
+    temp = 5.0 + 15.0 * torch.sin(2 * np.pi * (t - 100.0) / 365.25) + 5.0 * torch.randn(T, N, generator=g, device="cuda", dtype=torch.float64)
+    lday = (0.5 + 0.15 * torch.sin(2 * np.pi * (t - 80.0) / 365.25)).expand(T, N)
+    u = torch.rand(T, N, generator=g, device="cuda", dtype=torch.float64)
+    prcp = torch.where(u < 0.35, -6.0 * torch.log1p(-u / 0.35 * (1 - 1e-12)), torch.zeros_like(u))
+    rows = {"exphydro": (temp, lday, prcp), "m50": (prcp, temp, lday)}
+    if model_name in ("gr4j", "hbv"):
+        pet = 29.8 * lday * 24 * 0.611 * torch.exp(17.3 * temp / (temp + 237.3)) / (temp + 273.2)
+        rows.update(gr4j=(prcp, pet), hbv=(prcp, temp, pet))
+    out = torch.stack(rows[model_name], dim=2).contiguous()
+    del temp, u, prcp
+    return out
+
+
+def cpu_reference_rate(model_name, T, target_seconds=12.0):
+    """Time the CPU oracle (numpy port, one thread) on a bounded sample of the workload."""
+    import hydromodels_jl_b200 as hm
+    from hydromodels_jl_b200 import synthetic as sy
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hydro_oracle as ho
+    n = 256
+    Ts = min(T, 365)
+    rate = None
+    while True:
+        model, p, init = build_problem(hm, sy, model_name, 0, n, Ts)
+        inp = sy.forcing(model_name, 0, n, Ts)
+        t0 = time.perf_counter()
+        ho.run_model(model, inp, p, initstates=init)
+        dt = time.perf_counter() - t0
+        rate = n * Ts / dt
+        if dt >= target_seconds / 3 or n >= 65536:
+            break
+        n = int(min(65536, max(n * 2, n * target_seconds / max(dt, 1e-3) * 0.6)))
+    return rate, dt, f"{n} basins x {Ts} steps of the same synthetic workload, numpy oracle (oracle/hydro_oracle.py)", 1
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    model_name, N, T = WORKLOADS[args.workload]
+    rows_of = {"exphydro": 10, "gr4j": 15, "hbv": 18, "m50": 12}[model_name]
+    v_of = {"exphydro": 3, "gr4j": 2, "hbv": 3, "m50": 3}[model_name]
+    unit = "basin-timesteps/s"
+    config = {"workload": args.workload, "model": model_name, "basins_per_gpu": N, "timesteps": T,
+              "rows_out": rows_of, "forcing_rows": v_of, "output": "full [rows,N,T] as the reference returns",
+              "sharding": f"basins sharded over {world} rank(s), no data-path collective",
+              "l2": "inputs+outputs per step (GBs) exceed the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, args.steps)
+        rates = []
+        for _ in range(max(0, args.warmup > 0)):
+            cpu_reference_rate(model_name, T, 2.0)
+        t0 = time.perf_counter()
+        for _ in range(min(steps, 3)):
+            rate, dt, sample, cores = cpu_reference_rate(model_name, T, 8.0)
+            rates.append(rate)
+        v = float(np.median(rates))
+        print(json.dumps({
+            "impl": "reference", "metric": "basin-timesteps/sec", "value": v, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference is pure Julia (no Julia in this image): timed the CPU oracle port; the reference's own "
+                    "published figure is ~1.05e6 basin-timesteps/s on one thread (docs/src/get_start_en.md:408)"}))
+        return 0
+
+    import torch
+    import hydromodels_jl_b200 as hm
+    from hydromodels_jl_b200 import synthetic as sy
+    from hydromodels_jl_b200.engine import DeviceRun
+
+    torch.cuda.set_device(local_rank)
+    hm.engine.init(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n0 = rank * N
+    model, p, init = build_problem(hm, sy, model_name, n0, N, T)
+    eng = hm.B200Model(model)
+    run = DeviceRun(eng, N, T, p, initstates=init)
+    d_in = device_forcing(torch, model_name, N, T, sy.SEED + 17 * rank)
+    d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
+    stream = torch.cuda.current_stream()
+    info = eng.last_kernel.info()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        run.launch(d_in.data_ptr(), d_out.data_ptr(), stream.cuda_stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
+    e0.record(stream)
+    for a, b in evs:
+        a.record(stream)
+        run.launch(d_in.data_ptr(), d_out.data_ptr(), stream.cuda_stream)
+        b.record(stream)
+    e1.record(stream)
+    barrier()
+    wall1 = time.time()
+    total_ms = e0.elapsed_time(e1)
+    kernel_ms = [a.elapsed_time(b) for a, b in evs]
+    clocks = sampler.summary(wall0, wall1)
+    t_total = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t_total.item())
+    value = world * N * T * args.steps / (total_ms_max * 1e-3)
+
+    # roofline of the dominant (only) kernel: algorithmic bytes per launch / mean launch time
+    peak, peak_src = peaks()
+    bytes_per_unit = 8 * (v_of + rows_of)
+    k_ms = float(np.mean(kernel_ms))
+    achieved = bytes_per_unit * N * T / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "hb_stepper", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_basin_timestep": bytes_per_unit, "kernel_ms": k_ms,
+                "registers": info["registers_per_thread"], "blocks_per_sm": info["max_blocks_per_sm"],
+                "dyn_smem": info["dynamic_smem_bytes"]}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get(args.workload)
+        except Exception:
+            pass
+
+    # ---- end to end through the public functor, pinned host buffers --------------------------------
+    e2e = None
+    launches = args.steps
+    if not args.no_e2e:
+        try:
+            h_in = torch.empty((T, N, v_of), dtype=torch.float64, pin_memory=True)
+            h_in.copy_(d_in)
+            h_out = torch.empty((T, N, rows_of), dtype=torch.float64, pin_memory=True)
+            torch.cuda.synchronize()
+            np_in = h_in.numpy().transpose(2, 1, 0)      # [V, N, T] Fortran-ordered view, zero copy
+            np_out = h_out.numpy().transpose(2, 1, 0)
+            assert np_in.flags.f_contiguous and np_out.flags.f_contiguous
+            del d_out
+            torch.cuda.empty_cache()
+            eng(np_in, p, initstates=init, out=np_out)   # warm-up (allocates the library workspace)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                eng(np_in, p, initstates=init, out=np_out)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            e2e = {"value": world * N * T * args.e2e_steps / dt, "unit": unit,
+                   "h2d_bytes_per_step": int(h_in.numel() * 8 + sum(np.asarray(v).nbytes for v in p["params"].values()) + 8 * N * len(init)),
+                   "d2h_bytes_per_step": int(h_out.numel() * 8), "steps": args.e2e_steps, "s_per_step": dt / args.e2e_steps,
+                   "api": "B200Model.__call__(input, params, config; initstates) with pinned host arrays"}
+            launches += args.e2e_steps + 1
+        except Exception as ex:  # e.g. not enough pinnable host memory on the box
+            e2e = {"value": None, "unit": unit, "error": f"{type(ex).__name__}: {ex}"[:300]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, dt, sample, cores = cpu_reference_rate(model_name, T)
+        cpu = {"value": rate, "unit": unit, "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
+
+    sampler.stop()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "basin-timesteps/sec", "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "kernel_ms_each": [round(x, 4) for x in kernel_ms]}))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -11,5 +11,7 @@ from .components import (Chain, ConstantInterpolation, Dense, DiscreteSolver, Gr
                          LinearInterpolation, MutableSolver, NeuralFlux, ODESolver, SolverType, StateFlux,
                          UnitHydrograph, build_aggr_func, default_config, normalize_config)
 from . import models
+from .lowering import LoweringError, lower_stepper
+from .engine import B200Model, HydroB200Error, NoDeviceError, device_count
 
 __version__ = "0.1.0"

@@ -1,0 +1,69 @@
+// Ahead-of-time (nvcc, sm_100a) kernels that do not depend on a model: measurement probes used by
+// bench.py (FP64 FMA peak for the compute-bound roofline, L2 flush) and exported through the C-ABI.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hydrob200.h"
+
+namespace {
+
+// Dependent-chain FP64 FMA probe: 8 independent accumulators per thread, ITERS x 8 DFMA each.
+__global__ void __launch_bounds__(256) hb_fp64_probe(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;   // never true; keeps the chain alive
+}
+
+__global__ void hb_fill(double *p, int64_t n, double v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Measured FP64 FMA throughput of this GPU in TFLOP/s (2 flop per FMA); the denominator for the
+// compute-bound configs (MEASURED_PEAKS.json has no FP64 entry).
+int hb_probe_fp64_tflops(double *tflops) {
+    if (!tflops) return HB_ERR_INVALID;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return HB_ERR_NO_DEVICE; }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double *d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return HB_ERR_NOMEM;
+    const int iters = 1 << 14, blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    hb_fp64_probe<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        hb_fp64_probe<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess) return HB_ERR_CUDA;
+    const double flop = 2.0 * 8.0 * iters * (double)blocks * threads;
+    *tflops = flop / (best * 1e-3) / 1e12;
+    return HB_OK;
+}
+
+// Overwrite `n` doubles (use a buffer larger than the 126 MB L2 to flush it between timed runs).
+int hb_fill_device(double *p, int64_t n, double v, void *stream) {
+    if (!p || n < 0) return HB_ERR_INVALID;
+    hb_fill<<<1184, 256, 0, (cudaStream_t)stream>>>(p, n, v);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
+}  // extern "C"

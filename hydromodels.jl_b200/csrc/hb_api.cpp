@@ -1,0 +1,621 @@
+// libhydrob200.so — host side of the C-ABI declared in include/hydrob200.h.
+//
+// Responsibilities: splice a host-generated CUDA C body into the hand-written kernel templates
+// (templates/*.cu, embedded at build time), compile with NVRTC for sm_100a, cache cubins on
+// disk, load them lazily through the driver API (entry points fetched with
+// cudaGetDriverEntryPoint, so the library itself loads on a box without libcuda) and launch.
+// No CPU execution path exists: without a device every run call returns HB_ERR_NO_DEVICE.
+#include "../../include/hydrob200.h"
+
+#include <cuda.h>
+#include <cuda_runtime_api.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "templates_embedded.h"   // generated: kStepperTemplate, kRouteTemplate
+
+namespace {
+
+thread_local std::string g_err = "";
+int g_device = -1;
+std::string g_cache_dir;
+std::mutex g_mu;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[4096];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define HB_CUDA(expr)                                                                           \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) return fail(HB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---- driver entry points ------------------------------------------------------------------------
+struct Driver {
+    bool ok = false;
+    decltype(&cuModuleLoadData) ModuleLoadData = nullptr;
+    decltype(&cuModuleUnload) ModuleUnload = nullptr;
+    decltype(&cuModuleGetFunction) ModuleGetFunction = nullptr;
+    decltype(&cuFuncSetAttribute) FuncSetAttribute = nullptr;
+    decltype(&cuFuncGetAttribute) FuncGetAttribute = nullptr;
+    decltype(&cuLaunchKernel) LaunchKernel = nullptr;
+    decltype(&cuOccupancyMaxActiveBlocksPerMultiprocessor) Occupancy = nullptr;
+    decltype(&cuGetErrorString) GetErrorString = nullptr;
+} g_drv;
+
+template <typename F>
+bool load_sym(const char *name, F &fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+        return false;
+    fn = reinterpret_cast<F>(p);
+    return true;
+}
+
+int ensure_device() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        return fail(HB_ERR_NO_DEVICE, "no CUDA device available (%s); hydrob200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (g_device < 0) g_device = 0;
+    HB_CUDA(cudaSetDevice(g_device));
+    HB_CUDA(cudaFree(nullptr));   // create / bind the primary context
+    if (!g_drv.ok) {
+        bool ok = load_sym("cuModuleLoadData", g_drv.ModuleLoadData) && load_sym("cuModuleUnload", g_drv.ModuleUnload) &&
+                  load_sym("cuModuleGetFunction", g_drv.ModuleGetFunction) &&
+                  load_sym("cuFuncSetAttribute", g_drv.FuncSetAttribute) &&
+                  load_sym("cuFuncGetAttribute", g_drv.FuncGetAttribute) && load_sym("cuLaunchKernel", g_drv.LaunchKernel) &&
+                  load_sym("cuOccupancyMaxActiveBlocksPerMultiprocessor", g_drv.Occupancy) &&
+                  load_sym("cuGetErrorString", g_drv.GetErrorString);
+        if (!ok) return fail(HB_ERR_CUDA, "could not resolve CUDA driver entry points");
+        g_drv.ok = true;
+    }
+    return HB_OK;
+}
+
+int drv_fail(CUresult r, const char *what) {
+    const char *s = nullptr;
+    if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
+    return fail(HB_ERR_CUDA, "%s failed: %s", what, s ? s : "unknown driver error");
+}
+#define HB_DRV(expr)                                  \
+    do {                                              \
+        CUresult r_ = (expr);                         \
+        if (r_ != CUDA_SUCCESS) return drv_fail(r_, #expr); \
+    } while (0)
+
+// ---- small utilities -----------------------------------------------------------------------------
+uint64_t fnv1a(const std::string &s, uint64_t h = 1469598103934665603ull) {
+    for (unsigned char c : s) {
+        h ^= c;
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+std::string lib_dir() {
+    Dl_info info;
+    if (dladdr(reinterpret_cast<void *>(&hb_version), &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t k = p.find_last_of('/');
+        return k == std::string::npos ? "." : p.substr(0, k);
+    }
+    return ".";
+}
+
+std::string cache_dir() {
+    if (!g_cache_dir.empty()) return g_cache_dir;
+    const char *env = getenv("HB_CACHE_DIR");
+    std::string d = env && *env ? env : lib_dir() + "/cache";
+    mkdir(d.c_str(), 0755);
+    return d;
+}
+
+bool read_file(const std::string &path, std::vector<char> &out) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize(n > 0 ? n : 0);
+    bool ok = n > 0 && fread(out.data(), 1, n, f) == (size_t)n;
+    fclose(f);
+    return ok;
+}
+
+void write_file_atomic(const std::string &path, const void *data, size_t n) {
+    std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    bool ok = fwrite(data, 1, n, f) == n;
+    fclose(f);
+    if (ok) rename(tmp.c_str(), path.c_str());
+    else unlink(tmp.c_str());
+}
+
+// Replace each `//@@HB:NAME` marker line of the template by the body's section of that name.
+// Body format: lines `//@@HB:NAME` open a section that runs to the next marker.
+std::string splice(const char *tmpl, const char *body) {
+    struct Sec { std::string name, text; };
+    std::vector<Sec> secs;
+    {
+        std::string b = body ? body : "";
+        size_t pos = 0;
+        Sec *cur = nullptr;
+        while (pos < b.size()) {
+            size_t eol = b.find('\n', pos);
+            if (eol == std::string::npos) eol = b.size();
+            std::string line = b.substr(pos, eol - pos);
+            if (line.rfind("//@@HB:", 0) == 0) {
+                std::string nm = line.substr(7);
+                while (!nm.empty() && (nm.back() == '\r' || nm.back() == ' ')) nm.pop_back();
+                secs.push_back({nm, ""});
+                cur = &secs.back();
+            } else if (cur) {
+                cur->text += line;
+                cur->text += '\n';
+            }
+            pos = eol + 1;
+        }
+    }
+    std::string t = tmpl, out;
+    size_t pos = 0;
+    while (pos < t.size()) {
+        size_t eol = t.find('\n', pos);
+        if (eol == std::string::npos) eol = t.size();
+        std::string line = t.substr(pos, eol - pos);
+        size_t k = line.find_first_not_of(" \t");
+        if (k != std::string::npos && line.compare(k, 7, "//@@HB:") == 0) {
+            std::string nm = line.substr(k + 7);
+            while (!nm.empty() && (nm.back() == '\r' || nm.back() == ' ')) nm.pop_back();
+            out += "// ---- begin generated section " + nm + " ----\n";
+            for (auto &s : secs)
+                if (s.name == nm) out += s.text;
+            out += "// ---- end generated section " + nm + " ----\n";
+        } else {
+            out += line;
+            out += '\n';
+        }
+        pos = eol + 1;
+    }
+    return out;
+}
+
+}  // namespace
+
+// ---- model object ----------------------------------------------------------------------------------
+struct hb_model_s {
+    int kind = 0;   // 0 stepper
+    hb_stepper_spec spec{};
+    std::string source;
+    std::string kernel_name;
+    std::vector<char> cubin;
+    bool from_cache = false;
+    // device side (lazy)
+    CUmodule module = nullptr;
+    CUfunction func = nullptr;
+    int dyn_smem = 0;
+    int block = 128;
+    int uhw_total = 0, uhh_total = 0;
+    // workspace for hb_run (host-pointer entry point)
+    struct Buf { void *p = nullptr; size_t cap = 0; };
+    Buf ws[12];
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int nvrtc_compile(const std::string &src, const std::vector<std::string> &opts, std::vector<char> &cubin, bool &from_cache) {
+    int maj = 0, min = 0;
+    nvrtcVersion(&maj, &min);
+    std::string keysrc = src;
+    for (auto &o : opts) keysrc += "\n//opt:" + o;
+    keysrc += "\n//nvrtc:" + std::to_string(maj) + "." + std::to_string(min);
+    char name[64];
+    snprintf(name, sizeof name, "%016llx_%zu.cubin", (unsigned long long)fnv1a(keysrc), keysrc.size());
+    std::string path = cache_dir() + "/" + name;
+    if (!getenv("HB_NO_CACHE") && read_file(path, cubin)) {
+        from_cache = true;
+        return HB_OK;
+    }
+    from_cache = false;
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, src.c_str(), "hb_kernel.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        return fail(HB_ERR_COMPILE, "nvrtcCreateProgram failed");
+    std::vector<const char *> copts;
+    for (auto &o : opts) copts.push_back(o.c_str());
+    nvrtcResult r = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+    if (r != NVRTC_SUCCESS) {
+        size_t n = 0;
+        nvrtcGetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        nvrtcGetProgramLog(prog, &log[0]);
+        nvrtcDestroyProgram(&prog);
+        if (log.size() > 3500) log.resize(3500);
+        return fail(HB_ERR_COMPILE, "NVRTC: %s\n%s", nvrtcGetErrorString(r), log.c_str());
+    }
+    size_t n = 0;
+    nvrtcGetCUBINSize(prog, &n);
+    cubin.resize(n);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    write_file_atomic(path, cubin.data(), cubin.size());
+    return HB_OK;
+}
+
+int stepper_smem_bytes(const hb_stepper_spec &s, int block, int stages) {
+    auto up128 = [](int x) { return (x + 127) / 128 * 128; };
+    int warps = block / 32;
+    int nn = up128(s.nn_words * 8);
+    int in_b = up128(stages * 32 * s.n_inputs * 8);
+    int out_b = s.output_mode == HB_OUT_ROWS ? up128(2 * 32 * s.n_rows * 8) : 0;
+    return nn + warps * (in_b + out_b) + warps * stages * 8;
+}
+
+int load_model(hb_model_s *m) {
+    if (m->func) return HB_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    HB_DRV(g_drv.ModuleLoadData(&m->module, m->cubin.data()));
+    HB_DRV(g_drv.ModuleGetFunction(&m->func, m->module, m->kernel_name.c_str()));
+    if (m->dyn_smem > 48 * 1024)
+        HB_DRV(g_drv.FuncSetAttribute(m->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
+    return HB_OK;
+}
+
+int ws_reserve(hb_model_s::Buf &b, size_t bytes) {
+    if (bytes <= b.cap) return HB_OK;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HB_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.cap = bytes;
+    return HB_OK;
+}
+
+int check_desc(const hb_model_s *m, const hb_run_desc *d) {
+    const hb_stepper_spec &s = m->spec;
+    if (!d || d->struct_size != (int32_t)sizeof(hb_run_desc)) return fail(HB_ERR_INVALID, "hb_run_desc.struct_size mismatch");
+    if (d->n_nodes <= 0 || d->n_steps < 0) return fail(HB_ERR_INVALID, "n_nodes must be > 0 and n_steps >= 0");
+    if (!(d->min_value > 0)) return fail(HB_ERR_INVALID, "min_value must be positive, got %g", d->min_value);
+    if (s.n_inputs > 0 && d->n_steps > 0 && !d->input) return fail(HB_ERR_INVALID, "input is NULL");
+    if (s.n_params > 0 && (!d->params || !d->param_offset || !d->param_mode)) return fail(HB_ERR_INVALID, "params / param tables are NULL");
+    for (int j = 0; j < s.n_params; ++j) {
+        int mode = d->param_mode[j];
+        int64_t off = d->param_offset[j];
+        int64_t span = mode == HB_PARAM_SCALAR ? 1 : (mode == HB_PARAM_PER_NODE ? d->n_nodes : 1);
+        if (mode < 0 || mode - HB_PARAM_GATHER >= d->n_htype_sets) return fail(HB_ERR_INVALID, "param_mode[%d]=%d refers to a missing htypes set", j, mode);
+        if (mode >= HB_PARAM_GATHER && !d->htypes) return fail(HB_ERR_INVALID, "htypes is NULL but parameter %d gathers through it", j);
+        if (off < 0 || off + span > d->n_param_values) return fail(HB_ERR_INVALID, "parameter %d addresses outside params (offset %lld)", j, (long long)off);
+    }
+    if (m->uhw_total > 0 && !d->uh_weights) return fail(HB_ERR_INVALID, "uh_weights is NULL");
+    if (s.nn_words > 0 && !d->nn_params) return fail(HB_ERR_INVALID, "nn_params is NULL");
+    if (s.output_mode == HB_OUT_ROWS) {
+        if (s.n_rows > 0 && d->n_steps > 0 && !d->out) return fail(HB_ERR_INVALID, "out is NULL");
+    } else {
+        if (!d->objective || !d->target) return fail(HB_ERR_INVALID, "objective mode needs target and objective buffers");
+        if (d->warm_up < 1 || d->warm_up > d->n_steps) return fail(HB_ERR_INVALID, "warm_up must be in 1..n_steps");
+    }
+    return HB_OK;
+}
+
+// Launch with DEVICE pointers in `d` (param tables are host pointers).
+int launch_stepper(hb_model_s *m, const hb_run_desc *d, cudaStream_t stream) {
+    const hb_stepper_spec &s = m->spec;
+    // HbArgs mirror (templates/stepper.cu): 12 pointers, 2 i64, 1 double, 4 int, then int tables
+    unsigned char buf[160 + 8 * HB_MAX_PARAMS + 16];
+    memset(buf, 0, sizeof buf);
+    size_t o = 0;
+    auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
+    const void *ptrs[12] = {d->input, d->params, d->htypes, d->initstates, d->uh_weights, d->uh_hist_in,
+                            d->nn_params, d->target, d->out, d->objective, d->final_states, d->uh_hist_out};
+    put(ptrs, sizeof ptrs);
+    int64_t N = d->n_nodes, T = d->n_steps;
+    put(&N, 8);
+    put(&T, 8);
+    double minv = d->min_value;
+    put(&minv, 8);
+    int warm = d->warm_up, tpn = d->target_per_node;
+    // TMA bulk copies need 16-byte aligned global addresses: base pointer and per-step stride
+    int tma_in = ((reinterpret_cast<uintptr_t>(d->input) & 15) == 0) && ((N * s.n_inputs) % 2 == 0);
+    int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((N * s.n_rows) % 2 == 0);
+    if (getenv("HB_DISABLE_TMA")) tma_in = tma_out = 0;
+    put(&warm, 4);
+    put(&tpn, 4);
+    put(&tma_in, 4);
+    put(&tma_out, 4);
+    int np = s.n_params > 0 ? s.n_params : 1;
+    std::vector<int> tmp(np, 0);
+    for (int j = 0; j < s.n_params; ++j) tmp[j] = d->param_offset[j];
+    put(tmp.data(), 4 * np);
+    for (int j = 0; j < s.n_params; ++j) tmp[j] = d->param_mode[j];
+    put(tmp.data(), 4 * np);
+    void *params[1] = {buf};
+    unsigned grid = (unsigned)((N + m->block - 1) / m->block);
+    if (T == 0 && s.output_mode == HB_OUT_ROWS && !d->final_states) return HB_OK;
+    HB_DRV(g_drv.LaunchKernel(m->func, grid, 1, 1, m->block, 1, 1, m->dyn_smem, (CUstream)stream, params, nullptr));
+    return HB_OK;
+}
+
+}  // namespace
+
+// ================================ C-ABI ==============================================================
+extern "C" {
+
+int hb_version(void) { return HB_ABI_VERSION; }
+const char *hb_last_error(void) { return g_err.c_str(); }
+
+int hb_device_count(int *count) {
+    if (!count) return fail(HB_ERR_INVALID, "count is NULL");
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        c = 0;
+    }
+    *count = c;
+    return HB_OK;
+}
+
+int hb_init(int device) {
+    int cnt = 0;
+    hb_device_count(&cnt);
+    if (cnt == 0) return fail(HB_ERR_NO_DEVICE, "no CUDA device available; hydrob200 has no CPU fallback");
+    if (device < 0 || device >= cnt) return fail(HB_ERR_INVALID, "device %d out of range (0..%d)", device, cnt - 1);
+    g_device = device;
+    return ensure_device();
+}
+
+int hb_set_cache_dir(const char *path) {
+    if (!path) return fail(HB_ERR_INVALID, "path is NULL");
+    g_cache_dir = path;
+    mkdir(path, 0755);
+    return HB_OK;
+}
+
+int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t *out) {
+    if (!spec || !body || !out) return fail(HB_ERR_INVALID, "NULL argument");
+    if (spec->struct_size != (int32_t)sizeof(hb_stepper_spec)) return fail(HB_ERR_INVALID, "hb_stepper_spec.struct_size mismatch");
+    if (spec->n_inputs < 0 || spec->n_rows < 0 || spec->n_states < 0 || spec->n_params < 0 || spec->n_params > HB_MAX_PARAMS ||
+        spec->n_uh < 0 || spec->n_uh > HB_MAX_UH || spec->nn_words < 0)
+        return fail(HB_ERR_INVALID, "hb_stepper_spec out of range");
+    if (spec->output_mode != HB_OUT_ROWS && spec->output_mode != HB_OUT_OBJECTIVE) return fail(HB_ERR_INVALID, "bad output_mode");
+    hb_model_s *m = new hb_model_s();
+    m->spec = *spec;
+    m->block = spec->block_threads > 0 ? spec->block_threads : 128;
+    if (m->block % 32 || m->block > 1024) { delete m; return fail(HB_ERR_INVALID, "block_threads must be a multiple of 32 <= 1024"); }
+    int stages = spec->stages > 0 ? spec->stages : 4;
+    for (int u = 0; u < spec->n_uh; ++u) {
+        if (spec->uh_kmax[u] < 1) { delete m; return fail(HB_ERR_INVALID, "uh_kmax must be >= 1"); }
+        m->uhw_total += spec->uh_kmax[u];
+        m->uhh_total += spec->uh_kmax[u] - 1;
+    }
+    m->dyn_smem = stepper_smem_bytes(*spec, m->block, stages);
+    if (m->dyn_smem > 227 * 1024) {
+        const int need = m->dyn_smem;
+        delete m;
+        return fail(HB_ERR_INVALID, "kernel needs %d bytes of shared memory (> 227 KB)", need);
+    }
+    // resident blocks per SM the shared-memory budget allows (register limit is the compiler's)
+    int minblocks = (227 * 1024) / (m->dyn_smem + 1024);
+    int cap = 2048 / m->block;
+    if (minblocks > cap) minblocks = cap;
+    if (minblocks < 1) minblocks = 1;
+    if (minblocks > 4) minblocks = 4;   // 128 regs/thread at 128 threads x 4 blocks; FP64-heavy bodies need them
+    char defs[1024];
+    snprintf(defs, sizeof defs,
+             "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_UHW_TOTAL %d\n"
+             "#define HB_UHH_TOTAL %d\n#define HB_NN_WORDS %d\n#define HB_MODE %d\n#define HB_METRIC %d\n#define HB_SHARED_FORCING %d\n"
+             "#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n",
+             spec->n_inputs, spec->output_mode == HB_OUT_ROWS ? spec->n_rows : 0, spec->n_states, spec->n_params, m->uhw_total,
+             m->uhh_total, spec->nn_words, spec->output_mode, spec->metric, spec->shared_forcing ? 1 : 0, m->block, stages, minblocks);
+    std::string full_body = std::string(defs) + body;   // body may append to DEFINES (e.g. HB_NC)
+    m->source = splice(kStepperTemplate, full_body.c_str());
+    m->kernel_name = "hb_stepper";
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
+    if (spec->max_registers > 0) opts.push_back("--maxrregcount=" + std::to_string(spec->max_registers));
+    int rc = nvrtc_compile(m->source, opts, m->cubin, m->from_cache);
+    if (rc) { delete m; return rc; }
+    *out = m;
+    return HB_OK;
+}
+
+int hb_model_source(hb_model_t m, const char **src, int64_t *len) {
+    if (!m || !src) return fail(HB_ERR_INVALID, "NULL argument");
+    *src = m->source.c_str();
+    if (len) *len = (int64_t)m->source.size();
+    return HB_OK;
+}
+
+int hb_model_cubin(hb_model_t m, const void **cubin, int64_t *len) {
+    if (!m || !cubin) return fail(HB_ERR_INVALID, "NULL argument");
+    *cubin = m->cubin.data();
+    if (len) *len = (int64_t)m->cubin.size();
+    return HB_OK;
+}
+
+int hb_model_info(hb_model_t m, hb_kernel_info *info) {
+    if (!m || !info) return fail(HB_ERR_INVALID, "NULL argument");
+    int rc = load_model(m);
+    if (rc) return rc;
+    memset(info, 0, sizeof *info);
+    int v = 0;
+    HB_DRV(g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_NUM_REGS, m->func));
+    info->registers_per_thread = v;
+    HB_DRV(g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, m->func));
+    info->static_smem_bytes = v;
+    HB_DRV(g_drv.FuncGetAttribute(&v, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, m->func));
+    info->local_bytes_per_thread = v;
+    info->dynamic_smem_bytes = m->dyn_smem;
+    info->block_threads = m->block;
+    HB_DRV(g_drv.Occupancy(&v, m->func, m->block, m->dyn_smem));
+    info->max_blocks_per_sm = v;
+    info->from_cache = m->from_cache ? 1 : 0;
+    info->cubin_bytes = (int32_t)m->cubin.size();
+    return HB_OK;
+}
+
+int hb_free_model(hb_model_t m) {
+    if (!m) return HB_OK;
+    for (auto &b : m->ws)
+        if (b.p) cudaFree(b.p);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->module && g_drv.ModuleUnload) g_drv.ModuleUnload(m->module);
+    delete m;
+    return HB_OK;
+}
+
+int hb_run_device(hb_model_t m, const hb_run_desc *d, void *stream) {
+    if (!m) return fail(HB_ERR_INVALID, "model is NULL");
+    int rc = check_desc(m, d);
+    if (rc) return rc;
+    rc = load_model(m);
+    if (rc) return rc;
+    HB_CUDA(cudaSetDevice(g_device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d->elapsed_ms) {
+        if (!m->ev0) { HB_CUDA(cudaEventCreate(&m->ev0)); HB_CUDA(cudaEventCreate(&m->ev1)); }
+        HB_CUDA(cudaEventRecord(m->ev0, st));
+    }
+    rc = launch_stepper(m, d, st);
+    if (rc) return rc;
+    if (d->elapsed_ms) {
+        HB_CUDA(cudaEventRecord(m->ev1, st));
+        HB_CUDA(cudaEventSynchronize(m->ev1));
+        HB_CUDA(cudaEventElapsedTime(d->elapsed_ms, m->ev0, m->ev1));
+    }
+    return HB_OK;
+}
+
+int hb_run(hb_model_t m, const hb_run_desc *d) {
+    if (!m) return fail(HB_ERR_INVALID, "model is NULL");
+    int rc = check_desc(m, d);
+    if (rc) return rc;
+    rc = load_model(m);
+    if (rc) return rc;
+    HB_CUDA(cudaSetDevice(g_device));
+    if (!m->stream) HB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    const hb_stepper_spec &s = m->spec;
+    const int64_t N = d->n_nodes, T = d->n_steps;
+    const int64_t Nin = s.shared_forcing ? 1 : N;
+    hb_run_desc dd = *d;
+    struct In { int slot; const void *host; size_t bytes; const void **dev; };
+    const In ins[] = {
+        {0, d->input, (size_t)T * Nin * s.n_inputs * 8, (const void **)&dd.input},
+        {1, d->params, (size_t)d->n_param_values * 8, (const void **)&dd.params},
+        {2, d->htypes, (size_t)d->n_htype_sets * N * 4, (const void **)&dd.htypes},
+        {3, d->initstates, (size_t)s.n_states * N * 8, (const void **)&dd.initstates},
+        {4, d->uh_weights, (size_t)m->uhw_total * N * 8, (const void **)&dd.uh_weights},
+        {5, d->uh_hist_in, (size_t)m->uhh_total * N * 8, (const void **)&dd.uh_hist_in},
+        {6, d->nn_params, (size_t)s.nn_words * 8, (const void **)&dd.nn_params},
+        {7, d->target, s.output_mode == HB_OUT_OBJECTIVE ? (size_t)T * (d->target_per_node ? N : 1) * 8 : 0, (const void **)&dd.target},
+    };
+    for (const In &in : ins) {
+        *in.dev = nullptr;
+        if (!in.host || in.bytes == 0) continue;
+        if ((rc = ws_reserve(m->ws[in.slot], in.bytes))) return rc;
+        HB_CUDA(cudaMemcpyAsync(m->ws[in.slot].p, in.host, in.bytes, cudaMemcpyHostToDevice, m->stream));
+        *in.dev = m->ws[in.slot].p;
+    }
+    struct Out { int slot; void *host; size_t bytes; void **dev; };
+    const Out outs[] = {
+        {8, d->out, s.output_mode == HB_OUT_ROWS ? (size_t)T * N * s.n_rows * 8 : 0, (void **)&dd.out},
+        {9, d->objective, s.output_mode == HB_OUT_OBJECTIVE ? (size_t)N * 8 : 0, (void **)&dd.objective},
+        {10, d->final_states, (size_t)s.n_states * N * 8, (void **)&dd.final_states},
+        {11, d->uh_hist_out, (size_t)m->uhh_total * N * 8, (void **)&dd.uh_hist_out},
+    };
+    for (const Out &o : outs) {
+        *o.dev = nullptr;
+        if (!o.host || o.bytes == 0) continue;
+        if ((rc = ws_reserve(m->ws[o.slot], o.bytes))) return rc;
+        *o.dev = m->ws[o.slot].p;
+    }
+    dd.elapsed_ms = nullptr;
+    if (d->elapsed_ms) {
+        if (!m->ev0) { HB_CUDA(cudaEventCreate(&m->ev0)); HB_CUDA(cudaEventCreate(&m->ev1)); }
+        HB_CUDA(cudaEventRecord(m->ev0, m->stream));
+    }
+    if ((rc = launch_stepper(m, &dd, m->stream))) return rc;
+    if (d->elapsed_ms) HB_CUDA(cudaEventRecord(m->ev1, m->stream));
+    for (const Out &o : outs) {
+        if (!o.host || o.bytes == 0) continue;
+        HB_CUDA(cudaMemcpyAsync(o.host, m->ws[o.slot].p, o.bytes, cudaMemcpyDeviceToHost, m->stream));
+    }
+    HB_CUDA(cudaStreamSynchronize(m->stream));
+    if (d->elapsed_ms) HB_CUDA(cudaEventElapsedTime(d->elapsed_ms, m->ev0, m->ev1));
+    return HB_OK;
+}
+
+// ---- memory helpers ----------------------------------------------------------------------------------
+int hb_malloc_device(void **ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail(HB_ERR_INVALID, "bad argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(HB_ERR_NOMEM, "cudaMalloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e)); }
+    return HB_OK;
+}
+int hb_free_device(void *ptr) { if (ptr) HB_CUDA(cudaFree(ptr)); return HB_OK; }
+int hb_malloc_host(void **ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail(HB_ERR_INVALID, "bad argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaError_t e = cudaMallocHost(ptr, (size_t)bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(HB_ERR_NOMEM, "cudaMallocHost(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e)); }
+    return HB_OK;
+}
+int hb_free_host(void *ptr) { if (ptr) HB_CUDA(cudaFreeHost(ptr)); return HB_OK; }
+int hb_memcpy_h2d(void *dst, const void *src, int64_t bytes, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    HB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return HB_OK;
+}
+int hb_memcpy_d2h(void *dst, const void *src, int64_t bytes, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    HB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return HB_OK;
+}
+int hb_memset_device(void *dst, int value, int64_t bytes, void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    HB_CUDA(cudaMemsetAsync(dst, value, (size_t)bytes, (cudaStream_t)stream));
+    return HB_OK;
+}
+int hb_stream_synchronize(void *stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    HB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return HB_OK;
+}
+
+}  // extern "C"

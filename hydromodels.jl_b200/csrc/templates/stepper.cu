@@ -1,0 +1,332 @@
+// =============================================================================================
+// hb_stepper — fused explicit time-stepper for per-node bucket models on B200 (sm_100a).
+//
+// Replaces, in ONE streaming pass over t, what the reference does per component in two passes
+// over the whole series (hydrosolve MutableSolver: /root/reference/src/solve.jl:31-55; bucket
+// functors: src/bucket.jl:169-256; model sequencing: src/model.jl:241-309; UH: src/uh.jl:187-237):
+//
+//   for t in 1..T:   x  <- input[:, n, t]                      (ConstantInterpolation, interpolate.jl:49)
+//     for each component k (declaration order):
+//        fluxes(x, u_pre)  -> du ;  u <- max(min_value, u + du) ;  fluxes(x, u_post) -> rows
+//        (stateless flux: one evaluation;  unit hydrograph: causal ring-buffer dot product)
+//     out[:, n, t] <- [states..., outputs...]
+//
+// This file is a TEMPLATE: the host lowers the model's expression trees to CUDA C and the
+// library splices the text in at the //@@HB:<SECTION> markers, then NVRTC-compiles for sm_100a.
+//
+// Execution model: one thread per node (basin / grid cell / ensemble member), all state in
+// registers for the whole run.  Warps are autonomous — no block-wide barrier in the time loop.
+// Every warp owns 32 consecutive nodes, so its forcing for one step is ONE contiguous
+// 32*V*8-byte run of the time-major [T][N][V] array and its results for one step ONE contiguous
+// 32*R*8-byte run of [T][N][R]:
+//   * forcing:  lane 0 issues a TMA bulk copy (cp.async.bulk global->shared, mbarrier
+//     complete_tx) HB_STAGES time steps ahead into a per-warp ring; lanes read their V values
+//     from shared memory.  Every HBM read is a full-line, coalesced bulk transfer.
+//   * results:  lanes write their R values into a per-warp shared tile, lane 0 issues a TMA
+//     bulk store (cp.async.bulk shared->global, bulk_group) — double-buffered, fire and forget.
+// Shapes that cannot meet the 16-byte TMA alignment (odd N*V or N*R, the ragged last warp,
+// N == 1) take the per-thread ld.global / st.global path of the same kernel (warp-uniform
+// branch); results are identical.
+// =============================================================================================
+
+typedef long long i64;
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+//@@HB:DEFINES
+// (generated) HB_V HB_R HB_S HB_NP HB_NC HB_UHW_TOTAL HB_UHH_TOTAL HB_NN_WORDS HB_MODE HB_METRIC
+//             HB_SHARED_FORCING HB_BLOCK HB_STAGES HB_MINBLOCKS
+
+#define HB_OBUF 2
+#define HB_WARPS (HB_BLOCK / 32)
+#define HB_ARR(n) ((n) > 0 ? (n) : 1)
+
+struct HbArgs {
+    const double *in;
+    const double *params;
+    const int *htypes;
+    const double *init;
+    const double *uhw;
+    const double *uhh_in;
+    const double *nn;
+    const double *target;
+    double *out;
+    double *obj;
+    double *final_states;
+    double *uhh_out;
+    i64 N;
+    i64 T;
+    double min_value;
+    int warm_up;
+    int target_per_node;
+    int tma_in_ok;
+    int tma_out_ok;
+    int p_off[HB_ARR(HB_NP)];
+    int p_mode[HB_ARR(HB_NP)];
+};
+
+// ---- PTX wrappers (mbarrier + TMA bulk copies) ------------------------------------------------
+__device__ __forceinline__ u32 hb_smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void hb_mbar_init(u32 bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void hb_mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hb_mbar_wait(u32 bar, u32 parity) {
+    u32 ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void hb_bulk_g2s(u32 dst, const void *src, u32 bytes, u32 bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// shared -> global, tracked by bulk async-groups
+__device__ __forceinline__ void hb_bulk_s2g(void *dst, u32 src, u32 bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void hb_bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void hb_bulk_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void hb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- math helpers shared by all generated bodies ----------------------------------------------
+// 1/x for finite, normal x > 0: MUFU.RCP64H seed + Newton steps (quadratic; seed is ~2^-20).
+// The IEEE division the compiler would emit is ~3x as many FP64-pipe instructions.
+__device__ __forceinline__ double hb_rcp_pos(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+// step_func(x) = (tanh(5x)+1)/2 (/root/reference/src/HydroModels.jl:204) == 1/(1+exp(-10x)).
+// The argument of exp is capped at 700 so 1+exp stays finite (result < 1e-304 there; the
+// reference's tanh form returns exactly 0 below x ~ -3.8 — both are 0 to within 1e-16 absolute).
+__device__ __forceinline__ double hb_step(double x) {
+    const double z = fmin(-10.0 * x, 700.0);
+    return hb_rcp_pos(1.0 + exp(z));
+}
+// tanh(x) = 1 - 2/(1+exp(2x)), same capped-logistic evaluation (absolute error < 2e-16).
+__device__ __forceinline__ double hb_tanh(double x) {
+    const double z = fmin(2.0 * x, 700.0);
+    return fma(-2.0, hb_rcp_pos(1.0 + exp(z)), 1.0);
+}
+__device__ __forceinline__ double hb_leakyrelu(double x) { return fmax(0.01 * x, x); }
+__device__ __forceinline__ double hb_clamp(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+
+//@@HB:HELPERS
+
+// ---- the kernel -------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(const __grid_constant__ HbArgs a) {
+    extern __shared__ __align__(128) unsigned char hb_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const i64 n = (i64)blockIdx.x * HB_BLOCK + threadIdx.x;
+    const i64 n0w = n - lane;
+    const bool valid = n < a.N;
+    const bool full_warp = (n0w + 32) <= a.N;
+
+    // shared-memory carve-up: [MLP params][per-warp forcing ring][per-warp result tiles][mbarriers]
+    constexpr int kNNBytes = ((HB_NN_WORDS * 8 + 127) / 128) * 128;
+    constexpr int kInStage = 32 * HB_V * 8;                       // bytes of one warp-step of forcing
+    constexpr int kInBytes = ((HB_STAGES * kInStage + 127) / 128) * 128;
+    constexpr int kOutTile = 32 * HB_R * 8;                       // bytes of one warp-step of results
+    constexpr int kOutBytes = ((HB_OBUF * kOutTile + 127) / 128) * 128;
+    double *sNN = reinterpret_cast<double *>(hb_smem);
+    unsigned char *warp_base = hb_smem + kNNBytes + (size_t)warp * (kInBytes + kOutBytes);
+    double *sIn = reinterpret_cast<double *>(warp_base);
+    double *sOut = reinterpret_cast<double *>(warp_base + kInBytes);
+    u64 *bars = reinterpret_cast<u64 *>(hb_smem + kNNBytes + (size_t)HB_WARPS * (kInBytes + kOutBytes)) + warp * HB_STAGES;
+    (void)sNN; (void)sIn; (void)sOut; (void)bars;
+
+#if HB_NN_WORDS > 0
+    for (int i = threadIdx.x; i < HB_NN_WORDS; i += HB_BLOCK) sNN[i] = a.nn[i];
+    __syncthreads();
+#endif
+
+    // warp-uniform choice of the I/O path
+    const bool tma_in = (HB_SHARED_FORCING == 0) && (HB_V > 0) && a.tma_in_ok && full_warp;
+    const bool tma_out = (HB_MODE == 0) && (HB_R > 0) && a.tma_out_ok && full_warp;
+    if (!valid) return;   // ragged last warp: that warp is on the per-thread path (no warp syncs)
+
+    // ---- per-node constants: parameters (p[htypes], /root/reference/src/utils.jl:174-201) ------
+    double hb_p[HB_ARR(HB_NP)];
+#pragma unroll
+    for (int j = 0; j < HB_NP; ++j) {
+        const int mode = a.p_mode[j];
+        i64 idx = a.p_off[j];
+        if (mode == 1) idx += n;
+        else if (mode >= 2) idx += a.htypes[(i64)(mode - 2) * a.N + n];
+        hb_p[j] = a.params[idx];
+    }
+    // ---- states: initial value is used UNCLAMPED for the first increment (solve.jl:47-49) ------
+    double hb_u[HB_ARR(HB_S)];
+#pragma unroll
+    for (int s = 0; s < HB_S; ++s) hb_u[s] = a.init ? a.init[(i64)s * a.N + n] : 0.0;
+    // ---- unit-hydrograph ordinates and history -----------------------------------------------
+    double hb_uhw[HB_ARR(HB_UHW_TOTAL)];
+    double hb_uhh[HB_ARR(HB_UHH_TOTAL)];
+#pragma unroll
+    for (int k = 0; k < HB_UHW_TOTAL; ++k) hb_uhw[k] = a.uhw[(i64)k * a.N + n];
+#pragma unroll
+    for (int k = 0; k < HB_UHH_TOTAL; ++k) hb_uhh[k] = a.uhh_in ? a.uhh_in[(i64)k * a.N + n] : 0.0;
+    double hb_c[HB_ARR(HB_NC)];   // state-only subexpressions carried from one step to the next
+    const double hb_minv = a.min_value;
+    (void)hb_p; (void)hb_u; (void)hb_uhw; (void)hb_uhh; (void)hb_c; (void)hb_minv;
+
+#if HB_MODE == 1
+    // objective accumulators (shifted sums; metrics of …OptimizationExt.jl:34-68)
+    double q_n = 0.0, q_so = 0.0, q_ss = 0.0, q_soo = 0.0, q_sss = 0.0, q_sos = 0.0, q_sse = 0.0, q_shift = 0.0;
+#endif
+
+    //@@HB:PROLOGUE
+
+    const i64 T = a.T;
+    const i64 in_step = (HB_SHARED_FORCING ? 1 : a.N) * (i64)HB_V;   // doubles per time step
+    const double *in_warp = a.in + (HB_SHARED_FORCING ? 0 : n0w * HB_V);
+    const double *in_lane = a.in + (HB_SHARED_FORCING ? 0 : n * HB_V);
+    double *out_warp = a.out + n0w * HB_R;
+    double *out_lane = a.out + n * HB_R;
+    (void)in_warp; (void)out_warp; (void)out_lane;
+
+    if (tma_in) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < HB_STAGES; ++s) hb_mbar_init(hb_smem_u32(&bars[s]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            hb_fence_proxy_async();
+#pragma unroll
+            for (int s = 0; s < HB_STAGES; ++s) {
+                if (s < T) {
+                    hb_mbar_expect_tx(hb_smem_u32(&bars[s]), kInStage);
+                    hb_bulk_g2s(hb_smem_u32(sIn + s * 32 * HB_V), in_warp + (i64)s * in_step, kInStage, hb_smem_u32(&bars[s]));
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    int slot = 0;
+    u32 parity = 0;
+    int ob = 0;
+    for (i64 t = 0; t < T; ++t) {
+        // ---- forcing of this step -------------------------------------------------------------
+        double hb_x[HB_ARR(HB_V)];
+        if (tma_in) {
+            hb_mbar_wait(hb_smem_u32(&bars[slot]), parity);
+            const double *sx = sIn + slot * 32 * HB_V + lane * HB_V;
+#pragma unroll
+            for (int v = 0; v < HB_V; ++v) hb_x[v] = sx[v];
+            __syncwarp();   // every lane has consumed the slot -> refill it HB_STAGES steps ahead
+            if (lane == 0 && t + HB_STAGES < T) {
+                hb_mbar_expect_tx(hb_smem_u32(&bars[slot]), kInStage);
+                hb_bulk_g2s(hb_smem_u32(sIn + slot * 32 * HB_V), in_warp + (t + HB_STAGES) * in_step, kInStage,
+                            hb_smem_u32(&bars[slot]));
+            }
+            if (++slot == HB_STAGES) { slot = 0; parity ^= 1; }
+        } else {
+            const double *gx = in_lane + t * in_step;
+#pragma unroll
+            for (int v = 0; v < HB_V; ++v) hb_x[v] = gx[v];
+        }
+        double hb_out[HB_ARR(HB_R)];
+        (void)hb_x; (void)hb_out;
+#if HB_MODE == 1
+        double hb_sim = 0.0;
+#endif
+
+        //@@HB:STEP
+
+        // ---- results of this step -------------------------------------------------------------
+#if HB_MODE == 0 && HB_R > 0
+        if (tma_out) {
+            double *so = sOut + ob * 32 * HB_R;
+            if (t >= HB_OBUF) {   // the bulk store that last read this tile must have drained it
+                if (lane == 0) hb_bulk_wait_read<HB_OBUF - 1>();
+                __syncwarp();
+            }
+#pragma unroll
+            for (int r = 0; r < HB_R; ++r) so[lane * HB_R + r] = hb_out[r];
+            hb_fence_proxy_async();   // generic-proxy writes -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0) {
+                hb_bulk_s2g(out_warp + t * a.N * HB_R, hb_smem_u32(so), kOutTile);
+                hb_bulk_commit();
+            }
+            ob ^= 1;
+        } else {
+            double *go = out_lane + t * a.N * HB_R;
+#pragma unroll
+            for (int r = 0; r < HB_R; ++r) go[r] = hb_out[r];
+        }
+#endif
+#if HB_MODE == 1
+        if (t + 1 >= a.warm_up) {
+            double o = a.target_per_node ? a.target[t * a.N + n] : a.target[t];
+            double s = hb_sim;
+#if HB_METRIC == 3
+            o = log(o + 1e-6);
+            s = log(s + 1e-6);
+#endif
+            if (q_n == 0.0) q_shift = o;
+            const double od = o - q_shift, sd = s - q_shift, e = o - s;
+            q_n += 1.0; q_so += od; q_ss += sd;
+            q_soo = fma(od, od, q_soo); q_sss = fma(sd, sd, q_sss); q_sos = fma(od, sd, q_sos);
+            q_sse = fma(e, e, q_sse);
+        }
+#endif
+    }
+    if (tma_out && lane == 0) hb_bulk_wait<0>();   // shared tiles must outlive the last bulk stores
+
+    // ---- epilogue: final states / UH history for chunked-T runs, objective ---------------------
+    if (a.final_states) {
+#pragma unroll
+        for (int s = 0; s < HB_S; ++s) a.final_states[(i64)s * a.N + n] = hb_u[s];
+    }
+    if (a.uhh_out) {
+#pragma unroll
+        for (int k = 0; k < HB_UHH_TOTAL; ++k) a.uhh_out[(i64)k * a.N + n] = hb_uhh[k];
+    }
+#if HB_MODE == 1
+    {
+        const double var_o = q_soo - q_so * q_so / q_n;   // = sum (o - mean o)^2
+        double val;
+#if HB_METRIC == 0
+        val = q_sse / q_n;                                 // MSE
+#elif HB_METRIC == 1
+        val = -(1.0 - q_sse / var_o);                      // -NSE
+#else
+        const double var_s = q_sss - q_ss * q_ss / q_n;
+        const double cov = q_sos - q_so * q_ss / q_n;
+        const double r = cov / sqrt(var_o * var_s);
+        const double alpha = sqrt(var_s / var_o);          // std(sim)/std(obs), (n-1) cancels
+        const double beta = (q_ss + q_n * q_shift) / (q_so + q_n * q_shift);
+        val = -(1.0 - sqrt((r - 1.0) * (r - 1.0) + (alpha - 1.0) * (alpha - 1.0) + (beta - 1.0) * (beta - 1.0)));
+#endif
+        a.obj[n] = val;
+    }
+#endif
+    //@@HB:EPILOGUE
+}

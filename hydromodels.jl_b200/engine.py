@@ -1,0 +1,662 @@
+"""Engine: the drop-in functor `component(input, params, config; initstates)` on the GPU.
+
+`B200Model(component)` is the wrapper component of SURVEY.md §8(b): same call signature and
+result layout as the reference functors (`/root/reference/src/model.jl:241-309`,
+`src/bucket.jl:169-256`, `src/flux.jl:157-203`, `src/uh.jl:209-274`), executed by the
+NVRTC-compiled stepper behind the C-ABI `libhydrob200.so` (`include/hydrob200.h`, bound here
+with `ctypes`).  There is NO CPU path: if the library is missing, or there is no CUDA device,
+calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .components import (Component, ConstantInterpolation, HydroBucket, HydroConfig, HydroFlux, HydroModel,
+                         HydroRoute, LinearInterpolation, SolverType, UnitHydrograph, normalize_config)
+from .lowering import LoweringError, StepperProgram, lower_stepper
+from .symbolic import evaluate_np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhydrob200.so")
+
+HB_MAX_UH = 8
+HB_OUT_ROWS, HB_OUT_OBJECTIVE = 0, 1
+METRICS = {"mse": 0, "nse": 1, "kge": 2, "logkge": 3}
+
+
+class HydroB200Error(RuntimeError):
+    pass
+
+
+class NoDeviceError(HydroB200Error):
+    pass
+
+
+class StepperSpec(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_inputs", C.c_int32), ("n_rows", C.c_int32), ("n_states", C.c_int32),
+                ("n_params", C.c_int32), ("n_uh", C.c_int32), ("uh_kmax", C.c_int32 * HB_MAX_UH),
+                ("nn_words", C.c_int32), ("output_mode", C.c_int32), ("metric", C.c_int32),
+                ("shared_forcing", C.c_int32), ("block_threads", C.c_int32), ("stages", C.c_int32),
+                ("max_registers", C.c_int32)]
+
+
+class RunDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_htype_sets", C.c_int32), ("n_nodes", C.c_int64), ("n_steps", C.c_int64),
+                ("input", C.c_void_p), ("params", C.c_void_p), ("n_param_values", C.c_int64),
+                ("param_offset", C.c_void_p), ("param_mode", C.c_void_p), ("htypes", C.c_void_p),
+                ("initstates", C.c_void_p), ("uh_weights", C.c_void_p), ("uh_hist_in", C.c_void_p),
+                ("nn_params", C.c_void_p), ("target", C.c_void_p), ("target_per_node", C.c_int32),
+                ("warm_up", C.c_int32), ("min_value", C.c_double), ("out", C.c_void_p), ("objective", C.c_void_p),
+                ("final_states", C.c_void_p), ("uh_hist_out", C.c_void_p), ("elapsed_ms", C.c_void_p)]
+
+
+class KernelInfo(C.Structure):
+    _fields_ = [("registers_per_thread", C.c_int32), ("static_smem_bytes", C.c_int32), ("dynamic_smem_bytes", C.c_int32),
+                ("local_bytes_per_thread", C.c_int32), ("block_threads", C.c_int32), ("max_blocks_per_sm", C.c_int32),
+                ("from_cache", C.c_int32), ("cubin_bytes", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load `libhydrob200.so` (built in-tree by `__graft_entry__.build()`); fail loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HydroB200Error(f"{LIB_PATH} not found — run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                             "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.hb_last_error.restype = C.c_char_p
+    L.hb_version.restype = C.c_int
+    for name, args in {
+        "hb_device_count": [C.POINTER(C.c_int)], "hb_init": [C.c_int], "hb_set_cache_dir": [C.c_char_p],
+        "hb_compile_stepper": [C.POINTER(StepperSpec), C.c_char_p, C.POINTER(C.c_void_p)],
+        "hb_model_source": [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)],
+        "hb_model_cubin": [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)],
+        "hb_model_info": [C.c_void_p, C.POINTER(KernelInfo)], "hb_free_model": [C.c_void_p],
+        "hb_run": [C.c_void_p, C.POINTER(RunDesc)], "hb_run_device": [C.c_void_p, C.POINTER(RunDesc), C.c_void_p],
+        "hb_malloc_device": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_device": [C.c_void_p],
+        "hb_malloc_host": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_host": [C.c_void_p],
+        "hb_memcpy_h2d": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
+        "hb_memcpy_d2h": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
+        "hb_memset_device": [C.c_void_p, C.c_int, C.c_int64, C.c_void_p], "hb_stream_synchronize": [C.c_void_p],
+        "hb_probe_fp64_tflops": [C.POINTER(C.c_double)],
+        "hb_fill_device": [C.c_void_p, C.c_int64, C.c_double, C.c_void_p],
+    }.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    if L.hb_version() != 1:
+        raise HydroB200Error("libhydrob200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc == 0:
+        return
+    msg = lib().hb_last_error().decode("utf-8", "replace")
+    if rc == 2:
+        raise NoDeviceError(msg)
+    if rc == 1:
+        raise ValueError(msg)
+    if rc == 5:
+        raise MemoryError(msg)
+    raise HydroB200Error(msg)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib().hb_device_count(C.byref(n)))
+    return n.value
+
+
+def init(device: int = 0):
+    check(lib().hb_init(int(device)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# compiled kernels
+# ---------------------------------------------------------------------------------------------------
+class CompiledStepper:
+    def __init__(self, program: StepperProgram, *, metric: int = 0, shared_forcing: bool = False,
+                 block_threads: int = 0, stages: int = 0, max_registers: int = 0):
+        self.program = program
+        spec = StepperSpec()
+        spec.struct_size = C.sizeof(StepperSpec)
+        spec.n_inputs = len(program.input_names)
+        spec.n_rows = 0 if program.objective else len(program.row_names)
+        spec.n_states = len(program.state_names)
+        spec.n_params = len(program.param_slots)
+        spec.n_uh = len(program.uh)
+        if spec.n_uh > HB_MAX_UH:
+            raise LoweringError(f"at most {HB_MAX_UH} unit hydrographs per model")
+        for i, k in enumerate(program.uh_kmax):
+            spec.uh_kmax[i] = k
+        spec.nn_words = program.nn_words
+        spec.output_mode = HB_OUT_OBJECTIVE if program.objective else HB_OUT_ROWS
+        spec.metric = metric
+        spec.shared_forcing = 1 if shared_forcing else 0
+        spec.block_threads = block_threads
+        spec.stages = stages
+        spec.max_registers = max_registers
+        self.spec = spec
+        h = C.c_void_p()
+        check(lib().hb_compile_stepper(C.byref(spec), program.body.encode(), C.byref(h)))
+        self.handle = h
+
+    def source(self) -> str:
+        s = C.c_char_p()
+        n = C.c_int64()
+        check(lib().hb_model_source(self.handle, C.byref(s), C.byref(n)))
+        return s.value.decode()
+
+    def cubin(self) -> bytes:
+        p = C.c_void_p()
+        n = C.c_int64()
+        check(lib().hb_model_cubin(self.handle, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value)
+
+    def info(self) -> Dict[str, int]:
+        k = KernelInfo()
+        check(lib().hb_model_info(self.handle, C.byref(k)))
+        return {f: getattr(k, f) for f, _ in KernelInfo._fields_}
+
+    def __del__(self):
+        try:
+            if self.handle and _lib is not None:
+                _lib.hb_free_model(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------------
+# argument preparation (host side of the functor)
+# ---------------------------------------------------------------------------------------------------
+def _as_componentvector(params):
+    if not isinstance(params, dict) or "params" not in params:
+        # the reference has no method for plain vectors either (`src/utils.jl:15,22`)
+        raise TypeError("params must be a dict {'params': {...}, 'nns': {...}} (ComponentVector stand-in)")
+    return params
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class PreparedRun:
+    """Host arrays of one call, in the C-ABI layouts."""
+
+    def __init__(self):
+        self.keep: List[np.ndarray] = []
+
+
+def _check_config(cfg: HydroConfig, T: int):
+    if cfg.solver == SolverType.ODESolver:
+        raise NotImplementedError("ODESolver is not part of the B200 engine (explicit MutableSolver stepping only)")
+    if cfg.interpolator not in (ConstantInterpolation, LinearInterpolation):
+        raise NotImplementedError("only Constant/Linear interpolation at integer time indices is supported")
+    if len(cfg.timeidx) and list(cfg.timeidx) != list(range(1, T + 1)):
+        # values index `input` directly and pass 2 uses the whole input (`src/interpolate.jl:39,49`,
+        # `src/bucket.jl:190`): only 1:T is well-formed in the reference
+        raise ValueError("timeidx must be empty or 1:size(input, end)")
+
+
+def _uh_weight_table(uh: UnitHydrograph, pvals: Dict[str, np.ndarray]) -> np.ndarray:
+    """[K_max, n] normalised ordinates for `n` parameter sets (zero-padded; K = 0 → identity).
+    Semantics: `UnitHydrograph.weights` (`/root/reference/src/uh.jl:215-229,188`)."""
+    n = len(next(iter(pvals.values()))) if pvals else 1
+    lag = np.broadcast_to(np.asarray(evaluate_np(uh.uh_conds[0][0], pvals), dtype=np.float64), (n,))
+    K = np.ceil(lag).astype(np.int64)
+    K = np.maximum(K, 0)
+    kmax = max(1, int(K.max()) if n else 1)
+    thr = [np.broadcast_to(np.asarray(evaluate_np(c, pvals), dtype=np.float64), (n,)) for c, _ in uh.uh_conds]
+    S = np.ones((kmax + 1, n))
+    S[0] = 0.0
+    for k in range(1, kmax + 1):
+        env = dict(pvals)
+        env[uh.tvar] = np.float64(k)
+        val = np.ones(n)                     # S = 1 beyond the largest threshold
+        best = np.full(n, np.inf)
+        for (c, v), th in zip(uh.uh_conds, thr):   # the condition with the smallest threshold >= k wins
+            sel = (k <= th) & (th < best)
+            if sel.any():
+                cand = np.broadcast_to(np.asarray(evaluate_np(v, env), dtype=np.float64), (n,))
+                val = np.where(sel, cand, val)
+                best = np.where(sel, th, best)
+        S[k] = val
+    w = S[1:] - S[:-1]
+    kk = np.arange(1, kmax + 1)[:, None]
+    w = np.where(kk <= K[None, :], w, 0.0)
+    tot = w.sum(axis=0)
+    with np.errstate(all="ignore"):
+        w = np.where(K[None, :] > 0, w / tot, 0.0)
+    w[0, K == 0] = 1.0                      # K == 0: the reference returns the input unchanged
+    return np.ascontiguousarray(w)
+
+
+class B200Model:
+    """Wrapper component: `B200Model(model)(input, params, config; initstates)`."""
+
+    def __init__(self, component: Component, *, fast: bool = True, block_threads: int = 0, stages: int = 0,
+                 max_registers: int = 0):
+        self.component = component
+        self.fast = fast
+        self.block_threads, self.stages, self.max_registers = block_threads, stages, max_registers
+        self._cache: Dict[Tuple, CompiledStepper] = {}
+        self.last_kernel: Optional[CompiledStepper] = None
+        if isinstance(component, HydroModel):
+            comps = component.components
+        else:
+            comps = (component,)
+        if any(isinstance(c, HydroRoute) for c in comps):
+            raise NotImplementedError("HydroRoute models are not lowered yet")
+        self.multinode = component.htypes is not None if not isinstance(component, HydroModel) else \
+            all(c.htypes is not None for c in comps)
+
+    # -- name getters forward to the wrapped component ----------------------------------------------
+    def get_input_names(self): return self.component.get_input_names()
+    def get_output_names(self): return self.component.get_output_names()
+    def get_state_names(self): return self.component.get_state_names()
+    def get_param_names(self): return self.component.get_param_names()
+    def get_nn_names(self): return self.component.get_nn_names()
+
+    # -- compile ------------------------------------------------------------------------------------
+    def compiled(self, *, rows=None, objective=False, metric=0, shared_forcing=False,
+                 uh_kmax: Sequence[int] = ()) -> CompiledStepper:
+        key = (tuple(rows) if rows is not None else None, objective, metric, shared_forcing, tuple(uh_kmax))
+        if key not in self._cache:
+            prog = lower_stepper(self.component, rows=rows, objective=objective,
+                                 uh_kmax=list(uh_kmax) if len(uh_kmax) else None, fast=self.fast)
+            self._cache[key] = CompiledStepper(prog, metric=metric, shared_forcing=shared_forcing,
+                                               block_threads=self.block_threads, stages=self.stages,
+                                               max_registers=self.max_registers)
+        self.last_kernel = self._cache[key]
+        return self._cache[key]
+
+    # -- host argument marshalling ------------------------------------------------------------------
+    def _dims(self, input: np.ndarray, shared_forcing: bool, n_members: Optional[int]) -> Tuple[int, int]:
+        comp = self.component
+        V = len(comp.input_names)
+        kind = type(comp).__name__
+        if self.multinode:
+            if input.ndim != 3:
+                raise ValueError(f"{kind} with htypes only accepts 3D input (variables × nodes × time).\n"
+                                 f"For single-node computation, omit htypes.\nGot input shape: {input.shape}")
+            N = input.shape[1]
+        else:
+            if input.ndim != 2:
+                raise ValueError(f"{kind} without htypes only accepts 2D input (variables × time).\n"
+                                 f"For multi-node computation, provide htypes.\nGot input shape: {input.shape}")
+            N = 1
+        if input.shape[0] != V:
+            raise AssertionError("Input variables length mismatch")
+        if shared_forcing:
+            if N != 1:
+                raise ValueError("shared forcing expects a single forcing column")
+            N = int(n_members)
+        return N, input.shape[-1]
+
+    def prepare(self, prog: StepperProgram, params, N: int, *, ensemble: bool = False):
+        """Flat parameter table + modes + htypes + UH ordinates + MLP parameters."""
+        params = _as_componentvector(params)
+        pdict = params["params"]
+        names: List[str] = []
+        for nm, _ in prog.param_slots:
+            if nm not in names:
+                names.append(nm)
+        for u in prog.uh:
+            for nm in u.param_names:
+                if nm not in names:
+                    names.append(nm)
+        offs, chunks, pos = {}, [], 0
+        vecs: Dict[str, np.ndarray] = {}
+        for nm in names:
+            if nm not in pdict:
+                raise KeyError(f"Parameter {nm} does not exist in params")
+            v = np.atleast_1d(np.asarray(pdict[nm], dtype=np.float64)).reshape(-1)
+            vecs[nm] = v
+            offs[nm] = pos
+            chunks.append(v)
+            pos += v.size
+        flat = np.ascontiguousarray(np.concatenate(chunks)) if chunks else np.zeros(1)
+        sets0 = []
+        for h in prog.htype_sets:
+            if len(h) != N:
+                raise ValueError(f"htypes has {len(h)} entries but the input has {N} nodes")
+            sets0.append(np.asarray(h, dtype=np.int64) - 1)
+
+        def mode_of(nm: str, hs: Optional[int]) -> int:
+            v = vecs[nm]
+            if ensemble:                       # one parameter set per ensemble member
+                if v.size == N:
+                    return 1
+                if v.size == 1:
+                    return 0
+                raise ValueError(f"ensemble parameter {nm} must have 1 or {N} values")
+            if hs is None:
+                if v.size != 1:
+                    raise ValueError(f"single-node component expects scalar parameter {nm}")
+                return 0
+            h0 = sets0[hs]
+            if h0.size and (h0.min() < 0 or h0.max() >= v.size):
+                raise IndexError(f"BoundsError: attempt to access {v.size}-element parameter {nm} at index htypes")
+            if v.size == N and np.array_equal(h0, np.arange(N)):
+                return 1
+            return 2 + hs
+        p_off = np.array([offs[nm] for nm, _ in prog.param_slots] or [0], dtype=np.int32)
+        p_mode = np.array([mode_of(nm, hs) for nm, hs in prog.param_slots] or [0], dtype=np.int32)
+        htypes = np.ascontiguousarray(np.stack(sets0).astype(np.int32)) if sets0 else None
+        # unit hydrographs: ordinates per node (host-evaluated N×K table)
+        uhw = None
+        kmax: List[int] = []
+        if prog.uh:
+            tabs = []
+            for u, hs in zip(prog.uh, prog.uh_htype_set):
+                pv = {nm: vecs[nm] for nm in u.param_names}
+                if ensemble or hs is None:
+                    n = max([v.size for v in pv.values()] or [1])
+                    pv = {k: np.broadcast_to(v, (n,)) for k, v in pv.items()}
+                    w = _uh_weight_table(u, pv)
+                    w = np.broadcast_to(w, (w.shape[0], N)) if w.shape[1] == 1 else w
+                else:
+                    h0 = sets0[hs]
+                    for nm, v in pv.items():
+                        if h0.size and h0.max() >= v.size:
+                            raise IndexError(f"BoundsError: parameter {nm} indexed by htypes")
+                    w = _uh_weight_table(u, pv)[:, h0]
+                tabs.append(np.ascontiguousarray(w))
+                kmax.append(w.shape[0])
+            uhw = tabs
+        nn = None
+        if prog.nn_layout:
+            nns = params.get("nns", {})
+            parts = []
+            for name, off, n in prog.nn_layout:
+                if name not in nns:
+                    raise KeyError(f"Neural network parameters {name} do not exist in params[:nns]")
+                v = np.asarray(nns[name], dtype=np.float64).reshape(-1)
+                if v.size != n:
+                    raise ValueError(f"chain {name} expects {n} parameters, got {v.size}")
+                parts.append(v)
+            nn = np.ascontiguousarray(np.concatenate(parts))
+        return flat, p_off, p_mode, htypes, uhw, kmax, nn
+
+    def _initstates(self, prog: StepperProgram, initstates, N: int) -> Optional[np.ndarray]:
+        S = len(prog.state_names)
+        if S == 0 or initstates is None:
+            return None                       # zeros (`model._defaultstates`, `src/model.jl:51-52`)
+        if isinstance(initstates, dict):
+            out = np.empty((S, N), dtype=np.float64)
+            for i, s in enumerate(prog.state_names):
+                if s not in initstates:
+                    raise KeyError(f"State {s} not found in initstates")
+                out[i] = np.broadcast_to(np.asarray(initstates[s], dtype=np.float64), (N,))
+            return out
+        v = np.asarray(initstates, dtype=np.float64).reshape(-1)
+        if v.size != S * N:
+            raise ValueError(f"initstates has {v.size} elements, expected {S}*{N} (state-major, node-fastest)")
+        return np.ascontiguousarray(v.reshape(S, N))
+
+    # -- the functor ----------------------------------------------------------------------------------
+    def __call__(self, input, params, config=None, *, initstates=None, rows: Optional[Sequence[str]] = None,
+                 return_final_states: bool = False, out: Optional[np.ndarray] = None, timing: Optional[dict] = None):
+        cfg = normalize_config(config[0] if isinstance(config, (tuple, list)) else config)
+        if isinstance(config, (tuple, list)):
+            ncomp = len(self.component.components) if isinstance(self.component, HydroModel) else 1
+            if len(config) != ncomp:
+                raise ValueError("Component configs length must equal components length")
+            cfgs = [normalize_config(c) for c in config]
+            if any((c.min_value != cfg.min_value) for c in cfgs):
+                raise NotImplementedError("per-component min_value is not supported by the fused stepper")
+        input = np.asarray(input)
+        if input.dtype != np.float64:
+            input = input.astype(np.float64)
+        N, T = self._dims(input, False, None)
+        _check_config(cfg, T)
+        inp = input if input.flags.f_contiguous else np.asfortranarray(input)   # memory = [T][N][V]
+        # first pass over the parameters to size the unit hydrographs (compile-time K_max)
+        prog0 = self.compiled(rows=rows).program if not self._has_uh() else None
+        if prog0 is None:
+            probe = lower_stepper(self.component, rows=rows, fast=self.fast)
+            _, _, _, _, _, kmax, _ = self.prepare(probe, params, N)
+            ck = self.compiled(rows=rows, uh_kmax=kmax)
+        else:
+            ck = self.compiled(rows=rows)
+        prog = ck.program
+        flat, p_off, p_mode, htypes, uhw, kmax, nn = self.prepare(prog, params, N)
+        uhw_flat = np.ascontiguousarray(np.concatenate(uhw, axis=0)) if uhw else None
+        init = self._initstates(prog, initstates, N)
+        R = len(prog.row_names)
+        shape = (R, T) if not self.multinode else (R, N, T)
+        if out is None:
+            out = np.empty(shape, dtype=np.float64, order="F")                  # memory = [T][N][R]
+        elif out.shape != shape or not out.flags.f_contiguous or out.dtype != np.float64:
+            raise ValueError("out must be a Fortran-ordered float64 array of the result shape")
+        S = len(prog.state_names)
+        final = np.empty((S, N), dtype=np.float64) if (return_final_states and S) else None
+        elapsed = C.c_float(0.0)
+        d = RunDesc()
+        d.struct_size = C.sizeof(RunDesc)
+        d.n_htype_sets = 0 if htypes is None else htypes.shape[0]
+        d.n_nodes, d.n_steps = N, T
+        d.input = _ptr(inp)
+        d.params, d.n_param_values = _ptr(flat), flat.size
+        d.param_offset, d.param_mode = _ptr(p_off), _ptr(p_mode)
+        d.htypes = _ptr(htypes)
+        d.initstates = _ptr(init)
+        d.uh_weights = _ptr(uhw_flat)
+        d.nn_params = _ptr(nn)
+        d.min_value = cfg.min_value
+        d.warm_up = 1
+        d.out = _ptr(out)
+        d.final_states = _ptr(final)
+        d.elapsed_ms = C.cast(C.byref(elapsed), C.c_void_p)
+        check(lib().hb_run(ck.handle, C.byref(d)))
+        if timing is not None:
+            timing["kernel_ms"] = elapsed.value
+        if return_final_states:
+            return out, final
+        return out
+
+    def _has_uh(self) -> bool:
+        comps = self.component.components if isinstance(self.component, HydroModel) else (self.component,)
+        return any(isinstance(c, UnitHydrograph) for c in comps)
+
+    # -- calibration ensembles: fused objective --------------------------------------------------------
+    def objective(self, input, params, target, *, metric: str = "NSE", warm_up: int = 1, config=None,
+                  initstates=None, n_members: Optional[int] = None, timing: Optional[dict] = None) -> np.ndarray:
+        """`loss(target[warm_up:end], model(input, p_i, config; initstates)[end, warm_up:end])` for
+        every parameter set / node `i` in one launch
+        (`/root/reference/ext/HydroModelsOptimizationExt/HydroModelsOptimizationExt.jl:153-175`).
+
+        * single-node model + `n_members`: a calibration ensemble — `input` is `[V, T]`, shared by all
+          members, every parameter is a scalar or a vector of `n_members` values;
+        * multi-node model: one objective per node, `target` is `[T]` (shared) or `[N, T]`."""
+        m = metric.lower()
+        if m not in METRICS:
+            raise ValueError(f"Unknown metric: {metric}. Supported metrics: KGE, NSE, LogKGE, MSE")
+        cfg = normalize_config(config)
+        input = np.asarray(input, dtype=np.float64)
+        ensemble = n_members is not None
+        if ensemble and self.multinode:
+            raise ValueError("ensembles are built from single-node models")
+        N, T = self._dims(input, ensemble, n_members)
+        _check_config(cfg, T)
+        inp = input if input.flags.f_contiguous else np.asfortranarray(input)
+        if self._has_uh():
+            probe = lower_stepper(self.component, objective=True, fast=self.fast)
+            kmax = self.prepare(probe, params, N, ensemble=ensemble)[5]
+        else:
+            kmax = []
+        ck = self.compiled(objective=True, metric=METRICS[m], shared_forcing=ensemble, uh_kmax=kmax)
+        prog = ck.program
+        flat, p_off, p_mode, htypes, uhw, kmax, nn = self.prepare(prog, params, N, ensemble=ensemble)
+        uhw_flat = np.ascontiguousarray(np.concatenate(uhw, axis=0)) if uhw else None
+        init = self._initstates(prog, initstates, N)
+        tgt = np.asarray(target, dtype=np.float64)
+        per_node = 0
+        if tgt.ndim == 2:
+            if tgt.shape != (N, T):
+                raise ValueError("target must be [T] or [N, T]")
+            tgt = np.ascontiguousarray(tgt.T)
+            per_node = 1
+        elif tgt.shape != (T,):
+            raise ValueError("target must be [T] or [N, T]")
+        tgt = np.ascontiguousarray(tgt)
+        obj = np.empty(N, dtype=np.float64)
+        elapsed = C.c_float(0.0)
+        d = RunDesc()
+        d.struct_size = C.sizeof(RunDesc)
+        d.n_htype_sets = 0 if htypes is None else htypes.shape[0]
+        d.n_nodes, d.n_steps = N, T
+        d.input = _ptr(inp)
+        d.params, d.n_param_values = _ptr(flat), flat.size
+        d.param_offset, d.param_mode = _ptr(p_off), _ptr(p_mode)
+        d.htypes = _ptr(htypes)
+        d.initstates = _ptr(init)
+        d.uh_weights = _ptr(uhw_flat)
+        d.nn_params = _ptr(nn)
+        d.target, d.target_per_node, d.warm_up = _ptr(tgt), per_node, int(warm_up)
+        d.min_value = cfg.min_value
+        d.objective = _ptr(obj)
+        d.elapsed_ms = C.cast(C.byref(elapsed), C.c_void_p)
+        check(lib().hb_run(ck.handle, C.byref(d)))
+        if timing is not None:
+            timing["kernel_ms"] = elapsed.value
+        return obj
+
+
+def run_component(component: Component, input, params, config=None, *, initstates=None, **kwargs):
+    """`component(input, params, config; initstates)` — what `Component.__call__` dispatches to."""
+    eng = getattr(component, "_b200_engine", None)
+    if eng is None:
+        eng = B200Model(component)
+        component._b200_engine = eng
+    return eng(input, params, config, initstates=initstates, **kwargs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-resident runs (benchmarks, multi-GPU shards, chained calls): hb_run_device
+# ---------------------------------------------------------------------------------------------------
+class DeviceBuffer:
+    """A device allocation owned through the C-ABI (no torch needed)."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(lib().hb_malloc_device(C.byref(p), max(self.nbytes, 8)))
+        self.ptr = p.value
+
+    @classmethod
+    def from_host(cls, a: np.ndarray, stream=None) -> "DeviceBuffer":
+        a = np.ascontiguousarray(a)
+        b = cls(a.nbytes)
+        check(lib().hb_memcpy_h2d(b.ptr, a.ctypes.data_as(C.c_void_p), a.nbytes, stream))
+        check(lib().hb_stream_synchronize(stream))
+        return b
+
+    def to_host(self, shape, dtype=np.float64, order="C", stream=None) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype, order=order)
+        check(lib().hb_memcpy_d2h(out.ctypes.data_as(C.c_void_p), self.ptr, out.nbytes, stream))
+        check(lib().hb_stream_synchronize(stream))
+        return out
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            lib().hb_free_device(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceRun:
+    """Everything but forcing and results staged on the device once; `launch()` is then a pure
+    kernel launch on a caller-supplied stream (the unit `bench.py` times as `value`)."""
+
+    def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None,
+                 rows: Optional[Sequence[str]] = None, objective: Optional[str] = None, target=None,
+                 warm_up: int = 1, ensemble: bool = False):
+        self.eng, self.N, self.T = eng, int(N), int(T)
+        self.cfg = normalize_config(config)
+        _check_config(self.cfg, T)
+        obj = objective is not None
+        metric = METRICS[objective.lower()] if obj else 0
+        if eng._has_uh():
+            probe = lower_stepper(eng.component, rows=rows, objective=obj, fast=eng.fast)
+            kmax = eng.prepare(probe, params, N, ensemble=ensemble)[5]
+        else:
+            kmax = []
+        self.ck = eng.compiled(rows=rows, objective=obj, metric=metric, shared_forcing=ensemble, uh_kmax=kmax)
+        prog = self.ck.program
+        flat, p_off, p_mode, htypes, uhw, kmax, nn = eng.prepare(prog, params, N, ensemble=ensemble)
+        self._host = (p_off, p_mode)
+        self.bufs = {"params": DeviceBuffer.from_host(flat)}
+        self.n_param_values = flat.size
+        self.n_sets = 0 if htypes is None else htypes.shape[0]
+        if htypes is not None:
+            self.bufs["htypes"] = DeviceBuffer.from_host(htypes)
+        init = eng._initstates(prog, initstates, N)
+        if init is not None:
+            self.bufs["init"] = DeviceBuffer.from_host(init)
+        if uhw:
+            self.bufs["uhw"] = DeviceBuffer.from_host(np.concatenate(uhw, axis=0))
+        if nn is not None:
+            self.bufs["nn"] = DeviceBuffer.from_host(nn)
+        self.per_node_target = 0
+        if obj:
+            tgt = np.asarray(target, dtype=np.float64)
+            if tgt.ndim == 2:
+                tgt, self.per_node_target = np.ascontiguousarray(tgt.T), 1
+            self.bufs["target"] = DeviceBuffer.from_host(tgt)
+        self.warm_up = int(warm_up)
+        self.n_rows = 0 if obj else len(prog.row_names)
+        self.n_inputs = len(prog.input_names)
+        self.objective = obj
+
+    @property
+    def in_bytes(self) -> int:
+        return self.T * (1 if self.ck.spec.shared_forcing else self.N) * self.n_inputs * 8
+
+    @property
+    def out_bytes(self) -> int:
+        return self.N * 8 if self.objective else self.T * self.N * self.n_rows * 8
+
+    def launch(self, input_ptr: int, out_ptr: int, stream: Optional[int] = None, final_states_ptr: Optional[int] = None,
+               timed: bool = False) -> Optional[float]:
+        d = RunDesc()
+        d.struct_size = C.sizeof(RunDesc)
+        d.n_htype_sets = self.n_sets
+        d.n_nodes, d.n_steps = self.N, self.T
+        d.input = input_ptr
+        d.params, d.n_param_values = self.bufs["params"].ptr, self.n_param_values
+        d.param_offset, d.param_mode = _ptr(self._host[0]), _ptr(self._host[1])
+        d.htypes = self.bufs["htypes"].ptr if "htypes" in self.bufs else None
+        d.initstates = self.bufs["init"].ptr if "init" in self.bufs else None
+        d.uh_weights = self.bufs["uhw"].ptr if "uhw" in self.bufs else None
+        d.nn_params = self.bufs["nn"].ptr if "nn" in self.bufs else None
+        d.min_value = self.cfg.min_value
+        d.warm_up = self.warm_up
+        if self.objective:
+            d.target, d.target_per_node = self.bufs["target"].ptr, self.per_node_target
+            d.objective = out_ptr
+        else:
+            d.out = out_ptr
+        d.final_states = final_states_ptr
+        el = C.c_float(0.0)
+        if timed:
+            d.elapsed_ms = C.cast(C.byref(el), C.c_void_p)
+        check(lib().hb_run_device(self.ck.handle, C.byref(d), stream))
+        return el.value if timed else None

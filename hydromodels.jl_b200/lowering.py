@@ -1,0 +1,585 @@
+"""Lowering: HydroModel expression trees → the CUDA C body spliced into `templates/stepper.cu`.
+
+This is the host-side half of the engine (the north-star's "Julia host code lowers the model's
+Symbolics flux and state expressions to a CUDA C body"; a Julia twin of this file is sketched in
+INTEGRATION.md).  It replaces HydroModelCore's `build_bucket_func` / `build_flux_func` /
+`build_uh_func` code generators (call sites `/root/reference/src/bucket.jl:58`, `src/flux.jl:52`,
+`src/uh.jl:73`) — but instead of one Julia closure per component evaluated over the whole
+series, it emits ONE straight-line step for the whole model:
+
+    for each component, in declaration order (`/root/reference/src/model.jl:255-268`):
+        bucket with states : fluxes(pre-state) → dS → u ← max(min_value, u + dS) → fluxes(post-state)
+                             (`src/solve.jl:47-52`, `src/bucket.jl:184-192`: every state-dependent
+                             flux is evaluated twice per step)
+        stateless bucket / flux : one evaluation (`src/bucket.jl:196-204`, `src/flux.jl:157-166`)
+        unit hydrograph : y_t = Σ_k w_k x_{t-k+1} on a register ring (`src/uh.jl:187-237`)
+        neural flux : dense MLP on the listed inputs (`src/nn.jl:56-58`)
+
+Work the straight-line form makes removable (all value-preserving to ≤ 1e-15 relative):
+
+* hash-consing CSE across the pre-/post-state evaluations: anything that does not depend on the
+  bucket's own states (e.g. `pet`, `snowfall`) is computed once per step instead of twice;
+* parameter-only subexpressions (and reciprocals of parameter-only divisors) are hoisted to the
+  prologue (class P);
+* state-only subexpressions (e.g. `step_func(soilwater)`, `exp(-f*max(0,Smax-soilwater))`): the
+  post-update value at step t IS the pre-update value at step t+1 → carried in a register
+  (`hb_c[k]`) instead of being recomputed (class S);
+* `step_func` → logistic form (one exp + one reciprocal), integer / half-integer powers →
+  multiplications and `sqrt`.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .components import (Component, HydroBucket, HydroFlux, HydroModel, HydroRoute, NeuralFlux, StateFlux,
+                         UnitHydrograph)
+from .symbolic import Call, Const, Expr, Sym, evaluate, walk
+
+M_X, M_S, M_U = 1, 2, 4      # dependency bits: forcing, states, unit-hydrograph history
+
+_COST = {"add": 1, "sub": 1, "mul": 1, "neg": 0, "abs": 0, "min": 1, "max": 1, "clamp": 2, "div": 10, "rcp": 10,
+         "sqrt": 12, "exp": 25, "log": 30, "tanh": 40, "step": 36, "pow": 80, "fma": 1, "leakyrelu": 2}
+
+
+class LoweringError(ValueError):
+    pass
+
+
+def _c_double(v: float) -> str:
+    if math.isnan(v):
+        return "(0.0/0.0)"
+    if math.isinf(v):
+        return "(1.0/0.0)" if v > 0 else "(-1.0/0.0)"
+    s = repr(float(v))
+    if "e" not in s and "." not in s:
+        s += ".0"
+    return s
+
+
+@dataclass
+class Val:
+    """One SSA value of the per-step program."""
+    id: int
+    op: str                  # 'const' 'in' 'param' 'state' 'uh' 'nn' or an arithmetic op
+    args: Tuple[int, ...] = ()
+    payload: object = None
+    mask: int = 0
+    cost: int = 0            # cumulative cost of the subtree (for the carry heuristic)
+    erased: object = None    # structural key with state versions erased
+    vers: frozenset = frozenset()   # state versions appearing below
+
+
+@dataclass
+class StepperProgram:
+    body: str
+    input_names: List[str]
+    row_names: List[str]            # rows written per step, in order
+    all_row_names: List[str]
+    state_names: List[str]          # order of hb_u / initstates / final_states
+    param_slots: List[Tuple[str, Optional[int]]]   # hb_p[j] = (parameter name, htypes-set index | None)
+    htype_sets: List[np.ndarray]    # distinct 1-based htypes vectors
+    uh: List[UnitHydrograph]
+    uh_kmax: List[int]
+    uh_htype_set: List[Optional[int]]
+    nn_layout: List[Tuple[str, int, int]]          # (chain name, offset, n_params) in the smem block
+    nn_words: int
+    n_carry: int
+    objective: bool
+    stats: Dict[str, int] = field(default_factory=dict)
+
+
+class _Builder:
+    def __init__(self, fast: bool):
+        self.fast = fast
+        self.vals: List[Val] = []
+        self.memo: Dict[object, int] = {}
+        self.nn_calls: List[Tuple[int, Tuple[int, ...], List[int]]] = []   # (net index, input ids, output val ids)
+
+    # ---- value construction -------------------------------------------------------------------
+    def _new(self, key, op, args=(), payload=None, mask=0, cost=0, erased=None, vers=frozenset()) -> int:
+        if key in self.memo:
+            return self.memo[key]
+        v = Val(len(self.vals), op, tuple(args), payload, mask, cost, erased if erased is not None else key, vers)
+        self.vals.append(v)
+        self.memo[key] = v.id
+        return v.id
+
+    def const(self, x: float) -> int:
+        x = float(x)
+        return self._new(("const", x.hex()), "const", payload=x)
+
+    def leaf_in(self, idx: int) -> int:
+        return self._new(("in", idx), "in", payload=idx, mask=M_X)
+
+    def leaf_param(self, idx: int) -> int:
+        return self._new(("param", idx), "param", payload=idx)
+
+    def leaf_state(self, idx: int, ver: int) -> int:
+        return self._new(("state", idx, ver), "state", payload=(idx, ver), mask=M_S, erased=("state", idx),
+                         vers=frozenset([ver]))
+
+    def opaque(self, kind: str, payload, mask: int, cost: int = 1000) -> int:
+        return self._new((kind, payload), kind, payload=payload, mask=mask, cost=cost)
+
+    def is_const(self, i: int) -> bool:
+        return self.vals[i].op == "const"
+
+    def cval(self, i: int) -> float:
+        return self.vals[i].payload
+
+    def op(self, name: str, *args: int) -> int:
+        a = list(args)
+        if all(self.is_const(i) for i in a):           # constant folding (IEEE double, libm)
+            return self.const(_fold(name, [self.cval(i) for i in a]))
+        if name in ("add", "mul", "min", "max") and a[0] > a[1]:
+            a = [a[1], a[0]]                            # commutative normal form → more CSE hits
+        key = (name,) + tuple(a)
+        mask = 0
+        cost = _COST.get(name, 1)
+        vers = frozenset()
+        for i in a:
+            mask |= self.vals[i].mask
+            cost += self.vals[i].cost
+            vers |= self.vals[i].vers
+        er = [self.vals[i].erased for i in a]
+        if name in ("add", "mul", "min", "max"):
+            er.sort(key=repr)                           # pre/post twins must not depend on value ids
+        erased = (name,) + tuple(er)
+        return self._new(key, name, a, mask=mask, cost=cost, erased=erased, vers=vers)
+
+    # ---- expression trees ---------------------------------------------------------------------
+    def lower_expr(self, e: Expr, env: Dict[str, int], params: Dict[str, int]) -> int:
+        memo: Dict[object, int] = {}
+        for n in walk(e):
+            k = n.key()
+            if isinstance(n, Const):
+                memo[k] = self.const(n.value)
+            elif isinstance(n, Sym):
+                table = params if n.is_param else env
+                if n.name not in table:
+                    what = "Parameter" if n.is_param else "Variable"
+                    raise LoweringError(f"{what} {n.name} is not defined where it is used")
+                memo[k] = table[n.name]
+            else:
+                memo[k] = self._lower_call(n.op, [memo[x.key()] for x in n.args])
+        return memo[e.key()]
+
+    def _lower_call(self, op: str, a: List[int]) -> int:
+        if op == "div":
+            if self.fast and self.vals[a[1]].mask == 0 and not self.is_const(a[0]):
+                return self.op("mul", a[0], self.op("rcp", a[1]))   # divisor is parameter-only → hoisted 1/b
+            return self.op("div", a[0], a[1])
+        if op == "pow":
+            return self._lower_pow(a[0], a[1])
+        if op == "clamp":
+            return self.op("min", self.op("max", a[0], a[1]), a[2])
+        return self.op(op, *a)
+
+    def _lower_pow(self, base: int, ex: int) -> int:
+        if self.is_const(ex):
+            p = self.cval(ex)
+            if p == int(p) and abs(p) <= 16:
+                n = int(abs(p))
+                if n == 0:
+                    return self.const(1.0)
+                r = self._ipow(base, n)
+                return r if p > 0 else self.op("div", self.const(1.0), r)
+            if self.fast and p * 2 == int(p * 2) and 0 < p <= 8.5:     # half-integer: x^n * sqrt(x)
+                n = int(p)
+                s = self.op("sqrt", base)
+                return s if n == 0 else self.op("mul", self._ipow(base, n), s)
+        return self.op("pow", base, ex)
+
+    def _ipow(self, base: int, n: int) -> int:
+        result = None
+        sq = base
+        while n:
+            if n & 1:
+                result = sq if result is None else self.op("mul", result, sq)
+            n >>= 1
+            if n:
+                sq = self.op("mul", sq, sq)
+        return result
+
+
+def _fold(name: str, a: List[float]) -> float:
+    try:
+        if name == "add": return a[0] + a[1]
+        if name == "sub": return a[0] - a[1]
+        if name == "mul": return a[0] * a[1]
+        if name == "div": return a[0] / a[1] if a[1] != 0 else math.copysign(math.inf, a[0]) * math.copysign(1.0, a[1])
+        if name == "rcp": return 1.0 / a[0] if a[0] != 0 else math.copysign(math.inf, a[0])
+        if name == "neg": return -a[0]
+        if name == "pow": return math.pow(a[0], a[1])
+        if name == "exp": return math.exp(a[0])
+        if name == "log": return math.log(a[0])
+        if name == "sqrt": return math.sqrt(a[0])
+        if name == "abs": return abs(a[0])
+        if name == "tanh": return math.tanh(a[0])
+        if name == "step": return (math.tanh(5.0 * a[0]) + 1.0) * 0.5
+        if name == "min": return min(a[0], a[1])
+        if name == "max": return max(a[0], a[1])
+    except (OverflowError, ValueError):
+        return math.nan
+    raise LoweringError(f"cannot fold {name}")
+
+
+# ---------------------------------------------------------------------------------------------
+# model → program
+# ---------------------------------------------------------------------------------------------
+def _flatten(component: Component) -> Tuple[List[Component], List[str], List[str]]:
+    if isinstance(component, HydroModel):
+        return list(component.components), list(component.input_names), list(component.var_names)
+    return [component], list(component.input_names), list(component.state_names) + list(component.output_names)
+
+
+def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None, objective: bool = False,
+                  uh_kmax: Optional[Sequence[int]] = None, fast: bool = True) -> StepperProgram:
+    """Lower a per-node model (buckets, fluxes, neural fluxes, unit hydrographs) to one stepper
+    body.  `rows`: subset/order of result rows to write (default: all = the reference result);
+    `objective`: emit the last output row as `hb_sim` for the fused metric reduction instead of
+    rows; `uh_kmax[u]`: ordinates per unit hydrograph (from the run's parameters)."""
+    comps, input_names, all_rows = _flatten(component)
+    for c in comps:
+        if isinstance(c, HydroRoute):
+            raise LoweringError("HydroRoute is a grid-coupled component; it is lowered by lower_route")
+        if not isinstance(c, (HydroBucket, HydroFlux, UnitHydrograph)):
+            raise LoweringError(f"cannot lower component of type {type(c).__name__}")
+    b = _Builder(fast)
+
+    # ---- bookkeeping tables -------------------------------------------------------------------
+    htype_sets: List[np.ndarray] = []
+
+    def htype_set(c: Component) -> Optional[int]:
+        if c.htypes is None:
+            return None
+        for i, h in enumerate(htype_sets):
+            if h.shape == c.htypes.shape and np.array_equal(h, c.htypes):
+                return i
+        htype_sets.append(np.asarray(c.htypes))
+        return len(htype_sets) - 1
+
+    param_slots: List[Tuple[str, Optional[int]]] = []
+
+    def param_table(c: Component) -> Dict[str, int]:
+        hs = htype_set(c)
+        out = {}
+        for nm in c.param_names:
+            slot = (nm, hs)
+            if slot not in param_slots:
+                param_slots.append(slot)
+            out[nm] = b.leaf_param(param_slots.index(slot))
+        return out
+
+    state_names: List[str] = [s for c in comps for s in c.state_names]
+    if len(set(state_names)) != len(state_names):
+        raise LoweringError("duplicate state names across components")
+    uhs = [c for c in comps if isinstance(c, UnitHydrograph)]
+    if uh_kmax is None:
+        uh_kmax = [1] * len(uhs)
+    if len(uh_kmax) != len(uhs):
+        raise LoweringError("uh_kmax must have one entry per unit hydrograph")
+    uh_kmax = [max(1, int(k)) for k in uh_kmax]
+    uh_w_off = np.concatenate([[0], np.cumsum(uh_kmax)]).astype(int)
+    uh_h_off = np.concatenate([[0], np.cumsum([k - 1 for k in uh_kmax])]).astype(int)
+    nets: List = []           # distinct chains
+    nn_layout: List[Tuple[str, int, int]] = []
+
+    def net_index(chain) -> int:
+        for i, ch in enumerate(nets):
+            if ch.name == chain.name:
+                if ch != chain:
+                    raise LoweringError(f"two different chains share the name {chain.name}")
+                return i
+        off = sum(n for _, _, n in nn_layout)
+        nets.append(chain)
+        nn_layout.append((chain.name, off, chain.n_params))
+        return len(nets) - 1
+
+    # ---- walk the components in order, building the step DAG ------------------------------------
+    env: Dict[str, int] = {nm: b.leaf_in(i) for i, nm in enumerate(input_names)}
+    state_post: Dict[int, int] = {}           # state index → val id of the post-update value
+    uh_steps: List[Tuple[int, int]] = []      # (uh index, val id of x_t)
+    statements: List[Tuple[str, object]] = []  # ordered side effects ('update', (sidx, val)), …
+
+    def eval_fluxes(bucket: HydroBucket, local: Dict[str, int], ptab: Dict[str, int]) -> Dict[str, int]:
+        outs = {}
+        for f in bucket.fluxes:
+            if isinstance(f, NeuralFlux):
+                ni = net_index(f.chain)
+                ins = tuple(local[i] for i in f.input_names)
+                mask = 0
+                for i in ins:
+                    mask |= b.vals[i].mask
+                for j, o in enumerate(f.output_names):
+                    vid = b.opaque("nn", (ni, ins, j), mask)
+                    # erased key / versions so that pre/post twins of an NN output can be carried
+                    v = b.vals[vid]
+                    v.erased = ("nn", ni, tuple(b.vals[i].erased for i in ins), j)
+                    v.vers = frozenset().union(*[b.vals[i].vers for i in ins]) if ins else frozenset()
+                    v.args = ins
+                    local[o] = outs[o] = vid
+            else:
+                for eq in f.eqs:
+                    vid = b.lower_expr(eq.rhs, local, ptab)
+                    local[eq.lhs.name] = outs[eq.lhs.name] = vid
+        return outs
+
+    for c in comps:
+        missing = [i for i in c.input_names if i not in env]
+        if missing:
+            raise LoweringError(f"Input variables {missing} of component {c.name} not found")
+        if isinstance(c, HydroBucket):
+            ptab = param_table(c)
+            if not c.has_states:
+                local = {i: env[i] for i in c.input_names}
+                env.update(eval_fluxes(c, local, ptab))
+                continue
+            sidx = [state_names.index(s) for s in c.state_names]
+            # pass 1: pre-update states
+            local = {i: env[i] for i in c.input_names}
+            for s, si in zip(c.state_names, sidx):
+                local[s] = b.leaf_state(si, 0)
+            eval_fluxes(c, local, ptab)
+            dus = [b.lower_expr(d.expr, local, ptab) for d in c.dfluxes]
+            # update: u ← max(min_value, u + du)
+            for s, si, du in zip(c.state_names, sidx, dus):
+                post = b.leaf_state(si, 1)
+                state_post[si] = post
+                statements.append(("update", (si, b.leaf_state(si, 0), du)))
+            # pass 2: post-update states → rows
+            local = {i: env[i] for i in c.input_names}
+            for s, si in zip(c.state_names, sidx):
+                local[s] = state_post[si]
+            outs = eval_fluxes(c, local, ptab)
+            for s, si in zip(c.state_names, sidx):
+                env[s] = state_post[si]
+            env.update(outs)
+        elif isinstance(c, HydroFlux):
+            ptab = param_table(c)
+            local = {i: env[i] for i in c.input_names}
+            for eq in c.eqs:
+                vid = b.lower_expr(eq.rhs, local, ptab)
+                local[eq.lhs.name] = vid
+                env[eq.lhs.name] = vid
+        else:  # UnitHydrograph
+            u = uhs.index(c)
+            x = env[c.input_names[0]]
+            vid = b.opaque("uh", (u, x), b.vals[x].mask | M_U, cost=2 * uh_kmax[u])
+            b.vals[vid].args = (x,)
+            uh_steps.append((u, x))
+            env[c.output_names[0]] = vid
+
+    # ---- outputs ------------------------------------------------------------------------------------
+    if objective:
+        row_names = [all_rows[-1]]           # `[end, :]` of the result (`…OptimizationExt.jl:163,173`)
+    else:
+        row_names = list(all_rows) if rows is None else list(rows)
+    for r in row_names:
+        if r not in env:
+            raise LoweringError(f"row {r} is not produced by the model")
+    out_vals = [env[r] for r in row_names]
+
+    # ---- carry detection (class S) --------------------------------------------------------------------
+    by_erased: Dict[object, Dict[int, int]] = {}
+    for v in b.vals:
+        if v.mask == M_S and len(v.vers) == 1 and v.op not in ("state",):
+            by_erased.setdefault(v.erased, {})[next(iter(v.vers))] = v.id
+    users: Dict[int, List[int]] = {v.id: [] for v in b.vals}
+    for v in b.vals:
+        for a in v.args:
+            users[a].append(v.id)
+    root_uses = set(out_vals) | {du for k, p in statements if k == "update" for du in (p[2],)} | {x for _, x in uh_steps}
+    carried: Dict[int, Tuple[int, int]] = {}    # pre val id → (carry slot, post val id)
+    if fast:
+        for erased, d in by_erased.items():
+            if 0 in d and 1 in d:
+                pre, post = d[0], d[1]
+                if b.vals[pre].cost < 6:
+                    continue
+                # maximal: used by something that is not itself a pure pre-state expression, or a root
+                maximal = pre in root_uses or any(
+                    not (b.vals[u].mask == M_S and b.vals[u].vers == frozenset([0])) for u in users[pre])
+                # if a user is itself carried, this one is not needed separately
+                if maximal:
+                    carried[pre] = (len(carried), post)
+
+    # ---- liveness (dead-code elimination) from the roots ----------------------------------------------
+    live = set()
+    stack = list(out_vals) + [p[2] for k, p in statements if k == "update"] + [x for _, x in uh_steps] + \
+        [post for _, post in carried.values()]
+
+    def visit(i):
+        st = [i]
+        while st:
+            j = st.pop()
+            if j in live:
+                continue
+            live.add(j)
+            if j in carried:
+                continue                     # value comes from hb_c[], its subtree is not needed
+            st.extend(b.vals[j].args)
+    for i in stack:
+        visit(i)
+    # pre-state subtrees needed only to initialise carries are emitted in the prologue
+    # ---- emission ---------------------------------------------------------------------------------------
+    pro: List[str] = []
+    step: List[str] = []
+    pro_names: Dict[int, str] = {}
+
+    def nn_var(ni: int, ins: Tuple[int, ...], tag: str) -> str:
+        return f"nn{tag}{ni}_" + "_".join(str(k) for k in ins)
+
+    def pro_ref(i: int) -> str:
+        """Name of val i evaluated in the prologue: states read the (unclamped) initial values."""
+        v = b.vals[i]
+        if v.op == "const": return _c_double(v.payload)
+        if v.op == "param": return f"hb_p[{v.payload}]"
+        if v.op == "state": return f"hb_u[{v.payload[0]}]"
+        if v.op in ("in", "uh") or (v.mask & (M_X | M_U)):
+            raise LoweringError("internal: prologue value depends on forcing")
+        if i in pro_names:
+            return pro_names[i]
+        args = [pro_ref(a) for a in v.args]
+        nm = f"h{i}"
+        if v.op == "nn":
+            ni, ins, j = v.payload
+            arr = nn_var(ni, ins, "p")
+            if arr not in pro_names.values():
+                pro.append(f"double {arr}[{nets[ni].n_out}]; hb_mlp_{ni}(sNN, {', '.join(args)}, {arr});")
+                pro_names[-len(pro_names) - 1] = arr
+            pro.append(f"const double {nm} = {arr}[{j}];")
+        else:
+            pro.append(f"const double {nm} = {_expr_with(v, args, fast)};")
+        pro_names[i] = nm
+        return nm
+
+    def step_ref(i: int) -> str:
+        v = b.vals[i]
+        if v.op == "const": return _c_double(v.payload)
+        if v.op == "in": return f"hb_x[{v.payload}]"
+        if v.op == "param": return f"hb_p[{v.payload}]"
+        if v.op == "state":
+            si, ver = v.payload
+            return f"hb_u[{si}]" if ver == 0 else f"hb_un{si}"
+        if i in carried: return f"hb_c[{carried[i][0]}]"
+        if v.mask == 0: return pro_ref(i)          # class P: hoisted
+        return f"v{i}"
+
+    # carries: initial value = the pre-state expression at the (unclamped) initial states
+    for pre, (slot, post) in sorted(carried.items(), key=lambda kv: kv[1][0]):
+        pro.append(f"hb_c[{slot}] = {pro_ref(pre)};")
+
+    pending_updates = {p[0]: p for k, p in statements if k == "update"}
+    nn_done = set()
+    for v in b.vals:                                  # construction order is topological
+        i = v.id
+        if v.op == "state" and v.payload[1] == 1:
+            si = v.payload[0]                         # all increments of its bucket precede this leaf
+            step.append(f"const double hb_un{si} = fmax(hb_minv, hb_u[{si}] + {step_ref(pending_updates[si][2])});")
+            continue
+        if i not in live or v.mask == 0 or v.op in ("const", "in", "param", "state") or i in carried:
+            continue
+        if v.op == "uh":
+            u, x = v.payload
+            step.append(f"double v{i} = hb_uhw[{uh_w_off[u]}] * {step_ref(x)};")
+            for k in range(1, uh_kmax[u]):
+                step.append(f"v{i} = fma(hb_uhw[{uh_w_off[u] + k}], hb_uhh[{uh_h_off[u] + k - 1}], v{i});")
+        elif v.op == "nn":
+            ni, ins, j = v.payload
+            arr = nn_var(ni, ins, "s")
+            if arr not in nn_done:
+                nn_done.add(arr)
+                step.append(f"double {arr}[{nets[ni].n_out}]; hb_mlp_{ni}(sNN, {', '.join(step_ref(k) for k in ins)}, {arr});")
+            step.append(f"const double v{i} = {arr}[{j}];")
+        else:
+            step.append(f"const double v{i} = {_expr_with(v, [step_ref(a) for a in v.args], fast)};")
+    # end of step: rows, carries, states, UH history shift
+    if objective:
+        step.append(f"hb_sim = {step_ref(out_vals[0])};")
+    else:
+        for r, vid in enumerate(out_vals):
+            step.append(f"hb_out[{r}] = {step_ref(vid)};")
+    for pre, (slot, post) in sorted(carried.items(), key=lambda kv: kv[1][0]):
+        step.append(f"hb_c[{slot}] = {step_ref(post)};")
+    for si in sorted(state_post):
+        step.append(f"hb_u[{si}] = hb_un{si};")
+    for u, x in uh_steps:
+        K = uh_kmax[u]
+        for k in range(K - 2, 0, -1):
+            step.append(f"hb_uhh[{uh_h_off[u] + k}] = hb_uhh[{uh_h_off[u] + k - 1}];")
+        if K >= 2:
+            step.append(f"hb_uhh[{uh_h_off[u]}] = {step_ref(x)};")
+
+    helpers = [_mlp_helper(i, ch, off, fast) for i, (ch, (_, off, _)) in enumerate(zip(nets, nn_layout))]
+    body = "//@@HB:DEFINES\n" + f"#define HB_NC {len(carried)}\n" + \
+           "//@@HB:HELPERS\n" + "\n".join(helpers) + "\n" + \
+           "//@@HB:PROLOGUE\n" + "\n".join("    " + s for s in pro) + "\n" + \
+           "//@@HB:STEP\n" + "\n".join("        " + s for s in step) + "\n"
+    n_ops = sum(1 for v in b.vals if v.id in live and v.mask != 0 and v.op not in ("const", "in", "param", "state")
+                and v.id not in carried)
+    stats = {"step_values": n_ops, "prologue_values": len(pro), "carried": len(carried),
+             "exp_like_per_step": sum(1 for v in b.vals if v.id in live and v.mask != 0 and v.id not in carried
+                                      and v.op in ("exp", "step", "tanh", "log", "pow"))}
+    return StepperProgram(body=body, input_names=input_names, row_names=row_names, all_row_names=list(all_rows),
+                          state_names=state_names, param_slots=param_slots, htype_sets=htype_sets, uh=uhs,
+                          uh_kmax=list(uh_kmax), uh_htype_set=[htype_set(u) for u in uhs],
+                          nn_layout=nn_layout, nn_words=sum(n for _, _, n in nn_layout), n_carry=len(carried),
+                          objective=objective, stats=stats)
+
+
+def _expr_with(v: Val, a: List[str], fast: bool) -> str:
+    op = v.op
+    if op == "add": return f"{a[0]} + {a[1]}"
+    if op == "sub": return f"{a[0]} - {a[1]}"
+    if op == "mul": return f"{a[0]} * {a[1]}"
+    if op == "div": return f"{a[0]} / {a[1]}"
+    if op == "rcp": return f"1.0 / {a[0]}"
+    if op == "neg": return f"-{a[0]}"
+    if op == "pow": return f"pow({a[0]}, {a[1]})"
+    if op == "exp": return f"exp({a[0]})"
+    if op == "log": return f"log({a[0]})"
+    if op == "sqrt": return f"sqrt({a[0]})"
+    if op == "abs": return f"fabs({a[0]})"
+    if op == "tanh": return f"hb_tanh({a[0]})" if fast else f"tanh({a[0]})"
+    if op == "step": return f"hb_step({a[0]})" if fast else f"(tanh(5.0 * {a[0]}) + 1.0) * 0.5"
+    if op == "min": return f"fmin({a[0]}, {a[1]})"
+    if op == "max": return f"fmax({a[0]}, {a[1]})"
+    raise LoweringError(f"no emitter for {op}")
+
+
+_ACT_C = {"identity": "{}", "tanh": "hb_tanh({})", "leakyrelu": "hb_leakyrelu({})", "relu": "fmax(0.0, {})",
+          "sigmoid": "hb_rcp_pos(1.0 + exp(fmin(-({}), 700.0)))"}
+_ACT_C_EXACT = dict(_ACT_C, tanh="tanh({})", sigmoid="(1.0 / (1.0 + exp(-({}))))")
+
+
+def _mlp_helper(idx: int, chain, offset: int, fast: bool) -> str:
+    """Register-resident matvec chain: weights broadcast from shared memory (every lane reads the
+    same word → conflict-free), activations in registers.  Layout per layer: weight[out,in]
+    column-major then bias[out] (`/root/reference/src/nn.jl:52-58`)."""
+    acts = _ACT_C if fast else _ACT_C_EXACT
+    args = ", ".join(f"const double x{i}" for i in range(chain.n_in))
+    lines = [f"__device__ __forceinline__ void hb_mlp_{idx}(const double* __restrict__ sNN, {args}, double* __restrict__ y) {{",
+             f"    const double* w = sNN + {offset};",
+             f"    double a0[{chain.n_in}] = {{{', '.join(f'x{i}' for i in range(chain.n_in))}}};"]
+    off = 0
+    for li, l in enumerate(chain.layers):
+        src, dst = f"a{li}", f"a{li + 1}"
+        lines.append(f"    double {dst}[{l.n_out}];")
+        lines.append("#pragma unroll")
+        lines.append(f"    for (int o = 0; o < {l.n_out}; ++o) {{")
+        lines.append(f"        double z = w[{off + l.n_out * l.n_in} + o];")
+        lines.append("#pragma unroll")
+        lines.append(f"        for (int i = 0; i < {l.n_in}; ++i) z = fma(w[{off} + i * {l.n_out} + o], {src}[i], z);")
+        lines.append(f"        {dst}[o] = {acts[l.activation].format('z')};")
+        lines.append("    }")
+        off += l.n_params
+    last = f"a{len(chain.layers)}"
+    lines.append("#pragma unroll")
+    lines.append(f"    for (int o = 0; o < {chain.n_out}; ++o) y[o] = {last}[o];")
+    lines.append("}")
+    return "\n".join(lines)

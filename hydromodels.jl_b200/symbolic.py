@@ -365,3 +365,40 @@ def evaluate(e: Expr, env: Dict[str, float]) -> float:
         return r
 
     return rec(e)
+
+
+def evaluate_np(e: Expr, env):
+    """Vectorised (numpy) evaluation, literal operation order — host-side helper for O(N·K)
+    preparation work such as unit-hydrograph ordinates (never used for the time stepping)."""
+    import numpy as np
+
+    memo = {}
+    for n in walk(e):
+        k = n._key
+        if isinstance(n, Const):
+            memo[k] = np.float64(n.value)
+        elif isinstance(n, Sym):
+            memo[k] = env[n.name]
+        else:
+            a = [memo[x._key] for x in n.args]
+            op = n.op
+            with np.errstate(all="ignore"):
+                if op == "add": r = a[0] + a[1]
+                elif op == "sub": r = a[0] - a[1]
+                elif op == "mul": r = a[0] * a[1]
+                elif op == "div": r = a[0] / a[1]
+                elif op == "neg": r = -a[0]
+                elif op == "pow": r = np.power(a[0], a[1])
+                elif op == "exp": r = np.exp(a[0])
+                elif op == "log": r = np.log(a[0])
+                elif op == "sqrt": r = np.sqrt(a[0])
+                elif op == "abs": r = np.abs(a[0])
+                elif op == "tanh": r = np.tanh(a[0])
+                elif op == "step": r = (np.tanh(5.0 * a[0]) + 1.0) * 0.5
+                elif op == "min": r = np.minimum(a[0], a[1])
+                elif op == "max": r = np.maximum(a[0], a[1])
+                elif op == "clamp": r = np.minimum(np.maximum(a[0], a[1]), a[2])
+                else:  # pragma: no cover
+                    raise ValueError(op)
+            memo[k] = r
+    return memo[e._key]

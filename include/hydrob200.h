@@ -1,0 +1,173 @@
+/*
+ * hydrob200.h — C-ABI of libhydrob200.so, the B200 (sm_100a) forward-run engine for
+ * HydroModels.jl bucket models.
+ *
+ * This is the drop-in boundary of SURVEY.md §8(b).  The reference (pure Julia) has no FFI for
+ * this path; these entry points are what a Julia `ccall` binding for
+ *     (model::HydroModel)(input, params, config; initstates)      /root/reference/src/model.jl:241-309
+ * and the component functors it dispatches to
+ *     HydroBucket   /root/reference/src/bucket.jl:169-256   (hydrosolve: src/solve.jl:31-55)
+ *     HydroFlux     /root/reference/src/flux.jl:157-203
+ *     UnitHydrograph/root/reference/src/uh.jl:187-274
+ *     HydroRoute    /root/reference/src/route.jl:336-404
+ * binds (INTEGRATION.md shows the stub).  Plain C: pointers and sizes only, every function
+ * returns an int status (0 = ok), no exceptions cross the boundary, `hb_last_error()` returns
+ * a thread-local message the host turns into the reference's exceptions.
+ *
+ * Division of labour: the host language lowers the model's flux/state expressions to a CUDA C
+ * *body* (sections PROLOGUE / STEP / EPILOGUE); the library splices
+ * the body into its hand-written kernel templates, compiles them with NVRTC for sm_100a,
+ * caches the cubin and launches it.  There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with HB_ERR_NO_DEVICE.
+ *
+ * Array layouts are the reference's Julia column-major layouts, i.e. in C order:
+ *     input   [T][N][V]      (Julia  input[V, N, T];   src/bucket.jl:207-214)
+ *     output  [T][N][R]      (Julia  out[rows, N, T];  src/bucket.jl:243, src/model.jl:308)
+ *     states  [S][N]         (flat, state-major / node-fastest; src/model.jl:116-119)
+ *     params  flat values, one (offset, mode) per parameter name (src/utils.jl:174-201)
+ * All floating point is IEEE double (the reference's promote_type, src/solve.jl:42).
+ */
+#ifndef HYDROB200_H
+#define HYDROB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_ABI_VERSION 1
+
+/* status codes */
+enum {
+    HB_OK = 0,
+    HB_ERR_INVALID = 1,    /* bad argument / descriptor (DimensionMismatch, ArgumentError)   */
+    HB_ERR_NO_DEVICE = 2,  /* no CUDA device or driver: there is no CPU fallback             */
+    HB_ERR_COMPILE = 3,    /* NVRTC rejected the generated kernel (log in hb_last_error)     */
+    HB_ERR_CUDA = 4,       /* CUDA runtime / driver error                                    */
+    HB_ERR_NOMEM = 5
+};
+
+/* what the stepper writes */
+enum {
+    HB_OUT_ROWS = 0,       /* out[T][N][R]: the rows the body emits (all rows = reference result) */
+    HB_OUT_OBJECTIVE = 1   /* objective[N]: fused metric of the body's simulated row vs target   */
+};
+
+/* metrics of ext/HydroModelsOptimizationExt/HydroModelsOptimizationExt.jl:34-68 (value the
+ * optimiser minimises: -KGE, -NSE, -LogKGE, MSE) */
+enum { HB_METRIC_MSE = 0, HB_METRIC_NSE = 1, HB_METRIC_KGE = 2, HB_METRIC_LOGKGE = 3 };
+
+/* parameter addressing modes: value of parameter j for node n is
+ *   mode 0: params[offset_j]                 scalar (2D single-node call)
+ *   mode 1: params[offset_j + n]             one value per node (htypes == 1:N)
+ *   mode 2+k: params[offset_j + htypes[k][n]] gather through 0-based htypes set k           */
+enum { HB_PARAM_SCALAR = 0, HB_PARAM_PER_NODE = 1, HB_PARAM_GATHER = 2 };
+
+#define HB_MAX_PARAMS 96
+#define HB_MAX_UH 8
+
+typedef struct hb_model_s *hb_model_t;
+
+/* Static description of one fused per-node stepper kernel (a HydroModel made of buckets,
+ * fluxes, neural fluxes and unit hydrographs).  Everything here is compile-time for the
+ * generated kernel. */
+typedef struct {
+    int32_t struct_size;         /* sizeof(hb_stepper_spec) */
+    int32_t n_inputs;            /* V: forcing rows read per node-step                        */
+    int32_t n_rows;              /* R: rows written per node-step (HB_OUT_ROWS)               */
+    int32_t n_states;            /* S: state variables over all buckets                       */
+    int32_t n_params;            /* parameter names used by the body                          */
+    int32_t n_uh;                /* unit hydrographs fused into the stepper                   */
+    int32_t uh_kmax[HB_MAX_UH];  /* ordinates per UH (weights are zero-padded to this length) */
+    int32_t nn_words;            /* doubles of MLP parameters staged in shared memory         */
+    int32_t output_mode;         /* HB_OUT_ROWS | HB_OUT_OBJECTIVE                            */
+    int32_t metric;              /* HB_METRIC_* (objective mode)                              */
+    int32_t shared_forcing;      /* 1: input is [T][1][V], shared by all nodes (ensembles)    */
+    int32_t block_threads;       /* 0 = default (128)                                         */
+    int32_t stages;              /* forcing pipeline depth in time steps, 0 = default (4)     */
+    int32_t max_registers;       /* 0 = default; NVRTC --maxrregcount                         */
+} hb_stepper_spec;
+
+/* One forward run.  Pointers are HOST pointers for hb_run and DEVICE pointers for
+ * hb_run_device.  Optional pointers may be NULL. */
+typedef struct {
+    int32_t struct_size;         /* sizeof(hb_run_desc) */
+    int32_t n_htype_sets;
+    int64_t n_nodes;             /* N */
+    int64_t n_steps;             /* T */
+    const double *input;         /* [T][N][V]  ([T][1][V] when shared_forcing)                */
+    const double *params;        /* flat parameter values                                     */
+    int64_t n_param_values;      /* length of params                                          */
+    const int32_t *param_offset; /* [n_params]  (HOST pointer in both entry points)           */
+    const int32_t *param_mode;   /* [n_params]  (HOST pointer in both entry points)           */
+    const int32_t *htypes;       /* [n_htype_sets][N], 0-based, or NULL                       */
+    const double *initstates;    /* [S][N] or NULL (= zeros, src/bucket.jl:180,222)           */
+    const double *uh_weights;    /* [sum_u kmax_u][N]: normalised ordinates, zero-padded      */
+    const double *uh_hist_in;    /* [sum_u (kmax_u-1)][N] past UH inputs (chunked runs) / NULL */
+    const double *nn_params;     /* [nn_words] MLP parameters (shared by all nodes)           */
+    const double *target;        /* objective mode: observed series [T] or [T][N]             */
+    int32_t target_per_node;     /* 0: target[T] shared, 1: target[T][N]                      */
+    int32_t warm_up;             /* objective uses steps warm_up..T (1-based, as the reference) */
+    double min_value;            /* state clamp, > 0 (src/config.jl:46, src/solve.jl:50)      */
+    double *out;                 /* HB_OUT_ROWS: [T][N][R]                                    */
+    double *objective;           /* HB_OUT_OBJECTIVE: [N]                                     */
+    double *final_states;        /* [S][N] or NULL: states after step T (resume / BMI)        */
+    double *uh_hist_out;         /* [sum_u (kmax_u-1)][N] or NULL                             */
+    float *elapsed_ms;           /* optional HOST pointer: device time of the kernel(s)       */
+} hb_run_desc;
+
+typedef struct {
+    int32_t registers_per_thread;
+    int32_t static_smem_bytes;
+    int32_t dynamic_smem_bytes;
+    int32_t local_bytes_per_thread; /* spills */
+    int32_t block_threads;
+    int32_t max_blocks_per_sm;
+    int32_t from_cache;             /* 1 if the cubin came from the on-disk cache            */
+    int32_t cubin_bytes;
+} hb_kernel_info;
+
+/* ---- library / device ------------------------------------------------------------------ */
+int hb_version(void);                         /* HB_ABI_VERSION */
+const char *hb_last_error(void);              /* thread-local, never NULL */
+int hb_device_count(int *count);              /* HB_OK with *count == 0 when no driver */
+int hb_init(int device);                      /* select device for this process (one GPU per process) */
+int hb_set_cache_dir(const char *path);       /* cubin cache directory (default: $HB_CACHE_DIR or <lib dir>/cache) */
+
+/* ---- compile ---------------------------------------------------------------------------- */
+/* Splice `body` into the stepper template, NVRTC-compile for sm_100a (cached by source hash).
+ * Works without a device (compile only); the module is loaded lazily on first run. */
+int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t *out);
+/* The full CUDA source after splicing (for inspection, nvcc -Xptxas -v, ncu source pages). */
+int hb_model_source(hb_model_t m, const char **src, int64_t *len);
+int hb_model_cubin(hb_model_t m, const void **cubin, int64_t *len);
+int hb_model_info(hb_model_t m, hb_kernel_info *info);   /* needs a device */
+int hb_free_model(hb_model_t m);
+
+/* ---- run --------------------------------------------------------------------------------- */
+/* Host buffers: stages H2D, launches, stages D2H, returns after the stream is idle.  Pinned
+ * host buffers (hb_malloc_host / cudaHostRegister) are DMA'd directly. */
+int hb_run(hb_model_t m, const hb_run_desc *desc);
+/* Device buffers, asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
+int hb_run_device(hb_model_t m, const hb_run_desc *desc, void *stream);
+
+/* ---- memory helpers (so a host without a CUDA binding can own device / pinned buffers) ---- */
+int hb_malloc_device(void **ptr, int64_t bytes);
+int hb_free_device(void *ptr);
+int hb_malloc_host(void **ptr, int64_t bytes);   /* pinned */
+int hb_free_host(void *ptr);
+int hb_memcpy_h2d(void *dst, const void *src, int64_t bytes, void *stream);
+int hb_memcpy_d2h(void *dst, const void *src, int64_t bytes, void *stream);
+int hb_memset_device(void *dst, int value, int64_t bytes, void *stream);
+int hb_stream_synchronize(void *stream);
+
+
+/* ---- measurement probes (bench.py) --------------------------------------------------------- */
+int hb_probe_fp64_tflops(double *tflops);                       /* measured FP64 FMA peak (2 flop/FMA) */
+int hb_fill_device(double *p, int64_t n, double v, void *stream); /* L2 flush / buffer fill           */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDROB200_H */

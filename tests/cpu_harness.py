@@ -1,0 +1,123 @@
+"""TEST-ONLY: run a generated stepper *body* on the CPU to validate the lowering without a GPU.
+
+The CUDA C body that `lowering.lower_stepper` emits (sections PROLOGUE / STEP / HELPERS) is plain
+C arithmetic.  This harness splices the same text into a trivial serial C++ loop (one node at a
+time, per-thread I/O replaced by array indexing), compiles it with g++ and runs it through
+ctypes.  It exercises the lowering (CSE, hoisting, carried state-only values, UH rings, MLP
+helpers, row order) and `B200Model.prepare` marshalling in the `-m "not gpu"` suite; the kernel
+template, TMA staging and launch logic are only exercised by the `-m gpu` tests.  Nothing under
+`hydromodels.jl_b200/` imports this file.
+"""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+_SRC = r'''
+#include <cmath>
+#include <cstdint>
+typedef long long i64;
+static inline double hb_rcp_pos(double x) { return 1.0 / x; }
+static inline double hb_step(double x) { const double z = fmin(-10.0 * x, 700.0); return hb_rcp_pos(1.0 + exp(z)); }
+static inline double hb_tanh(double x) { const double z = fmin(2.0 * x, 700.0); return fma(-2.0, hb_rcp_pos(1.0 + exp(z)), 1.0); }
+static inline double hb_leakyrelu(double x) { return fmax(0.01 * x, x); }
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+#define HB_ARR(n) ((n) > 0 ? (n) : 1)
+@DEFINES@
+@HELPERS@
+extern "C" int run(i64 N, i64 T, int shared, const double* in, const double* params, const int* p_off,
+                   const int* p_mode, const int* htypes, const double* init, const double* uhw,
+                   const double* nn, double minv, double* out, double* sim, double* final_states) {
+    const double* sNN = nn; (void)sNN;
+    for (i64 n = 0; n < N; ++n) {
+        double hb_p[HB_ARR(HB_NP)], hb_u[HB_ARR(HB_S)], hb_uhw[HB_ARR(HB_UHW_TOTAL)], hb_uhh[HB_ARR(HB_UHH_TOTAL)], hb_c[HB_ARR(HB_NC)];
+        for (int j = 0; j < HB_NP; ++j) {
+            i64 idx = p_off[j];
+            if (p_mode[j] == 1) idx += n; else if (p_mode[j] >= 2) idx += htypes[(i64)(p_mode[j] - 2) * N + n];
+            hb_p[j] = params[idx];
+        }
+        for (int s = 0; s < HB_S; ++s) hb_u[s] = init ? init[(i64)s * N + n] : 0.0;
+        for (int k = 0; k < HB_UHW_TOTAL; ++k) hb_uhw[k] = uhw[(i64)k * N + n];
+        for (int k = 0; k < HB_UHH_TOTAL; ++k) hb_uhh[k] = 0.0;
+        const double hb_minv = minv;
+        (void)hb_p; (void)hb_u; (void)hb_uhw; (void)hb_uhh; (void)hb_c; (void)hb_minv;
+@PROLOGUE@
+        for (i64 t = 0; t < T; ++t) {
+            double hb_x[HB_ARR(HB_V)], hb_out[HB_ARR(HB_R)], hb_sim = 0.0;
+            for (int v = 0; v < HB_V; ++v) hb_x[v] = shared ? in[t * HB_V + v] : in[(t * N + n) * HB_V + v];
+            (void)hb_out; (void)hb_sim;
+@STEP@
+            for (int r = 0; r < HB_R; ++r) out[(t * N + n) * HB_R + r] = hb_out[r];
+            if (sim) sim[t * N + n] = hb_sim;
+        }
+        if (final_states) for (int s = 0; s < HB_S; ++s) final_states[(i64)s * N + n] = hb_u[s];
+    }
+    return 0;
+}
+'''
+
+
+def _sections(body: str):
+    secs, cur = {}, None
+    for line in body.splitlines():
+        if line.startswith("//@@HB:"):
+            cur = line[7:].strip()
+            secs.setdefault(cur, [])
+        elif cur is not None:
+            secs[cur].append(line)
+    return {k: "\n".join(v) for k, v in secs.items()}
+
+
+def run_body_on_cpu(eng, input, params, config=None, initstates=None, rows=None, objective=False,
+                    ensemble_members=None, return_final_states=False):
+    """Mirror of `B200Model.__call__` that executes the generated body with g++ instead of NVRTC."""
+    from hydromodels_jl_b200.components import normalize_config
+    from hydromodels_jl_b200.lowering import lower_stepper
+
+    cfg = normalize_config(config)
+    input = np.asarray(input, dtype=np.float64)
+    ensemble = ensemble_members is not None
+    N, T = eng._dims(input, ensemble, ensemble_members)
+    inp = np.asfortranarray(input)
+    probe = lower_stepper(eng.component, rows=rows, objective=objective, fast=eng.fast)
+    kmax = eng.prepare(probe, params, N, ensemble=ensemble)[5]
+    prog = lower_stepper(eng.component, rows=rows, objective=objective, uh_kmax=kmax or None, fast=eng.fast)
+    flat, p_off, p_mode, htypes, uhw, kmax, nn = eng.prepare(prog, params, N, ensemble=ensemble)
+    uhw_flat = np.ascontiguousarray(np.concatenate(uhw, axis=0)) if uhw else np.zeros(1)
+    init = eng._initstates(prog, initstates, N)
+    R = 0 if objective else len(prog.row_names)
+    secs = _sections(prog.body)
+    defines = "\n".join([
+        f"#define HB_V {len(prog.input_names)}", f"#define HB_R {R}", f"#define HB_S {len(prog.state_names)}",
+        f"#define HB_NP {len(prog.param_slots)}", f"#define HB_UHW_TOTAL {sum(prog.uh_kmax)}",
+        f"#define HB_UHH_TOTAL {sum(k - 1 for k in prog.uh_kmax)}", secs.get("DEFINES", "")])
+    src = (_SRC.replace("@DEFINES@", defines).replace("@HELPERS@", secs.get("HELPERS", ""))
+           .replace("@PROLOGUE@", secs.get("PROLOGUE", "")).replace("@STEP@", secs.get("STEP", "")))
+    tag = hashlib.sha1(src.encode()).hexdigest()[:16]
+    d = os.path.join(tempfile.gettempdir(), "hb_cpu_harness")
+    os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, f"h{tag}.so")
+    if not os.path.exists(so):
+        cpp = os.path.join(d, f"h{tag}.cpp")
+        open(cpp, "w").write(src)
+        # -ffp-contract=off: no FMA contraction beyond the explicit fma() calls; plain IEEE
+        subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", cpp, "-o", so], check=True)
+    L = C.CDLL(so)
+    out = np.zeros((R, N, T) if eng.multinode or ensemble else (R, T), order="F")
+    sim = np.zeros((T, N)) if objective else None
+    S = len(prog.state_names)
+    final = np.zeros((S, N)) if return_final_states else None
+    P = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    L.run.argtypes = [C.c_int64, C.c_int64, C.c_int] + [C.c_void_p] * 8 + [C.c_double] + [C.c_void_p] * 3
+    L.run(N, T, 1 if ensemble else 0, P(inp), P(flat), P(p_off), P(p_mode), P(htypes), P(init), P(uhw_flat),
+          P(nn if nn is not None else np.zeros(1)), cfg.min_value, P(out), P(sim), P(final))
+    if objective:
+        return sim.T.copy()          # [N, T] simulated last row
+    if return_final_states:
+        return out, final
+    return out

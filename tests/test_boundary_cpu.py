@@ -1,0 +1,62 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/hydrob200.h declares, compiles
+kernels without a device, and fails loudly (no CPU fallback) when asked to run without one."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hydromodels_jl_b200 as hm
+from hydromodels_jl_b200 import engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hydrob200.h")).read()
+    declared = set(re.findall(r"^\s*(?:const\s+char\s*\*|int)\s*(hb_\w+)\s*\(", hdr, flags=re.M))
+    assert {"hb_compile_stepper", "hb_run", "hb_run_device", "hb_last_error", "hb_version"} <= declared
+    lib = ctypes.CDLL(engine.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared in hydrob200.h but not exported"
+    assert engine.lib().hb_version() == 1
+
+
+def test_struct_sizes_match_header():
+    # the library checks struct_size; a mismatch would surface as HB_ERR_INVALID at compile time
+    eng = hm.B200Model(hm.models.exphydro())
+    ck = eng.compiled()
+    assert len(ck.cubin()) > 1000 and "hb_stepper" in ck.source()
+    assert "cp.async.bulk" in ck.source()
+
+
+def test_nvrtc_error_is_reported():
+    from hydromodels_jl_b200.lowering import lower_stepper
+    prog = lower_stepper(hm.models.exphydro())
+    prog.body = prog.body.replace("hb_out[0] =", "hb_out[0] = undefined_symbol +")
+    with pytest.raises(engine.HydroB200Error, match="undefined_symbol"):
+        engine.CompiledStepper(prog)
+
+
+@pytest.mark.skipif(hm.device_count() > 0, reason="needs a box without a GPU")
+def test_no_device_means_no_result():
+    model = hm.models.exphydro()
+    with pytest.raises(hm.NoDeviceError, match="no CPU fallback"):
+        model(np.zeros((3, 10)), {"params": dict(f=0.0167, Smax=1709.46, Qmax=18.47, Df=2.674, Tmax=0.17, Tmin=-2.09)})
+
+
+def test_argument_errors_raise_before_any_device_work():
+    model = hm.models.exphydro(htypes=np.arange(1, 9))
+    p = {"params": {k: np.full(8, 1.0) for k in ["Tmin", "Tmax", "Df", "Smax", "Qmax", "f"]}}
+    with pytest.raises(ValueError, match="only accepts 3D input"):
+        model(np.zeros((3, 10)), p)
+    with pytest.raises(AssertionError, match="Input variables length mismatch"):
+        model(np.zeros((2, 8, 10)), p)
+    with pytest.raises(TypeError):
+        model(np.zeros((3, 8, 10)), [1.0, 2.0])
+    with pytest.raises(NotImplementedError):
+        model(np.zeros((3, 8, 10)), p, hm.HydroConfig(solver=hm.ODESolver))
+    with pytest.raises(ValueError, match="reads 'b' before it is defined"):
+        s = hm.Symbols("a b c", "")
+        hm.HydroBucket(fluxes=[hm.HydroFlux("c ~ b + a", symbols=s), hm.HydroFlux("b ~ a", symbols=s)])

@@ -1,0 +1,206 @@
+"""Parity tests proper: the CUDA path (through the C-ABI libhydrob200.so) against the CPU oracle
+on identical seeded inputs.  Tolerance = the north star's: 1e-10 relative in Float64, with an
+absolute floor of 1e-12 (mm) for values the reference itself only resolves to ~1e-16 absolute
+because `tanh(5x)+1` cancels."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import hydromodels_jl_b200 as hm
+from hydromodels_jl_b200 import synthetic as sy
+from hydromodels_jl_b200.engine import DeviceBuffer, DeviceRun
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+import hydro_oracle as ho  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-10, 1e-12
+DOCS_P = dict(f=0.0167, Smax=1709.46, Qmax=18.47, Df=2.674, Tmax=0.17, Tmin=-2.09)
+
+
+def assert_parity(got, ref, rtol=RTOL, atol=ATOL):
+    assert got.shape == ref.shape
+    assert np.all(np.isfinite(got))
+    err = np.abs(got - ref) - (rtol * np.abs(ref) + atol)
+    assert err.max() <= 0, f"max excess {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+def case(name, N, T, shared=False, n0=0):
+    ht = (np.arange(N) % 7 + 1) if shared else np.arange(1, N + 1)
+    ntypes = int(ht.max())
+    model = getattr(hm.models, name)(htypes=ht)
+    inp = sy.forcing(name, n0, n0 + N, T)
+    p = {"params": sy.parameters(name, n0, n0 + ntypes)}
+    if name == "m50":
+        et, q = hm.models.m50_chains()
+        p["nns"] = {"etnn": et.init_params(1) * 0.5, "qnn": q.init_params(2) * 0.5}
+    init = {k: np.full(N, v) for k, v in sy.INIT[name].items()}
+    return model, inp, p, init
+
+
+# ---- BASELINE config 1: single basin, README/docs run ------------------------------------------
+def test_exphydro_single_basin_published_run(golden):
+    d = golden("exphydro_01013500.npz")
+    inp = np.stack([d["temp"], d["lday"], d["prcp"]])
+    model = hm.models.exphydro(docs_variant=True)
+    init = dict(snowpack=0.0, soilwater=1303.0)
+    got = model(inp, {"params": DOCS_P}, initstates=init)           # the functor itself
+    assert got.shape == (10, 10000)
+    assert_parity(got, ho.run_model(model, inp, {"params": DOCS_P}, initstates=init))
+    # the reference's published table (6 digits) and, with the clamp off, its published NSE
+    assert np.allclose(got[:, 9999], [279.852, 1517.0, 0.176836, 0.14, 0.0, -0.0, 0.156927, 0.742322, 0.0, 0.742322],
+                       rtol=6e-6, atol=2e-6)
+    got0 = model(inp, {"params": DOCS_P}, hm.HydroConfig(min_value=1e-300), initstates=init)
+    obs, sim = d["flow"], got0[-1]
+    nse = 1 - np.sum((obs - sim) ** 2) / np.sum((obs - obs.mean()) ** 2)
+    assert abs(nse - 0.7323810502829138) < 1e-12
+
+
+# ---- multi-node parity on every model family, TMA path and ragged/odd shapes ---------------------
+@pytest.mark.parametrize("name", ["exphydro", "gr4j", "hbv", "m50"])
+@pytest.mark.parametrize("N,shared", [(256, False), (1000, True), (33, False), (1, False)])
+def test_multinode_matches_oracle(name, N, shared):
+    T = 120 if name == "m50" else 200
+    model, inp, p, init = case(name, N, T, shared)
+    got = model(inp, p, initstates=init)
+    assert got.shape == (len(model.var_names), N, T) and got.flags.f_contiguous
+    assert_parity(got, ho.run_model(model, inp, p, initstates=init))
+
+
+def test_tma_and_fallback_paths_agree_bitwise(monkeypatch):
+    model, inp, p, init = case("exphydro", 2048, 100)
+    a = model(inp, p, initstates=init)
+    monkeypatch.setenv("HB_DISABLE_TMA", "1")
+    b = model(inp, p, initstates=init)
+    assert np.array_equal(a, b)
+
+
+def test_multinode_equals_replicated_single_node(golden):
+    """`test/base/run_multi_bucket.jl:79,115,171,190` (atol 1e-10), independent and shared htypes."""
+    d = golden("exphydro_01013500.npz")
+    T, N = 300, 96
+    inp = np.stack([d["temp"][:T], d["lday"][:T], d["prcp"][:T]])
+    single = hm.models.exphydro()(inp, {"params": DOCS_P}, initstates=dict(snowpack=0.0, soilwater=1303.0))
+    inp3 = np.asfortranarray(np.repeat(inp[:, None, :], N, axis=1))
+    for ht in (np.arange(1, N + 1), np.arange(N) % 3 + 1):
+        p = {"params": {k: np.full(int(ht.max()), v) for k, v in DOCS_P.items()}}
+        init = np.concatenate([np.zeros(N), np.full(N, 1303.0)])         # flat, state-major
+        out = hm.models.exphydro(htypes=ht)(inp3, p, initstates=init)
+        assert np.array_equal(out, np.repeat(single[:, None, :], N, axis=1))
+        assert np.all(out[:2] >= 1e-6)
+
+
+def test_rows_subset_default_states_and_min_value():
+    model, inp, p, _ = case("gr4j", 320, 150)
+    cfg = hm.HydroConfig(min_value=1e-3)
+    ref = ho.run_model(model, inp, p, cfg)
+    got = hm.B200Model(model)(inp, p, cfg, rows=["flow", "soilwater"])
+    assert_parity(got, ref[[model.var_names.index("flow"), model.var_names.index("soilwater")]])
+
+
+def test_chunked_run_resumes_bit_identically():
+    """States are rows: `initstates = final states` continues a run (SURVEY.md §5 checkpoint row)."""
+    model, inp, p, init = case("hbv", 512, 180)
+    eng = hm.B200Model(model)
+    full = eng(inp, p, initstates=init)
+    a, fin = eng(np.asfortranarray(inp[:, :, :77]), p, initstates=init, return_final_states=True)
+    b = eng(np.asfortranarray(inp[:, :, 77:]), p, initstates=fin.reshape(-1))
+    assert np.array_equal(np.concatenate([a, b], axis=2), full)
+
+
+def test_standalone_flux_uh_bucket_components():
+    s = hm.Symbols("a b c d", "p1 p2")
+    flux = hm.HydroFlux(["c ~ a * p1 + b * p2", "d ~ a + p1 + b + p2"], symbols=s)
+    inp = np.array([[2.0, 3.0], [3.0, 2.0], [4.0, 1.0]]).T
+    assert np.array_equal(flux(inp, {"params": dict(p1=3.0, p2=4.0)}),
+                          np.array([[18.0, 12.0], [17.0, 12.0], [16.0, 12.0]]).T)     # exact KAT
+    fl3 = hm.HydroFlux(["c ~ a * p1 + b * p2"], symbols=s, htypes=np.arange(1, 11))
+    inp3 = np.asfortranarray(np.repeat(np.array([[2.0, 3.0, 1.0], [3.0, 2.0, 2.0]])[:, None, :], 10, axis=1))
+    out3 = fl3(inp3, {"params": dict(p1=np.full(10, 3.0), p2=np.full(10, 4.0))})
+    assert np.array_equal(out3, np.repeat(np.array([[18.0, 17.0, 11.0]])[:, None, :], 10, axis=1))
+    g = hm.models.gr4j(htypes=np.array([1, 2, 2, 1, 3]))
+    uh = g.components[2]
+    x = np.asfortranarray(np.abs(np.random.default_rng(0).normal(size=(1, 5, 80))))
+    pu = {"params": dict(x4=np.array([1.39, 2.7, 0.0]))}
+    got = uh(x, pu)
+    assert_parity(got, ho.run_uh(uh, x, pu))
+    assert np.array_equal(got[0, 4], x[0, 4])                       # K = 0 node: identity
+    assert np.allclose(got[0, 1], got[0, 2], atol=1e-8)             # same htype ⇒ same weights (run_unithydro.jl:114-118)
+    bucket = hm.models.exphydro().components[0]
+    inpb = sy.forcing("exphydro", 0, 1, 90)[[0, 2, 1], 0, :]        # bucket input order: temp, prcp, lday
+    assert bucket.input_names == ["temp", "prcp", "lday"]
+    pb = {"params": dict(Tmin=-2.09, Tmax=0.17, Df=2.674)}
+    assert_parity(bucket(inpb, pb), ho.run_bucket(bucket, inpb, pb))
+
+
+# ---- calibration ensemble: fused objective -------------------------------------------------------
+@pytest.mark.parametrize("metric", ["NSE", "KGE", "MSE", "LogKGE"])
+def test_ensemble_objective_matches_oracle(metric, golden):
+    h = golden("hbv_sample.npz")
+    T, M, warm = 730, 300, 31
+    inp = np.stack([h["prec"][:T], h["temp"][:T], h["pet"][:T]])
+    model = hm.models.hbv()
+    pm = sy.parameters("hbv", 0, M)
+    init = dict(snowpack=0.0, meltwater=0.0, soilwater=100.0, suz=3.0, slz=10.0)
+    truth = ho.run_model(model, inp, {"params": {k: v[7] for k, v in pm.items()}}, initstates=init)[-1]
+    target = truth * (1 + 0.05 * np.sin(np.arange(T) / 9.0)) + 0.01
+    got = hm.B200Model(model).objective(inp, {"params": pm}, target, metric=metric, warm_up=warm, initstates=init,
+                                        n_members=M)
+    ref = np.array([ho.objective(metric, target,
+                                 ho.run_model(model, inp, {"params": {k: v[i] for k, v in pm.items()}}, initstates=init)[-1],
+                                 warm_up=warm) for i in range(0, M, 10)])
+    assert np.allclose(got[::10], ref, rtol=1e-9, atol=1e-12)
+
+
+def test_device_resident_run_and_per_node_objective():
+    model, inp, p, init = case("exphydro", 4096, 64)
+    ref = model(inp, p, initstates=init)
+    eng = hm.B200Model(model)
+    run = DeviceRun(eng, 4096, 64, p, initstates=init)
+    din, dout = DeviceBuffer.from_host(inp.ravel(order="K")), DeviceBuffer(run.out_bytes)
+    ms = run.launch(din.ptr, dout.ptr, None, timed=True)
+    assert ms > 0
+    assert np.array_equal(dout.to_host((10, 4096, 64), order="F"), ref)
+    tgt = ref[-1] * 1.1 + 0.05
+    obj = eng.objective(inp, p, tgt, metric="NSE", warm_up=5, initstates=init)
+    o5 = ho.objective("NSE", tgt[5], ref[-1][5], warm_up=5)
+    assert abs(obj[5] - o5) < 1e-9
+
+
+# ---- size-independent properties at a large size ----------------------------------------------------
+def test_large_run_properties():
+    """200k basins × 100 steps (no oracle at this size): states ≥ min_value, finite rows, a random
+    subset re-run alone gives bit-identical rows, and a sampled set of basins matches the oracle."""
+    N, T = 200_000, 100
+    model, inp, p, init = case("exphydro", N, T)
+    out = model(inp, p, initstates=init)
+    assert np.all(np.isfinite(out)) and np.all(out[:2] >= 1e-6)
+    assert np.allclose(out[9], out[7] + out[8], rtol=1e-15, atol=0)         # flow = baseflow + surfaceflow
+    idx = np.sort(np.random.default_rng(1).choice(N, 64, replace=False))
+    sub = hm.models.exphydro(htypes=np.arange(1, 65))
+    psub = {"params": {k: v[idx] for k, v in p["params"].items()}}
+    isub = {k: v[idx] for k, v in init.items()}
+    inps = np.asfortranarray(inp[:, idx, :])
+    assert np.array_equal(sub(inps, psub, initstates=isub), out[:, idx, :])
+    assert_parity(out[:, idx, :], ho.run_model(sub, inps, psub, initstates=isub))
+
+
+# ---- error behaviour at the boundary -------------------------------------------------
+def test_boundary_errors():
+    model, inp, p, init = case("exphydro", 8, 10)
+    with pytest.raises(ValueError, match="only accepts 3D input"):
+        model(inp[:, 0, :], p)
+    with pytest.raises(AssertionError, match="Input variables length mismatch"):
+        model(np.asfortranarray(inp[:2]), p)
+    with pytest.raises(KeyError, match="does not exist in params"):
+        model(inp, {"params": {k: v for k, v in p["params"].items() if k != "Df"}})
+    with pytest.raises(IndexError, match="BoundsError"):
+        hm.models.exphydro(htypes=np.arange(2, 10))(inp, p)
+    with pytest.raises(ValueError, match="min_value must be positive"):
+        hm.HydroConfig(min_value=0.0)
+    with pytest.raises(ValueError, match="timeidx"):
+        model(inp, p, hm.HydroConfig(timeidx=[2, 3, 4]))
+    with pytest.raises(TypeError):
+        model(inp, np.zeros(6))
