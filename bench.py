@@ -146,6 +146,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--block", type=int, default=0, help="tuning: threads per block of the stepper")
+    ap.add_argument("--stages", type=int, default=0, help="tuning: forcing pipeline depth (time steps)")
+    ap.add_argument("--maxreg", type=int, default=0, help="tuning: NVRTC --maxrregcount")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -195,7 +198,7 @@ def main():
 
     n0 = rank * N
     model, p, init = build_problem(hm, sy, model_name, n0, N, T)
-    eng = hm.B200Model(model)
+    eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
     run = DeviceRun(eng, N, T, p, initstates=init)
     d_in = device_forcing(torch, model_name, N, T, sy.SEED + 17 * rank)
     d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
@@ -243,7 +246,7 @@ def main():
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_basin_timestep": bytes_per_unit, "kernel_ms": k_ms,
                 "registers": info["registers_per_thread"], "blocks_per_sm": info["max_blocks_per_sm"],
-                "dyn_smem": info["dynamic_smem_bytes"]}
+                "dyn_smem": info["dynamic_smem_bytes"], "block": info["block_threads"], "spill_bytes": info["local_bytes_per_thread"]}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:

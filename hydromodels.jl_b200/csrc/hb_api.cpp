@@ -435,7 +435,7 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
              "#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n",
              spec->n_inputs, spec->output_mode == HB_OUT_ROWS ? spec->n_rows : 0, spec->n_states, spec->n_params, m->uhw_total,
              m->uhh_total, spec->nn_words, spec->output_mode, spec->metric, spec->shared_forcing ? 1 : 0, m->block, stages, minblocks);
-    std::string full_body = std::string(defs) + body;   // body may append to DEFINES (e.g. HB_NC)
+    std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";   // body may append to DEFINES (e.g. HB_NC)
     m->source = splice(kStepperTemplate, full_body.c_str());
     m->kernel_name = "hb_stepper";
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};

@@ -107,34 +107,8 @@ __device__ __forceinline__ void hb_bulk_wait() {
 }
 __device__ __forceinline__ void hb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- math helpers shared by all generated bodies ----------------------------------------------
-// 1/x for finite, normal x > 0: MUFU.RCP64H seed + Newton steps (quadratic; seed is ~2^-20).
-// The IEEE division the compiler would emit is ~3x as many FP64-pipe instructions.
-__device__ __forceinline__ double hb_rcp_pos(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
-}
-// step_func(x) = (tanh(5x)+1)/2 (/root/reference/src/HydroModels.jl:204) == 1/(1+exp(-10x)).
-// The argument of exp is capped at 700 so 1+exp stays finite (result < 1e-304 there; the
-// reference's tanh form returns exactly 0 below x ~ -3.8 — both are 0 to within 1e-16 absolute).
-__device__ __forceinline__ double hb_step(double x) {
-    const double z = fmin(-10.0 * x, 700.0);
-    return hb_rcp_pos(1.0 + exp(z));
-}
-// tanh(x) = 1 - 2/(1+exp(2x)), same capped-logistic evaluation (absolute error < 2e-16).
-__device__ __forceinline__ double hb_tanh(double x) {
-    const double z = fmin(2.0 * x, 700.0);
-    return fma(-2.0, hb_rcp_pos(1.0 + exp(z)), 1.0);
-}
-__device__ __forceinline__ double hb_leakyrelu(double x) { return fmax(0.01 * x, x); }
-__device__ __forceinline__ double hb_clamp(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+// ---- math helpers shared by all generated bodies: templates/hb_math.cuh -----------------------
+//@@HB:MATH
 
 //@@HB:HELPERS
 
@@ -209,7 +183,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     const double *in_lane = a.in + (HB_SHARED_FORCING ? 0 : n * HB_V);
     double *out_warp = a.out + n0w * HB_R;
     double *out_lane = a.out + n * HB_R;
-    (void)in_warp; (void)out_warp; (void)out_lane;
+    (void)in_warp; (void)out_warp; (void)out_lane; (void)in_lane;
 
     if (tma_in) {
         if (lane == 0) {
@@ -231,6 +205,14 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     int slot = 0;
     u32 parity = 0;
     int ob = 0;
+    // running pointers (strength-reduced: no 64-bit multiplies in the time loop)
+    const i64 out_step = a.N * (i64)HB_R;
+    const double *pf_ptr = in_warp + (i64)HB_STAGES * in_step;   // forcing prefetched HB_STAGES steps ahead
+    const double *gx = in_lane;
+    double *ow_ptr = out_warp;
+    double *go = out_lane;
+    (void)pf_ptr; (void)gx; (void)ow_ptr; (void)go; (void)out_step;
+#pragma unroll 1
     for (i64 t = 0; t < T; ++t) {
         // ---- forcing of this step -------------------------------------------------------------
         double hb_x[HB_ARR(HB_V)];
@@ -242,14 +224,14 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
             __syncwarp();   // every lane has consumed the slot -> refill it HB_STAGES steps ahead
             if (lane == 0 && t + HB_STAGES < T) {
                 hb_mbar_expect_tx(hb_smem_u32(&bars[slot]), kInStage);
-                hb_bulk_g2s(hb_smem_u32(sIn + slot * 32 * HB_V), in_warp + (t + HB_STAGES) * in_step, kInStage,
-                            hb_smem_u32(&bars[slot]));
+                hb_bulk_g2s(hb_smem_u32(sIn + slot * 32 * HB_V), pf_ptr, kInStage, hb_smem_u32(&bars[slot]));
             }
+            pf_ptr += in_step;
             if (++slot == HB_STAGES) { slot = 0; parity ^= 1; }
         } else {
-            const double *gx = in_lane + t * in_step;
 #pragma unroll
             for (int v = 0; v < HB_V; ++v) hb_x[v] = gx[v];
+            gx += in_step;
         }
         double hb_out[HB_ARR(HB_R)];
         (void)hb_x; (void)hb_out;
@@ -272,14 +254,15 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
             hb_fence_proxy_async();   // generic-proxy writes -> visible to the async proxy
             __syncwarp();
             if (lane == 0) {
-                hb_bulk_s2g(out_warp + t * a.N * HB_R, hb_smem_u32(so), kOutTile);
+                hb_bulk_s2g(ow_ptr, hb_smem_u32(so), kOutTile);
                 hb_bulk_commit();
             }
+            ow_ptr += out_step;
             ob ^= 1;
         } else {
-            double *go = out_lane + t * a.N * HB_R;
 #pragma unroll
             for (int r = 0; r < HB_R; ++r) go[r] = hb_out[r];
+            go += out_step;
         }
 #endif
 #if HB_MODE == 1

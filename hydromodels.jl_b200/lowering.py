@@ -480,7 +480,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
         i = v.id
         if v.op == "state" and v.payload[1] == 1:
             si = v.payload[0]                         # all increments of its bucket precede this leaf
-            step.append(f"const double hb_un{si} = fmax(hb_minv, hb_u[{si}] + {step_ref(pending_updates[si][2])});")
+            step.append(f"const double hb_un{si} = hb_max(hb_minv, hb_u[{si}] + {step_ref(pending_updates[si][2])});")
             continue
         if i not in live or v.mask == 0 or v.op in ("const", "in", "param", "state") or i in carried:
             continue
@@ -541,19 +541,19 @@ def _expr_with(v: Val, a: List[str], fast: bool) -> str:
     if op == "rcp": return f"1.0 / {a[0]}"
     if op == "neg": return f"-{a[0]}"
     if op == "pow": return f"pow({a[0]}, {a[1]})"
-    if op == "exp": return f"exp({a[0]})"
+    if op == "exp": return f"hb_exp({a[0]})" if fast else f"exp({a[0]})"
     if op == "log": return f"log({a[0]})"
     if op == "sqrt": return f"sqrt({a[0]})"
     if op == "abs": return f"fabs({a[0]})"
     if op == "tanh": return f"hb_tanh({a[0]})" if fast else f"tanh({a[0]})"
     if op == "step": return f"hb_step({a[0]})" if fast else f"(tanh(5.0 * {a[0]}) + 1.0) * 0.5"
-    if op == "min": return f"fmin({a[0]}, {a[1]})"
-    if op == "max": return f"fmax({a[0]}, {a[1]})"
+    if op == "min": return f"hb_min({a[0]}, {a[1]})" if fast else f"fmin({a[0]}, {a[1]})"
+    if op == "max": return f"hb_max({a[0]}, {a[1]})" if fast else f"fmax({a[0]}, {a[1]})"
     raise LoweringError(f"no emitter for {op}")
 
 
-_ACT_C = {"identity": "{}", "tanh": "hb_tanh({})", "leakyrelu": "hb_leakyrelu({})", "relu": "fmax(0.0, {})",
-          "sigmoid": "hb_rcp_pos(1.0 + exp(fmin(-({}), 700.0)))"}
+_ACT_C = {"identity": "{}", "tanh": "hb_tanh({})", "leakyrelu": "hb_leakyrelu({})", "relu": "hb_max(0.0, {})",
+          "sigmoid": "hb_rcp(1.0 + hb_exp_narrow(hb_clamp_abs(-({}), HB_HI_700)))"}
 _ACT_C_EXACT = dict(_ACT_C, tanh="tanh({})", sigmoid="(1.0 / (1.0 + exp(-({}))))")
 
 

@@ -20,10 +20,8 @@ _SRC = r'''
 #include <cmath>
 #include <cstdint>
 typedef long long i64;
-static inline double hb_rcp_pos(double x) { return 1.0 / x; }
-static inline double hb_step(double x) { const double z = fmin(-10.0 * x, 700.0); return hb_rcp_pos(1.0 + exp(z)); }
-static inline double hb_tanh(double x) { const double z = fmin(2.0 * x, 700.0); return fma(-2.0, hb_rcp_pos(1.0 + exp(z)), 1.0); }
-static inline double hb_leakyrelu(double x) { return fmax(0.01 * x, x); }
+#define HB_HOST_TEST 1
+#include "@MATH_HEADER@"
 #define __device__
 #define __forceinline__ inline
 #define __restrict__
@@ -96,9 +94,11 @@ def run_body_on_cpu(eng, input, params, config=None, initstates=None, rows=None,
         f"#define HB_V {len(prog.input_names)}", f"#define HB_R {R}", f"#define HB_S {len(prog.state_names)}",
         f"#define HB_NP {len(prog.param_slots)}", f"#define HB_UHW_TOTAL {sum(prog.uh_kmax)}",
         f"#define HB_UHH_TOTAL {sum(k - 1 for k in prog.uh_kmax)}", secs.get("DEFINES", "")])
-    src = (_SRC.replace("@DEFINES@", defines).replace("@HELPERS@", secs.get("HELPERS", ""))
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hydromodels.jl_b200", "csrc",
+                       "templates", "hb_math.cuh")
+    src = (_SRC.replace("@DEFINES@", defines).replace("@MATH_HEADER@", hdr).replace("@HELPERS@", secs.get("HELPERS", ""))
            .replace("@PROLOGUE@", secs.get("PROLOGUE", "")).replace("@STEP@", secs.get("STEP", "")))
-    tag = hashlib.sha1(src.encode()).hexdigest()[:16]
+    tag = hashlib.sha1((src + open(hdr).read()).encode()).hexdigest()[:16]
     d = os.path.join(tempfile.gettempdir(), "hb_cpu_harness")
     os.makedirs(d, exist_ok=True)
     so = os.path.join(d, f"h{tag}.so")

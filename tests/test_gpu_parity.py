@@ -122,7 +122,9 @@ def test_standalone_flux_uh_bucket_components():
     assert np.array_equal(out3, np.repeat(np.array([[18.0, 17.0, 11.0]])[:, None, :], 10, axis=1))
     g = hm.models.gr4j(htypes=np.array([1, 2, 2, 1, 3]))
     uh = g.components[2]
-    x = np.asfortranarray(np.abs(np.random.default_rng(0).normal(size=(1, 5, 80))))
+    x = np.abs(np.random.default_rng(0).normal(size=(1, 5, 80)))
+    x[0, 2] = x[0, 1]                                               # nodes 1 and 2 share htype 2 and the input
+    x = np.asfortranarray(x)
     pu = {"params": dict(x4=np.array([1.39, 2.7, 0.0]))}
     got = uh(x, pu)
     assert_parity(got, ho.run_uh(uh, x, pu))

@@ -1,0 +1,79 @@
+"""CPU-only accuracy tests of templates/hb_math.cuh (the same source the kernels compile, built
+here as host C++ with HB_HOST_TEST) against libm."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HDR = os.path.join(ROOT, "hydromodels.jl_b200", "csrc", "templates", "hb_math.cuh")
+
+
+@pytest.fixture(scope="module")
+def hbm():
+    d = tempfile.mkdtemp(prefix="hb_math_")
+    src = os.path.join(d, "m.cpp")
+    open(src, "w").write(f'''#define HB_HOST_TEST 1
+#include "{HDR}"
+extern "C" void apply(int which, long n, const double* x, double* y) {{
+    for (long i = 0; i < n; ++i) {{
+        switch (which) {{
+            case 0: y[i] = hb_exp(x[i]); break;
+            case 1: y[i] = hb_step(x[i]); break;
+            case 2: y[i] = hb_tanh(x[i]); break;
+            case 3: y[i] = hb_rcp(x[i]); break;
+        }}
+    }}
+}}''')
+    so = os.path.join(d, "m.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", src, "-o", so], check=True)
+    lib = C.CDLL(so)
+
+    def f(which, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        lib.apply(C.c_int(which), C.c_long(x.size), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p))
+        return y
+    return f
+
+
+def test_exp_full_range(hbm):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-700, 700, 200000), rng.uniform(-2, 2, 200000), rng.normal(0, 1e-3, 1000),
+                        np.array([0.0, -0.0, 1.0, -1.0, 709.7, -708.0, 1e-300])])
+    rel = np.abs(hbm(0, x) - np.exp(x)) / np.exp(x)
+    assert rel.max() < 4e-16
+    edge = hbm(0, np.array([710.0, 1e6, np.inf, -746.0, -1e6, -np.inf, -740.0, -745.0]))
+    assert np.all(np.isinf(edge[:3])) and np.all(edge[3:6] == 0.0)
+    assert np.allclose(edge[6:], np.exp([-740.0, -745.0]), rtol=0, atol=1e-323)  # subnormal results, gradual underflow
+
+
+def test_step_func_against_reference_form(hbm):
+    """|hb_step(x) − (tanh(5x)+1)/2| ≤ 2e-16 absolute everywhere (the reference form itself only
+    resolves to ~1.1e-16 absolute), and relative 1e-15 where the value is not tiny."""
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-100, 100, 200000), rng.uniform(-3, 3, 200000), rng.normal(0, 1e-6, 1000),
+                        np.array([0.0, 1e-6, 1303.0, -1303.0, 1e300, -1e300, np.inf, -np.inf])])
+    got = hbm(1, x)
+    ref = (np.tanh(5.0 * x) + 1.0) * 0.5
+    assert np.all(np.isfinite(got)) and got.min() >= 0.0 and got.max() <= 1.0
+    assert np.abs(got - ref).max() < 2.5e-16
+    # against the exact logistic in extended precision the relative error is ~1 ulp even where the
+    # value is tiny (the reference's tanh form loses all relative accuracy there)
+    xl = np.clip(x, -60.0, 60.0).astype(np.longdouble)
+    truth = 1.0 / (1.0 + np.exp(-10.0 * xl))
+    sel = np.abs(x) <= 60.0
+    # conditioning: rounding z = -10x to double alone moves exp(z) by |z|·1.1e-16 relative
+    tol = 6e-16 + np.abs(10.0 * x[sel]) * 1.2e-16
+    assert np.all(np.abs(got[sel] - truth[sel]) / truth[sel] < tol)
+
+
+def test_tanh_and_rcp(hbm):
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.uniform(-30, 30, 200000), rng.normal(0, 1e-4, 1000), [0.0, 400.0, -400.0]])
+    assert np.abs(hbm(2, x) - np.tanh(x)).max() < 4.5e-16      # 2 ulp of 1.0
+    y = np.concatenate([rng.uniform(1e-3, 1e3, 100000), -rng.uniform(1e-3, 1e3, 100000), 10.0 ** rng.uniform(-250, 250, 100000)])
+    assert (np.abs(hbm(3, y) * y - 1.0)).max() < 5e-16
