@@ -18,6 +18,20 @@ __global__ void __launch_bounds__(256) hb_fp64_probe(double *out, int iters, dou
     if (s == 123.456) out[0] = s;   // never true; keeps the chain alive
 }
 
+// FP64 tensor-core probe: mma.sync m8n8k4 f64 (SASS DMMA), 4 independent accumulator tiles per warp.
+__global__ void __launch_bounds__(256) hb_dmma_probe(double *out, int iters, double a, double b) {
+    double c0[2] = {0.0, 0.0}, c1[2] = {1.0, 1.0}, c2[2] = {2.0, 2.0}, c3[2] = {3.0, 3.0};
+    const double av = a + threadIdx.x * 1e-9, bv = b;
+    for (int i = 0; i < iters; ++i) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[0]), "+d"(c0[1]) : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c1[0]), "+d"(c1[1]) : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c2[0]), "+d"(c2[1]) : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c3[0]), "+d"(c3[1]) : "d"(av), "d"(bv));
+    }
+    const double s = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1];
+    if (s == 123.456) out[0] = s;
+}
+
 __global__ void hb_fill(double *p, int64_t n, double v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -55,6 +69,39 @@ int hb_probe_fp64_tflops(double *tflops) {
     cudaFree(d);
     if (cudaGetLastError() != cudaSuccess) return HB_ERR_CUDA;
     const double flop = 2.0 * 8.0 * iters * (double)blocks * threads;
+    *tflops = flop / (best * 1e-3) / 1e12;
+    return HB_OK;
+}
+
+// Measured FP64 tensor-core (DMMA m8n8k4) throughput in TFLOP/s: decides whether the MLP-fused
+// stepper should contract its dense layers on the tensor pipe or on the FP64 FMA pipe.
+int hb_probe_dmma_tflops(double *tflops) {
+    if (!tflops) return HB_ERR_INVALID;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return HB_ERR_NO_DEVICE; }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double *d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return HB_ERR_NOMEM;
+    const int iters = 1 << 12, blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    hb_dmma_probe<<<blocks, threads>>>(d, iters, 0.5, 1e-3);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        hb_dmma_probe<<<blocks, threads>>>(d, iters, 0.5, 1e-3);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess) return HB_ERR_CUDA;
+    const double flop = 2.0 * 8 * 8 * 4 * 4.0 * iters * (double)blocks * (threads / 32);   // 4 MMAs of 8x8x4 per warp-iteration
     *tflops = flop / (best * 1e-3) / 1e12;
     return HB_OK;
 }

@@ -58,6 +58,8 @@ struct Driver {
     decltype(&cuLaunchKernel) LaunchKernel = nullptr;
     decltype(&cuOccupancyMaxActiveBlocksPerMultiprocessor) Occupancy = nullptr;
     decltype(&cuGetErrorString) GetErrorString = nullptr;
+    decltype(&cuModuleGetGlobal) ModuleGetGlobal = nullptr;
+    decltype(&cuMemcpyDtoDAsync) MemcpyDtoDAsync = nullptr;
 } g_drv;
 
 template <typename F>
@@ -88,7 +90,8 @@ int ensure_device() {
                   load_sym("cuFuncSetAttribute", g_drv.FuncSetAttribute) &&
                   load_sym("cuFuncGetAttribute", g_drv.FuncGetAttribute) && load_sym("cuLaunchKernel", g_drv.LaunchKernel) &&
                   load_sym("cuOccupancyMaxActiveBlocksPerMultiprocessor", g_drv.Occupancy) &&
-                  load_sym("cuGetErrorString", g_drv.GetErrorString);
+                  load_sym("cuGetErrorString", g_drv.GetErrorString) && load_sym("cuModuleGetGlobal", g_drv.ModuleGetGlobal) &&
+                  load_sym("cuMemcpyDtoDAsync", g_drv.MemcpyDtoDAsync);
         if (!ok) return fail(HB_ERR_CUDA, "could not resolve CUDA driver entry points");
         g_drv.ok = true;
     }
@@ -207,8 +210,9 @@ std::string splice(const char *tmpl, const char *body) {
 
 // ---- model object ----------------------------------------------------------------------------------
 struct hb_model_s {
-    int kind = 0;   // 0 stepper
+    int kind = 0;   // 0 stepper, 1 route
     hb_stepper_spec spec{};
+    hb_route_spec rspec{};
     std::string source;
     std::string kernel_name;
     std::vector<char> cubin;
@@ -219,6 +223,7 @@ struct hb_model_s {
     int dyn_smem = 0;
     int block = 128;
     int uhw_total = 0, uhh_total = 0;
+    CUdeviceptr nn_const = 0;   // module-scope __constant__ hb_nn_const[]
     // workspace for hb_run (host-pointer entry point)
     struct Buf { void *p = nullptr; size_t cap = 0; };
     Buf ws[12];
@@ -269,7 +274,7 @@ int nvrtc_compile(const std::string &src, const std::vector<std::string> &opts, 
 int stepper_smem_bytes(const hb_stepper_spec &s, int block, int stages) {
     auto up128 = [](int x) { return (x + 127) / 128 * 128; };
     int warps = block / 32;
-    int nn = up128(s.nn_words * 8);
+    int nn = 0;   // MLP parameters live in the module's constant bank (hb_nn_const), not in shared memory
     int in_b = up128(stages * 32 * s.n_inputs * 8);
     int out_b = s.output_mode == HB_OUT_ROWS ? up128(2 * 32 * s.n_rows * 8) : 0;
     return nn + warps * (in_b + out_b) + warps * stages * 8;
@@ -283,6 +288,11 @@ int load_model(hb_model_s *m) {
     HB_DRV(g_drv.ModuleGetFunction(&m->func, m->module, m->kernel_name.c_str()));
     if (m->dyn_smem > 48 * 1024)
         HB_DRV(g_drv.FuncSetAttribute(m->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
+    if (m->spec.nn_words > 0) {
+        size_t bytes = 0;
+        HB_DRV(g_drv.ModuleGetGlobal(&m->nn_const, &bytes, m->module, "hb_nn_const"));
+        if (bytes != (size_t)m->spec.nn_words * 8) return fail(HB_ERR_CUDA, "hb_nn_const has %zu bytes, expected %d", bytes, m->spec.nn_words * 8);
+    }
     return HB_OK;
 }
 
@@ -360,6 +370,8 @@ int launch_stepper(hb_model_s *m, const hb_run_desc *d, cudaStream_t stream) {
     void *params[1] = {buf};
     unsigned grid = (unsigned)((N + m->block - 1) / m->block);
     if (T == 0 && s.output_mode == HB_OUT_ROWS && !d->final_states) return HB_OK;
+    if (s.nn_words > 0)   // MLP parameters -> constant bank (stream-ordered before the launch)
+        HB_DRV(g_drv.MemcpyDtoDAsync(m->nn_const, (CUdeviceptr)(uintptr_t)d->nn_params, (size_t)s.nn_words * 8, (CUstream)stream));
     HB_DRV(g_drv.LaunchKernel(m->func, grid, 1, 1, m->block, 1, 1, m->dyn_smem, (CUstream)stream, params, nullptr));
     return HB_OK;
 }
@@ -428,6 +440,11 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
     if (minblocks > cap) minblocks = cap;
     if (minblocks < 1) minblocks = 1;
     if (minblocks > 4) minblocks = 4;   // 128 regs/thread at 128 threads x 4 blocks; FP64-heavy bodies need them
+    if (spec->max_registers > 0) {      // register budget per thread -> resident blocks the compiler must allow
+        int byregs = 65536 / (spec->max_registers * m->block);
+        if (byregs < 1) byregs = 1;
+        if (byregs < minblocks) minblocks = byregs;
+    }
     char defs[1024];
     snprintf(defs, sizeof defs,
              "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_UHW_TOTAL %d\n"
@@ -439,7 +456,6 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
     m->source = splice(kStepperTemplate, full_body.c_str());
     m->kernel_name = "hb_stepper";
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
-    if (spec->max_registers > 0) opts.push_back("--maxrregcount=" + std::to_string(spec->max_registers));
     int rc = nvrtc_compile(m->source, opts, m->cubin, m->from_cache);
     if (rc) { delete m; return rc; }
     *out = m;
@@ -571,6 +587,99 @@ int hb_run(hb_model_t m, const hb_run_desc *d) {
     }
     HB_CUDA(cudaStreamSynchronize(m->stream));
     if (d->elapsed_ms) HB_CUDA(cudaEventElapsedTime(d->elapsed_ms, m->ev0, m->ev1));
+    return HB_OK;
+}
+
+// ---- routing ---------------------------------------------------------------------------------------------
+int hb_compile_route(const hb_route_spec *spec, const char *body, hb_model_t *out) {
+    if (!spec || !body || !out) return fail(HB_ERR_INVALID, "NULL argument");
+    if (spec->struct_size != (int32_t)sizeof(hb_route_spec)) return fail(HB_ERR_INVALID, "hb_route_spec.struct_size mismatch");
+    if (spec->n_inputs < 0 || spec->n_inputs > 16 || spec->n_params < 0 || spec->n_params > HB_MAX_PARAMS)
+        return fail(HB_ERR_INVALID, "hb_route_spec out of range");
+    hb_model_s *m = new hb_model_s();
+    m->kind = 1;
+    m->rspec = *spec;
+    m->block = spec->block_threads > 0 ? spec->block_threads : 256;
+    m->dyn_smem = 0;
+    char defs[256];
+    snprintf(defs, sizeof defs, "//@@HB:DEFINES\n#define HB_RV %d\n#define HB_NP %d\n#define HB_BLOCK %d\n", spec->n_inputs,
+             spec->n_params, m->block);
+    std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";
+    m->source = splice(kRouteTemplate, full_body.c_str());
+    m->kernel_name = "hb_route_step";
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
+    int rc = nvrtc_compile(m->source, opts, m->cubin, m->from_cache);
+    if (rc) { delete m; return rc; }
+    *out = m;
+    return HB_OK;
+}
+
+int hb_run_route_device(hb_model_t m, const hb_route_desc *d, void *stream) {
+    if (!m || m->kind != 1) return fail(HB_ERR_INVALID, "not a route model");
+    if (!d || d->struct_size != (int32_t)sizeof(hb_route_desc)) return fail(HB_ERR_INVALID, "hb_route_desc.struct_size mismatch");
+    const hb_route_spec &s = m->rspec;
+    if (d->n_nodes <= 0 || d->n_steps < 0 || !d->records || !d->up_ptr || !d->up_idx) return fail(HB_ERR_INVALID, "bad route descriptor");
+    if (!(d->min_value > 0)) return fail(HB_ERR_INVALID, "min_value must be positive, got %g", d->min_value);
+    if (d->s_row < 0 || d->s_row >= d->n_rows || d->o_row < 0 || d->o_row >= d->n_rows) return fail(HB_ERR_INVALID, "route rows outside the record");
+    for (int v = 0; v < s.n_inputs; ++v)
+        if (d->in_row[v] < 0 || d->in_row[v] >= d->n_rows) return fail(HB_ERR_INVALID, "route input row outside the record");
+    int rc = load_model(m);
+    if (rc) return rc;
+    HB_CUDA(cudaSetDevice(g_device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t N = d->n_nodes, T = d->n_steps;
+    // ping-pong state / outflow buffers (library workspace)
+    for (int k = 0; k < 4; ++k)
+        if ((rc = ws_reserve(m->ws[k], (size_t)N * 8))) return rc;
+    double *sbuf[2] = {(double *)m->ws[0].p, (double *)m->ws[1].p};
+    double *qbuf[2] = {(double *)m->ws[2].p, (double *)m->ws[3].p};
+    if (d->initstates) HB_CUDA(cudaMemcpyAsync(sbuf[0], d->initstates, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
+    else HB_CUDA(cudaMemsetAsync(sbuf[0], 0, (size_t)N * 8, st));
+    if (d->elapsed_ms) {
+        if (!m->ev0) { HB_CUDA(cudaEventCreate(&m->ev0)); HB_CUDA(cudaEventCreate(&m->ev1)); }
+        HB_CUDA(cudaEventRecord(m->ev0, st));
+    }
+    const int nv = s.n_inputs > 0 ? s.n_inputs : 1, np = s.n_params > 0 ? s.n_params : 1;
+    unsigned grid = (unsigned)((N + m->block - 1) / m->block);
+    for (int64_t t = -1; t < T; ++t) {
+        // HbRouteArgs mirror (templates/route.cu): 9 pointers, 3 i64, 1 double, 3 int, int tables
+        unsigned char buf[9 * 8 + 3 * 8 + 8 + 3 * 4 + 4 * (16 + 2 * HB_MAX_PARAMS) + 16];
+        memset(buf, 0, sizeof buf);
+        size_t o = 0;
+        auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
+        // step t >= 0 reads s/q half (t & 1), written by launch t-1, and writes the other half;
+        // the prologue launch (t = -1) reads the initial state and writes the outflows of step 0
+        const int cur = t < 0 ? 0 : (int)(t & 1);
+        const void *ptrs[9] = {d->records, d->params, d->htypes, sbuf[cur], sbuf[cur ^ 1], qbuf[cur], qbuf[cur ^ 1], d->up_ptr, d->up_idx};
+        if (t < 0) { ptrs[4] = sbuf[1]; ptrs[5] = qbuf[1]; ptrs[6] = qbuf[0]; }
+        put(ptrs, sizeof ptrs);
+        put(&N, 8);
+        put(&t, 8);
+        put(&T, 8);
+        double minv = d->min_value;
+        put(&minv, 8);
+        int R = d->n_rows, sr = d->s_row, orow = d->o_row;
+        put(&R, 4);
+        put(&sr, 4);
+        put(&orow, 4);
+        std::vector<int> tmp(nv > np ? nv : np, 0);
+        for (int v = 0; v < s.n_inputs; ++v) tmp[v] = d->in_row[v];
+        put(tmp.data(), 4 * nv);
+        for (int j = 0; j < np; ++j) tmp[j] = j < s.n_params ? d->param_offset[j] : 0;
+        put(tmp.data(), 4 * np);
+        for (int j = 0; j < np; ++j) tmp[j] = j < s.n_params ? d->param_mode[j] : 0;
+        put(tmp.data(), 4 * np);
+        void *params[1] = {buf};
+        HB_DRV(g_drv.LaunchKernel(m->func, grid, 1, 1, m->block, 1, 1, 0, (CUstream)st, params, nullptr));
+    }
+    // launch t = T-1 wrote the state half ((T-1) & 1) ^ 1 == T & 1
+    if (d->final_states)
+        HB_CUDA(cudaMemcpyAsync(d->final_states, sbuf[(int)(T & 1)], (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
+    if (d->elapsed_ms) {
+        HB_CUDA(cudaEventRecord(m->ev1, st));
+        HB_CUDA(cudaEventSynchronize(m->ev1));
+        HB_CUDA(cudaEventElapsedTime(d->elapsed_ms, m->ev0, m->ev1));
+    }
     return HB_OK;
 }
 

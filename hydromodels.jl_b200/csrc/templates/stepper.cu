@@ -110,6 +110,13 @@ __device__ __forceinline__ void hb_fence_proxy_async() { asm volatile("fence.pro
 // ---- math helpers shared by all generated bodies: templates/hb_math.cuh -----------------------
 //@@HB:MATH
 
+// ---- MLP parameters: module-scope constant bank (filled by the host before each launch) so that
+//      every weight is a c[3][imm] operand of its DFMA; shared across all nodes (src/nn.jl:140-165)
+#if HB_NN_WORDS > 0
+__constant__ double hb_nn_const[HB_NN_WORDS];
+#define HB_NNW(i) hb_nn_const[i]
+#endif
+
 //@@HB:HELPERS
 
 // ---- the kernel -------------------------------------------------------------------------------
@@ -123,7 +130,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     const bool full_warp = (n0w + 32) <= a.N;
 
     // shared-memory carve-up: [MLP params][per-warp forcing ring][per-warp result tiles][mbarriers]
-    constexpr int kNNBytes = ((HB_NN_WORDS * 8 + 127) / 128) * 128;
+    constexpr int kNNBytes = 0;   // MLP parameters live in the constant bank (hb_nn_const)
     constexpr int kInStage = 32 * HB_V * 8;                       // bytes of one warp-step of forcing
     constexpr int kInBytes = ((HB_STAGES * kInStage + 127) / 128) * 128;
     constexpr int kOutTile = 32 * HB_R * 8;                       // bytes of one warp-step of results
@@ -135,10 +142,6 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     u64 *bars = reinterpret_cast<u64 *>(hb_smem + kNNBytes + (size_t)HB_WARPS * (kInBytes + kOutBytes)) + warp * HB_STAGES;
     (void)sNN; (void)sIn; (void)sOut; (void)bars;
 
-#if HB_NN_WORDS > 0
-    for (int i = threadIdx.x; i < HB_NN_WORDS; i += HB_BLOCK) sNN[i] = a.nn[i];
-    __syncthreads();
-#endif
 
     // warp-uniform choice of the I/O path
     const bool tma_in = (HB_SHARED_FORCING == 0) && (HB_V > 0) && a.tma_in_ok && full_warp;

@@ -16,9 +16,9 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .components import (Component, ConstantInterpolation, HydroBucket, HydroConfig, HydroFlux, HydroModel,
-                         HydroRoute, LinearInterpolation, SolverType, UnitHydrograph, normalize_config)
-from .lowering import LoweringError, StepperProgram, lower_stepper
+from .components import (Component, ConstantInterpolation, D8_CODES, GridAggregation, HydroBucket, HydroConfig, HydroFlux,
+                         HydroModel, HydroRoute, LinearInterpolation, SolverType, UnitHydrograph, normalize_config)
+from .lowering import LoweringError, RouteProgram, StepperProgram, lower_route, lower_stepper
 from .symbolic import evaluate_np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -61,6 +61,19 @@ class KernelInfo(C.Structure):
                 ("from_cache", C.c_int32), ("cubin_bytes", C.c_int32)]
 
 
+class RouteSpec(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_inputs", C.c_int32), ("n_params", C.c_int32), ("block_threads", C.c_int32)]
+
+
+class RouteDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_htype_sets", C.c_int32), ("n_nodes", C.c_int64), ("n_steps", C.c_int64),
+                ("records", C.c_void_p), ("n_rows", C.c_int32), ("s_row", C.c_int32), ("o_row", C.c_int32),
+                ("in_row", C.c_void_p), ("params", C.c_void_p), ("n_param_values", C.c_int64),
+                ("param_offset", C.c_void_p), ("param_mode", C.c_void_p), ("htypes", C.c_void_p),
+                ("initstates", C.c_void_p), ("up_ptr", C.c_void_p), ("up_idx", C.c_void_p), ("min_value", C.c_double),
+                ("final_states", C.c_void_p), ("elapsed_ms", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -82,12 +95,14 @@ def lib():
         "hb_model_cubin": [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)],
         "hb_model_info": [C.c_void_p, C.POINTER(KernelInfo)], "hb_free_model": [C.c_void_p],
         "hb_run": [C.c_void_p, C.POINTER(RunDesc)], "hb_run_device": [C.c_void_p, C.POINTER(RunDesc), C.c_void_p],
+        "hb_compile_route": [C.POINTER(RouteSpec), C.c_char_p, C.POINTER(C.c_void_p)],
+        "hb_run_route_device": [C.c_void_p, C.POINTER(RouteDesc), C.c_void_p],
         "hb_malloc_device": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_device": [C.c_void_p],
         "hb_malloc_host": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_host": [C.c_void_p],
         "hb_memcpy_h2d": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
         "hb_memcpy_d2h": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
         "hb_memset_device": [C.c_void_p, C.c_int, C.c_int64, C.c_void_p], "hb_stream_synchronize": [C.c_void_p],
-        "hb_probe_fp64_tflops": [C.POINTER(C.c_double)],
+        "hb_probe_fp64_tflops": [C.POINTER(C.c_double)], "hb_probe_dmma_tflops": [C.POINTER(C.c_double)],
         "hb_fill_device": [C.c_void_p, C.c_int64, C.c_double, C.c_void_p],
     }.items():
         fn = getattr(L, name)
@@ -178,6 +193,53 @@ class CompiledStepper:
             pass
 
 
+class CompiledRoute:
+    def __init__(self, program: RouteProgram, block_threads: int = 0):
+        self.program = program
+        spec = RouteSpec(C.sizeof(RouteSpec), len(program.input_names), len(program.param_slots), block_threads)
+        self.spec = spec
+        h = C.c_void_p()
+        check(lib().hb_compile_route(C.byref(spec), program.body.encode(), C.byref(h)))
+        self.handle = h
+
+    def source(self) -> str:
+        s = C.c_char_p()
+        n = C.c_int64()
+        check(lib().hb_model_source(self.handle, C.byref(s), C.byref(n)))
+        return s.value.decode()
+
+    def __del__(self):
+        try:
+            if self.handle and _lib is not None:
+                _lib.hb_free_model(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def upstream_csr(aggr, n_nodes: int):
+    """CSR list of upstream nodes (0-based) — the gather form of `build_aggr_func`
+    (`/root/reference/src/route.jl:336-365`).  Grid: upstream nodes ordered by their D8 code, the order
+    in which the reference adds its eight shifted arrays."""
+    if isinstance(aggr, GridAggregation):
+        down = aggr.downstream()
+        pos0 = aggr.positions - 1
+        codes = aggr.flwdir[pos0[:, 0], pos0[:, 1]]
+        rank = np.array([D8_CODES.index(int(c)) if int(c) in D8_CODES else 99 for c in codes])
+        src = np.nonzero(down >= 0)[0]
+        order = np.lexsort((rank[src], down[src]))
+        src, dst = src[order], down[src][order]
+    else:
+        if aggr.n_nodes != n_nodes:
+            raise ValueError("graph aggregation node count does not match the input")
+        e = np.asarray(aggr.edges, dtype=np.int64).reshape(-1, 2) - 1
+        order = np.argsort(e[:, 1], kind="stable") if len(e) else np.zeros(0, dtype=np.int64)
+        src, dst = e[order, 0], e[order, 1]
+    ptr = np.zeros(n_nodes + 1, dtype=np.int64)
+    np.add.at(ptr, dst + 1, 1)
+    return np.cumsum(ptr).astype(np.int32), np.ascontiguousarray(src.astype(np.int32) if len(src) else np.zeros(1, dtype=np.int32))
+
+
 # ---------------------------------------------------------------------------------------------------
 # argument preparation (host side of the functor)
 # ---------------------------------------------------------------------------------------------------
@@ -257,8 +319,20 @@ class B200Model:
             comps = component.components
         else:
             comps = (component,)
-        if any(isinstance(c, HydroRoute) for c in comps):
-            raise NotImplementedError("HydroRoute models are not lowered yet")
+        self.route: Optional[HydroRoute] = None
+        self.lumped: Optional[HydroModel] = None
+        n_routes = sum(isinstance(c, HydroRoute) for c in comps)
+        if n_routes:
+            if n_routes > 1 or not isinstance(comps[-1], HydroRoute):
+                raise NotImplementedError("one HydroRoute, as the last component, is supported")
+            self.route = comps[-1]
+            if len(comps) > 1:
+                lumped = HydroModel(components=comps[:-1], name="##lumped_part")
+                if set(lumped.input_names) != set(component.input_names):
+                    raise NotImplementedError("HydroRoute inputs must be produced by the preceding components")
+                # keep the model's own input row order
+                self.lumped = HydroModel(components=comps[:-1], name="##lumped_part", input_names=component.input_names)
+            self._route_kernel: Optional[CompiledRoute] = None
         self.multinode = component.htypes is not None if not isinstance(component, HydroModel) else \
             all(c.htypes is not None for c in comps)
 
@@ -274,13 +348,22 @@ class B200Model:
                  uh_kmax: Sequence[int] = ()) -> CompiledStepper:
         key = (tuple(rows) if rows is not None else None, objective, metric, shared_forcing, tuple(uh_kmax))
         if key not in self._cache:
-            prog = lower_stepper(self.component, rows=rows, objective=objective,
-                                 uh_kmax=list(uh_kmax) if len(uh_kmax) else None, fast=self.fast)
+            prog = lower_stepper(self._stepper_component(), rows=rows, objective=objective,
+                                 uh_kmax=list(uh_kmax) if len(uh_kmax) else None, fast=self.fast,
+                                 holes=self._route_rows())
+            # MLP-fused bodies keep 16+16 activations per net in registers: give them 168 (3 blocks/SM)
+            maxreg = self.max_registers or (168 if prog.nn_words else 0)
             self._cache[key] = CompiledStepper(prog, metric=metric, shared_forcing=shared_forcing,
                                                block_threads=self.block_threads, stages=self.stages,
-                                               max_registers=self.max_registers)
+                                               max_registers=maxreg)
         self.last_kernel = self._cache[key]
         return self._cache[key]
+
+    def _stepper_component(self) -> Component:
+        return self.lumped if self.route is not None else self.component
+
+    def _route_rows(self) -> List[str]:
+        return [] if self.route is None else self.route.state_names + self.route.output_names
 
     # -- host argument marshalling ------------------------------------------------------------------
     def _dims(self, input: np.ndarray, shared_forcing: bool, n_members: Optional[int]) -> Tuple[int, int]:
@@ -420,13 +503,21 @@ class B200Model:
         input = np.asarray(input)
         if input.dtype != np.float64:
             input = input.astype(np.float64)
+        if self.route is not None:
+            if rows is not None or out is not None:
+                raise NotImplementedError("rows= / out= are not supported for models with a HydroRoute")
+            if input.ndim != 3:
+                raise ValueError("HydroRoute only accepts 3D input (variables x nodes x time).\n"
+                                 "Routing is inherently spatial and requires multiple nodes.\n"
+                                 f"Got input shape: {input.shape}")
+            return self._call_routed(input, params, cfg, initstates, return_final_states, timing)
         N, T = self._dims(input, False, None)
         _check_config(cfg, T)
         inp = input if input.flags.f_contiguous else np.asfortranarray(input)   # memory = [T][N][V]
         # first pass over the parameters to size the unit hydrographs (compile-time K_max)
         prog0 = self.compiled(rows=rows).program if not self._has_uh() else None
         if prog0 is None:
-            probe = lower_stepper(self.component, rows=rows, fast=self.fast)
+            probe = lower_stepper(self._stepper_component(), rows=rows, fast=self.fast)
             _, _, _, _, _, kmax, _ = self.prepare(probe, params, N)
             ck = self.compiled(rows=rows, uh_kmax=kmax)
         else:
@@ -467,8 +558,116 @@ class B200Model:
             return out, final
         return out
 
+    # -- models ending in a HydroRoute: per-node stepper, then one routing launch per time step ---------
+    def _call_routed(self, input, params, cfg, initstates, return_final_states, timing):
+        params = _as_componentvector(params)
+        comp, route = self.component, self.route
+        all_rows = comp.state_names + comp.output_names if not isinstance(comp, HydroModel) else comp.var_names
+        V, N, T = input.shape
+        if V != len(comp.input_names):
+            raise AssertionError("Input variables length mismatch")
+        if len(route.htypes) != N:
+            raise ValueError(f"htypes has {len(route.htypes)} entries but the input has {N} nodes")
+        _check_config(cfg, T)
+        R = len(all_rows)
+        # route inputs that are model inputs (stand-alone HydroRoute) ride along as extra record rows
+        extra = [nm for nm in route.input_names if nm not in all_rows]
+        rec_rows = all_rows + extra
+        Rr = len(rec_rows)
+        s_name, o_name = route.state_names[0], route.output_names[0]
+        state_names = comp.state_names
+        init_all = None
+        if initstates is not None:
+            if isinstance(initstates, dict):
+                init_all = {k: np.broadcast_to(np.asarray(v, dtype=np.float64), (N,)) for k, v in initstates.items()}
+            else:
+                v = np.asarray(initstates, dtype=np.float64).reshape(-1)
+                if v.size != len(state_names) * N:
+                    raise ValueError(f"initstates has {v.size} elements, expected {len(state_names)}*{N}")
+                init_all = {s: v[i * N:(i + 1) * N] for i, s in enumerate(state_names)}
+        rec = DeviceBuffer(T * N * Rr * 8)
+        kernel_ms = 0.0
+        if self.lumped is not None:
+            inp = input if input.flags.f_contiguous else np.asfortranarray(input)
+            if self._has_uh():
+                probe = lower_stepper(self.lumped, rows=rec_rows, fast=self.fast, holes=self._route_rows())
+                kmax = self.prepare(probe, params, N)[5]
+            else:
+                kmax = []
+            ck = self.compiled(rows=rec_rows, uh_kmax=kmax)
+            run = DeviceRun(self, N, T, params, config=cfg,
+                            initstates=None if init_all is None else {k: v for k, v in init_all.items() if k != s_name},
+                            rows=rec_rows, _kmax=kmax)
+            din = DeviceBuffer.from_host(inp.ravel(order="K"))
+            kernel_ms += run.launch(din.ptr, rec.ptr, None, timed=True)
+            din.free()
+        else:
+            host = np.zeros((T, N, Rr))
+            for nm in extra:
+                host[:, :, rec_rows.index(nm)] = input[comp.input_names.index(nm)].T
+            check(lib().hb_memcpy_h2d(rec.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes, None))
+            check(lib().hb_stream_synchronize(None))
+        # ---- route ----
+        if self._route_kernel is None:
+            self._route_kernel = CompiledRoute(lower_route(route, fast=self.fast))
+        rk = self._route_kernel
+        pdict = params["params"]
+        chunks, offs, pos = [], [], 0
+        h0 = np.asarray(route.htypes, dtype=np.int64) - 1
+        modes = []
+        for nm, _ in rk.program.param_slots:
+            if nm not in pdict:
+                raise KeyError(f"Parameter {nm} does not exist in params")
+            v = np.atleast_1d(np.asarray(pdict[nm], dtype=np.float64)).reshape(-1)
+            if h0.size and (h0.min() < 0 or h0.max() >= v.size):
+                raise IndexError(f"BoundsError: attempt to access {v.size}-element parameter {nm} at index htypes")
+            modes.append(1 if (v.size == N and np.array_equal(h0, np.arange(N))) else 2)
+            offs.append(pos)
+            chunks.append(v)
+            pos += v.size
+        flat = np.ascontiguousarray(np.concatenate(chunks)) if chunks else np.zeros(1)
+        p_off = np.array(offs or [0], dtype=np.int32)
+        p_mode = np.array(modes or [0], dtype=np.int32)
+        up_ptr, up_idx = upstream_csr(route.aggr, N)
+        bufs = [DeviceBuffer.from_host(flat), DeviceBuffer.from_host(h0.astype(np.int32)),
+                DeviceBuffer.from_host(up_ptr), DeviceBuffer.from_host(up_idx)]
+        dinit = None
+        if init_all is not None and s_name in init_all:
+            dinit = DeviceBuffer.from_host(np.ascontiguousarray(init_all[s_name]))
+        in_row = np.array([rec_rows.index(nm) for nm in route.input_names] or [0], dtype=np.int32)
+        el = C.c_float(0.0)
+        d = RouteDesc()
+        d.struct_size = C.sizeof(RouteDesc)
+        d.n_htype_sets = 1
+        d.n_nodes, d.n_steps = N, T
+        d.records, d.n_rows = rec.ptr, Rr
+        d.s_row, d.o_row = rec_rows.index(s_name), rec_rows.index(o_name)
+        d.in_row = _ptr(in_row)
+        d.params, d.n_param_values = bufs[0].ptr, flat.size
+        d.param_offset, d.param_mode = _ptr(p_off), _ptr(p_mode)
+        d.htypes = bufs[1].ptr
+        d.initstates = dinit.ptr if dinit is not None else None
+        d.up_ptr, d.up_idx = bufs[2].ptr, bufs[3].ptr
+        d.min_value = cfg.min_value
+        d.elapsed_ms = C.cast(C.byref(el), C.c_void_p)
+        check(lib().hb_run_route_device(rk.handle, C.byref(d), None))
+        kernel_ms += el.value
+        full = rec.to_host((Rr, N, T), order="F")
+        rec.free()
+        for b in bufs:
+            b.free()
+        if timing is not None:
+            timing["kernel_ms"] = kernel_ms
+        out = full if not extra else np.asfortranarray(full[:R])
+        if return_final_states:
+            return out, np.ascontiguousarray(out[:len(state_names), :, -1])
+        return out
+
     def _has_uh(self) -> bool:
-        comps = self.component.components if isinstance(self.component, HydroModel) else (self.component,)
+        c0 = self._stepper_component()
+        if c0 is None:
+            return False
+        comps = c0.components if isinstance(c0, HydroModel) else (c0,)
         return any(isinstance(c, UnitHydrograph) for c in comps)
 
     # -- calibration ensembles: fused objective --------------------------------------------------------
@@ -588,14 +787,17 @@ class DeviceRun:
 
     def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None,
                  rows: Optional[Sequence[str]] = None, objective: Optional[str] = None, target=None,
-                 warm_up: int = 1, ensemble: bool = False):
+                 warm_up: int = 1, ensemble: bool = False, _kmax=None):
         self.eng, self.N, self.T = eng, int(N), int(T)
         self.cfg = normalize_config(config)
         _check_config(self.cfg, T)
         obj = objective is not None
         metric = METRICS[objective.lower()] if obj else 0
-        if eng._has_uh():
-            probe = lower_stepper(eng.component, rows=rows, objective=obj, fast=eng.fast)
+        if _kmax is not None:
+            kmax = _kmax
+        elif eng._has_uh():
+            probe = lower_stepper(eng._stepper_component(), rows=rows, objective=obj, fast=eng.fast,
+                                  holes=eng._route_rows())
             kmax = eng.prepare(probe, params, N, ensemble=ensemble)[5]
         else:
             kmax = []

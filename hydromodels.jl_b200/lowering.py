@@ -238,7 +238,8 @@ def _flatten(component: Component) -> Tuple[List[Component], List[str], List[str
 
 
 def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None, objective: bool = False,
-                  uh_kmax: Optional[Sequence[int]] = None, fast: bool = True) -> StepperProgram:
+                  uh_kmax: Optional[Sequence[int]] = None, fast: bool = True,
+                  holes: Sequence[str] = ()) -> StepperProgram:
     """Lower a per-node model (buckets, fluxes, neural fluxes, unit hydrographs) to one stepper
     body.  `rows`: subset/order of result rows to write (default: all = the reference result);
     `objective`: emit the last output row as `hb_sim` for the fused metric reduction instead of
@@ -379,10 +380,12 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
         row_names = [all_rows[-1]]           # `[end, :]` of the result (`…OptimizationExt.jl:163,173`)
     else:
         row_names = list(all_rows) if rows is None else list(rows)
+    zero = b.const(0.0)
     for r in row_names:
-        if r not in env:
+        if r not in env and r not in holes:
             raise LoweringError(f"row {r} is not produced by the model")
-    out_vals = [env[r] for r in row_names]
+    # `holes`: rows another kernel fills in later (the route's state / outflow rows) — written as 0.0
+    out_vals = [env[r] if r in env else zero for r in row_names]
 
     # ---- carry detection (class S) --------------------------------------------------------------------
     by_erased: Dict[object, Dict[int, int]] = {}
@@ -558,28 +561,102 @@ _ACT_C_EXACT = dict(_ACT_C, tanh="tanh({})", sigmoid="(1.0 / (1.0 + exp(-({}))))
 
 
 def _mlp_helper(idx: int, chain, offset: int, fast: bool) -> str:
-    """Register-resident matvec chain: weights broadcast from shared memory (every lane reads the
-    same word → conflict-free), activations in registers.  Layout per layer: weight[out,in]
-    column-major then bias[out] (`/root/reference/src/nn.jl:52-58`)."""
+    """Register-resident matvec chain as straight-line code (every weight index is a compile-time
+    constant, so `HB_NNW(i)` becomes a constant-bank operand of the DFMA — no load instruction, no
+    register).  Layout per layer: weight[out,in] column-major then bias[out]
+    (`/root/reference/src/nn.jl:52-58`)."""
     acts = _ACT_C if fast else _ACT_C_EXACT
     args = ", ".join(f"const double x{i}" for i in range(chain.n_in))
-    lines = [f"__device__ __forceinline__ void hb_mlp_{idx}(const double* __restrict__ sNN, {args}, double* __restrict__ y) {{",
-             f"    const double* w = sNN + {offset};",
-             f"    double a0[{chain.n_in}] = {{{', '.join(f'x{i}' for i in range(chain.n_in))}}};"]
-    off = 0
+    lines = [f"__device__ __forceinline__ void hb_mlp_{idx}(const double* __restrict__ sNN, {args}, double* __restrict__ y) {{"]
+    prev = [f"x{i}" for i in range(chain.n_in)]
+    off = offset
     for li, l in enumerate(chain.layers):
-        src, dst = f"a{li}", f"a{li + 1}"
-        lines.append(f"    double {dst}[{l.n_out}];")
-        lines.append("#pragma unroll")
-        lines.append(f"    for (int o = 0; o < {l.n_out}; ++o) {{")
-        lines.append(f"        double z = w[{off + l.n_out * l.n_in} + o];")
-        lines.append("#pragma unroll")
-        lines.append(f"        for (int i = 0; i < {l.n_in}; ++i) z = fma(w[{off} + i * {l.n_out} + o], {src}[i], z);")
-        lines.append(f"        {dst}[o] = {acts[l.activation].format('z')};")
-        lines.append("    }")
+        cur = []
+        bias = off + l.n_out * l.n_in
+        for o in range(l.n_out):
+            nm = f"a{li + 1}_{o}"
+            lines.append(f"    double {nm} = HB_NNW({bias + o});")
+            cur.append(nm)
+        # input-major order: 16 independent accumulator chains advance together (ILP)
+        for i in range(l.n_in):
+            for o in range(l.n_out):
+                lines.append(f"    {cur[o]} = fma(HB_NNW({off + i * l.n_out + o}), {prev[i]}, {cur[o]});")
+        for o in range(l.n_out):
+            if l.activation != "identity":
+                lines.append(f"    {cur[o]} = {acts[l.activation].format(cur[o])};")
         off += l.n_params
-    last = f"a{len(chain.layers)}"
-    lines.append("#pragma unroll")
-    lines.append(f"    for (int o = 0; o < {chain.n_out}; ++o) y[o] = {last}[o];")
+        prev = cur
+    for o in range(chain.n_out):
+        lines.append(f"    y[{o}] = {prev[o]};")
     lines.append("}")
     return "\n".join(lines)
+
+
+# ---------------------------------------------------------------------------------------------
+# HydroRoute → body of templates/route.cu
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class RouteProgram:
+    body: str
+    input_names: List[str]
+    state_name: str
+    output_name: str
+    param_slots: List[Tuple[str, Optional[int]]]
+    htype_sets: List[np.ndarray]
+
+
+def _emit_scalar_function(b: "_Builder", root: int, name: str, signature: str, refs: Dict[int, str], fast: bool) -> str:
+    """Straight-line device function computing value `root`; `refs` names the leaves."""
+    lines = [f"__device__ __forceinline__ double {name}({signature}) {{"]
+    names: Dict[int, str] = dict(refs)
+
+    def ref(i: int) -> str:
+        v = b.vals[i]
+        if i in names:
+            return names[i]
+        if v.op == "const":
+            return _c_double(v.payload)
+        if v.op == "in":
+            return f"hb_x[{v.payload}]"
+        if v.op == "param":
+            return f"hb_p[{v.payload}]"
+        args = [ref(a) for a in v.args]
+        names[i] = f"r{i}"
+        lines.append(f"    const double r{i} = {_expr_with(v, args, fast)};")
+        return names[i]
+
+    out = ref(root)
+    lines.append(f"    return {out};")
+    lines.append("}")
+    return "\n".join(lines)
+
+
+def lower_route(route: HydroRoute, *, fast: bool = True) -> RouteProgram:
+    """Lower a `HydroRoute`'s outflow flux and state increment
+    (`/root/reference/src/route.jl:387-403`) to the two device functions `route.cu` calls."""
+    b = _Builder(fast)
+    htype_sets = [np.asarray(route.htypes)]
+    param_slots: List[Tuple[str, Optional[int]]] = [(nm, 0) for nm in route.param_names]
+    ptab = {nm: b.leaf_param(i) for i, nm in enumerate(route.param_names)}
+    env = {nm: b.leaf_in(i) for i, nm in enumerate(route.input_names)}
+    s_leaf = b.opaque("routestate", 0, M_S, cost=0)
+    q_leaf = b.opaque("routeout", 0, M_S, cost=0)
+    sname, oname = route.state_names[0], route.output_names[0]
+    env_flux = dict(env)
+    env_flux[sname] = s_leaf
+    q_val = None
+    for f in route.rfluxes:
+        for eq in f.eqs:
+            q_val = b.lower_expr(eq.rhs, env_flux, ptab)
+            env_flux[eq.lhs.name] = q_val
+    env_ds = dict(env)
+    env_ds[sname] = s_leaf
+    env_ds[oname] = q_leaf
+    ds_val = b.lower_expr(route.dfluxes[0].expr, env_ds, ptab)
+    f1 = _emit_scalar_function(b, q_val, "hb_rflux", "const double* hb_x, const double hb_s, const double* hb_p",
+                               {s_leaf: "hb_s"}, fast)
+    f2 = _emit_scalar_function(b, ds_val, "hb_rds", "const double* hb_x, const double hb_s, const double hb_q, const double* hb_p",
+                               {s_leaf: "hb_s", q_leaf: "hb_q"}, fast)
+    body = "//@@HB:HELPERS\n" + f1 + "\n" + f2 + "\n"
+    return RouteProgram(body=body, input_names=list(route.input_names), state_name=sname, output_name=oname,
+                        param_slots=param_slots, htype_sets=htype_sets)

@@ -86,7 +86,7 @@ typedef struct {
     int32_t shared_forcing;      /* 1: input is [T][1][V], shared by all nodes (ensembles)    */
     int32_t block_threads;       /* 0 = default (128)                                         */
     int32_t stages;              /* forcing pipeline depth in time steps, 0 = default (4)     */
-    int32_t max_registers;       /* 0 = default; NVRTC --maxrregcount                         */
+    int32_t max_registers;       /* 0 = default (128); register budget per thread -> __launch_bounds__ min blocks */
 } hb_stepper_spec;
 
 /* One forward run.  Pointers are HOST pointers for hb_run and DEVICE pointers for
@@ -152,6 +152,45 @@ int hb_run(hb_model_t m, const hb_run_desc *desc);
 /* Device buffers, asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
 int hb_run_device(hb_model_t m, const hb_run_desc *desc, void *stream);
 
+/* ---- grid / graph routing (HydroRoute, /root/reference/src/route.jl:336-404) ------------------- */
+/* One route component with one state and one outflow, stepping in place on the model's records:
+ * rows `in_row[]` of rec[T][N][R] are its inputs (written earlier by the per-node stepper), rows
+ * `s_row` / `o_row` receive its state and outflow.  Topology = CSR list of UPSTREAM nodes
+ * (0-based): the D8 push of build_aggr_func(flwdir, positions) or adjacency' * q, as a gather. */
+typedef struct {
+    int32_t struct_size;        /* sizeof(hb_route_spec) */
+    int32_t n_inputs;           /* route inputs read from the records */
+    int32_t n_params;
+    int32_t block_threads;      /* 0 = default (256) */
+} hb_route_spec;
+
+typedef struct {
+    int32_t struct_size;        /* sizeof(hb_route_desc) */
+    int32_t n_htype_sets;
+    int64_t n_nodes;            /* N */
+    int64_t n_steps;            /* T */
+    double *records;            /* DEVICE [T][N][R] */
+    int32_t n_rows;             /* R */
+    int32_t s_row, o_row;       /* record rows of the route state / outflow */
+    const int32_t *in_row;      /* HOST [n_inputs] record rows of the route inputs */
+    const double *params;       /* DEVICE flat parameter values */
+    int64_t n_param_values;
+    const int32_t *param_offset;/* HOST [n_params] */
+    const int32_t *param_mode;  /* HOST [n_params] */
+    const int32_t *htypes;      /* DEVICE [n_htype_sets][N] 0-based or NULL */
+    const double *initstates;   /* DEVICE [N] or NULL (= zeros) */
+    const int32_t *up_ptr;      /* DEVICE [N+1] */
+    const int32_t *up_idx;      /* DEVICE [up_ptr[N]] */
+    double min_value;
+    double *final_states;       /* DEVICE [N] or NULL */
+    float *elapsed_ms;          /* optional HOST pointer */
+} hb_route_desc;
+
+int hb_compile_route(const hb_route_spec *spec, const char *body, hb_model_t *out);
+/* T+1 launches of hb_route_step on `stream` (device pointers; returns after enqueueing unless
+ * elapsed_ms is requested). */
+int hb_run_route_device(hb_model_t m, const hb_route_desc *desc, void *stream);
+
 /* ---- memory helpers (so a host without a CUDA binding can own device / pinned buffers) ---- */
 int hb_malloc_device(void **ptr, int64_t bytes);
 int hb_free_device(void *ptr);
@@ -165,6 +204,7 @@ int hb_stream_synchronize(void *stream);
 
 /* ---- measurement probes (bench.py) --------------------------------------------------------- */
 int hb_probe_fp64_tflops(double *tflops);                       /* measured FP64 FMA peak (2 flop/FMA) */
+int hb_probe_dmma_tflops(double *tflops);                       /* measured FP64 tensor (DMMA m8n8k4) peak */
 int hb_fill_device(double *p, int64_t n, double v, void *stream); /* L2 flush / buffer fill           */
 
 #ifdef __cplusplus

@@ -206,3 +206,73 @@ def test_boundary_errors():
         model(inp, p, hm.HydroConfig(timeidx=[2, 3, 4]))
     with pytest.raises(TypeError):
         model(inp, np.zeros(6))
+
+
+# ---- HydroRoute (Jacobi D8 / graph routing), SURVEY.md §8 a10 ------------------------------------------
+def _route_only(flwdir, positions, with_q_term=False):
+    s = hm.Symbols("q q_routed s_river", "lag")
+    f = "q_routed ~ s_river / (1 + lag) + q" if with_q_term else "q_routed ~ s_river / (1 + lag)"
+    return hm.HydroRoute(rfluxes=[hm.HydroFlux(f, symbols=s)], dfluxes=[hm.StateFlux("s_river ~ q - q_routed", symbols=s)],
+                         aggr_func=hm.build_aggr_func(flwdir, positions), htypes=np.arange(1, len(positions) + 1))
+
+
+def test_standalone_route_worked_example():
+    """`test/base/run_hydro_route.jl:5-45` / SURVEY.md Appendix E.2."""
+    flwdir = np.array([[1, 4, 8], [1, 4, 4], [1, 1, 2]])
+    positions = [(i, j) for i in (1, 2, 3) for j in (1, 2, 3)]
+    route = _route_only(flwdir, positions)
+    x = np.ones((1, 9, 20))
+    p = {"params": dict(lag=np.full(9, 0.2))}
+    out = route(x, p)
+    assert out.shape == (2, 9, 20) and np.all(out >= 0)
+    assert np.allclose(out[0, :, 2], [1.194444, 2.305556, 1.194444, 1.194444, 5.222222, 1.194444, 1.194444, 5.5, 4.805556], atol=1e-6)
+    assert_parity(out, ho.run_route(route, x, p))
+    assert out[1, 8].mean() > out[1, 0].mean()
+    with pytest.raises(ValueError, match="HydroRoute only accepts 3D input"):
+        route(np.ones((1, 20)), p)
+
+
+@pytest.mark.parametrize("R,Cc,T", [(3, 3, 100), (37, 53, 60)])
+def test_grid_model_matches_oracle(R, Cc, T):
+    """`test/base/run_spatial_model.jl:10-141`: ExpHydro + q ~ flow*area_coef + D8 route; irregular
+    node list (some cells missing), sinks and off-grid directions included."""
+    rng = np.random.default_rng(R * 100 + Cc)
+    if R == 3:
+        flw = np.array([[1, 4, 8], [1, 4, 4], [1, 1, 2]])
+        pos = [(i, j) for i in (1, 2, 3) for j in (1, 2, 3)]
+    else:
+        flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128, 0, 3], size=(R, Cc))
+        pos = [(r + 1, c + 1) for r in range(R) for c in range(Cc) if rng.random() < 0.9]
+    N = len(pos)
+    model = hm.models.exphydro_grid(flw, pos)
+    assert model.var_names[2] == "s_river" and model.var_names[-2:] == ["q", "q_routed"]
+    inp = sy.forcing("exphydro", 0, N, T)
+    p = {"params": dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))}
+    init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 2, N))
+    got = model(inp, p, initstates=init)
+    assert got.shape == (13, N, T)
+    ref = ho.run_model(model, inp, p, initstates=init)
+    assert_parity(got, ref)
+    assert np.all(got[:3] >= 1e-6)
+    # flat (state-major) initstates give the same result
+    flat = np.concatenate([init["snowpack"], init["soilwater"], init["s_river"]])
+    assert np.array_equal(model(inp, p, initstates=flat), got)
+
+
+def test_graph_route_equals_grid_route():
+    """`build_aggr_func(graph)` = adjacency' * q (`src/route.jl:336-340`) with the D8 topology gives the
+    same series as the grid aggregation."""
+    flwdir = np.array([[1, 4, 8], [1, 4, 4], [1, 1, 2]])
+    positions = [(i, j) for i in (1, 2, 3) for j in (1, 2, 3)]
+    grid = _route_only(flwdir, positions, with_q_term=True)
+    down = grid.aggr.downstream()
+    edges = [(n + 1, d + 1) for n, d in enumerate(down) if d >= 0]
+    s = hm.Symbols("q q_routed s_river", "lag")
+    graph = hm.HydroRoute(rfluxes=[hm.HydroFlux("q_routed ~ s_river / (1 + lag) + q", symbols=s)],
+                          dfluxes=[hm.StateFlux("s_river ~ q - q_routed", symbols=s)],
+                          aggr_func=hm.build_aggr_func(9, edges), htypes=np.arange(1, 10))
+    x = np.asfortranarray(np.abs(np.random.default_rng(4).normal(size=(1, 9, 50))))
+    p = {"params": dict(lag=np.linspace(0.1, 1.0, 9))}
+    a, b = grid(x, p), graph(x, p)
+    assert np.allclose(a, b, rtol=1e-14, atol=0)
+    assert_parity(b, ho.run_route(graph, x, p))
