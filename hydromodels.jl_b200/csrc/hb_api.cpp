@@ -226,9 +226,10 @@ struct hb_model_s {
     CUdeviceptr nn_const = 0;   // module-scope __constant__ hb_nn_const[]
     // workspace for hb_run (host-pointer entry point)
     struct Buf { void *p = nullptr; size_t cap = 0; };
-    Buf ws[12];
-    cudaStream_t stream = nullptr;
+    Buf ws[16];
+    cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
 };
 
 namespace {
@@ -504,6 +505,9 @@ int hb_free_model(hb_model_t m) {
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->stream_h2d) cudaStreamDestroy(m->stream_h2d);
+    if (m->stream_d2h) cudaStreamDestroy(m->stream_d2h);
+    for (auto e : m->chunk_ev) cudaEventDestroy(e);
     if (m->module && g_drv.ModuleUnload) g_drv.ModuleUnload(m->module);
     delete m;
     return HB_OK;
@@ -533,26 +537,34 @@ int hb_run_device(hb_model_t m, const hb_run_desc *d, void *stream) {
 
 int hb_run(hb_model_t m, const hb_run_desc *d) {
     if (!m) return fail(HB_ERR_INVALID, "model is NULL");
+    if (m->kind != 0) return fail(HB_ERR_INVALID, "not a stepper model");
     int rc = check_desc(m, d);
     if (rc) return rc;
     rc = load_model(m);
     if (rc) return rc;
     HB_CUDA(cudaSetDevice(g_device));
-    if (!m->stream) HB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    if (!m->stream) {
+        HB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        HB_CUDA(cudaStreamCreateWithFlags(&m->stream_h2d, cudaStreamNonBlocking));
+        HB_CUDA(cudaStreamCreateWithFlags(&m->stream_d2h, cudaStreamNonBlocking));
+        HB_CUDA(cudaEventCreate(&m->ev0));
+        HB_CUDA(cudaEventCreate(&m->ev1));
+    }
     const hb_stepper_spec &s = m->spec;
     const int64_t N = d->n_nodes, T = d->n_steps;
     const int64_t Nin = s.shared_forcing ? 1 : N;
+    const bool rows_mode = s.output_mode == HB_OUT_ROWS;
     hb_run_desc dd = *d;
+    // ---- small, time-independent inputs: one H2D each on the compute stream ----
     struct In { int slot; const void *host; size_t bytes; const void **dev; };
     const In ins[] = {
-        {0, d->input, (size_t)T * Nin * s.n_inputs * 8, (const void **)&dd.input},
         {1, d->params, (size_t)d->n_param_values * 8, (const void **)&dd.params},
         {2, d->htypes, (size_t)d->n_htype_sets * N * 4, (const void **)&dd.htypes},
         {3, d->initstates, (size_t)s.n_states * N * 8, (const void **)&dd.initstates},
         {4, d->uh_weights, (size_t)m->uhw_total * N * 8, (const void **)&dd.uh_weights},
         {5, d->uh_hist_in, (size_t)m->uhh_total * N * 8, (const void **)&dd.uh_hist_in},
         {6, d->nn_params, (size_t)s.nn_words * 8, (const void **)&dd.nn_params},
-        {7, d->target, s.output_mode == HB_OUT_OBJECTIVE ? (size_t)T * (d->target_per_node ? N : 1) * 8 : 0, (const void **)&dd.target},
+        {7, d->target, !rows_mode ? (size_t)T * (d->target_per_node ? N : 1) * 8 : 0, (const void **)&dd.target},
     };
     for (const In &in : ins) {
         *in.dev = nullptr;
@@ -561,31 +573,92 @@ int hb_run(hb_model_t m, const hb_run_desc *d) {
         HB_CUDA(cudaMemcpyAsync(m->ws[in.slot].p, in.host, in.bytes, cudaMemcpyHostToDevice, m->stream));
         *in.dev = m->ws[in.slot].p;
     }
-    struct Out { int slot; void *host; size_t bytes; void **dev; };
-    const Out outs[] = {
-        {8, d->out, s.output_mode == HB_OUT_ROWS ? (size_t)T * N * s.n_rows * 8 : 0, (void **)&dd.out},
-        {9, d->objective, s.output_mode == HB_OUT_OBJECTIVE ? (size_t)N * 8 : 0, (void **)&dd.objective},
-        {10, d->final_states, (size_t)s.n_states * N * 8, (void **)&dd.final_states},
-        {11, d->uh_hist_out, (size_t)m->uhh_total * N * 8, (void **)&dd.uh_hist_out},
-    };
-    for (const Out &o : outs) {
-        *o.dev = nullptr;
-        if (!o.host || o.bytes == 0) continue;
-        if ((rc = ws_reserve(m->ws[o.slot], o.bytes))) return rc;
-        *o.dev = m->ws[o.slot].p;
+    const size_t in_step = (size_t)Nin * s.n_inputs * 8;          // forcing bytes per time step
+    const size_t out_step = rows_mode ? (size_t)N * s.n_rows * 8 : 0;
+    if ((rc = ws_reserve(m->ws[0], in_step * T))) return rc;
+    if (rows_mode && (rc = ws_reserve(m->ws[8], out_step * T))) return rc;
+    if (!rows_mode && (rc = ws_reserve(m->ws[9], (size_t)N * 8))) return rc;
+    const size_t st_bytes = (size_t)s.n_states * N * 8, uh_bytes = (size_t)m->uhh_total * N * 8;
+    // ---- time chunks: H2D(c+1) | kernel(c) | D2H(c-1) overlap on three streams; the bucket states
+    //      and UH history are carried between chunk launches in device ping-pong buffers (a chunked
+    //      run is bit-identical to a one-shot run: states are clamped values, carried subexpressions
+    //      are functions of the state).  Objective mode reduces over the whole series: one chunk.
+    int64_t nchunk = 1;
+    if (rows_mode && T > 1) {
+        size_t per_chunk = (size_t)256 << 20;                     // ~256 MiB of results per chunk
+        if (const char *e = getenv("HB_CHUNK_BYTES")) { long long v = atoll(e); if (v > 0) per_chunk = (size_t)v; }
+        nchunk = (int64_t)((out_step * T + per_chunk - 1) / per_chunk);
+        if (nchunk > T) nchunk = T;
+        if (nchunk > 256) nchunk = 256;
+        if (nchunk < 1) nchunk = 1;
+        if (getenv("HB_NO_PIPELINE")) nchunk = 1;
     }
-    dd.elapsed_ms = nullptr;
-    if (d->elapsed_ms) {
-        if (!m->ev0) { HB_CUDA(cudaEventCreate(&m->ev0)); HB_CUDA(cudaEventCreate(&m->ev1)); }
-        HB_CUDA(cudaEventRecord(m->ev0, m->stream));
+    if (nchunk > 1) {
+        if (st_bytes && ((rc = ws_reserve(m->ws[12], st_bytes)) || (rc = ws_reserve(m->ws[13], st_bytes)))) return rc;
+        if (uh_bytes && ((rc = ws_reserve(m->ws[14], uh_bytes)) || (rc = ws_reserve(m->ws[15], uh_bytes)))) return rc;
+    } else {
+        if (d->final_states && st_bytes && (rc = ws_reserve(m->ws[12], st_bytes))) return rc;
+        if (d->uh_hist_out && uh_bytes && (rc = ws_reserve(m->ws[14], uh_bytes))) return rc;
     }
-    if ((rc = launch_stepper(m, &dd, m->stream))) return rc;
-    if (d->elapsed_ms) HB_CUDA(cudaEventRecord(m->ev1, m->stream));
-    for (const Out &o : outs) {
-        if (!o.host || o.bytes == 0) continue;
-        HB_CUDA(cudaMemcpyAsync(o.host, m->ws[o.slot].p, o.bytes, cudaMemcpyDeviceToHost, m->stream));
+    while ((int64_t)m->chunk_ev.size() < 2 * nchunk) {
+        cudaEvent_t e;
+        HB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        m->chunk_ev.push_back(e);
     }
+    HB_CUDA(cudaEventRecord(m->ev0, m->stream));
+    // the copy streams must not start before the workspace of a previous call is idle
+    HB_CUDA(cudaStreamWaitEvent(m->stream_h2d, m->ev0, 0));
+    const void *state_in = dd.initstates, *uhh_in = dd.uh_hist_in;
+    int last_state_slot = -1, last_uh_slot = -1;
+    for (int64_t c = 0; c < nchunk; ++c) {
+        const int64_t t0 = T * c / nchunk, t1 = T * (c + 1) / nchunk;
+        if (t1 > t0 && in_step) {
+            HB_CUDA(cudaMemcpyAsync((char *)m->ws[0].p + in_step * t0, (const char *)d->input + in_step * t0, in_step * (t1 - t0),
+                                    cudaMemcpyHostToDevice, m->stream_h2d));
+        }
+        HB_CUDA(cudaEventRecord(m->chunk_ev[2 * c], m->stream_h2d));
+        HB_CUDA(cudaStreamWaitEvent(m->stream, m->chunk_ev[2 * c], 0));
+        hb_run_desc dc = dd;
+        dc.elapsed_ms = nullptr;
+        dc.n_steps = t1 - t0;
+        dc.input = (const double *)((const char *)m->ws[0].p + in_step * t0);
+        dc.out = rows_mode ? (double *)((char *)m->ws[8].p + out_step * t0) : nullptr;
+        dc.objective = rows_mode ? nullptr : (double *)m->ws[9].p;
+        dc.initstates = (const double *)state_in;
+        dc.uh_hist_in = (const double *)uhh_in;
+        const bool last = (c == nchunk - 1);
+        dc.final_states = nullptr;
+        dc.uh_hist_out = nullptr;
+        if (st_bytes && (!last || d->final_states)) {
+            last_state_slot = 12 + (int)(c & 1);
+            if (nchunk == 1) last_state_slot = 12;
+            dc.final_states = (double *)m->ws[last_state_slot].p;
+        }
+        if (uh_bytes && (!last || d->uh_hist_out)) {
+            last_uh_slot = 14 + (int)(c & 1);
+            if (nchunk == 1) last_uh_slot = 14;
+            dc.uh_hist_out = (double *)m->ws[last_uh_slot].p;
+        }
+        if ((rc = launch_stepper(m, &dc, m->stream))) return rc;
+        state_in = dc.final_states;
+        uhh_in = dc.uh_hist_out;
+        if (rows_mode && t1 > t0) {
+            HB_CUDA(cudaEventRecord(m->chunk_ev[2 * c + 1], m->stream));
+            HB_CUDA(cudaStreamWaitEvent(m->stream_d2h, m->chunk_ev[2 * c + 1], 0));
+            HB_CUDA(cudaMemcpyAsync((char *)d->out + out_step * t0, (char *)m->ws[8].p + out_step * t0, out_step * (t1 - t0),
+                                    cudaMemcpyDeviceToHost, m->stream_d2h));
+        }
+    }
+    HB_CUDA(cudaEventRecord(m->ev1, m->stream));
+    if (!rows_mode) HB_CUDA(cudaMemcpyAsync(d->objective, m->ws[9].p, (size_t)N * 8, cudaMemcpyDeviceToHost, m->stream));
+    if (d->final_states && st_bytes && last_state_slot >= 0)
+        HB_CUDA(cudaMemcpyAsync(d->final_states, m->ws[last_state_slot].p, st_bytes, cudaMemcpyDeviceToHost, m->stream));
+    if (d->uh_hist_out && uh_bytes && last_uh_slot >= 0)
+        HB_CUDA(cudaMemcpyAsync(d->uh_hist_out, m->ws[last_uh_slot].p, uh_bytes, cudaMemcpyDeviceToHost, m->stream));
     HB_CUDA(cudaStreamSynchronize(m->stream));
+    HB_CUDA(cudaStreamSynchronize(m->stream_d2h));
+    HB_CUDA(cudaStreamSynchronize(m->stream_h2d));
+    // device time of the compute stream from first to last kernel (includes waits for forcing chunks)
     if (d->elapsed_ms) HB_CUDA(cudaEventElapsedTime(d->elapsed_ms, m->ev0, m->ev1));
     return HB_OK;
 }

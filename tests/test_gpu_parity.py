@@ -110,6 +110,20 @@ def test_chunked_run_resumes_bit_identically():
     assert np.array_equal(np.concatenate([a, b], axis=2), full)
 
 
+@pytest.mark.parametrize("name", ["gr4j", "hbv"])
+def test_pipelined_host_run_is_bit_identical(monkeypatch, name):
+    """`hb_run` splits long runs into time chunks (H2D | kernel | D2H overlap) carrying states and UH
+    history on the device: results must not depend on the chunking."""
+    model, inp, p, init = case(name, 640, 97)
+    eng = hm.B200Model(model)
+    monkeypatch.setenv("HB_NO_PIPELINE", "1")
+    one, fin1 = eng(inp, p, initstates=init, return_final_states=True)
+    monkeypatch.delenv("HB_NO_PIPELINE")
+    monkeypatch.setenv("HB_CHUNK_BYTES", str(640 * len(model.var_names) * 8 * 5))     # 5 steps per chunk
+    many, fin2 = eng(inp, p, initstates=init, return_final_states=True)
+    assert np.array_equal(one, many) and np.array_equal(fin1, fin2)
+
+
 def test_standalone_flux_uh_bucket_components():
     s = hm.Symbols("a b c d", "p1 p2")
     flux = hm.HydroFlux(["c ~ a * p1 + b * p2", "d ~ a + p1 + b + p2"], symbols=s)
