@@ -35,6 +35,11 @@ WORKLOADS = {
     "hbv_100k_basins_x_730d": ("hbv", 100_000, 730),
     "m50_50k_basins_x_3650d": ("m50", 50_000, 3650),
     "exphydro_64k_basins_x_365d": ("exphydro", 65_536, 365),
+    # BASELINE config 3: calibration ensemble, shared forcing, fused objective (no rows written)
+    "hbv_ensemble_1M_members_x_7305d": ("hbv_ensemble", 1_000_000, 7305),
+    # BASELINE config 5 (single-GPU slice): distributed ExpHydro + D8 routing on a 2048 x 2048 grid
+    "exphydro_grid_2048x2048_x_60d": ("exphydro_grid", 2048 * 2048, 60),
+    "exphydro_grid_512x512_x_60d": ("exphydro_grid", 512 * 512, 60),
 }
 DEFAULT_WORKLOAD = "exphydro_1M_basins_x_365d"
 
@@ -166,8 +171,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     model_name, N, T = WORKLOADS[args.workload]
-    rows_of = {"exphydro": 10, "gr4j": 15, "hbv": 18, "m50": 12}[model_name]
-    v_of = {"exphydro": 3, "gr4j": 2, "hbv": 3, "m50": 3}[model_name]
+    rows_of = {"exphydro": 10, "gr4j": 15, "hbv": 18, "m50": 12, "hbv_ensemble": 0, "exphydro_grid": 13}[model_name]
+    v_of = {"exphydro": 3, "gr4j": 2, "hbv": 3, "m50": 3, "hbv_ensemble": 0, "exphydro_grid": 3}[model_name]
     unit = "basin-timesteps/s"
     config = {"workload": args.workload, "model": model_name, "basins_per_gpu": N, "timesteps": T,
               "rows_out": rows_of, "forcing_rows": v_of, "output": "full [rows,N,T] as the reference returns",
@@ -208,11 +213,55 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n0 = rank * N
-    model, p, init = build_problem(hm, sy, model_name, n0, N, T)
-    eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
-    run = DeviceRun(eng, N, T, p, initstates=init)
-    d_in = device_forcing(torch, model_name, N, T, sy.SEED + 17 * rank)
-    d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
+    special = model_name in ("hbv_ensemble", "exphydro_grid")
+    if model_name == "hbv_ensemble":
+        # one basin, N parameter sets: forcing [T][1][3] shared by all members, objective = -NSE
+        args.no_e2e = True
+        model = hm.models.hbv()
+        p = {"params": sy.parameters("hbv", n0, n0 + N)}
+        init = {k: np.full(N, v) for k, v in sy.INIT["hbv"].items()}
+        forcing1 = sy.forcing("hbv", 0, 1, T)
+        target = np.abs(forcing1[0, 0] * 0.3 + 0.5)
+        eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
+        run = DeviceRun(eng, N, T, p, initstates=init, objective="NSE", target=target, warm_up=366, ensemble=True)
+        d_in = torch.from_numpy(np.ascontiguousarray(forcing1[:, 0, :].T)).cuda()
+        d_out = torch.empty((N,), device="cuda", dtype=torch.float64)
+    elif model_name == "exphydro_grid":
+        # weak scaling: every rank owns a `side`-row strip of a (side*world) x side grid; the strips are
+        # coupled through the D8 flow directions, so boundary outflows are exchanged every step
+        from hydromodels_jl_b200.engine import RoutedDeviceRun
+        from hydromodels_jl_b200.parallel import ShardedRoutedRun
+        args.no_e2e = True
+        side = int(round(N ** 0.5))
+        Ng = N * world
+        rng = np.random.default_rng(sy.SEED)
+        flw = rng.choice(np.array([1, 2, 4, 8, 16, 32, 64, 128]), size=(side * world, side), p=[.3, .2, .3, .05, .03, .02, .05, .05])
+        rr, cc = np.divmod(np.arange(Ng), side)
+        pos = np.stack([rr + 1, cc + 1], axis=1)
+        model = hm.models.exphydro_grid(flw, pos)
+        pp = sy.parameters("exphydro", 0, Ng)
+        pp.update(area_coef=np.full(Ng, 1.0), lag=rng.uniform(0.1, 2.0, Ng))
+        p = {"params": pp}
+        init = dict(snowpack=np.zeros(Ng), soilwater=np.full(Ng, 1303.0), s_river=np.zeros(Ng))
+        eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
+        if world > 1:
+            sharded = ShardedRoutedRun(eng, Ng, T, p, initstates=init)
+            assert sharded.N == N
+
+            class _Run:                      # same launch signature as the single-GPU runs
+                def launch(self, ip, op, stream=None):
+                    sharded.launch(ip, op)
+            run = _Run()
+        else:
+            run = RoutedDeviceRun(eng, N, T, p, initstates=init)
+        d_in = device_forcing(torch, "exphydro", N, T, sy.SEED + 17 * rank)
+        d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
+    else:
+        model, p, init = build_problem(hm, sy, model_name, n0, N, T)
+        eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
+        run = DeviceRun(eng, N, T, p, initstates=init)
+        d_in = device_forcing(torch, model_name, N, T, sy.SEED + 17 * rank)
+        d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
     stream = torch.cuda.current_stream()
     info = eng.last_kernel.info()
 
@@ -251,9 +300,11 @@ def main():
     # roofline of the dominant (only) kernel: algorithmic bytes per launch / mean launch time
     peak, peak_src = peaks()
     bytes_per_unit = 8 * (v_of + rows_of)
+    launches_per_step = (T + 2) if model_name == "exphydro_grid" else 1
     k_ms = float(np.mean(kernel_ms))
     achieved = bytes_per_unit * N * T / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "hb_stepper", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kname = {"exphydro_grid": "hb_stepper + T x hb_route_step", "hbv_ensemble": "hb_stepper (objective mode)"}.get(model_name, "hb_stepper")
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_basin_timestep": bytes_per_unit, "kernel_ms": k_ms,
                 "registers": info["registers_per_thread"], "blocks_per_sm": info["max_blocks_per_sm"],
@@ -267,7 +318,7 @@ def main():
 
     # ---- end to end through the public functor, pinned host buffers --------------------------------
     e2e = None
-    launches = args.steps
+    launches = args.steps * launches_per_step
     if not args.no_e2e:
         try:
             h_in = torch.empty((T, N, v_of), dtype=torch.float64, pin_memory=True)
@@ -299,7 +350,7 @@ def main():
             e2e = {"value": None, "unit": unit, "error": f"{type(ex).__name__}: {ex}"[:300]}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not special:
         rate, dt, sample, cores, rate1 = cpu_reference_rate(model_name, T)
         cpu = {"value": rate, "unit": unit, "cores": cores, "kind": "port", "sample": sample, "seconds": dt,
                "one_thread_value": rate1,

@@ -466,7 +466,8 @@ def build_aggr_func(*args):
     a, b = args
     if np.ndim(a) == 2:
         flw = np.asarray(a).astype(np.int64)
-        pos = np.asarray([tuple(p) for p in b], dtype=np.int64).reshape(-1, 2)
+        pos = (np.asarray(b, dtype=np.int64) if isinstance(b, np.ndarray)
+               else np.asarray([tuple(p) for p in b], dtype=np.int64)).reshape(-1, 2)
         R, C = flw.shape
         if pos.size and (pos.min() < 1 or pos[:, 0].max() > R or pos[:, 1].max() > C):
             raise IndexError("positions outside flwdir")  # BoundsError in the reference

@@ -377,6 +377,52 @@ int launch_stepper(hb_model_s *m, const hb_run_desc *d, cudaStream_t stream) {
     return HB_OK;
 }
 
+int launch_route_step(hb_model_s *m, const hb_route_desc *d, int64_t t, const double *s_prev, double *s_next,
+                      const double *q_cur, double *q_next, cudaStream_t st) {
+    const hb_route_spec &s = m->rspec;
+    const int64_t N = d->n_nodes, T = d->n_steps;
+    const int nv = s.n_inputs > 0 ? s.n_inputs : 1, np = s.n_params > 0 ? s.n_params : 1;
+    // HbRouteArgs mirror (templates/route.cu): 9 pointers, 3 i64, 1 double, 3 int, int tables
+    unsigned char buf[9 * 8 + 3 * 8 + 8 + 3 * 4 + 4 * (16 + 2 * HB_MAX_PARAMS) + 16];
+    memset(buf, 0, sizeof buf);
+    size_t o = 0;
+    auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
+    const void *ptrs[9] = {d->records, d->params, d->htypes, s_prev, s_next, q_cur, q_next, d->up_ptr, d->up_idx};
+    put(ptrs, sizeof ptrs);
+    put(&N, 8);
+    put(&t, 8);
+    put(&T, 8);
+    double minv = d->min_value;
+    put(&minv, 8);
+    int R = d->n_rows, sr = d->s_row, orow = d->o_row;
+    put(&R, 4);
+    put(&sr, 4);
+    put(&orow, 4);
+    std::vector<int> tmp(nv > np ? nv : np, 0);
+    for (int v = 0; v < s.n_inputs; ++v) tmp[v] = d->in_row[v];
+    put(tmp.data(), 4 * nv);
+    for (int j = 0; j < np; ++j) tmp[j] = j < s.n_params ? d->param_offset[j] : 0;
+    put(tmp.data(), 4 * np);
+    for (int j = 0; j < np; ++j) tmp[j] = j < s.n_params ? d->param_mode[j] : 0;
+    put(tmp.data(), 4 * np);
+    void *params[1] = {buf};
+    unsigned grid = (unsigned)((N + m->block - 1) / m->block);
+    HB_DRV(g_drv.LaunchKernel(m->func, grid, 1, 1, m->block, 1, 1, 0, (CUstream)st, params, nullptr));
+    return HB_OK;
+}
+
+int check_route_desc(const hb_model_s *m, const hb_route_desc *d) {
+    if (!m || m->kind != 1) return fail(HB_ERR_INVALID, "not a route model");
+    if (!d || d->struct_size != (int32_t)sizeof(hb_route_desc)) return fail(HB_ERR_INVALID, "hb_route_desc.struct_size mismatch");
+    const hb_route_spec &s = m->rspec;
+    if (d->n_nodes <= 0 || d->n_steps < 0 || !d->records || !d->up_ptr || !d->up_idx) return fail(HB_ERR_INVALID, "bad route descriptor");
+    if (!(d->min_value > 0)) return fail(HB_ERR_INVALID, "min_value must be positive, got %g", d->min_value);
+    if (d->s_row < 0 || d->s_row >= d->n_rows || d->o_row < 0 || d->o_row >= d->n_rows) return fail(HB_ERR_INVALID, "route rows outside the record");
+    for (int v = 0; v < s.n_inputs; ++v)
+        if (d->in_row[v] < 0 || d->in_row[v] >= d->n_rows) return fail(HB_ERR_INVALID, "route input row outside the record");
+    return HB_OK;
+}
+
 }  // namespace
 
 // ================================ C-ABI ==============================================================
@@ -688,14 +734,8 @@ int hb_compile_route(const hb_route_spec *spec, const char *body, hb_model_t *ou
 }
 
 int hb_run_route_device(hb_model_t m, const hb_route_desc *d, void *stream) {
-    if (!m || m->kind != 1) return fail(HB_ERR_INVALID, "not a route model");
-    if (!d || d->struct_size != (int32_t)sizeof(hb_route_desc)) return fail(HB_ERR_INVALID, "hb_route_desc.struct_size mismatch");
-    const hb_route_spec &s = m->rspec;
-    if (d->n_nodes <= 0 || d->n_steps < 0 || !d->records || !d->up_ptr || !d->up_idx) return fail(HB_ERR_INVALID, "bad route descriptor");
-    if (!(d->min_value > 0)) return fail(HB_ERR_INVALID, "min_value must be positive, got %g", d->min_value);
-    if (d->s_row < 0 || d->s_row >= d->n_rows || d->o_row < 0 || d->o_row >= d->n_rows) return fail(HB_ERR_INVALID, "route rows outside the record");
-    for (int v = 0; v < s.n_inputs; ++v)
-        if (d->in_row[v] < 0 || d->in_row[v] >= d->n_rows) return fail(HB_ERR_INVALID, "route input row outside the record");
+    int rc0 = check_route_desc(m, d);
+    if (rc0) return rc0;
     int rc = load_model(m);
     if (rc) return rc;
     HB_CUDA(cudaSetDevice(g_device));
@@ -712,38 +752,13 @@ int hb_run_route_device(hb_model_t m, const hb_route_desc *d, void *stream) {
         if (!m->ev0) { HB_CUDA(cudaEventCreate(&m->ev0)); HB_CUDA(cudaEventCreate(&m->ev1)); }
         HB_CUDA(cudaEventRecord(m->ev0, st));
     }
-    const int nv = s.n_inputs > 0 ? s.n_inputs : 1, np = s.n_params > 0 ? s.n_params : 1;
-    unsigned grid = (unsigned)((N + m->block - 1) / m->block);
     for (int64_t t = -1; t < T; ++t) {
-        // HbRouteArgs mirror (templates/route.cu): 9 pointers, 3 i64, 1 double, 3 int, int tables
-        unsigned char buf[9 * 8 + 3 * 8 + 8 + 3 * 4 + 4 * (16 + 2 * HB_MAX_PARAMS) + 16];
-        memset(buf, 0, sizeof buf);
-        size_t o = 0;
-        auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
         // step t >= 0 reads s/q half (t & 1), written by launch t-1, and writes the other half;
         // the prologue launch (t = -1) reads the initial state and writes the outflows of step 0
         const int cur = t < 0 ? 0 : (int)(t & 1);
-        const void *ptrs[9] = {d->records, d->params, d->htypes, sbuf[cur], sbuf[cur ^ 1], qbuf[cur], qbuf[cur ^ 1], d->up_ptr, d->up_idx};
-        if (t < 0) { ptrs[4] = sbuf[1]; ptrs[5] = qbuf[1]; ptrs[6] = qbuf[0]; }
-        put(ptrs, sizeof ptrs);
-        put(&N, 8);
-        put(&t, 8);
-        put(&T, 8);
-        double minv = d->min_value;
-        put(&minv, 8);
-        int R = d->n_rows, sr = d->s_row, orow = d->o_row;
-        put(&R, 4);
-        put(&sr, 4);
-        put(&orow, 4);
-        std::vector<int> tmp(nv > np ? nv : np, 0);
-        for (int v = 0; v < s.n_inputs; ++v) tmp[v] = d->in_row[v];
-        put(tmp.data(), 4 * nv);
-        for (int j = 0; j < np; ++j) tmp[j] = j < s.n_params ? d->param_offset[j] : 0;
-        put(tmp.data(), 4 * np);
-        for (int j = 0; j < np; ++j) tmp[j] = j < s.n_params ? d->param_mode[j] : 0;
-        put(tmp.data(), 4 * np);
-        void *params[1] = {buf};
-        HB_DRV(g_drv.LaunchKernel(m->func, grid, 1, 1, m->block, 1, 1, 0, (CUstream)st, params, nullptr));
+        if (t < 0) rc = launch_route_step(m, d, t, sbuf[0], sbuf[1], qbuf[1], qbuf[0], st);
+        else rc = launch_route_step(m, d, t, sbuf[cur], sbuf[cur ^ 1], qbuf[cur], qbuf[cur ^ 1], st);
+        if (rc) return rc;
     }
     // launch t = T-1 wrote the state half ((T-1) & 1) ^ 1 == T & 1
     if (d->final_states)
@@ -754,6 +769,16 @@ int hb_run_route_device(hb_model_t m, const hb_route_desc *d, void *stream) {
         HB_CUDA(cudaEventElapsedTime(d->elapsed_ms, m->ev0, m->ev1));
     }
     return HB_OK;
+}
+
+int hb_route_step_device(hb_model_t m, const hb_route_desc *d, int64_t t, const double *s_prev, double *s_next,
+                         const double *q_cur, double *q_next, void *stream) {
+    int rc = check_route_desc(m, d);
+    if (rc) return rc;
+    if (t < -1 || t >= d->n_steps || !s_prev || !s_next || !q_cur || !q_next) return fail(HB_ERR_INVALID, "bad route step arguments");
+    if ((rc = load_model(m))) return rc;
+    HB_CUDA(cudaSetDevice(g_device));
+    return launch_route_step(m, d, t, s_prev, s_next, q_cur, q_next, (cudaStream_t)stream);
 }
 
 // ---- memory helpers ----------------------------------------------------------------------------------

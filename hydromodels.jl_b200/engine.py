@@ -97,6 +97,8 @@ def lib():
         "hb_run": [C.c_void_p, C.POINTER(RunDesc)], "hb_run_device": [C.c_void_p, C.POINTER(RunDesc), C.c_void_p],
         "hb_compile_route": [C.POINTER(RouteSpec), C.c_char_p, C.POINTER(C.c_void_p)],
         "hb_run_route_device": [C.c_void_p, C.POINTER(RouteDesc), C.c_void_p],
+        "hb_route_step_device": [C.c_void_p, C.POINTER(RouteDesc), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p],
         "hb_malloc_device": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_device": [C.c_void_p],
         "hb_malloc_host": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_host": [C.c_void_p],
         "hb_memcpy_h2d": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
@@ -225,7 +227,9 @@ def upstream_csr(aggr, n_nodes: int):
         down = aggr.downstream()
         pos0 = aggr.positions - 1
         codes = aggr.flwdir[pos0[:, 0], pos0[:, 1]]
-        rank = np.array([D8_CODES.index(int(c)) if int(c) in D8_CODES else 99 for c in codes])
+        lut = np.full(256, 99, dtype=np.int64)
+        lut[list(D8_CODES)] = np.arange(8)
+        rank = np.where((codes >= 0) & (codes < 256), lut[np.clip(codes, 0, 255)], 99)
         src = np.nonzero(down >= 0)[0]
         order = np.lexsort((rank[src], down[src]))
         src, dst = src[order], down[src][order]
@@ -388,9 +392,15 @@ class B200Model:
             N = int(n_members)
         return N, input.shape[-1]
 
-    def prepare(self, prog: StepperProgram, params, N: int, *, ensemble: bool = False):
-        """Flat parameter table + modes + htypes + UH ordinates + MLP parameters."""
+    def prepare(self, prog: StepperProgram, params, N: int, *, ensemble: bool = False,
+                node_range: Optional[Tuple[int, int]] = None):
+        """Flat parameter table + modes + htypes + UH ordinates + MLP parameters.  `node_range=(n0, n1)`:
+        this process owns nodes `[n0, n1)` of a model described globally (multi-GPU shards): htypes are
+        sliced, per-node parameter vectors are sliced, shared (gathered) vectors are kept whole."""
         params = _as_componentvector(params)
+        n0, n1 = node_range if node_range is not None else (0, N)
+        if node_range is not None and n1 - n0 != N:
+            raise ValueError("node_range does not match the local node count")
         pdict = params["params"]
         names: List[str] = []
         for nm, _ in prog.param_slots:
@@ -400,22 +410,21 @@ class B200Model:
             for nm in u.param_names:
                 if nm not in names:
                     names.append(nm)
-        offs, chunks, pos = {}, [], 0
         vecs: Dict[str, np.ndarray] = {}
         for nm in names:
             if nm not in pdict:
                 raise KeyError(f"Parameter {nm} does not exist in params")
-            v = np.atleast_1d(np.asarray(pdict[nm], dtype=np.float64)).reshape(-1)
-            vecs[nm] = v
-            offs[nm] = pos
-            chunks.append(v)
-            pos += v.size
-        flat = np.ascontiguousarray(np.concatenate(chunks)) if chunks else np.zeros(1)
-        sets0 = []
+            vecs[nm] = np.atleast_1d(np.asarray(pdict[nm], dtype=np.float64)).reshape(-1)
+        sets0, ident = [], []
         for h in prog.htype_sets:
-            if len(h) != N:
+            if node_range is None and len(h) != N:
                 raise ValueError(f"htypes has {len(h)} entries but the input has {N} nodes")
-            sets0.append(np.asarray(h, dtype=np.int64) - 1)
+            if node_range is not None and len(h) < n1:
+                raise ValueError("node_range exceeds htypes")
+            h0 = np.asarray(h, dtype=np.int64) - 1
+            ident.append(bool(np.array_equal(h0[n0:n1], np.arange(n0, n1))))
+            sets0.append(h0[n0:n1] if node_range is not None else h0)
+        n_global = max([len(h) for h in prog.htype_sets] or [N])
 
         def mode_of(nm: str, hs: Optional[int]) -> int:
             v = vecs[nm]
@@ -432,11 +441,23 @@ class B200Model:
             h0 = sets0[hs]
             if h0.size and (h0.min() < 0 or h0.max() >= v.size):
                 raise IndexError(f"BoundsError: attempt to access {v.size}-element parameter {nm} at index htypes")
-            if v.size == N and np.array_equal(h0, np.arange(N)):
+            if v.size == n_global and ident[hs]:
                 return 1
             return 2 + hs
+        modes = [mode_of(nm, hs) for nm, hs in prog.param_slots]
+        # a name used per-node by every slot is uploaded as its local slice; otherwise whole
+        per_node_only = {nm: all(m == 1 for (n2, _), m in zip(prog.param_slots, modes) if n2 == nm) for nm in names}
+        offs, chunks, pos = {}, [], 0
+        for nm in names:
+            v = vecs[nm]
+            if node_range is not None and per_node_only.get(nm, False) and v.size == n_global and any(n2 == nm for n2, _ in prog.param_slots):
+                v = v[n0:n1]
+            offs[nm] = pos
+            chunks.append(v)
+            pos += v.size
+        flat = np.ascontiguousarray(np.concatenate(chunks)) if chunks else np.zeros(1)
         p_off = np.array([offs[nm] for nm, _ in prog.param_slots] or [0], dtype=np.int32)
-        p_mode = np.array([mode_of(nm, hs) for nm, hs in prog.param_slots] or [0], dtype=np.int32)
+        p_mode = np.array(modes or [0], dtype=np.int32)
         htypes = np.ascontiguousarray(np.stack(sets0).astype(np.int32)) if sets0 else None
         # unit hydrographs: ordinates per node (host-evaluated N×K table)
         uhw = None
@@ -473,7 +494,8 @@ class B200Model:
             nn = np.ascontiguousarray(np.concatenate(parts))
         return flat, p_off, p_mode, htypes, uhw, kmax, nn
 
-    def _initstates(self, prog: StepperProgram, initstates, N: int) -> Optional[np.ndarray]:
+    def _initstates(self, prog: StepperProgram, initstates, N: int,
+                    node_range: Optional[Tuple[int, int]] = None) -> Optional[np.ndarray]:
         S = len(prog.state_names)
         if S == 0 or initstates is None:
             return None                       # zeros (`model._defaultstates`, `src/model.jl:51-52`)
@@ -482,8 +504,13 @@ class B200Model:
             for i, s in enumerate(prog.state_names):
                 if s not in initstates:
                     raise KeyError(f"State {s} not found in initstates")
-                out[i] = np.broadcast_to(np.asarray(initstates[s], dtype=np.float64), (N,))
+                v = np.asarray(initstates[s], dtype=np.float64)
+                if node_range is not None and v.ndim == 1 and v.size != N:
+                    v = v[node_range[0]:node_range[1]]
+                out[i] = np.broadcast_to(v, (N,))
             return out
+        if node_range is not None:
+            raise NotImplementedError("sharded runs take initstates as a dict of per-state vectors")
         v = np.asarray(initstates, dtype=np.float64).reshape(-1)
         if v.size != S * N:
             raise ValueError(f"initstates has {v.size} elements, expected {S}*{N} (state-major, node-fastest)")
@@ -608,54 +635,12 @@ class B200Model:
             check(lib().hb_memcpy_h2d(rec.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes, None))
             check(lib().hb_stream_synchronize(None))
         # ---- route ----
-        if self._route_kernel is None:
-            self._route_kernel = CompiledRoute(lower_route(route, fast=self.fast))
-        rk = self._route_kernel
-        pdict = params["params"]
-        chunks, offs, pos = [], [], 0
-        h0 = np.asarray(route.htypes, dtype=np.int64) - 1
-        modes = []
-        for nm, _ in rk.program.param_slots:
-            if nm not in pdict:
-                raise KeyError(f"Parameter {nm} does not exist in params")
-            v = np.atleast_1d(np.asarray(pdict[nm], dtype=np.float64)).reshape(-1)
-            if h0.size and (h0.min() < 0 or h0.max() >= v.size):
-                raise IndexError(f"BoundsError: attempt to access {v.size}-element parameter {nm} at index htypes")
-            modes.append(1 if (v.size == N and np.array_equal(h0, np.arange(N))) else 2)
-            offs.append(pos)
-            chunks.append(v)
-            pos += v.size
-        flat = np.ascontiguousarray(np.concatenate(chunks)) if chunks else np.zeros(1)
-        p_off = np.array(offs or [0], dtype=np.int32)
-        p_mode = np.array(modes or [0], dtype=np.int32)
-        up_ptr, up_idx = upstream_csr(route.aggr, N)
-        bufs = [DeviceBuffer.from_host(flat), DeviceBuffer.from_host(h0.astype(np.int32)),
-                DeviceBuffer.from_host(up_ptr), DeviceBuffer.from_host(up_idx)]
-        dinit = None
-        if init_all is not None and s_name in init_all:
-            dinit = DeviceBuffer.from_host(np.ascontiguousarray(init_all[s_name]))
-        in_row = np.array([rec_rows.index(nm) for nm in route.input_names] or [0], dtype=np.int32)
-        el = C.c_float(0.0)
-        d = RouteDesc()
-        d.struct_size = C.sizeof(RouteDesc)
-        d.n_htype_sets = 1
-        d.n_nodes, d.n_steps = N, T
-        d.records, d.n_rows = rec.ptr, Rr
-        d.s_row, d.o_row = rec_rows.index(s_name), rec_rows.index(o_name)
-        d.in_row = _ptr(in_row)
-        d.params, d.n_param_values = bufs[0].ptr, flat.size
-        d.param_offset, d.param_mode = _ptr(p_off), _ptr(p_mode)
-        d.htypes = bufs[1].ptr
-        d.initstates = dinit.ptr if dinit is not None else None
-        d.up_ptr, d.up_idx = bufs[2].ptr, bufs[3].ptr
-        d.min_value = cfg.min_value
-        d.elapsed_ms = C.cast(C.byref(el), C.c_void_p)
-        check(lib().hb_run_route_device(rk.handle, C.byref(d), None))
-        kernel_ms += el.value
+        stage = RouteStage(self, N, T, params, cfg, rec_rows,
+                           None if init_all is None or s_name not in init_all else init_all[s_name])
+        kernel_ms += stage.launch(rec.ptr, None, timed=True)
+        stage.free()
         full = rec.to_host((Rr, N, T), order="F")
         rec.free()
-        for b in bufs:
-            b.free()
         if timing is not None:
             timing["kernel_ms"] = kernel_ms
         out = full if not extra else np.asfortranarray(full[:R])
@@ -787,7 +772,7 @@ class DeviceRun:
 
     def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None,
                  rows: Optional[Sequence[str]] = None, objective: Optional[str] = None, target=None,
-                 warm_up: int = 1, ensemble: bool = False, _kmax=None):
+                 warm_up: int = 1, ensemble: bool = False, _kmax=None, node_range: Optional[Tuple[int, int]] = None):
         self.eng, self.N, self.T = eng, int(N), int(T)
         self.cfg = normalize_config(config)
         _check_config(self.cfg, T)
@@ -798,19 +783,19 @@ class DeviceRun:
         elif eng._has_uh():
             probe = lower_stepper(eng._stepper_component(), rows=rows, objective=obj, fast=eng.fast,
                                   holes=eng._route_rows())
-            kmax = eng.prepare(probe, params, N, ensemble=ensemble)[5]
+            kmax = eng.prepare(probe, params, N, ensemble=ensemble, node_range=node_range)[5]
         else:
             kmax = []
         self.ck = eng.compiled(rows=rows, objective=obj, metric=metric, shared_forcing=ensemble, uh_kmax=kmax)
         prog = self.ck.program
-        flat, p_off, p_mode, htypes, uhw, kmax, nn = eng.prepare(prog, params, N, ensemble=ensemble)
+        flat, p_off, p_mode, htypes, uhw, kmax, nn = eng.prepare(prog, params, N, ensemble=ensemble, node_range=node_range)
         self._host = (p_off, p_mode)
         self.bufs = {"params": DeviceBuffer.from_host(flat)}
         self.n_param_values = flat.size
         self.n_sets = 0 if htypes is None else htypes.shape[0]
         if htypes is not None:
             self.bufs["htypes"] = DeviceBuffer.from_host(htypes)
-        init = eng._initstates(prog, initstates, N)
+        init = eng._initstates(prog, initstates, N, node_range)
         if init is not None:
             self.bufs["init"] = DeviceBuffer.from_host(init)
         if uhw:
@@ -862,3 +847,123 @@ class DeviceRun:
             d.elapsed_ms = C.cast(C.byref(el), C.c_void_p)
         check(lib().hb_run_device(self.ck.handle, C.byref(d), stream))
         return el.value if timed else None
+
+
+class RouteStage:
+    """Device-resident arguments of the routing stage of a model (`hb_run_route_device`): parameters,
+    htypes, upstream CSR, initial state — staged once; `launch()` enqueues the T+1 routing kernels."""
+
+    def __init__(self, eng: B200Model, N: int, T: int, params, cfg: HydroConfig, rec_rows: Sequence[str], init_state,
+                 node_range: Optional[Tuple[int, int]] = None, csr=None):
+        """`node_range=(n0, n1)` + `csr=(up_ptr, up_idx)`: this process owns nodes `[n0, n1)`; `up_idx`
+        addresses local nodes `< N` and ghost slots `>= N` (see `parallel.RoutePartition`)."""
+        route = eng.route
+        if eng._route_kernel is None:
+            eng._route_kernel = CompiledRoute(lower_route(route, fast=eng.fast))
+        self.rk = eng._route_kernel
+        self.N, self.T, self.cfg = int(N), int(T), cfg
+        pdict = _as_componentvector(params)["params"]
+        chunks, offs, pos, modes = [], [], 0, []
+        h0 = np.asarray(route.htypes, dtype=np.int64) - 1
+        n_global = len(h0)
+        n0, n1 = node_range if node_range is not None else (0, N)
+        if n1 - n0 != N or n1 > n_global or (node_range is None and n_global != N):
+            raise ValueError(f"htypes has {n_global} entries but the input has {N} nodes")
+        ident = np.array_equal(h0[n0:n1], np.arange(n0, n1))
+        h0 = h0[n0:n1]
+        for nm, _ in self.rk.program.param_slots:
+            if nm not in pdict:
+                raise KeyError(f"Parameter {nm} does not exist in params")
+            v = np.atleast_1d(np.asarray(pdict[nm], dtype=np.float64)).reshape(-1)
+            if h0.size and (h0.min() < 0 or h0.max() >= v.size):
+                raise IndexError(f"BoundsError: attempt to access {v.size}-element parameter {nm} at index htypes")
+            per_node = v.size == n_global and ident
+            modes.append(1 if per_node else 2)
+            if per_node:
+                v = v[n0:n1]
+            offs.append(pos)
+            chunks.append(v)
+            pos += v.size
+        flat = np.ascontiguousarray(np.concatenate(chunks)) if chunks else np.zeros(1)
+        self.n_param_values = flat.size
+        self.p_off = np.array(offs or [0], dtype=np.int32)
+        self.p_mode = np.array(modes or [0], dtype=np.int32)
+        up_ptr, up_idx = csr if csr is not None else upstream_csr(route.aggr, N)
+        self.bufs = [DeviceBuffer.from_host(flat), DeviceBuffer.from_host(h0.astype(np.int32)),
+                     DeviceBuffer.from_host(up_ptr), DeviceBuffer.from_host(up_idx)]
+        if init_state is not None:
+            init_state = np.asarray(init_state, dtype=np.float64)
+            if node_range is not None and init_state.ndim == 1 and init_state.size != N:
+                init_state = init_state[n0:n1]
+        self.dinit = None if init_state is None else DeviceBuffer.from_host(
+            np.ascontiguousarray(np.broadcast_to(init_state, (N,))))
+        self.in_row = np.array([list(rec_rows).index(nm) for nm in route.input_names] or [0], dtype=np.int32)
+        self.n_rows = len(rec_rows)
+        self.s_row = list(rec_rows).index(route.state_names[0])
+        self.o_row = list(rec_rows).index(route.output_names[0])
+
+    def launch(self, rec_ptr: int, stream: Optional[int] = None, timed: bool = False) -> Optional[float]:
+        el = C.c_float(0.0)
+        d = RouteDesc()
+        d.struct_size = C.sizeof(RouteDesc)
+        d.n_htype_sets = 1
+        d.n_nodes, d.n_steps = self.N, self.T
+        d.records, d.n_rows = rec_ptr, self.n_rows
+        d.s_row, d.o_row = self.s_row, self.o_row
+        d.in_row = _ptr(self.in_row)
+        d.params, d.n_param_values = self.bufs[0].ptr, self.n_param_values
+        d.param_offset, d.param_mode = _ptr(self.p_off), _ptr(self.p_mode)
+        d.htypes = self.bufs[1].ptr
+        d.initstates = self.dinit.ptr if self.dinit is not None else None
+        d.up_ptr, d.up_idx = self.bufs[2].ptr, self.bufs[3].ptr
+        d.min_value = self.cfg.min_value
+        if timed:
+            d.elapsed_ms = C.cast(C.byref(el), C.c_void_p)
+        check(lib().hb_run_route_device(self.rk.handle, C.byref(d), stream))
+        return el.value if timed else None
+
+    def _desc(self, rec_ptr: int) -> RouteDesc:
+        d = RouteDesc()
+        d.struct_size = C.sizeof(RouteDesc)
+        d.n_htype_sets = 1
+        d.n_nodes, d.n_steps = self.N, self.T
+        d.records, d.n_rows = rec_ptr, self.n_rows
+        d.s_row, d.o_row = self.s_row, self.o_row
+        d.in_row = _ptr(self.in_row)
+        d.params, d.n_param_values = self.bufs[0].ptr, self.n_param_values
+        d.param_offset, d.param_mode = _ptr(self.p_off), _ptr(self.p_mode)
+        d.htypes = self.bufs[1].ptr
+        d.up_ptr, d.up_idx = self.bufs[2].ptr, self.bufs[3].ptr
+        d.min_value = self.cfg.min_value
+        return d
+
+    def step(self, rec_ptr: int, t: int, s_prev: int, s_next: int, q_cur: int, q_next: int, stream: Optional[int] = None):
+        """One routing step on caller-owned ping-pong buffers (`hb_route_step_device`)."""
+        d = self._desc(rec_ptr)
+        check(lib().hb_route_step_device(self.rk.handle, C.byref(d), C.c_int64(t), s_prev, s_next, q_cur, q_next, stream))
+
+    def free(self):
+        for b in self.bufs + ([self.dinit] if self.dinit is not None else []):
+            b.free()
+        self.bufs, self.dinit = [], None
+
+
+class RoutedDeviceRun:
+    """Device-resident run of a model that ends in a HydroRoute: the per-node stepper over all T steps
+    into the [T][N][R] records, then T+1 routing launches filling the route's two rows in place."""
+
+    def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None):
+        if eng.route is None or eng.lumped is None:
+            raise ValueError("RoutedDeviceRun needs a model with per-node components followed by a HydroRoute")
+        self.cfg = normalize_config(config)
+        rows = eng.component.var_names
+        s_name = eng.route.state_names[0]
+        init = None if initstates is None else {k: v for k, v in initstates.items() if k != s_name}
+        self.stepper = DeviceRun(eng, N, T, params, config=self.cfg, initstates=init, rows=rows)
+        self.stage = RouteStage(eng, N, T, params, self.cfg, rows, None if initstates is None else initstates.get(s_name))
+        self.N, self.T, self.n_rows = int(N), int(T), len(rows)
+        self.in_bytes, self.out_bytes = self.stepper.in_bytes, T * N * len(rows) * 8
+
+    def launch(self, input_ptr: int, rec_ptr: int, stream: Optional[int] = None):
+        self.stepper.launch(input_ptr, rec_ptr, stream)
+        self.stage.launch(rec_ptr, stream)

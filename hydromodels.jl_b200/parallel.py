@@ -73,3 +73,150 @@ def gather_nodes(local: np.ndarray, n_nodes: int, group=None, device: Optional[s
     for r, (a, b) in enumerate(sizes):
         full[..., a:b] = outs[r].cpu().numpy()[..., :b - a]
     return full
+
+
+# ---------------------------------------------------------------------------------------------------
+# Sharded routing: contiguous node slices + ghost outflows exchanged every step
+# ---------------------------------------------------------------------------------------------------
+class RoutePartition:
+    """Split a routed node set (global upstream CSR) into contiguous per-rank slices.
+
+    For rank r owning `[n0, n1)`, upstream nodes outside the slice become GHOST slots appended to the
+    local outflow buffer (`q[N_local + g]`), sorted by global id — so the ghosts owned by one peer form
+    one contiguous run, which is exactly what that peer sends (its boundary outflows, in id order).
+    Every rank derives all send/recv lists from the global topology; nothing is negotiated at run time.
+    On a D8 grid sharded into row strips the ghosts of a strip are (part of) the boundary rows of its
+    two neighbours — 8 bytes per boundary cell per step."""
+
+    def __init__(self, up_ptr: np.ndarray, up_idx: np.ndarray, n_nodes: int, world: int):
+        self.n_nodes, self.world = int(n_nodes), int(world)
+        self.up_ptr = np.asarray(up_ptr, dtype=np.int64)
+        self.up_idx = np.asarray(up_idx, dtype=np.int64)[: int(self.up_ptr[-1])]
+        self.ranges = [shard_range(n_nodes, r, world) for r in range(world)]
+        self._starts = np.array([a for a, _ in self.ranges] + [n_nodes], dtype=np.int64)
+        self._ghosts = [self._ghost_ids(r) for r in range(world)]
+
+    def _ghost_ids(self, rank: int) -> np.ndarray:
+        n0, n1 = self.ranges[rank]
+        li = self.up_idx[self.up_ptr[n0]:self.up_ptr[n1]]
+        return np.unique(li[(li < n0) | (li >= n1)])
+
+    def owner(self, ids: np.ndarray) -> np.ndarray:
+        return np.searchsorted(self._starts, ids, side="right") - 1
+
+    def local_csr(self, rank: int):
+        """(up_ptr int32 [Nl+1], up_idx int32 with ghost slots >= Nl, n_ghost)."""
+        n0, n1 = self.ranges[rank]
+        ptr = (self.up_ptr[n0:n1 + 1] - self.up_ptr[n0]).astype(np.int32)
+        li = self.up_idx[self.up_ptr[n0]:self.up_ptr[n1]]
+        gh = self._ghosts[rank]
+        remote = (li < n0) | (li >= n1)
+        idx = np.where(remote, (n1 - n0) + np.searchsorted(gh, li), li - n0).astype(np.int32)
+        if idx.size == 0:
+            idx = np.zeros(1, dtype=np.int32)
+        return ptr, np.ascontiguousarray(idx), int(gh.size)
+
+    def recv_plan(self, rank: int):
+        """[(peer, ghost offset, count)]: peer's values land in ghost slots [offset, offset+count)."""
+        gh = self._ghosts[rank]
+        own = self.owner(gh)
+        plan = []
+        for p in np.unique(own):
+            sel = np.nonzero(own == p)[0]
+            plan.append((int(p), int(sel[0]), int(sel.size)))
+        return plan
+
+    def send_plan(self, rank: int):
+        """[(peer, local indices)]: the outflows of these local nodes, in this order, go to `peer`."""
+        n0, n1 = self.ranges[rank]
+        plan = []
+        for p in range(self.world):
+            if p == rank:
+                continue
+            gh = self._ghosts[p]
+            mine = gh[(gh >= n0) & (gh < n1)]
+            if mine.size:
+                plan.append((p, (mine - n0).astype(np.int64)))
+        return plan
+
+
+def exchange_ghosts(q, n_local: int, send_plan, recv_plan, group=None):
+    """Fill the ghost slots of the outflow buffer `q` (torch tensor `[n_local + n_ghost]`) with the
+    peers' boundary outflows: grouped point-to-point sends/receives (NCCL on GPUs, gloo in tests)."""
+    import torch
+    import torch.distributed as dist
+
+    if not send_plan and not recv_plan:
+        return
+    ops, keep = [], []
+    for peer, idx in send_plan:
+        buf = q[:n_local].index_select(0, idx).contiguous()
+        keep.append(buf)
+        ops.append(dist.P2POp(dist.isend, buf, peer, group=group))
+    for peer, off, cnt in recv_plan:
+        ops.append(dist.P2POp(dist.irecv, q[n_local + off:n_local + off + cnt], peer, group=group))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+
+
+class ShardedRoutedRun:
+    """Multi-GPU run of a model ending in a HydroRoute: this rank owns nodes `[n0, n1)`.
+
+    1. the per-node stepper runs all T steps on the local nodes (no communication);
+    2. T+1 routing launches (`hb_route_step_device`); between consecutive launches the freshly computed
+       outflows of the boundary nodes are exchanged so every rank's ghost slots hold its upstream
+       neighbours' outflows for the next step — the only data-path collective of the whole run.
+    Records stay sharded (`[T][N_local][R]` per rank)."""
+
+    def __init__(self, eng, n_nodes: int, T: int, params, *, config=None, initstates=None, group=None):
+        import torch
+        import torch.distributed as dist
+        from .components import normalize_config
+        from .engine import DeviceRun, RouteStage, upstream_csr
+
+        if eng.route is None or eng.lumped is None:
+            raise ValueError("ShardedRoutedRun needs per-node components followed by a HydroRoute")
+        self.group = group
+        self.rank, self.world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+        self.part = RoutePartition(*upstream_csr(eng.route.aggr, n_nodes), n_nodes, self.world)
+        self.n0, self.n1 = self.part.ranges[self.rank]
+        Nl = self.n1 - self.n0
+        cfg = normalize_config(config)
+        rows = eng.component.var_names
+        s_name = eng.route.state_names[0]
+        init = None if initstates is None else {k: v for k, v in initstates.items() if k != s_name}
+        rng = (self.n0, self.n1)
+        self.stepper = DeviceRun(eng, Nl, T, params, config=cfg, initstates=init, rows=rows, node_range=rng)
+        ptr, idx, self.n_ghost = self.part.local_csr(self.rank)
+        self.stage = RouteStage(eng, Nl, T, params, cfg, rows, None if initstates is None else initstates.get(s_name),
+                                node_range=rng, csr=(ptr, idx))
+        self.N, self.T, self.n_rows = Nl, int(T), len(rows)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.s = [torch.zeros(Nl, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.q = [torch.zeros(Nl + self.n_ghost, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.send = [(p, torch.from_numpy(ix).to(dev)) for p, ix in self.part.send_plan(self.rank)]
+        self.recv = self.part.recv_plan(self.rank)
+        self.init_state = None
+        if self.stage.dinit is not None:
+            self.init_state = torch.zeros(Nl, dtype=torch.float64, device=dev)
+            host = self.stage.dinit.to_host((Nl,))
+            self.init_state.copy_(torch.from_numpy(host))
+        self.in_bytes, self.out_bytes = self.stepper.in_bytes, T * Nl * len(rows) * 8
+
+    def launch(self, input_ptr: int, rec_ptr: int):
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+        self.stepper.launch(input_ptr, rec_ptr, stream)
+        s, q = self.s, self.q
+        if self.init_state is not None:
+            s[0].copy_(self.init_state)
+        else:
+            s[0].zero_()
+        # prologue: outflows of step 0 from the initial state, then their ghosts
+        self.stage.step(rec_ptr, -1, s[0].data_ptr(), s[1].data_ptr(), q[1].data_ptr(), q[0].data_ptr(), stream)
+        exchange_ghosts(q[0], self.N, self.send, self.recv, self.group)
+        for t in range(self.T):
+            cur = t & 1
+            self.stage.step(rec_ptr, t, s[cur].data_ptr(), s[cur ^ 1].data_ptr(), q[cur].data_ptr(), q[cur ^ 1].data_ptr(), stream)
+            if t + 1 < self.T:
+                exchange_ghosts(q[cur ^ 1], self.N, self.send, self.recv, self.group)

@@ -190,6 +190,12 @@ int hb_compile_route(const hb_route_spec *spec, const char *body, hb_model_t *ou
 /* T+1 launches of hb_route_step on `stream` (device pointers; returns after enqueueing unless
  * elapsed_ms is requested). */
 int hb_run_route_device(hb_model_t m, const hb_route_desc *desc, void *stream);
+/* ONE routing step (t = -1 is the prologue that only produces the outflows of step 0) on caller-owned
+ * ping-pong buffers: s_prev/s_next [n_nodes], q_cur/q_next [n_nodes + n_ghost].  Multi-GPU runs own
+ * a slice of the nodes; `up_idx` entries >= n_nodes address ghost slots of q_cur that the host fills
+ * with the neighbouring ranks' boundary outflows between steps (NCCL send/recv, see parallel.py). */
+int hb_route_step_device(hb_model_t m, const hb_route_desc *desc, int64_t t, const double *s_prev, double *s_next,
+                         const double *q_cur, double *q_next, void *stream);
 
 /* ---- memory helpers (so a host without a CUDA binding can own device / pinned buffers) ---- */
 int hb_malloc_device(void **ptr, int64_t bytes);

@@ -65,3 +65,86 @@ def test_two_rank_sharded_run_matches_single_rank():
     assert np.array_equal(full_final, ref[:2, :, -1])
     ref_obj = np.array([ho.objective("nse", ref[-1, i] * 1.1 + 0.01, ref[-1, i]) for i in range(N)])
     assert np.array_equal(full_obj, ref_obj)
+
+
+# ---- sharded routing: partition + ghost exchange (gloo), numpy Jacobi step standing in for the kernel ----
+def _route_worker(rank, world, port, R, Cc, T, q_in, lag, flw, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hydromodels_jl_b200.engine import upstream_csr
+    pos = [(r + 1, c + 1) for r in range(R) for c in range(Cc)]
+    N = len(pos)
+    aggr = hm.build_aggr_func(flw, pos)
+    part = par.RoutePartition(*upstream_csr(aggr, N), N, world)
+    n0, n1 = part.ranges[rank]
+    Nl = n1 - n0
+    ptr, idx, ng = part.local_csr(rank)
+    send = [(p, torch.from_numpy(ix)) for p, ix in part.send_plan(rank)]
+    recv = part.recv_plan(rank)
+    s = np.zeros(Nl)
+    qb = [torch.zeros(Nl + ng, dtype=torch.float64) for _ in range(2)]
+    lg = lag[n0:n1]
+    rflux = lambda x, st: st / (1 + lg) + x
+    out = np.zeros((2, Nl, T))
+    qb[0][:Nl] = torch.from_numpy(rflux(q_in[n0:n1, 0], s))
+    par.exchange_ghosts(qb[0], Nl, send, recv)
+    for t in range(T):
+        cur = t & 1
+        qc = qb[cur].numpy()
+        inflow = np.array([qc[idx[ptr[n]:ptr[n + 1]]].sum() for n in range(Nl)])
+        x = q_in[n0:n1, t]
+        s = np.maximum(1e-6, s + ((x - qc[:Nl]) + inflow))
+        out[0, :, t], out[1, :, t] = s, rflux(x, s)
+        if t + 1 < T:
+            qb[cur ^ 1][:Nl] = torch.from_numpy(rflux(q_in[n0:n1, t + 1], s))
+            par.exchange_ghosts(qb[cur ^ 1], Nl, send, recv)
+    full = par.gather_nodes(out.reshape(2 * T, Nl) if False else np.ascontiguousarray(out.transpose(0, 2, 1)).reshape(2 * T, Nl), N)
+    if rank == 0:
+        q.put(full.reshape(2, T, N).transpose(0, 2, 1))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_route_partition_and_ghost_exchange(world):
+    import hydro_oracle as ho
+    rng = np.random.default_rng(11)
+    R, Cc, T = 9, 7, 12
+    flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128, 0], size=(R, Cc))
+    N = R * Cc
+    q_in = np.abs(rng.normal(size=(N, T)))
+    lag = rng.uniform(0.1, 2.0, N)
+    ctx = mp.get_context("spawn")
+    qu = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_route_worker, args=(r, world, port, R, Cc, T, q_in, lag, flw, qu)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = qu.get(timeout=120)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    s = hm.Symbols("q q_routed s_river", "lag")
+    pos = [(r + 1, c + 1) for r in range(R) for c in range(Cc)]
+    route = hm.HydroRoute(rfluxes=[hm.HydroFlux("q_routed ~ s_river / (1 + lag) + q", symbols=s)],
+                          dfluxes=[hm.StateFlux("s_river ~ q - q_routed", symbols=s)],
+                          aggr_func=hm.build_aggr_func(flw, pos), htypes=np.arange(1, N + 1))
+    ref = ho.run_route(route, q_in[None, :, :], {"params": dict(lag=lag)})
+    assert np.allclose(got, ref, rtol=1e-13, atol=1e-14)
+
+
+def test_route_partition_plans_are_consistent():
+    from hydromodels_jl_b200.engine import upstream_csr
+    rng = np.random.default_rng(5)
+    R, Cc = 12, 10
+    flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128], size=(R, Cc))
+    pos = [(r + 1, c + 1) for r in range(R) for c in range(Cc)]
+    N = len(pos)
+    part = par.RoutePartition(*upstream_csr(hm.build_aggr_func(flw, pos), N), N, 4)
+    for r in range(4):
+        for peer, off, cnt in part.recv_plan(r):
+            sends = dict(part.send_plan(peer))
+            assert r in sends and len(sends[r]) == cnt          # what r expects is what peer sends
+        ptr, idx, ng = part.local_csr(r)
+        n0, n1 = part.ranges[r]
+        assert ptr[-1] == part.up_ptr[n1] - part.up_ptr[n0] and idx.max(initial=0) < (n1 - n0) + ng
