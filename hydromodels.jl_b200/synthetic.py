@@ -58,7 +58,7 @@ def forcing(model: str, n0: int, n1: int, T: int, seed: int = SEED) -> np.ndarra
 _BOUNDS = {
     "exphydro": dict(Tmin=(-3.0, 0.0), Tmax=(0.0, 3.0), Df=(0.5, 5.0), Smax=(100.0, 2000.0), Qmax=(10.0, 50.0),
                      f=(0.005, 0.1)),
-    "gr4j": dict(x1=(100.0, 1200.0), x2=(-5.0, 3.0), x3=(20.0, 300.0), x4=(1.1, 2.9)),
+    "gr4j": dict(x1=(100.0, 1200.0), x2=(-5.0, 3.0), x3=(60.0, 300.0), x4=(1.1, 2.9)),
     "hbv": dict(TT=(-1.5, 1.5), CFMAX=(1.0, 8.0), CFR=(0.0, 0.1), CWH=(0.0, 0.2), LP=(0.3, 1.0), FC=(50.0, 500.0),
                 BETA=(0.2, 1.0), PPERC=(0.01, 0.2), UZL=(5.0, 60.0), k0=(0.05, 0.5), k1=(0.01, 0.3), k2=(0.001, 0.1)),
     "m50": dict(Tmin=(-3.0, 0.0), Tmax=(0.0, 3.0), Df=(0.5, 5.0)),
