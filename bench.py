@@ -165,7 +165,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--block", type=int, default=0, help="tuning: threads per block of the stepper")
     ap.add_argument("--stages", type=int, default=0, help="tuning: forcing pipeline depth (time steps)")
-    ap.add_argument("--maxreg", type=int, default=0, help="tuning: NVRTC --maxrregcount")
+    ap.add_argument("--maxreg", type=int, default=0, help="tuning: register budget per thread")
+    ap.add_argument("--regconst", type=int, default=-1, help="tuning: exp constants resident in registers (0/1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -258,7 +259,8 @@ def main():
         d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
     else:
         model, p, init = build_problem(hm, sy, model_name, n0, N, T)
-        eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
+        kw = {} if args.regconst < 0 else {"regconst": bool(args.regconst)}
+        eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg, **kw)
         run = DeviceRun(eng, N, T, p, initstates=init)
         d_in = device_forcing(torch, model_name, N, T, sy.SEED + 17 * rank)
         d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)

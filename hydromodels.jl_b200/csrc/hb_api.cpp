@@ -275,7 +275,8 @@ int nvrtc_compile(const std::string &src, const std::vector<std::string> &opts, 
 int stepper_smem_bytes(const hb_stepper_spec &s, int block, int stages) {
     auto up128 = [](int x) { return (x + 127) / 128 * 128; };
     int warps = block / 32;
-    int nn = 0;   // MLP parameters live in the module's constant bank (hb_nn_const), not in shared memory
+    // per-thread MLP path: parameters in the module's constant bank; tensor path: staged in shared memory + scratch
+    int nn = s.nn_tensor ? up128(s.nn_words * 8) + warps * 1024 : 0;
     int in_b = up128(stages * 32 * s.n_inputs * 8);
     int out_b = s.output_mode == HB_OUT_ROWS ? up128(2 * 32 * s.n_rows * 8) : 0;
     return nn + warps * (in_b + out_b) + warps * stages * 8;
@@ -486,19 +487,21 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
     int cap = 2048 / m->block;
     if (minblocks > cap) minblocks = cap;
     if (minblocks < 1) minblocks = 1;
-    if (minblocks > 4) minblocks = 4;   // 128 regs/thread at 128 threads x 4 blocks; FP64-heavy bodies need them
     if (spec->max_registers > 0) {      // register budget per thread -> resident blocks the compiler must allow
         int byregs = 65536 / (spec->max_registers * m->block);
         if (byregs < 1) byregs = 1;
         if (byregs < minblocks) minblocks = byregs;
+    } else if (minblocks > 4) {
+        minblocks = 4;                  // default: 128 regs/thread at 128 threads x 4 blocks; FP64-heavy bodies need them
     }
     char defs[1024];
     snprintf(defs, sizeof defs,
              "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_UHW_TOTAL %d\n"
              "#define HB_UHH_TOTAL %d\n#define HB_NN_WORDS %d\n#define HB_MODE %d\n#define HB_METRIC %d\n#define HB_SHARED_FORCING %d\n"
-             "#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n",
+             "#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n#define HB_NN_MMA %d\n",
              spec->n_inputs, spec->output_mode == HB_OUT_ROWS ? spec->n_rows : 0, spec->n_states, spec->n_params, m->uhw_total,
-             m->uhh_total, spec->nn_words, spec->output_mode, spec->metric, spec->shared_forcing ? 1 : 0, m->block, stages, minblocks);
+             m->uhh_total, spec->nn_words, spec->output_mode, spec->metric, spec->shared_forcing ? 1 : 0, m->block, stages, minblocks,
+             spec->nn_tensor ? 1 : 0);
     std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";   // body may append to DEFINES (e.g. HB_NC)
     m->source = splice(kStepperTemplate, full_body.c_str());
     m->kernel_name = "hb_stepper";

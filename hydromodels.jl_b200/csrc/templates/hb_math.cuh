@@ -71,26 +71,76 @@ HB_CONST double HB_EXPC[10] = {
     5.00000000000001838553e-01   // r^2
 };
 
-// |x| saturated at a bound given by the HIGH WORD of its double representation (3 integer
+// |x| saturated at (just above) a bound given by the HIGH WORD of its double representation (3 integer
 // instructions, no FP64-pipe work; the NaN-aware fmin/fmax the compiler emits cost ~6 each).
 // A NaN is mapped to +/-bound as well (NaN forcing is not propagated through exp/step_func).
 HB_DEV double hb_clamp_abs(double x, int bound_hi) {
     const int hi = hb_double2hiint(x);
-    const int ahi = hi & 0x7fffffff;
-    const int chi = (ahi < bound_hi ? ahi : bound_hi) | (hi & 0x80000000);
-    return hb_hiloint2double(chi, ahi < bound_hi ? hb_double2loint(x) : 0);
+    const unsigned ahi = (unsigned)hi & 0x7fffffffu;
+    const unsigned chi = (ahi < (unsigned)bound_hi ? ahi : (unsigned)bound_hi) | ((unsigned)hi & 0x80000000u);
+    // the low word is kept: a saturated value lies in [bound, bound * (1 + 2^-20)) — still inside the
+    // range the callers need (3 instructions: LOP3, VIMNMX.U32, LOP3)
+    return hb_hiloint2double((int)chi, hb_double2loint(x));
 }
 #define HB_HI_700 0x4085e000   // high word of 700.0
 #define HB_HI_746 0x40875000   // high word of 746.0
 
+// The 13 constants of the exp kernel.  Inside a long time loop the compiler re-materialises each
+// 64-bit immediate with two UMOVs per use (81 of ~490 instructions per ExpHydro step); when
+// HB_REGCONST is defined the kernel loads them ONCE into registers (opaque to constant propagation)
+// and every helper takes them from `hb_K`.
+struct HbExpK { double log2e, nln2hi, nln2lo, c[10]; };
+HB_DEV double hb_opaque(double x) {
+#ifndef HB_HOST_TEST
+    asm volatile("" : "+d"(x));
+#endif
+    return x;
+}
+#ifndef HB_HOST_TEST
+// mutable module-scope copy: a load from it cannot be constant-folded or re-materialised by ptxas
+__device__ double hb_expk_mem[13] = {1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+    2.5110037605963777712e-08, 2.76326396390410297493e-07, 2.7557240918578969823e-06, 2.4801485482328492419e-05,
+    1.98412698900471137067e-04, 1.38888889523147746524e-03, 8.33333333331960061091e-03, 4.16666666664880954954e-02,
+    1.66666666666666808057e-01, 5.00000000000001838553e-01};
+#endif
+HB_DEV HbExpK hb_expk_load() {
+    HbExpK K;
+#ifdef HB_HOST_TEST
+    K.log2e = 1.4426950408889634074; K.nln2hi = -6.93147180369123816490e-01; K.nln2lo = -1.90821492927058770002e-10;
+    for (int i = 0; i < 10; ++i) K.c[i] = HB_EXPC[i];
+#else
+    const volatile double *m = hb_expk_mem;
+    K.log2e = m[0]; K.nln2hi = m[1]; K.nln2lo = m[2];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) K.c[i] = m[3 + i];
+#endif
+    return K;
+}
+
 // k = round(x / ln2), p = exp(x - k ln2) ~ [0.70, 1.42]
-HB_DEV double hb_exp_reduce(double x, int &k) {
+HB_DEV double hb_exp_reduce_k(double x, int &k, const HbExpK &K) {
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: round-to-nearest-integer trick
-    double t = fma(x, 1.4426950408889634074, MAGIC);    // x * log2(e)
+    double t = fma(x, K.log2e, MAGIC);                  // x * log2(e)
     k = hb_double2loint(t);
     t -= MAGIC;
-    double r = fma(t, -6.93147180369123816490e-01, x);  // ln2 high part (trailing zeros: t*hi exact)
-    r = fma(t, -1.90821492927058770002e-10, r);         // ln2 low part
+    double r = fma(t, K.nln2hi, x);                     // ln2 high part (trailing zeros: t*hi exact)
+    r = fma(t, K.nln2lo, r);                            // ln2 low part
+    double p = K.c[0];
+#ifndef HB_HOST_TEST
+#pragma unroll
+#endif
+    for (int i = 1; i < 10; ++i) p = fma(p, r, K.c[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return p;
+}
+HB_DEV double hb_exp_reduce(double x, int &k) {
+    const double MAGIC = 6755399441055744.0;
+    double t = fma(x, 1.4426950408889634074, MAGIC);
+    k = hb_double2loint(t);
+    t -= MAGIC;
+    double r = fma(t, -6.93147180369123816490e-01, x);
+    r = fma(t, -1.90821492927058770002e-10, r);
     double p = HB_EXPC[0];
 #ifndef HB_HOST_TEST
 #pragma unroll
@@ -143,3 +193,18 @@ HB_DEV double hb_min(double a, double b) { return a < b ? a : b; }
 HB_DEV double hb_max(double a, double b) { return a > b ? a : b; }
 HB_DEV double hb_leakyrelu(double x) { return hb_max(0.01 * x, x); }
 HB_DEV double hb_clamp(double x, double lo, double hi) { return hb_min(hb_max(x, lo), hi); }
+
+// ---- register-constant variants (HB_REGCONST): same arithmetic, constants from `K` ----------------
+HB_DEV double hb_exp_narrow_k(double x, const HbExpK &K) {
+    int k;
+    const double p = hb_exp_reduce_k(x, k, K);
+    return hb_hiloint2double(hb_double2hiint(p) + (k << 20), hb_double2loint(p));
+}
+HB_DEV double hb_exp_k(double x, const HbExpK &K) {
+    int k;
+    const double p = hb_exp_reduce_k(hb_clamp_abs(x, HB_HI_746), k, K);
+    const int k1 = k >> 1, k2 = k - k1;
+    return (p * hb_hiloint2double((k1 + 1023) << 20, 0)) * hb_hiloint2double((k2 + 1023) << 20, 0);
+}
+HB_DEV double hb_step_k(double x, const HbExpK &K) { return hb_rcp(1.0 + hb_exp_narrow_k(hb_clamp_abs(-10.0 * x, HB_HI_700), K)); }
+HB_DEV double hb_tanh_k(double x, const HbExpK &K) { return fma(-2.0, hb_rcp(1.0 + hb_exp_narrow_k(hb_clamp_abs(2.0 * x, HB_HI_700), K)), 1.0); }

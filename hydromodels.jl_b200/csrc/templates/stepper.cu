@@ -37,6 +37,9 @@ typedef unsigned int u32;
 // (generated) HB_V HB_R HB_S HB_NP HB_NC HB_UHW_TOTAL HB_UHH_TOTAL HB_NN_WORDS HB_MODE HB_METRIC
 //             HB_SHARED_FORCING HB_BLOCK HB_STAGES HB_MINBLOCKS
 
+#ifndef HB_NN_MMA
+#define HB_NN_MMA 0
+#endif
 #define HB_OBUF 2
 #define HB_WARPS (HB_BLOCK / 32)
 #define HB_ARR(n) ((n) > 0 ? (n) : 1)
@@ -116,6 +119,11 @@ __device__ __forceinline__ void hb_fence_proxy_async() { asm volatile("fence.pro
 __constant__ double hb_nn_const[HB_NN_WORDS];
 #define HB_NNW(i) hb_nn_const[i]
 #endif
+// D(8x8) += A(8x4) * B(4x8) on the FP64 tensor pipe (SASS DMMA).  Fragments: A lane l -> A[l/4][l%4],
+// B lane l -> B[l%4][l/4], C/D lane l -> C[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void hb_dmma(double &d0, double &d1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 
 //@@HB:HELPERS
 
@@ -129,24 +137,35 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     const bool valid = n < a.N;
     const bool full_warp = (n0w + 32) <= a.N;
 
-    // shared-memory carve-up: [MLP params][per-warp forcing ring][per-warp result tiles][mbarriers]
-    constexpr int kNNBytes = 0;   // MLP parameters live in the constant bank (hb_nn_const)
+    // shared-memory carve-up: [MLP params + per-warp MMA scratch][per-warp forcing ring][per-warp result tiles][mbarriers]
+#if HB_NN_MMA
+    constexpr int kNNBytes = ((HB_NN_WORDS * 8 + 127) / 128) * 128 + HB_WARPS * 1024;
+#else
+    constexpr int kNNBytes = 0;   // per-thread MLP path: parameters live in the constant bank (hb_nn_const)
+#endif
     constexpr int kInStage = 32 * HB_V * 8;                       // bytes of one warp-step of forcing
     constexpr int kInBytes = ((HB_STAGES * kInStage + 127) / 128) * 128;
     constexpr int kOutTile = 32 * HB_R * 8;                       // bytes of one warp-step of results
     constexpr int kOutBytes = ((HB_OBUF * kOutTile + 127) / 128) * 128;
     double *sNN = reinterpret_cast<double *>(hb_smem);
+    double *hb_scr = reinterpret_cast<double *>(hb_smem + ((HB_NN_WORDS * 8 + 127) / 128) * 128) + warp * 128;   // 1 KB per warp
     unsigned char *warp_base = hb_smem + kNNBytes + (size_t)warp * (kInBytes + kOutBytes);
     double *sIn = reinterpret_cast<double *>(warp_base);
     double *sOut = reinterpret_cast<double *>(warp_base + kInBytes);
     u64 *bars = reinterpret_cast<u64 *>(hb_smem + kNNBytes + (size_t)HB_WARPS * (kInBytes + kOutBytes)) + warp * HB_STAGES;
-    (void)sNN; (void)sIn; (void)sOut; (void)bars;
-
+    (void)sNN; (void)hb_scr; (void)sIn; (void)sOut; (void)bars;
+#if HB_NN_MMA
+    // tensor-core MLP path: dense-layer weights are read as MMA fragments (lane-dependent addresses)
+    for (int i = threadIdx.x; i < HB_NN_WORDS; i += HB_BLOCK) sNN[i] = a.nn[i];
+    __syncthreads();
+#endif
 
     // warp-uniform choice of the I/O path
     const bool tma_in = (HB_SHARED_FORCING == 0) && (HB_V > 0) && a.tma_in_ok && full_warp;
     const bool tma_out = (HB_MODE == 0) && (HB_R > 0) && a.tma_out_ok && full_warp;
-    if (!valid) return;   // ragged last warp: that warp is on the per-thread path (no warp syncs)
+    // Lanes past the last node of a ragged warp stay alive (warp-collective MMA / shuffles in the body
+    // need all 32 lanes): they shadow the last node (`nc`) and never store.
+    const i64 nc = valid ? n : a.N - 1;
 
     // ---- per-node constants: parameters (p[htypes], /root/reference/src/utils.jl:174-201) ------
     double hb_p[HB_ARR(HB_NP)];
@@ -154,21 +173,21 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     for (int j = 0; j < HB_NP; ++j) {
         const int mode = a.p_mode[j];
         i64 idx = a.p_off[j];
-        if (mode == 1) idx += n;
-        else if (mode >= 2) idx += a.htypes[(i64)(mode - 2) * a.N + n];
+        if (mode == 1) idx += nc;
+        else if (mode >= 2) idx += a.htypes[(i64)(mode - 2) * a.N + nc];
         hb_p[j] = a.params[idx];
     }
     // ---- states: initial value is used UNCLAMPED for the first increment (solve.jl:47-49) ------
     double hb_u[HB_ARR(HB_S)];
 #pragma unroll
-    for (int s = 0; s < HB_S; ++s) hb_u[s] = a.init ? a.init[(i64)s * a.N + n] : 0.0;
+    for (int s = 0; s < HB_S; ++s) hb_u[s] = a.init ? a.init[(i64)s * a.N + nc] : 0.0;
     // ---- unit-hydrograph ordinates and history -----------------------------------------------
     double hb_uhw[HB_ARR(HB_UHW_TOTAL)];
     double hb_uhh[HB_ARR(HB_UHH_TOTAL)];
 #pragma unroll
-    for (int k = 0; k < HB_UHW_TOTAL; ++k) hb_uhw[k] = a.uhw[(i64)k * a.N + n];
+    for (int k = 0; k < HB_UHW_TOTAL; ++k) hb_uhw[k] = a.uhw[(i64)k * a.N + nc];
 #pragma unroll
-    for (int k = 0; k < HB_UHH_TOTAL; ++k) hb_uhh[k] = a.uhh_in ? a.uhh_in[(i64)k * a.N + n] : 0.0;
+    for (int k = 0; k < HB_UHH_TOTAL; ++k) hb_uhh[k] = a.uhh_in ? a.uhh_in[(i64)k * a.N + nc] : 0.0;
     double hb_c[HB_ARR(HB_NC)];   // state-only subexpressions carried from one step to the next
     const double hb_minv = a.min_value;
     (void)hb_p; (void)hb_u; (void)hb_uhw; (void)hb_uhh; (void)hb_c; (void)hb_minv;
@@ -178,12 +197,19 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     double q_n = 0.0, q_so = 0.0, q_ss = 0.0, q_soo = 0.0, q_sss = 0.0, q_sos = 0.0, q_sse = 0.0, q_shift = 0.0;
 #endif
 
+#ifdef HB_REGCONST
+    const HbExpK hb_K = hb_expk_load();    // exp constants resident in registers for the whole run
+#define hb_step(x) hb_step_k((x), hb_K)
+#define hb_exp(x) hb_exp_k((x), hb_K)
+#define hb_tanh(x) hb_tanh_k((x), hb_K)
+#endif
+
     //@@HB:PROLOGUE
 
     const i64 T = a.T;
     const i64 in_step = (HB_SHARED_FORCING ? 1 : a.N) * (i64)HB_V;   // doubles per time step
     const double *in_warp = a.in + (HB_SHARED_FORCING ? 0 : n0w * HB_V);
-    const double *in_lane = a.in + (HB_SHARED_FORCING ? 0 : n * HB_V);
+    const double *in_lane = a.in + (HB_SHARED_FORCING ? 0 : nc * HB_V);
     double *out_warp = a.out + n0w * HB_R;
     double *out_lane = a.out + n * HB_R;
     (void)in_warp; (void)out_warp; (void)out_lane; (void)in_lane;
@@ -263,14 +289,16 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
             ow_ptr += out_step;
             ob ^= 1;
         } else {
+            if (valid) {
 #pragma unroll
-            for (int r = 0; r < HB_R; ++r) go[r] = hb_out[r];
+                for (int r = 0; r < HB_R; ++r) go[r] = hb_out[r];
+            }
             go += out_step;
         }
 #endif
 #if HB_MODE == 1
         if (t + 1 >= a.warm_up) {
-            double o = a.target_per_node ? a.target[t * a.N + n] : a.target[t];
+            double o = a.target_per_node ? a.target[t * a.N + nc] : a.target[t];
             double s = hb_sim;
 #if HB_METRIC == 3
             o = log(o + 1e-6);
@@ -287,6 +315,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     if (tma_out && lane == 0) hb_bulk_wait<0>();   // shared tiles must outlive the last bulk stores
 
     // ---- epilogue: final states / UH history for chunked-T runs, objective ---------------------
+    if (!valid) return;
     if (a.final_states) {
 #pragma unroll
         for (int s = 0; s < HB_S; ++s) a.final_states[(i64)s * a.N + n] = hb_u[s];

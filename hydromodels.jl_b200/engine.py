@@ -42,7 +42,7 @@ class StepperSpec(C.Structure):
                 ("n_params", C.c_int32), ("n_uh", C.c_int32), ("uh_kmax", C.c_int32 * HB_MAX_UH),
                 ("nn_words", C.c_int32), ("output_mode", C.c_int32), ("metric", C.c_int32),
                 ("shared_forcing", C.c_int32), ("block_threads", C.c_int32), ("stages", C.c_int32),
-                ("max_registers", C.c_int32)]
+                ("max_registers", C.c_int32), ("nn_tensor", C.c_int32)]
 
 
 class RunDesc(C.Structure):
@@ -164,6 +164,7 @@ class CompiledStepper:
         spec.block_threads = block_threads
         spec.stages = stages
         spec.max_registers = max_registers
+        spec.nn_tensor = 1 if getattr(program, "nn_tensor", False) else 0
         self.spec = spec
         h = C.c_void_p()
         check(lib().hb_compile_stepper(C.byref(spec), program.body.encode(), C.byref(h)))
@@ -313,9 +314,11 @@ class B200Model:
     """Wrapper component: `B200Model(model)(input, params, config; initstates)`."""
 
     def __init__(self, component: Component, *, fast: bool = True, block_threads: int = 0, stages: int = 0,
-                 max_registers: int = 0):
+                 max_registers: int = 0, nn_tensor: bool = True, regconst: bool = False):
         self.component = component
         self.fast = fast
+        self.regconst = regconst
+        self.nn_tensor = nn_tensor        # dense chains on the FP64 tensor pipe (DMMA) where their shape fits
         self.block_threads, self.stages, self.max_registers = block_threads, stages, max_registers
         self._cache: Dict[Tuple, CompiledStepper] = {}
         self.last_kernel: Optional[CompiledStepper] = None
@@ -354,7 +357,7 @@ class B200Model:
         if key not in self._cache:
             prog = lower_stepper(self._stepper_component(), rows=rows, objective=objective,
                                  uh_kmax=list(uh_kmax) if len(uh_kmax) else None, fast=self.fast,
-                                 holes=self._route_rows())
+                                 holes=self._route_rows(), nn_tensor=self.nn_tensor, regconst=self.regconst)
             # MLP-fused bodies keep 16+16 activations per net in registers: give them 168 (3 blocks/SM)
             maxreg = self.max_registers or (168 if prog.nn_words else 0)
             self._cache[key] = CompiledStepper(prog, metric=metric, shared_forcing=shared_forcing,

@@ -90,6 +90,7 @@ class StepperProgram:
     n_carry: int
     objective: bool
     stats: Dict[str, int] = field(default_factory=dict)
+    nn_tensor: bool = False         # some dense chain is lowered to FP64 MMA fragments
 
 
 class _Builder:
@@ -177,6 +178,14 @@ class _Builder:
             return self._lower_pow(a[0], a[1])
         if op == "clamp":
             return self.op("min", self.op("max", a[0], a[1]), a[2])
+        if op == "step" and self.fast:
+            # step_func(a - b) + step_func(b - a) == 1 (logistic symmetry): the snow/rain split of every
+            # reference model evaluates both — the second one costs a subtraction instead of exp + rcp
+            x = self.vals[a[0]]
+            if x.op == "sub":
+                twin = self.memo.get(("sub", x.args[1], x.args[0]))
+                if twin is not None and ("step", twin) in self.memo:
+                    return self.op("sub", self.const(1.0), self.memo[("step", twin)])
         return self.op(op, *a)
 
     def _lower_pow(self, base: int, ex: int) -> int:
@@ -239,7 +248,7 @@ def _flatten(component: Component) -> Tuple[List[Component], List[str], List[str
 
 def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None, objective: bool = False,
                   uh_kmax: Optional[Sequence[int]] = None, fast: bool = True,
-                  holes: Sequence[str] = ()) -> StepperProgram:
+                  holes: Sequence[str] = (), nn_tensor: bool = False, regconst: bool = False) -> StepperProgram:
     """Lower a per-node model (buckets, fluxes, neural fluxes, unit hydrographs) to one stepper
     body.  `rows`: subset/order of result rows to write (default: all = the reference result);
     `objective`: emit the last output row as `hb_sim` for the fused metric reduction instead of
@@ -434,6 +443,13 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
     step: List[str] = []
     pro_names: Dict[int, str] = {}
 
+    # dense chains whose shape fits the FP64 tensor-core fragments are contracted with DMMA
+    net_mma = [bool(nn_tensor and fast and _mma_eligible(ch)) for ch in nets]
+
+    def nn_call(ni: int, args: List[str], arr: str) -> str:
+        pre = "sNN, hb_scr, lane, " if net_mma[ni] else "sNN, "
+        return f"hb_mlp_{ni}({pre}{', '.join(args)}, {arr});"
+
     def nn_var(ni: int, ins: Tuple[int, ...], tag: str) -> str:
         return f"nn{tag}{ni}_" + "_".join(str(k) for k in ins)
 
@@ -453,7 +469,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
             ni, ins, j = v.payload
             arr = nn_var(ni, ins, "p")
             if arr not in pro_names.values():
-                pro.append(f"double {arr}[{nets[ni].n_out}]; hb_mlp_{ni}(sNN, {', '.join(args)}, {arr});")
+                pro.append(f"double {arr}[{nets[ni].n_out}]; " + nn_call(ni, args, arr))
                 pro_names[-len(pro_names) - 1] = arr
             pro.append(f"const double {nm} = {arr}[{j}];")
         else:
@@ -497,7 +513,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
             arr = nn_var(ni, ins, "s")
             if arr not in nn_done:
                 nn_done.add(arr)
-                step.append(f"double {arr}[{nets[ni].n_out}]; hb_mlp_{ni}(sNN, {', '.join(step_ref(k) for k in ins)}, {arr});")
+                step.append(f"double {arr}[{nets[ni].n_out}]; " + nn_call(ni, [step_ref(k) for k in ins], arr))
             step.append(f"const double v{i} = {arr}[{j}];")
         else:
             step.append(f"const double v{i} = {_expr_with(v, [step_ref(a) for a in v.args], fast)};")
@@ -518,8 +534,9 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
         if K >= 2:
             step.append(f"hb_uhh[{uh_h_off[u]}] = {step_ref(x)};")
 
-    helpers = [_mlp_helper(i, ch, off, fast) for i, (ch, (_, off, _)) in enumerate(zip(nets, nn_layout))]
-    body = "//@@HB:DEFINES\n" + f"#define HB_NC {len(carried)}\n" + \
+    helpers = [(_mlp_helper_mma if net_mma[i] else _mlp_helper)(i, ch, off, fast)
+               for i, (ch, (_, off, _)) in enumerate(zip(nets, nn_layout))]
+    body = "//@@HB:DEFINES\n" + f"#define HB_NC {len(carried)}\n" + ("#define HB_REGCONST 1\n" if (regconst and not nets) else "") + \
            "//@@HB:HELPERS\n" + "\n".join(helpers) + "\n" + \
            "//@@HB:PROLOGUE\n" + "\n".join("    " + s for s in pro) + "\n" + \
            "//@@HB:STEP\n" + "\n".join("        " + s for s in step) + "\n"
@@ -532,7 +549,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                           state_names=state_names, param_slots=param_slots, htype_sets=htype_sets, uh=uhs,
                           uh_kmax=list(uh_kmax), uh_htype_set=[htype_set(u) for u in uhs],
                           nn_layout=nn_layout, nn_words=sum(n for _, _, n in nn_layout), n_carry=len(carried),
-                          objective=objective, stats=stats)
+                          objective=objective, stats=stats, nn_tensor=any(net_mma))
 
 
 def _expr_with(v: Val, a: List[str], fast: bool) -> str:
@@ -660,3 +677,94 @@ def lower_route(route: HydroRoute, *, fast: bool = True) -> RouteProgram:
     body = "//@@HB:HELPERS\n" + f1 + "\n" + f2 + "\n"
     return RouteProgram(body=body, input_names=list(route.input_names), state_name=sname, output_name=oname,
                         param_slots=param_slots, htype_sets=htype_sets)
+
+
+def _mma_eligible(chain) -> bool:
+    """Shapes the DMMA lowering handles: `n_in <= 4 -> H (-> H')* -> 1` with every hidden width a
+    multiple of 8 and at most 32 (M50: 3-16-16-1 and 2-16-16-1, `test/base/run_single_lumped.jl:216-229`)."""
+    L = chain.layers
+    if len(L) < 2 or L[0].n_in > 4 or L[-1].n_out != 1:
+        return False
+    return all(l.n_out % 8 == 0 and 8 <= l.n_out <= 32 for l in L[:-1])
+
+
+def _mlp_helper_mma(idx: int, chain, offset: int, fast: bool) -> str:
+    """Warp-cooperative dense chain on the FP64 tensor pipe (`mma.sync.m8n8k4.f64`, SASS DMMA).
+
+    The warp's 32 basins are the M dimension (4 tiles of 8), neurons the N dimension, layer inputs K:
+    `D[basin][neuron] = sum_k A[basin][k] * W[neuron][k] + bias`.  Lane (q = lane/4, j = lane%4) holds,
+    for every M tile mt, the accumulator pair of neurons `8*nt + 2j + {0,1}` of basin `8*mt + q`.  The
+    K index of the next layer is only summed over, so its order is free: chunk `c = 2*nt + e` of the
+    next layer's A fragment is DEFINED as the neuron this very lane already holds (`8*nt + 2j + e`)
+    and the weight fragment is gathered with the same permutation — activations never move between
+    lanes from one layer to the next.  Only the layer-0 inputs (owned by lane = basin) and the final
+    scalar output go through a 1 KB per-warp shared scratch."""
+    acts = _ACT_C
+    L = chain.layers
+    args = ", ".join(f"const double x{i}" for i in range(chain.n_in))
+    o = [f"__device__ __forceinline__ void hb_mlp_{idx}(const double* __restrict__ sW, double* __restrict__ scr, const int lane, {args}, double* __restrict__ y) {{",
+         "    const int q = lane >> 2, j = lane & 3;"]
+    for k in range(4):
+        o.append(f"    scr[lane * 4 + {k}] = {'x%d' % k if k < chain.n_in else '0.0'};")
+    o += ["    __syncwarp();", "    double afr[4];", "#pragma unroll",
+          "    for (int mt = 0; mt < 4; ++mt) afr[mt] = scr[(mt * 8 + q) * 4 + j];", "    __syncwarp();"]
+    off = offset
+    # layer 0: K = 4 (inputs zero-padded), one chunk
+    l0 = L[0]
+    nt0 = l0.n_out // 8
+    bias = off + l0.n_out * l0.n_in
+    o.append(f"    double h0[4][{nt0}][2];")
+    o.append("#pragma unroll")
+    o.append(f"    for (int nt = 0; nt < {nt0}; ++nt) {{")
+    o.append(f"        const double b = (j < {l0.n_in}) ? sW[{off} + j * {l0.n_out} + nt * 8 + q] : 0.0;")
+    o.append(f"        const double c0 = sW[{bias} + nt * 8 + 2 * j], c1 = sW[{bias} + nt * 8 + 2 * j + 1];")
+    o.append("#pragma unroll")
+    o.append("        for (int mt = 0; mt < 4; ++mt) { h0[mt][nt][0] = c0; h0[mt][nt][1] = c1; hb_dmma(h0[mt][nt][0], h0[mt][nt][1], afr[mt], b); }")
+    o.append("    }")
+    if l0.activation != "identity":
+        o.append("#pragma unroll")
+        o.append(f"    for (int mt = 0; mt < 4; ++mt) for (int nt = 0; nt < {nt0}; ++nt) for (int e = 0; e < 2; ++e) h0[mt][nt][e] = {acts[l0.activation].format('h0[mt][nt][e]')};")
+    off += l0.n_params
+    prev, prev_nt = "h0", nt0
+    for li in range(1, len(L) - 1):
+        l = L[li]
+        ntl = l.n_out // 8
+        cur = f"h{li}"
+        bias = off + l.n_out * l.n_in
+        o.append(f"    double {cur}[4][{ntl}][2];")
+        o.append("#pragma unroll")
+        o.append(f"    for (int nt = 0; nt < {ntl}; ++nt) {{")
+        o.append(f"        const double c0 = sW[{bias} + nt * 8 + 2 * j], c1 = sW[{bias} + nt * 8 + 2 * j + 1];")
+        o.append("#pragma unroll")
+        o.append(f"        for (int mt = 0; mt < 4; ++mt) {{ {cur}[mt][nt][0] = c0; {cur}[mt][nt][1] = c1; }}")
+        o.append("#pragma unroll")
+        o.append(f"        for (int c = 0; c < {l.n_in // 4}; ++c) {{")
+        o.append(f"            const double b = sW[{off} + ((c >> 1) * 8 + 2 * j + (c & 1)) * {l.n_out} + nt * 8 + q];")
+        o.append("#pragma unroll")
+        o.append(f"            for (int mt = 0; mt < 4; ++mt) hb_dmma({cur}[mt][nt][0], {cur}[mt][nt][1], {prev}[mt][c >> 1][c & 1], b);")
+        o.append("        }")
+        o.append("    }")
+        if l.activation != "identity":
+            o.append("#pragma unroll")
+            o.append(f"    for (int mt = 0; mt < 4; ++mt) for (int nt = 0; nt < {ntl}; ++nt) for (int e = 0; e < 2; ++e) {cur}[mt][nt][e] = {acts[l.activation].format(cur + '[mt][nt][e]')};")
+        off += l.n_params
+        prev, prev_nt = cur, ntl
+    # last layer: H -> 1, per-lane partial dot + quad reduction
+    ll = L[-1]
+    o.append("    double yv[4];")
+    o.append("#pragma unroll")
+    o.append("    for (int mt = 0; mt < 4; ++mt) {")
+    o.append("        double part = 0.0;")
+    o.append("#pragma unroll")
+    o.append(f"        for (int nt = 0; nt < {prev_nt}; ++nt) for (int e = 0; e < 2; ++e) part = fma(sW[{off} + nt * 8 + 2 * j + e], {prev}[mt][nt][e], part);")
+    o.append("        part += __shfl_xor_sync(0xffffffffu, part, 1);")
+    o.append("        part += __shfl_xor_sync(0xffffffffu, part, 2);")
+    z = f"(part + sW[{off + ll.n_in}])"
+    o.append(f"        yv[mt] = {acts[ll.activation].format(z) if ll.activation != 'identity' else z};")
+    o.append("    }")
+    o.append("    if (j == 0) {")
+    o.append("#pragma unroll")
+    o.append("        for (int mt = 0; mt < 4; ++mt) scr[mt * 8 + q] = yv[mt];")
+    o.append("    }")
+    o += ["    __syncwarp();", "    y[0] = scr[lane];", "    __syncwarp();", "}"]
+    return "\n".join(o)

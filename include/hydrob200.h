@@ -87,6 +87,8 @@ typedef struct {
     int32_t block_threads;       /* 0 = default (128)                                         */
     int32_t stages;              /* forcing pipeline depth in time steps, 0 = default (4)     */
     int32_t max_registers;       /* 0 = default (128); register budget per thread -> __launch_bounds__ min blocks */
+    int32_t nn_tensor;           /* 1: the body contracts its dense layers with FP64 MMA (DMMA) fragments: MLP
+                                    parameters are staged in shared memory + 1 KB scratch per warp */
 } hb_stepper_spec;
 
 /* One forward run.  Pointers are HOST pointers for hb_run and DEVICE pointers for

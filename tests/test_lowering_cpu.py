@@ -118,9 +118,10 @@ def test_objective_row_and_final_states():
 
 
 def test_lowering_statistics_exphydro():
-    """The optimisations the design relies on actually fire: 7 exp-class evaluations per step
-    (the reference evaluates 12 tanh + 4 exp), 4 carried state-only values."""
+    """The optimisations the design relies on actually fire: 6 exp-class evaluations per step
+    (the reference evaluates 12 tanh + 4 exp; step(Tmin-temp)/step(temp-Tmin) share one), 4 carried
+    state-only values."""
     prog = hm.lower_stepper(hm.models.exphydro())
-    assert prog.stats["exp_like_per_step"] == 7
+    assert prog.stats["exp_like_per_step"] == 6
     assert prog.n_carry >= 3
     assert prog.row_names == hm.models.exphydro().var_names
