@@ -277,8 +277,9 @@ int stepper_smem_bytes(const hb_stepper_spec &s, int block, int stages) {
     int warps = block / 32;
     // per-thread MLP path: parameters in the module's constant bank; tensor path: staged in shared memory + scratch
     int nn = s.nn_tensor ? up128(s.nn_words * 8) + warps * 1024 : 0;
-    int in_b = up128(stages * 32 * s.n_inputs * 8);
-    int out_b = s.output_mode == HB_OUT_ROWS ? up128(2 * 32 * s.n_rows * 8) : 0;
+    const int es = s.precision ? 4 : 8;
+    int in_b = up128(stages * 32 * s.n_inputs * es);
+    int out_b = s.output_mode == HB_OUT_ROWS ? up128(2 * 32 * s.n_rows * es) : 0;
     return nn + warps * (in_b + out_b) + warps * stages * 8;
 }
 
@@ -356,8 +357,9 @@ int launch_stepper(hb_model_s *m, const hb_run_desc *d, cudaStream_t stream) {
     put(&minv, 8);
     int warm = d->warm_up, tpn = d->target_per_node;
     // TMA bulk copies need 16-byte aligned global addresses: base pointer and per-step stride
-    int tma_in = ((reinterpret_cast<uintptr_t>(d->input) & 15) == 0) && ((N * s.n_inputs) % 2 == 0);
-    int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((N * s.n_rows) % 2 == 0);
+    const int es = s.precision ? 4 : 8;
+    int tma_in = ((reinterpret_cast<uintptr_t>(d->input) & 15) == 0) && ((N * s.n_inputs * es) % 16 == 0);
+    int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((N * s.n_rows * es) % 16 == 0);
     if (getenv("HB_DISABLE_TMA")) tma_in = tma_out = 0;
     put(&warm, 4);
     put(&tpn, 4);
@@ -466,6 +468,8 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
         spec->n_uh < 0 || spec->n_uh > HB_MAX_UH || spec->nn_words < 0)
         return fail(HB_ERR_INVALID, "hb_stepper_spec out of range");
     if (spec->output_mode != HB_OUT_ROWS && spec->output_mode != HB_OUT_OBJECTIVE) return fail(HB_ERR_INVALID, "bad output_mode");
+    if (spec->precision != 0 && spec->precision != 1) return fail(HB_ERR_INVALID, "precision must be 0 (Float64) or 1 (Float32)");
+    if (spec->precision && spec->nn_tensor) return fail(HB_ERR_INVALID, "the FP64 tensor path is not available in Float32 mode");
     hb_model_s *m = new hb_model_s();
     m->spec = *spec;
     m->block = spec->block_threads > 0 ? spec->block_threads : 128;
@@ -498,10 +502,10 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
     snprintf(defs, sizeof defs,
              "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_UHW_TOTAL %d\n"
              "#define HB_UHH_TOTAL %d\n#define HB_NN_WORDS %d\n#define HB_MODE %d\n#define HB_METRIC %d\n#define HB_SHARED_FORCING %d\n"
-             "#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n#define HB_NN_MMA %d\n",
+             "#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n#define HB_NN_MMA %d\n#define HB_F32 %d\n",
              spec->n_inputs, spec->output_mode == HB_OUT_ROWS ? spec->n_rows : 0, spec->n_states, spec->n_params, m->uhw_total,
              m->uhh_total, spec->nn_words, spec->output_mode, spec->metric, spec->shared_forcing ? 1 : 0, m->block, stages, minblocks,
-             spec->nn_tensor ? 1 : 0);
+             spec->nn_tensor ? 1 : 0, spec->precision ? 1 : 0);
     std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";   // body may append to DEFINES (e.g. HB_NC)
     m->source = splice(kStepperTemplate, full_body.c_str());
     m->kernel_name = "hb_stepper";
@@ -622,8 +626,9 @@ int hb_run(hb_model_t m, const hb_run_desc *d) {
         HB_CUDA(cudaMemcpyAsync(m->ws[in.slot].p, in.host, in.bytes, cudaMemcpyHostToDevice, m->stream));
         *in.dev = m->ws[in.slot].p;
     }
-    const size_t in_step = (size_t)Nin * s.n_inputs * 8;          // forcing bytes per time step
-    const size_t out_step = rows_mode ? (size_t)N * s.n_rows * 8 : 0;
+    const size_t es = s.precision ? 4 : 8;
+    const size_t in_step = (size_t)Nin * s.n_inputs * es;         // forcing bytes per time step
+    const size_t out_step = rows_mode ? (size_t)N * s.n_rows * es : 0;
     if ((rc = ws_reserve(m->ws[0], in_step * T))) return rc;
     if (rows_mode && (rc = ws_reserve(m->ws[8], out_step * T))) return rc;
     if (!rows_mode && (rc = ws_reserve(m->ws[9], (size_t)N * 8))) return rc;
@@ -670,8 +675,8 @@ int hb_run(hb_model_t m, const hb_run_desc *d) {
         hb_run_desc dc = dd;
         dc.elapsed_ms = nullptr;
         dc.n_steps = t1 - t0;
-        dc.input = (const double *)((const char *)m->ws[0].p + in_step * t0);
-        dc.out = rows_mode ? (double *)((char *)m->ws[8].p + out_step * t0) : nullptr;
+        dc.input = (const char *)m->ws[0].p + in_step * t0;
+        dc.out = rows_mode ? (void *)((char *)m->ws[8].p + out_step * t0) : nullptr;
         dc.objective = rows_mode ? nullptr : (double *)m->ws[9].p;
         dc.initstates = (const double *)state_in;
         dc.uh_hist_in = (const double *)uhh_in;

@@ -208,3 +208,15 @@ HB_DEV double hb_exp_k(double x, const HbExpK &K) {
 }
 HB_DEV double hb_step_k(double x, const HbExpK &K) { return hb_rcp(1.0 + hb_exp_narrow_k(hb_clamp_abs(-10.0 * x, HB_HI_700), K)); }
 HB_DEV double hb_tanh_k(double x, const HbExpK &K) { return fma(-2.0, hb_rcp(1.0 + hb_exp_narrow_k(hb_clamp_abs(2.0 * x, HB_HI_700), K)), 1.0); }
+
+// ---- opt-in Float32 mode: same functions on float (libdevice expf is ~1-2 ulp; the FP32 pipe is not the
+//      bottleneck, the halved HBM traffic is the point) ---------------------------------------------
+#ifndef HB_HOST_TEST
+HB_DEV float hb_exp(float x) { return expf(x); }
+HB_DEV float hb_rcp(float x) { return __frcp_rn(x); }
+HB_DEV float hb_step(float x) { return __frcp_rn(1.0f + expf(fminf(fmaxf(-10.0f * x, -80.0f), 80.0f))); }
+HB_DEV float hb_tanh(float x) { return fmaf(-2.0f, __frcp_rn(1.0f + expf(fminf(fmaxf(2.0f * x, -80.0f), 80.0f))), 1.0f); }
+HB_DEV float hb_min(float a, float b) { return a < b ? a : b; }
+HB_DEV float hb_max(float a, float b) { return a > b ? a : b; }
+HB_DEV float hb_leakyrelu(float x) { return hb_max(0.01f * x, x); }
+#endif

@@ -40,12 +40,23 @@ typedef unsigned int u32;
 #ifndef HB_NN_MMA
 #define HB_NN_MMA 0
 #endif
+#ifndef HB_F32
+#define HB_F32 0
+#endif
+// `real` = the arithmetic type of the run: double (the reference's promote_type, src/solve.jl:42) or,
+// opt-in, float (forcing and result streams are then float32 too; parameters, initial states, UH
+// ordinates, MLP parameters, targets and objectives stay double in memory)
+#if HB_F32
+typedef float real;
+#else
+typedef double real;
+#endif
 #define HB_OBUF 2
 #define HB_WARPS (HB_BLOCK / 32)
 #define HB_ARR(n) ((n) > 0 ? (n) : 1)
 
 struct HbArgs {
-    const double *in;
+    const real *in;
     const double *params;
     const int *htypes;
     const double *init;
@@ -53,7 +64,7 @@ struct HbArgs {
     const double *uhh_in;
     const double *nn;
     const double *target;
-    double *out;
+    real *out;
     double *obj;
     double *final_states;
     double *uhh_out;
@@ -117,7 +128,7 @@ __device__ __forceinline__ void hb_fence_proxy_async() { asm volatile("fence.pro
 //      every weight is a c[3][imm] operand of its DFMA; shared across all nodes (src/nn.jl:140-165)
 #if HB_NN_WORDS > 0
 __constant__ double hb_nn_const[HB_NN_WORDS];
-#define HB_NNW(i) hb_nn_const[i]
+#define HB_NNW(i) ((real)hb_nn_const[i])
 #endif
 // D(8x8) += A(8x4) * B(4x8) on the FP64 tensor pipe (SASS DMMA).  Fragments: A lane l -> A[l/4][l%4],
 // B lane l -> B[l%4][l/4], C/D lane l -> C[l/4][2*(l%4) + {0,1}].
@@ -143,15 +154,15 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
 #else
     constexpr int kNNBytes = 0;   // per-thread MLP path: parameters live in the constant bank (hb_nn_const)
 #endif
-    constexpr int kInStage = 32 * HB_V * 8;                       // bytes of one warp-step of forcing
+    constexpr int kInStage = 32 * HB_V * (int)sizeof(real);                      // bytes of one warp-step of forcing
     constexpr int kInBytes = ((HB_STAGES * kInStage + 127) / 128) * 128;
-    constexpr int kOutTile = 32 * HB_R * 8;                       // bytes of one warp-step of results
+    constexpr int kOutTile = 32 * HB_R * (int)sizeof(real);                      // bytes of one warp-step of results
     constexpr int kOutBytes = ((HB_OBUF * kOutTile + 127) / 128) * 128;
-    double *sNN = reinterpret_cast<double *>(hb_smem);
+    real *sNN = reinterpret_cast<real *>(hb_smem);   // tensor path only (Float64): staged MLP parameters
     double *hb_scr = reinterpret_cast<double *>(hb_smem + ((HB_NN_WORDS * 8 + 127) / 128) * 128) + warp * 128;   // 1 KB per warp
     unsigned char *warp_base = hb_smem + kNNBytes + (size_t)warp * (kInBytes + kOutBytes);
-    double *sIn = reinterpret_cast<double *>(warp_base);
-    double *sOut = reinterpret_cast<double *>(warp_base + kInBytes);
+    real *sIn = reinterpret_cast<real *>(warp_base);
+    real *sOut = reinterpret_cast<real *>(warp_base + kInBytes);
     u64 *bars = reinterpret_cast<u64 *>(hb_smem + kNNBytes + (size_t)HB_WARPS * (kInBytes + kOutBytes)) + warp * HB_STAGES;
     (void)sNN; (void)hb_scr; (void)sIn; (void)sOut; (void)bars;
 #if HB_NN_MMA
@@ -168,28 +179,28 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     const i64 nc = valid ? n : a.N - 1;
 
     // ---- per-node constants: parameters (p[htypes], /root/reference/src/utils.jl:174-201) ------
-    double hb_p[HB_ARR(HB_NP)];
+    real hb_p[HB_ARR(HB_NP)];
 #pragma unroll
     for (int j = 0; j < HB_NP; ++j) {
         const int mode = a.p_mode[j];
         i64 idx = a.p_off[j];
         if (mode == 1) idx += nc;
         else if (mode >= 2) idx += a.htypes[(i64)(mode - 2) * a.N + nc];
-        hb_p[j] = a.params[idx];
+        hb_p[j] = (real)a.params[idx];
     }
     // ---- states: initial value is used UNCLAMPED for the first increment (solve.jl:47-49) ------
-    double hb_u[HB_ARR(HB_S)];
+    real hb_u[HB_ARR(HB_S)];
 #pragma unroll
-    for (int s = 0; s < HB_S; ++s) hb_u[s] = a.init ? a.init[(i64)s * a.N + nc] : 0.0;
+    for (int s = 0; s < HB_S; ++s) hb_u[s] = a.init ? (real)a.init[(i64)s * a.N + nc] : (real)0.0;
     // ---- unit-hydrograph ordinates and history -----------------------------------------------
-    double hb_uhw[HB_ARR(HB_UHW_TOTAL)];
-    double hb_uhh[HB_ARR(HB_UHH_TOTAL)];
+    real hb_uhw[HB_ARR(HB_UHW_TOTAL)];
+    real hb_uhh[HB_ARR(HB_UHH_TOTAL)];
 #pragma unroll
-    for (int k = 0; k < HB_UHW_TOTAL; ++k) hb_uhw[k] = a.uhw[(i64)k * a.N + nc];
+    for (int k = 0; k < HB_UHW_TOTAL; ++k) hb_uhw[k] = (real)a.uhw[(i64)k * a.N + nc];
 #pragma unroll
-    for (int k = 0; k < HB_UHH_TOTAL; ++k) hb_uhh[k] = a.uhh_in ? a.uhh_in[(i64)k * a.N + nc] : 0.0;
-    double hb_c[HB_ARR(HB_NC)];   // state-only subexpressions carried from one step to the next
-    const double hb_minv = a.min_value;
+    for (int k = 0; k < HB_UHH_TOTAL; ++k) hb_uhh[k] = a.uhh_in ? (real)a.uhh_in[(i64)k * a.N + nc] : (real)0.0;
+    real hb_c[HB_ARR(HB_NC)];   // state-only subexpressions carried from one step to the next
+    const real hb_minv = (real)a.min_value;
     (void)hb_p; (void)hb_u; (void)hb_uhw; (void)hb_uhh; (void)hb_c; (void)hb_minv;
 
 #if HB_MODE == 1
@@ -208,10 +219,10 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
 
     const i64 T = a.T;
     const i64 in_step = (HB_SHARED_FORCING ? 1 : a.N) * (i64)HB_V;   // doubles per time step
-    const double *in_warp = a.in + (HB_SHARED_FORCING ? 0 : n0w * HB_V);
-    const double *in_lane = a.in + (HB_SHARED_FORCING ? 0 : nc * HB_V);
-    double *out_warp = a.out + n0w * HB_R;
-    double *out_lane = a.out + n * HB_R;
+    const real *in_warp = a.in + (HB_SHARED_FORCING ? 0 : n0w * HB_V);
+    const real *in_lane = a.in + (HB_SHARED_FORCING ? 0 : nc * HB_V);
+    real *out_warp = a.out + n0w * HB_R;
+    real *out_lane = a.out + n * HB_R;
     (void)in_warp; (void)out_warp; (void)out_lane; (void)in_lane;
 
     if (tma_in) {
@@ -236,18 +247,18 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     int ob = 0;
     // running pointers (strength-reduced: no 64-bit multiplies in the time loop)
     const i64 out_step = a.N * (i64)HB_R;
-    const double *pf_ptr = in_warp + (i64)HB_STAGES * in_step;   // forcing prefetched HB_STAGES steps ahead
-    const double *gx = in_lane;
-    double *ow_ptr = out_warp;
-    double *go = out_lane;
+    const real *pf_ptr = in_warp + (i64)HB_STAGES * in_step;   // forcing prefetched HB_STAGES steps ahead
+    const real *gx = in_lane;
+    real *ow_ptr = out_warp;
+    real *go = out_lane;
     (void)pf_ptr; (void)gx; (void)ow_ptr; (void)go; (void)out_step;
 #pragma unroll 1
     for (i64 t = 0; t < T; ++t) {
         // ---- forcing of this step -------------------------------------------------------------
-        double hb_x[HB_ARR(HB_V)];
+        real hb_x[HB_ARR(HB_V)];
         if (tma_in) {
             hb_mbar_wait(hb_smem_u32(&bars[slot]), parity);
-            const double *sx = sIn + slot * 32 * HB_V + lane * HB_V;
+            const real *sx = sIn + slot * 32 * HB_V + lane * HB_V;
 #pragma unroll
             for (int v = 0; v < HB_V; ++v) hb_x[v] = sx[v];
             __syncwarp();   // every lane has consumed the slot -> refill it HB_STAGES steps ahead
@@ -262,10 +273,10 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
             for (int v = 0; v < HB_V; ++v) hb_x[v] = gx[v];
             gx += in_step;
         }
-        double hb_out[HB_ARR(HB_R)];
+        real hb_out[HB_ARR(HB_R)];
         (void)hb_x; (void)hb_out;
 #if HB_MODE == 1
-        double hb_sim = 0.0;
+        real hb_sim = (real)0.0;
 #endif
 
         //@@HB:STEP
@@ -273,7 +284,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
         // ---- results of this step -------------------------------------------------------------
 #if HB_MODE == 0 && HB_R > 0
         if (tma_out) {
-            double *so = sOut + ob * 32 * HB_R;
+            real *so = sOut + ob * 32 * HB_R;
             if (t >= HB_OBUF) {   // the bulk store that last read this tile must have drained it
                 if (lane == 0) hb_bulk_wait_read<HB_OBUF - 1>();
                 __syncwarp();
@@ -299,7 +310,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
 #if HB_MODE == 1
         if (t + 1 >= a.warm_up) {
             double o = a.target_per_node ? a.target[t * a.N + nc] : a.target[t];
-            double s = hb_sim;
+            double s = (double)hb_sim;
 #if HB_METRIC == 3
             o = log(o + 1e-6);
             s = log(s + 1e-6);
@@ -318,11 +329,11 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     if (!valid) return;
     if (a.final_states) {
 #pragma unroll
-        for (int s = 0; s < HB_S; ++s) a.final_states[(i64)s * a.N + n] = hb_u[s];
+        for (int s = 0; s < HB_S; ++s) a.final_states[(i64)s * a.N + n] = (double)hb_u[s];
     }
     if (a.uhh_out) {
 #pragma unroll
-        for (int k = 0; k < HB_UHH_TOTAL; ++k) a.uhh_out[(i64)k * a.N + n] = hb_uhh[k];
+        for (int k = 0; k < HB_UHH_TOTAL; ++k) a.uhh_out[(i64)k * a.N + n] = (double)hb_uhh[k];
     }
 #if HB_MODE == 1
     {

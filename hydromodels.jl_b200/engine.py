@@ -42,7 +42,7 @@ class StepperSpec(C.Structure):
                 ("n_params", C.c_int32), ("n_uh", C.c_int32), ("uh_kmax", C.c_int32 * HB_MAX_UH),
                 ("nn_words", C.c_int32), ("output_mode", C.c_int32), ("metric", C.c_int32),
                 ("shared_forcing", C.c_int32), ("block_threads", C.c_int32), ("stages", C.c_int32),
-                ("max_registers", C.c_int32), ("nn_tensor", C.c_int32)]
+                ("max_registers", C.c_int32), ("precision", C.c_int32), ("nn_tensor", C.c_int32)]
 
 
 class RunDesc(C.Structure):
@@ -165,6 +165,7 @@ class CompiledStepper:
         spec.stages = stages
         spec.max_registers = max_registers
         spec.nn_tensor = 1 if getattr(program, "nn_tensor", False) else 0
+        spec.precision = 1 if getattr(program, "precision", "f64") == "f32" else 0
         self.spec = spec
         h = C.c_void_p()
         check(lib().hb_compile_stepper(C.byref(spec), program.body.encode(), C.byref(h)))
@@ -314,8 +315,14 @@ class B200Model:
     """Wrapper component: `B200Model(model)(input, params, config; initstates)`."""
 
     def __init__(self, component: Component, *, fast: bool = True, block_threads: int = 0, stages: int = 0,
-                 max_registers: int = 0, nn_tensor: bool = True, regconst: bool = False):
+                 max_registers: int = 0, nn_tensor: bool = True, regconst: bool = False, precision: str = "f64"):
+        """`precision="f32"` is the opt-in Float32 mode: forcing and results are float32 arrays, the body
+        computes in float (stated tolerance: DESIGN.md §5, `tests/test_gpu_parity.py::test_float32_mode`)."""
+        if precision not in ("f64", "f32"):
+            raise ValueError("precision must be 'f64' or 'f32'")
         self.component = component
+        self.precision = precision
+        self.dtype = np.float64 if precision == "f64" else np.float32
         self.fast = fast
         self.regconst = regconst
         self.nn_tensor = nn_tensor        # dense chains on the FP64 tensor pipe (DMMA) where their shape fits
@@ -357,7 +364,8 @@ class B200Model:
         if key not in self._cache:
             prog = lower_stepper(self._stepper_component(), rows=rows, objective=objective,
                                  uh_kmax=list(uh_kmax) if len(uh_kmax) else None, fast=self.fast,
-                                 holes=self._route_rows(), nn_tensor=self.nn_tensor, regconst=self.regconst)
+                                 holes=self._route_rows(), nn_tensor=self.nn_tensor, regconst=self.regconst,
+                                 precision=self.precision)
             # MLP-fused bodies keep 16+16 activations per net in registers: give them 168 (3 blocks/SM)
             maxreg = self.max_registers or (168 if prog.nn_words else 0)
             self._cache[key] = CompiledStepper(prog, metric=metric, shared_forcing=shared_forcing,
@@ -531,9 +539,11 @@ class B200Model:
             if any((c.min_value != cfg.min_value) for c in cfgs):
                 raise NotImplementedError("per-component min_value is not supported by the fused stepper")
         input = np.asarray(input)
-        if input.dtype != np.float64:
-            input = input.astype(np.float64)
+        if input.dtype != self.dtype:
+            input = input.astype(self.dtype)
         if self.route is not None:
+            if self.precision != "f64":
+                raise NotImplementedError("Float32 mode is not available for models with a HydroRoute")
             if rows is not None or out is not None:
                 raise NotImplementedError("rows= / out= are not supported for models with a HydroRoute")
             if input.ndim != 3:
@@ -559,9 +569,9 @@ class B200Model:
         R = len(prog.row_names)
         shape = (R, T) if not self.multinode else (R, N, T)
         if out is None:
-            out = np.empty(shape, dtype=np.float64, order="F")                  # memory = [T][N][R]
-        elif out.shape != shape or not out.flags.f_contiguous or out.dtype != np.float64:
-            raise ValueError("out must be a Fortran-ordered float64 array of the result shape")
+            out = np.empty(shape, dtype=self.dtype, order="F")                  # memory = [T][N][R]
+        elif out.shape != shape or not out.flags.f_contiguous or out.dtype != self.dtype:
+            raise ValueError(f"out must be a Fortran-ordered {np.dtype(self.dtype).name} array of the result shape")
         S = len(prog.state_names)
         final = np.empty((S, N), dtype=np.float64) if (return_final_states and S) else None
         elapsed = C.c_float(0.0)
@@ -672,7 +682,7 @@ class B200Model:
         if m not in METRICS:
             raise ValueError(f"Unknown metric: {metric}. Supported metrics: KGE, NSE, LogKGE, MSE")
         cfg = normalize_config(config)
-        input = np.asarray(input, dtype=np.float64)
+        input = np.asarray(input, dtype=self.dtype)
         ensemble = n_members is not None
         if ensemble and self.multinode:
             raise ValueError("ensembles are built from single-node models")
@@ -818,11 +828,11 @@ class DeviceRun:
 
     @property
     def in_bytes(self) -> int:
-        return self.T * (1 if self.ck.spec.shared_forcing else self.N) * self.n_inputs * 8
+        return self.T * (1 if self.ck.spec.shared_forcing else self.N) * self.n_inputs * (4 if self.ck.spec.precision else 8)
 
     @property
     def out_bytes(self) -> int:
-        return self.N * 8 if self.objective else self.T * self.N * self.n_rows * 8
+        return self.N * 8 if self.objective else self.T * self.N * self.n_rows * (4 if self.ck.spec.precision else 8)
 
     def launch(self, input_ptr: int, out_ptr: int, stream: Optional[int] = None, final_states_ptr: Optional[int] = None,
                timed: bool = False) -> Optional[float]:

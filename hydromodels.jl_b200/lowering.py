@@ -91,6 +91,7 @@ class StepperProgram:
     objective: bool
     stats: Dict[str, int] = field(default_factory=dict)
     nn_tensor: bool = False         # some dense chain is lowered to FP64 MMA fragments
+    precision: str = "f64"          # "f64" (reference arithmetic) | "f32" (opt-in)
 
 
 class _Builder:
@@ -248,7 +249,8 @@ def _flatten(component: Component) -> Tuple[List[Component], List[str], List[str
 
 def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None, objective: bool = False,
                   uh_kmax: Optional[Sequence[int]] = None, fast: bool = True,
-                  holes: Sequence[str] = (), nn_tensor: bool = False, regconst: bool = False) -> StepperProgram:
+                  holes: Sequence[str] = (), nn_tensor: bool = False, regconst: bool = False,
+                  precision: str = "f64") -> StepperProgram:
     """Lower a per-node model (buckets, fluxes, neural fluxes, unit hydrographs) to one stepper
     body.  `rows`: subset/order of result rows to write (default: all = the reference result);
     `objective`: emit the last output row as `hb_sim` for the fused metric reduction instead of
@@ -444,7 +446,9 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
     pro_names: Dict[int, str] = {}
 
     # dense chains whose shape fits the FP64 tensor-core fragments are contracted with DMMA
-    net_mma = [bool(nn_tensor and fast and _mma_eligible(ch)) for ch in nets]
+    if precision not in ("f64", "f32"):
+        raise LoweringError("precision must be 'f64' or 'f32'")
+    net_mma = [bool(nn_tensor and fast and precision == "f64" and _mma_eligible(ch)) for ch in nets]
 
     def nn_call(ni: int, args: List[str], arr: str) -> str:
         pre = "sNN, hb_scr, lane, " if net_mma[ni] else "sNN, "
@@ -540,6 +544,8 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
            "//@@HB:HELPERS\n" + "\n".join(helpers) + "\n" + \
            "//@@HB:PROLOGUE\n" + "\n".join("    " + s for s in pro) + "\n" + \
            "//@@HB:STEP\n" + "\n".join("        " + s for s in step) + "\n"
+    if precision == "f32":
+        body = _body_to_f32(body)
     n_ops = sum(1 for v in b.vals if v.id in live and v.mask != 0 and v.op not in ("const", "in", "param", "state")
                 and v.id not in carried)
     stats = {"step_values": n_ops, "prologue_values": len(pro), "carried": len(carried),
@@ -549,7 +555,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                           state_names=state_names, param_slots=param_slots, htype_sets=htype_sets, uh=uhs,
                           uh_kmax=list(uh_kmax), uh_htype_set=[htype_set(u) for u in uhs],
                           nn_layout=nn_layout, nn_words=sum(n for _, _, n in nn_layout), n_carry=len(carried),
-                          objective=objective, stats=stats, nn_tensor=any(net_mma))
+                          objective=objective, stats=stats, nn_tensor=any(net_mma), precision=precision)
 
 
 def _expr_with(v: Val, a: List[str], fast: bool) -> str:
@@ -768,3 +774,23 @@ def _mlp_helper_mma(idx: int, chain, offset: int, fast: bool) -> str:
     o.append("    }")
     o += ["    __syncwarp();", "    y[0] = scr[lane];", "    __syncwarp();", "}"]
     return "\n".join(o)
+
+
+_FLOAT_LIT = None
+
+
+def _body_to_f32(body: str) -> str:
+    """Opt-in Float32 mode: the generated text is type-generic except for the spelled-out `double` and the
+    floating literals — retype both (`real`, `…f`); the math helpers are overloaded on float."""
+    import re
+    global _FLOAT_LIT
+    if _FLOAT_LIT is None:
+        _FLOAT_LIT = re.compile(r"(?<![\w.])(\d+\.\d*(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)(?![\w.])")
+    out = []
+    for line in body.split("\n"):
+        if line.startswith("//@@HB:") or line.startswith("#define"):
+            out.append(line)
+            continue
+        line = re.sub(r"\bdouble\b", "real", line)
+        out.append(_FLOAT_LIT.sub(lambda m: m.group(1) + "f", line))
+    return "\n".join(out)

@@ -87,6 +87,8 @@ typedef struct {
     int32_t block_threads;       /* 0 = default (128)                                         */
     int32_t stages;              /* forcing pipeline depth in time steps, 0 = default (4)     */
     int32_t max_registers;       /* 0 = default (128); register budget per thread -> __launch_bounds__ min blocks */
+    int32_t precision;           /* 0 = Float64 (reference arithmetic), 1 = opt-in Float32: `input` and `out` are float
+                                    arrays and the body computes in float; everything else stays double */
     int32_t nn_tensor;           /* 1: the body contracts its dense layers with FP64 MMA (DMMA) fragments: MLP
                                     parameters are staged in shared memory + 1 KB scratch per warp */
 } hb_stepper_spec;
@@ -98,7 +100,7 @@ typedef struct {
     int32_t n_htype_sets;
     int64_t n_nodes;             /* N */
     int64_t n_steps;             /* T */
-    const double *input;         /* [T][N][V]  ([T][1][V] when shared_forcing)                */
+    const void *input;           /* [T][N][V]  ([T][1][V] when shared_forcing); double, or float in Float32 mode */
     const double *params;        /* flat parameter values                                     */
     int64_t n_param_values;      /* length of params                                          */
     const int32_t *param_offset; /* [n_params]  (HOST pointer in both entry points)           */
@@ -112,7 +114,7 @@ typedef struct {
     int32_t target_per_node;     /* 0: target[T] shared, 1: target[T][N]                      */
     int32_t warm_up;             /* objective uses steps warm_up..T (1-based, as the reference) */
     double min_value;            /* state clamp, > 0 (src/config.jl:46, src/solve.jl:50)      */
-    double *out;                 /* HB_OUT_ROWS: [T][N][R]                                    */
+    void *out;                   /* HB_OUT_ROWS: [T][N][R]; double, or float in Float32 mode  */
     double *objective;           /* HB_OUT_OBJECTIVE: [N]                                     */
     double *final_states;        /* [S][N] or NULL: states after step T (resume / BMI)        */
     double *uh_hist_out;         /* [sum_u (kmax_u-1)][N] or NULL                             */

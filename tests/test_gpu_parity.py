@@ -290,3 +290,28 @@ def test_graph_route_equals_grid_route():
     a, b = grid(x, p), graph(x, p)
     assert np.allclose(a, b, rtol=1e-14, atol=0)
     assert_parity(b, ho.run_route(graph, x, p))
+
+
+# ---- opt-in Float32 mode (north star: "an opt-in Float32 mode has a stated NSE/flow tolerance") ---------
+@pytest.mark.parametrize("name,T", [("exphydro", 1460), ("gr4j", 1460), ("hbv", 730), ("m50", 365)])
+def test_float32_mode(name, T):
+    """Stated tolerance of the Float32 mode against the Float64 oracle, per node over the whole series:
+    NSE(flow_f32, flow_f64) >= 1 - 1e-6, and every row's RMSE <= 1e-4 of that row's range (+1e-5 abs)."""
+    N = 256
+    model, inp, p, init = case(name, N, T)
+    ref = ho.run_model(model, inp, p, initstates=init)
+    eng = hm.B200Model(model, precision="f32")
+    got = eng(inp.astype(np.float32), p, initstates=init)
+    assert got.dtype == np.float32 and got.shape == ref.shape and np.all(np.isfinite(got))
+    flow32, flow64 = got[-1].astype(np.float64), ref[-1]
+    nse = 1 - np.sum((flow32 - flow64) ** 2, axis=1) / np.sum((flow64 - flow64.mean(axis=1, keepdims=True)) ** 2, axis=1)
+    assert nse.min() >= 1 - 1e-6, nse.min()
+    rmse = np.sqrt(np.mean((got.astype(np.float64) - ref) ** 2, axis=2))
+    span = ref.max(axis=2) - ref.min(axis=2)
+    assert np.all(rmse <= 1e-4 * span + 1e-5), float((rmse - 1e-4 * span).max())
+    # Float32 results do not depend on the I/O path either
+    os.environ["HB_DISABLE_TMA"] = "1"
+    try:
+        assert np.array_equal(eng(inp.astype(np.float32), p, initstates=init), got)
+    finally:
+        del os.environ["HB_DISABLE_TMA"]
