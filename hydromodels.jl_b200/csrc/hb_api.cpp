@@ -210,9 +210,10 @@ std::string splice(const char *tmpl, const char *body) {
 
 // ---- model object ----------------------------------------------------------------------------------
 struct hb_model_s {
-    int kind = 0;   // 0 stepper, 1 route
+    int kind = 0;   // 0 stepper, 1 route, 2 fused grid
     hb_stepper_spec spec{};
     hb_route_spec rspec{};
+    hb_grid_spec gspec{};
     std::string source;
     std::string kernel_name;
     std::vector<char> cubin;
@@ -255,6 +256,9 @@ int nvrtc_compile(const std::string &src, const std::vector<std::string> &opts, 
     for (auto &o : opts) copts.push_back(o.c_str());
     nvrtcResult r = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
     if (r != NVRTC_SUCCESS) {
+        if (const char *dump = getenv("HB_DUMP_FAILED_SOURCE")) {   // debugging aid: keep the rejected source
+            if (FILE *f = fopen(dump, "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+        }
         size_t n = 0;
         nvrtcGetProgramLogSize(prog, &n);
         std::string log(n, '\0');
@@ -787,6 +791,107 @@ int hb_route_step_device(hb_model_t m, const hb_route_desc *d, int64_t t, const 
     if ((rc = load_model(m))) return rc;
     HB_CUDA(cudaSetDevice(g_device));
     return launch_route_step(m, d, t, s_prev, s_next, q_cur, q_next, (cudaStream_t)stream);
+}
+
+// ---- fused dense-grid model -------------------------------------------------------------------------------
+int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out) {
+    if (!spec || !body || !out) return fail(HB_ERR_INVALID, "NULL argument");
+    if (spec->struct_size != (int32_t)sizeof(hb_grid_spec)) return fail(HB_ERR_INVALID, "hb_grid_spec.struct_size mismatch");
+    if (spec->n_params < 0 || spec->n_params > HB_MAX_PARAMS || spec->n_params_stepper > spec->n_params || spec->n_route_inputs < 1 ||
+        spec->n_route_inputs > 16 || spec->n_rows < 2 || spec->s_row < 0 || spec->s_row >= spec->n_rows || spec->o_row < 0 ||
+        spec->o_row >= spec->n_rows)
+        return fail(HB_ERR_INVALID, "hb_grid_spec out of range");
+    const int tc = spec->steps_per_chunk, bw = spec->block_w, bh = spec->block_h;
+    if (tc < 1 || tc > 8 || bw % 32 || bw < 32 || bh < 1 || bw * bh > 1024 || bw - 2 * tc < 1 || bh - 2 * tc < 1)
+        return fail(HB_ERR_INVALID, "bad grid tiling (steps_per_chunk %d, block %d x %d)", tc, bw, bh);
+    hb_model_s *m = new hb_model_s();
+    m->kind = 2;
+    m->gspec = *spec;
+    m->block = bw * bh;
+    m->dyn_smem = m->block * 8 + (m->block / 32) * 32 * spec->n_rows * 8 + m->block + 64;
+    char defs[768];
+    snprintf(defs, sizeof defs,
+             "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_NPS %d\n#define HB_RV %d\n"
+             "#define HB_SROW %d\n#define HB_OROW %d\n#define HB_TC %d\n#define HB_BW %d\n#define HB_BH %d\n#define HB_UHW_TOTAL 0\n"
+             "#define HB_UHH_TOTAL 0\n#define HB_NN_WORDS 0\n",
+             spec->n_inputs, spec->n_rows, spec->n_states, spec->n_params, spec->n_params_stepper, spec->n_route_inputs, spec->s_row,
+             spec->o_row, tc, bw, bh);
+    std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";
+    m->source = splice(kGridTemplate, full_body.c_str());
+    m->kernel_name = "hb_grid_chunk";
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
+    int rc = nvrtc_compile(m->source, opts, m->cubin, m->from_cache);
+    if (rc) { delete m; return rc; }
+    *out = m;
+    return HB_OK;
+}
+
+int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
+    if (!m || m->kind != 2) return fail(HB_ERR_INVALID, "not a grid model");
+    if (!d || d->struct_size != (int32_t)sizeof(hb_grid_desc)) return fail(HB_ERR_INVALID, "hb_grid_desc.struct_size mismatch");
+    const hb_grid_spec &s = m->gspec;
+    if (d->rows <= 0 || d->cols <= 0 || d->n_steps < 0 || !d->input || !d->out || !d->flwdir) return fail(HB_ERR_INVALID, "bad grid descriptor");
+    if (!(d->min_value > 0)) return fail(HB_ERR_INVALID, "min_value must be positive, got %g", d->min_value);
+    if (s.n_params > 0 && (!d->params || !d->param_offset || !d->param_mode)) return fail(HB_ERR_INVALID, "params / param tables are NULL");
+    int rc = load_model(m);
+    if (rc) return rc;
+    HB_CUDA(cudaSetDevice(g_device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t N = (int64_t)d->rows * d->cols, T = d->n_steps;
+    const size_t sb = (size_t)(s.n_states > 0 ? s.n_states : 1) * N * 8;
+    for (int k = 0; k < 2; ++k) {
+        if ((rc = ws_reserve(m->ws[k], sb))) return rc;
+        if ((rc = ws_reserve(m->ws[2 + k], (size_t)N * 8))) return rc;
+    }
+    if (d->elapsed_ms) {
+        if (!m->ev0) { HB_CUDA(cudaEventCreate(&m->ev0)); HB_CUDA(cudaEventCreate(&m->ev1)); }
+        HB_CUDA(cudaEventRecord(m->ev0, st));
+    }
+    const int tc = s.steps_per_chunk;
+    const unsigned gx = (unsigned)((d->cols + (s.block_w - 2 * tc) - 1) / (s.block_w - 2 * tc));
+    const unsigned gy = (unsigned)((d->rows + (s.block_h - 2 * tc) - 1) / (s.block_h - 2 * tc));
+    const void *su_in = d->init_bucket, *rs_in = d->init_route;
+    int half = 0;
+    const int np = s.n_params > 0 ? s.n_params : 1;
+    for (int64_t t0 = 0; t0 < T; t0 += tc) {
+        // HbGridArgs mirror (templates/grid.cu): 9 pointers, 2 i64, 3 int (+pad), 1 double, int tables
+        unsigned char buf[9 * 8 + 2 * 8 + 16 + 8 + 8 * HB_MAX_PARAMS + 16];
+        memset(buf, 0, sizeof buf);
+        size_t o = 0;
+        auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
+        void *su_out = m->ws[half].p, *rs_out = m->ws[2 + half].p;
+        const void *ptrs[9] = {d->input, d->out, d->params, d->htypes, su_in, su_out, rs_in, rs_out, d->flwdir};
+        put(ptrs, sizeof ptrs);
+        put(&N, 8);
+        put(&t0, 8);
+        int ns = (int)((T - t0) < tc ? (T - t0) : tc), rows = d->rows, cols = d->cols, pad = 0;
+        put(&ns, 4);
+        put(&rows, 4);
+        put(&cols, 4);
+        put(&pad, 4);
+        double minv = d->min_value;
+        put(&minv, 8);
+        std::vector<int> tmp(np, 0);
+        for (int j = 0; j < s.n_params; ++j) tmp[j] = d->param_offset[j];
+        put(tmp.data(), 4 * np);
+        for (int j = 0; j < s.n_params; ++j) tmp[j] = d->param_mode[j];
+        put(tmp.data(), 4 * np);
+        void *params[1] = {buf};
+        HB_DRV(g_drv.LaunchKernel(m->func, gx, gy, 1, m->block, 1, 1, m->dyn_smem, (CUstream)st, params, nullptr));
+        su_in = su_out;
+        rs_in = rs_out;
+        half ^= 1;
+    }
+    if (T > 0) {
+        if (d->final_bucket && s.n_states > 0) HB_CUDA(cudaMemcpyAsync(d->final_bucket, su_in, (size_t)s.n_states * N * 8, cudaMemcpyDeviceToDevice, st));
+        if (d->final_route) HB_CUDA(cudaMemcpyAsync(d->final_route, rs_in, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    if (d->elapsed_ms) {
+        HB_CUDA(cudaEventRecord(m->ev1, st));
+        HB_CUDA(cudaEventSynchronize(m->ev1));
+        HB_CUDA(cudaEventElapsedTime(d->elapsed_ms, m->ev0, m->ev1));
+    }
+    return HB_OK;
 }
 
 // ---- memory helpers ----------------------------------------------------------------------------------

@@ -57,6 +57,7 @@ struct HbRouteArgs {
 
 extern "C" __global__ void __launch_bounds__(HB_BLOCK) hb_route_step(const __grid_constant__ HbRouteArgs a) {
     const i64 n = (i64)blockIdx.x * HB_BLOCK + threadIdx.x;
+    hb_math_init();   // exp table -> shared memory (block barrier inside)
     if (n >= a.N) return;
     double hb_p[HB_ARR(HB_NP)];
 #pragma unroll

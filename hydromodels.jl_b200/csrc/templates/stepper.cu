@@ -147,6 +147,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     const i64 n0w = n - lane;
     const bool valid = n < a.N;
     const bool full_warp = (n0w + 32) <= a.N;
+    hb_math_init();   // exp table -> shared memory (block barrier inside)
 
     // shared-memory carve-up: [MLP params + per-warp MMA scratch][per-warp forcing ring][per-warp result tiles][mbarriers]
 #if HB_NN_MMA
@@ -206,13 +207,6 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
 #if HB_MODE == 1
     // objective accumulators (shifted sums; metrics of …OptimizationExt.jl:34-68)
     double q_n = 0.0, q_so = 0.0, q_ss = 0.0, q_soo = 0.0, q_sss = 0.0, q_sos = 0.0, q_sse = 0.0, q_shift = 0.0;
-#endif
-
-#ifdef HB_REGCONST
-    const HbExpK hb_K = hb_expk_load();    // exp constants resident in registers for the whole run
-#define hb_step(x) hb_step_k((x), hb_K)
-#define hb_exp(x) hb_exp_k((x), hb_K)
-#define hb_tanh(x) hb_tanh_k((x), hb_K)
 #endif
 
     //@@HB:PROLOGUE

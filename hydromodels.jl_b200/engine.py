@@ -18,7 +18,7 @@ import numpy as np
 
 from .components import (Component, ConstantInterpolation, D8_CODES, GridAggregation, HydroBucket, HydroConfig, HydroFlux,
                          HydroModel, HydroRoute, LinearInterpolation, SolverType, UnitHydrograph, normalize_config)
-from .lowering import LoweringError, RouteProgram, StepperProgram, lower_route, lower_stepper
+from .lowering import GridProgram, LoweringError, RouteProgram, StepperProgram, lower_grid, lower_route, lower_stepper
 from .symbolic import evaluate_np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -74,6 +74,22 @@ class RouteDesc(C.Structure):
                 ("final_states", C.c_void_p), ("elapsed_ms", C.c_void_p)]
 
 
+class GridSpec(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_inputs", C.c_int32), ("n_rows", C.c_int32), ("n_states", C.c_int32),
+                ("n_params", C.c_int32), ("n_params_stepper", C.c_int32), ("n_route_inputs", C.c_int32),
+                ("s_row", C.c_int32), ("o_row", C.c_int32), ("steps_per_chunk", C.c_int32), ("block_w", C.c_int32),
+                ("block_h", C.c_int32)]
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_htype_sets", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("n_steps", C.c_int64), ("input", C.c_void_p), ("out", C.c_void_p), ("params", C.c_void_p),
+                ("n_param_values", C.c_int64), ("param_offset", C.c_void_p), ("param_mode", C.c_void_p),
+                ("htypes", C.c_void_p), ("init_bucket", C.c_void_p), ("init_route", C.c_void_p), ("flwdir", C.c_void_p),
+                ("min_value", C.c_double), ("final_bucket", C.c_void_p), ("final_route", C.c_void_p),
+                ("elapsed_ms", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -96,6 +112,8 @@ def lib():
         "hb_model_info": [C.c_void_p, C.POINTER(KernelInfo)], "hb_free_model": [C.c_void_p],
         "hb_run": [C.c_void_p, C.POINTER(RunDesc)], "hb_run_device": [C.c_void_p, C.POINTER(RunDesc), C.c_void_p],
         "hb_compile_route": [C.POINTER(RouteSpec), C.c_char_p, C.POINTER(C.c_void_p)],
+        "hb_compile_grid": [C.POINTER(GridSpec), C.c_char_p, C.POINTER(C.c_void_p)],
+        "hb_run_grid_device": [C.c_void_p, C.POINTER(GridDesc), C.c_void_p],
         "hb_run_route_device": [C.c_void_p, C.POINTER(RouteDesc), C.c_void_p],
         "hb_route_step_device": [C.c_void_p, C.POINTER(RouteDesc), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p],
@@ -980,3 +998,119 @@ class RoutedDeviceRun:
     def launch(self, input_ptr: int, rec_ptr: int, stream: Optional[int] = None):
         self.stepper.launch(input_ptr, rec_ptr, stream)
         self.stage.launch(rec_ptr, stream)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused dense-grid path (templates/grid.cu): buckets + D8 route in one pass, records written once
+# ---------------------------------------------------------------------------------------------------
+def dense_grid_shape(aggr, n_nodes: int) -> Optional[Tuple[int, int]]:
+    """(rows, cols) when the node list is the complete grid in row-major order, else None."""
+    if not isinstance(aggr, GridAggregation):
+        return None
+    R, Cc = aggr.flwdir.shape
+    if R * Cc != n_nodes or len(aggr.positions) != n_nodes:
+        return None
+    rr, cc = np.divmod(np.arange(n_nodes), Cc)
+    if np.array_equal(aggr.positions[:, 0], rr + 1) and np.array_equal(aggr.positions[:, 1], cc + 1):
+        return R, Cc
+    return None
+
+
+class CompiledGrid:
+    def __init__(self, program: GridProgram, steps_per_chunk: int = 2, block_w: int = 32, block_h: int = 16):
+        self.program = program
+        sp, rp = program.stepper, program.route
+        spec = GridSpec(C.sizeof(GridSpec), len(sp.input_names), len(program.row_names), len(sp.state_names),
+                        len(sp.param_slots) + len(rp.param_slots), len(sp.param_slots), len(rp.input_names),
+                        program.s_row, program.o_row, steps_per_chunk, block_w, block_h)
+        self.spec = spec
+        h = C.c_void_p()
+        check(lib().hb_compile_grid(C.byref(spec), program.body.encode(), C.byref(h)))
+        self.handle = h
+
+    def source(self) -> str:
+        s = C.c_char_p()
+        n = C.c_int64()
+        check(lib().hb_model_source(self.handle, C.byref(s), C.byref(n)))
+        return s.value.decode()
+
+    def info(self) -> Dict[str, int]:
+        k = KernelInfo()
+        check(lib().hb_model_info(self.handle, C.byref(k)))
+        return {f: getattr(k, f) for f, _ in KernelInfo._fields_}
+
+    def __del__(self):
+        try:
+            if self.handle and _lib is not None:
+                _lib.hb_free_model(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class GridDeviceRun:
+    """Device-resident run of `[buckets…, HydroRoute]` on a dense D8 grid with the fused kernel."""
+
+    def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None,
+                 steps_per_chunk: int = 2, block_w: int = 32, block_h: int = 16):
+        if eng.route is None or eng.lumped is None:
+            raise ValueError("GridDeviceRun needs per-node components followed by a HydroRoute")
+        shape = dense_grid_shape(eng.route.aggr, N)
+        if shape is None:
+            raise ValueError("the fused grid kernel needs the complete grid in row-major node order")
+        self.rows, self.cols = shape
+        self.cfg = normalize_config(config)
+        _check_config(self.cfg, T)
+        rows = eng.component.var_names
+        key = ("grid", steps_per_chunk, block_w, block_h)
+        if key not in eng._cache:
+            eng._cache[key] = CompiledGrid(lower_grid(eng.lumped, eng.route, rows, fast=eng.fast), steps_per_chunk, block_w, block_h)
+        self.ck = eng._cache[key]
+        sp, rp = self.ck.program.stepper, self.ck.program.route
+        flat1, off1, mode1, ht1, _, _, _ = eng.prepare(sp, params, N)
+        stage = RouteStage(eng, N, T, params, self.cfg, rows, None if initstates is None else initstates.get(eng.route.state_names[0]))
+        flat2 = stage.bufs[0].to_host((stage.n_param_values,))
+        n_sets1 = 0 if ht1 is None else ht1.shape[0]
+        flat = np.concatenate([flat1, flat2])
+        p_off = np.concatenate([off1[:len(sp.param_slots)], stage.p_off[:len(rp.param_slots)] + flat1.size]).astype(np.int32)
+        # the route's gather modes address its own htypes set, appended after the stepper's sets
+        mode2 = np.where(stage.p_mode[:len(rp.param_slots)] >= 2, stage.p_mode[:len(rp.param_slots)] + n_sets1, stage.p_mode[:len(rp.param_slots)])
+        p_mode = np.concatenate([mode1[:len(sp.param_slots)], mode2]).astype(np.int32)
+        h_route = np.asarray(eng.route.htypes, dtype=np.int64) - 1
+        hts = ([ht1] if ht1 is not None else []) + [h_route.astype(np.int32)[None, :]]
+        htypes = np.ascontiguousarray(np.concatenate(hts, axis=0))
+        if p_off.size == 0:
+            p_off, p_mode = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        self._host = (np.ascontiguousarray(p_off), np.ascontiguousarray(p_mode))
+        self.n_sets = htypes.shape[0]
+        self.n_param_values = flat.size
+        self.bufs = {"params": DeviceBuffer.from_host(flat), "htypes": DeviceBuffer.from_host(htypes),
+                     "flw": DeviceBuffer.from_host(np.where(np.isin(eng.route.aggr.flwdir, D8_CODES), eng.route.aggr.flwdir, 0).astype(np.uint8))}
+        init = eng._initstates(sp, None if initstates is None else {k: v for k, v in initstates.items()
+                                                                     if k != eng.route.state_names[0]}, N)
+        if init is not None:
+            self.bufs["init"] = DeviceBuffer.from_host(init)
+        if stage.dinit is not None:
+            self.bufs["rinit"] = DeviceBuffer.from_host(stage.dinit.to_host((N,)))
+        stage.free()
+        self.N, self.T, self.n_rows = int(N), int(T), len(rows)
+        self.in_bytes, self.out_bytes = T * N * len(sp.input_names) * 8, T * N * len(rows) * 8
+
+    def launch(self, input_ptr: int, rec_ptr: int, stream: Optional[int] = None, timed: bool = False) -> Optional[float]:
+        d = GridDesc()
+        d.struct_size = C.sizeof(GridDesc)
+        d.n_htype_sets = self.n_sets
+        d.rows, d.cols, d.n_steps = self.rows, self.cols, self.T
+        d.input, d.out = input_ptr, rec_ptr
+        d.params, d.n_param_values = self.bufs["params"].ptr, self.n_param_values
+        d.param_offset, d.param_mode = _ptr(self._host[0]), _ptr(self._host[1])
+        d.htypes = self.bufs["htypes"].ptr
+        d.init_bucket = self.bufs["init"].ptr if "init" in self.bufs else None
+        d.init_route = self.bufs["rinit"].ptr if "rinit" in self.bufs else None
+        d.flwdir = self.bufs["flw"].ptr
+        d.min_value = self.cfg.min_value
+        el = C.c_float(0.0)
+        if timed:
+            d.elapsed_ms = C.cast(C.byref(el), C.c_void_p)
+        check(lib().hb_run_grid_device(self.ck.handle, C.byref(d), stream))
+        return el.value if timed else None

@@ -540,7 +540,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
 
     helpers = [(_mlp_helper_mma if net_mma[i] else _mlp_helper)(i, ch, off, fast)
                for i, (ch, (_, off, _)) in enumerate(zip(nets, nn_layout))]
-    body = "//@@HB:DEFINES\n" + f"#define HB_NC {len(carried)}\n" + ("#define HB_REGCONST 1\n" if (regconst and not nets) else "") + \
+    body = "//@@HB:DEFINES\n" + f"#define HB_NC {len(carried)}\n" + \
            "//@@HB:HELPERS\n" + "\n".join(helpers) + "\n" + \
            "//@@HB:PROLOGUE\n" + "\n".join("    " + s for s in pro) + "\n" + \
            "//@@HB:STEP\n" + "\n".join("        " + s for s in step) + "\n"
@@ -794,3 +794,46 @@ def _body_to_f32(body: str) -> str:
         line = re.sub(r"\bdouble\b", "real", line)
         out.append(_FLOAT_LIT.sub(lambda m: m.group(1) + "f", line))
     return "\n".join(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-cell components + HydroRoute on a dense grid → body of templates/grid.cu
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class GridProgram:
+    body: str
+    stepper: StepperProgram          # the per-cell part (rows = all model rows, the route's are holes)
+    route: RouteProgram
+    row_names: List[str]
+    s_row: int
+    o_row: int
+
+
+def lower_grid(lumped: HydroModel, route: HydroRoute, row_names: Sequence[str], *, fast: bool = True) -> GridProgram:
+    """Fuse the per-cell step (`lower_stepper`) and the route's two device functions (`lower_route`) into
+    one body: the route's inputs are taken from the rows the per-cell step has just produced."""
+    holes = route.state_names + route.output_names
+    sp = lower_stepper(lumped, rows=list(row_names), fast=fast, holes=holes)
+    if sp.uh or sp.nn_layout:
+        raise LoweringError("the fused grid kernel supports bucket / flux components only")
+    rp = lower_route(route, fast=fast)
+    missing = [nm for nm in rp.input_names if nm not in row_names]
+    if missing:
+        raise LoweringError(f"route inputs {missing} are not rows of the model")
+    sel = "0"
+    for v in reversed(range(len(rp.input_names))):
+        sel = f"((v) == {v} ? hb_out[{list(row_names).index(rp.input_names[v])}] : {sel})"
+    secs: Dict[str, List[str]] = {}
+    cur = None
+    for src in (sp.body, rp.body):
+        for line in src.split("\n"):
+            if line.startswith("//@@HB:"):
+                cur = line[7:].strip()
+                secs.setdefault(cur, [])
+            elif cur is not None:
+                secs[cur].append(line)
+    secs.setdefault("DEFINES", []).append(f"#define HB_ROUTE_IN(v) {sel}")
+    body = "".join(f"//@@HB:{k}\n" + "\n".join(v) + "\n" for k, v in secs.items())
+    return GridProgram(body=body, stepper=sp, route=rp, row_names=list(row_names),
+                       s_row=list(row_names).index(route.state_names[0]),
+                       o_row=list(row_names).index(route.output_names[0]))

@@ -201,6 +201,44 @@ int hb_run_route_device(hb_model_t m, const hb_route_desc *desc, void *stream);
 int hb_route_step_device(hb_model_t m, const hb_route_desc *desc, int64_t t, const double *s_prev, double *s_next,
                          const double *q_cur, double *q_next, void *stream);
 
+/* ---- fused dense-grid model: per-cell buckets + D8 HydroRoute in one pass (templates/grid.cu) ------- */
+typedef struct {
+    int32_t struct_size;        /* sizeof(hb_grid_spec) */
+    int32_t n_inputs;           /* V */
+    int32_t n_rows;             /* R: all model rows (bucket rows + the route's state and outflow) */
+    int32_t n_states;           /* S: bucket states (the route state is separate) */
+    int32_t n_params;           /* all parameter slots: per-cell part first, then the route's */
+    int32_t n_params_stepper;   /* slots of the per-cell part */
+    int32_t n_route_inputs;
+    int32_t s_row, o_row;       /* record rows of the route state / outflow */
+    int32_t steps_per_chunk;    /* T_c = halo depth (1..4) */
+    int32_t block_w, block_h;   /* region (tile + halo) in cells; block_w % 32 == 0, block_w*block_h <= 512 */
+} hb_grid_spec;
+
+typedef struct {
+    int32_t struct_size;        /* sizeof(hb_grid_desc) */
+    int32_t n_htype_sets;
+    int32_t rows, cols;         /* grid shape; node n = r * cols + c (0-based), N = rows * cols */
+    int64_t n_steps;            /* T */
+    const double *input;        /* DEVICE [T][N][V] */
+    double *out;                /* DEVICE [T][N][R] */
+    const double *params;       /* DEVICE flat values */
+    int64_t n_param_values;
+    const int32_t *param_offset;/* HOST [n_params] */
+    const int32_t *param_mode;  /* HOST [n_params] */
+    const int32_t *htypes;      /* DEVICE [n_htype_sets][N] 0-based or NULL */
+    const double *init_bucket;  /* DEVICE [S][N] or NULL */
+    const double *init_route;   /* DEVICE [N] or NULL */
+    const uint8_t *flwdir;      /* DEVICE [rows][cols] D8 codes */
+    double min_value;
+    double *final_bucket;       /* DEVICE [S][N] or NULL */
+    double *final_route;        /* DEVICE [N] or NULL */
+    float *elapsed_ms;          /* optional HOST pointer */
+} hb_grid_desc;
+
+int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out);
+int hb_run_grid_device(hb_model_t m, const hb_grid_desc *desc, void *stream);   /* ceil(T / T_c) launches */
+
 /* ---- memory helpers (so a host without a CUDA binding can own device / pinned buffers) ---- */
 int hb_malloc_device(void **ptr, int64_t bytes);
 int hb_free_device(void *ptr);
