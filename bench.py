@@ -166,7 +166,10 @@ def main():
     ap.add_argument("--block", type=int, default=0, help="tuning: threads per block of the stepper")
     ap.add_argument("--stages", type=int, default=0, help="tuning: forcing pipeline depth (time steps)")
     ap.add_argument("--maxreg", type=int, default=0, help="tuning: register budget per thread")
-    ap.add_argument("--regconst", type=int, default=-1, help="tuning: exp constants resident in registers (0/1)")
+    ap.add_argument("--grid-tc", type=int, default=2, help="fused grid kernel: time steps per launch (= halo depth)")
+    ap.add_argument("--grid-bw", type=int, default=32, help="fused grid kernel: region width (cells)")
+    ap.add_argument("--grid-bh", type=int, default=32, help="fused grid kernel: region height (cells)")
+    ap.add_argument("--fused-grid", action="store_true", help="grid workload: experimental single-pass kernel (grid.cu)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -253,14 +256,18 @@ def main():
                 def launch(self, ip, op, stream=None):
                     sharded.launch(ip, op)
             run = _Run()
-        else:
+        elif not args.fused_grid:
             run = RoutedDeviceRun(eng, N, T, p, initstates=init)
+        else:
+            from hydromodels_jl_b200.engine import GridDeviceRun
+            run = GridDeviceRun(eng, N, T, p, initstates=init, steps_per_chunk=args.grid_tc, block_w=args.grid_bw,
+                                block_h=args.grid_bh)
+            eng.last_kernel = run.ck
         d_in = device_forcing(torch, "exphydro", N, T, sy.SEED + 17 * rank)
         d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
     else:
         model, p, init = build_problem(hm, sy, model_name, n0, N, T)
-        kw = {} if args.regconst < 0 else {"regconst": bool(args.regconst)}
-        eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg, **kw)
+        eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
         run = DeviceRun(eng, N, T, p, initstates=init)
         d_in = device_forcing(torch, model_name, N, T, sy.SEED + 17 * rank)
         d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
@@ -302,10 +309,13 @@ def main():
     # roofline of the dominant (only) kernel: algorithmic bytes per launch / mean launch time
     peak, peak_src = peaks()
     bytes_per_unit = 8 * (v_of + rows_of)
-    launches_per_step = (T + 2) if model_name == "exphydro_grid" else 1
+    launches_per_step = 1
+    if model_name == "exphydro_grid":
+        launches_per_step = (T + 2) if (not args.fused_grid or world > 1) else -(-T // args.grid_tc)
     k_ms = float(np.mean(kernel_ms))
     achieved = bytes_per_unit * N * T / (k_ms * 1e-3) / 1e9
-    kname = {"exphydro_grid": "hb_stepper + T x hb_route_step", "hbv_ensemble": "hb_stepper (objective mode)"}.get(model_name, "hb_stepper")
+    kname = {"exphydro_grid": "hb_stepper + T x hb_route_step" if (not args.fused_grid or world > 1) else "hb_grid_chunk",
+             "hbv_ensemble": "hb_stepper (objective mode)"}.get(model_name, "hb_stepper")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_basin_timestep": bytes_per_unit, "kernel_ms": k_ms,

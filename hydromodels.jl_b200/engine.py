@@ -333,7 +333,7 @@ class B200Model:
     """Wrapper component: `B200Model(model)(input, params, config; initstates)`."""
 
     def __init__(self, component: Component, *, fast: bool = True, block_threads: int = 0, stages: int = 0,
-                 max_registers: int = 0, nn_tensor: bool = True, regconst: bool = False, precision: str = "f64"):
+                 max_registers: int = 0, nn_tensor: bool = True, precision: str = "f64"):
         """`precision="f32"` is the opt-in Float32 mode: forcing and results are float32 arrays, the body
         computes in float (stated tolerance: DESIGN.md §5, `tests/test_gpu_parity.py::test_float32_mode`)."""
         if precision not in ("f64", "f32"):
@@ -342,8 +342,10 @@ class B200Model:
         self.precision = precision
         self.dtype = np.float64 if precision == "f64" else np.float32
         self.fast = fast
-        self.regconst = regconst
         self.nn_tensor = nn_tensor        # dense chains on the FP64 tensor pipe (DMMA) where their shape fits
+        # [buckets…, HydroRoute] on a dense D8 grid: single-pass fused kernel (templates/grid.cu).  Opt-in: at
+        # 2048² it measures 16.5-21.9 ms vs 17.5 ms for the generic stepper + per-step route path
+        self.use_fused_grid = False
         self.block_threads, self.stages, self.max_registers = block_threads, stages, max_registers
         self._cache: Dict[Tuple, CompiledStepper] = {}
         self.last_kernel: Optional[CompiledStepper] = None
@@ -382,7 +384,7 @@ class B200Model:
         if key not in self._cache:
             prog = lower_stepper(self._stepper_component(), rows=rows, objective=objective,
                                  uh_kmax=list(uh_kmax) if len(uh_kmax) else None, fast=self.fast,
-                                 holes=self._route_rows(), nn_tensor=self.nn_tensor, regconst=self.regconst,
+                                 holes=self._route_rows(), nn_tensor=self.nn_tensor,
                                  precision=self.precision)
             # MLP-fused bodies keep 16+16 activations per net in registers: give them 168 (3 blocks/SM)
             maxreg = self.max_registers or (168 if prog.nn_words else 0)
@@ -643,6 +645,22 @@ class B200Model:
                 if v.size != len(state_names) * N:
                     raise ValueError(f"initstates has {v.size} elements, expected {len(state_names)}*{N}")
                 init_all = {s: v[i * N:(i + 1) * N] for i, s in enumerate(state_names)}
+        # dense row-major grid, bucket/flux components only: fused single-pass kernel (templates/grid.cu)
+        if (self.lumped is not None and not extra and self.use_fused_grid and dense_grid_shape(route.aggr, N) is not None
+                and not self._has_uh() and not self.lumped.nn_names and N * T > 0):
+            run = GridDeviceRun(self, N, T, params, config=cfg, initstates=init_all)
+            inp = input if input.flags.f_contiguous else np.asfortranarray(input)
+            din = DeviceBuffer.from_host(inp.ravel(order="K"))
+            rec = DeviceBuffer(T * N * R * 8)
+            ms = run.launch(din.ptr, rec.ptr, None, timed=True)
+            full = rec.to_host((R, N, T), order="F")
+            din.free()
+            rec.free()
+            if timing is not None:
+                timing["kernel_ms"] = ms
+            if return_final_states:
+                return full, np.ascontiguousarray(full[:len(state_names), :, -1])
+            return full
         rec = DeviceBuffer(T * N * Rr * 8)
         kernel_ms = 0.0
         if self.lumped is not None:
@@ -1017,7 +1035,7 @@ def dense_grid_shape(aggr, n_nodes: int) -> Optional[Tuple[int, int]]:
 
 
 class CompiledGrid:
-    def __init__(self, program: GridProgram, steps_per_chunk: int = 2, block_w: int = 32, block_h: int = 16):
+    def __init__(self, program: GridProgram, steps_per_chunk: int = 2, block_w: int = 32, block_h: int = 32):
         self.program = program
         sp, rp = program.stepper, program.route
         spec = GridSpec(C.sizeof(GridSpec), len(sp.input_names), len(program.row_names), len(sp.state_names),
@@ -1052,7 +1070,7 @@ class GridDeviceRun:
     """Device-resident run of `[buckets…, HydroRoute]` on a dense D8 grid with the fused kernel."""
 
     def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None,
-                 steps_per_chunk: int = 2, block_w: int = 32, block_h: int = 16):
+                 steps_per_chunk: int = 2, block_w: int = 32, block_h: int = 32):
         if eng.route is None or eng.lumped is None:
             raise ValueError("GridDeviceRun needs per-node components followed by a HydroRoute")
         shape = dense_grid_shape(eng.route.aggr, N)

@@ -249,8 +249,7 @@ def _flatten(component: Component) -> Tuple[List[Component], List[str], List[str
 
 def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None, objective: bool = False,
                   uh_kmax: Optional[Sequence[int]] = None, fast: bool = True,
-                  holes: Sequence[str] = (), nn_tensor: bool = False, regconst: bool = False,
-                  precision: str = "f64") -> StepperProgram:
+                  holes: Sequence[str] = (), nn_tensor: bool = False, precision: str = "f64") -> StepperProgram:
     """Lower a per-node model (buckets, fluxes, neural fluxes, unit hydrographs) to one stepper
     body.  `rows`: subset/order of result rows to write (default: all = the reference result);
     `objective`: emit the last output row as `hb_sim` for the fused metric reduction instead of

@@ -315,3 +315,31 @@ def test_float32_mode(name, T):
         assert np.array_equal(eng(inp.astype(np.float32), p, initstates=init), got)
     finally:
         del os.environ["HB_DISABLE_TMA"]
+
+
+# ---- fused dense-grid kernel (templates/grid.cu) ----------------------------------------------------------
+@pytest.mark.parametrize("R,Cc,T", [(5, 4, 7), (40, 70, 33), (61, 29, 20)])
+def test_fused_grid_kernel_matches_oracle_and_generic_path(R, Cc, T):
+    """Dense row-major grids can take the single-pass kernel (tile + halo, T_c steps per launch); it must agree with
+    the oracle and, bit for bit, with the generic stepper + per-step route path — including tiles cut by
+    the grid border, chunk remainders (T not a multiple of T_c) and sinks / off-grid directions."""
+    rng = np.random.default_rng(R * 1000 + Cc)
+    flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128, 0, 5], size=(R, Cc))
+    rr, cc = np.divmod(np.arange(R * Cc), Cc)
+    pos = np.stack([rr + 1, cc + 1], axis=1)
+    N = R * Cc
+    model = hm.models.exphydro_grid(flw, pos)
+    inp = sy.forcing("exphydro", 0, N, T)
+    p = {"params": dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))}
+    init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 2, N))
+    eng = hm.B200Model(model)
+    eng.use_fused_grid = True                     # opt-in path
+    fused = eng(inp, p, initstates=init)
+    assert any(k[0] == "grid" for k in eng._cache if isinstance(k, tuple) and k and k[0] == "grid")
+    assert_parity(fused, ho.run_model(model, inp, p, initstates=init))
+    eng2 = hm.B200Model(model)
+    eng2.use_fused_grid = False
+    generic = eng2(inp, p, initstates=init)
+    assert np.array_equal(fused, generic)
+    # default (zero) initial states
+    assert np.array_equal(eng(inp, p), eng2(inp, p))
