@@ -114,3 +114,42 @@ int hb_fill_device(double *p, int64_t n, double v, void *stream) {
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// SparseRouteConvolution (/root/reference/src/route.jl:593-610): out[dest, :] += causal_conv(in[source, :],
+// weights[row, :]) over the nnz (dest, source) rows of a SparseRouteKernel — IRF river routing.
+// Rows are grouped by destination (CSR, original row order kept inside a group, so the summation order is
+// the reference's); one thread per (destination, time step): out[t][d] = sum_rows sum_{lag<=min(t,H)}
+// w[row][lag] * in[t-lag+1][src(row)].  Layouts are the Julia column-major arrays: in [T][n_in],
+// out [T][n_out], weights [H][nnz] (CSR-ordered rows).
+// =============================================================================================
+namespace {
+__global__ void __launch_bounds__(256) hb_sparse_conv_kernel(int n_out, int n_in, long long T, int H, long long nnz,
+                                                             const int *__restrict__ row_ptr, const int *__restrict__ src,
+                                                             const double *__restrict__ w, const double *__restrict__ in,
+                                                             double *__restrict__ out) {
+    const int d = blockIdx.x * 32 + (threadIdx.x & 31);
+    const long long t = (long long)blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (d >= n_out || t >= T) return;
+    double total = 0.0;
+    const int upper = (int)((t + 1) < H ? (t + 1) : H);
+    for (int row = row_ptr[d]; row < row_ptr[d + 1]; ++row) {
+        const double *x = in + src[row];
+        const double *wr = w + row;
+        double acc = 0.0;
+        for (int lag = 0; lag < upper; ++lag) acc += wr[(long long)lag * nnz] * x[(t - lag) * n_in];   // _causal_conv_add!
+        total += acc;
+    }
+    out[t * n_out + d] = total;
+}
+}  // namespace
+
+extern "C" int hb_sparse_route_conv_device(int n_out, int n_in, int64_t T, int H, int64_t nnz, const int32_t *row_ptr,
+                                           const int32_t *src, const double *weights, const double *input, double *out,
+                                           void *stream) {
+    if (n_out <= 0 || n_in <= 0 || T < 0 || H <= 0 || nnz < 0 || !row_ptr || !out) return HB_ERR_INVALID;
+    if (T == 0) return HB_OK;
+    dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((T + 7) / 8));
+    hb_sparse_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}

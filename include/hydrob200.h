@@ -239,6 +239,13 @@ typedef struct {
 int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out);
 int hb_run_grid_device(hb_model_t m, const hb_grid_desc *desc, void *stream);   /* ceil(T / T_c) launches */
 
+/* ---- IRF river routing: SparseRouteConvolution (/root/reference/src/route.jl:593-610) -------------------
+ * out[t][d] = sum over the kernel rows of destination d (CSR `row_ptr`, original row order) of the causal
+ * convolution of in[.][src[row]] with weights[.][row].  DEVICE pointers; in [T][n_in], out [T][n_out],
+ * weights [H][nnz] with rows in CSR order. */
+int hb_sparse_route_conv_device(int n_out, int n_in, int64_t n_steps, int horizon, int64_t nnz, const int32_t *row_ptr,
+                                const int32_t *src, const double *weights, const double *input, double *out, void *stream);
+
 /* ---- memory helpers (so a host without a CUDA binding can own device / pinned buffers) ---- */
 int hb_malloc_device(void **ptr, int64_t bytes);
 int hb_free_device(void *ptr);

@@ -343,3 +343,31 @@ def test_fused_grid_kernel_matches_oracle_and_generic_path(R, Cc, T):
     assert np.array_equal(fused, generic)
     # default (zero) initial states
     assert np.array_equal(eng(inp, p), eng2(inp, p))
+
+
+# ---- IRF river routing: SparseRouteConvolution -----------------------------------------
+def test_sparse_route_convolution_matches_oracle():
+    """`/root/reference/src/route.jl:593-610`: the reference has no test or fixture for this operator, so the
+    parity is oracle-pinned; the oracle itself is checked against `np.convolve` in tests/test_irf_cpu.py."""
+    from hydromodels_jl_b200 import irf
+    rng = np.random.default_rng(3)
+    n, H, T = 60, 16, 200
+    A = np.zeros((n, n))
+    for i in range(n - 1):
+        A[rng.integers(i + 1, n), i] = 1.0
+    route = irf.RouteIRF(["k"], lambda p, dt, h: (1 - np.exp(-dt / p[0])) * np.exp(-np.arange(h) * dt / p[0]))
+    kernels = irf.build_irf_kernels(route, rng.uniform(0.5, 3.0, (n, 1)), horizon=H)
+    K = irf.aggregate_route_kernel(A, kernels, topo_order=irf.topological_order(A), horizon=H)
+    conv = irf.SparseRouteConvolution(K)
+    x = np.abs(rng.normal(size=(n, T)))
+    got = conv(x)
+    ref = ho.sparse_route_convolution(K.indices, K.weights, K.n_out, K.n_in, x)
+    assert got.shape == (n, T)
+    assert_parity(got, ref)
+    assert_parity(conv(x[0]) if n == 1 else conv(x)[:1], ref[:1])
+    with pytest.raises(ValueError, match="does not match kernel.n_in"):
+        conv(x[:5])
+    # T shorter than the horizon, and a kernel with an empty destination
+    K2 = irf.SparseRouteKernel(np.array([[1, 2], [3, 1], [3, 2]]), rng.random((3, 8)), 3, 2)
+    x2 = rng.random((2, 5))
+    assert_parity(irf.SparseRouteConvolution(K2)(x2), ho.sparse_route_convolution(K2.indices, K2.weights, 3, 2, x2))
