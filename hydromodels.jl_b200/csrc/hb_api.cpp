@@ -511,6 +511,7 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
              m->uhh_total, spec->nn_words, spec->output_mode, spec->metric, spec->shared_forcing ? 1 : 0, m->block, stages, minblocks,
              spec->nn_tensor ? 1 : 0, spec->precision ? 1 : 0);
     std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";   // body may append to DEFINES (e.g. HB_NC)
+    if (const char *x = getenv("HB_EXTRA_DEFINES")) full_body = std::string("//@@HB:DEFINES\n") + x + "\n" + full_body;   // tuning experiments
     m->source = splice(kStepperTemplate, full_body.c_str());
     m->kernel_name = "hb_stepper";
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};

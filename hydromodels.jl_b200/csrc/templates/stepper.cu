@@ -175,9 +175,14 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     // warp-uniform choice of the I/O path
     const bool tma_in = (HB_SHARED_FORCING == 0) && (HB_V > 0) && a.tma_in_ok && full_warp;
     const bool tma_out = (HB_MODE == 0) && (HB_R > 0) && a.tma_out_ok && full_warp;
-    // Lanes past the last node of a ragged warp stay alive (warp-collective MMA / shuffles in the body
-    // need all 32 lanes): they shadow the last node (`nc`) and never store.
+    // Tensor-path bodies contain warp-collective MMAs / shuffles: lanes past the last node of a ragged warp
+    // stay alive, shadow the last node (`nc`) and never store.  Every other body lets them exit here (the
+    // ragged warp is on the per-thread path, which has no warp syncs) — measurably faster code
+    // (GR4J 100k x 3650: 8.4 vs 9.4 ms).
     const i64 nc = valid ? n : a.N - 1;
+#if !HB_NN_MMA
+    if (!valid) return;
+#endif
 
     // ---- per-node constants: parameters (p[htypes], /root/reference/src/utils.jl:174-201) ------
     real hb_p[HB_ARR(HB_NP)];
