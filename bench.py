@@ -166,11 +166,18 @@ def main():
     ap.add_argument("--block", type=int, default=0, help="tuning: threads per block of the stepper")
     ap.add_argument("--stages", type=int, default=0, help="tuning: forcing pipeline depth (time steps)")
     ap.add_argument("--maxreg", type=int, default=0, help="tuning: register budget per thread")
-    ap.add_argument("--grid-tc", type=int, default=2, help="fused grid kernel: time steps per launch (= halo depth)")
+    ap.add_argument("--grid-tc", type=int, default=0, help="grid kernels: time steps per launch (0 = 16 for wave, 2 for tile)")
     ap.add_argument("--grid-bw", type=int, default=32, help="fused grid kernel: region width (cells)")
     ap.add_argument("--grid-bh", type=int, default=32, help="fused grid kernel: region height (cells)")
-    ap.add_argument("--fused-grid", action="store_true", help="grid workload: experimental single-pass kernel (grid.cu)")
+    ap.add_argument("--grid-kernel", default="wave", choices=["wave", "tile", "generic"],
+                    help="grid workload: wave = single-pass L2-dataflow kernel (gridwave.cu, default); tile = tile + halo "
+                         "(grid.cu); generic = stepper over all T, then one routing launch per step")
+    ap.add_argument("--fused-grid", action="store_true", help="(round-1 flag) same as --grid-kernel tile")
     args = ap.parse_args()
+    if args.fused_grid:
+        args.grid_kernel = "tile"
+    if args.grid_tc <= 0:
+        args.grid_tc = 16 if args.grid_kernel == "wave" else 2
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -256,13 +263,18 @@ def main():
                 def launch(self, ip, op, stream=None):
                     sharded.launch(ip, op)
             run = _Run()
-        elif not args.fused_grid:
+        elif args.grid_kernel == "generic":
             run = RoutedDeviceRun(eng, N, T, p, initstates=init)
         else:
             from hydromodels_jl_b200.engine import GridDeviceRun
-            run = GridDeviceRun(eng, N, T, p, initstates=init, steps_per_chunk=args.grid_tc, block_w=args.grid_bw,
-                                block_h=args.grid_bh)
+            if args.grid_kernel == "wave":
+                run = GridDeviceRun(eng, N, T, p, initstates=init, variant="wave", steps_per_chunk=args.grid_tc,
+                                    block_w=args.block, stages=args.stages, max_registers=args.maxreg)
+            else:
+                run = GridDeviceRun(eng, N, T, p, initstates=init, steps_per_chunk=args.grid_tc, block_w=args.grid_bw,
+                                    block_h=args.grid_bh)
             eng.last_kernel = run.ck
+            grid_run = run
         d_in = device_forcing(torch, "exphydro", N, T, sy.SEED + 17 * rank)
         d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
     else:
@@ -311,10 +323,15 @@ def main():
     bytes_per_unit = 8 * (v_of + rows_of)
     launches_per_step = 1
     if model_name == "exphydro_grid":
-        launches_per_step = (T + 2) if (not args.fused_grid or world > 1) else -(-T // args.grid_tc)
+        generic = args.grid_kernel == "generic" or world > 1
+        if not generic:
+            args.grid_tc = grid_run.check()          # raises if a warp of the wave kernel gave up waiting
+            config["grid_kernel"], config["steps_per_launch"] = args.grid_kernel, args.grid_tc
+        launches_per_step = (T + 2) if generic else -(-T // args.grid_tc)
     k_ms = float(np.mean(kernel_ms))
     achieved = bytes_per_unit * N * T / (k_ms * 1e-3) / 1e9
-    kname = {"exphydro_grid": "hb_stepper + T x hb_route_step" if (not args.fused_grid or world > 1) else "hb_grid_chunk",
+    kname = {"exphydro_grid": "hb_stepper + T x hb_route_step" if (args.grid_kernel == "generic" or world > 1) else
+             ("hb_grid_wave" if args.grid_kernel == "wave" else "hb_grid_chunk"),
              "hbv_ensemble": "hb_stepper (objective mode)"}.get(model_name, "hb_stepper")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -224,6 +224,8 @@ struct hb_model_s {
     int dyn_smem = 0;
     int block = 128;
     int uhw_total = 0, uhh_total = 0;
+    int wave_tc = 0;            // WAVE grid kernel: steps per launch after clamping
+    bool wave_err_init = false;
     CUdeviceptr nn_const = 0;   // module-scope __constant__ hb_nn_const[]
     // workspace for hb_run (host-pointer entry point)
     struct Buf { void *p = nullptr; size_t cap = 0; };
@@ -803,29 +805,86 @@ int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out)
         spec->o_row >= spec->n_rows)
         return fail(HB_ERR_INVALID, "hb_grid_spec out of range");
     const int tc = spec->steps_per_chunk, bw = spec->block_w, bh = spec->block_h;
-    if (tc < 1 || tc > 8 || bw % 32 || bw < 32 || bh < 1 || bw * bh > 1024 || bw - 2 * tc < 1 || bh - 2 * tc < 1)
-        return fail(HB_ERR_INVALID, "bad grid tiling (steps_per_chunk %d, block %d x %d)", tc, bw, bh);
     hb_model_s *m = new hb_model_s();
     m->kind = 2;
     m->gspec = *spec;
-    m->block = bw * bh;
-    m->dyn_smem = m->block * 8 + (m->block / 32) * 32 * spec->n_rows * 8 + m->block + 64;
-    char defs[768];
-    snprintf(defs, sizeof defs,
-             "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_NPS %d\n#define HB_RV %d\n"
-             "#define HB_SROW %d\n#define HB_OROW %d\n#define HB_TC %d\n#define HB_BW %d\n#define HB_BH %d\n#define HB_UHW_TOTAL 0\n"
-             "#define HB_UHH_TOTAL 0\n#define HB_NN_WORDS 0\n",
-             spec->n_inputs, spec->n_rows, spec->n_states, spec->n_params, spec->n_params_stepper, spec->n_route_inputs, spec->s_row,
-             spec->o_row, tc, bw, bh);
+    char defs[1024];
+    if (spec->variant == HB_GRID_WAVE) {
+        m->block = bw > 0 ? bw : 128;
+        const int stages = spec->stages > 0 ? spec->stages : 3;
+        if (tc < 1 || tc > 4096 || m->block % 32 || m->block > 1024 || stages > 16 || spec->n_inputs < 1) {
+            delete m;
+            return fail(HB_ERR_INVALID, "bad wave configuration (steps_per_chunk %d, block %d, stages %d)", tc, bw, stages);
+        }
+        auto up128 = [](int x) { return (x + 127) / 128 * 128; };
+        const int warps = m->block / 32;
+        m->dyn_smem = warps * (up128(stages * 32 * spec->n_inputs * 8) + up128(3 * 32 * spec->n_rows * 8)) + warps * stages * 8;
+        if (m->dyn_smem > 227 * 1024) { delete m; return fail(HB_ERR_INVALID, "wave kernel needs %d bytes of shared memory", m->dyn_smem); }
+        int minblocks = (227 * 1024) / (m->dyn_smem + 1024 + 1024);
+        const int cap = 2048 / m->block;
+        if (minblocks > cap) minblocks = cap;
+        if (minblocks < 1) minblocks = 1;
+        if (spec->max_registers > 0) {
+            int byregs = 65536 / (spec->max_registers * m->block);
+            if (byregs < 1) byregs = 1;
+            if (byregs < minblocks) minblocks = byregs;
+        } else if (minblocks > 4) {
+            minblocks = 4;
+        }
+        snprintf(defs, sizeof defs,
+                 "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_NPS %d\n#define HB_RV %d\n"
+                 "#define HB_SROW %d\n#define HB_OROW %d\n#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n"
+                 "#define HB_UHW_TOTAL 0\n#define HB_UHH_TOTAL 0\n#define HB_NN_WORDS 0\n",
+                 spec->n_inputs, spec->n_rows, spec->n_states, spec->n_params, spec->n_params_stepper, spec->n_route_inputs, spec->s_row,
+                 spec->o_row, m->block, stages, minblocks);
+        m->kernel_name = "hb_grid_wave";
+    } else if (spec->variant == HB_GRID_TILE) {
+        if (tc < 1 || tc > 8 || bw % 32 || bw < 32 || bh < 1 || bw * bh > 1024 || bw - 2 * tc < 1 || bh - 2 * tc < 1) {
+            delete m;
+            return fail(HB_ERR_INVALID, "bad grid tiling (steps_per_chunk %d, block %d x %d)", tc, bw, bh);
+        }
+        m->block = bw * bh;
+        m->dyn_smem = m->block * 8 + (m->block / 32) * 32 * spec->n_rows * 8 + m->block + 64;
+        snprintf(defs, sizeof defs,
+                 "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_NPS %d\n#define HB_RV %d\n"
+                 "#define HB_SROW %d\n#define HB_OROW %d\n#define HB_TC %d\n#define HB_BW %d\n#define HB_BH %d\n#define HB_UHW_TOTAL 0\n"
+                 "#define HB_UHH_TOTAL 0\n#define HB_NN_WORDS 0\n",
+                 spec->n_inputs, spec->n_rows, spec->n_states, spec->n_params, spec->n_params_stepper, spec->n_route_inputs, spec->s_row,
+                 spec->o_row, tc, bw, bh);
+        m->kernel_name = "hb_grid_chunk";
+    } else {
+        delete m;
+        return fail(HB_ERR_INVALID, "unknown grid kernel variant %d", spec->variant);
+    }
     std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";
-    m->source = splice(kGridTemplate, full_body.c_str());
-    m->kernel_name = "hb_grid_chunk";
+    if (const char *x = getenv("HB_EXTRA_DEFINES")) full_body = std::string("//@@HB:DEFINES\n") + x + "\n" + full_body;   // tuning experiments
+    m->source = splice(spec->variant == HB_GRID_WAVE ? kGridWaveTemplate : kGridTemplate, full_body.c_str());
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
     int rc = nvrtc_compile(m->source, opts, m->cubin, m->from_cache);
     if (rc) { delete m; return rc; }
     *out = m;
     return HB_OK;
 }
+
+namespace {
+
+// WAVE variant: T_c is limited by forward progress — a warp waits on blocks up to `band` logical indices
+// ahead, recursively one step shallower each hop, so T_c * band blocks must be co-resident at once.
+int wave_steps_per_launch(hb_model_s *m, int cols, int *out_tc) {
+    int per_sm = 0, sms = 0;
+    HB_DRV(g_drv.Occupancy(&per_sm, m->func, m->block, m->dyn_smem));
+    HB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device));
+    const int resident = per_sm * sms;
+    const int band = (cols + m->block - 1) / m->block + 2;
+    int tc = m->gspec.steps_per_chunk;
+    const int fit = (resident / 2) / band;
+    if (fit < 1) return fail(HB_ERR_INVALID, "grid too wide for the wave kernel (%d columns, %d co-resident blocks)", cols, resident);
+    if (tc > fit) tc = fit;
+    *out_tc = tc;
+    return HB_OK;
+}
+
+}  // namespace
 
 int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
     if (!m || m->kind != 2) return fail(HB_ERR_INVALID, "not a grid model");
@@ -844,34 +903,70 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
         if ((rc = ws_reserve(m->ws[k], sb))) return rc;
         if ((rc = ws_reserve(m->ws[2 + k], (size_t)N * 8))) return rc;
     }
+    const bool wave = s.variant == HB_GRID_WAVE;
+    int tc = s.steps_per_chunk;
+    if (wave) {
+        if ((rc = wave_steps_per_launch(m, d->cols, &tc))) return rc;
+        m->wave_tc = tc;
+        if ((rc = ws_reserve(m->ws[4], (size_t)2 * N * 16))) return rc;      // {outflow, step tag} words, two slots
+        if ((rc = ws_reserve(m->ws[6], 256))) return rc;
+        HB_CUDA(cudaMemsetAsync(m->ws[4].p, 0, (size_t)2 * N * 16, st));      // tags = 0: nothing published yet
+        HB_CUDA(cudaMemsetAsync(m->ws[6].p, 0, 4, st));                       // ticket (the error word [1] is sticky)
+        if (!m->wave_err_init) { HB_CUDA(cudaMemsetAsync((char *)m->ws[6].p + 4, 0, 4, st)); m->wave_err_init = true; }
+    }
     if (d->elapsed_ms) {
         if (!m->ev0) { HB_CUDA(cudaEventCreate(&m->ev0)); HB_CUDA(cudaEventCreate(&m->ev1)); }
         HB_CUDA(cudaEventRecord(m->ev0, st));
     }
-    const int tc = s.steps_per_chunk;
-    const unsigned gx = (unsigned)((d->cols + (s.block_w - 2 * tc) - 1) / (s.block_w - 2 * tc));
-    const unsigned gy = (unsigned)((d->rows + (s.block_h - 2 * tc) - 1) / (s.block_h - 2 * tc));
+    unsigned gx, gy;
+    if (wave) {
+        gx = (unsigned)((N + m->block - 1) / m->block);
+        gy = 1;
+    } else {
+        gx = (unsigned)((d->cols + (s.block_w - 2 * tc) - 1) / (s.block_w - 2 * tc));
+        gy = (unsigned)((d->rows + (s.block_h - 2 * tc) - 1) / (s.block_h - 2 * tc));
+    }
     const void *su_in = d->init_bucket, *rs_in = d->init_route;
     int half = 0;
     const int np = s.n_params > 0 ? s.n_params : 1;
+    uint32_t ticket_base = 0;
     for (int64_t t0 = 0; t0 < T; t0 += tc) {
-        // HbGridArgs mirror (templates/grid.cu): 9 pointers, 2 i64, 3 int (+pad), 1 double, int tables
-        unsigned char buf[9 * 8 + 2 * 8 + 16 + 8 + 8 * HB_MAX_PARAMS + 16];
+        // HbGridArgs / HbWaveArgs mirrors (templates/grid.cu, templates/gridwave.cu)
+        unsigned char buf[12 * 8 + 2 * 8 + 32 + 8 + 8 * HB_MAX_PARAMS + 16];
         memset(buf, 0, sizeof buf);
         size_t o = 0;
         auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
         void *su_out = m->ws[half].p, *rs_out = m->ws[2 + half].p;
         const void *ptrs[9] = {d->input, d->out, d->params, d->htypes, su_in, su_out, rs_in, rs_out, d->flwdir};
         put(ptrs, sizeof ptrs);
-        put(&N, 8);
-        put(&t0, 8);
         int ns = (int)((T - t0) < tc ? (T - t0) : tc), rows = d->rows, cols = d->cols, pad = 0;
-        put(&ns, 4);
-        put(&rows, 4);
-        put(&cols, 4);
-        put(&pad, 4);
         double minv = d->min_value;
-        put(&minv, 8);
+        if (wave) {
+            const void *wp[3] = {m->ws[4].p, m->ws[5].p, m->ws[6].p};
+            put(wp, sizeof wp);
+            put(&N, 8);
+            put(&t0, 8);
+            // TMA bulk copies need 16-byte aligned global addresses: base pointers and per-step strides
+            int tma_in = ((reinterpret_cast<uintptr_t>(d->input) & 15) == 0) && ((N * s.n_inputs * 8) % 16 == 0);
+            int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((N * s.n_rows * 8) % 16 == 0);
+            if (getenv("HB_DISABLE_TMA")) tma_in = tma_out = 0;
+            put(&ticket_base, 4);
+            put(&ns, 4);
+            put(&rows, 4);
+            put(&cols, 4);
+            put(&tma_in, 4);
+            put(&tma_out, 4);
+            put(&minv, 8);
+            ticket_base += gx;
+        } else {
+            put(&N, 8);
+            put(&t0, 8);
+            put(&ns, 4);
+            put(&rows, 4);
+            put(&cols, 4);
+            put(&pad, 4);
+            put(&minv, 8);
+        }
         std::vector<int> tmp(np, 0);
         for (int j = 0; j < s.n_params; ++j) tmp[j] = d->param_offset[j];
         put(tmp.data(), 4 * np);
@@ -891,6 +986,21 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
         HB_CUDA(cudaEventRecord(m->ev1, st));
         HB_CUDA(cudaEventSynchronize(m->ev1));
         HB_CUDA(cudaEventElapsedTime(d->elapsed_ms, m->ev0, m->ev1));
+    }
+    return HB_OK;
+}
+
+int hb_grid_status(hb_model_t m, void *stream, int32_t *steps_per_launch) {
+    if (!m || m->kind != 2) return fail(HB_ERR_INVALID, "not a grid model");
+    if (steps_per_launch) *steps_per_launch = m->gspec.variant == HB_GRID_WAVE ? m->wave_tc : m->gspec.steps_per_chunk;
+    if (m->gspec.variant != HB_GRID_WAVE || !m->ws[6].p) return HB_OK;
+    HB_CUDA(cudaSetDevice(g_device));
+    HB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    uint32_t err = 0;
+    HB_CUDA(cudaMemcpy(&err, (char *)m->ws[6].p + 4, 4, cudaMemcpyDeviceToHost));
+    if (err) {
+        cudaMemset((char *)m->ws[6].p + 4, 0, 4);
+        return fail(HB_ERR_CUDA, "hb_grid_wave: a warp gave up waiting for a neighbouring warp's outflows (forward-progress failure); results are invalid");
     }
     return HB_OK;
 }

@@ -78,7 +78,7 @@ class GridSpec(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("n_inputs", C.c_int32), ("n_rows", C.c_int32), ("n_states", C.c_int32),
                 ("n_params", C.c_int32), ("n_params_stepper", C.c_int32), ("n_route_inputs", C.c_int32),
                 ("s_row", C.c_int32), ("o_row", C.c_int32), ("steps_per_chunk", C.c_int32), ("block_w", C.c_int32),
-                ("block_h", C.c_int32)]
+                ("block_h", C.c_int32), ("variant", C.c_int32), ("stages", C.c_int32), ("max_registers", C.c_int32)]
 
 
 class GridDesc(C.Structure):
@@ -114,6 +114,7 @@ def lib():
         "hb_compile_route": [C.POINTER(RouteSpec), C.c_char_p, C.POINTER(C.c_void_p)],
         "hb_compile_grid": [C.POINTER(GridSpec), C.c_char_p, C.POINTER(C.c_void_p)],
         "hb_run_grid_device": [C.c_void_p, C.POINTER(GridDesc), C.c_void_p],
+        "hb_grid_status": [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)],
         "hb_run_route_device": [C.c_void_p, C.POINTER(RouteDesc), C.c_void_p],
         "hb_route_step_device": [C.c_void_p, C.POINTER(RouteDesc), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p],
@@ -343,9 +344,11 @@ class B200Model:
         self.dtype = np.float64 if precision == "f64" else np.float32
         self.fast = fast
         self.nn_tensor = nn_tensor        # dense chains on the FP64 tensor pipe (DMMA) where their shape fits
-        # [buckets…, HydroRoute] on a dense D8 grid: single-pass fused kernel (templates/grid.cu).  Opt-in: at
-        # 2048² it measures 16.5-21.9 ms vs 17.5 ms for the generic stepper + per-step route path
-        self.use_fused_grid = False
+        # [buckets…, HydroRoute] on a dense row-major D8 grid: "wave" = single-pass kernel whose warps exchange
+        # outflows through L2 (templates/gridwave.cu, default); "tile" = tile + halo kernel (templates/grid.cu);
+        # "generic" = stepper over all T, then one routing launch per step (any node list / graph)
+        self.grid_kernel = "wave"
+        self.grid_steps_per_launch = 16
         self.block_threads, self.stages, self.max_registers = block_threads, stages, max_registers
         self._cache: Dict[Tuple, CompiledStepper] = {}
         self.last_kernel: Optional[CompiledStepper] = None
@@ -371,6 +374,14 @@ class B200Model:
             all(c.htypes is not None for c in comps)
 
     # -- name getters forward to the wrapped component ----------------------------------------------
+    @property
+    def use_fused_grid(self) -> bool:
+        return self.grid_kernel != "generic"
+
+    @use_fused_grid.setter
+    def use_fused_grid(self, on: bool):     # round-1 switch: True = the tile + halo kernel, False = the generic path
+        self.grid_kernel = "tile" if on else "generic"
+
     def get_input_names(self): return self.component.get_input_names()
     def get_output_names(self): return self.component.get_output_names()
     def get_state_names(self): return self.component.get_state_names()
@@ -648,11 +659,17 @@ class B200Model:
         # dense row-major grid, bucket/flux components only: fused single-pass kernel (templates/grid.cu)
         if (self.lumped is not None and not extra and self.use_fused_grid and dense_grid_shape(route.aggr, N) is not None
                 and not self._has_uh() and not self.lumped.nn_names and N * T > 0):
-            run = GridDeviceRun(self, N, T, params, config=cfg, initstates=init_all)
+            if self.grid_kernel == "wave":
+                run = GridDeviceRun(self, N, T, params, config=cfg, initstates=init_all, variant="wave",
+                                    steps_per_chunk=self.grid_steps_per_launch, block_w=self.block_threads, stages=self.stages,
+                                    max_registers=self.max_registers)
+            else:
+                run = GridDeviceRun(self, N, T, params, config=cfg, initstates=init_all)
             inp = input if input.flags.f_contiguous else np.asfortranarray(input)
             din = DeviceBuffer.from_host(inp.ravel(order="K"))
             rec = DeviceBuffer(T * N * R * 8)
             ms = run.launch(din.ptr, rec.ptr, None, timed=True)
+            run.check()
             full = rec.to_host((R, N, T), order="F")
             din.free()
             rec.free()
@@ -1034,13 +1051,18 @@ def dense_grid_shape(aggr, n_nodes: int) -> Optional[Tuple[int, int]]:
     return None
 
 
+GRID_VARIANTS = {"tile": 0, "wave": 1}
+
+
 class CompiledGrid:
-    def __init__(self, program: GridProgram, steps_per_chunk: int = 2, block_w: int = 32, block_h: int = 32):
+    def __init__(self, program: GridProgram, steps_per_chunk: int = 2, block_w: int = 32, block_h: int = 32,
+                 variant: str = "tile", stages: int = 0, max_registers: int = 0):
         self.program = program
         sp, rp = program.stepper, program.route
         spec = GridSpec(C.sizeof(GridSpec), len(sp.input_names), len(program.row_names), len(sp.state_names),
                         len(sp.param_slots) + len(rp.param_slots), len(sp.param_slots), len(rp.input_names),
-                        program.s_row, program.o_row, steps_per_chunk, block_w, block_h)
+                        program.s_row, program.o_row, steps_per_chunk, block_w, block_h, GRID_VARIANTS[variant], stages,
+                        max_registers)
         self.spec = spec
         h = C.c_void_p()
         check(lib().hb_compile_grid(C.byref(spec), program.body.encode(), C.byref(h)))
@@ -1070,7 +1092,8 @@ class GridDeviceRun:
     """Device-resident run of `[buckets…, HydroRoute]` on a dense D8 grid with the fused kernel."""
 
     def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None,
-                 steps_per_chunk: int = 2, block_w: int = 32, block_h: int = 32):
+                 steps_per_chunk: int = 2, block_w: int = 32, block_h: int = 32, variant: str = "tile", stages: int = 0,
+                 max_registers: int = 0):
         if eng.route is None or eng.lumped is None:
             raise ValueError("GridDeviceRun needs per-node components followed by a HydroRoute")
         shape = dense_grid_shape(eng.route.aggr, N)
@@ -1080,9 +1103,10 @@ class GridDeviceRun:
         self.cfg = normalize_config(config)
         _check_config(self.cfg, T)
         rows = eng.component.var_names
-        key = ("grid", steps_per_chunk, block_w, block_h)
+        key = ("grid", variant, steps_per_chunk, block_w, block_h, stages, max_registers)
         if key not in eng._cache:
-            eng._cache[key] = CompiledGrid(lower_grid(eng.lumped, eng.route, rows, fast=eng.fast), steps_per_chunk, block_w, block_h)
+            eng._cache[key] = CompiledGrid(lower_grid(eng.lumped, eng.route, rows, fast=eng.fast), steps_per_chunk, block_w, block_h,
+                                           variant, stages, max_registers)
         self.ck = eng._cache[key]
         sp, rp = self.ck.program.stepper, self.ck.program.route
         flat1, off1, mode1, ht1, _, _, _ = eng.prepare(sp, params, N)
@@ -1132,3 +1156,9 @@ class GridDeviceRun:
             d.elapsed_ms = C.cast(C.byref(el), C.c_void_p)
         check(lib().hb_run_grid_device(self.ck.handle, C.byref(d), stream))
         return el.value if timed else None
+
+    def check(self, stream: Optional[int] = None) -> int:
+        """Synchronise and raise if a warp of the wave kernel gave up waiting; returns the steps per launch used."""
+        tc = C.c_int32(0)
+        check(lib().hb_grid_status(self.ck.handle, stream, C.byref(tc)))
+        return tc.value

@@ -201,7 +201,13 @@ int hb_run_route_device(hb_model_t m, const hb_route_desc *desc, void *stream);
 int hb_route_step_device(hb_model_t m, const hb_route_desc *desc, int64_t t, const double *s_prev, double *s_next,
                          const double *q_cur, double *q_next, void *stream);
 
-/* ---- fused dense-grid model: per-cell buckets + D8 HydroRoute in one pass (templates/grid.cu) ------- */
+/* ---- fused dense-grid model: per-cell buckets + D8 HydroRoute in one pass ----------------------------
+ * Replaces, for `[buckets..., HydroRoute]` models whose node list is the complete row-major grid, the two-pass
+ * generic path above (/root/reference/src/model.jl:273-309 sequencing + src/route.jl:336-404).  Two kernel
+ * variants: HB_GRID_WAVE (templates/gridwave.cu, default: warps exchange outflows through L2 with
+ * release/acquire step counters, no redundant work) and HB_GRID_TILE (templates/grid.cu: tile + halo). */
+#define HB_GRID_TILE 0
+#define HB_GRID_WAVE 1
 typedef struct {
     int32_t struct_size;        /* sizeof(hb_grid_spec) */
     int32_t n_inputs;           /* V */
@@ -211,8 +217,13 @@ typedef struct {
     int32_t n_params_stepper;   /* slots of the per-cell part */
     int32_t n_route_inputs;
     int32_t s_row, o_row;       /* record rows of the route state / outflow */
-    int32_t steps_per_chunk;    /* T_c = halo depth (1..4) */
-    int32_t block_w, block_h;   /* region (tile + halo) in cells; block_w % 32 == 0, block_w*block_h <= 512 */
+    int32_t steps_per_chunk;    /* T_c: steps per launch.  TILE: = halo depth (1..8).  WAVE: 1..4096, clamped at run
+                                 * time so that the dependency cone fits in the co-resident blocks */
+    int32_t block_w, block_h;   /* TILE: region (tile + halo) in cells; block_w % 32 == 0, block_w*block_h <= 1024.
+                                 * WAVE: block_w = threads per block (0 = 128), block_h ignored */
+    int32_t variant;            /* HB_GRID_TILE | HB_GRID_WAVE */
+    int32_t stages;             /* WAVE: forcing pipeline depth in time steps (0 = 3) */
+    int32_t max_registers;      /* WAVE: register budget per thread (0 = compiler's choice at 4 blocks/SM) */
 } hb_grid_spec;
 
 typedef struct {
@@ -238,6 +249,10 @@ typedef struct {
 
 int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out);
 int hb_run_grid_device(hb_model_t m, const hb_grid_desc *desc, void *stream);   /* ceil(T / T_c) launches */
+/* WAVE variant: synchronises `stream` and reports whether any warp of the runs enqueued so far gave up waiting
+ * for a neighbour (bounded poll loops; would indicate a forward-progress bug or a foreign kernel hogging the
+ * SMs).  Returns HB_ERR_CUDA with a message if so; `steps_per_launch` (optional) receives the clamped T_c. */
+int hb_grid_status(hb_model_t m, void *stream, int32_t *steps_per_launch);
 
 /* ---- IRF river routing: SparseRouteConvolution (/root/reference/src/route.jl:593-610) -------------------
  * out[t][d] = sum over the kernel rows of destination d (CSR `row_ptr`, original row order) of the causal

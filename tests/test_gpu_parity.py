@@ -345,6 +345,37 @@ def test_fused_grid_kernel_matches_oracle_and_generic_path(R, Cc, T):
     assert np.array_equal(eng(inp, p), eng2(inp, p))
 
 
+# ---- wave grid kernel (templates/gridwave.cu): the default path for dense row-major grids --------------------
+@pytest.mark.parametrize("R,Cc,T,tc", [(5, 4, 7, 16), (40, 70, 33, 5), (61, 29, 20, 1), (64, 64, 40, 16), (33, 128, 50, 7),
+                                       (300, 256, 24, 16)])
+def test_wave_grid_kernel_matches_oracle_and_generic_path(R, Cc, T, tc):
+    """Warps exchange outflows through L2 with release/acquire step counters (no halo, no second pass).  Must agree
+    with the oracle and, bit for bit, with the generic stepper + per-step route path: TMA-aligned and odd shapes,
+    ragged last warp, rows shorter than a warp, several launches (T_c = 1, remainders), many resident blocks."""
+    rng = np.random.default_rng(R * 1000 + Cc)
+    flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128, 0, 5], size=(R, Cc))
+    rr, cc = np.divmod(np.arange(R * Cc), Cc)
+    pos = np.stack([rr + 1, cc + 1], axis=1)
+    N = R * Cc
+    model = hm.models.exphydro_grid(flw, pos)
+    inp = sy.forcing("exphydro", 0, N, T)
+    p = {"params": dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))}
+    init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 2, N))
+    eng = hm.B200Model(model)
+    assert eng.grid_kernel == "wave"
+    eng.grid_steps_per_launch = tc
+    wave = eng(inp, p, initstates=init)
+    assert any(isinstance(k, tuple) and k[:2] == ("grid", "wave") for k in eng._cache)
+    if N * T <= 200_000:
+        assert_parity(wave, ho.run_model(model, inp, p, initstates=init))
+    eng2 = hm.B200Model(model)
+    eng2.grid_kernel = "generic"
+    generic = eng2(inp, p, initstates=init)
+    assert np.array_equal(wave, generic)
+    assert np.array_equal(eng(inp, p), eng2(inp, p))          # default (zero) initial states
+    assert np.array_equal(eng(inp, p, initstates=init), wave)  # step counters / tickets are reset between runs
+
+
 # ---- IRF river routing: SparseRouteConvolution (SURVEY.md §8f row 1) -----------------------------------------
 def test_sparse_route_convolution_matches_oracle():
     """`/root/reference/src/route.jl:593-610`: the reference has no test or fixture for this operator, so the
