@@ -818,7 +818,9 @@ int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out)
         }
         auto up128 = [](int x) { return (x + 127) / 128 * 128; };
         const int warps = m->block / 32;
-        m->dyn_smem = warps * (up128(stages * 32 * spec->n_inputs * 8) + up128(3 * 32 * spec->n_rows * 8)) + warps * stages * 8;
+        const int obuf = getenv("HB_WAVE_OBUF") ? atoi(getenv("HB_WAVE_OBUF")) : 3;     // tuning: record tiles per warp (2 or 3)
+        if (obuf < 2 || obuf > 4) { delete m; return fail(HB_ERR_INVALID, "HB_WAVE_OBUF must be 2..4"); }
+        m->dyn_smem = warps * (up128(stages * 32 * spec->n_inputs * 8) + up128(obuf * 32 * spec->n_rows * 8)) + warps * stages * 8;
         if (m->dyn_smem > 227 * 1024) { delete m; return fail(HB_ERR_INVALID, "wave kernel needs %d bytes of shared memory", m->dyn_smem); }
         int minblocks = (227 * 1024) / (m->dyn_smem + 1024 + 1024);
         const int cap = 2048 / m->block;
@@ -834,9 +836,9 @@ int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out)
         snprintf(defs, sizeof defs,
                  "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_NPS %d\n#define HB_RV %d\n"
                  "#define HB_SROW %d\n#define HB_OROW %d\n#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n"
-                 "#define HB_UHW_TOTAL 0\n#define HB_UHH_TOTAL 0\n#define HB_NN_WORDS 0\n",
+                 "#define HB_UHW_TOTAL 0\n#define HB_UHH_TOTAL 0\n#define HB_NN_WORDS 0\n#define HB_OBUF %d\n",
                  spec->n_inputs, spec->n_rows, spec->n_states, spec->n_params, spec->n_params_stepper, spec->n_route_inputs, spec->s_row,
-                 spec->o_row, m->block, stages, minblocks);
+                 spec->o_row, m->block, stages, minblocks, obuf);
         m->kernel_name = "hb_grid_wave";
     } else if (spec->variant == HB_GRID_TILE) {
         if (tc < 1 || tc > 8 || bw % 32 || bw < 32 || bh < 1 || bw * bh > 1024 || bw - 2 * tc < 1 || bh - 2 * tc < 1) {

@@ -46,7 +46,9 @@ typedef unsigned int u32;
 // (generated) HB_V HB_R HB_S HB_NP HB_NPS HB_NC HB_RV HB_SROW HB_OROW HB_BLOCK HB_STAGES HB_MINBLOCKS
 //             and   HB_ROUTE_IN(v) -> hb_out[row of route input v]
 
-#define HB_OBUF 3
+#ifndef HB_OBUF
+#define HB_OBUF 3                   // record tiles per warp (2: the store of step i-2 must have drained before bucket i)
+#endif
 #define HB_WARPS (HB_BLOCK / 32)
 #define HB_ARR(n) ((n) > 0 ? (n) : 1)
 typedef double real;
