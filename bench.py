@@ -255,7 +255,21 @@ def main():
         p = {"params": pp}
         init = dict(snowpack=np.zeros(Ng), soilwater=np.full(Ng, 1303.0), s_river=np.zeros(Ng))
         eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
-        if world > 1:
+        if world > 1 and args.grid_kernel == "wave":
+            # row strips + ghost rows, bucket / river states exchanged every `grid_tc` steps (temporal blocking)
+            from hydromodels_jl_b200.parallel import ShardedGridRun
+            sharded = ShardedGridRun(eng, side * world, side, T, p, initstates=init, halo=args.grid_tc, stages=args.stages,
+                                     max_registers=args.maxreg, block_threads=args.block)
+            assert sharded.N == N
+            eng.last_kernel = sharded.run.ck
+            grid_run = sharded
+            n_ghost = sharded.plan.n_local - N
+
+            class _Run:
+                def launch(self, ip, op, stream=None):
+                    sharded.launch(ip, op)
+            run = _Run()
+        elif world > 1:
             sharded = ShardedRoutedRun(eng, Ng, T, p, initstates=init)
             assert sharded.N == N
 
@@ -276,6 +290,22 @@ def main():
             eng.last_kernel = run.ck
             grid_run = run
         d_in = device_forcing(torch, "exphydro", N, T, sy.SEED + 17 * rank)
+        if world > 1 and args.grid_kernel == "wave":
+            # forcing of the ghost rows: the adjacent rows of the neighbouring ranks' forcing (same generator, their seed)
+            pl = sharded.plan
+            parts = []
+            if rank > 0:
+                up = device_forcing(torch, "exphydro", N, T, sy.SEED + 17 * (rank - 1))
+                parts.append(up[:, N - (pl.r0 - pl.g0) * side:, :].clone())
+                del up
+            parts.append(d_in)
+            if rank < world - 1:
+                dn = device_forcing(torch, "exphydro", N, T, sy.SEED + 17 * (rank + 1))
+                parts.append(dn[:, :(pl.g1 - pl.r1) * side, :].clone())
+                del dn
+            d_in = torch.cat(parts, dim=1).contiguous()
+            del parts
+            torch.cuda.empty_cache()
         d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
     else:
         model, p, init = build_problem(hm, sy, model_name, n0, N, T)
@@ -323,14 +353,14 @@ def main():
     bytes_per_unit = 8 * (v_of + rows_of)
     launches_per_step = 1
     if model_name == "exphydro_grid":
-        generic = args.grid_kernel == "generic" or world > 1
+        generic = args.grid_kernel == "generic" or (world > 1 and args.grid_kernel != "wave")
         if not generic:
             args.grid_tc = grid_run.check()          # raises if a warp of the wave kernel gave up waiting
             config["grid_kernel"], config["steps_per_launch"] = args.grid_kernel, args.grid_tc
         launches_per_step = (T + 2) if generic else -(-T // args.grid_tc)
     k_ms = float(np.mean(kernel_ms))
     achieved = bytes_per_unit * N * T / (k_ms * 1e-3) / 1e9
-    kname = {"exphydro_grid": "hb_stepper + T x hb_route_step" if (args.grid_kernel == "generic" or world > 1) else
+    kname = {"exphydro_grid": "hb_stepper + T x hb_route_step" if (args.grid_kernel == "generic" or (world > 1 and args.grid_kernel != "wave")) else
              ("hb_grid_wave" if args.grid_kernel == "wave" else "hb_grid_chunk"),
              "hbv_ensemble": "hb_stepper (objective mode)"}.get(model_name, "hb_stepper")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",

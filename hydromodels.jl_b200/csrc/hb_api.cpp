@@ -893,6 +893,8 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
     if (!d || d->struct_size != (int32_t)sizeof(hb_grid_desc)) return fail(HB_ERR_INVALID, "hb_grid_desc.struct_size mismatch");
     const hb_grid_spec &s = m->gspec;
     if (d->rows <= 0 || d->cols <= 0 || d->n_steps < 0 || !d->input || !d->out || !d->flwdir) return fail(HB_ERR_INVALID, "bad grid descriptor");
+    if (d->out_node_count > 0 && (s.variant != HB_GRID_WAVE || d->out_first_node < 0 || d->out_first_node + d->out_node_count > (int64_t)d->rows * d->cols))
+        return fail(HB_ERR_INVALID, "an output node range needs the wave kernel and must lie inside the grid");
     if (!(d->min_value > 0)) return fail(HB_ERR_INVALID, "min_value must be positive, got %g", d->min_value);
     if (s.n_params > 0 && (!d->params || !d->param_offset || !d->param_mode)) return fail(HB_ERR_INVALID, "params / param tables are NULL");
     int rc = load_model(m);
@@ -934,7 +936,7 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
     uint32_t ticket_base = 0;
     for (int64_t t0 = 0; t0 < T; t0 += tc) {
         // HbGridArgs / HbWaveArgs mirrors (templates/grid.cu, templates/gridwave.cu)
-        unsigned char buf[12 * 8 + 2 * 8 + 32 + 8 + 8 * HB_MAX_PARAMS + 16];
+        unsigned char buf[12 * 8 + 4 * 8 + 32 + 8 + 8 * HB_MAX_PARAMS + 16];
         memset(buf, 0, sizeof buf);
         size_t o = 0;
         auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
@@ -948,9 +950,13 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
             put(wp, sizeof wp);
             put(&N, 8);
             put(&t0, 8);
+            const int64_t out_first = d->out_node_count > 0 ? d->out_first_node : 0, out_count = d->out_node_count > 0 ? d->out_node_count : N;
+            put(&out_first, 8);
+            put(&out_count, 8);
             // TMA bulk copies need 16-byte aligned global addresses: base pointers and per-step strides
             int tma_in = ((reinterpret_cast<uintptr_t>(d->input) & 15) == 0) && ((N * s.n_inputs * 8) % 16 == 0);
-            int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((N * s.n_rows * 8) % 16 == 0);
+            int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((out_count * s.n_rows * 8) % 16 == 0) &&
+                          ((out_first * s.n_rows * 8) % 16 == 0);
             if (getenv("HB_DISABLE_TMA")) tma_in = tma_out = 0;
             put(&ticket_base, 4);
             put(&ns, 4);

@@ -68,6 +68,8 @@ struct HbWaveArgs {
     u32 *ticket;              // [0] block ticket (monotone over the run), [1] error flag
     i64 N;
     i64 t0;                   // first step of this chunk
+    i64 out_first;            // records are written for cells [out_first, out_first + out_count) only — a strip of a
+    i64 out_count;            //   multi-GPU run computes ghost rows whose records belong to the neighbouring rank
     u32 ticket_base;          // value of the ticket when this launch started
     int nsteps;               // steps in this chunk
     int rows, cols;
@@ -159,7 +161,8 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
     u64 *bars = reinterpret_cast<u64 *>(hb_smem + (size_t)HB_WARPS * (kInBytes + kOutBytes)) + warp * HB_STAGES;
 
     const bool tma_in = a.tma_in_ok && full_warp;
-    const bool tma_out = a.tma_out_ok && full_warp;
+    const bool tma_out = a.tma_out_ok && full_warp && n0w >= a.out_first && n0w + 32 <= a.out_first + a.out_count;
+    const bool out_valid = valid && n >= a.out_first && n < a.out_first + a.out_count;
 
     // ---- per-cell constants ---------------------------------------------------------------------
     real hb_p[HB_ARR(HB_NP)];
@@ -212,11 +215,11 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
 
     const int ns = a.nsteps;
     const i64 in_step = a.N * (i64)HB_V;
-    const i64 out_step = a.N * (i64)HB_R;
+    const i64 out_step = a.out_count * (i64)HB_R;
     const real *in_warp = a.in + (a.t0 * a.N + n0w) * HB_V;
     const real *gx = a.in + (a.t0 * a.N + nc) * HB_V;
-    real *ow_ptr = a.out + (a.t0 * a.N + n0w) * HB_R;
-    real *go = a.out + (a.t0 * a.N + nc) * HB_R;
+    real *ow_ptr = a.out + (a.t0 * a.out_count + (n0w - a.out_first)) * HB_R;
+    real *go = a.out + (a.t0 * a.out_count + (nc - a.out_first)) * HB_R;
 
     if (tma_in) {
         if (lane == 0) {
@@ -348,7 +351,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
                     hb_bulk_s2g(ow_ptr, hb_smem_u32(so), kOutTile);
                     hb_bulk_commit();
                 }
-            } else if (valid) {
+            } else if (out_valid) {
 #pragma unroll
                 for (int r = 0; r < HB_R; ++r) go[r] = so[lane * HB_R + r];
             }

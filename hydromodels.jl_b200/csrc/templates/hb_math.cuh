@@ -84,7 +84,7 @@ __constant__ const double HB_EXP2T_SRC[64] = {HB_EXP2_TABLE};
 __shared__ double hb_exp2t[64];
 // every thread of the block calls this once at kernel entry (contains a block barrier)
 __device__ __forceinline__ void hb_math_init() {
-    if (threadIdx.x < 64) hb_exp2t[threadIdx.x] = HB_EXP2T_SRC[threadIdx.x];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) hb_exp2t[i] = HB_EXP2T_SRC[i];   // any block size
     __syncthreads();
 }
 #endif

@@ -87,7 +87,7 @@ class GridDesc(C.Structure):
                 ("n_param_values", C.c_int64), ("param_offset", C.c_void_p), ("param_mode", C.c_void_p),
                 ("htypes", C.c_void_p), ("init_bucket", C.c_void_p), ("init_route", C.c_void_p), ("flwdir", C.c_void_p),
                 ("min_value", C.c_double), ("final_bucket", C.c_void_p), ("final_route", C.c_void_p),
-                ("elapsed_ms", C.c_void_p)]
+                ("elapsed_ms", C.c_void_p), ("out_first_node", C.c_int64), ("out_node_count", C.c_int64)]
 
 
 _lib = None
@@ -1089,17 +1089,28 @@ class CompiledGrid:
 
 
 class GridDeviceRun:
-    """Device-resident run of `[buckets…, HydroRoute]` on a dense D8 grid with the fused kernel."""
+    """Device-resident run of `[buckets…, HydroRoute]` on a dense D8 grid with a fused kernel.
+
+    `row_range=(g0, g1)`: this process runs grid rows `[g0, g1)` only (a strip of a multi-GPU run, ghost rows
+    included — see `parallel.ShardedGridRun`); `N` is then the number of cells of the strip and flow directions
+    leaving the strip count as off-grid."""
 
     def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None,
-                 steps_per_chunk: int = 2, block_w: int = 32, block_h: int = 32, variant: str = "tile", stages: int = 0,
-                 max_registers: int = 0):
+                 steps_per_chunk: int = 2, block_w: Optional[int] = None, block_h: int = 32, variant: str = "tile", stages: int = 0,
+                 max_registers: int = 0, row_range: Optional[Tuple[int, int]] = None):
+        if block_w is None:
+            block_w = 32 if variant == "tile" else 0       # tile: region width in cells; wave: threads per block (0 = 128)
         if eng.route is None or eng.lumped is None:
             raise ValueError("GridDeviceRun needs per-node components followed by a HydroRoute")
-        shape = dense_grid_shape(eng.route.aggr, N)
+        n_global = len(eng.route.htypes)
+        shape = dense_grid_shape(eng.route.aggr, n_global)
         if shape is None:
-            raise ValueError("the fused grid kernel needs the complete grid in row-major node order")
-        self.rows, self.cols = shape
+            raise ValueError("the fused grid kernels need the complete grid in row-major node order")
+        g0, g1 = row_range if row_range is not None else (0, shape[0])
+        self.rows, self.cols = g1 - g0, shape[1]
+        node_range = None if row_range is None else (g0 * self.cols, g1 * self.cols)
+        if N != self.rows * self.cols:
+            raise ValueError(f"{N} nodes given for a {self.rows} x {self.cols} grid (strip)")
         self.cfg = normalize_config(config)
         _check_config(self.cfg, T)
         rows = eng.component.var_names
@@ -1109,8 +1120,10 @@ class GridDeviceRun:
                                            variant, stages, max_registers)
         self.ck = eng._cache[key]
         sp, rp = self.ck.program.stepper, self.ck.program.route
-        flat1, off1, mode1, ht1, _, _, _ = eng.prepare(sp, params, N)
-        stage = RouteStage(eng, N, T, params, self.cfg, rows, None if initstates is None else initstates.get(eng.route.state_names[0]))
+        flat1, off1, mode1, ht1, _, _, _ = eng.prepare(sp, params, N, node_range=node_range)
+        dummy_csr = (np.zeros(N + 1, dtype=np.int32), np.zeros(1, dtype=np.int32))     # the grid kernels gather through flwdir
+        stage = RouteStage(eng, N, T, params, self.cfg, rows, None if initstates is None else initstates.get(eng.route.state_names[0]),
+                           node_range=node_range, csr=dummy_csr)
         flat2 = stage.bufs[0].to_host((stage.n_param_values,))
         n_sets1 = 0 if ht1 is None else ht1.shape[0]
         flat = np.concatenate([flat1, flat2])
@@ -1119,6 +1132,8 @@ class GridDeviceRun:
         mode2 = np.where(stage.p_mode[:len(rp.param_slots)] >= 2, stage.p_mode[:len(rp.param_slots)] + n_sets1, stage.p_mode[:len(rp.param_slots)])
         p_mode = np.concatenate([mode1[:len(sp.param_slots)], mode2]).astype(np.int32)
         h_route = np.asarray(eng.route.htypes, dtype=np.int64) - 1
+        if node_range is not None:
+            h_route = h_route[node_range[0]:node_range[1]]
         hts = ([ht1] if ht1 is not None else []) + [h_route.astype(np.int32)[None, :]]
         htypes = np.ascontiguousarray(np.concatenate(hts, axis=0))
         if p_off.size == 0:
@@ -1126,31 +1141,46 @@ class GridDeviceRun:
         self._host = (np.ascontiguousarray(p_off), np.ascontiguousarray(p_mode))
         self.n_sets = htypes.shape[0]
         self.n_param_values = flat.size
+        flw = eng.route.aggr.flwdir[g0:g1]
         self.bufs = {"params": DeviceBuffer.from_host(flat), "htypes": DeviceBuffer.from_host(htypes),
-                     "flw": DeviceBuffer.from_host(np.where(np.isin(eng.route.aggr.flwdir, D8_CODES), eng.route.aggr.flwdir, 0).astype(np.uint8))}
+                     "flw": DeviceBuffer.from_host(np.where(np.isin(flw, D8_CODES), flw, 0).astype(np.uint8))}
         init = eng._initstates(sp, None if initstates is None else {k: v for k, v in initstates.items()
-                                                                     if k != eng.route.state_names[0]}, N)
+                                                                     if k != eng.route.state_names[0]}, N, node_range)
         if init is not None:
             self.bufs["init"] = DeviceBuffer.from_host(init)
         if stage.dinit is not None:
             self.bufs["rinit"] = DeviceBuffer.from_host(stage.dinit.to_host((N,)))
         stage.free()
-        self.N, self.T, self.n_rows = int(N), int(T), len(rows)
+        self.N, self.T, self.n_rows, self.n_states = int(N), int(T), len(rows), len(sp.state_names)
         self.in_bytes, self.out_bytes = T * N * len(sp.input_names) * 8, T * N * len(rows) * 8
 
-    def launch(self, input_ptr: int, rec_ptr: int, stream: Optional[int] = None, timed: bool = False) -> Optional[float]:
+    def launch_chunk(self, input_ptr: int, rec_ptr: int, n_steps: int, init_bucket: Optional[int], init_route: Optional[int],
+                     final_bucket: Optional[int], final_route: Optional[int], out_first: int = 0, out_count: int = 0,
+                     stream: Optional[int] = None):
+        """`n_steps` steps from caller-owned state buffers (`[S][N]` / `[N]` device pointers, None = zeros / not wanted);
+        records of nodes `[out_first, out_first + out_count)` only (0 = all).  Asynchronous on `stream`."""
+        d = self._desc(input_ptr, rec_ptr, n_steps)
+        d.init_bucket, d.init_route, d.final_bucket, d.final_route = init_bucket, init_route, final_bucket, final_route
+        d.out_first_node, d.out_node_count = out_first, out_count
+        check(lib().hb_run_grid_device(self.ck.handle, C.byref(d), stream))
+
+    def _desc(self, input_ptr: int, rec_ptr: int, n_steps: int) -> GridDesc:
         d = GridDesc()
         d.struct_size = C.sizeof(GridDesc)
         d.n_htype_sets = self.n_sets
-        d.rows, d.cols, d.n_steps = self.rows, self.cols, self.T
+        d.rows, d.cols, d.n_steps = self.rows, self.cols, n_steps
         d.input, d.out = input_ptr, rec_ptr
         d.params, d.n_param_values = self.bufs["params"].ptr, self.n_param_values
         d.param_offset, d.param_mode = _ptr(self._host[0]), _ptr(self._host[1])
         d.htypes = self.bufs["htypes"].ptr
-        d.init_bucket = self.bufs["init"].ptr if "init" in self.bufs else None
-        d.init_route = self.bufs["rinit"].ptr if "rinit" in self.bufs else None
         d.flwdir = self.bufs["flw"].ptr
         d.min_value = self.cfg.min_value
+        return d
+
+    def launch(self, input_ptr: int, rec_ptr: int, stream: Optional[int] = None, timed: bool = False) -> Optional[float]:
+        d = self._desc(input_ptr, rec_ptr, self.T)
+        d.init_bucket = self.bufs["init"].ptr if "init" in self.bufs else None
+        d.init_route = self.bufs["rinit"].ptr if "rinit" in self.bufs else None
         el = C.c_float(0.0)
         if timed:
             d.elapsed_ms = C.cast(C.byref(el), C.c_void_p)

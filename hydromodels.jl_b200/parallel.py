@@ -6,7 +6,7 @@ results (objective values, final states) over `torch.distributed` (NCCL on GPUs,
 tests)."""
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -220,3 +220,118 @@ class ShardedRoutedRun:
             self.stage.step(rec_ptr, t, s[cur].data_ptr(), s[cur ^ 1].data_ptr(), q[cur].data_ptr(), q[cur ^ 1].data_ptr(), stream)
             if t + 1 < self.T:
                 exchange_ghosts(q[cur ^ 1], self.N, self.send, self.recv, self.group)
+
+
+# ---------------------------------------------------------------------------------------------------
+# dense D8 grids with the single-pass wave kernel: row strips + ghost rows, states exchanged every H steps
+# ---------------------------------------------------------------------------------------------------
+class GridStripPlan:
+    """Row-strip decomposition of a `rows x cols` grid for temporal blocking ("H-step temporal
+    blocking").  Rank k owns rows `[r0, r1)` and computes rows `[g0, g1)` = its strip plus up to `halo` ghost
+    rows on either side.  D8 routing moves water one cell per step (src/route.jl:387-403), so after h steps
+    without communication exactly the outermost h ghost rows on each side may differ from a whole-grid run —
+    the owned rows stay exact for `halo` steps, after which the ghost rows' STATES (bucket states + river
+    state) are refreshed from the neighbouring ranks.  One exchange of `(S+1) * halo * cols * 8` bytes per
+    edge every `halo` steps replaces the per-step outflow exchange of `ShardedRoutedRun`."""
+
+    def __init__(self, rows: int, cols: int, rank: int, world: int, halo: int):
+        self.rows, self.cols, self.rank, self.world, self.halo = rows, cols, rank, world, halo
+        self.r0, self.r1 = shard_range(rows, rank, world)
+        if world > 1 and min(shard_range(rows, k, world)[1] - shard_range(rows, k, world)[0] for k in range(world)) < halo:
+            raise ValueError(f"every strip needs at least halo = {halo} rows")
+        self.g0, self.g1 = max(0, self.r0 - halo), min(rows, self.r1 + halo)
+        self.n_local = (self.g1 - self.g0) * cols
+        self.out_first = (self.r0 - self.g0) * cols
+        self.out_count = (self.r1 - self.r0) * cols
+
+    def node_range(self) -> Tuple[int, int]:
+        return self.g0 * self.cols, self.g1 * self.cols
+
+    def exchanges(self) -> List[Tuple[int, Tuple[int, int], Tuple[int, int]]]:
+        """[(peer, (send_lo, send_hi), (recv_lo, recv_hi))] in LOCAL node indices: owned rows next to the edge go
+        out, the ghost rows beyond the edge come in."""
+        C_, H, out = self.cols, self.halo, []
+        if self.rank > 0:                                   # upper edge: global rows r0-H..r0 are the peer's, r0..r0+H mine
+            out.append((self.rank - 1, ((self.r0 - self.g0) * C_, (self.r0 - self.g0 + H) * C_), (0, (self.r0 - self.g0) * C_)))
+        if self.rank < self.world - 1:
+            out.append((self.rank + 1, ((self.r1 - H - self.g0) * C_, (self.r1 - self.g0) * C_),
+                        ((self.r1 - self.g0) * C_, (self.g1 - self.g0) * C_)))
+        return out
+
+
+def exchange_strip_states(states: Sequence, plan: GridStripPlan, group=None):
+    """Refresh the ghost rows of every state array (`[..., n_local]` torch tensors, node axis last and contiguous)
+    from the neighbouring ranks (grouped send/recv: NCCL on GPUs, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    ops, keep = [], []
+    for peer, (s0, s1), (q0, q1) in plan.exchanges():
+        for st in states:
+            flat = st.reshape(-1, st.shape[-1])
+            for row in range(flat.shape[0]):
+                snd = flat[row, s0:s1].contiguous()
+                keep.append(snd)
+                ops.append(dist.P2POp(dist.isend, snd, peer, group))
+                ops.append(dist.P2POp(dist.irecv, flat[row, q0:q1], peer, group))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+
+class ShardedGridRun:
+    """Multi-GPU run of `[buckets…, HydroRoute]` on a dense D8 grid with the wave kernel: every rank runs its row
+    strip plus `halo` ghost rows for `halo` steps at a time (`GridDeviceRun.launch_chunk`), then the ghost rows'
+    states are exchanged.  Records stay sharded: `[T][owned cells][R]` per rank, ghost rows are not stored.
+    The forcing passed to `launch` covers the rank's COMPUTED rows: `[T][plan.n_local][V]`."""
+
+    def __init__(self, eng, rows: int, cols: int, T: int, params, *, config=None, initstates=None, halo: int = 16, group=None,
+                 stages: int = 0, max_registers: int = 0, block_threads: int = 0):
+        import torch
+        import torch.distributed as dist
+        from .engine import GridDeviceRun
+
+        self.group = group
+        self.rank, self.world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+        self.plan = GridStripPlan(rows, cols, self.rank, self.world, halo)
+        pl = self.plan
+        self.run = GridDeviceRun(eng, pl.n_local, T, params, config=config, initstates=initstates, variant="wave",
+                                 steps_per_chunk=halo, block_w=block_threads, stages=stages, max_registers=max_registers,
+                                 row_range=(pl.g0, pl.g1))
+        self.T, self.N, self.n_rows = int(T), pl.out_count, self.run.n_rows
+        S = self.run.n_states
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.bucket = [torch.zeros((max(S, 1), pl.n_local), dtype=torch.float64, device=dev) for _ in range(2)]
+        self.river = [torch.zeros(pl.n_local, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.init_bucket = self.init_river = None
+        if "init" in self.run.bufs:
+            self.init_bucket = torch.from_numpy(self.run.bufs["init"].to_host((max(S, 1), pl.n_local))).to(dev)
+        if "rinit" in self.run.bufs:
+            self.init_river = torch.from_numpy(self.run.bufs["rinit"].to_host((pl.n_local,))).to(dev)
+        self.n_inputs = len(self.run.ck.program.stepper.input_names)
+        self.in_bytes, self.out_bytes = T * pl.n_local * self.n_inputs * 8, T * pl.out_count * self.n_rows * 8
+
+    def launch(self, input_ptr: int, rec_ptr: int):
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+        pl, H = self.plan, self.plan.halo
+        cur = 0
+        if self.init_bucket is not None:
+            self.bucket[0].copy_(self.init_bucket)
+        else:
+            self.bucket[0].zero_()
+        if self.init_river is not None:
+            self.river[0].copy_(self.init_river)
+        else:
+            self.river[0].zero_()
+        for t0 in range(0, self.T, H):
+            ns = min(H, self.T - t0)
+            self.run.launch_chunk(input_ptr + t0 * pl.n_local * self.n_inputs * 8, rec_ptr + t0 * pl.out_count * self.n_rows * 8, ns,
+                                  self.bucket[cur].data_ptr(), self.river[cur].data_ptr(),
+                                  self.bucket[cur ^ 1].data_ptr(), self.river[cur ^ 1].data_ptr(),
+                                  pl.out_first, pl.out_count, stream)
+            cur ^= 1
+            if t0 + ns < self.T and self.world > 1:
+                exchange_strip_states([self.bucket[cur], self.river[cur]], pl, self.group)
+
+    def check(self) -> int:
+        return self.run.check()

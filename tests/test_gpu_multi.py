@@ -73,3 +73,80 @@ def test_sharded_grid_routing_matches_single_gpu():
     model, p, init, N = _grid_problem(R, Cc, T)
     single = model(sy.forcing("exphydro", 0, N, T), p, initstates=init)
     assert np.array_equal(got, single)
+
+
+def _strip_worker(rank, world, port, R, Cc, T, halo, q):
+    import torch
+    import torch.distributed as dist
+    from hydromodels_jl_b200 import parallel as par
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    hm.engine.init(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    model, p, init, N = _grid_problem(R, Cc, T)
+    eng = hm.B200Model(model)
+    run = par.ShardedGridRun(eng, R, Cc, T, p, initstates=init, halo=halo)
+    n_lo, n_hi = run.plan.node_range()
+    inp = sy.forcing("exphydro", n_lo, n_hi, T)                     # forcing of the computed rows (ghost rows included)
+    d_in = torch.from_numpy(np.ascontiguousarray(inp.transpose(2, 1, 0))).cuda()
+    rec = torch.zeros((T, run.N, run.n_rows), dtype=torch.float64, device="cuda")
+    run.launch(d_in.data_ptr(), rec.data_ptr())
+    run.launch(d_in.data_ptr(), rec.data_ptr())                     # relaunch must reproduce (states reset)
+    run.check()
+    q.put((run.plan.r0 * Cc, run.plan.r1 * Cc, rec.cpu().numpy().transpose(2, 1, 0)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("R,Cc,T,halo", [(40, 33, 50, 4), (96, 64, 40, 16)])
+def test_sharded_wave_grid_matches_single_gpu(R, Cc, T, halo):
+    """Row strips + ghost rows, states exchanged every `halo` steps (temporal blocking): bit-identical to one GPU."""
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 34500 + (os.getpid() % 2000) + halo
+    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, R, Cc, T, halo, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    model, p, init, N = _grid_problem(R, Cc, T)
+    got = np.zeros((13, N, T))
+    for _ in range(world):
+        a, b, part = q.get(timeout=300)
+        got[:, a:b, :] = part
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    single = model(sy.forcing("exphydro", 0, N, T), p, initstates=init)
+    assert np.array_equal(got, single)
+
+
+def test_strip_of_a_grid_on_one_gpu_matches_the_whole_grid():
+    """The pieces of the sharded wave run that one GPU can check: a strip with ghost rows, chunked launches from explicit
+    states, records of the owned rows only."""
+    import torch
+    from hydromodels_jl_b200 import parallel as par
+    from hydromodels_jl_b200.engine import GridDeviceRun
+    R, Cc, T, halo = 50, 40, 23, 5
+    model, p, init, N = _grid_problem(R, Cc, T)
+    whole = model(sy.forcing("exphydro", 0, N, T), p, initstates=init)
+    eng = hm.B200Model(model)
+    for rank, world in [(0, 3), (1, 3), (2, 3)]:
+        pl = par.GridStripPlan(R, Cc, rank, world, halo)
+        n_lo, n_hi = pl.node_range()
+        run = GridDeviceRun(eng, pl.n_local, T, p, initstates=init, variant="wave", steps_per_chunk=halo, row_range=(pl.g0, pl.g1))
+        d_in = torch.from_numpy(np.ascontiguousarray(sy.forcing("exphydro", n_lo, n_hi, T).transpose(2, 1, 0))).cuda()
+        rec = torch.zeros((T, pl.out_count, 13), dtype=torch.float64, device="cuda")
+        # one chunk of `halo` steps from the initial states: the owned rows are exact (ghost rows may not be)
+        b0 = torch.from_numpy(run.bufs["init"].to_host((2, pl.n_local))).cuda()
+        r0 = torch.from_numpy(run.bufs["rinit"].to_host((pl.n_local,))).cuda()
+        b1, r1 = torch.zeros_like(b0), torch.zeros_like(r0)
+        run.launch_chunk(d_in.data_ptr(), rec.data_ptr(), halo, b0.data_ptr(), r0.data_ptr(), b1.data_ptr(), r1.data_ptr(),
+                         pl.out_first, pl.out_count, None)
+        run.check()
+        got = rec.cpu().numpy().transpose(2, 1, 0)[:, :, :halo]
+        assert np.array_equal(got, whole[:, pl.r0 * Cc:pl.r1 * Cc, :halo])
+        own = slice(pl.out_first, pl.out_first + pl.out_count)
+        assert np.array_equal(b1.cpu().numpy()[:, own], whole[:2, pl.r0 * Cc:pl.r1 * Cc, halo - 1])
+        assert np.array_equal(r1.cpu().numpy()[own], whole[2, pl.r0 * Cc:pl.r1 * Cc, halo - 1])

@@ -148,3 +148,80 @@ def test_route_partition_plans_are_consistent():
         ptr, idx, ng = part.local_csr(r)
         n0, n1 = part.ranges[r]
         assert ptr[-1] == part.up_ptr[n1] - part.up_ptr[n0] and idx.max(initial=0) < (n1 - n0) + ng
+
+
+# ---- temporal blocking for the wave grid kernel: row strips + ghost rows, states exchanged every `halo` steps ----
+def _strip_worker(rank, world, port, R, Cc, T, halo, flw, qu):
+    """The oracle stands in for `GridDeviceRun.launch_chunk`: each rank runs ExpHydro + D8 route on its strip
+    plus ghost rows for `halo` steps from explicit states, then refreshes the ghost rows' states."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import hydro_oracle as ho
+    N = R * Cc
+    pl = par.GridStripPlan(R, Cc, rank, world, halo)
+    n_lo, n_hi = pl.node_range()
+    rows_l = pl.g1 - pl.g0
+    rr, cc = np.divmod(np.arange(pl.n_local), Cc)
+    model = hm.models.exphydro_grid(flw[pl.g0:pl.g1], np.stack([rr + 1, cc + 1], axis=1))
+    rng = np.random.default_rng(3)
+    pg = dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))
+    p = {"params": {k: v[n_lo:n_hi] for k, v in pg.items()}}
+    inp = sy.forcing("exphydro", 0, N, T)[:, n_lo:n_hi, :]
+    states = [torch.zeros(pl.n_local, dtype=torch.float64), torch.full((pl.n_local,), 1303.0, dtype=torch.float64),
+              torch.from_numpy(rng.uniform(0, 2, N)[n_lo:n_hi].copy())]           # snowpack, soilwater, s_river
+    out = np.zeros((13, pl.out_count, T))
+    for t0 in range(0, T, halo):
+        ns = min(halo, T - t0)
+        init = dict(snowpack=states[0].numpy(), soilwater=states[1].numpy(), s_river=states[2].numpy())
+        full = ho.run_model(model, inp[:, :, t0:t0 + ns], p, initstates=init)
+        out[:, :, t0:t0 + ns] = full[:, pl.out_first:pl.out_first + pl.out_count, :]
+        states = [torch.from_numpy(np.ascontiguousarray(full[i, :, -1])) for i in range(3)]
+        if t0 + ns < T:
+            par.exchange_strip_states(states, pl)
+    qu.put((pl.r0 * Cc, pl.r1 * Cc, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,halo", [(2, 3), (3, 2)])
+def test_strip_plan_with_ghost_rows_reproduces_the_whole_grid(world, halo):
+    import hydro_oracle as ho
+    rng = np.random.default_rng(17)
+    R, Cc, T = 11, 6, 10
+    flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128, 0], size=(R, Cc))
+    N = R * Cc
+    ctx = mp.get_context("spawn")
+    qu = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, R, Cc, T, halo, flw, qu)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = np.zeros((13, N, T))
+    for _ in range(world):
+        a, b, part = qu.get(timeout=180)
+        got[:, a:b, :] = part
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    rr, cc = np.divmod(np.arange(N), Cc)
+    model = hm.models.exphydro_grid(flw, np.stack([rr + 1, cc + 1], axis=1))
+    rng = np.random.default_rng(3)
+    pg = dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))
+    init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 2, N))
+    ref = ho.run_model(model, sy.forcing("exphydro", 0, N, T), {"params": pg}, initstates=init)
+    assert np.array_equal(got, ref)          # same arithmetic on every owned cell: bit-identical
+
+
+def test_strip_plan_geometry():
+    for rows, cols, world, halo in [(4096, 4096, 8, 16), (11, 6, 3, 2), (64, 64, 1, 16)]:
+        plans = [par.GridStripPlan(rows, cols, k, world, halo) for k in range(world)]
+        assert plans[0].r0 == 0 and plans[-1].r1 == rows
+        for a, b in zip(plans[:-1], plans[1:]):
+            assert a.r1 == b.r0
+            (pa, sa, qa), = [e for e in a.exchanges() if e[0] == b.rank]
+            (pb, sb, qb), = [e for e in b.exchanges() if e[0] == a.rank]
+            assert sa[1] - sa[0] == qb[1] - qb[0] == halo * cols and sb[1] - sb[0] == qa[1] - qa[0] == halo * cols
+            # what a sends are its last owned rows = b's upper ghost rows, in global numbering
+            assert a.g0 * cols + sa[0] == b.g0 * cols + qb[0] and b.g0 * cols + sb[0] == a.g0 * cols + qa[0]
+        for pl in plans:
+            assert pl.out_first + pl.out_count <= pl.n_local and pl.out_count == (pl.r1 - pl.r0) * cols
