@@ -153,13 +153,57 @@ def cpu_reference_rate(model_name, T, target_seconds=12.0):
             f"(oracle/hydro_oracle.c, OpenMP over node blocks, {cores} threads; best of 2)", cores, rate1)
 
 
+def bench_raster_ingest(args):
+    """D8 flow directions of a 4096 x 4096 DEM and the gather of 3 forcing rasters
+    (30 steps x 4096 x 4096) into the stepper's [T][N][V] layout, both HBM-bound; device-resident, CUDA events."""
+    import torch
+    import ctypes as C
+    import hydromodels_jl_b200 as hm
+    from hydromodels_jl_b200.engine import check, lib
+    hm.engine.init(0)
+    peak, peak_src = peaks()
+    n, T, V = 4096, 30, 3
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    dem = torch.randn(n, n, generator=g, device="cuda", dtype=torch.float64) * 50 + 500
+    flw = torch.empty((n, n), device="cuda", dtype=torch.uint8)
+    cubes = [torch.randn(T, n, n, generator=g, device="cuda", dtype=torch.float64) for _ in range(V)]
+    rr, cc = torch.meshgrid(torch.arange(n, device="cuda", dtype=torch.int32), torch.arange(n, device="cuda", dtype=torch.int32), indexing="ij")
+    d_r, d_c = rr.reshape(-1).contiguous(), cc.reshape(-1).contiguous()
+    ptrs = torch.tensor([c.data_ptr() for c in cubes], dtype=torch.int64, device="cuda")
+    out = torch.empty((T, n * n, V), device="cuda", dtype=torch.float64)
+    res = {}
+    for name, fn, nbytes in [
+            ("d8_flow_direction", lambda: check(lib().hb_d8_flow_direction_device(dem.data_ptr(), n, n, n, 1, 30.0, 30.0, flw.data_ptr(), None)), n * n * 9),
+            ("pack_forcing_trc", lambda: check(lib().hb_pack_forcing_device(ptrs.data_ptr(), V, T, n * n, n, 1, d_r.data_ptr(), d_c.data_ptr(), n * n, out.data_ptr(), None)),
+             T * n * n * V * 16),
+            ("pack_forcing_tcr", lambda: check(lib().hb_pack_forcing_device(ptrs.data_ptr(), V, T, n * n, 1, n, d_r.data_ptr(), d_c.data_ptr(), n * n, out.data_ptr(), None)),
+             T * n * n * V * 16)]:
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        res[name] = {"ms": ms, "algorithmic_GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak}
+    print(json.dumps({"metric": "raster ingest (cells or cell-steps)/s", "value": n * n * T / (res["pack_forcing_trc"]["ms"] * 1e-3), "unit": "cell-timesteps/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": 3, "ms_per_step": res["pack_forcing_trc"]["ms"], "higher_is_better": True,
+                      "dtype": "f64", "data": "synthetic", "config": {"workload": "raster_ingest_4096", "grid": [n, n], "timesteps": T, "variables": V,
+                                                                   "l2": "every launch moves > 1 GB, far beyond the 126 MB L2"},
+                      "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "kernels": res},
+                      "gpu_launches": 3 * (args.steps + 3)}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -181,6 +225,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "raster_ingest_4096":
+        return bench_raster_ingest(args) if rank == 0 else 0
     model_name, N, T = WORKLOADS[args.workload]
     rows_of = {"exphydro": 10, "gr4j": 15, "hbv": 18, "m50": 12, "hbv_ensemble": 0, "exphydro_grid": 13}[model_name]
     v_of = {"exphydro": 3, "gr4j": 2, "hbv": 3, "m50": 3, "hbv_ensemble": 0, "exphydro_grid": 3}[model_name]

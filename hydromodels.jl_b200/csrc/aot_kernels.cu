@@ -153,3 +153,92 @@ extern "C" int hb_sparse_route_conv_device(int n_out, int n_in, int64_t T, int H
     hb_sparse_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
+
+// =============================================================================================
+// Raster ingest (/root/reference/ext/HydroModelsRastersExt):
+//
+// hb_d8_flow_direction — compute_d8_flow_direction (HydroModelsRastersExt.jl:32-109): every cell drains to the
+//   neighbour with the steepest downward slope (center - neighbour) / distance; neighbours visited in the order
+//   E, SE, S, SW, W, NW, N, NE, a later neighbour wins only on a strictly greater slope (max starts at -Inf, so a
+//   pit still points at its least-uphill neighbour); NaN cells get 0 and are skipped as neighbours; diagonal
+//   distance sqrt(cx^2+cy^2), orthogonal distance max(cx, cy).  One thread per cell, a (32+2) x (8+2) tile of the
+//   DEM staged in shared memory so every DEM value is read from HBM once (8 B in, 1 B out per cell).
+//
+// hb_pack_forcing — load_netcdf_data + the assembly of the model input (netcdf_loader.jl:29-62, :119-136): gather
+//   V rasters [T][.][.] at the node positions into the stepper's forcing layout [T][N][V] (= Julia input[V,N,T]).
+//   One thread per (node, step); the V values of a node are written as one contiguous run.
+// =============================================================================================
+namespace {
+
+constexpr int kD8TileW = 32, kD8TileH = 8;
+
+__global__ void __launch_bounds__(kD8TileW *kD8TileH) hb_d8_kernel(const double *__restrict__ dem, int rows, int cols, long long row_stride,
+                                                                   long long col_stride, double dist_orth, double dist_diag,
+                                                                   unsigned char *__restrict__ out) {
+    __shared__ double tile[kD8TileH + 2][kD8TileW + 2];
+    const int c0 = blockIdx.x * kD8TileW, r0 = blockIdx.y * kD8TileH;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int i = threadIdx.x; i < (kD8TileH + 2) * (kD8TileW + 2); i += kD8TileW * kD8TileH) {
+        const int lr = i / (kD8TileW + 2), lc = i % (kD8TileW + 2);
+        const int r = r0 + lr - 1, c = c0 + lc - 1;
+        tile[lr][lc] = (r >= 0 && r < rows && c >= 0 && c < cols) ? dem[r * row_stride + c * col_stride] : nan;   // off-grid == NoData
+    }
+    __syncthreads();
+    const int lc = threadIdx.x % kD8TileW, lr = threadIdx.x / kD8TileW;
+    const int r = r0 + lr, c = c0 + lc;
+    if (r >= rows || c >= cols) return;
+    const double center = tile[lr + 1][lc + 1];
+    int code = 0;
+    if (center == center) {
+        const int dr[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+        const int dc[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+        double best = __longlong_as_double(0xfff0000000000000ll);   // -Inf
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double nb = tile[lr + 1 + dr[k]][lc + 1 + dc[k]];
+            if (nb == nb) {
+                const double slope = (center - nb) / ((k & 1) ? dist_diag : dist_orth);
+                if (slope > best) {
+                    best = slope;
+                    code = 1 << k;
+                }
+            }
+        }
+    }
+    out[(long long)r * cols + c] = (unsigned char)code;
+}
+
+__global__ void __launch_bounds__(256) hb_pack_kernel(const double *const *__restrict__ vars, int n_vars, long long T, long long t_stride,
+                                                      long long row_stride, long long col_stride, const int *__restrict__ node_row,
+                                                      const int *__restrict__ node_col, long long N, double *__restrict__ out) {
+    const long long n = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long t = blockIdx.y;
+    if (n >= N) return;
+    const long long off = t * t_stride + node_row[n] * row_stride + node_col[n] * col_stride;
+    double *o = out + (t * N + n) * n_vars;
+    for (int v = 0; v < n_vars; ++v) o[v] = vars[v][off];
+}
+
+}  // namespace
+
+extern "C" int hb_d8_flow_direction_device(const double *dem, int rows, int cols, int64_t row_stride, int64_t col_stride,
+                                           double cellsize_x, double cellsize_y, uint8_t *flow_dir, void *stream) {
+    if (!dem || !flow_dir || rows <= 0 || cols <= 0 || !(cellsize_x > 0) || !(cellsize_y > 0)) return HB_ERR_INVALID;
+    const double orth = cellsize_x > cellsize_y ? cellsize_x : cellsize_y;          // max(cellsize_x, cellsize_y)
+    const double diag = sqrt(cellsize_x * cellsize_x + cellsize_y * cellsize_y);
+    dim3 grid((unsigned)((cols + kD8TileW - 1) / kD8TileW), (unsigned)((rows + kD8TileH - 1) / kD8TileH));
+    hb_d8_kernel<<<grid, kD8TileW * kD8TileH, 0, (cudaStream_t)stream>>>(dem, rows, cols, row_stride, col_stride, orth, diag, flow_dir);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
+extern "C" int hb_pack_forcing_device(const double *const *vars_device_array, int n_vars, int64_t n_steps, int64_t t_stride,
+                                      int64_t row_stride, int64_t col_stride, const int32_t *node_row, const int32_t *node_col,
+                                      int64_t n_nodes, double *out, void *stream) {
+    if (!vars_device_array || n_vars <= 0 || n_steps < 0 || n_nodes <= 0 || !node_row || !node_col || !out) return HB_ERR_INVALID;
+    if (n_steps == 0) return HB_OK;
+    if (n_steps > 65535) return HB_ERR_INVALID;   // one grid row per step; callers chunk the time axis
+    dim3 grid((unsigned)((n_nodes + 255) / 256), (unsigned)n_steps);
+    hb_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(vars_device_array, n_vars, n_steps, t_stride, row_stride, col_stride, node_row,
+                                                          node_col, n_nodes, out);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}

@@ -118,6 +118,9 @@ def lib():
         "hb_run_route_device": [C.c_void_p, C.POINTER(RouteDesc), C.c_void_p],
         "hb_route_step_device": [C.c_void_p, C.POINTER(RouteDesc), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p],
+        "hb_d8_flow_direction_device": [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p],
+        "hb_pack_forcing_device": [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p, C.c_void_p],
         "hb_malloc_device": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_device": [C.c_void_p],
         "hb_malloc_host": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_host": [C.c_void_p],
         "hb_memcpy_h2d": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],

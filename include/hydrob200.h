@@ -264,6 +264,19 @@ int hb_grid_status(hb_model_t m, void *stream, int32_t *steps_per_launch);
 int hb_sparse_route_conv_device(int n_out, int n_in, int64_t n_steps, int horizon, int64_t nnz, const int32_t *row_ptr,
                                 const int32_t *src, const double *weights, const double *input, double *out, void *stream);
 
+/* ---- raster ingest (/root/reference/ext/HydroModelsRastersExt) -------------------------------------------------
+ * compute_d8_flow_direction (HydroModelsRastersExt.jl:32-109): steepest-descent D8 codes (1 E, 2 SE, 4 S, 8 SW, 16 W,
+ * 32 NW, 64 N, 128 NE; 0 for NaN cells) from a DEM.  dem[r * row_stride + c * col_stride] (element strides: a Julia
+ * matrix is row_stride 1, col_stride rows); flow_dir is [rows][cols] row-major, the layout hb_grid_desc.flwdir takes. */
+int hb_d8_flow_direction_device(const double *dem, int32_t rows, int32_t cols, int64_t row_stride, int64_t col_stride,
+                                double cellsize_x, double cellsize_y, uint8_t *flow_dir, void *stream);
+/* load_netcdf_data + input assembly (netcdf_loader.jl:29-62, :119-136): gather `n_vars` rasters (DEVICE array of DEVICE
+ * pointers; element (t, r, c) at t * t_stride + r * row_stride + c * col_stride) at the node positions (0-based) into
+ * the stepper's forcing layout out[n_steps][n_nodes][n_vars].  n_steps <= 65535 per call. */
+int hb_pack_forcing_device(const double *const *vars_device_array, int32_t n_vars, int64_t n_steps, int64_t t_stride,
+                           int64_t row_stride, int64_t col_stride, const int32_t *node_row, const int32_t *node_col,
+                           int64_t n_nodes, double *out, void *stream);
+
 /* ---- memory helpers (so a host without a CUDA binding can own device / pinned buffers) ---- */
 int hb_malloc_device(void **ptr, int64_t bytes);
 int hb_free_device(void *ptr);
