@@ -10,7 +10,7 @@ from .components import (Chain, ConstantInterpolation, Dense, DiscreteSolver, Gr
                          HydroBucket, HydroConfig, HydroFlux, HydroModel, HydroRoute, ImmutableSolver,
                          LinearInterpolation, MutableSolver, NeuralFlux, ODESolver, SolverType, StateFlux,
                          UnitHydrograph, build_aggr_func, default_config, normalize_config)
-from . import irf, models, rasters
+from . import calibration, irf, models, rasters
 from .lowering import LoweringError, lower_stepper
 from .engine import B200Model, HydroB200Error, NoDeviceError, device_count
 

@@ -1,0 +1,169 @@
+"""Calibration on the device: the reference's `OptimizationProblem(component, input, target; …)`
+(`/root/reference/ext/HydroModelsOptimizationExt/HydroModelsOptimizationExt.jl:72-199`) and a population optimiser
+driving the ensemble objective kernel without host round trips.
+
+The reference's objective evaluates ONE parameter vector per call on the host and is handed to Optimization.jl
+(BlackBoxOptim's adaptive DE in every example, `docs/src/tutorials/optimimal_parameters.md:189-195`).  Here:
+
+* `OptimizationProblem(...)` keeps the reference's keywords (`metric`, `loss`-less, `warm_up`, `lb_pas`, `ub_pas`,
+  `fixed_params`, `default_initstates`) and offers `prob.objective(p)` — same value the reference's closure returns —
+  and `prob.objective_batch(P)` for a whole population in one launch (`B200Model.objective`, ensemble mode);
+* `solve(prob, DifferentialEvolution(...), maxiters=…)` runs DE/rand/1/bin entirely on the GPU: per generation
+  `hb_de_trial_device` (mutation + crossover + bounds) writes the trial population straight into the stepper's
+  parameter buffer, `hb_run_device` in objective mode scores it, `hb_de_select_device` keeps the better member and
+  records the generation's best — three kernels on one stream, nothing crosses PCIe until the end.
+
+Models with unit hydrographs are not supported by the device loop (their ordinates are host-evaluated per parameter
+set); use `objective_batch` from a host optimiser for those.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Mapping, Optional, Sequence
+
+import numpy as np
+
+from .components import Component
+
+
+@dataclass
+class DifferentialEvolution:
+    """DE/rand/1/bin.  `popsize` members, differential weight `F`, crossover rate `CR`."""
+    popsize: int = 1024
+    F: float = 0.7
+    CR: float = 0.9
+    seed: int = 0
+
+
+@dataclass
+class Solution:
+    u: np.ndarray                      # best calibrated vector (order = prob.calibrated)
+    params: Dict[str, float]           # all parameters, fixed ones included
+    objective: float
+    history: np.ndarray                # best objective after every generation (index 0 = initial population)
+    n_evaluations: int
+    population: np.ndarray             # final population [popsize, D]
+    fitness: np.ndarray
+    gpu_launches: int = 0
+    elapsed_s: float = 0.0
+    extras: dict = field(default_factory=dict)
+
+
+class OptimizationProblem:
+    """`OptimizationProblem(component, input[V, T], target[T]; metric, warm_up, lb_pas, ub_pas, fixed_params,
+    default_initstates)` for a single-node component.  Parameters named in `fixed_params` keep their value, all others
+    are calibrated within `[lb_pas, ub_pas]` (sequences in the order of `calibrated`, or mappings by name)."""
+
+    def __init__(self, component: Component, input, target, *, metric: str = "NSE", warm_up: int = 1, lb_pas=None, ub_pas=None,
+                 fixed_params: Optional[Mapping] = None, default_initstates: Optional[Mapping] = None, config=None):
+        from .engine import METRICS, B200Model
+        if metric.lower() not in METRICS:
+            raise ValueError(f"Unknown metric: {metric}. Supported metrics: KGE, NSE, LogKGE, MSE")
+        self.component, self.metric, self.warm_up, self.config = component, metric, int(warm_up), config
+        self.input = np.asarray(input, dtype=np.float64)
+        self.target = np.asarray(target, dtype=np.float64)
+        if self.input.ndim != 2 or self.target.shape != (self.input.shape[1],):
+            raise ValueError("input must be [variables, time] and target [time]")
+        fixed = dict(fixed_params.get("params", fixed_params)) if fixed_params else {}
+        names = list(component.get_param_names())
+        unknown = [k for k in fixed if k not in names]
+        if unknown:
+            raise KeyError(f"fixed parameters {unknown} are not parameters of the component")
+        self.fixed = {k: float(v) for k, v in fixed.items()}
+        self.calibrated: List[str] = [nm for nm in names if nm not in self.fixed]
+
+        def bounds(b, what):
+            if b is None:
+                raise ValueError(f"{what} is required: the device optimiser samples inside the bounds")
+            if isinstance(b, Mapping):
+                b = [b[nm] for nm in self.calibrated]
+            b = np.asarray(b, dtype=np.float64).reshape(-1)
+            if b.size != len(self.calibrated):
+                raise ValueError(f"{what} has {b.size} entries for {len(self.calibrated)} calibrated parameters")
+            return b
+        self.lb, self.ub = bounds(lb_pas, "lb_pas"), bounds(ub_pas, "ub_pas")
+        if np.any(self.ub < self.lb):
+            raise ValueError("ub_pas < lb_pas")
+        self.initstates = None if default_initstates is None else {k: float(v) for k, v in default_initstates.items()}
+        self.engine = B200Model(component)
+
+    def _params(self, P: np.ndarray) -> Dict:
+        P = np.atleast_2d(np.asarray(P, dtype=np.float64))
+        d = {nm: np.ascontiguousarray(P[:, j]) for j, nm in enumerate(self.calibrated)}
+        d.update({k: np.array([v]) for k, v in self.fixed.items()})
+        return {"params": d}
+
+    def objective_batch(self, P) -> np.ndarray:
+        """Objective of every row of `P[n, D]` (minimised: -NSE, -KGE, -LogKGE or MSE), one ensemble launch."""
+        P = np.atleast_2d(np.asarray(P, dtype=np.float64))
+        n = P.shape[0]
+        init = None if self.initstates is None else {k: np.full(n, v) for k, v in self.initstates.items()}
+        return self.engine.objective(self.input, self._params(P), self.target, metric=self.metric, warm_up=self.warm_up,
+                                     config=self.config, initstates=init, n_members=n)
+
+    def objective(self, p) -> float:
+        """The reference's closure `(p, c) -> loss(target[warm_up:end], component(input, p, c)[end, warm_up:end])`."""
+        return float(self.objective_batch(np.asarray(p, dtype=np.float64)[None, :])[0])
+
+
+def solve(prob: OptimizationProblem, alg: Optional[DifferentialEvolution] = None, *, maxiters: int = 100) -> Solution:
+    """Differential evolution on the device; returns the best member after `maxiters` generations."""
+    import time
+    from .engine import DeviceBuffer, DeviceRun, check, lib
+    alg = alg or DifferentialEvolution()
+    N, D = int(alg.popsize), len(prob.calibrated)
+    if N < 4:
+        raise ValueError("differential evolution needs at least 4 members")
+    if D == 0:
+        raise ValueError("nothing to calibrate: every parameter is fixed")
+    eng = prob.engine
+    if eng._has_uh():
+        raise NotImplementedError("the device loop does not cover unit-hydrograph models (host-evaluated ordinates); "
+                                  "drive prob.objective_batch from a host optimiser instead")
+    T = prob.input.shape[1]
+    rng = np.random.default_rng(alg.seed)
+    P0 = prob.lb + rng.random((N, D)) * (prob.ub - prob.lb)
+    init = None if prob.initstates is None else {k: np.full(N, v) for k, v in prob.initstates.items()}
+    run = DeviceRun(eng, N, T, prob._params(P0), config=prob.config, initstates=init, objective=prob.metric,
+                    target=prob.target, warm_up=prob.warm_up, ensemble=True)
+    slots = run.ck.program.param_slots
+    off_of = {nm: int(run._host[0][j]) for j, (nm, _) in enumerate(slots)}
+    missing = [nm for nm in prob.calibrated if nm not in off_of]
+    if missing:
+        raise KeyError(f"calibrated parameters {missing} are not used by the model's kernels")
+    dim_off = np.array([off_of[nm] for nm in prob.calibrated], dtype=np.int64)
+    n_flat = run.n_param_values
+    trial = run.bufs["params"]                                         # the stepper reads the TRIAL population
+    flat0 = trial.to_host((n_flat,))
+    pop = DeviceBuffer.from_host(flat0)
+    d_off, d_lb, d_ub = DeviceBuffer.from_host(dim_off), DeviceBuffer.from_host(prob.lb), DeviceBuffer.from_host(prob.ub)
+    fit, tfit, hist = DeviceBuffer(N * 8), DeviceBuffer(N * 8), DeviceBuffer((maxiters + 1) * 16)
+    inp = prob.input if prob.input.flags.f_contiguous else np.asfortranarray(prob.input)
+    d_in = DeviceBuffer.from_host(inp.ravel(order="K"))
+    L = lib()
+    t0 = time.perf_counter()
+    run.launch(d_in.ptr, fit.ptr, None)                                # initial population (the trial buffer holds it)
+    # generation 0 bookkeeping: "select" of the population against itself records the best
+    check(L.hb_de_select_device(pop.ptr, trial.ptr, fit.ptr, fit.ptr, d_off.ptr, D, N, hist.ptr, 0, None))
+    launches = 3
+    for g in range(1, maxiters + 1):
+        check(L.hb_de_trial_device(pop.ptr, trial.ptr, d_off.ptr, D, N, d_lb.ptr, d_ub.ptr, float(alg.F), float(alg.CR),
+                                   C.c_uint64(alg.seed), g, None))
+        run.launch(d_in.ptr, tfit.ptr, None)
+        check(L.hb_de_select_device(pop.ptr, trial.ptr, fit.ptr, tfit.ptr, d_off.ptr, D, N, hist.ptr, g, None))
+        launches += 4
+    check(L.hb_stream_synchronize(None))
+    elapsed = time.perf_counter() - t0
+    flat = pop.to_host((n_flat,))
+    fitness = fit.to_host((N,))
+    history = hist.to_host((maxiters + 1, 2))
+    population = np.stack([flat[o:o + N] for o in dim_off], axis=1)
+    best = int(np.argmin(fitness))
+    params = dict(prob.fixed)
+    params.update({nm: float(population[best, j]) for j, nm in enumerate(prob.calibrated)})
+    for b in (pop, d_off, d_lb, d_ub, fit, tfit, hist, d_in):
+        b.free()
+    return Solution(u=population[best].copy(), params=params, objective=float(fitness[best]), history=history[:, 0].copy(),
+                    n_evaluations=N * (maxiters + 1), population=population, fitness=fitness, gpu_launches=launches,
+                    elapsed_s=elapsed)

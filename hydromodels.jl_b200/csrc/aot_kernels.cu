@@ -242,3 +242,117 @@ extern "C" int hb_pack_forcing_device(const double *const *vars_device_array, in
                                                           node_col, n_nodes, out);
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
+
+// =============================================================================================
+// On-device calibration: differential evolution DE/rand/1/bin around the ensemble
+// objective kernel (hb_stepper, objective mode).  The reference builds an Optimization.jl problem whose objective
+// runs the model once per candidate on the host (ext/HydroModelsOptimizationExt/...jl:153-175) and hands it to
+// BlackBoxOptim's DE (docs/src/tutorials/optimimal_parameters.md:189-195); here a whole population is one launch
+// of the ensemble kernel and mutation / crossover / selection are two small kernels in between, so a generation
+// never leaves the device.  Populations are stored exactly as the stepper reads its parameters: dimension d of
+// member i at base[dim_off[d] + i] (parameter-major, member-fastest).
+// Random numbers are counter based (SplitMix64 of seed, generation, member, draw index), so the sequence does not
+// depend on the launch geometry and the numpy restatement in oracle/ reproduces it bit for bit; the arithmetic
+// uses explicit round-to-nearest operations (no FMA contraction) for the same reason.
+// =============================================================================================
+namespace {
+
+__device__ __forceinline__ double hb_de_uniform(unsigned long long seed, unsigned gen, unsigned member, unsigned k) {
+    unsigned long long c = ((unsigned long long)gen << 40) ^ ((unsigned long long)member << 8) ^ (unsigned long long)k;
+    unsigned long long z = seed + (c + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * 1.1102230246251565e-16;   // [0, 1)
+}
+
+__global__ void __launch_bounds__(256) hb_de_trial_kernel(const double *__restrict__ pop, double *__restrict__ trial,
+                                                          const long long *__restrict__ dim_off, int D, int N,
+                                                          const double *__restrict__ lb, const double *__restrict__ ub, double F,
+                                                          double CR, unsigned long long seed, unsigned gen) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    // three distinct members, all different from i: offsets o1, o2, o3 in 1..N-1, pairwise distinct
+    int o1 = 1 + (int)(hb_de_uniform(seed, gen, i, 0) * (N - 1));
+    int o2 = 1 + (int)(hb_de_uniform(seed, gen, i, 1) * (N - 2));
+    int o3 = 1 + (int)(hb_de_uniform(seed, gen, i, 2) * (N - 3));
+    if (o1 > N - 1) o1 = N - 1;
+    if (o2 > N - 2) o2 = N - 2;
+    if (o3 > N - 3) o3 = N - 3;
+    if (o2 >= o1) ++o2;
+    const int lo = o1 < o2 ? o1 : o2, hi = o1 < o2 ? o2 : o1;
+    if (o3 >= lo) ++o3;
+    if (o3 >= hi) ++o3;
+    const int r1 = (i + o1) % N, r2 = (i + o2) % N, r3 = (i + o3) % N;
+    int jrand = (int)(hb_de_uniform(seed, gen, i, 3) * D);
+    if (jrand > D - 1) jrand = D - 1;
+    for (int d = 0; d < D; ++d) {
+        const double *p = pop + dim_off[d];
+        double v = p[i];
+        if (hb_de_uniform(seed, gen, i, 4 + d) < CR || d == jrand) v = __dadd_rn(p[r1], __dmul_rn(F, __dsub_rn(p[r2], p[r3])));
+        v = v < lb[d] ? lb[d] : v;
+        v = v > ub[d] ? ub[d] : v;
+        trial[dim_off[d] + i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) hb_de_select_kernel(double *__restrict__ pop, const double *__restrict__ trial, double *__restrict__ fit,
+                                                           const double *__restrict__ trial_fit, const long long *__restrict__ dim_off, int D,
+                                                           int N) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    if (trial_fit[i] <= fit[i]) {          // a NaN objective never replaces a member
+        fit[i] = trial_fit[i];
+        for (int d = 0; d < D; ++d) pop[dim_off[d] + i] = trial[dim_off[d] + i];
+    }
+}
+
+// best (lowest) objective of the population and its first index -> hist[2*slot], hist[2*slot+1]; one block
+__global__ void __launch_bounds__(1024) hb_de_best_kernel(const double *__restrict__ fit, int N, double *__restrict__ hist, int slot) {
+    __shared__ double sv[1024];
+    __shared__ int si[1024];
+    double bv = __longlong_as_double(0x7ff0000000000000ll);
+    int bi = -1;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        const double v = fit[i];
+        if (v < bv) { bv = v; bi = i; }
+    }
+    sv[threadIdx.x] = bv;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const double v = sv[threadIdx.x + s];
+            const int j = si[threadIdx.x + s];
+            if (j >= 0 && (v < sv[threadIdx.x] || si[threadIdx.x] < 0 || (v == sv[threadIdx.x] && j < si[threadIdx.x]))) {
+                sv[threadIdx.x] = v;
+                si[threadIdx.x] = j;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        hist[2 * slot] = sv[0];
+        hist[2 * slot + 1] = (double)si[0];
+    }
+}
+
+}  // namespace
+
+extern "C" int hb_de_trial_device(const double *pop, double *trial, const int64_t *dim_offset, int n_dims, int n_members,
+                                  const double *lower, const double *upper, double F, double CR, uint64_t seed, uint32_t generation,
+                                  void *stream) {
+    if (!pop || !trial || !dim_offset || !lower || !upper || n_dims <= 0 || n_members < 4) return HB_ERR_INVALID;
+    hb_de_trial_kernel<<<(n_members + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pop, trial, (const long long *)dim_offset, n_dims, n_members,
+                                                                                lower, upper, F, CR, seed, generation);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
+extern "C" int hb_de_select_device(double *pop, const double *trial, double *fitness, const double *trial_fitness,
+                                   const int64_t *dim_offset, int n_dims, int n_members, double *history, int history_slot, void *stream) {
+    if (!pop || !trial || !fitness || !trial_fitness || !dim_offset || n_dims <= 0 || n_members <= 0) return HB_ERR_INVALID;
+    hb_de_select_kernel<<<(n_members + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pop, trial, fitness, trial_fitness,
+                                                                                 (const long long *)dim_offset, n_dims, n_members);
+    if (history) hb_de_best_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(fitness, n_members, history, history_slot);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}

@@ -211,7 +211,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
 
 #if HB_MODE == 1
     // objective accumulators (shifted sums; metrics of …OptimizationExt.jl:34-68)
-    double q_n = 0.0, q_so = 0.0, q_ss = 0.0, q_soo = 0.0, q_sss = 0.0, q_sos = 0.0, q_sse = 0.0, q_shift = 0.0;
+    double q_n = 0.0, q_so = 0.0, q_ss = 0.0, q_soo = 0.0, q_sss = 0.0, q_sos = 0.0, q_sse = 0.0, q_shift = 0.0, q_shift_s = 0.0;
 #endif
 
     //@@HB:PROLOGUE
@@ -314,8 +314,10 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
             o = log(o + 1e-6);
             s = log(s + 1e-6);
 #endif
-            if (q_n == 0.0) q_shift = o;
-            const double od = o - q_shift, sd = s - q_shift, e = o - s;
+            // each series is shifted by its OWN first value: a simulated series many orders of magnitude below the observed
+            // one (degenerate parameter sets are routine inside a calibration) keeps its variance and covariance
+            if (q_n == 0.0) { q_shift = o; q_shift_s = s; }
+            const double od = o - q_shift, sd = s - q_shift_s, e = o - s;
             q_n += 1.0; q_so += od; q_ss += sd;
             q_soo = fma(od, od, q_soo); q_sss = fma(sd, sd, q_sss); q_sos = fma(od, sd, q_sos);
             q_sse = fma(e, e, q_sse);
@@ -347,7 +349,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
         const double cov = q_sos - q_so * q_ss / q_n;
         const double r = cov / sqrt(var_o * var_s);
         const double alpha = sqrt(var_s / var_o);          // std(sim)/std(obs), (n-1) cancels
-        const double beta = (q_ss + q_n * q_shift) / (q_so + q_n * q_shift);
+        const double beta = (q_ss + q_n * q_shift_s) / (q_so + q_n * q_shift);
         val = -(1.0 - sqrt((r - 1.0) * (r - 1.0) + (alpha - 1.0) * (alpha - 1.0) + (beta - 1.0) * (beta - 1.0)));
 #endif
         a.obj[n] = val;

@@ -277,6 +277,22 @@ int hb_pack_forcing_device(const double *const *vars_device_array, int32_t n_var
                            int64_t row_stride, int64_t col_stride, const int32_t *node_row, const int32_t *node_col,
                            int64_t n_nodes, double *out, void *stream);
 
+/* ---- on-device calibration: differential evolution around the ensemble objective kernel -----------------------
+ * Replaces the host loop `solve(OptimizationProblem(component, input, target; ...), BBO_adaptive_de_rand_1_bin...)`
+ * (/root/reference/ext/HydroModelsOptimizationExt/HydroModelsOptimizationExt.jl:72-199, docs/src/tutorials/
+ * optimimal_parameters.md:189-195) for population methods: candidates live where the stepper reads its parameters
+ * (dimension d of member i at base[dim_offset[d] + i]); one generation = hb_de_trial_device, hb_run_device in
+ * objective mode on the trial buffer, hb_de_select_device — all DEVICE pointers, asynchronous on `stream`.
+ * DE/rand/1/bin, clamped to [lower, upper]; counter-based SplitMix64 draws keyed by (seed, generation, member). */
+int hb_de_trial_device(const double *pop, double *trial, const int64_t *dim_offset, int32_t n_dims, int32_t n_members,
+                       const double *lower, const double *upper, double F, double CR, uint64_t seed, uint32_t generation,
+                       void *stream);
+/* trial replaces member where trial_fitness <= fitness; `history` (optional, DEVICE [2 * slots]) receives the best
+ * objective of the population and its index at slot `history_slot`. */
+int hb_de_select_device(double *pop, const double *trial, double *fitness, const double *trial_fitness,
+                        const int64_t *dim_offset, int32_t n_dims, int32_t n_members, double *history, int32_t history_slot,
+                        void *stream);
+
 /* ---- memory helpers (so a host without a CUDA binding can own device / pinned buffers) ---- */
 int hb_malloc_device(void **ptr, int64_t bytes);
 int hb_free_device(void *ptr);

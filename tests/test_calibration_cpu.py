@@ -1,0 +1,60 @@
+"""CPU-only: the numpy restatement of the device DE kernels (oracle/hydro_oracle.py: de_uniform, de_trial, de_select)
+and the host-side checks of `calibration.OptimizationProblem` (keywords of the reference's
+`ext/HydroModelsOptimizationExt/HydroModelsOptimizationExt.jl:72-199`)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import hydromodels_jl_b200 as hm
+from hydromodels_jl_b200 import calibration as cal
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+import hydro_oracle as ho  # noqa: E402
+
+
+def test_de_draws_are_uniform_and_counter_based():
+    u = ho.de_uniform(42, 3, np.arange(200_000), 7)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3 and abs(u.var() - 1 / 12) < 2e-3
+    assert np.array_equal(u[:10], ho.de_uniform(42, 3, np.arange(10), 7))           # a function of the counter only
+    assert not np.array_equal(u[:10], ho.de_uniform(42, 4, np.arange(10), 7))
+    assert ho.de_uniform(0, 0, 0, 0) == (np.uint64(0xE220A8397B1DCDAF) >> np.uint64(11)) * 2.0 ** -53   # SplitMix64(0) known answer
+
+
+@pytest.mark.parametrize("N,D", [(4, 1), (5, 3), (64, 6), (1000, 13)])
+def test_de_trial_indices_are_distinct_and_trials_stay_in_bounds(N, D):
+    rng = np.random.default_rng(N)
+    lb, ub = -rng.random(D), 1 + rng.random(D)
+    pop = lb + rng.random((N, D)) * (ub - lb)
+    for gen in (1, 2, 77):
+        trial, (r1, r2, r3) = ho.de_trial(pop, lb, ub, 0.9, 0.5, 7, gen)
+        i = np.arange(N)
+        assert np.all((r1 != i) & (r2 != i) & (r3 != i) & (r1 != r2) & (r1 != r3) & (r2 != r3))
+        assert np.all((0 <= r1) & (r1 < N) & (0 <= r3) & (r3 < N))
+        assert np.all(trial >= lb) and np.all(trial <= ub)
+        assert np.all(np.any(trial != pop, axis=1) | (N < 6))                         # jrand: at least one mutated dimension
+    keep_pop, keep_fit = ho.de_select(pop, trial, np.zeros(N), np.where(np.arange(N) % 2 == 0, -1.0, np.nan))
+    assert np.array_equal(keep_pop[::2], trial[::2]) and np.array_equal(keep_pop[1::2], pop[1::2])   # NaN never wins
+    assert np.array_equal(keep_fit, np.where(np.arange(N) % 2 == 0, -1.0, 0.0))
+
+
+def test_optimization_problem_keywords():
+    model = hm.models.exphydro()
+    inp, tgt = np.zeros((3, 10)), np.zeros(10)
+    lb, ub = [-3, 0, 0, 100, 10, 0], [0, 3, 5, 2000, 50, 0.1]
+    prob = cal.OptimizationProblem(model, inp, tgt, metric="KGE", warm_up=2, lb_pas=lb, ub_pas=ub)
+    assert prob.calibrated == model.get_param_names() and prob.fixed == {}
+    prob = cal.OptimizationProblem(model, inp, tgt, lb_pas=dict(Tmin=-3, Tmax=0, Df=0, Smax=100), ub_pas=dict(Tmin=0, Tmax=3, Df=5, Smax=2000),
+                                   fixed_params={"params": dict(Qmax=18.47, f=0.0167)})
+    assert prob.calibrated == ["Tmin", "Tmax", "Df", "Smax"] and prob.fixed == dict(Qmax=18.47, f=0.0167)
+    p = prob._params(np.array([[-1.0, 1.0, 2.0, 1500.0]]))["params"]
+    assert p["Smax"][0] == 1500.0 and p["f"][0] == 0.0167
+    with pytest.raises(ValueError, match="Unknown metric"):
+        cal.OptimizationProblem(model, inp, tgt, metric="rmse", lb_pas=lb, ub_pas=ub)
+    with pytest.raises(ValueError, match="lb_pas is required"):
+        cal.OptimizationProblem(model, inp, tgt)
+    with pytest.raises(KeyError, match="not parameters of the component"):
+        cal.OptimizationProblem(model, inp, tgt, lb_pas=lb, ub_pas=ub, fixed_params=dict(nope=1.0))
+    with pytest.raises(ValueError, match="entries"):
+        cal.OptimizationProblem(model, inp, tgt, lb_pas=lb[:3], ub_pas=ub)

@@ -1,0 +1,118 @@
+"""GPU: on-device calibration — DE kernels bit-exact against their numpy restatement, the
+problem's objective equal to the reference's closure evaluated with the oracle, and a planted-truth calibration."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import hydromodels_jl_b200 as hm
+from hydromodels_jl_b200 import calibration as cal
+from hydromodels_jl_b200 import synthetic as sy
+from hydromodels_jl_b200.engine import DeviceBuffer, check, lib
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+import hydro_oracle as ho  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+LB = np.array([-3.0, 0.0, 0.5, 500.0, 5.0, 0.005])
+UB = np.array([0.0, 3.0, 5.0, 2500.0, 40.0, 0.1])
+TRUE = np.array([-2.09, 0.17, 2.674, 1709.46, 18.47, 0.0167])        # docs/src/get_start_en.md:288-301
+INIT = dict(snowpack=0.0, soilwater=1303.0)
+
+
+def _problem(T=730, metric="NSE", **kw):
+    model = hm.models.exphydro()
+    inp = sy.forcing("exphydro", 0, 1, T)[:, 0, :]
+    p = {"params": dict(zip(model.get_param_names(), TRUE))}
+    target = ho.run_model(model, inp, p, initstates=INIT)[-1]
+    return model, inp, target, cal.OptimizationProblem(model, inp, target, metric=metric, warm_up=30, lb_pas=LB, ub_pas=UB,
+                                                       default_initstates=INIT, **kw)
+
+
+@pytest.mark.parametrize("N,D,offs", [(4, 1, [0]), (37, 3, [0, 37, 74]), (1000, 6, [0, 1000, 2001, 3001, 4001, 5002])])
+def test_de_kernels_match_the_numpy_restatement_bit_for_bit(N, D, offs):
+    rng = np.random.default_rng(N + D)
+    lb, ub = -rng.random(D), 1 + rng.random(D)
+    pop = lb + rng.random((N, D)) * (ub - lb)
+    n_flat = offs[-1] + N + 3
+    flat = rng.random(n_flat)                                           # values between the dimensions must survive
+    for d in range(D):
+        flat[offs[d]:offs[d] + N] = pop[:, d]
+    d_pop, d_trial = DeviceBuffer.from_host(flat), DeviceBuffer.from_host(flat)
+    d_off = DeviceBuffer.from_host(np.array(offs, dtype=np.int64))
+    d_lb, d_ub = DeviceBuffer.from_host(lb), DeviceBuffer.from_host(ub)
+    for gen in (1, 5):
+        check(lib().hb_de_trial_device(d_pop.ptr, d_trial.ptr, d_off.ptr, D, N, d_lb.ptr, d_ub.ptr, 0.7, 0.9, 12345, gen, None))
+        got = d_trial.to_host((n_flat,))
+        ref, _ = ho.de_trial(pop, lb, ub, 0.7, 0.9, 12345, gen)
+        assert np.array_equal(np.stack([got[o:o + N] for o in offs], axis=1), ref)
+        mask = np.ones(n_flat, bool)
+        for o in offs:
+            mask[o:o + N] = False
+        assert np.array_equal(got[mask], flat[mask])
+    fit, tfit = rng.random(N), rng.random(N)
+    tfit[::7] = np.nan
+    d_fit, d_tfit, d_hist = DeviceBuffer.from_host(fit), DeviceBuffer.from_host(tfit), DeviceBuffer.from_host(np.zeros(4))
+    check(lib().hb_de_select_device(d_pop.ptr, d_trial.ptr, d_fit.ptr, d_tfit.ptr, d_off.ptr, D, N, d_hist.ptr, 1, None))
+    new_pop, new_fit = ho.de_select(pop, ref, fit, tfit)
+    got = d_pop.to_host((n_flat,))
+    assert np.array_equal(np.stack([got[o:o + N] for o in offs], axis=1), new_pop)
+    assert np.array_equal(d_fit.to_host((N,)), new_fit)
+    hist = d_hist.to_host((4,))
+    assert hist[2] == new_fit.min() and int(hist[3]) == int(np.argmin(new_fit))
+
+
+@pytest.mark.parametrize("metric", ["NSE", "KGE", "LogKGE", "MSE"])
+def test_problem_objective_is_the_references_closure(metric):
+    model, inp, target, prob = _problem(T=400, metric=metric)
+    rng = np.random.default_rng(1)
+    P = LB + rng.random((5, 6)) * (UB - LB)
+    got = prob.objective_batch(P)
+    for k in range(5):
+        sim = ho.run_model(model, inp, {"params": dict(zip(model.get_param_names(), P[k]))}, initstates=INIT)[-1]
+        ref = ho.objective(metric.lower(), target, sim, warm_up=30)    # loss(target[warm_up:end], output[end, warm_up:end])
+        if metric == "LogKGE" and np.std(np.log(sim[29:] + 1e-6)) < 1e-8:
+            # a flow of ~1e-17 mm/d: log(sim + 1e-6) is constant to 11 digits and its correlation is ill-conditioned in
+            # ANY arithmetic (the two-pass oracle keeps ~4 digits here); the kernel must stay finite and close
+            assert got[k] == pytest.approx(ref, rel=1e-6)
+            continue
+        assert got[k] == pytest.approx(ref, rel=1e-9, abs=1e-12)
+    assert prob.objective(P[2]) == got[2]
+    assert prob.objective(TRUE) == pytest.approx(0.0 if metric == "MSE" else -1.0, abs=1e-9)
+
+
+def test_device_de_recovers_planted_parameters_and_follows_the_oracle_loop():
+    model, inp, target, prob = _problem()
+    alg = cal.DifferentialEvolution(popsize=512, F=0.7, CR=0.9, seed=3)
+    sol = cal.solve(prob, alg, maxiters=150)
+    assert sol.objective < -0.999 and sol.n_evaluations == 512 * 151 and sol.gpu_launches == 3 + 4 * 150
+    assert np.all(np.diff(sol.history) <= 0) and sol.history[-1] == sol.objective == sol.fitness.min()
+    assert np.all(sol.population >= LB) and np.all(sol.population <= UB)
+    assert prob.objective(sol.u) == pytest.approx(sol.objective, rel=1e-12)
+    # the snow and flow parameters are identifiable from 2 years of synthetic flow
+    assert abs(sol.params["Smax"] - TRUE[3]) / TRUE[3] < 0.1 and abs(sol.params["f"] - TRUE[5]) / TRUE[5] < 0.1
+    # same loop on the host with the oracle kernels and the device objective: identical trajectory for a few generations
+    rng = np.random.default_rng(alg.seed)
+    pop = LB + rng.random((512, 6)) * (UB - LB)
+    fit = prob.objective_batch(pop)
+    hist = [fit.min()]
+    for g in range(1, 6):
+        trial, _ = ho.de_trial(pop, LB, UB, alg.F, alg.CR, alg.seed, g)
+        pop, fit = ho.de_select(pop, trial, fit, prob.objective_batch(trial))
+        hist.append(fit.min())
+    assert np.array_equal(np.array(hist), sol.history[:6])
+
+
+def test_fixed_parameters_and_unsupported_models():
+    model, inp, target, _ = _problem(T=365)
+    prob = cal.OptimizationProblem(model, inp, target, warm_up=30, lb_pas=LB[[0, 1, 2, 3]], ub_pas=UB[[0, 1, 2, 3]],
+                                   fixed_params=dict(Qmax=TRUE[4], f=TRUE[5]), default_initstates=INIT)
+    sol = cal.solve(prob, cal.DifferentialEvolution(popsize=128, seed=1), maxiters=60)
+    assert sol.objective < -0.99 and sol.params["Qmax"] == TRUE[4] and sol.u.shape == (4,)
+    gr4j = hm.models.gr4j()
+    with pytest.raises(NotImplementedError, match="unit-hydrograph"):
+        probg = cal.OptimizationProblem(gr4j, np.ones((2, 50)), np.ones(50), lb_pas=[100, -5, 20, 1.1], ub_pas=[1200, 3, 300, 2.9])
+        cal.solve(probg, cal.DifferentialEvolution(popsize=8), maxiters=1)
