@@ -8,7 +8,7 @@ from .symbolic import (Const, Eq, Equation, Expr, Sym, Symbols, clamp, exp, hmax
                        sqrt, step_func, tanh, variables)
 from .components import (Chain, ConstantInterpolation, Dense, DiscreteSolver, GraphAggregation, GridAggregation,
                          HydroBucket, HydroConfig, HydroFlux, HydroModel, HydroRoute, ImmutableSolver,
-                         LinearInterpolation, MutableSolver, NeuralFlux, ODESolver, SolverType, StateFlux,
+                         LinearInterpolation, MutableSolver, NeuralBucket, NeuralFlux, ODESolver, SolverType, StateFlux,
                          UnitHydrograph, build_aggr_func, default_config, normalize_config)
 from . import calibration, irf, models, rasters
 from .lowering import LoweringError, lower_stepper

@@ -303,6 +303,47 @@ class NeuralFlux(Component):
         self.name = name or f"##neural_flux#{chain.name}"
 
 
+class NeuralBucket(Component):
+    """`NeuralBucket(; name, flux_network, state_network, output_network, n_inputs, n_states, n_outputs, inputs, states,
+    outputs, htypes)` (`/root/reference/src/nn.jl:195-262`): an RNN-style bucket,
+
+        flux_t  = flux_network(vcat(S_{t-1}, x_t))
+        S_t     = S_{t-1} + state_network(vcat(S_{t-1}, flux_t))     (residual update — no `min_value` clamp)
+        y_t     = output_network(flux_t)
+
+    returning `[states; outputs]` like a `HydroBucket` (`:308-326`).  The three chains' parameters are `params[:nns]`
+    entries named after the chains and are shared by all nodes (`:329-358`)."""
+
+    def __init__(self, *, name: str, flux_network: "Chain", state_network: "Chain", output_network: "Chain", n_inputs: int,
+                 n_states: int, n_outputs: int, inputs: Sequence[str], states: Sequence[str], outputs: Sequence[str], htypes=None):
+        if len(inputs) != n_inputs:
+            raise AssertionError("Number of input names must match n_inputs")
+        if len(states) != n_states:
+            raise AssertionError("Number of state names must match n_states")
+        if len(outputs) != n_outputs:
+            raise AssertionError("Number of output names must match n_outputs")
+        n_fluxes = flux_network.n_out
+        if flux_network.n_in != n_states + n_inputs:
+            raise DimensionMismatchError(f"flux_network takes {flux_network.n_in} inputs, expected n_states + n_inputs = {n_states + n_inputs}")
+        if state_network.n_in != n_states + n_fluxes or state_network.n_out != n_states:
+            raise DimensionMismatchError(f"state_network must map n_states + n_fluxes = {n_states + n_fluxes} => n_states = {n_states}")
+        if output_network.n_in != n_fluxes or output_network.n_out != n_outputs:
+            raise DimensionMismatchError(f"output_network must map n_fluxes = {n_fluxes} => n_outputs = {n_outputs}")
+        self.name = name
+        self.flux_network, self.state_network, self.output_network = flux_network, state_network, output_network
+        self.n_inputs, self.n_states, self.n_outputs, self.n_fluxes = n_inputs, n_states, n_outputs, n_fluxes
+        self.input_names = [str(getattr(v, "name", v)) for v in inputs]
+        self.state_names = [str(getattr(v, "name", v)) for v in states]
+        self.output_names = [str(getattr(v, "name", v)) for v in outputs]
+        self.param_names = []
+        self.nn_names = [flux_network.name, state_network.name, output_network.name]
+        self.htypes = None if htypes is None else np.asarray(htypes, dtype=np.int64)
+
+    @property
+    def has_states(self) -> bool:
+        return True
+
+
 # ---------------------------------------------------------------------------------------
 # Bucket
 # ---------------------------------------------------------------------------------------

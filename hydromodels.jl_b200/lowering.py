@@ -35,7 +35,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .components import (Component, HydroBucket, HydroFlux, HydroModel, HydroRoute, NeuralFlux, StateFlux,
+from .components import (Component, HydroBucket, HydroFlux, HydroModel, HydroRoute, NeuralBucket, NeuralFlux, StateFlux,
                          UnitHydrograph)
 from .symbolic import Call, Const, Expr, Sym, evaluate, walk
 
@@ -258,7 +258,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
     for c in comps:
         if isinstance(c, HydroRoute):
             raise LoweringError("HydroRoute is a grid-coupled component; it is lowered by lower_route")
-        if not isinstance(c, (HydroBucket, HydroFlux, UnitHydrograph)):
+        if not isinstance(c, (HydroBucket, HydroFlux, UnitHydrograph, NeuralBucket)):
             raise LoweringError(f"cannot lower component of type {type(c).__name__}")
     b = _Builder(fast)
 
@@ -317,22 +317,29 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
     uh_steps: List[Tuple[int, int]] = []      # (uh index, val id of x_t)
     statements: List[Tuple[str, object]] = []  # ordered side effects ('update', (sidx, val)), …
 
+    raw_states = set()                        # states updated without the min_value clamp (NeuralBucket)
+
+    def nn_outputs(chain, ins: Tuple[int, ...]) -> List[int]:
+        ni = net_index(chain)
+        mask = 0
+        for i in ins:
+            mask |= b.vals[i].mask
+        out = []
+        for j in range(chain.n_out):
+            vid = b.opaque("nn", (ni, ins, j), mask)
+            # erased key / versions so that pre/post twins of an NN output can be carried
+            v = b.vals[vid]
+            v.erased = ("nn", ni, tuple(b.vals[i].erased for i in ins), j)
+            v.vers = frozenset().union(*[b.vals[i].vers for i in ins]) if ins else frozenset()
+            v.args = ins
+            out.append(vid)
+        return out
+
     def eval_fluxes(bucket: HydroBucket, local: Dict[str, int], ptab: Dict[str, int]) -> Dict[str, int]:
         outs = {}
         for f in bucket.fluxes:
             if isinstance(f, NeuralFlux):
-                ni = net_index(f.chain)
-                ins = tuple(local[i] for i in f.input_names)
-                mask = 0
-                for i in ins:
-                    mask |= b.vals[i].mask
-                for j, o in enumerate(f.output_names):
-                    vid = b.opaque("nn", (ni, ins, j), mask)
-                    # erased key / versions so that pre/post twins of an NN output can be carried
-                    v = b.vals[vid]
-                    v.erased = ("nn", ni, tuple(b.vals[i].erased for i in ins), j)
-                    v.vers = frozenset().union(*[b.vals[i].vers for i in ins]) if ins else frozenset()
-                    v.args = ins
+                for o, vid in zip(f.output_names, nn_outputs(f.chain, tuple(local[i] for i in f.input_names))):
                     local[o] = outs[o] = vid
             else:
                 for eq in f.eqs:
@@ -370,6 +377,23 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
             for s, si in zip(c.state_names, sidx):
                 env[s] = state_post[si]
             env.update(outs)
+        elif isinstance(c, NeuralBucket):
+            # /root/reference/src/nn.jl:270-291: fluxes from the PREVIOUS state, residual state update (no clamp),
+            # outputs from those same fluxes; rows = [new states; outputs] (:308-326)
+            htype_set(c)
+            sidx = [state_names.index(s) for s in c.state_names]
+            pre = tuple(b.leaf_state(si, 0) for si in sidx)
+            xs = tuple(env[i] for i in c.input_names)
+            flux = tuple(nn_outputs(c.flux_network, pre + xs))
+            delta = nn_outputs(c.state_network, pre + flux)
+            for si, du in zip(sidx, delta):
+                state_post[si] = b.leaf_state(si, 1)
+                raw_states.add(si)
+                statements.append(("update", (si, b.leaf_state(si, 0), du)))
+            for o, vid in zip(c.output_names, nn_outputs(c.output_network, flux)):
+                env[o] = vid
+            for s, si in zip(c.state_names, sidx):
+                env[s] = state_post[si]
         elif isinstance(c, HydroFlux):
             ptab = param_table(c)
             local = {i: env[i] for i in c.input_names}
@@ -502,7 +526,10 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
         i = v.id
         if v.op == "state" and v.payload[1] == 1:
             si = v.payload[0]                         # all increments of its bucket precede this leaf
-            step.append(f"const double hb_un{si} = hb_max(hb_minv, hb_u[{si}] + {step_ref(pending_updates[si][2])});")
+            if si in raw_states:
+                step.append(f"const double hb_un{si} = hb_u[{si}] + {step_ref(pending_updates[si][2])};")
+            else:
+                step.append(f"const double hb_un{si} = hb_max(hb_minv, hb_u[{si}] + {step_ref(pending_updates[si][2])});")
             continue
         if i not in live or v.mask == 0 or v.op in ("const", "in", "param", "state") or i in carried:
             continue

@@ -402,3 +402,51 @@ def test_sparse_route_convolution_matches_oracle():
     K2 = irf.SparseRouteKernel(np.array([[1, 2], [3, 1], [3, 2]]), rng.random((3, 8)), 3, 2)
     x2 = rng.random((2, 5))
     assert_parity(irf.SparseRouteConvolution(K2)(x2), ho.sparse_route_convolution(K2.indices, K2.weights, 3, 2, x2))
+
+
+# ---- NeuralBucket (/root/reference/src/nn.jl:195-371) ---------------------------------------------
+def _neural_bucket(N=None, hidden=16):
+    from hydromodels_jl_b200.components import Chain, Dense
+    flux = Chain((Dense(5, hidden, "tanh"), Dense(hidden, 4, "leakyrelu")), "flux_net")
+    state = Chain((Dense(6, hidden, "tanh"), Dense(hidden, 2, "identity")), "state_net")
+    outp = Chain((Dense(4, hidden, "tanh"), Dense(hidden, 2, "identity")), "output_net")
+    nb = hm.NeuralBucket(name="nb", flux_network=flux, state_network=state, output_network=outp, n_inputs=3, n_states=2, n_outputs=2,
+                         inputs=["prcp", "temp", "lday"], states=["s1", "s2"], outputs=["et", "q"],
+                         htypes=None if N is None else np.ones(N, dtype=int))
+    rng = np.random.default_rng(9)
+    p = {"params": {}, "nns": {c.name: c.init_params(i) * 0.6 + rng.normal(0, 0.03, c.n_params) for i, c in enumerate((flux, state, outp))}}
+    return nb, p
+
+
+@pytest.mark.parametrize("N,T,tensor", [(None, 60, True), (64, 40, True), (37, 25, True), (37, 25, False), (1000, 30, True)])
+def test_neural_bucket_matches_oracle(N, T, tensor):
+    """RNN-style bucket: fluxes from the previous state, residual update without a clamp, outputs from those fluxes; the dense
+    layers run on the FP64 tensor path where they fit (`tensor`) or per thread; single-node, aligned, ragged shapes."""
+    nb, p = _neural_bucket(N)
+    rng = np.random.default_rng(T)
+    x = rng.normal(size=(3, T) if N is None else (3, N, T))
+    init = dict(s1=0.3, s2=-0.2) if N is None else dict(s1=rng.normal(size=N), s2=rng.normal(size=N))
+    eng = hm.B200Model(nb, nn_tensor=tensor)
+    got = eng(x, p, initstates=init)
+    ref = ho.run_component(nb, x, p, initstates=init)
+    assert got.shape == ref.shape == ((4, T) if N is None else (4, N, T))
+    assert_parity(got, ref)
+    assert_parity(eng(x, p), ho.run_component(nb, x, p))                     # default (zero) initial states
+    if N is not None and N >= 64:       # nodes are independent: a 5-node run reproduces the first 5 nodes
+        sub = hm.B200Model(_neural_bucket(5)[0], nn_tensor=tensor)(x[:, :5], p, initstates={k: v[:5] for k, v in init.items()})
+        assert_parity(got[:, :5], sub)
+
+
+def test_neural_bucket_inside_a_model():
+    """A NeuralBucket is an AbstractHydroBucket: it sequences with other components in a HydroModel (`src/nn.jl:175-176`)."""
+    N, T = 48, 30
+    nb, p = _neural_bucket(N)
+    s = hm.Symbols("et q total", "k")
+    post = hm.HydroFlux("total ~ k * (q + et)", symbols=s, htypes=np.ones(N, dtype=int))
+    model = hm.HydroModel(components=[nb, post], name="nb_model")
+    assert model.var_names == ["s1", "s2", "et", "q", "total"]
+    p = {"params": dict(k=np.array([0.5])), "nns": p["nns"]}
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(3, N, T))
+    init = dict(s1=rng.normal(size=N), s2=np.zeros(N))
+    assert_parity(model(x, p, initstates=init), ho.run_model(model, x, p, initstates=init))
