@@ -137,3 +137,48 @@ def test_grid_2048x2048_d8_routing():
     ps = {"params": {k: v[idx] for k, v in pp.items()}}
     ref = ho.run_model(sub, inp, ps, initstates={k: v[idx] for k, v in init.items()})
     assert_parity(got, ref)
+
+
+def test_grid_2048x2048_wave_kernel_is_bit_identical_to_the_two_pass_path():
+    """BASELINE config 5 at one GPU's size, all eight D8 directions + sinks: the single-pass wave kernel (32 768 blocks, four
+    launches of <= 16 steps, 4 blocks per SM exchanging outflows through L2) against the generic stepper + per-step route path —
+    every one of the 4.19 M x 50 x 13 values, plus a relaunch (tickets / tags reset) and the strip + ghost-row decomposition."""
+    import torch
+    import bench
+    from hydromodels_jl_b200.engine import GridDeviceRun
+    from hydromodels_jl_b200 import parallel as par
+    hm.engine.init(0)
+    side, T = 2048, 50
+    N = side * side
+    rng = np.random.default_rng(1)
+    flw = rng.choice(np.array([1, 2, 4, 8, 16, 32, 64, 128, 0]), size=(side, side), p=[.25, .2, .25, .05, .05, .05, .05, .05, .05])
+    rr, cc = np.divmod(np.arange(N), side)
+    model = hm.models.exphydro_grid(flw, np.stack([rr + 1, cc + 1], axis=1))
+    p = {"params": dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 2.0, N))}
+    init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 1, N))
+    d_in = bench.device_forcing(torch, "exphydro", N, T, 5)
+    st = torch.cuda.current_stream().cuda_stream
+    eng = hm.B200Model(model)
+    ref = torch.empty((T, N, 13), device="cuda", dtype=torch.float64)
+    RoutedDeviceRun(eng, N, T, p, initstates=init).launch(d_in.data_ptr(), ref.data_ptr(), st)
+    got = torch.zeros((T, N, 13), device="cuda", dtype=torch.float64)
+    run = GridDeviceRun(eng, N, T, p, initstates=init, variant="wave", steps_per_chunk=16)
+    for _ in range(2):
+        got.zero_()
+        run.launch(d_in.data_ptr(), got.data_ptr(), st)
+        assert run.check() == 16
+        assert bool(torch.equal(got, ref))
+    assert float(ref[:, :, 12].max()) > float(ref[:, :, 11].max())           # routing did accumulate flow
+    # the middle strip of a 4-way decomposition, 16 ghost rows either side, first 16 steps from the initial states
+    pl = par.GridStripPlan(side, side, 1, 4, 16)
+    n_lo, n_hi = pl.node_range()
+    strip = GridDeviceRun(eng, pl.n_local, T, p, initstates=init, variant="wave", steps_per_chunk=16, row_range=(pl.g0, pl.g1))
+    s_in = d_in[:, n_lo:n_hi, :].contiguous()
+    s_out = torch.zeros((16, pl.out_count, 13), device="cuda", dtype=torch.float64)
+    b0 = torch.from_numpy(strip.bufs["init"].to_host((2, pl.n_local))).cuda()
+    r0 = torch.from_numpy(strip.bufs["rinit"].to_host((pl.n_local,))).cuda()
+    b1, r1 = torch.zeros_like(b0), torch.zeros_like(r0)
+    strip.launch_chunk(s_in.data_ptr(), s_out.data_ptr(), 16, b0.data_ptr(), r0.data_ptr(), b1.data_ptr(), r1.data_ptr(),
+                       pl.out_first, pl.out_count, st)
+    strip.check()
+    assert bool(torch.equal(s_out, ref[:16, pl.r0 * side:pl.r1 * side, :]))

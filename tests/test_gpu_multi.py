@@ -101,9 +101,10 @@ def _strip_worker(rank, world, port, R, Cc, T, halo, q):
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("R,Cc,T,halo", [(40, 33, 50, 4), (96, 64, 40, 16)])
 def test_sharded_wave_grid_matches_single_gpu(R, Cc, T, halo):
-    """Row strips + ghost rows, states exchanged every `halo` steps (temporal blocking): bit-identical to one GPU."""
+    """Row strips + ghost rows, states exchanged every `halo` steps (temporal blocking): bit-identical to one GPU.  Uses
+    up to 4 GPUs when the box has them (interior ranks exchange with two neighbours)."""
     import torch.multiprocessing as mp
-    world = 2
+    world = min(_ngpu(), 4)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 34500 + (os.getpid() % 2000) + halo
