@@ -197,6 +197,51 @@ def bench_raster_ingest(args):
     return 0
 
 
+def bench_irf(args):
+    """SparseRouteConvolution on a synthetic river network — 65 536 nodes, 8 source rows per destination
+    (nnz = 524 288), horizon 32, 3650 steps: 2 * nnz * T * H = 1.2e11 flop per pass, FP64-FMA bound."""
+    import torch
+    import ctypes as C
+    import hydromodels_jl_b200 as hm
+    from hydromodels_jl_b200.engine import check, lib
+    hm.engine.init(0)
+    n, per, H, T = 65536, 8, 32, 3650
+    nnz = n * per
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    row_ptr = (torch.arange(n + 1, device="cuda", dtype=torch.int32) * per).contiguous()
+    # sources: the destination itself and 7 nodes a short way "upstream" of it (river networks are local in node order)
+    src = (torch.arange(n, device="cuda").view(n, 1) - torch.randint(0, 256, (n, per), generator=g, device="cuda")).clamp_(min=0)
+    src[:, 0] = torch.arange(n, device="cuda")
+    src = src.to(torch.int32).reshape(-1).contiguous()
+    w = torch.rand(H, nnz, generator=g, device="cuda", dtype=torch.float64) / H
+    x = torch.rand(T, n, generator=g, device="cuda", dtype=torch.float64)
+    out = torch.empty(T, n, device="cuda", dtype=torch.float64)
+    L = lib()
+    L.hb_sparse_route_conv_device.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64] + [C.c_void_p] * 6
+    fn = lambda: check(L.hb_sparse_route_conv_device(n, n, T, H, nnz, row_ptr.data_ptr(), src.data_ptr(), w.data_ptr(), x.data_ptr(), out.data_ptr(), None))
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    flop = 2.0 * nnz * T * H
+    v = C.c_double()
+    L.hb_probe_fp64_tflops(C.byref(v))
+    peak, peak_src = peaks()
+    print(json.dumps({"metric": "node-timesteps/sec of the IRF routing convolution", "value": n * T / (ms * 1e-3), "unit": "node-timesteps/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "irf_route_65536x3650_h32", "nodes": n, "nnz": nnz, "horizon": H, "timesteps": T},
+                      "roofline": {"bound": "fp64", "achieved": flop / ms / 1e9, "peak": v.value, "unit": "TFLOP/s", "frac": flop / ms / 1e9 / v.value,
+                                   "peak_source": "measured DFMA probe (hb_probe_fp64_tflops)", "kernel": "hb_sparse_conv", "kernel_ms": ms,
+                                   "hbm_GBps_compulsory": (2 * n * T * 8 + nnz * H * 8) / ms / 1e6, "hbm_peak": peak},
+                      "gpu_launches": args.steps + 3}))
+    return 0
+
+
 def bench_calibration(args):
     """differential evolution on the device — ExpHydro, 65 536 members x 10 years x `steps`
     generations; every generation is trial kernel + ensemble objective kernel + selection kernel, no host round trip."""
@@ -230,7 +275,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096", "calibrate_exphydro"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096", "calibrate_exphydro", "irf_route"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -256,6 +301,8 @@ def main():
         return bench_raster_ingest(args) if rank == 0 else 0
     if args.workload == "calibrate_exphydro":
         return bench_calibration(args) if rank == 0 else 0
+    if args.workload == "irf_route":
+        return bench_irf(args) if rank == 0 else 0
     model_name, N, T = WORKLOADS[args.workload]
     rows_of = {"exphydro": 10, "gr4j": 15, "hbv": 18, "m50": 12, "hbv_ensemble": 0, "exphydro_grid": 13}[model_name]
     v_of = {"exphydro": 3, "gr4j": 2, "hbv": 3, "m50": 3, "hbv_ensemble": 0, "exphydro_grid": 3}[model_name]

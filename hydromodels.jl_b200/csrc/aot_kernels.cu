@@ -2,6 +2,7 @@
 // bench.py (FP64 FMA peak for the compute-bound roofline, L2 flush) and exported through the C-ABI.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/hydrob200.h"
 
@@ -144,13 +145,104 @@ __global__ void __launch_bounds__(256) hb_sparse_conv_kernel(int n_out, int n_in
 }
 }  // namespace
 
+namespace {
+// Register-tiled variant (horizon <= HP): a thread owns one destination and TT = 8 consecutive time steps.  For one kernel
+// row it keeps the 8 input values that the current lag needs in a register ring (moving to the next lag loads ONE new
+// value), so a row costs TT + H - 1 input loads for TT * H multiply-adds instead of TT * H loads; the row's H weights are
+// staged once per block in shared memory (the 8 warps of a block are 8 time tiles of the same 32 destinations).  Same
+// operation order as the kernel above (lags ascending inside a row, rows in CSR order), so the results are bit-identical.
+template <int HP>
+__global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in, long long T, int H, long long nnz,
+                                                            const int *__restrict__ row_ptr, const int *__restrict__ src,
+                                                            const double *__restrict__ w, const double *__restrict__ in,
+                                                            double *__restrict__ out) {
+    constexpr int TT = 8;
+    __shared__ double sw[HP][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = blockIdx.x * 32 + lane;
+    const long long t0 = ((long long)blockIdx.y * 8 + warp) * TT;
+    const int r_begin = d < n_out ? row_ptr[d] : 0;
+    const int nrows = d < n_out ? row_ptr[d + 1] - r_begin : 0;
+    int maxrows = nrows;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, maxrows, o);
+        maxrows = other > maxrows ? other : maxrows;
+    }
+    double total[TT];
+#pragma unroll
+    for (int k = 0; k < TT; ++k) total[k] = 0.0;
+    // the weights of row r+1 are fetched into registers while row r is being computed (their latency would otherwise sit
+    // between the two block barriers of every row)
+    double wn[HP / 8];
+    int src_next = 0;
+#pragma unroll
+    for (int i = 0; i < HP / 8; ++i) wn[i] = (0 < nrows && warp + 8 * i < H) ? w[(long long)(warp + 8 * i) * nnz + r_begin] : 0.0;
+    if (0 < nrows) src_next = src[r_begin];
+    for (int r = 0; r < maxrows; ++r) {
+        const bool has = r < nrows;
+        const long long row = (long long)r_begin + r;
+        const int src_row = src_next;
+        __syncthreads();                                   // the previous row's weights are no longer read
+#pragma unroll
+        for (int i = 0; i < HP / 8; ++i) sw[warp + 8 * i][lane] = wn[i];
+        __syncthreads();
+        {
+            const bool has_next = r + 1 < nrows;
+#pragma unroll
+            for (int i = 0; i < HP / 8; ++i) wn[i] = (has_next && warp + 8 * i < H) ? w[(long long)(warp + 8 * i) * nnz + row + 1] : 0.0;
+            if (has_next) src_next = src[row + 1];
+        }
+        if (has && t0 < T) {
+            const double *x = in + src_row;
+            double ring[TT], acc[TT];
+#pragma unroll
+            for (int k = 0; k < TT; ++k) {
+                ring[k] = (t0 + k < T) ? x[(t0 + k) * n_in] : 0.0;
+                acc[k] = 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < HP / TT; ++c) {
+#pragma unroll
+                for (int j = 0; j < TT; ++j) {
+                    const int l = c * TT + j;
+                    if (l > 0) {                           // lag l needs x[t0 - l] in place of x[t0 + TT - l]
+                        const long long m = t0 - l;
+                        ring[(TT - j) % TT] = (m >= 0 && l < H) ? x[m * n_in] : 0.0;   // before the series starts: nothing to add
+                    }
+                    const double wl = sw[l][lane];
+#pragma unroll
+                    for (int k = 0; k < TT; ++k) acc[k] = fma(wl, ring[(k - j + TT) % TT], acc[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < TT; ++k) total[k] += acc[k];
+        }
+    }
+    if (d < n_out) {
+#pragma unroll
+        for (int k = 0; k < TT; ++k)
+            if (t0 + k < T) out[(t0 + k) * n_out + d] = total[k];
+    }
+}
+}  // namespace
+
 extern "C" int hb_sparse_route_conv_device(int n_out, int n_in, int64_t T, int H, int64_t nnz, const int32_t *row_ptr,
                                            const int32_t *src, const double *weights, const double *input, double *out,
                                            void *stream) {
     if (n_out <= 0 || n_in <= 0 || T < 0 || H <= 0 || nnz < 0 || !row_ptr || !out) return HB_ERR_INVALID;
     if (T == 0) return HB_OK;
-    dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((T + 7) / 8));
-    hb_sparse_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
+    const bool naive = H > 64 || getenv("HB_IRF_NAIVE") != nullptr;
+    if (naive) {
+        dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((T + 7) / 8));
+        hb_sparse_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
+    } else {
+        dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((T + 63) / 64));
+        if (H <= 32)
+            hb_sparse_conv_tiled<32><<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
+        else
+            hb_sparse_conv_tiled<64><<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
+    }
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
 

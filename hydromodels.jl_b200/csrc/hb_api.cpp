@@ -225,6 +225,7 @@ struct hb_model_s {
     int block = 128;
     int uhw_total = 0, uhh_total = 0;
     int wave_tc = 0;            // WAVE grid kernel: steps per launch after clamping
+    int wave_qslots = 2;        // WAVE grid kernel: outflow words per cell
     bool wave_err_init = false;
     CUdeviceptr nn_const = 0;   // module-scope __constant__ hb_nn_const[]
     // workspace for hb_run (host-pointer entry point)
@@ -819,6 +820,8 @@ int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out)
         auto up128 = [](int x) { return (x + 127) / 128 * 128; };
         const int warps = m->block / 32;
         const int obuf = getenv("HB_WAVE_OBUF") ? atoi(getenv("HB_WAVE_OBUF")) : 3;     // tuning: record tiles per warp (2 or 3)
+        m->wave_qslots = getenv("HB_WAVE_QSLOTS") ? atoi(getenv("HB_WAVE_QSLOTS")) : 2; // tuning: outflow words per cell (2..8)
+        if (m->wave_qslots < 2 || m->wave_qslots > 8) { delete m; return fail(HB_ERR_INVALID, "HB_WAVE_QSLOTS must be 2..8"); }
         if (obuf < 2 || obuf > 4) { delete m; return fail(HB_ERR_INVALID, "HB_WAVE_OBUF must be 2..4"); }
         m->dyn_smem = warps * (up128(stages * 32 * spec->n_inputs * 8) + up128(obuf * 32 * spec->n_rows * 8)) + warps * stages * 8;
         if (m->dyn_smem > 227 * 1024) { delete m; return fail(HB_ERR_INVALID, "wave kernel needs %d bytes of shared memory", m->dyn_smem); }
@@ -836,9 +839,9 @@ int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out)
         snprintf(defs, sizeof defs,
                  "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_NPS %d\n#define HB_RV %d\n"
                  "#define HB_SROW %d\n#define HB_OROW %d\n#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n"
-                 "#define HB_UHW_TOTAL 0\n#define HB_UHH_TOTAL 0\n#define HB_NN_WORDS 0\n#define HB_OBUF %d\n",
+                 "#define HB_UHW_TOTAL 0\n#define HB_UHH_TOTAL 0\n#define HB_NN_WORDS 0\n#define HB_OBUF %d\n#define HB_QSLOTS %d\n",
                  spec->n_inputs, spec->n_rows, spec->n_states, spec->n_params, spec->n_params_stepper, spec->n_route_inputs, spec->s_row,
-                 spec->o_row, m->block, stages, minblocks, obuf);
+                 spec->o_row, m->block, stages, minblocks, obuf, m->wave_qslots);
         m->kernel_name = "hb_grid_wave";
     } else if (spec->variant == HB_GRID_TILE) {
         if (tc < 1 || tc > 8 || bw % 32 || bw < 32 || bh < 1 || bw * bh > 1024 || bw - 2 * tc < 1 || bh - 2 * tc < 1) {
@@ -912,9 +915,10 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
     if (wave) {
         if ((rc = wave_steps_per_launch(m, d->cols, &tc))) return rc;
         m->wave_tc = tc;
-        if ((rc = ws_reserve(m->ws[4], (size_t)2 * N * 16))) return rc;      // {outflow, step tag} words, two slots
+        const size_t qslots = (size_t)m->wave_qslots;
+        if ((rc = ws_reserve(m->ws[4], qslots * N * 16))) return rc;          // {outflow, step tag} words, ring over the step index
         if ((rc = ws_reserve(m->ws[6], 256))) return rc;
-        HB_CUDA(cudaMemsetAsync(m->ws[4].p, 0, (size_t)2 * N * 16, st));      // tags = 0: nothing published yet
+        HB_CUDA(cudaMemsetAsync(m->ws[4].p, 0, qslots * N * 16, st));         // tags = 0: nothing published yet
         HB_CUDA(cudaMemsetAsync(m->ws[6].p, 0, 4, st));                       // ticket (the error word [1] is sticky)
         if (!m->wave_err_init) { HB_CUDA(cudaMemsetAsync((char *)m->ws[6].p + 4, 0, 4, st)); m->wave_err_init = true; }
     }

@@ -63,7 +63,7 @@ struct HbWaveArgs {
     const double *rs_in;      // [N] river state at the start of the chunk (NULL: zeros)
     double *rs_out;
     const unsigned char *flw; // [rows][cols] D8 codes (anything else: sink)
-    double *qbuf;             // [2][N] words {q, tag}: outflow of step t in half (t & 1), tag = t + 1
+    double *qbuf;             // [HB_QSLOTS][N] words {q, tag}: outflow of step t in slot t % HB_QSLOTS, tag = t + 1
     int *unused;
     u32 *ticket;              // [0] block ticket (monotone over the run), [1] error flag
     i64 N;
@@ -133,6 +133,9 @@ __device__ __forceinline__ i64 hb_peek(const double *slot, double &v) {
 
 //@@HB:HELPERS
 
+#ifndef HB_QSLOTS
+#define HB_QSLOTS 2               // outflow words per cell (ring over the step index); > 2 relaxes the back-pressure on the downstream cell
+#endif
 #ifndef HB_SPIN_LIMIT
 #define HB_SPIN_LIMIT (1 << 22)   // polls (with back-off ~ 0.1-0.2 us each) before a warp gives up
 #endif
@@ -288,7 +291,11 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
             // ---- river part of step i-1: poll the upstream words (= gather) and the downstream word ----
             const i64 t_abs = a.t0 + (i - 1);
             const i64 need = t_abs + 1;
-            const double *qb = a.qbuf + 2 * ((t_abs & 1) * a.N + nc);
+            const double *qb = a.qbuf + 2 * ((t_abs % HB_QSLOTS) * a.N + nc);
+            // back-pressure: publishing step t+1 overwrites step t+1-HB_QSLOTS, which the downstream cell read in ITS river part
+            // of that step, i.e. before it published step t+2-HB_QSLOTS (tag t+3-HB_QSLOTS)
+            const i64 bp_step = t_abs + 2 - HB_QSLOTS;
+            const double *qdown = a.qbuf + 2 * ((((bp_step % HB_QSLOTS) + HB_QSLOTS) % HB_QSLOTS) * a.N + nc + down_off);
             double qin[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) qin[k] = 0.0;
@@ -304,7 +311,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
                     if ((pending >> k) & 1u) ptag[k] = hb_peek(qb - 2 * ((i64)kDr[k] * a.cols + kDc[k]), pv[k]);
                 }
                 ptag[8] = 0;
-                if ((pending >> 8) & 1u) ptag[8] = hb_peek(qb + 2 * down_off, pv[8]);
+                if ((pending >> 8) & 1u) ptag[8] = hb_peek(qdown, pv[8]);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     if (((pending >> k) & 1u) && ptag[k] == need) {
@@ -312,7 +319,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
                         pending &= ~(1u << k);
                     }
                 }
-                if (((pending >> 8) & 1u) && ptag[8] >= need) pending &= ~(1u << 8);
+                if (((pending >> 8) & 1u) && ptag[8] >= bp_step + 1) pending &= ~(1u << 8);
                 if (pending) {
                     if (++spins > HB_SPIN_LIMIT) {
                         gave_up = true;
@@ -337,7 +344,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
             for (int v = 0; v < HB_RV; ++v) xr[v] = xr_next[v];
             q_cur = hb_rflux(xr, rs, hb_p + HB_NPS);
             const i64 t_abs = a.t0 + i;
-            if (valid) hb_publish(a.qbuf + 2 * ((t_abs & 1) * a.N + nc), q_cur, t_abs + 1);
+            if (valid) hb_publish(a.qbuf + 2 * ((t_abs % HB_QSLOTS) * a.N + nc), q_cur, t_abs + 1);
         }
         if (i > 0) {
             // ---- record of step i-1 leaves ------------------------------------------------------------------

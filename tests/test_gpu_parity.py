@@ -404,6 +404,25 @@ def test_sparse_route_convolution_matches_oracle():
     assert_parity(irf.SparseRouteConvolution(K2)(x2), ho.sparse_route_convolution(K2.indices, K2.weights, 3, 2, x2))
 
 
+@pytest.mark.parametrize("n,per,H,T", [(70, 3, 16, 203), (33, 5, 32, 64), (100, 2, 40, 130), (40, 4, 64, 77), (20, 2, 70, 150), (5, 1, 1, 9)])
+def test_sparse_route_convolution_tiled_kernel(n, per, H, T, monkeypatch):
+    """The register-tiled kernel (horizon <= 64: ring of 8 inputs per thread, weights staged in shared memory) against the
+    oracle and, bit for bit, against the one-thread-per-(destination, step) kernel: ragged time tiles, horizons that are not a
+    multiple of the tile, T shorter than the horizon, destinations with different row counts, horizon > 64 (falls back)."""
+    from hydromodels_jl_b200 import irf
+    rng = np.random.default_rng(n * H)
+    rows = [(d + 1, int(s) + 1) for d in range(n) for s in rng.choice(n, size=rng.integers(0, per + 1), replace=False)]
+    if not rows:
+        rows = [(1, 1)]
+    K = irf.SparseRouteKernel(np.array(rows), rng.random((len(rows), H)) / H, n, n)
+    x = rng.normal(size=(n, T))
+    conv = irf.SparseRouteConvolution(K)
+    got = conv(x)
+    assert_parity(got, ho.sparse_route_convolution(K.indices, K.weights, n, n, x))
+    monkeypatch.setenv("HB_IRF_NAIVE", "1")
+    assert np.array_equal(conv(x), got)
+
+
 # ---- NeuralBucket (SURVEY.md §8f row 4, /root/reference/src/nn.jl:195-371) ---------------------------------------------
 def _neural_bucket(N=None, hidden=16):
     from hydromodels_jl_b200.components import Chain, Dense
