@@ -146,21 +146,36 @@ __global__ void __launch_bounds__(256) hb_sparse_conv_kernel(int n_out, int n_in
 }  // namespace
 
 namespace {
-// Register-tiled variant (horizon <= HP): a thread owns one destination and TT = 8 consecutive time steps.  For one kernel
-// row it keeps the 8 input values that the current lag needs in a register ring (moving to the next lag loads ONE new
-// value), so a row costs TT + H - 1 input loads for TT * H multiply-adds instead of TT * H loads; the row's H weights are
-// staged once per block in shared memory (the 8 warps of a block are 8 time tiles of the same 32 destinations).  Same
-// operation order as the kernel above (lags ascending inside a row, rows in CSR order), so the results are bit-identical.
+// Tiled variant (horizon <= HP): a block owns 32 destinations x 64 time steps (8 warps x 8 steps), a thread one destination
+// and TT = 8 consecutive steps.  Per kernel row the block stages, with cp.async straight into shared memory and one row
+// AHEAD of the arithmetic (double buffer), the row's H weights and the 64 + H - 1 input values its 8 time tiles need; a
+// thread then slides a register ring of 8 inputs over the lags (one shared-memory load per lag), so a row costs each
+// thread H + 7 LDS for 8 * H DFMAs and no global load sits in front of the multiply-adds.  Operation order = the kernel
+// above (lags ascending inside a row, rows in CSR order): results are bit-identical.
+__device__ __forceinline__ void hb_cp_async8(void *smem_dst, const void *gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 8 : 0;                      // src-size 0: nothing is read, the 8 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
+#ifndef HB_IRF_TT
+#define HB_IRF_TT 16                                   // time steps per thread
+#endif
 template <int HP>
 __global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in, long long T, int H, long long nnz,
                                                             const int *__restrict__ row_ptr, const int *__restrict__ src,
                                                             const double *__restrict__ w, const double *__restrict__ in,
                                                             double *__restrict__ out) {
-    constexpr int TT = 8;
-    __shared__ double sw[HP][32];
+    constexpr int TT = HB_IRF_TT;
+    constexpr int BT = 8 * TT;                         // time steps per block (8 warps)
+    constexpr int WP = BT + HP;                        // staged input window: steps [t_blk - HP, t_blk + BT)
+    extern __shared__ __align__(16) double hb_irf_smem[];
+    double(*sx)[WP][32] = reinterpret_cast<double(*)[WP][32]>(hb_irf_smem);                       // [2][WP][32]
+    double(*sw)[HP][32] = reinterpret_cast<double(*)[HP][32]>(hb_irf_smem + 2 * WP * 32);        // [2][HP][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = blockIdx.x * 32 + lane;
-    const long long t0 = ((long long)blockIdx.y * 8 + warp) * TT;
+    const long long t_blk = (long long)blockIdx.y * BT;
+    const long long t0 = t_blk + warp * TT;
     const int r_begin = d < n_out ? row_ptr[d] : 0;
     const int nrows = d < n_out ? row_ptr[d + 1] - r_begin : 0;
     int maxrows = nrows;
@@ -169,36 +184,40 @@ __global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in,
         const int other = __shfl_xor_sync(0xffffffffu, maxrows, o);
         maxrows = other > maxrows ? other : maxrows;
     }
+    auto stage = [&](int r, int buf) {                 // this thread's share of row r: window rows / lags warp, warp+8, ...
+        const bool has = r < nrows;
+        const long long row = (long long)r_begin + r;
+        const double *x = in + (has ? src[row] : 0);
+        for (int m = warp; m < WP; m += 8) {
+            const long long t = t_blk - HP + m;
+            const bool ok = has && t >= 0 && t < T;
+            hb_cp_async8(&sx[buf][m][lane], ok ? x + t * n_in : in, ok);
+        }
+        for (int l = warp; l < HP; l += 8) {
+            const bool ok = has && l < H;
+            hb_cp_async8(&sw[buf][l][lane], ok ? w + (long long)l * nnz + row : w, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     double total[TT];
 #pragma unroll
     for (int k = 0; k < TT; ++k) total[k] = 0.0;
-    // the weights of row r+1 are fetched into registers while row r is being computed (their latency would otherwise sit
-    // between the two block barriers of every row)
-    double wn[HP / 8];
-    int src_next = 0;
-#pragma unroll
-    for (int i = 0; i < HP / 8; ++i) wn[i] = (0 < nrows && warp + 8 * i < H) ? w[(long long)(warp + 8 * i) * nnz + r_begin] : 0.0;
-    if (0 < nrows) src_next = src[r_begin];
+    if (maxrows > 0) stage(0, 0);
     for (int r = 0; r < maxrows; ++r) {
-        const bool has = r < nrows;
-        const long long row = (long long)r_begin + r;
-        const int src_row = src_next;
-        __syncthreads();                                   // the previous row's weights are no longer read
-#pragma unroll
-        for (int i = 0; i < HP / 8; ++i) sw[warp + 8 * i][lane] = wn[i];
-        __syncthreads();
-        {
-            const bool has_next = r + 1 < nrows;
-#pragma unroll
-            for (int i = 0; i < HP / 8; ++i) wn[i] = (has_next && warp + 8 * i < H) ? w[(long long)(warp + 8 * i) * nnz + row + 1] : 0.0;
-            if (has_next) src_next = src[row + 1];
+        const int buf = r & 1;
+        if (r + 1 < maxrows) {
+            stage(r + 1, buf ^ 1);                     // buffer buf^1 was released by the barrier that ended row r-1
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        if (has && t0 < T) {
-            const double *x = in + src_row;
+        __syncthreads();                               // row r has landed for every thread of the block
+        if (r < nrows && t0 < T) {
+            const int base = HP + warp * TT;           // window index of step t0
             double ring[TT], acc[TT];
 #pragma unroll
             for (int k = 0; k < TT; ++k) {
-                ring[k] = (t0 + k < T) ? x[(t0 + k) * n_in] : 0.0;
+                ring[k] = sx[buf][base + k][lane];
                 acc[k] = 0.0;
             }
 #pragma unroll
@@ -206,11 +225,8 @@ __global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in,
 #pragma unroll
                 for (int j = 0; j < TT; ++j) {
                     const int l = c * TT + j;
-                    if (l > 0) {                           // lag l needs x[t0 - l] in place of x[t0 + TT - l]
-                        const long long m = t0 - l;
-                        ring[(TT - j) % TT] = (m >= 0 && l < H) ? x[m * n_in] : 0.0;   // before the series starts: nothing to add
-                    }
-                    const double wl = sw[l][lane];
+                    if (l > 0) ring[(TT - j) % TT] = sx[buf][base - l][lane];   // lag l needs x[t0 - l] in place of x[t0 + TT - l]
+                    const double wl = sw[buf][l][lane];
 #pragma unroll
                     for (int k = 0; k < TT; ++k) acc[k] = fma(wl, ring[(k - j + TT) % TT], acc[k]);
                 }
@@ -218,12 +234,26 @@ __global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in,
 #pragma unroll
             for (int k = 0; k < TT; ++k) total[k] += acc[k];
         }
+        __syncthreads();                               // row r's buffer may be overwritten (by the stage of row r+2)
     }
     if (d < n_out) {
 #pragma unroll
         for (int k = 0; k < TT; ++k)
             if (t0 + k < T) out[(t0 + k) * n_out + d] = total[k];
     }
+}
+
+template <int HP>
+int hb_launch_conv_tiled(dim3 grid, cudaStream_t st, int n_out, int n_in, long long T, int H, long long nnz, const int *row_ptr,
+                         const int *src, const double *w, const double *in, double *out) {
+    const int smem = (2 * (8 * HB_IRF_TT + HP) * 32 + 2 * HP * 32) * 8;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(hb_sparse_conv_tiled<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HB_ERR_CUDA;
+        configured = true;
+    }
+    hb_sparse_conv_tiled<HP><<<grid, 256, smem, st>>>(n_out, n_in, T, H, nnz, row_ptr, src, w, in, out);
+    return HB_OK;
 }
 }  // namespace
 
@@ -237,11 +267,10 @@ extern "C" int hb_sparse_route_conv_device(int n_out, int n_in, int64_t T, int H
         dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((T + 7) / 8));
         hb_sparse_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
     } else {
-        dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((T + 63) / 64));
-        if (H <= 32)
-            hb_sparse_conv_tiled<32><<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
-        else
-            hb_sparse_conv_tiled<64><<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
+        dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((T + 8 * HB_IRF_TT - 1) / (8 * HB_IRF_TT)));
+        const int rc = H <= 32 ? hb_launch_conv_tiled<32>(grid, (cudaStream_t)stream, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out)
+                               : hb_launch_conv_tiled<64>(grid, (cudaStream_t)stream, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
+        if (rc) return rc;
     }
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
