@@ -469,3 +469,26 @@ def test_neural_bucket_inside_a_model():
     x = rng.normal(size=(3, N, T))
     init = dict(s1=rng.normal(size=N), s2=np.zeros(N))
     assert_parity(model(x, p, initstates=init), ho.run_model(model, x, p, initstates=init))
+
+
+def test_wave_grid_kernel_with_shared_hru_types():
+    """Parameters shared through `htypes` (`p[htypes]`, src/utils.jl:174-201) on the single-pass grid kernel: three HRU types
+    spread over the grid, for the buckets and for the route alike; same result as the generic path and the oracle."""
+    R, Cc, T = 20, 48, 30
+    rng = np.random.default_rng(4)
+    N = R * Cc
+    flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128], size=(R, Cc))
+    rr, cc = np.divmod(np.arange(N), Cc)
+    ht = rng.integers(1, 4, N)
+    model = hm.models.exphydro_grid(flw, np.stack([rr + 1, cc + 1], axis=1), htypes=ht)
+    p3 = {k: v[:3] for k, v in sy.parameters("exphydro", 0, 3).items()}
+    p = {"params": dict(p3, area_coef=np.array([0.8, 1.0, 1.3]), lag=np.array([0.2, 1.0, 2.5]))}
+    init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 1, N))
+    inp = sy.forcing("exphydro", 0, N, T)
+    eng = hm.B200Model(model)
+    wave = eng(inp, p, initstates=init)
+    assert any(isinstance(k, tuple) and k[:2] == ("grid", "wave") for k in eng._cache)
+    assert_parity(wave, ho.run_model(model, inp, p, initstates=init))
+    eng2 = hm.B200Model(model)
+    eng2.grid_kernel = "generic"
+    assert np.array_equal(wave, eng2(inp, p, initstates=init))
