@@ -197,6 +197,46 @@ def bench_raster_ingest(args):
     return 0
 
 
+def cpu_reference_rate_grid(T, target_seconds=10.0):
+    """CPU baseline of the distributed workload: the C oracle (per-component passes + D8 Jacobi routing, OpenMP) on a
+    square sample of the same synthetic grid model."""
+    import hydromodels_jl_b200 as hm
+    from hydromodels_jl_b200 import synthetic as sy
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hydro_oracle_c as hoc
+    cores = hoc.max_threads()
+
+    def problem(side):
+        rng = np.random.default_rng(sy.SEED)
+        n = side * side
+        flw = rng.choice(np.array([1, 2, 4, 8, 16, 32, 64, 128]), size=(side, side), p=[.3, .2, .3, .05, .03, .02, .05, .05])
+        rr, cc = np.divmod(np.arange(n), side)
+        model = hm.models.exphydro_grid(flw, np.stack([rr + 1, cc + 1], axis=1))
+        pp = sy.parameters("exphydro", 0, n)
+        pp.update(area_coef=np.full(n, 1.0), lag=rng.uniform(0.1, 2.0, n))
+        init = dict(snowpack=np.zeros(n), soilwater=np.full(n, 1303.0), s_river=np.zeros(n))
+        return model, sy.forcing("exphydro", 0, n, T), {"params": pp}, init
+    side = 128
+    model, inp, p, init = problem(side)
+    hoc.run_model(model, inp, p, initstates=init)
+    t0 = time.perf_counter()
+    hoc.run_model(model, inp, p, initstates=init, n_threads=1)
+    rate1 = side * side * T / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    hoc.run_model(model, inp, p, initstates=init)
+    est = side * side * T / (time.perf_counter() - t0)
+    side = int(min(1024, max(128, (est * target_seconds / 2 / T) ** 0.5))) // 32 * 32
+    model, inp, p, init = problem(side)
+    hoc.run_model(model, inp, p, initstates=init)
+    best = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter()
+        hoc.run_model(model, inp, p, initstates=init)
+        best = min(best, time.perf_counter() - t0)
+    return (side * side * T / best, best, f"{side} x {side} cells x {T} steps of the same synthetic grid model, C oracle (oracle/hydro_oracle.c: "
+            f"component passes + D8 Jacobi routing, OpenMP, {cores} threads; best of 2)", cores, rate1)
+
+
 def bench_irf(args):
     """SparseRouteConvolution on a synthetic river network — 65 536 nodes, 8 source rows per destination
     (nnz = 524 288), horizon 32, 3650 steps: 2 * nnz * T * H = 1.2e11 flop per pass, FP64-FMA bound."""
@@ -319,7 +359,7 @@ def main():
         rates = []
         rate1 = None
         for _ in range(min(steps, 3)):
-            rate, dt, sample, cores, rate1 = cpu_reference_rate(model_name, T, 8.0)
+            rate, dt, sample, cores, rate1 = cpu_reference_rate_grid(T, 8.0) if model_name == "exphydro_grid" else cpu_reference_rate(model_name, T, 8.0)
             rates.append(rate)
         v = float(np.median(rates))
         print(json.dumps({
@@ -531,8 +571,8 @@ def main():
             e2e = {"value": None, "unit": unit, "error": f"{type(ex).__name__}: {ex}"[:300]}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu and not special:
-        rate, dt, sample, cores, rate1 = cpu_reference_rate(model_name, T)
+    if rank == 0 and world == 1 and not args.no_cpu and (not special or model_name == "exphydro_grid"):
+        rate, dt, sample, cores, rate1 = cpu_reference_rate_grid(T) if model_name == "exphydro_grid" else cpu_reference_rate(model_name, T)
         cpu = {"value": rate, "unit": unit, "cores": cores, "kind": "port", "sample": sample, "seconds": dt,
                "one_thread_value": rate1,
                "reference_published_one_thread": 1.05e6}    # docs/src/get_start_en.md:408 (hardware not stated)
