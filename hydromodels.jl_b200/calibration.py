@@ -13,8 +13,10 @@ The reference's objective evaluates ONE parameter vector per call on the host an
   parameter buffer, `hb_run_device` in objective mode scores it, `hb_de_select_device` keeps the better member and
   records the generation's best — three kernels on one stream, nothing crosses PCIe until the end.
 
-Models with unit hydrographs are not supported by the device loop (their ordinates are host-evaluated per parameter
-set); use `objective_batch` from a host optimiser for those.
+Unit hydrographs: a normal run reads host-built ordinates, but a search changes the unit-hydrograph parameters every
+generation, so the device loop compiles the stepper with `uh_on_device` — the kernel prologue evaluates the S-curve
+ordinates of each member from its own parameters (`UnitHydrograph.weights`), with the number of ordinates reserved
+from the parameter bounds.
 """
 from __future__ import annotations
 
@@ -107,6 +109,28 @@ class OptimizationProblem:
         return float(self.objective_batch(np.asarray(p, dtype=np.float64)[None, :])[0])
 
 
+def _uh_kmax_from_bounds(prob: OptimizationProblem) -> List[int]:
+    """Ordinates to reserve per unit hydrograph: the largest `ceil(max_lag(p))` over the corners of the parameter box."""
+    import itertools
+    import math
+    from .components import HydroModel, UnitHydrograph
+    from .symbolic import evaluate
+    comp = prob.component
+    uhs = [c for c in (comp.components if isinstance(comp, HydroModel) else (comp,)) if isinstance(c, UnitHydrograph)]
+    out = []
+    for uh in uhs:
+        ranges = []
+        for nm in uh.param_names:
+            if nm in prob.fixed:
+                ranges.append((prob.fixed[nm],))
+            else:
+                j = prob.calibrated.index(nm)
+                ranges.append((float(prob.lb[j]), float(prob.ub[j])))
+        lag = max(evaluate(uh.uh_conds[0][0], dict(zip(uh.param_names, corner))) for corner in itertools.product(*ranges))
+        out.append(max(1, int(math.ceil(lag))))
+    return out
+
+
 def solve(prob: OptimizationProblem, alg: Optional[DifferentialEvolution] = None, *, maxiters: int = 100) -> Solution:
     """Differential evolution on the device; returns the best member after `maxiters` generations."""
     import time
@@ -118,15 +142,14 @@ def solve(prob: OptimizationProblem, alg: Optional[DifferentialEvolution] = None
     if D == 0:
         raise ValueError("nothing to calibrate: every parameter is fixed")
     eng = prob.engine
-    if eng._has_uh():
-        raise NotImplementedError("the device loop does not cover unit-hydrograph models (host-evaluated ordinates); "
-                                  "drive prob.objective_batch from a host optimiser instead")
+    uh_dev = eng._has_uh()
+    kmax = _uh_kmax_from_bounds(prob) if uh_dev else None
     T = prob.input.shape[1]
     rng = np.random.default_rng(alg.seed)
     P0 = prob.lb + rng.random((N, D)) * (prob.ub - prob.lb)
     init = None if prob.initstates is None else {k: np.full(N, v) for k, v in prob.initstates.items()}
     run = DeviceRun(eng, N, T, prob._params(P0), config=prob.config, initstates=init, objective=prob.metric,
-                    target=prob.target, warm_up=prob.warm_up, ensemble=True)
+                    target=prob.target, warm_up=prob.warm_up, ensemble=True, _kmax=kmax, uh_on_device=uh_dev)
     slots = run.ck.program.param_slots
     off_of = {nm: int(run._host[0][j]) for j, (nm, _) in enumerate(slots)}
     missing = [nm for nm in prob.calibrated if nm not in off_of]

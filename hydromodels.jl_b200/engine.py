@@ -397,13 +397,13 @@ class B200Model:
 
     # -- compile ------------------------------------------------------------------------------------
     def compiled(self, *, rows=None, objective=False, metric=0, shared_forcing=False,
-                 uh_kmax: Sequence[int] = ()) -> CompiledStepper:
-        key = (tuple(rows) if rows is not None else None, objective, metric, shared_forcing, tuple(uh_kmax))
+                 uh_kmax: Sequence[int] = (), uh_on_device: bool = False) -> CompiledStepper:
+        key = (tuple(rows) if rows is not None else None, objective, metric, shared_forcing, tuple(uh_kmax), bool(uh_on_device))
         if key not in self._cache:
             prog = lower_stepper(self._stepper_component(), rows=rows, objective=objective,
                                  uh_kmax=list(uh_kmax) if len(uh_kmax) else None, fast=self.fast,
                                  holes=self._route_rows(), nn_tensor=self.nn_tensor,
-                                 precision=self.precision)
+                                 precision=self.precision, uh_on_device=uh_on_device)
             # MLP-fused bodies keep 16+16 activations per net in registers: give them 168 (3 blocks/SM)
             maxreg = self.max_registers or (168 if prog.nn_words else 0)
             self._cache[key] = CompiledStepper(prog, metric=metric, shared_forcing=shared_forcing,
@@ -853,7 +853,10 @@ class DeviceRun:
 
     def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None,
                  rows: Optional[Sequence[str]] = None, objective: Optional[str] = None, target=None,
-                 warm_up: int = 1, ensemble: bool = False, _kmax=None, node_range: Optional[Tuple[int, int]] = None):
+                 warm_up: int = 1, ensemble: bool = False, _kmax=None, node_range: Optional[Tuple[int, int]] = None,
+                 uh_on_device: bool = False):
+        """`uh_on_device`: unit-hydrograph ordinates are evaluated in the kernel prologue from the parameters in the device
+        buffer (`_kmax` then gives the ordinates to reserve per unit hydrograph) — the host table is only a placeholder."""
         self.eng, self.N, self.T = eng, int(N), int(T)
         self.cfg = normalize_config(config)
         _check_config(self.cfg, T)
@@ -867,9 +870,12 @@ class DeviceRun:
             kmax = eng.prepare(probe, params, N, ensemble=ensemble, node_range=node_range)[5]
         else:
             kmax = []
-        self.ck = eng.compiled(rows=rows, objective=obj, metric=metric, shared_forcing=ensemble, uh_kmax=kmax)
+        self.ck = eng.compiled(rows=rows, objective=obj, metric=metric, shared_forcing=ensemble, uh_kmax=kmax,
+                               uh_on_device=uh_on_device)
         prog = self.ck.program
-        flat, p_off, p_mode, htypes, uhw, kmax, nn = eng.prepare(prog, params, N, ensemble=ensemble, node_range=node_range)
+        flat, p_off, p_mode, htypes, uhw, kmax_host, nn = eng.prepare(prog, params, N, ensemble=ensemble, node_range=node_range)
+        if uh_on_device and uhw:
+            uhw = [np.zeros((k, N)) for k in kmax]            # placeholder: the prologue overwrites every ordinate
         self._host = (p_off, p_mode)
         self.bufs = {"params": DeviceBuffer.from_host(flat)}
         self.n_param_values = flat.size

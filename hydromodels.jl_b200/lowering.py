@@ -92,6 +92,7 @@ class StepperProgram:
     stats: Dict[str, int] = field(default_factory=dict)
     nn_tensor: bool = False         # some dense chain is lowered to FP64 MMA fragments
     precision: str = "f64"          # "f64" (reference arithmetic) | "f32" (opt-in)
+    uh_on_device: bool = False      # the prologue evaluates the unit-hydrograph ordinates (host table ignored)
 
 
 class _Builder:
@@ -249,7 +250,8 @@ def _flatten(component: Component) -> Tuple[List[Component], List[str], List[str
 
 def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None, objective: bool = False,
                   uh_kmax: Optional[Sequence[int]] = None, fast: bool = True,
-                  holes: Sequence[str] = (), nn_tensor: bool = False, precision: str = "f64") -> StepperProgram:
+                  holes: Sequence[str] = (), nn_tensor: bool = False, precision: str = "f64",
+                  uh_on_device: bool = False) -> StepperProgram:
     """Lower a per-node model (buckets, fluxes, neural fluxes, unit hydrographs) to one stepper
     body.  `rows`: subset/order of result rows to write (default: all = the reference result);
     `objective`: emit the last output row as `hb_sim` for the fused metric reduction instead of
@@ -315,6 +317,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
     env: Dict[str, int] = {nm: b.leaf_in(i) for i, nm in enumerate(input_names)}
     state_post: Dict[int, int] = {}           # state index → val id of the post-update value
     uh_steps: List[Tuple[int, int]] = []      # (uh index, val id of x_t)
+    uh_device: List[Tuple[int, List[int], List[List[int]]]] = []   # (uh index, threshold vals, value vals per k)
     statements: List[Tuple[str, object]] = []  # ordered side effects ('update', (sidx, val)), …
 
     raw_states = set()                        # states updated without the min_value clamp (NeuralBucket)
@@ -403,6 +406,11 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                 env[eq.lhs.name] = vid
         else:  # UnitHydrograph
             u = uhs.index(c)
+            if uh_on_device:
+                ptab = param_table(c)
+                thr = [b.lower_expr(cnd, {}, ptab) for cnd, _ in c.uh_conds]
+                vals = [[b.lower_expr(v, {c.tvar: b.const(float(k))}, ptab) for _, v in c.uh_conds] for k in range(1, uh_kmax[u] + 1)]
+                uh_device.append((u, thr, vals))
             x = env[c.input_names[0]]
             vid = b.opaque("uh", (u, x), b.vals[x].mask | M_U, cost=2 * uh_kmax[u])
             b.vals[vid].args = (x,)
@@ -519,6 +527,23 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
     # carries: initial value = the pre-state expression at the (unclamped) initial states
     for pre, (slot, post) in sorted(carried.items(), key=lambda kv: kv[1][0]):
         pro.append(f"hb_c[{slot}] = {pro_ref(pre)};")
+    # unit-hydrograph ordinates evaluated on the device (UnitHydrograph.weights: K = ceil(max_lag), S(k) = value of the
+    # condition with the smallest threshold >= k, 1 beyond the largest; w_k = S(k) - S(k-1), normalised; K == 0: identity)
+    for u, thr, vals in uh_device:
+        K = uh_kmax[u]
+        th = [pro_ref(i) for i in thr]
+        vnames = [[pro_ref(vi) for vi in row] for row in vals]     # materialise every operand at prologue scope first
+        pro.append(f"{{ const double ulag = {th[0]};")
+        pro.append(f"  const int uK = ulag > 0.0 ? (int)hb_min((double){K}, ceil(ulag)) : 0;")
+        pro.append("  double us_prev = 0.0, usum = 0.0;")
+        for k in range(1, K + 1):
+            pro.append("  { double uval = 1.0, ubest = 1.0e300;")
+            for ci, vn in enumerate(vnames[k - 1]):
+                pro.append(f"    if ({float(k)} <= {th[ci]} && {th[ci]} < ubest) {{ uval = {vn}; ubest = {th[ci]}; }}")
+            pro.append(f"    const double uw = {k} <= uK ? uval - us_prev : 0.0; us_prev = uval; usum += uw; hb_uhw[{uh_w_off[u] + k - 1}] = uw; }}")
+        pro.append(f"  if (uK > 0) {{ const double uinv = 1.0 / usum; " +
+                   " ".join(f"hb_uhw[{uh_w_off[u] + k}] *= uinv;" for k in range(K)) + " }")
+        pro.append(f"  else {{ hb_uhw[{uh_w_off[u]}] = 1.0; }} }}")
 
     pending_updates = {p[0]: p for k, p in statements if k == "update"}
     nn_done = set()
@@ -581,7 +606,8 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                           state_names=state_names, param_slots=param_slots, htype_sets=htype_sets, uh=uhs,
                           uh_kmax=list(uh_kmax), uh_htype_set=[htype_set(u) for u in uhs],
                           nn_layout=nn_layout, nn_words=sum(n for _, _, n in nn_layout), n_carry=len(carried),
-                          objective=objective, stats=stats, nn_tensor=any(net_mma), precision=precision)
+                          objective=objective, stats=stats, nn_tensor=any(net_mma), precision=precision,
+                          uh_on_device=bool(uh_on_device and uhs))
 
 
 def _expr_with(v: Val, a: List[str], fast: bool) -> str:

@@ -74,7 +74,7 @@ def _sections(body: str):
 
 
 def run_body_on_cpu(eng, input, params, config=None, initstates=None, rows=None, objective=False,
-                    ensemble_members=None, return_final_states=False):
+                    ensemble_members=None, return_final_states=False, uh_on_device=False, uh_kmax=None):
     """Mirror of `B200Model.__call__` that executes the generated body with g++ instead of NVRTC."""
     from hydromodels_jl_b200.components import normalize_config
     from hydromodels_jl_b200.lowering import lower_stepper
@@ -85,9 +85,11 @@ def run_body_on_cpu(eng, input, params, config=None, initstates=None, rows=None,
     N, T = eng._dims(input, ensemble, ensemble_members)
     inp = np.asfortranarray(input)
     probe = lower_stepper(eng.component, rows=rows, objective=objective, fast=eng.fast)
-    kmax = eng.prepare(probe, params, N, ensemble=ensemble)[5]
-    prog = lower_stepper(eng.component, rows=rows, objective=objective, uh_kmax=kmax or None, fast=eng.fast)
-    flat, p_off, p_mode, htypes, uhw, kmax, nn = eng.prepare(prog, params, N, ensemble=ensemble)
+    kmax = uh_kmax or eng.prepare(probe, params, N, ensemble=ensemble)[5]
+    prog = lower_stepper(eng.component, rows=rows, objective=objective, uh_kmax=kmax or None, fast=eng.fast, uh_on_device=uh_on_device)
+    flat, p_off, p_mode, htypes, uhw, _, nn = eng.prepare(prog, params, N, ensemble=ensemble)
+    if uh_on_device and uhw:
+        uhw = [np.full((k, N), np.nan) for k in kmax]       # the prologue must overwrite every ordinate
     uhw_flat = np.ascontiguousarray(np.concatenate(uhw, axis=0)) if uhw else np.zeros(1)
     init = eng._initstates(prog, initstates, N)
     R = 0 if objective else len(prog.row_names)

@@ -112,7 +112,26 @@ def test_fixed_parameters_and_unsupported_models():
                                    fixed_params=dict(Qmax=TRUE[4], f=TRUE[5]), default_initstates=INIT)
     sol = cal.solve(prob, cal.DifferentialEvolution(popsize=128, seed=1), maxiters=60)
     assert sol.objective < -0.99 and sol.params["Qmax"] == TRUE[4] and sol.u.shape == (4,)
-    gr4j = hm.models.gr4j()
-    with pytest.raises(NotImplementedError, match="unit-hydrograph"):
-        probg = cal.OptimizationProblem(gr4j, np.ones((2, 50)), np.ones(50), lb_pas=[100, -5, 20, 1.1], ub_pas=[1200, 3, 300, 2.9])
-        cal.solve(probg, cal.DifferentialEvolution(popsize=8), maxiters=1)
+
+
+def test_device_de_on_a_unit_hydrograph_model():
+    """GR4J + two unit hydrographs (BASELINE config 2's model): every generation changes x4, so the kernel prologue evaluates
+    each member's S-curve ordinates itself.  The device loop's objective must equal the host-table objective of the same
+    members, and the search must recover a planted x4."""
+    model = hm.models.gr4j()
+    T = 730
+    inp = sy.forcing("gr4j", 0, 1, T)[:, 0, :]
+    names = model.get_param_names()
+    truth = dict(x1=350.0, x2=0.5, x3=90.0, x4=1.7)
+    init = {k: float(v) for k, v in sy.INIT["gr4j"].items()}
+    target = ho.run_model(model, inp, {"params": truth}, initstates=init)[-1]
+    lb = np.array([dict(x1=100.0, x2=-5.0, x3=20.0, x4=1.1)[n] for n in names])
+    ub = np.array([dict(x1=1200.0, x2=3.0, x3=300.0, x4=2.9)[n] for n in names])
+    prob = cal.OptimizationProblem(model, inp, target, metric="NSE", warm_up=60, lb_pas=lb, ub_pas=ub, default_initstates=init)
+    assert cal._uh_kmax_from_bounds(prob) == [3, 6]
+    sol = cal.solve(prob, cal.DifferentialEvolution(popsize=256, seed=5), maxiters=80)
+    assert np.all(np.diff(sol.history) <= 0) and sol.objective < -0.995
+    # the loop's fitness (ordinates evaluated on the device) vs the ensemble objective with host-built ordinates
+    host = prob.objective_batch(sol.population)
+    assert np.allclose(sol.fitness, host, rtol=1e-9, atol=1e-12)
+    assert abs(sol.params["x4"] - truth["x4"]) < 0.1

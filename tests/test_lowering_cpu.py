@@ -125,3 +125,21 @@ def test_lowering_statistics_exphydro():
     assert prog.stats["exp_like_per_step"] == 6
     assert prog.n_carry >= 3
     assert prog.row_names == hm.models.exphydro().var_names
+
+
+def test_unit_hydrograph_ordinates_evaluated_in_the_prologue():
+    """`uh_on_device`: the kernel prologue computes the S-curve ordinates from the node's parameters (what the device-resident
+    calibration needs) — same rows as with the host-built table, also when the reserved K exceeds a node's own K."""
+    N, T = 9, 80
+    model = hm.models.gr4j(htypes=np.arange(1, N + 1))
+    inp = sy.forcing("gr4j", 0, N, T)
+    p = {"params": sy.parameters("gr4j", 0, N)}
+    p["params"]["x4"] = np.linspace(1.05, 2.9, N)                      # K from (2, 3) to (3, 6)
+    init = {k: np.full(N, v) for k, v in sy.INIT["gr4j"].items()}
+    eng = hm.B200Model(model)
+    host = run_body_on_cpu(eng, inp, p, initstates=init)
+    for kmax in ([3, 6], [4, 8]):
+        dev = run_body_on_cpu(eng, inp, p, initstates=init, uh_on_device=True, uh_kmax=kmax)
+        assert np.all(np.isfinite(dev))
+        assert_parity(dev, host)
+    assert_parity(host, ho.run_model(model, inp, p, initstates=init))
