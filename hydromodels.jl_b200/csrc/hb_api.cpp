@@ -896,8 +896,11 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
     if (!d || d->struct_size != (int32_t)sizeof(hb_grid_desc)) return fail(HB_ERR_INVALID, "hb_grid_desc.struct_size mismatch");
     const hb_grid_spec &s = m->gspec;
     if (d->rows <= 0 || d->cols <= 0 || d->n_steps < 0 || !d->input || !d->out || !d->flwdir) return fail(HB_ERR_INVALID, "bad grid descriptor");
-    if (d->out_node_count > 0 && (s.variant != HB_GRID_WAVE || d->out_first_node < 0 || d->out_first_node + d->out_node_count > (int64_t)d->rows * d->cols))
-        return fail(HB_ERR_INVALID, "an output node range needs the wave kernel and must lie inside the grid");
+    const bool window = d->out_rows > 0 || d->out_cols > 0;
+    const int o_r0 = d->out_rows > 0 ? d->out_row0 : 0, o_nr = d->out_rows > 0 ? d->out_rows : d->rows;
+    const int o_c0 = d->out_cols > 0 ? d->out_col0 : 0, o_nc = d->out_cols > 0 ? d->out_cols : d->cols;
+    if (window && (s.variant != HB_GRID_WAVE || o_r0 < 0 || o_c0 < 0 || o_r0 + o_nr > d->rows || o_c0 + o_nc > d->cols))
+        return fail(HB_ERR_INVALID, "an output window needs the wave kernel and must lie inside the grid");
     if (!(d->min_value > 0)) return fail(HB_ERR_INVALID, "min_value must be positive, got %g", d->min_value);
     if (s.n_params > 0 && (!d->params || !d->param_offset || !d->param_mode)) return fail(HB_ERR_INVALID, "params / param tables are NULL");
     int rc = load_model(m);
@@ -954,14 +957,16 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
             put(wp, sizeof wp);
             put(&N, 8);
             put(&t0, 8);
-            const int64_t out_first = d->out_node_count > 0 ? d->out_first_node : 0, out_count = d->out_node_count > 0 ? d->out_node_count : N;
-            put(&out_first, 8);
-            put(&out_count, 8);
+            put(&o_r0, 4);
+            put(&o_nr, 4);
+            put(&o_c0, 4);
+            put(&o_nc, 4);
             // TMA bulk copies need 16-byte aligned global addresses: base pointers and per-step strides
             int tma_in = ((reinterpret_cast<uintptr_t>(d->input) & 15) == 0) && ((N * s.n_inputs * 8) % 16 == 0);
-            int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((out_count * s.n_rows * 8) % 16 == 0) &&
-                          ((out_first * s.n_rows * 8) % 16 == 0);
+            int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && (((int64_t)o_nr * o_nc * s.n_rows * 8) % 16 == 0);
             if (getenv("HB_DISABLE_TMA")) tma_in = tma_out = 0;
+            if (getenv("HB_DISABLE_TMA_IN")) tma_in = 0;
+            if (getenv("HB_DISABLE_TMA_OUT")) tma_out = 0;
             put(&ticket_base, 4);
             put(&ns, 4);
             put(&rows, 4);

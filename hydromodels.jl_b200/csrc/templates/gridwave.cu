@@ -68,8 +68,9 @@ struct HbWaveArgs {
     u32 *ticket;              // [0] block ticket (monotone over the run), [1] error flag
     i64 N;
     i64 t0;                   // first step of this chunk
-    i64 out_first;            // records are written for cells [out_first, out_first + out_count) only — a strip of a
-    i64 out_count;            //   multi-GPU run computes ghost rows whose records belong to the neighbouring rank
+    int out_r0, out_nr;       // records are written for the cells of rows [out_r0, out_r0 + out_nr) x columns
+    int out_c0, out_nc;       //   [out_c0, out_c0 + out_nc) only, as out[T][out_nr][out_nc][R]: a strip / panel of a multi-GPU run
+                              //   computes ghost rows / columns whose records belong to the neighbouring rank
     u32 ticket_base;          // value of the ticket when this launch started
     int nsteps;               // steps in this chunk
     int rows, cols;
@@ -164,8 +165,14 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
     u64 *bars = reinterpret_cast<u64 *>(hb_smem + (size_t)HB_WARPS * (kInBytes + kOutBytes)) + warp * HB_STAGES;
 
     const bool tma_in = a.tma_in_ok && full_warp;
-    const bool tma_out = a.tma_out_ok && full_warp && n0w >= a.out_first && n0w + 32 <= a.out_first + a.out_count;
-    const bool out_valid = valid && n >= a.out_first && n < a.out_first + a.out_count;
+    // position of this cell / of the warp's first cell in the output window
+    const int o_r = (int)(nc / a.cols) - a.out_r0, o_c = (int)(nc % a.cols) - a.out_c0;
+    const int ow_r = (int)(n0w / a.cols) - a.out_r0, ow_c = (int)(n0w % a.cols) - a.out_c0;
+    const bool out_valid = valid && o_r >= 0 && o_r < a.out_nr && o_c >= 0 && o_c < a.out_nc;
+    const i64 o_rel = (i64)o_r * a.out_nc + o_c, ow_rel = (i64)ow_r * a.out_nc + ow_c;
+    // the bulk store needs the warp's 32 cells in one row, inside the window, at a 16-byte aligned record offset
+    const bool tma_out = a.tma_out_ok && full_warp && (n0w % a.cols) + 32 <= a.cols && ow_r >= 0 && ow_r < a.out_nr && ow_c >= 0 &&
+                         ow_c + 32 <= a.out_nc && ((ow_rel * HB_R * 8) & 15) == 0;
 
     // ---- per-cell constants ---------------------------------------------------------------------
     real hb_p[HB_ARR(HB_NP)];
@@ -218,11 +225,11 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
 
     const int ns = a.nsteps;
     const i64 in_step = a.N * (i64)HB_V;
-    const i64 out_step = a.out_count * (i64)HB_R;
+    const i64 out_step = (i64)a.out_nr * a.out_nc * HB_R;
     const real *in_warp = a.in + (a.t0 * a.N + n0w) * HB_V;
     const real *gx = a.in + (a.t0 * a.N + nc) * HB_V;
-    real *ow_ptr = a.out + (a.t0 * a.out_count + (n0w - a.out_first)) * HB_R;
-    real *go = a.out + (a.t0 * a.out_count + (nc - a.out_first)) * HB_R;
+    real *ow_ptr = a.out + a.t0 * out_step + ow_rel * HB_R;
+    real *go = a.out + a.t0 * out_step + o_rel * HB_R;
 
     if (tma_in) {
         if (lane == 0) {
@@ -259,6 +266,10 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
                 const real *sx = sIn + slot * 32 * HB_V + lane * HB_V;
 #pragma unroll
                 for (int v = 0; v < HB_V; ++v) hb_x[v] = sx[v];
+                // generic-proxy reads of the slot -> ordered before the async-proxy refill of the same slot.  Without this
+                // fence the TMA write can overtake the loads above (seen as wrong forcing from the third step of a launch
+                // on in ~40 % of cold first launches; __syncwarp alone orders the generic proxy only)
+                hb_fence_proxy_async();
                 __syncwarp();
                 if (lane == 0 && i + HB_STAGES < ns) {
                     hb_mbar_expect_tx(hb_smem_u32(&bars[slot]), kInStage);

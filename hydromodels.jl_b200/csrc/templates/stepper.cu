@@ -260,6 +260,10 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
             const real *sx = sIn + slot * 32 * HB_V + lane * HB_V;
 #pragma unroll
             for (int v = 0; v < HB_V; ++v) hb_x[v] = sx[v];
+            // cross-proxy write-after-read: the lanes' generic-proxy loads of the slot must be ordered before the
+            // async-proxy (TMA) refill of the same slot; __syncwarp orders the generic proxy only (the wave grid
+            // kernel, which shares this ring, showed overtaken loads on cold launches without the fence)
+            hb_fence_proxy_async();
             __syncwarp();   // every lane has consumed the slot -> refill it HB_STAGES steps ahead
             if (lane == 0 && t + HB_STAGES < T) {
                 hb_mbar_expect_tx(hb_smem_u32(&bars[slot]), kInStage);

@@ -87,7 +87,8 @@ class GridDesc(C.Structure):
                 ("n_param_values", C.c_int64), ("param_offset", C.c_void_p), ("param_mode", C.c_void_p),
                 ("htypes", C.c_void_p), ("init_bucket", C.c_void_p), ("init_route", C.c_void_p), ("flwdir", C.c_void_p),
                 ("min_value", C.c_double), ("final_bucket", C.c_void_p), ("final_route", C.c_void_p),
-                ("elapsed_ms", C.c_void_p), ("out_first_node", C.c_int64), ("out_node_count", C.c_int64)]
+                ("elapsed_ms", C.c_void_p), ("out_row0", C.c_int32), ("out_rows", C.c_int32), ("out_col0", C.c_int32),
+                ("out_cols", C.c_int32)]
 
 
 _lib = None
@@ -1177,12 +1178,18 @@ class GridDeviceRun:
 
     def launch_chunk(self, input_ptr: int, rec_ptr: int, n_steps: int, init_bucket: Optional[int], init_route: Optional[int],
                      final_bucket: Optional[int], final_route: Optional[int], out_first: int = 0, out_count: int = 0,
-                     stream: Optional[int] = None):
-        """`n_steps` steps from caller-owned state buffers (`[S][N]` / `[N]` device pointers, None = zeros / not wanted);
-        records of nodes `[out_first, out_first + out_count)` only (0 = all).  Asynchronous on `stream`."""
+                     stream: Optional[int] = None, out_window: Optional[Tuple[int, int, int, int]] = None):
+        """`n_steps` steps from caller-owned state buffers (`[S][N]` / `[N]` device pointers, None = zeros / not wanted).
+        Records are written for whole rows `[out_first, out_first + out_count)` (node range, 0 = all) or for the window
+        `out_window = (row0, rows, col0, cols)`, as `[T][rows][cols][R]`.  Asynchronous on `stream`."""
         d = self._desc(input_ptr, rec_ptr, n_steps)
         d.init_bucket, d.init_route, d.final_bucket, d.final_route = init_bucket, init_route, final_bucket, final_route
-        d.out_first_node, d.out_node_count = out_first, out_count
+        if out_window is not None:
+            d.out_row0, d.out_rows, d.out_col0, d.out_cols = [int(x) for x in out_window]
+        elif out_count:
+            if out_first % self.cols or out_count % self.cols:
+                raise ValueError("an output node range must consist of whole grid rows")
+            d.out_row0, d.out_rows = out_first // self.cols, out_count // self.cols
         check(lib().hb_run_grid_device(self.ck.handle, C.byref(d), stream))
 
     def _desc(self, input_ptr: int, rec_ptr: int, n_steps: int) -> GridDesc:

@@ -245,9 +245,10 @@ typedef struct {
     double *final_bucket;       /* DEVICE [S][N] or NULL */
     double *final_route;        /* DEVICE [N] or NULL */
     float *elapsed_ms;          /* optional HOST pointer */
-    int64_t out_first_node;     /* WAVE: records are written for nodes [out_first_node, out_first_node + out_node_count) only, */
-    int64_t out_node_count;     /*   as out[T][out_node_count][R] (0 = all nodes).  A strip of a multi-GPU run computes ghost rows */
-                                /*   (depth = steps between state exchanges) whose records belong to the neighbouring rank.      */
+    int32_t out_row0, out_rows; /* WAVE: records are written only for the cells of rows [out_row0, out_row0 + out_rows) x columns   */
+    int32_t out_col0, out_cols; /*   [out_col0, out_col0 + out_cols), as out[T][out_rows][out_cols][R] (0 rows / cols = all).  A strip or */
+                                /*   panel of a multi-GPU run computes ghost rows / columns (depth = steps between state exchanges)     */
+                                /*   whose records belong to the neighbouring rank.                                                      */
 } hb_grid_desc;
 
 int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out);

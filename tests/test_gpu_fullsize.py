@@ -163,11 +163,16 @@ def test_grid_2048x2048_wave_kernel_is_bit_identical_to_the_two_pass_path():
     RoutedDeviceRun(eng, N, T, p, initstates=init).launch(d_in.data_ptr(), ref.data_ptr(), st)
     got = torch.zeros((T, N, 13), device="cuda", dtype=torch.float64)
     run = GridDeviceRun(eng, N, T, p, initstates=init, variant="wave", steps_per_chunk=16)
-    for _ in range(2):
+    for rep in range(2):
         got.zero_()
         run.launch(d_in.data_ptr(), got.data_ptr(), st)
         assert run.check() == 16
-        assert bool(torch.equal(got, ref))
+        if not bool(torch.equal(got, ref)):
+            bad = (got != ref).nonzero()
+            t, n, r = [int(x) for x in bad[0]]
+            raise AssertionError(f"rep {rep}: {bad.shape[0]} values differ; rows {torch.unique(bad[:, 2]).tolist()}, steps "
+                                 f"{torch.unique(bad[:, 0]).tolist()[:12]}, first (t, n, row) = {(t, n, r)} at grid ({n // side}, {n % side}): "
+                                 f"got {got[t, n, r].item()!r} ref {ref[t, n, r].item()!r}; cells {torch.unique(bad[:, 1]).numel()}")
     assert float(ref[:, :, 12].max()) > float(ref[:, :, 11].max())           # routing did accumulate flow
     # the middle strip of a 4-way decomposition, 16 ghost rows either side, first 16 steps from the initial states
     pl = par.GridStripPlan(side, side, 1, 4, 16)

@@ -147,7 +147,85 @@ def test_strip_of_a_grid_on_one_gpu_matches_the_whole_grid():
                          pl.out_first, pl.out_count, None)
         run.check()
         got = rec.cpu().numpy().transpose(2, 1, 0)[:, :, :halo]
-        assert np.array_equal(got, whole[:, pl.r0 * Cc:pl.r1 * Cc, :halo])
+        ref = whole[:, pl.r0 * Cc:pl.r1 * Cc, :halo]
+        if not np.array_equal(got, ref):
+            bad = np.argwhere(got != ref)
+            raise AssertionError(f"strip {rank}/{world}: {len(bad)} values differ; rows {np.unique(bad[:, 0])}, steps {np.unique(bad[:, 2])}, "
+                                 f"cells {np.unique(bad[:, 1])[:16]}, first {bad[0]}: got {got[tuple(bad[0])]!r} ref {ref[tuple(bad[0])]!r}")
         own = slice(pl.out_first, pl.out_first + pl.out_count)
         assert np.array_equal(b1.cpu().numpy()[:, own], whole[:2, pl.r0 * Cc:pl.r1 * Cc, halo - 1])
         assert np.array_equal(r1.cpu().numpy()[own], whole[2, pl.r0 * Cc:pl.r1 * Cc, halo - 1])
+
+
+def _panel_worker(rank, world, port, R, Cc, T, halo, q):
+    import torch
+    import torch.distributed as dist
+    from hydromodels_jl_b200 import parallel as par
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    hm.engine.init(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    model, p, init, N = _grid_problem(R, Cc, T)
+    run = par.ShardedPanelRun(hm.B200Model(model), R, Cc, T, p, initstates=init, halo=halo)
+    inp = sy.forcing("exphydro", 0, N, T)[:, run.plan.idx, :]       # forcing of the computed cells, local row-major order
+    d_in = torch.from_numpy(np.ascontiguousarray(inp.transpose(2, 1, 0))).cuda()
+    rec = torch.zeros((T, run.N, run.n_rows), dtype=torch.float64, device="cuda")
+    run.launch(d_in.data_ptr(), rec.data_ptr())
+    run.launch(d_in.data_ptr(), rec.data_ptr())
+    run.check()
+    q.put((run.plan.c0, run.plan.c1, rec.cpu().numpy().transpose(2, 1, 0)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("R,Cc,T,halo", [(30, 41, 25, 4), (64, 256, 70, 32)])
+def test_sharded_column_panels_match_single_gpu(R, Cc, T, halo):
+    """Column panels + ghost columns (sub-model restricted to the panel's cells, global parameter vectors gathered through
+    htypes), states exchanged every `halo` steps: bit-identical to one GPU."""
+    import torch.multiprocessing as mp
+    world = min(_ngpu(), 4)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 36500 + (os.getpid() % 2000) + halo
+    procs = [ctx.Process(target=_panel_worker, args=(r, world, port, R, Cc, T, halo, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    model, p, init, N = _grid_problem(R, Cc, T)
+    got = np.zeros((13, R, Cc, T))
+    for _ in range(world):
+        a, b, part = q.get(timeout=300)
+        got[:, :, a:b, :] = part.reshape(13, R, b - a, T)
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    single = model(sy.forcing("exphydro", 0, N, T), p, initstates=init)
+    assert np.array_equal(got.reshape(13, N, T), single)
+
+
+def test_panel_of_a_grid_on_one_gpu_matches_the_whole_grid():
+    """One GPU's view of the column-panel decomposition: the sub-model of a panel with ghost columns, one chunk of `halo`
+    steps from the initial states, records of the owned window only (TMA-aligned 32-column ghosts and odd ones)."""
+    import torch
+    from hydromodels_jl_b200 import parallel as par
+    from hydromodels_jl_b200.engine import GridDeviceRun
+    for R, Cc, T, halo in [(40, 192, 33, 32), (25, 70, 12, 5)]:
+        model, p, init, N = _grid_problem(R, Cc, T)
+        whole = model(sy.forcing("exphydro", 0, N, T), p, initstates=init).reshape(13, R, Cc, T)
+        for rank, world in [(0, 3), (1, 3), (2, 3)]:
+            pl = par.GridPanelPlan(R, Cc, rank, world, halo)
+            sub = par.submodel_for_cells(model, pl.idx, model.components[-1].aggr.flwdir[:, pl.g0:pl.g1])
+            eng = hm.B200Model(sub)
+            li = {k: v[pl.idx] for k, v in init.items()}
+            run = GridDeviceRun(eng, pl.n_local, T, p, initstates=li, variant="wave", steps_per_chunk=16)
+            d_in = torch.from_numpy(np.ascontiguousarray(sy.forcing("exphydro", 0, N, T)[:, pl.idx, :].transpose(2, 1, 0))).cuda()
+            rec = torch.zeros((T, pl.out_count, 13), dtype=torch.float64, device="cuda")
+            b0 = torch.from_numpy(run.bufs["init"].to_host((2, pl.n_local))).cuda()
+            r0 = torch.from_numpy(run.bufs["rinit"].to_host((pl.n_local,))).cuda()
+            b1, r1 = torch.zeros_like(b0), torch.zeros_like(r0)
+            ns = min(halo, T)
+            run.launch_chunk(d_in.data_ptr(), rec.data_ptr(), ns, b0.data_ptr(), r0.data_ptr(), b1.data_ptr(), r1.data_ptr(),
+                             out_window=pl.out_window)
+            run.check()
+            got = rec.cpu().numpy().transpose(2, 1, 0).reshape(13, R, pl.c1 - pl.c0, T)[:, :, :, :ns]
+            assert np.array_equal(got, whole[:, :, pl.c0:pl.c1, :ns])

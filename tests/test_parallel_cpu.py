@@ -225,3 +225,64 @@ def test_strip_plan_geometry():
             assert a.g0 * cols + sa[0] == b.g0 * cols + qb[0] and b.g0 * cols + sb[0] == a.g0 * cols + qa[0]
         for pl in plans:
             assert pl.out_first + pl.out_count <= pl.n_local and pl.out_count == (pl.r1 - pl.r0) * cols
+
+
+# ---- column panels: ghost COLUMNS, sub-model restricted to the panel's cells -----------------------------------------
+def _panel_worker(rank, world, port, R, Cc, T, halo, flw, qu):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import hydro_oracle as ho
+    N = R * Cc
+    pl = par.GridPanelPlan(R, Cc, rank, world, halo)
+    rr, cc = np.divmod(np.arange(N), Cc)
+    whole = hm.models.exphydro_grid(flw, np.stack([rr + 1, cc + 1], axis=1), htypes=np.arange(1, N + 1))
+    sub = par.submodel_for_cells(whole, pl.idx, flw[:, pl.g0:pl.g1])
+    rng = np.random.default_rng(3)
+    pg = dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))
+    inp = sy.forcing("exphydro", 0, N, T)[:, pl.idx, :]
+    s_river0 = rng.uniform(0, 2, N)
+    states = [torch.zeros(pl.n_local, dtype=torch.float64), torch.full((pl.n_local,), 1303.0, dtype=torch.float64),
+              torch.from_numpy(s_river0[pl.idx].copy())]
+    r0, nr, c0, nc = pl.out_window
+    own = (np.arange(r0, r0 + nr)[:, None] * pl.local_cols + np.arange(c0, c0 + nc)[None, :]).reshape(-1)
+    out = np.zeros((13, pl.out_count, T))
+    for t0 in range(0, T, halo):
+        ns = min(halo, T - t0)
+        init = dict(snowpack=states[0].numpy(), soilwater=states[1].numpy(), s_river=states[2].numpy())
+        full = ho.run_model(sub, inp[:, :, t0:t0 + ns], {"params": pg}, initstates=init)       # GLOBAL parameter vectors
+        out[:, :, t0:t0 + ns] = full[:, own, :]
+        states = [torch.from_numpy(np.ascontiguousarray(full[i, :, -1])) for i in range(3)]
+        if t0 + ns < T:
+            par.exchange_panel_states(states, pl)
+    qu.put((pl.c0, pl.c1, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,halo", [(2, 3), (3, 2)])
+def test_panel_plan_with_ghost_columns_reproduces_the_whole_grid(world, halo):
+    import hydro_oracle as ho
+    rng = np.random.default_rng(23)
+    R, Cc, T = 6, 13, 9
+    flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128, 0], size=(R, Cc))
+    N = R * Cc
+    ctx = mp.get_context("spawn")
+    qu = ctx.Queue()
+    port = 35500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_panel_worker, args=(r, world, port, R, Cc, T, halo, flw, qu)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = np.zeros((13, R, Cc, T))
+    for _ in range(world):
+        a, b, part = qu.get(timeout=180)
+        got[:, :, a:b, :] = part.reshape(13, R, b - a, T)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    rr, cc = np.divmod(np.arange(N), Cc)
+    model = hm.models.exphydro_grid(flw, np.stack([rr + 1, cc + 1], axis=1))
+    rng = np.random.default_rng(3)
+    pg = dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))
+    init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 2, N))
+    ref = ho.run_model(model, sy.forcing("exphydro", 0, N, T), {"params": pg}, initstates=init)
+    assert np.array_equal(got.reshape(13, N, T), ref)
