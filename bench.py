@@ -40,6 +40,8 @@ WORKLOADS = {
     # BASELINE config 5 (single-GPU slice): distributed ExpHydro + D8 routing on a 2048 x 2048 grid
     "exphydro_grid_2048x2048_x_60d": ("exphydro_grid", 2048 * 2048, 60),
     "exphydro_grid_512x512_x_60d": ("exphydro_grid", 512 * 512, 60),
+    # BASELINE config 5 proper: ONE 4096 x 4096 grid, sharded over the ranks (strong scaling; 60 steps fit a single GPU too)
+    "exphydro_grid_4096x4096_total_x_60d": ("exphydro_grid", 4096 * 4096, 60),
 }
 DEFAULT_WORKLOAD = "exphydro_1M_basins_x_365d"
 
@@ -329,6 +331,9 @@ def main():
                     help="grid workload: wave = single-pass L2-dataflow kernel (gridwave.cu, default); tile = tile + halo "
                          "(grid.cu); generic = stepper over all T, then one routing launch per step")
     ap.add_argument("--fused-grid", action="store_true", help="(round-1 flag) same as --grid-kernel tile")
+    ap.add_argument("--grid-split", default="rows", choices=["rows", "cols"],
+                    help="multi-GPU grid workload: row strips (the ranks' square grids stacked vertically) or column panels (side by side; "
+                         "the wave kernel runs tall narrow sub-grids faster than short wide ones)")
     args = ap.parse_args()
     if args.fused_grid:
         args.grid_kernel = "tile"
@@ -344,6 +349,9 @@ def main():
     if args.workload == "irf_route":
         return bench_irf(args) if rank == 0 else 0
     model_name, N, T = WORKLOADS[args.workload]
+    total_grid = "_total_" in args.workload
+    if total_grid:
+        N //= int(os.environ.get("WORLD_SIZE", "1"))          # cells owned per rank
     rows_of = {"exphydro": 10, "gr4j": 15, "hbv": 18, "m50": 12, "hbv_ensemble": 0, "exphydro_grid": 13}[model_name]
     v_of = {"exphydro": 3, "gr4j": 2, "hbv": 3, "m50": 3, "hbv_ensemble": 0, "exphydro_grid": 3}[model_name]
     unit = "basin-timesteps/s"
@@ -408,8 +416,16 @@ def main():
         side = int(round(N ** 0.5))
         Ng = N * world
         rng = np.random.default_rng(sy.SEED)
-        flw = rng.choice(np.array([1, 2, 4, 8, 16, 32, 64, 128]), size=(side * world, side), p=[.3, .2, .3, .05, .03, .02, .05, .05])
-        rr, cc = np.divmod(np.arange(Ng), side)
+        panels = world > 1 and args.grid_kernel == "wave" and args.grid_split == "cols"
+        g_rows, g_cols = (side, side * world) if panels else (side * world, side)
+        if total_grid:
+            g_rows = g_cols = int(round(Ng ** 0.5))
+            side = g_cols
+            config["scaling_note"] = f"one {g_rows} x {g_cols} grid cut into {world} {'column panels' if panels else 'row strips'}"
+            if world > 1 and args.grid_kernel != "wave":
+                raise SystemExit("the total-grid workload is sharded with the wave kernel only")
+        flw = rng.choice(np.array([1, 2, 4, 8, 16, 32, 64, 128]), size=(g_rows, g_cols), p=[.3, .2, .3, .05, .03, .02, .05, .05])
+        rr, cc = np.divmod(np.arange(Ng), g_cols)
         pos = np.stack([rr + 1, cc + 1], axis=1)
         model = hm.models.exphydro_grid(flw, pos)
         pp = sy.parameters("exphydro", 0, Ng)
@@ -417,10 +433,24 @@ def main():
         p = {"params": pp}
         init = dict(snowpack=np.zeros(Ng), soilwater=np.full(Ng, 1303.0), s_river=np.zeros(Ng))
         eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
-        if world > 1 and args.grid_kernel == "wave":
+        if panels:
+            # column panels + 32 ghost columns, states exchanged every 32 steps
+            from hydromodels_jl_b200.parallel import ShardedPanelRun
+            sharded = ShardedPanelRun(eng, g_rows, g_cols, T, p, initstates=init, halo=32, stages=args.stages,
+                                      max_registers=args.maxreg, block_threads=args.block, steps_per_launch=args.grid_tc)
+            assert sharded.N == N
+            eng.last_kernel = sharded.run.ck
+            grid_run = sharded
+            config["grid_split"] = "column panels, 32 ghost columns"
+
+            class _Run:
+                def launch(self, ip, op, stream=None):
+                    sharded.launch(ip, op)
+            run = _Run()
+        elif world > 1 and args.grid_kernel == "wave":
             # row strips + ghost rows, bucket / river states exchanged every `grid_tc` steps (temporal blocking)
             from hydromodels_jl_b200.parallel import ShardedGridRun
-            sharded = ShardedGridRun(eng, side * world, side, T, p, initstates=init, halo=args.grid_tc, stages=args.stages,
+            sharded = ShardedGridRun(eng, g_rows, g_cols, T, p, initstates=init, halo=args.grid_tc, stages=args.stages,
                                      max_registers=args.maxreg, block_threads=args.block)
             assert sharded.N == N
             eng.last_kernel = sharded.run.ck
@@ -451,8 +481,26 @@ def main():
                                     block_h=args.grid_bh)
             eng.last_kernel = run.ck
             grid_run = run
-        d_in = device_forcing(torch, "exphydro", N, T, sy.SEED + 17 * rank)
-        if world > 1 and args.grid_kernel == "wave":
+        d_in = device_forcing(torch, "exphydro", sharded.plan.n_local if (total_grid and world > 1) else N, T, sy.SEED + 17 * rank)
+        if total_grid:
+            pass          # one seed for the whole computed region of the rank (ghost cells included): timing only
+        elif panels:
+            # forcing of the ghost columns: the adjacent columns of the neighbouring ranks' panels (same generator, their seed)
+            pl = sharded.plan
+            parts = []
+            if rank > 0:
+                left = device_forcing(torch, "exphydro", N, T, sy.SEED + 17 * (rank - 1)).view(T, side, side, v_of)
+                parts.append(left[:, :, side - (pl.c0 - pl.g0):, :].clone())
+                del left
+            parts.append(d_in.view(T, side, side, v_of))
+            if rank < world - 1:
+                right = device_forcing(torch, "exphydro", N, T, sy.SEED + 17 * (rank + 1)).view(T, side, side, v_of)
+                parts.append(right[:, :, :pl.g1 - pl.c1, :].clone())
+                del right
+            d_in = torch.cat(parts, dim=2).reshape(T, pl.n_local, v_of).contiguous()
+            del parts
+            torch.cuda.empty_cache()
+        elif world > 1 and args.grid_kernel == "wave":
             # forcing of the ghost rows: the adjacent rows of the neighbouring ranks' forcing (same generator, their seed)
             pl = sharded.plan
             parts = []
@@ -582,7 +630,7 @@ def main():
         print(json.dumps({
             "metric": "basin-timesteps/sec", "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "scaling": "strong" if total_grid else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "kernel_ms_each": [round(x, 4) for x in kernel_ms]}))
     if dist is not None:
