@@ -331,6 +331,9 @@ def main():
                     help="grid workload: wave = single-pass L2-dataflow kernel (gridwave.cu, default); tile = tile + halo "
                          "(grid.cu); generic = stepper over all T, then one routing launch per step")
     ap.add_argument("--fused-grid", action="store_true", help="(round-1 flag) same as --grid-kernel tile")
+    ap.add_argument("--grid-panels", type=int, default=-1,
+                    help="single-GPU grid workload, wave kernel: run the grid as this many column panels one after the other "
+                         "(0 = auto: one per ~1024 columns; 1 = one kernel over the whole grid; -1 = auto for grids wider than 3000 columns)")
     ap.add_argument("--grid-split", default="rows", choices=["rows", "cols"],
                     help="multi-GPU grid workload: row strips (the ranks' square grids stacked vertically) or column panels (side by side; "
                          "the wave kernel runs tall narrow sub-grids faster than short wide ones)")
@@ -473,7 +476,13 @@ def main():
             run = RoutedDeviceRun(eng, N, T, p, initstates=init)
         else:
             from hydromodels_jl_b200.engine import GridDeviceRun
-            if args.grid_kernel == "wave":
+            n_panels = args.grid_panels if args.grid_panels >= 0 else (0 if g_cols > 3000 else 1)
+            if args.grid_kernel == "wave" and n_panels != 1:
+                from hydromodels_jl_b200.parallel import PanelledGridRun
+                run = PanelledGridRun(eng, g_rows, g_cols, T, p, initstates=init, panels=n_panels, steps_per_launch=args.grid_tc,
+                                      block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
+                config["grid_panels"] = run.K
+            elif args.grid_kernel == "wave":
                 run = GridDeviceRun(eng, N, T, p, initstates=init, variant="wave", steps_per_chunk=args.grid_tc,
                                     block_w=args.block, stages=args.stages, max_registers=args.maxreg)
             else:

@@ -943,7 +943,7 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
     uint32_t ticket_base = 0;
     for (int64_t t0 = 0; t0 < T; t0 += tc) {
         // HbGridArgs / HbWaveArgs mirrors (templates/grid.cu, templates/gridwave.cu)
-        unsigned char buf[12 * 8 + 4 * 8 + 32 + 8 + 8 * HB_MAX_PARAMS + 16];
+        unsigned char buf[12 * 8 + 4 * 8 + 32 + 8 + 32 + 8 * HB_MAX_PARAMS + 16];
         memset(buf, 0, sizeof buf);
         size_t o = 0;
         auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
@@ -962,8 +962,11 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
             put(&o_c0, 4);
             put(&o_nc, 4);
             // TMA bulk copies need 16-byte aligned global addresses: base pointers and per-step strides
-            int tma_in = ((reinterpret_cast<uintptr_t>(d->input) & 15) == 0) && ((N * s.n_inputs * 8) % 16 == 0);
-            int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && (((int64_t)o_nr * o_nc * s.n_rows * 8) % 16 == 0);
+            const int64_t in_ts = d->in_t_stride > 0 ? d->in_t_stride : N, out_ts = d->out_t_stride > 0 ? d->out_t_stride : (int64_t)o_nr * o_nc;
+            const int in_pitch = d->in_pitch > 0 ? d->in_pitch : d->cols, in_col0 = d->in_pitch > 0 ? d->in_col0 : 0;
+            const int out_pitch = d->out_pitch > 0 ? d->out_pitch : o_nc, out_base = d->out_pitch > 0 ? d->out_base : 0;
+            int tma_in = ((reinterpret_cast<uintptr_t>(d->input) & 15) == 0) && ((in_ts * s.n_inputs * 8) % 16 == 0);
+            int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((out_ts * s.n_rows * 8) % 16 == 0);
             if (getenv("HB_DISABLE_TMA")) tma_in = tma_out = 0;
             if (getenv("HB_DISABLE_TMA_IN")) tma_in = 0;
             if (getenv("HB_DISABLE_TMA_OUT")) tma_out = 0;
@@ -974,6 +977,12 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
             put(&tma_in, 4);
             put(&tma_out, 4);
             put(&minv, 8);
+            put(&in_ts, 8);
+            put(&out_ts, 8);
+            put(&in_pitch, 4);
+            put(&in_col0, 4);
+            put(&out_pitch, 4);
+            put(&out_base, 4);
             ticket_base += gx;
         } else {
             put(&N, 8);

@@ -76,6 +76,12 @@ struct HbWaveArgs {
     int rows, cols;
     int tma_in_ok, tma_out_ok;
     double min_value;
+    // pitched addressing: a sub-grid (column panel) run in place on the arrays of a wider grid.  Forcing of local cell (r, c) at
+    // step t: in[(t * in_tstride + r * in_pitch + in_col0 + c) * V]; record of an owned cell:
+    // out[(t * out_tstride + (r - out_r0) * out_pitch + out_base + (c - out_c0)) * R].  Compact sub-grids: in_pitch = cols,
+    // in_col0 = 0, in_tstride = N; out_pitch = out_nc, out_base = 0, out_tstride = out_nr * out_nc.
+    i64 in_tstride, out_tstride;
+    int in_pitch, in_col0, out_pitch, out_base;
     int p_off[HB_ARR(HB_NP)];
     int p_mode[HB_ARR(HB_NP)];
 };
@@ -164,12 +170,14 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
     real *sOut = reinterpret_cast<real *>(warp_base + kInBytes);
     u64 *bars = reinterpret_cast<u64 *>(hb_smem + (size_t)HB_WARPS * (kInBytes + kOutBytes)) + warp * HB_STAGES;
 
-    const bool tma_in = a.tma_in_ok && full_warp;
+    const i64 in_cell = (nc / a.cols) * a.in_pitch + a.in_col0 + (nc % a.cols);        // this cell / the warp's first cell in the forcing array
+    const i64 in_cell_w = (n0w / a.cols) * a.in_pitch + a.in_col0 + (n0w % a.cols);
+    const bool tma_in = a.tma_in_ok && full_warp && (n0w % a.cols) + 32 <= a.cols && ((in_cell_w * HB_V * 8) & 15) == 0;
     // position of this cell / of the warp's first cell in the output window
     const int o_r = (int)(nc / a.cols) - a.out_r0, o_c = (int)(nc % a.cols) - a.out_c0;
     const int ow_r = (int)(n0w / a.cols) - a.out_r0, ow_c = (int)(n0w % a.cols) - a.out_c0;
     const bool out_valid = valid && o_r >= 0 && o_r < a.out_nr && o_c >= 0 && o_c < a.out_nc;
-    const i64 o_rel = (i64)o_r * a.out_nc + o_c, ow_rel = (i64)ow_r * a.out_nc + ow_c;
+    const i64 o_rel = (i64)o_r * a.out_pitch + a.out_base + o_c, ow_rel = (i64)ow_r * a.out_pitch + a.out_base + ow_c;
     // the bulk store needs the warp's 32 cells in one row, inside the window, at a 16-byte aligned record offset
     const bool tma_out = a.tma_out_ok && full_warp && (n0w % a.cols) + 32 <= a.cols && ow_r >= 0 && ow_r < a.out_nr && ow_c >= 0 &&
                          ow_c + 32 <= a.out_nc && ((ow_rel * HB_R * 8) & 15) == 0;
@@ -224,10 +232,10 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
     //@@HB:PROLOGUE
 
     const int ns = a.nsteps;
-    const i64 in_step = a.N * (i64)HB_V;
-    const i64 out_step = (i64)a.out_nr * a.out_nc * HB_R;
-    const real *in_warp = a.in + (a.t0 * a.N + n0w) * HB_V;
-    const real *gx = a.in + (a.t0 * a.N + nc) * HB_V;
+    const i64 in_step = a.in_tstride * HB_V;
+    const i64 out_step = a.out_tstride * HB_R;
+    const real *in_warp = a.in + (a.t0 * a.in_tstride + in_cell_w) * HB_V;
+    const real *gx = a.in + (a.t0 * a.in_tstride + in_cell) * HB_V;
     real *ow_ptr = a.out + a.t0 * out_step + ow_rel * HB_R;
     real *go = a.out + a.t0 * out_step + o_rel * HB_R;
 

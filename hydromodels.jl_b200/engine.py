@@ -88,7 +88,8 @@ class GridDesc(C.Structure):
                 ("htypes", C.c_void_p), ("init_bucket", C.c_void_p), ("init_route", C.c_void_p), ("flwdir", C.c_void_p),
                 ("min_value", C.c_double), ("final_bucket", C.c_void_p), ("final_route", C.c_void_p),
                 ("elapsed_ms", C.c_void_p), ("out_row0", C.c_int32), ("out_rows", C.c_int32), ("out_col0", C.c_int32),
-                ("out_cols", C.c_int32)]
+                ("out_cols", C.c_int32), ("in_t_stride", C.c_int64), ("out_t_stride", C.c_int64), ("in_pitch", C.c_int32),
+                ("in_col0", C.c_int32), ("out_pitch", C.c_int32), ("out_base", C.c_int32)]
 
 
 _lib = None
@@ -357,6 +358,7 @@ class B200Model:
         # "generic" = stepper over all T, then one routing launch per step (any node list / graph)
         self.grid_kernel = "wave"
         self.grid_steps_per_launch = 16
+        self.grid_panel_min_cols = 3072      # wave kernel: grids at least this wide run as column panels (parallel.PanelledGridRun)
         self.block_threads, self.stages, self.max_registers = block_threads, stages, max_registers
         self._cache: Dict[Tuple, CompiledStepper] = {}
         self.last_kernel: Optional[CompiledStepper] = None
@@ -667,7 +669,15 @@ class B200Model:
         # dense row-major grid, bucket/flux components only: fused single-pass kernel (templates/grid.cu)
         if (self.lumped is not None and not extra and self.use_fused_grid and dense_grid_shape(route.aggr, N) is not None
                 and not self._has_uh() and not self.lumped.nn_names and N * T > 0):
-            if self.grid_kernel == "wave":
+            shape = dense_grid_shape(route.aggr, N)
+            if self.grid_kernel == "wave" and shape[1] >= self.grid_panel_min_cols:
+                # a wide grid runs faster as column panels, one after the other, in place on the whole grid's arrays
+                from .parallel import PanelledGridRun
+                run = PanelledGridRun(self, shape[0], shape[1], T, params, config=cfg, initstates=init_all,
+                                      steps_per_launch=self.grid_steps_per_launch, block_threads=self.block_threads,
+                                      stages=self.stages, max_registers=self.max_registers)
+                self._cache[("grid", "wave", "panels", run.K)] = run.ck
+            elif self.grid_kernel == "wave":
                 run = GridDeviceRun(self, N, T, params, config=cfg, initstates=init_all, variant="wave",
                                     steps_per_chunk=self.grid_steps_per_launch, block_w=self.block_threads, stages=self.stages,
                                     max_registers=self.max_registers)
@@ -677,7 +687,11 @@ class B200Model:
             din = DeviceBuffer.from_host(inp.ravel(order="K"))
             rec = DeviceBuffer(T * N * R * 8)
             try:
-                ms = run.launch(din.ptr, rec.ptr, None, timed=True)
+                if isinstance(run, GridDeviceRun):
+                    ms = run.launch(din.ptr, rec.ptr, None, timed=True)
+                else:
+                    run.launch(din.ptr, rec.ptr, None)
+                    ms = None
                 run.check()
                 full = rec.to_host((R, N, T), order="F")
             except HydroB200Error as ex:
@@ -1178,12 +1192,19 @@ class GridDeviceRun:
 
     def launch_chunk(self, input_ptr: int, rec_ptr: int, n_steps: int, init_bucket: Optional[int], init_route: Optional[int],
                      final_bucket: Optional[int], final_route: Optional[int], out_first: int = 0, out_count: int = 0,
-                     stream: Optional[int] = None, out_window: Optional[Tuple[int, int, int, int]] = None):
+                     stream: Optional[int] = None, out_window: Optional[Tuple[int, int, int, int]] = None,
+                     in_pitched: Optional[Tuple[int, int, int]] = None, out_pitched: Optional[Tuple[int, int, int]] = None):
         """`n_steps` steps from caller-owned state buffers (`[S][N]` / `[N]` device pointers, None = zeros / not wanted).
         Records are written for whole rows `[out_first, out_first + out_count)` (node range, 0 = all) or for the window
-        `out_window = (row0, rows, col0, cols)`, as `[T][rows][cols][R]`.  Asynchronous on `stream`."""
+        `out_window = (row0, rows, col0, cols)`, as `[T][rows][cols][R]`.  `in_pitched = (t_stride, pitch, col0)` /
+        `out_pitched = (t_stride, pitch, base)` (in cells) address the forcing / the records of this sub-grid inside the
+        arrays of a wider grid (`hb_grid_desc`).  Asynchronous on `stream`."""
         d = self._desc(input_ptr, rec_ptr, n_steps)
         d.init_bucket, d.init_route, d.final_bucket, d.final_route = init_bucket, init_route, final_bucket, final_route
+        if in_pitched is not None:
+            d.in_t_stride, d.in_pitch, d.in_col0 = [int(x) for x in in_pitched]
+        if out_pitched is not None:
+            d.out_t_stride, d.out_pitch, d.out_base = [int(x) for x in out_pitched]
         if out_window is not None:
             d.out_row0, d.out_rows, d.out_col0, d.out_cols = [int(x) for x in out_window]
         elif out_count:

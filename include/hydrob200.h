@@ -249,6 +249,11 @@ typedef struct {
     int32_t out_col0, out_cols; /*   [out_col0, out_col0 + out_cols), as out[T][out_rows][out_cols][R] (0 rows / cols = all).  A strip or */
                                 /*   panel of a multi-GPU run computes ghost rows / columns (depth = steps between state exchanges)     */
                                 /*   whose records belong to the neighbouring rank.                                                      */
+    /* WAVE, pitched addressing (all 0 = compact arrays): run a sub-grid (a column panel of a wider grid) in place on the wider
+     * grid's arrays.  Forcing of local cell (r, c) at step t is input[(t * in_t_stride + r * in_pitch + in_col0 + c) * V]; the
+     * record of an owned cell goes to out[(t * out_t_stride + (r - out_row0) * out_pitch + out_base + (c - out_col0)) * R]. */
+    int64_t in_t_stride, out_t_stride;
+    int32_t in_pitch, in_col0, out_pitch, out_base;
 } hb_grid_desc;
 
 int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out);

@@ -229,3 +229,28 @@ def test_panel_of_a_grid_on_one_gpu_matches_the_whole_grid():
             run.check()
             got = rec.cpu().numpy().transpose(2, 1, 0).reshape(13, R, pl.c1 - pl.c0, T)[:, :, :, :ns]
             assert np.array_equal(got, whole[:, :, pl.c0:pl.c1, :ns])
+
+
+@pytest.mark.parametrize("R,Cc,T,K,halo", [(40, 256, 70, 3, 32), (25, 70, 20, 2, 5), (64, 192, 45, 1, 32)])
+def test_panelled_run_on_one_gpu_matches_the_single_kernel(R, Cc, T, K, halo):
+    """A wide grid run as K column panels one after the other on ONE GPU, in place on the whole grid's forcing and record arrays
+    (pitched addressing), ghost-column states copied between panels every `halo` steps: every value equals the one-kernel run."""
+    import torch
+    from hydromodels_jl_b200 import parallel as par
+    model, p, init, N = _grid_problem(R, Cc, T)
+    inp = sy.forcing("exphydro", 0, N, T)
+    whole = model(inp, p, initstates=init)
+    run = par.PanelledGridRun(hm.B200Model(model), R, Cc, T, p, initstates=init, panels=K, halo=halo)
+    assert run.K == K
+    d_in = torch.from_numpy(np.ascontiguousarray(inp.transpose(2, 1, 0))).cuda()
+    rec = torch.zeros((T, N, 13), dtype=torch.float64, device="cuda")
+    for rep in range(2):
+        rec.zero_()
+        run.launch(d_in.data_ptr(), rec.data_ptr())
+        run.check()
+        got = rec.cpu().numpy().transpose(2, 1, 0)
+        if not np.array_equal(got, whole):
+            bad = np.argwhere(got != whole)
+            cells = np.unique(bad[:, 1])
+            raise AssertionError(f"rep {rep}: {len(bad)} values differ; rows {np.unique(bad[:, 0])}, steps {np.unique(bad[:, 2])[:10]}, grid columns "
+                                 f"{np.unique(cells % Cc)[:20]}, grid rows {np.unique(cells // Cc)[:10]}, first {bad[0]}: {got[tuple(bad[0])]!r} vs {whole[tuple(bad[0])]!r}")

@@ -492,3 +492,27 @@ def test_wave_grid_kernel_with_shared_hru_types():
     eng2 = hm.B200Model(model)
     eng2.grid_kernel = "generic"
     assert np.array_equal(wave, eng2(inp, p, initstates=init))
+
+
+def test_wide_grid_takes_the_panelled_path_through_the_functor():
+    """`B200Model.__call__` on a grid wider than `grid_panel_min_cols`: column panels one after the other, same result."""
+    R, Cc, T = 12, 300, 40
+    rng = np.random.default_rng(8)
+    N = R * Cc
+    flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128, 0], size=(R, Cc))
+    rr, cc = np.divmod(np.arange(N), Cc)
+    model = hm.models.exphydro_grid(flw, np.stack([rr + 1, cc + 1], axis=1))
+    p = {"params": dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))}
+    init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 2, N))
+    inp = sy.forcing("exphydro", 0, N, T)
+    eng = hm.B200Model(model)
+    eng.grid_panel_min_cols = 128                  # force the path at test size: 300 columns -> 1 panel per ~1024 would be 1; use 2
+    from hydromodels_jl_b200 import parallel as par
+    one = hm.B200Model(model)
+    one.grid_panel_min_cols = 10 ** 9
+    ref = one(inp, p, initstates=init)
+    got = eng(inp, p, initstates=init)
+    assert any(isinstance(k, tuple) and k[:3] == ("grid", "wave", "panels") for k in eng._cache)
+    assert np.array_equal(got, ref)
+    run = par.PanelledGridRun(eng, R, Cc, T, p, initstates=init, panels=3)
+    assert run.K == 3
