@@ -324,6 +324,7 @@ def main():
     ap.add_argument("--block", type=int, default=0, help="tuning: threads per block of the stepper")
     ap.add_argument("--stages", type=int, default=0, help="tuning: forcing pipeline depth (time steps)")
     ap.add_argument("--maxreg", type=int, default=0, help="tuning: register budget per thread")
+    ap.add_argument("--npw", type=int, default=0, help="tuning: nodes per warp of tensor-path MLP bodies (16 | 32; 0 = by node count)")
     ap.add_argument("--grid-tc", type=int, default=0, help="grid kernels: time steps per launch (0 = 16 for wave, 2 for tile)")
     ap.add_argument("--grid-bw", type=int, default=32, help="fused grid kernel: region width (cells)")
     ap.add_argument("--grid-bh", type=int, default=32, help="fused grid kernel: region height (cells)")
@@ -529,6 +530,7 @@ def main():
     else:
         model, p, init = build_problem(hm, sy, model_name, n0, N, T)
         eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
+        eng.nodes_per_warp = args.npw
         run = DeviceRun(eng, N, T, p, initstates=init)
         d_in = device_forcing(torch, model_name, N, T, sy.SEED + 17 * rank)
         d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)

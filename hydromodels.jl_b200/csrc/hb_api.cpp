@@ -282,11 +282,12 @@ int nvrtc_compile(const std::string &src, const std::vector<std::string> &opts, 
 int stepper_smem_bytes(const hb_stepper_spec &s, int block, int stages) {
     auto up128 = [](int x) { return (x + 127) / 128 * 128; };
     int warps = block / 32;
+    const int npw = s.nodes_per_warp == 16 ? 16 : 32;
     // per-thread MLP path: parameters in the module's constant bank; tensor path: staged in shared memory + scratch
     int nn = s.nn_tensor ? up128(s.nn_words * 8) + warps * 1024 : 0;
     const int es = s.precision ? 4 : 8;
-    int in_b = up128(stages * 32 * s.n_inputs * es);
-    int out_b = s.output_mode == HB_OUT_ROWS ? up128(2 * 32 * s.n_rows * es) : 0;
+    int in_b = up128(stages * npw * s.n_inputs * es);
+    int out_b = s.output_mode == HB_OUT_ROWS ? up128(2 * npw * s.n_rows * es) : 0;
     return nn + warps * (in_b + out_b) + warps * stages * 8;
 }
 
@@ -379,7 +380,8 @@ int launch_stepper(hb_model_s *m, const hb_run_desc *d, cudaStream_t stream) {
     for (int j = 0; j < s.n_params; ++j) tmp[j] = d->param_mode[j];
     put(tmp.data(), 4 * np);
     void *params[1] = {buf};
-    unsigned grid = (unsigned)((N + m->block - 1) / m->block);
+    const int64_t nodes_per_block = (int64_t)(m->block / 32) * (s.nodes_per_warp == 16 ? 16 : 32);
+    unsigned grid = (unsigned)((N + nodes_per_block - 1) / nodes_per_block);
     if (T == 0 && s.output_mode == HB_OUT_ROWS && !d->final_states) return HB_OK;
     if (s.nn_words > 0)   // MLP parameters -> constant bank (stream-ordered before the launch)
         HB_DRV(g_drv.MemcpyDtoDAsync(m->nn_const, (CUdeviceptr)(uintptr_t)d->nn_params, (size_t)s.nn_words * 8, (CUstream)stream));
@@ -477,6 +479,9 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
     if (spec->output_mode != HB_OUT_ROWS && spec->output_mode != HB_OUT_OBJECTIVE) return fail(HB_ERR_INVALID, "bad output_mode");
     if (spec->precision != 0 && spec->precision != 1) return fail(HB_ERR_INVALID, "precision must be 0 (Float64) or 1 (Float32)");
     if (spec->precision && spec->nn_tensor) return fail(HB_ERR_INVALID, "the FP64 tensor path is not available in Float32 mode");
+    if (spec->nodes_per_warp != 0 && spec->nodes_per_warp != 32 && spec->nodes_per_warp != 16)
+        return fail(HB_ERR_INVALID, "nodes_per_warp must be 0, 16 or 32");
+    if (spec->nodes_per_warp == 16 && !spec->nn_tensor) return fail(HB_ERR_INVALID, "nodes_per_warp = 16 is meant for tensor-path MLP bodies");
     hb_model_s *m = new hb_model_s();
     m->spec = *spec;
     m->block = spec->block_threads > 0 ? spec->block_threads : 128;
@@ -509,10 +514,10 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
     snprintf(defs, sizeof defs,
              "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_UHW_TOTAL %d\n"
              "#define HB_UHH_TOTAL %d\n#define HB_NN_WORDS %d\n#define HB_MODE %d\n#define HB_METRIC %d\n#define HB_SHARED_FORCING %d\n"
-             "#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n#define HB_NN_MMA %d\n#define HB_F32 %d\n",
+             "#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n#define HB_NN_MMA %d\n#define HB_F32 %d\n#define HB_NPW %d\n",
              spec->n_inputs, spec->output_mode == HB_OUT_ROWS ? spec->n_rows : 0, spec->n_states, spec->n_params, m->uhw_total,
              m->uhh_total, spec->nn_words, spec->output_mode, spec->metric, spec->shared_forcing ? 1 : 0, m->block, stages, minblocks,
-             spec->nn_tensor ? 1 : 0, spec->precision ? 1 : 0);
+             spec->nn_tensor ? 1 : 0, spec->precision ? 1 : 0, spec->nodes_per_warp == 16 ? 16 : 32);
     std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";   // body may append to DEFINES (e.g. HB_NC)
     if (const char *x = getenv("HB_EXTRA_DEFINES")) full_body = std::string("//@@HB:DEFINES\n") + x + "\n" + full_body;   // tuning experiments
     m->source = splice(kStepperTemplate, full_body.c_str());

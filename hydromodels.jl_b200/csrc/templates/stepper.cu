@@ -51,6 +51,10 @@ typedef float real;
 #else
 typedef double real;
 #endif
+#ifndef HB_NPW
+#define HB_NPW 32     // nodes per warp.  16: lanes l and l+16 carry the SAME node — the scalar code runs identically in both halves
+#endif                //   (free under SIMT) while the warp-cooperative tensor-core MLPs spread half as many basins over the 32 lanes:
+                      //   twice the warps for a small, MLP-heavy (latency-bound) run such as M50 on 50 k basins
 #define HB_OBUF 2
 #define HB_WARPS (HB_BLOCK / 32)
 #define HB_ARR(n) ((n) > 0 ? (n) : 1)
@@ -143,10 +147,11 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     extern __shared__ __align__(128) unsigned char hb_smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const i64 n = (i64)blockIdx.x * HB_BLOCK + threadIdx.x;
-    const i64 n0w = n - lane;
+    const int ln = lane % HB_NPW;                       // this lane's node within the warp (HB_NPW == 16: lane and lane+16 share it)
+    const i64 n0w = ((i64)blockIdx.x * HB_WARPS + warp) * HB_NPW;
+    const i64 n = n0w + ln;
     const bool valid = n < a.N;
-    const bool full_warp = (n0w + 32) <= a.N;
+    const bool full_warp = (n0w + HB_NPW) <= a.N;
     hb_math_init();   // exp table -> shared memory (block barrier inside)
 
     // shared-memory carve-up: [MLP params + per-warp MMA scratch][per-warp forcing ring][per-warp result tiles][mbarriers]
@@ -155,9 +160,9 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
 #else
     constexpr int kNNBytes = 0;   // per-thread MLP path: parameters live in the constant bank (hb_nn_const)
 #endif
-    constexpr int kInStage = 32 * HB_V * (int)sizeof(real);                      // bytes of one warp-step of forcing
+    constexpr int kInStage = HB_NPW * HB_V * (int)sizeof(real);                      // bytes of one warp-step of forcing
     constexpr int kInBytes = ((HB_STAGES * kInStage + 127) / 128) * 128;
-    constexpr int kOutTile = 32 * HB_R * (int)sizeof(real);                      // bytes of one warp-step of results
+    constexpr int kOutTile = HB_NPW * HB_R * (int)sizeof(real);                      // bytes of one warp-step of results
     constexpr int kOutBytes = ((HB_OBUF * kOutTile + 127) / 128) * 128;
     real *sNN = reinterpret_cast<real *>(hb_smem);   // tensor path only (Float64): staged MLP parameters
     double *hb_scr = reinterpret_cast<double *>(hb_smem + ((HB_NN_WORDS * 8 + 127) / 128) * 128) + warp * 128;   // 1 KB per warp
@@ -234,7 +239,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
             for (int s = 0; s < HB_STAGES; ++s) {
                 if (s < T) {
                     hb_mbar_expect_tx(hb_smem_u32(&bars[s]), kInStage);
-                    hb_bulk_g2s(hb_smem_u32(sIn + s * 32 * HB_V), in_warp + (i64)s * in_step, kInStage, hb_smem_u32(&bars[s]));
+                    hb_bulk_g2s(hb_smem_u32(sIn + s * HB_NPW * HB_V), in_warp + (i64)s * in_step, kInStage, hb_smem_u32(&bars[s]));
                 }
             }
         }
@@ -257,7 +262,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
         real hb_x[HB_ARR(HB_V)];
         if (tma_in) {
             hb_mbar_wait(hb_smem_u32(&bars[slot]), parity);
-            const real *sx = sIn + slot * 32 * HB_V + lane * HB_V;
+            const real *sx = sIn + slot * HB_NPW * HB_V + ln * HB_V;
 #pragma unroll
             for (int v = 0; v < HB_V; ++v) hb_x[v] = sx[v];
             // cross-proxy write-after-read: the lanes' generic-proxy loads of the slot must be ordered before the
@@ -267,7 +272,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
             __syncwarp();   // every lane has consumed the slot -> refill it HB_STAGES steps ahead
             if (lane == 0 && t + HB_STAGES < T) {
                 hb_mbar_expect_tx(hb_smem_u32(&bars[slot]), kInStage);
-                hb_bulk_g2s(hb_smem_u32(sIn + slot * 32 * HB_V), pf_ptr, kInStage, hb_smem_u32(&bars[slot]));
+                hb_bulk_g2s(hb_smem_u32(sIn + slot * HB_NPW * HB_V), pf_ptr, kInStage, hb_smem_u32(&bars[slot]));
             }
             pf_ptr += in_step;
             if (++slot == HB_STAGES) { slot = 0; parity ^= 1; }
@@ -287,13 +292,13 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
         // ---- results of this step -------------------------------------------------------------
 #if HB_MODE == 0 && HB_R > 0
         if (tma_out) {
-            real *so = sOut + ob * 32 * HB_R;
+            real *so = sOut + ob * HB_NPW * HB_R;
             if (t >= HB_OBUF) {   // the bulk store that last read this tile must have drained it
                 if (lane == 0) hb_bulk_wait_read<HB_OBUF - 1>();
                 __syncwarp();
             }
 #pragma unroll
-            for (int r = 0; r < HB_R; ++r) so[lane * HB_R + r] = hb_out[r];
+            for (int r = 0; r < HB_R; ++r) so[ln * HB_R + r] = hb_out[r];   // HB_NPW == 16: both copies of a node store the same values
             hb_fence_proxy_async();   // generic-proxy writes -> visible to the async proxy
             __syncwarp();
             if (lane == 0) {

@@ -42,7 +42,7 @@ class StepperSpec(C.Structure):
                 ("n_params", C.c_int32), ("n_uh", C.c_int32), ("uh_kmax", C.c_int32 * HB_MAX_UH),
                 ("nn_words", C.c_int32), ("output_mode", C.c_int32), ("metric", C.c_int32),
                 ("shared_forcing", C.c_int32), ("block_threads", C.c_int32), ("stages", C.c_int32),
-                ("max_registers", C.c_int32), ("precision", C.c_int32), ("nn_tensor", C.c_int32)]
+                ("max_registers", C.c_int32), ("precision", C.c_int32), ("nn_tensor", C.c_int32), ("nodes_per_warp", C.c_int32)]
 
 
 class RunDesc(C.Structure):
@@ -172,7 +172,7 @@ def init(device: int = 0):
 # ---------------------------------------------------------------------------------------------------
 class CompiledStepper:
     def __init__(self, program: StepperProgram, *, metric: int = 0, shared_forcing: bool = False,
-                 block_threads: int = 0, stages: int = 0, max_registers: int = 0):
+                 block_threads: int = 0, stages: int = 0, max_registers: int = 0, nodes_per_warp: int = 0):
         self.program = program
         spec = StepperSpec()
         spec.struct_size = C.sizeof(StepperSpec)
@@ -193,6 +193,7 @@ class CompiledStepper:
         spec.stages = stages
         spec.max_registers = max_registers
         spec.nn_tensor = 1 if getattr(program, "nn_tensor", False) else 0
+        spec.nodes_per_warp = nodes_per_warp if spec.nn_tensor else 0
         spec.precision = 1 if getattr(program, "precision", "f64") == "f32" else 0
         self.spec = spec
         h = C.c_void_p()
@@ -356,6 +357,7 @@ class B200Model:
         # [buckets…, HydroRoute] on a dense row-major D8 grid: "wave" = single-pass kernel whose warps exchange
         # outflows through L2 (templates/gridwave.cu, default); "tile" = tile + halo kernel (templates/grid.cu);
         # "generic" = stepper over all T, then one routing launch per step (any node list / graph)
+        self.nodes_per_warp = 0           # tensor-path MLP bodies: 0 = default (32), 16 = two lanes per node (stepper.cu HB_NPW)
         self.grid_kernel = "wave"
         self.grid_steps_per_launch = 16
         self.grid_panel_min_cols = 3072      # wave kernel: grids at least this wide run as column panels (parallel.PanelledGridRun)
@@ -400,8 +402,12 @@ class B200Model:
 
     # -- compile ------------------------------------------------------------------------------------
     def compiled(self, *, rows=None, objective=False, metric=0, shared_forcing=False,
-                 uh_kmax: Sequence[int] = (), uh_on_device: bool = False) -> CompiledStepper:
-        key = (tuple(rows) if rows is not None else None, objective, metric, shared_forcing, tuple(uh_kmax), bool(uh_on_device))
+                 uh_kmax: Sequence[int] = (), uh_on_device: bool = False, n_nodes: int = 0) -> CompiledStepper:
+        # tensor-path MLP bodies: `nodes_per_warp = 16` doubles the warps of a small run (stepper.cu HB_NPW).  Measured on M50
+        # 50 k x 3650: 48.6 ms vs 46.1 ms at 32 — the kernel is FP64-pipe bound (math_pipe_throttle), not short of warps, and
+        # the duplicated scalar work costs more than the extra warps hide — so 32 stays the default and 16 is opt-in.
+        npw = self.nodes_per_warp or 32
+        key = (tuple(rows) if rows is not None else None, objective, metric, shared_forcing, tuple(uh_kmax), bool(uh_on_device), npw)
         if key not in self._cache:
             prog = lower_stepper(self._stepper_component(), rows=rows, objective=objective,
                                  uh_kmax=list(uh_kmax) if len(uh_kmax) else None, fast=self.fast,
@@ -411,7 +417,7 @@ class B200Model:
             maxreg = self.max_registers or (168 if prog.nn_words else 0)
             self._cache[key] = CompiledStepper(prog, metric=metric, shared_forcing=shared_forcing,
                                                block_threads=self.block_threads, stages=self.stages,
-                                               max_registers=maxreg)
+                                               max_registers=maxreg, nodes_per_warp=npw)
         self.last_kernel = self._cache[key]
         return self._cache[key]
 
@@ -596,13 +602,13 @@ class B200Model:
         _check_config(cfg, T)
         inp = input if input.flags.f_contiguous else np.asfortranarray(input)   # memory = [T][N][V]
         # first pass over the parameters to size the unit hydrographs (compile-time K_max)
-        prog0 = self.compiled(rows=rows).program if not self._has_uh() else None
+        prog0 = self.compiled(rows=rows, n_nodes=N).program if not self._has_uh() else None
         if prog0 is None:
             probe = lower_stepper(self._stepper_component(), rows=rows, fast=self.fast)
             _, _, _, _, _, kmax, _ = self.prepare(probe, params, N)
-            ck = self.compiled(rows=rows, uh_kmax=kmax)
+            ck = self.compiled(rows=rows, uh_kmax=kmax, n_nodes=N)
         else:
-            ck = self.compiled(rows=rows)
+            ck = self.compiled(rows=rows, n_nodes=N)
         prog = ck.program
         flat, p_off, p_mode, htypes, uhw, kmax, nn = self.prepare(prog, params, N)
         uhw_flat = np.ascontiguousarray(np.concatenate(uhw, axis=0)) if uhw else None
@@ -886,7 +892,7 @@ class DeviceRun:
         else:
             kmax = []
         self.ck = eng.compiled(rows=rows, objective=obj, metric=metric, shared_forcing=ensemble, uh_kmax=kmax,
-                               uh_on_device=uh_on_device)
+                               uh_on_device=uh_on_device, n_nodes=N)
         prog = self.ck.program
         flat, p_off, p_mode, htypes, uhw, kmax_host, nn = eng.prepare(prog, params, N, ensemble=ensemble, node_range=node_range)
         if uh_on_device and uhw:

@@ -761,27 +761,28 @@ def _mlp_helper_mma(idx: int, chain, offset: int, fast: bool) -> str:
     L = chain.layers
     args = ", ".join(f"const double x{i}" for i in range(chain.n_in))
     o = [f"__device__ __forceinline__ void hb_mlp_{idx}(const double* __restrict__ sW, double* __restrict__ scr, const int lane, {args}, double* __restrict__ y) {{",
-         "    const int q = lane >> 2, j = lane & 3;"]
+         "    const int q = lane >> 2, j = lane & 3;",
+         "    constexpr int HB_MT = HB_NPW / 8;     // M tiles of 8 basins (HB_NPW == 16: lanes 16..31 mirror lanes 0..15, only their tiles are skipped)"]
     for k in range(4):
         o.append(f"    scr[lane * 4 + {k}] = {'x%d' % k if k < chain.n_in else '0.0'};")
-    o += ["    __syncwarp();", "    double afr[4];", "#pragma unroll",
-          "    for (int mt = 0; mt < 4; ++mt) afr[mt] = scr[(mt * 8 + q) * 4 + j];", "    __syncwarp();"]
+    o += ["    __syncwarp();", "    double afr[HB_MT];", "#pragma unroll",
+          "    for (int mt = 0; mt < HB_MT; ++mt) afr[mt] = scr[(mt * 8 + q) * 4 + j];", "    __syncwarp();"]
     off = offset
     # layer 0: K = 4 (inputs zero-padded), one chunk
     l0 = L[0]
     nt0 = l0.n_out // 8
     bias = off + l0.n_out * l0.n_in
-    o.append(f"    double h0[4][{nt0}][2];")
+    o.append(f"    double h0[HB_MT][{nt0}][2];")
     o.append("#pragma unroll")
     o.append(f"    for (int nt = 0; nt < {nt0}; ++nt) {{")
     o.append(f"        const double b = (j < {l0.n_in}) ? sW[{off} + j * {l0.n_out} + nt * 8 + q] : 0.0;")
     o.append(f"        const double c0 = sW[{bias} + nt * 8 + 2 * j], c1 = sW[{bias} + nt * 8 + 2 * j + 1];")
     o.append("#pragma unroll")
-    o.append("        for (int mt = 0; mt < 4; ++mt) { h0[mt][nt][0] = c0; h0[mt][nt][1] = c1; hb_dmma(h0[mt][nt][0], h0[mt][nt][1], afr[mt], b); }")
+    o.append("        for (int mt = 0; mt < HB_MT; ++mt) { h0[mt][nt][0] = c0; h0[mt][nt][1] = c1; hb_dmma(h0[mt][nt][0], h0[mt][nt][1], afr[mt], b); }")
     o.append("    }")
     if l0.activation != "identity":
         o.append("#pragma unroll")
-        o.append(f"    for (int mt = 0; mt < 4; ++mt) for (int nt = 0; nt < {nt0}; ++nt) for (int e = 0; e < 2; ++e) h0[mt][nt][e] = {acts[l0.activation].format('h0[mt][nt][e]')};")
+        o.append(f"    for (int mt = 0; mt < HB_MT; ++mt) for (int nt = 0; nt < {nt0}; ++nt) for (int e = 0; e < 2; ++e) h0[mt][nt][e] = {acts[l0.activation].format('h0[mt][nt][e]')};")
     off += l0.n_params
     prev, prev_nt = "h0", nt0
     for li in range(1, len(L) - 1):
@@ -789,29 +790,29 @@ def _mlp_helper_mma(idx: int, chain, offset: int, fast: bool) -> str:
         ntl = l.n_out // 8
         cur = f"h{li}"
         bias = off + l.n_out * l.n_in
-        o.append(f"    double {cur}[4][{ntl}][2];")
+        o.append(f"    double {cur}[HB_MT][{ntl}][2];")
         o.append("#pragma unroll")
         o.append(f"    for (int nt = 0; nt < {ntl}; ++nt) {{")
         o.append(f"        const double c0 = sW[{bias} + nt * 8 + 2 * j], c1 = sW[{bias} + nt * 8 + 2 * j + 1];")
         o.append("#pragma unroll")
-        o.append(f"        for (int mt = 0; mt < 4; ++mt) {{ {cur}[mt][nt][0] = c0; {cur}[mt][nt][1] = c1; }}")
+        o.append(f"        for (int mt = 0; mt < HB_MT; ++mt) {{ {cur}[mt][nt][0] = c0; {cur}[mt][nt][1] = c1; }}")
         o.append("#pragma unroll")
         o.append(f"        for (int c = 0; c < {l.n_in // 4}; ++c) {{")
         o.append(f"            const double b = sW[{off} + ((c >> 1) * 8 + 2 * j + (c & 1)) * {l.n_out} + nt * 8 + q];")
         o.append("#pragma unroll")
-        o.append(f"            for (int mt = 0; mt < 4; ++mt) hb_dmma({cur}[mt][nt][0], {cur}[mt][nt][1], {prev}[mt][c >> 1][c & 1], b);")
+        o.append(f"            for (int mt = 0; mt < HB_MT; ++mt) hb_dmma({cur}[mt][nt][0], {cur}[mt][nt][1], {prev}[mt][c >> 1][c & 1], b);")
         o.append("        }")
         o.append("    }")
         if l.activation != "identity":
             o.append("#pragma unroll")
-            o.append(f"    for (int mt = 0; mt < 4; ++mt) for (int nt = 0; nt < {ntl}; ++nt) for (int e = 0; e < 2; ++e) {cur}[mt][nt][e] = {acts[l.activation].format(cur + '[mt][nt][e]')};")
+            o.append(f"    for (int mt = 0; mt < HB_MT; ++mt) for (int nt = 0; nt < {ntl}; ++nt) for (int e = 0; e < 2; ++e) {cur}[mt][nt][e] = {acts[l.activation].format(cur + '[mt][nt][e]')};")
         off += l.n_params
         prev, prev_nt = cur, ntl
     # last layer: H -> 1, per-lane partial dot + quad reduction
     ll = L[-1]
-    o.append("    double yv[4];")
+    o.append("    double yv[HB_MT];")
     o.append("#pragma unroll")
-    o.append("    for (int mt = 0; mt < 4; ++mt) {")
+    o.append("    for (int mt = 0; mt < HB_MT; ++mt) {")
     o.append("        double part = 0.0;")
     o.append("#pragma unroll")
     o.append(f"        for (int nt = 0; nt < {prev_nt}; ++nt) for (int e = 0; e < 2; ++e) part = fma(sW[{off} + nt * 8 + 2 * j + e], {prev}[mt][nt][e], part);")
@@ -822,9 +823,9 @@ def _mlp_helper_mma(idx: int, chain, offset: int, fast: bool) -> str:
     o.append("    }")
     o.append("    if (j == 0) {")
     o.append("#pragma unroll")
-    o.append("        for (int mt = 0; mt < 4; ++mt) scr[mt * 8 + q] = yv[mt];")
+    o.append("        for (int mt = 0; mt < HB_MT; ++mt) scr[mt * 8 + q] = yv[mt];")
     o.append("    }")
-    o += ["    __syncwarp();", "    y[0] = scr[lane];", "    __syncwarp();", "}"]
+    o += ["    __syncwarp();", "    y[0] = scr[lane % HB_NPW];", "    __syncwarp();", "}"]
     return "\n".join(o)
 
 

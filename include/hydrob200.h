@@ -91,6 +91,8 @@ typedef struct {
                                     arrays and the body computes in float; everything else stays double */
     int32_t nn_tensor;           /* 1: the body contracts its dense layers with FP64 MMA (DMMA) fragments: MLP
                                     parameters are staged in shared memory + 1 KB scratch per warp */
+    int32_t nodes_per_warp;      /* 0 / 32: one node per lane.  16: lanes l and l+16 carry the same node, so the warp-cooperative
+                                    MLPs spread 16 basins over 32 lanes and a small, MLP-heavy run gets twice the warps */
 } hb_stepper_spec;
 
 /* One forward run.  Pointers are HOST pointers for hb_run and DEVICE pointers for

@@ -516,3 +516,23 @@ def test_wide_grid_takes_the_panelled_path_through_the_functor():
     assert np.array_equal(got, ref)
     run = par.PanelledGridRun(eng, R, Cc, T, p, initstates=init, panels=3)
     assert run.K == 3
+
+
+@pytest.mark.parametrize("N,npw", [(64, 16), (37, 16), (16, 16), (1000, 16), (64, 32)])
+def test_m50_with_16_nodes_per_warp_is_bit_identical(N, npw):
+    """`nodes_per_warp = 16` (stepper.cu HB_NPW): lanes l and l+16 carry the same basin and the tensor-core MLPs spread 16 basins
+    over the warp — twice the warps for small MLP-heavy runs.  Same arithmetic in the same order: bit-identical to 32 nodes per
+    warp, aligned, ragged and single-warp sizes; and within tolerance of the oracle."""
+    T = 45
+    model, inp, p, init = case("m50", N, T)
+    e32 = hm.B200Model(model)
+    e32.nodes_per_warp = 32
+    ref = e32(inp, p, initstates=init)
+    e = hm.B200Model(model)
+    e.nodes_per_warp = npw
+    got = e(inp, p, initstates=init)
+    assert e.last_kernel.spec.nodes_per_warp == npw and e.last_kernel.spec.nn_tensor == 1
+    assert np.array_equal(got, ref)
+    assert_parity(got, ho.run_model(model, inp, p, initstates=init))
+    auto = hm.B200Model(model)
+    assert np.array_equal(auto(inp, p, initstates=init), ref) and auto.last_kernel.spec.nodes_per_warp == 32      # the default
