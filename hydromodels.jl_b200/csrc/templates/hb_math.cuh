@@ -139,14 +139,13 @@ HB_DEV double hb_exp(double x) {
     return (p * s1) * s2;
 }
 
-// 1/x for finite normal x of either sign: MUFU.RCP64H seed (>= 20 bits) + 2 Newton steps (80 bits).
+// 1/x for finite normal x of either sign: MUFU.RCP64H seed (>= 20 bits) + ONE cubic step r (1 + e + e^2), e = 1 - x r:
+// residual e^3 <= 2^-60, three FP64 operations instead of the four of two Newton steps.
 HB_DEV double hb_rcp(double x) {
-    double r = hb_rcp_seed(x);
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double r = hb_rcp_seed(x);
+    const double e = fma(-x, r, 1.0);
+    const double p = fma(e, e, e);
+    return fma(r, p, r);
 }
 HB_DEV double hb_rcp_pos(double x) { return hb_rcp(x); }
 
@@ -154,8 +153,28 @@ HB_DEV double hb_rcp_pos(double x) { return hb_rcp(x); }
 // z = -10x saturates at +/-700: there the logistic is 1 to the last bit / < 1e-304 (the
 // reference's tanh form returns exactly 0 from x ~ -3.8 on; both are 0 within 1e-16 absolute).
 HB_DEV double hb_step(double x) { return hb_rcp(1.0 + hb_exp_narrow(hb_clamp_abs(-10.0 * x, HB_HI_700))); }
-// tanh(x) = 1 - 2/(1+exp(2x)), same saturated logistic (absolute error < 4.5e-16).
-HB_DEV double hb_tanh(double x) { return fma(-2.0, hb_rcp(1.0 + hb_exp_narrow(hb_clamp_abs(2.0 * x, HB_HI_700))), 1.0); }
+// tanh(x) = 1 - 2/(1+exp(2x)), same saturated logistic (absolute error < 4.5e-16).  The factor 2 is folded into the
+// argument reduction (t = round(x * 128/ln2), r = x - t ln2/128, exp(2x) = 2^(t/64) e^(2r) with the polynomial in r
+// carrying the powers of two), so a tanh costs 15 FP64 operations: M50 evaluates 64 of them per basin-step and is bound
+// by the FP64 pipe.
+#define HB_HI_350 0x4075e000   // high word of 350.0
+HB_DEV double hb_tanh(double x) {
+    const double MAGIC = 6755399441055744.0;
+    const double xc = hb_clamp_abs(x, HB_HI_350);
+    double t = fma(xc, 184.66496523378732, MAGIC);          // x * 128/ln2
+    const int ti = hb_double2loint(t);
+    t -= MAGIC;
+    double r = fma(t, -0.005415212333900854, xc);            // ln2/128 high part (half of the ln2/64 split: exact)
+    r = fma(t, -1.42237187383136425e-11, r);                 // ln2/128 low part
+    double q = fma(r, 2.66666666666666666667e-01, 6.66666666666666666667e-01);   // e^(2r) = sum (2r)^n / n!
+    q = fma(q, r, 1.33333333333333333333e+00);
+    q = fma(q, r, 2.0);
+    q = fma(q, r, 2.0);
+    q = fma(q, r, 1.0);
+    const double m = hb_exp2t[ti & 63] * q;
+    const double e2x = hb_hiloint2double(hb_double2hiint(m) + ((ti >> 6) << 20), hb_double2loint(m));
+    return fma(-2.0, hb_rcp(1.0 + e2x), 1.0);
+}
 // min / max as one compare + select (the IEEE-NaN-aware fmin/fmax cost twice as much).  NaN
 // handling differs from Julia's min/max (which propagate NaN) exactly as fmin/fmax would.
 HB_DEV double hb_min(double a, double b) { return a < b ? a : b; }
