@@ -152,10 +152,28 @@ HB_DEV double hb_rcp_pos(double x) { return hb_rcp(x); }
 // step_func(x) = (tanh(5x)+1)/2 (/root/reference/src/HydroModels.jl:204) == 1/(1+exp(-10x)).
 // z = -10x saturates at +/-700: there the logistic is 1 to the last bit / < 1e-304 (the
 // reference's tanh form returns exactly 0 from x ~ -3.8 on; both are 0 within 1e-16 absolute).
-HB_DEV double hb_step(double x) { return hb_rcp(1.0 + hb_exp_narrow(hb_clamp_abs(-10.0 * x, HB_HI_700))); }
+HB_DEV double hb_step(double x) {
+    int k;
+    const double MAGIC = 6755399441055744.0;
+    const double z = hb_clamp_abs(-10.0 * x, HB_HI_700);
+    double t = fma(z, 92.33248261689366, MAGIC);
+    const int ti = hb_double2loint(t);
+    t -= MAGIC;
+    double r = fma(t, -0.010830424667801708, z);
+    r = fma(t, -2.8447437476627285e-11, r);
+    k = ti >> 6;
+    double q = fma(r, 8.33333333333333333333e-03, 4.16666666666666666667e-02);
+    q = fma(q, r, 1.66666666666666666667e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    const double tj = hb_exp2t[ti & 63];
+    const double tk = hb_hiloint2double(hb_double2hiint(tj) + (k << 20), hb_double2loint(tj));   // 2^k T_j, a normal double for |z| <= 700
+    return hb_rcp(fma(tk, q, 1.0));                         // 1 + exp(z) in one fma
+}
 // tanh(x) = 1 - 2/(1+exp(2x)), same saturated logistic (absolute error < 4.5e-16).  The factor 2 is folded into the
 // argument reduction (t = round(x * 128/ln2), r = x - t ln2/128, exp(2x) = 2^(t/64) e^(2r) with the polynomial in r
-// carrying the powers of two), so a tanh costs 15 FP64 operations: M50 evaluates 64 of them per basin-step and is bound
+// carrying the powers of two) and the table product is fused with the `1 +`, so a tanh costs 14 FP64 operations: M50 evaluates 64 of them per basin-step and is bound
 // by the FP64 pipe.
 #define HB_HI_350 0x4075e000   // high word of 350.0
 HB_DEV double hb_tanh(double x) {
@@ -171,9 +189,11 @@ HB_DEV double hb_tanh(double x) {
     q = fma(q, r, 2.0);
     q = fma(q, r, 2.0);
     q = fma(q, r, 1.0);
-    const double m = hb_exp2t[ti & 63] * q;
-    const double e2x = hb_hiloint2double(hb_double2hiint(m) + ((ti >> 6) << 20), hb_double2loint(m));
-    return fma(-2.0, hb_rcp(1.0 + e2x), 1.0);
+    // 1 + exp(2x) = 1 + (2^k T_j) q in ONE fma: 2^k goes onto the table entry by an integer add to its exponent field
+    // (|2x| <= 700: the scaled entry stays a normal double)
+    const double tj = hb_exp2t[ti & 63];
+    const double tk = hb_hiloint2double(hb_double2hiint(tj) + ((ti >> 6) << 20), hb_double2loint(tj));
+    return fma(-2.0, hb_rcp(fma(tk, q, 1.0)), 1.0);
 }
 // min / max as one compare + select (the IEEE-NaN-aware fmin/fmax cost twice as much).  NaN
 // handling differs from Julia's min/max (which propagate NaN) exactly as fmin/fmax would.
