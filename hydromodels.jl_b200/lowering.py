@@ -618,7 +618,7 @@ def _expr_with(v: Val, a: List[str], fast: bool) -> str:
     if op == "div": return f"{a[0]} / {a[1]}"
     if op == "rcp": return f"1.0 / {a[0]}"
     if op == "neg": return f"-{a[0]}"
-    if op == "pow": return f"pow({a[0]}, {a[1]})"
+    if op == "pow": return f"hb_pow({a[0]}, {a[1]})" if fast else f"pow({a[0]}, {a[1]})"
     if op == "exp": return f"hb_exp({a[0]})" if fast else f"exp({a[0]})"
     if op == "log": return f"log({a[0]})"
     if op == "sqrt": return f"sqrt({a[0]})"
