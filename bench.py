@@ -587,6 +587,9 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 10.0:     # nvidia-smi needs seconds to enumerate an 8-GPU box
+        time.sleep(0.05)
     time.sleep(0.25)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
