@@ -536,3 +536,13 @@ def test_m50_with_16_nodes_per_warp_is_bit_identical(N, npw):
     assert_parity(got, ho.run_model(model, inp, p, initstates=init))
     auto = hm.B200Model(model)
     assert np.array_equal(auto(inp, p, initstates=init), ref) and auto.last_kernel.spec.nodes_per_warp == 32      # the default
+
+
+def test_wave_grid_fuzz_against_the_generic_path():
+    """20 random grids (1-column, 1-row, narrower than a warp, ragged, odd T, T_c = 1 ...) through the wave kernel and, where
+    they fit, through column panels on one GPU: every value bit-identical to the generic path (`tools/fuzz_wave.py` runs more)."""
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "tools", "fuzz_wave.py"), "20", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "FUZZ PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
