@@ -54,37 +54,85 @@ HB_DEV int hb_double2hiint(double x) {
 #endif
 }
 
-// exp(x) = 2^k * 2^(j/64) * exp(r):  t = round(x * 64/ln2), j = t mod 64, k = t div 64, r = x - t*ln2/64,
-// |r| <= ln2/128, exp(r) by its degree-5 Taylor polynomial (truncation 3.5e-17 relative).  The 64-entry
-// table lives in shared memory (lane-dependent index); 10 FP64-pipe instructions per exp instead of the
-// 16 of a table-free degree-11 kernel — the FP64 pipe and the board's power cap are what bound the
+// exp(x) = 2^k * 2^(j/256) * exp(r):  t = round(x * 256/ln2), j = t mod 256, k = t div 256, r = x - t*ln2/256,
+// |r| <= ln2/512, exp(r) by its degree-4 Taylor polynomial (truncation 3.8e-17 relative).  The 256-entry table (2 KB) lives in
+// shared memory (lane-dependent index); 9 FP64-pipe instructions per exp instead of the 16 of a table-free degree-11 kernel
+// (a 64-entry table needs degree 5: one more) — the FP64 pipe and the board's power cap are what bound the
 // transcendental-heavy bodies (ExpHydro: 6 exp-class evaluations per step, M50: 64 tanh per step).
 #define HB_EXP2_TABLE \
-    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, \
-    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199, \
-    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418, \
-    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812, \
-    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687, \
-    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783, \
-    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303, \
-    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112, \
-    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647, \
-    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384, \
-    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267, \
-    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364, \
-    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062, \
-    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989, \
-    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656, \
-    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951
+    1.0, 1.0027112750502025, 1.0054299011128027, 1.0081558981184175, \
+    1.0108892860517005, 1.0136300849514894, 1.016378314910953, 1.019133996077738, \
+    1.0218971486541166, 1.0246677928971357, 1.0274459491187637, 1.030231637686041, \
+    1.0330248790212284, 1.0358256936019572, 1.0386341019613787, 1.041450124688316, \
+    1.0442737824274138, 1.0471050958792898, 1.0499440858006872, 1.0527907730046264, \
+    1.0556451783605572, 1.0585073227945128, 1.061377227289262, 1.0642549128844645, \
+    1.0671404006768237, 1.0700337118202419, 1.0729348675259756, 1.075843889062791, \
+    1.0787607977571199, 1.0816856149932152, 1.0846183622133092, 1.0875590609177697, \
+    1.0905077326652577, 1.0934643990728858, 1.0964290818163769, 1.099401802630222, \
+    1.102382583307841, 1.1053714457017412, 1.1083684117236787, 1.1113735033448175, \
+    1.1143867425958924, 1.1174081515673693, 1.1204377524096067, 1.12347556733302, \
+    1.1265216186082418, 1.129575928566288, 1.1326385195987192, 1.1357094141578055, \
+    1.1387886347566916, 1.1418762039695616, 1.1449721444318042, 1.148076478840179, \
+    1.1511892299529827, 1.154310420590216, 1.1574400736337511, 1.1605782120274988, \
+    1.1637248587775775, 1.1668800369524817, 1.1700437696832502, 1.1732160801636373, \
+    1.1763969916502812, 1.1795865274628758, 1.182784710984341, 1.1859915656609938, \
+    1.189207115002721, 1.1924313825831512, 1.1956643920398273, 1.1989061670743806, \
+    1.202156731452703, 1.2054161090051239, 1.2086843236265816, 1.2119613992768012, \
+    1.215247359980469, 1.2185422298274085, 1.2218460329727576, 1.2251587936371455, \
+    1.22848053610687, 1.2318112847340759, 1.2351510639369334, 1.2384998981998165, \
+    1.241857812073484, 1.245224830175258, 1.2486009771892048, 1.2519862778663162, \
+    1.255380757024691, 1.2587844395497165, 1.2621973503942507, 1.2656195145788063, \
+    1.2690509571917332, 1.2724917033894028, 1.275941778396392, 1.2794012075056693, \
+    1.2828700160787783, 1.2863482295460256, 1.2898358734066657, 1.2933329732290895, \
+    1.2968395546510096, 1.3003556433796506, 1.3038812651919358, 1.3074164459346773, \
+    1.3109612115247644, 1.3145155879493546, 1.318079601266064, 1.3216532776031575, \
+    1.3252366431597413, 1.3288297242059544, 1.3324325470831615, 1.3360451382041458, \
+    1.339667524053303, 1.3432997311868353, 1.3469417862329458, 1.3505937158920345, \
+    1.3542555469368927, 1.3579273062129011, 1.3616090206382248, 1.365300717204012, \
+    1.3690024229745905, 1.3727141650876684, 1.3764359707545302, 1.380167867260238, \
+    1.383909881963832, 1.387662042298529, 1.3914243757719262, 1.3951969099662003, \
+    1.3989796725383112, 1.4027726912202048, 1.4065759938190154, 1.4103896082172707, \
+    1.4142135623730951, 1.4180478843204152, 1.4218926021691656, 1.4257477441054942, \
+    1.42961333839197, 1.433489413367789, 1.4373759974489824, 1.4412731191286257, \
+    1.4451808069770467, 1.449099089642035, 1.4530279958490526, 1.4569675544014438, \
+    1.460917794180647, 1.4648787441464057, 1.4688504333369818, 1.4728328908693675, \
+    1.4768261459394993, 1.4808302278224719, 1.4848451658727524, 1.488870989524397, \
+    1.4929077282912648, 1.4969554117672355, 1.5010140696264256, 1.5050837316234065, \
+    1.5091644275934228, 1.5132561874526098, 1.5173590411982147, 1.5214730189088146, \
+    1.5255981507445384, 1.529734466947287, 1.533881997840956, 1.5380407738316568, \
+    1.5422108254079407, 1.5463921831410214, 1.550584877685, 1.5547889397770887, \
+    1.559004400237837, 1.5632312899713576, 1.567469639965553, 1.5717194812923414, \
+    1.5759808451078865, 1.5802537626528246, 1.5845382652524937, 1.588834384317164, \
+    1.593142151342267, 1.597461597908627, 1.6017927556826934, 1.606135656416771, \
+    1.6104903319492543, 1.6148568142048607, 1.6192351351948637, 1.6236253270173289, \
+    1.6280274218573478, 1.632441451987275, 1.6368674497669644, 1.6413054476440063, \
+    1.645755478153965, 1.6502175739206177, 1.6546917676561943, 1.6591780921616162, \
+    1.6636765803267364, 1.6681872651305825, 1.6727101796415966, 1.6772453570178785, \
+    1.681792830507429, 1.6863526334483934, 1.6909247992693053, 1.6955093614893326, \
+    1.7001063537185235, 1.7047158096580513, 1.709337763100463, 1.713972247929926, \
+    1.718619298122478, 1.723278947746274, 1.7279512309618377, 1.732636182022311, \
+    1.7373338352737062, 1.7420442251551564, 1.746767386199169, 1.7515033530318782, \
+    1.7562521603732995, 1.761013843037584, 1.7657884359332727, 1.7705759740635547, \
+    1.7753764925265212, 1.7801900265154245, 1.785016611318935, 1.789856282321401, \
+    1.7947090750031072, 1.7995750249405351, 1.804454167806624, 1.809346539371032, \
+    1.8142521755003989, 1.8191711121586085, 1.8241033854070534, 1.8290490314048973, \
+    1.8340080864093424, 1.8389805867758937, 1.843966568958626, 1.8489660695104508, \
+    1.8539791250833855, 1.8590057724288205, 1.864046048397789, 1.8690999899412386, \
+    1.8741676341103, 1.8792490180565602, 1.8843441790323345, 1.8894531543909392, \
+    1.8945759815869656, 1.8997126981765553, 1.9048633418176741, 1.9100279502703899, \
+    1.9152065613971474, 1.9203992131630474, 1.925605943636125, 1.930826790987627, \
+    1.9360617934922943, 1.9413109895286405, 1.9465744175792332, 1.9518521162309783, \
+    1.9571441241754002, 1.9624504802089273, 1.9677712232331759, 1.9731063922552343, \
+    1.978456026387951, 1.9838201648502194, 1.9891988469672663, 1.9945921121709402
 #ifdef HB_HOST_TEST
-static const double hb_exp2t[64] = {HB_EXP2_TABLE};
+static const double hb_exp2t[256] = {HB_EXP2_TABLE};
 static inline void hb_math_init() {}
 #else
-__constant__ const double HB_EXP2T_SRC[64] = {HB_EXP2_TABLE};
-__shared__ double hb_exp2t[64];
+__constant__ const double HB_EXP2T_SRC[256] = {HB_EXP2_TABLE};
+__shared__ double hb_exp2t[256];
 // every thread of the block calls this once at kernel entry (contains a block barrier)
 __device__ __forceinline__ void hb_math_init() {
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) hb_exp2t[i] = HB_EXP2T_SRC[i];   // any block size
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hb_exp2t[i] = HB_EXP2T_SRC[i];   // any block size
     __syncthreads();
 }
 #endif
@@ -103,21 +151,20 @@ HB_DEV double hb_clamp_abs(double x, int bound_hi) {
 #define HB_HI_700 0x4085e000   // high word of 700.0
 #define HB_HI_746 0x40875000   // high word of 746.0
 
-// m = 2^(j/64) * exp(r) in [1, 2), k such that exp(x) = m * 2^k
+// m = 2^(j/256) * exp(r) in [1, 2), k such that exp(x) = m * 2^k
 HB_DEV double hb_exp_reduce(double x, int &k) {
     const double MAGIC = 6755399441055744.0;               // 1.5 * 2^52: round-to-nearest-integer trick
-    double t = fma(x, 92.33248261689366, MAGIC);            // x * 64/ln2
+    double t = fma(x, 369.32993046757463, MAGIC);           // x * 256/ln2
     const int ti = hb_double2loint(t);
     t -= MAGIC;
-    double r = fma(t, -0.010830424667801708, x);            // ln2/64 high part (24 trailing zero bits: t*hi exact)
-    r = fma(t, -2.8447437476627285e-11, r);                 // ln2/64 low part
-    k = ti >> 6;
-    double q = fma(r, 8.33333333333333333333e-03, 4.16666666666666666667e-02);
-    q = fma(q, r, 1.66666666666666666667e-01);
+    double r = fma(t, -0.002707606166950427, x);            // ln2/256 high part (a quarter of the ln2/64 split: t*hi exact)
+    r = fma(t, -7.111859369156821e-12, r);                  // ln2/256 low part
+    k = ti >> 8;
+    double q = fma(r, 4.16666666666666666667e-02, 1.66666666666666666667e-01);   // |r| <= ln2/512: r^5/120 < 3.8e-17
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     q = fma(q, r, 1.0);                                      // exp(r)
-    return hb_exp2t[ti & 63] * q;
+    return hb_exp2t[ti & 255] * q;
 }
 
 // exp(x) for |x| <= ~700: the result is a normal double, so 2^k is applied by adding k to the
@@ -156,43 +203,41 @@ HB_DEV double hb_step(double x) {
     int k;
     const double MAGIC = 6755399441055744.0;
     const double z = hb_clamp_abs(-10.0 * x, HB_HI_700);
-    double t = fma(z, 92.33248261689366, MAGIC);
+    double t = fma(z, 369.32993046757463, MAGIC);
     const int ti = hb_double2loint(t);
     t -= MAGIC;
-    double r = fma(t, -0.010830424667801708, z);
-    r = fma(t, -2.8447437476627285e-11, r);
-    k = ti >> 6;
-    double q = fma(r, 8.33333333333333333333e-03, 4.16666666666666666667e-02);
-    q = fma(q, r, 1.66666666666666666667e-01);
+    double r = fma(t, -0.002707606166950427, z);
+    r = fma(t, -7.111859369156821e-12, r);
+    k = ti >> 8;
+    double q = fma(r, 4.16666666666666666667e-02, 1.66666666666666666667e-01);
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     q = fma(q, r, 1.0);
-    const double tj = hb_exp2t[ti & 63];
+    const double tj = hb_exp2t[ti & 255];
     const double tk = hb_hiloint2double(hb_double2hiint(tj) + (k << 20), hb_double2loint(tj));   // 2^k T_j, a normal double for |z| <= 700
     return hb_rcp(fma(tk, q, 1.0));                         // 1 + exp(z) in one fma
 }
 // tanh(x) = 1 - 2/(1+exp(2x)), same saturated logistic (absolute error < 4.5e-16).  The factor 2 is folded into the
-// argument reduction (t = round(x * 128/ln2), r = x - t ln2/128, exp(2x) = 2^(t/64) e^(2r) with the polynomial in r
-// carrying the powers of two) and the table product is fused with the `1 +`, so a tanh costs 14 FP64 operations: M50 evaluates 64 of them per basin-step and is bound
+// argument reduction (t = round(x * 512/ln2), r = x - t ln2/512, exp(2x) = 2^(t/256) e^(2r) with the polynomial in r
+// carrying the powers of two) and the table product is fused with the `1 +`, so a tanh costs 13 FP64 operations: M50 evaluates 64 of them per basin-step and is bound
 // by the FP64 pipe.
 #define HB_HI_350 0x4075e000   // high word of 350.0
 HB_DEV double hb_tanh(double x) {
     const double MAGIC = 6755399441055744.0;
     const double xc = hb_clamp_abs(x, HB_HI_350);
-    double t = fma(xc, 184.66496523378732, MAGIC);          // x * 128/ln2
+    double t = fma(xc, 738.6598609351493, MAGIC);           // x * 512/ln2
     const int ti = hb_double2loint(t);
     t -= MAGIC;
-    double r = fma(t, -0.005415212333900854, xc);            // ln2/128 high part (half of the ln2/64 split: exact)
-    r = fma(t, -1.42237187383136425e-11, r);                 // ln2/128 low part
-    double q = fma(r, 2.66666666666666666667e-01, 6.66666666666666666667e-01);   // e^(2r) = sum (2r)^n / n!
-    q = fma(q, r, 1.33333333333333333333e+00);
+    double r = fma(t, -0.0013538030834752135, xc);           // ln2/512 high part (an eighth of the ln2/64 split: exact)
+    r = fma(t, -3.5559296845784106e-12, r);                  // ln2/512 low part
+    double q = fma(r, 6.66666666666666666667e-01, 1.33333333333333333333e+00);   // e^(2r) = sum (2r)^n / n!, |2r| <= ln2/512
     q = fma(q, r, 2.0);
     q = fma(q, r, 2.0);
     q = fma(q, r, 1.0);
     // 1 + exp(2x) = 1 + (2^k T_j) q in ONE fma: 2^k goes onto the table entry by an integer add to its exponent field
     // (|2x| <= 700: the scaled entry stays a normal double)
-    const double tj = hb_exp2t[ti & 63];
-    const double tk = hb_hiloint2double(hb_double2hiint(tj) + ((ti >> 6) << 20), hb_double2loint(tj));
+    const double tj = hb_exp2t[ti & 255];
+    const double tk = hb_hiloint2double(hb_double2hiint(tj) + ((ti >> 8) << 20), hb_double2loint(tj));
     return fma(-2.0, hb_rcp(fma(tk, q, 1.0)), 1.0);
 }
 // log(x) for positive normal x — the classic argument reduction x = 2^k m, m in [sqrt(1/2), sqrt(2)), f = m - 1, s = f / (2 + f),
