@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--stages", type=int, default=0, help="tuning: forcing pipeline depth (time steps)")
     ap.add_argument("--maxreg", type=int, default=0, help="tuning: register budget per thread")
     ap.add_argument("--npw", type=int, default=0, help="tuning: nodes per warp of tensor-path MLP bodies (16 | 32; 0 = by node count)")
-    ap.add_argument("--grid-tc", type=int, default=0, help="grid kernels: time steps per launch (0 = 16 for wave, 2 for tile)")
+    ap.add_argument("--grid-tc", type=int, default=0, help="grid kernels: time steps per launch (0 = auto for wave: from the grid width; 2 for tile)")
     ap.add_argument("--grid-bw", type=int, default=32, help="fused grid kernel: region width (cells)")
     ap.add_argument("--grid-bh", type=int, default=32, help="fused grid kernel: region height (cells)")
     ap.add_argument("--grid-kernel", default="wave", choices=["wave", "tile", "generic"],
@@ -379,8 +379,10 @@ def main():
     args = ap.parse_args()
     if args.fused_grid:
         args.grid_kernel = "tile"
-    if args.grid_tc <= 0:
-        args.grid_tc = 16 if args.grid_kernel == "wave" else 2
+    if args.grid_tc <= 0 and args.grid_kernel != "wave":
+        args.grid_tc = 2
+    if args.grid_tc < 0:
+        args.grid_tc = 0          # wave: 0 = the library chooses from the grid width
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -494,7 +496,7 @@ def main():
         elif world > 1 and args.grid_kernel == "wave":
             # row strips + ghost rows, bucket / river states exchanged every `grid_tc` steps (temporal blocking)
             from hydromodels_jl_b200.parallel import ShardedGridRun
-            sharded = ShardedGridRun(eng, g_rows, g_cols, T, p, initstates=init, halo=args.grid_tc, stages=args.stages,
+            sharded = ShardedGridRun(eng, g_rows, g_cols, T, p, initstates=init, halo=args.grid_tc or 16, stages=args.stages,
                                      max_registers=args.maxreg, block_threads=args.block)
             assert sharded.N == N
             eng.last_kernel = sharded.run.ck

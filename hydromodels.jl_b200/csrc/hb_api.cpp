@@ -818,7 +818,7 @@ int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out)
     if (spec->variant == HB_GRID_WAVE) {
         m->block = bw > 0 ? bw : 128;
         const int stages = spec->stages > 0 ? spec->stages : 3;
-        if (tc < 1 || tc > 4096 || m->block % 32 || m->block > 1024 || stages > 16 || spec->n_inputs < 1) {
+        if (tc < 0 || tc > 4096 || m->block % 32 || m->block > 1024 || stages > 16 || spec->n_inputs < 1) {
             delete m;
             return fail(HB_ERR_INVALID, "bad wave configuration (steps_per_chunk %d, block %d, stages %d)", tc, bw, stages);
         }
@@ -889,6 +889,16 @@ int wave_steps_per_launch(hb_model_s *m, int cols, int *out_tc) {
     int tc = m->gspec.steps_per_chunk;
     const int fit = (resident / 2) / band;
     if (fit < 1) return fail(HB_ERR_INVALID, "grid too wide for the wave kernel (%d columns, %d co-resident blocks)", cols, resident);
+    if (tc <= 0) {
+        // automatic: the rows of the last T_c steps behind the dispatch frontier cannot run freely (each waits for the row
+        // below to be dispatched), so T_c rows should be a small share of the co-resident rows — about a quarter measured
+        // best (2048 columns: 8 steps per launch, 1024: 18, 512 and narrower: 32), while few steps per launch pay the
+        // per-launch prologue more often
+        const long long resident_cells = (long long)resident * m->block;
+        tc = (int)(resident_cells / (4LL * cols));
+        if (tc < 4) tc = 4;
+        if (tc > 32) tc = 32;
+    }
     if (tc > fit) tc = fit;
     *out_tc = tc;
     return HB_OK;

@@ -359,7 +359,7 @@ class B200Model:
         # "generic" = stepper over all T, then one routing launch per step (any node list / graph)
         self.nodes_per_warp = 0           # tensor-path MLP bodies: 0 = default (32), 16 = two lanes per node (stepper.cu HB_NPW)
         self.grid_kernel = "wave"
-        self.grid_steps_per_launch = 16
+        self.grid_steps_per_launch = 0       # wave kernel: steps per launch (0 = chosen by the library from the grid width)
         self.grid_panel_min_cols = 3072      # wave kernel: grids at least this wide run as column panels (parallel.PanelledGridRun)
         self.block_threads, self.stages, self.max_registers = block_threads, stages, max_registers
         self._cache: Dict[Tuple, CompiledStepper] = {}

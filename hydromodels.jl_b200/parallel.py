@@ -415,7 +415,7 @@ class ShardedPanelRun:
     `[T][rows][owned columns][R]` for the owned cells."""
 
     def __init__(self, eng, rows: int, cols: int, T: int, params, *, config=None, initstates=None, halo: int = 32, group=None,
-                 stages: int = 0, max_registers: int = 0, block_threads: int = 0, steps_per_launch: int = 16):
+                 stages: int = 0, max_registers: int = 0, block_threads: int = 0, steps_per_launch: int = 0):
         import torch
         import torch.distributed as dist
         from .engine import B200Model, GridDeviceRun
@@ -470,7 +470,7 @@ class PanelledGridRun:
     than as one sub-grid (the wave kernel prefers tall, narrow sub-grids)."""
 
     def __init__(self, eng, rows: int, cols: int, T: int, params, *, config=None, initstates=None, panels: int = 0, halo: int = 32,
-                 steps_per_launch: int = 16, stages: int = 0, max_registers: int = 0, block_threads: int = 0):
+                 steps_per_launch: int = 0, stages: int = 0, max_registers: int = 0, block_threads: int = 0):
         import torch
         from .engine import B200Model, GridDeviceRun
         K = int(panels) if panels else max(1, int(round(cols / 1024)))

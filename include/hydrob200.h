@@ -220,7 +220,8 @@ typedef struct {
     int32_t n_route_inputs;
     int32_t s_row, o_row;       /* record rows of the route state / outflow */
     int32_t steps_per_chunk;    /* T_c: steps per launch.  TILE: = halo depth (1..8).  WAVE: 1..4096, clamped at run
-                                 * time so that the dependency cone fits in the co-resident blocks */
+                                 * time so that the dependency cone fits in the co-resident blocks; 0 = chosen from the
+                                 * grid width (a quarter of the co-resident rows, 4..32) */
     int32_t block_w, block_h;   /* TILE: region (tile + halo) in cells; block_w % 32 == 0, block_w*block_h <= 1024.
                                  * WAVE: block_w = threads per block (0 = 128), block_h ignored */
     int32_t variant;            /* HB_GRID_TILE | HB_GRID_WAVE */
