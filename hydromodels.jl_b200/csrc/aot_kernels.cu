@@ -247,11 +247,8 @@ template <int HP>
 int hb_launch_conv_tiled(dim3 grid, cudaStream_t st, int n_out, int n_in, long long T, int H, long long nnz, const int *row_ptr,
                          const int *src, const double *w, const double *in, double *out) {
     const int smem = (2 * (8 * HB_IRF_TT + HP) * 32 + 2 * HP * 32) * 8;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(hb_sparse_conv_tiled<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HB_ERR_CUDA;
-        configured = true;
-    }
+    // per device and per context: set on every call (a host-side attribute write, negligible next to the launch)
+    if (cudaFuncSetAttribute(hb_sparse_conv_tiled<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HB_ERR_CUDA;
     hb_sparse_conv_tiled<HP><<<grid, 256, smem, st>>>(n_out, n_in, T, H, nnz, row_ptr, src, w, in, out);
     return HB_OK;
 }
