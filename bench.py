@@ -401,7 +401,7 @@ def main():
     rows_of = {"exphydro": 10, "gr4j": 15, "hbv": 18, "m50": 12, "hbv_ensemble": 0, "exphydro_grid": 13}[model_name]
     v_of = {"exphydro": 3, "gr4j": 2, "hbv": 3, "m50": 3, "hbv_ensemble": 0, "exphydro_grid": 3}[model_name]
     unit = "basin-timesteps/s"
-    config = {"workload": args.workload, "model": model_name, "basins_per_gpu": N, "timesteps": T,
+    config = {"workload": args.workload, "bucket_model": model_name, "basins_per_gpu": N, "timesteps": T,
               "rows_out": rows_of, "forcing_rows": v_of, "output": "full [rows,N,T] as the reference returns",
               "sharding": f"basins sharded over {world} rank(s), no data-path collective",
               "l2": "inputs+outputs per step (GBs) exceed the 126 MB L2; no flush needed"}
