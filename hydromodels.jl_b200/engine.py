@@ -402,17 +402,20 @@ class B200Model:
 
     # -- compile ------------------------------------------------------------------------------------
     def compiled(self, *, rows=None, objective=False, metric=0, shared_forcing=False,
-                 uh_kmax: Sequence[int] = (), uh_on_device: bool = False, n_nodes: int = 0) -> CompiledStepper:
+                 uh_kmax: Sequence[int] = (), uh_on_device: bool = False, n_nodes: int = 0,
+                 component_min: Optional[Sequence[float]] = None) -> CompiledStepper:
         # tensor-path MLP bodies: `nodes_per_warp = 16` doubles the warps of a small run (stepper.cu HB_NPW).  Measured on M50
         # 50 k x 3650: 48.6 ms vs 46.1 ms at 32 — the kernel is FP64-pipe bound (math_pipe_throttle), not short of warps, and
         # the duplicated scalar work costs more than the extra warps hide — so 32 stays the default and 16 is opt-in.
         npw = self.nodes_per_warp or 32
-        key = (tuple(rows) if rows is not None else None, objective, metric, shared_forcing, tuple(uh_kmax), bool(uh_on_device), npw)
+        key = (tuple(rows) if rows is not None else None, objective, metric, shared_forcing, tuple(uh_kmax), bool(uh_on_device), npw,
+               tuple(component_min) if component_min is not None else None)
         if key not in self._cache:
             prog = lower_stepper(self._stepper_component(), rows=rows, objective=objective,
                                  uh_kmax=list(uh_kmax) if len(uh_kmax) else None, fast=self.fast,
                                  holes=self._route_rows(), nn_tensor=self.nn_tensor,
-                                 precision=self.precision, uh_on_device=uh_on_device)
+                                 precision=self.precision, uh_on_device=uh_on_device,
+                                 component_min_values=component_min)
             # MLP-fused bodies keep 16+16 activations per net in registers: give them 168 (3 blocks/SM)
             maxreg = self.max_registers or (168 if prog.nn_words else 0)
             self._cache[key] = CompiledStepper(prog, metric=metric, shared_forcing=shared_forcing,
@@ -577,14 +580,29 @@ class B200Model:
     # -- the functor ----------------------------------------------------------------------------------
     def __call__(self, input, params, config=None, *, initstates=None, rows: Optional[Sequence[str]] = None,
                  return_final_states: bool = False, out: Optional[np.ndarray] = None, timing: Optional[dict] = None):
-        cfg = normalize_config(config[0] if isinstance(config, (tuple, list)) else config)
+        # per-component configs (`/root/reference/src/model.jl:140-152`): a tuple, or {"components": tuple}
+        if isinstance(config, dict) and "components" in config:
+            if not isinstance(config["components"], (tuple, list)):
+                raise ValueError("components field in config must be a Tuple")
+            config = tuple(config["components"])
+        component_min = None
         if isinstance(config, (tuple, list)):
             ncomp = len(self.component.components) if isinstance(self.component, HydroModel) else 1
             if len(config) != ncomp:
                 raise ValueError("Component configs length must equal components length")
             cfgs = [normalize_config(c) for c in config]
-            if any((c.min_value != cfg.min_value) for c in cfgs):
-                raise NotImplementedError("per-component min_value is not supported by the fused stepper")
+            cfg = cfgs[0]
+            for c in cfgs[1:]:
+                if c.solver == SolverType.ODESolver or c.interpolator not in (ConstantInterpolation, LinearInterpolation) \
+                        or list(c.timeidx) != list(cfg.timeidx):
+                    _check_config(c, len(cfg.timeidx))
+                    raise NotImplementedError("per-component timeidx must agree across components")
+            if any(c.min_value != cfg.min_value for c in cfgs):
+                if self.route is not None:
+                    raise NotImplementedError("per-component min_value is not supported for models with a HydroRoute")
+                component_min = tuple(float(c.min_value) for c in cfgs)     # baked into the body as literals
+        else:
+            cfg = normalize_config(config)
         input = np.asarray(input)
         if input.dtype != self.dtype:
             input = input.astype(self.dtype)
@@ -602,13 +620,13 @@ class B200Model:
         _check_config(cfg, T)
         inp = input if input.flags.f_contiguous else np.asfortranarray(input)   # memory = [T][N][V]
         # first pass over the parameters to size the unit hydrographs (compile-time K_max)
-        prog0 = self.compiled(rows=rows, n_nodes=N).program if not self._has_uh() else None
+        prog0 = self.compiled(rows=rows, n_nodes=N, component_min=component_min).program if not self._has_uh() else None
         if prog0 is None:
             probe = lower_stepper(self._stepper_component(), rows=rows, fast=self.fast)
             _, _, _, _, _, kmax, _ = self.prepare(probe, params, N)
-            ck = self.compiled(rows=rows, uh_kmax=kmax, n_nodes=N)
+            ck = self.compiled(rows=rows, uh_kmax=kmax, n_nodes=N, component_min=component_min)
         else:
-            ck = self.compiled(rows=rows, n_nodes=N)
+            ck = self.compiled(rows=rows, n_nodes=N, component_min=component_min)
         prog = ck.program
         flat, p_off, p_mode, htypes, uhw, kmax, nn = self.prepare(prog, params, N)
         uhw_flat = np.ascontiguousarray(np.concatenate(uhw, axis=0)) if uhw else None

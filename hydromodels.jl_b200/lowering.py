@@ -251,12 +251,17 @@ def _flatten(component: Component) -> Tuple[List[Component], List[str], List[str
 def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None, objective: bool = False,
                   uh_kmax: Optional[Sequence[int]] = None, fast: bool = True,
                   holes: Sequence[str] = (), nn_tensor: bool = False, precision: str = "f64",
-                  uh_on_device: bool = False) -> StepperProgram:
+                  uh_on_device: bool = False,
+                  component_min_values: Optional[Sequence[Optional[float]]] = None) -> StepperProgram:
     """Lower a per-node model (buckets, fluxes, neural fluxes, unit hydrographs) to one stepper
     body.  `rows`: subset/order of result rows to write (default: all = the reference result);
     `objective`: emit the last output row as `hb_sim` for the fused metric reduction instead of
-    rows; `uh_kmax[u]`: ordinates per unit hydrograph (from the run's parameters)."""
+    rows; `uh_kmax[u]`: ordinates per unit hydrograph (from the run's parameters);
+    `component_min_values[c]`: the state floor of component c when the call carries per-component configs
+    (`/root/reference/src/model.jl:140-152`) — baked in as a literal; None = the run's `min_value` argument."""
     comps, input_names, all_rows = _flatten(component)
+    if component_min_values is not None and len(component_min_values) != len(comps):
+        raise LoweringError("Component configs length must equal components length")
     for c in comps:
         if isinstance(c, HydroRoute):
             raise LoweringError("HydroRoute is a grid-coupled component; it is lowered by lower_route")
@@ -321,6 +326,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
     statements: List[Tuple[str, object]] = []  # ordered side effects ('update', (sidx, val)), …
 
     raw_states = set()                        # states updated without the min_value clamp (NeuralBucket)
+    state_floor: Dict[int, float] = {}        # state index → literal floor (per-component configs)
 
     def nn_outputs(chain, ins: Tuple[int, ...]) -> List[int]:
         ni = net_index(chain)
@@ -350,7 +356,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                     local[eq.lhs.name] = outs[eq.lhs.name] = vid
         return outs
 
-    for c in comps:
+    for ci, c in enumerate(comps):
         missing = [i for i in c.input_names if i not in env]
         if missing:
             raise LoweringError(f"Input variables {missing} of component {c.name} not found")
@@ -361,6 +367,9 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                 env.update(eval_fluxes(c, local, ptab))
                 continue
             sidx = [state_names.index(s) for s in c.state_names]
+            if component_min_values is not None and component_min_values[ci] is not None:
+                for si in sidx:
+                    state_floor[si] = float(component_min_values[ci])
             # pass 1: pre-update states
             local = {i: env[i] for i in c.input_names}
             for s, si in zip(c.state_names, sidx):
@@ -554,7 +563,8 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
             if si in raw_states:
                 step.append(f"const double hb_un{si} = hb_u[{si}] + {step_ref(pending_updates[si][2])};")
             else:
-                step.append(f"const double hb_un{si} = hb_max(hb_minv, hb_u[{si}] + {step_ref(pending_updates[si][2])});")
+                floor = _c_double(state_floor[si]) if si in state_floor else "hb_minv"
+                step.append(f"const double hb_un{si} = hb_max({floor}, hb_u[{si}] + {step_ref(pending_updates[si][2])});")
             continue
         if i not in live or v.mask == 0 or v.op in ("const", "in", "param", "state") or i in carried:
             continue

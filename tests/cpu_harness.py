@@ -79,14 +79,20 @@ def run_body_on_cpu(eng, input, params, config=None, initstates=None, rows=None,
     from hydromodels_jl_b200.components import normalize_config
     from hydromodels_jl_b200.lowering import lower_stepper
 
-    cfg = normalize_config(config)
+    cmin = None
+    if isinstance(config, (tuple, list)):                 # per-component configs: floors baked in as literals
+        cfgs = [normalize_config(c) for c in config]
+        cfg, cmin = cfgs[0], [c.min_value for c in cfgs]
+    else:
+        cfg = normalize_config(config)
     input = np.asarray(input, dtype=np.float64)
     ensemble = ensemble_members is not None
     N, T = eng._dims(input, ensemble, ensemble_members)
     inp = np.asfortranarray(input)
     probe = lower_stepper(eng.component, rows=rows, objective=objective, fast=eng.fast)
     kmax = uh_kmax or eng.prepare(probe, params, N, ensemble=ensemble)[5]
-    prog = lower_stepper(eng.component, rows=rows, objective=objective, uh_kmax=kmax or None, fast=eng.fast, uh_on_device=uh_on_device)
+    prog = lower_stepper(eng.component, rows=rows, objective=objective, uh_kmax=kmax or None, fast=eng.fast, uh_on_device=uh_on_device,
+                         component_min_values=cmin)
     flat, p_off, p_mode, htypes, uhw, _, nn = eng.prepare(prog, params, N, ensemble=ensemble)
     if uh_on_device and uhw:
         uhw = [np.full((k, N), np.nan) for k in kmax]       # the prologue must overwrite every ordinate

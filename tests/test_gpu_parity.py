@@ -100,6 +100,20 @@ def test_rows_subset_default_states_and_min_value():
     assert_parity(got, ref[[model.var_names.index("flow"), model.var_names.index("soilwater")]])
 
 
+def test_per_component_configs():
+    """One config per component (`/root/reference/src/model.jl:140-152`), tuple and {"components": …} forms."""
+    model, inp, p, init = case("exphydro", 257, 400)
+    cfgs = (hm.HydroConfig(min_value=1e-2), hm.HydroConfig(min_value=1e-6))
+    ref = ho.run_model(model, inp, p, cfgs, init)
+    eng = hm.B200Model(model)
+    got = eng(inp, p, cfgs, initstates=init)
+    assert_parity(got, ref)
+    assert np.min(got[0]) == 1e-2
+    assert np.array_equal(eng(inp, p, {"components": cfgs}, initstates=init), got)
+    with pytest.raises(ValueError, match="Component configs length"):
+        eng(inp, p, cfgs[:1], initstates=init)
+
+
 def test_chunked_run_resumes_bit_identically():
     """States are rows: `initstates = final states` continues a run (SURVEY.md §5 checkpoint row)."""
     model, inp, p, init = case("hbv", 512, 180)

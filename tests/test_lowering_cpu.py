@@ -143,3 +143,18 @@ def test_unit_hydrograph_ordinates_evaluated_in_the_prologue():
         assert np.all(np.isfinite(dev))
         assert_parity(dev, host)
     assert_parity(host, ho.run_model(model, inp, p, initstates=init))
+
+
+def test_per_component_configs_bake_their_state_floors():
+    """`_normalize_component_configs` (`/root/reference/src/model.jl:140-152`): one config per component; here
+    the floors differ (the snow bucket empties in summer, so its floor is active every year)."""
+    model, inp, p, init = _multinode_case("exphydro", 5, 400)
+    cfgs = (hm.HydroConfig(min_value=1e-2), hm.HydroConfig(min_value=1e-6))
+    ref = ho.run_model(model, inp, p, cfgs, init)
+    got = run_body_on_cpu(hm.B200Model(model), inp, p, cfgs, init)
+    assert_parity(got, ref)
+    assert np.min(ref[0]) == 1e-2 and not np.allclose(ref, ho.run_model(model, inp, p, cfgs[1], init))
+    same = ho.run_model(model, inp, p, {"components": cfgs}, init)
+    assert np.array_equal(same, ref)
+    with pytest.raises(ValueError, match="Component configs length"):
+        ho.run_model(model, inp, p, cfgs[:1], init)
