@@ -349,13 +349,47 @@ def bench_calibration(args):
     return 0
 
 
+def bench_gradient(args):
+    """SURVEY.md §8f row 3 (second half): d NSE / d parameters of an ExpHydro calibration ensemble, 262 144 members x 10
+    years, 6 directions per launch (forward-mode tangents in the fused stepper) beside the plain objective launch."""
+    import hydromodels_jl_b200 as hm
+    from hydromodels_jl_b200 import synthetic as sy
+    hm.engine.init(0)
+    T, N = 3650, 262144
+    model = hm.models.exphydro()
+    eng = hm.B200Model(model)
+    inp = sy.forcing("exphydro", 0, 1, T)[:, 0, :]
+    p = {"params": sy.parameters("exphydro", 0, N)}
+    init = dict(snowpack=0.0, soilwater=1303.0)
+    target = 0.5 + 5.0 * np.random.default_rng(1).random(T)
+    kw = dict(metric="NSE", warm_up=366, initstates=init, n_members=N)
+    ms_g, ms_o = [], []
+    for i in range(args.warmup + args.steps):
+        tg, to = {}, {}
+        loss, g = eng.gradient(inp, p, target, timing=tg, **kw)
+        obj = eng.objective(inp, p, target, timing=to, **kw)
+        if i >= args.warmup:
+            ms_g.append(tg["kernel_ms"]); ms_o.append(to["kernel_ms"])
+    info = tg["kernel"].info()
+    mg, mo = float(np.mean(ms_g)), float(np.mean(ms_o))
+    print(json.dumps({"metric": "member-timesteps/sec of a gradient run (objective + 6 derivatives per member)", "value": N * T / (mg * 1e-3),
+                      "unit": "member-timesteps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mg,
+                      "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "gradient_exphydro_262144x3650", "members": N, "timesteps": T, "directions": 6, "metric": "NSE"},
+                      "objective_only_ms": mo, "gradient_over_objective": mg / mo, "registers": info["registers_per_thread"],
+                      "spill_bytes": info["local_bytes_per_thread"], "blocks_per_sm": info["max_blocks_per_sm"],
+                      "max_abs_loss_difference_vs_objective_kernel": float(np.abs(loss - obj).max()), "gpu_launches": 2 * (args.warmup + args.steps),
+                      "timing": "CUDA events around each kernel (hb_run elapsed_ms)"}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096", "calibrate_exphydro", "irf_route", "exphydro_single_basin_365d"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096", "calibrate_exphydro", "gradient_exphydro", "irf_route", "exphydro_single_basin_365d"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -390,6 +424,8 @@ def main():
         return bench_raster_ingest(args) if rank == 0 else 0
     if args.workload == "calibrate_exphydro":
         return bench_calibration(args) if rank == 0 else 0
+    if args.workload == "gradient_exphydro":
+        return bench_gradient(args) if rank == 0 else 0
     if args.workload == "irf_route":
         return bench_irf(args) if rank == 0 else 0
     if args.workload == "exphydro_single_basin_365d":

@@ -343,6 +343,7 @@ int check_desc(const hb_model_s *m, const hb_run_desc *d) {
     } else {
         if (!d->objective || !d->target) return fail(HB_ERR_INVALID, "objective mode needs target and objective buffers");
         if (d->warm_up < 1 || d->warm_up > d->n_steps) return fail(HB_ERR_INVALID, "warm_up must be in 1..n_steps");
+        if (s.n_tangents > 0 && !d->gradient) return fail(HB_ERR_INVALID, "gradient run needs the gradient buffer");
     }
     return HB_OK;
 }
@@ -355,8 +356,10 @@ int launch_stepper(hb_model_s *m, const hb_run_desc *d, cudaStream_t stream) {
     memset(buf, 0, sizeof buf);
     size_t o = 0;
     auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
+    // gradient runs have no record stream: the `out` slot carries the [D][N] gradient buffer
     const void *ptrs[12] = {d->input, d->params, d->htypes, d->initstates, d->uh_weights, d->uh_hist_in,
-                            d->nn_params, d->target, d->out, d->objective, d->final_states, d->uh_hist_out};
+                            d->nn_params, d->target, s.n_tangents > 0 ? (void *)d->gradient : d->out, d->objective, d->final_states,
+                            d->uh_hist_out};
     put(ptrs, sizeof ptrs);
     int64_t N = d->n_nodes, T = d->n_steps;
     put(&N, 8);
@@ -482,6 +485,10 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
     if (spec->nodes_per_warp != 0 && spec->nodes_per_warp != 32 && spec->nodes_per_warp != 16)
         return fail(HB_ERR_INVALID, "nodes_per_warp must be 0, 16 or 32");
     if (spec->nodes_per_warp == 16 && !spec->nn_tensor) return fail(HB_ERR_INVALID, "nodes_per_warp = 16 is meant for tensor-path MLP bodies");
+    if (spec->n_tangents < 0 || spec->n_tangents > HB_MAX_TANGENTS) return fail(HB_ERR_INVALID, "n_tangents must be in 0..%d", HB_MAX_TANGENTS);
+    if (spec->n_tangents > 0 && (spec->output_mode != HB_OUT_OBJECTIVE || spec->precision || spec->nn_words > 0))
+        return fail(HB_ERR_INVALID, "gradient runs need objective mode, Float64 and a body without MLPs");
+    if (spec->metric < 0 || spec->metric > HB_METRIC_SSE) return fail(HB_ERR_INVALID, "unknown metric %d", spec->metric);
     hb_model_s *m = new hb_model_s();
     m->spec = *spec;
     m->block = spec->block_threads > 0 ? spec->block_threads : 128;
@@ -514,10 +521,11 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
     snprintf(defs, sizeof defs,
              "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_UHW_TOTAL %d\n"
              "#define HB_UHH_TOTAL %d\n#define HB_NN_WORDS %d\n#define HB_MODE %d\n#define HB_METRIC %d\n#define HB_SHARED_FORCING %d\n"
-             "#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n#define HB_NN_MMA %d\n#define HB_F32 %d\n#define HB_NPW %d\n",
+             "#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n#define HB_NN_MMA %d\n#define HB_F32 %d\n#define HB_NPW %d\n"
+             "#define HB_TANGENTS %d\n",
              spec->n_inputs, spec->output_mode == HB_OUT_ROWS ? spec->n_rows : 0, spec->n_states, spec->n_params, m->uhw_total,
              m->uhh_total, spec->nn_words, spec->output_mode, spec->metric, spec->shared_forcing ? 1 : 0, m->block, stages, minblocks,
-             spec->nn_tensor ? 1 : 0, spec->precision ? 1 : 0, spec->nodes_per_warp == 16 ? 16 : 32);
+             spec->nn_tensor ? 1 : 0, spec->precision ? 1 : 0, spec->nodes_per_warp == 16 ? 16 : 32, spec->n_tangents);
     std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";   // body may append to DEFINES (e.g. HB_NC)
     if (const char *x = getenv("HB_EXTRA_DEFINES")) full_body = std::string("//@@HB:DEFINES\n") + x + "\n" + full_body;   // tuning experiments
     m->source = splice(kStepperTemplate, full_body.c_str());
@@ -645,6 +653,8 @@ int hb_run(hb_model_t m, const hb_run_desc *d) {
     if ((rc = ws_reserve(m->ws[0], in_step * T))) return rc;
     if (rows_mode && (rc = ws_reserve(m->ws[8], out_step * T))) return rc;
     if (!rows_mode && (rc = ws_reserve(m->ws[9], (size_t)N * 8))) return rc;
+    const size_t grad_bytes = (size_t)s.n_tangents * N * 8;
+    if (grad_bytes && (rc = ws_reserve(m->ws[10], grad_bytes))) return rc;
     const size_t st_bytes = (size_t)s.n_states * N * 8, uh_bytes = (size_t)m->uhh_total * N * 8;
     // ---- time chunks: H2D(c+1) | kernel(c) | D2H(c-1) overlap on three streams; the bucket states
     //      and UH history are carried between chunk launches in device ping-pong buffers (a chunked
@@ -691,6 +701,7 @@ int hb_run(hb_model_t m, const hb_run_desc *d) {
         dc.input = (const char *)m->ws[0].p + in_step * t0;
         dc.out = rows_mode ? (void *)((char *)m->ws[8].p + out_step * t0) : nullptr;
         dc.objective = rows_mode ? nullptr : (double *)m->ws[9].p;
+        dc.gradient = grad_bytes ? (double *)m->ws[10].p : nullptr;
         dc.initstates = (const double *)state_in;
         dc.uh_hist_in = (const double *)uhh_in;
         const bool last = (c == nchunk - 1);
@@ -718,6 +729,7 @@ int hb_run(hb_model_t m, const hb_run_desc *d) {
     }
     HB_CUDA(cudaEventRecord(m->ev1, m->stream));
     if (!rows_mode) HB_CUDA(cudaMemcpyAsync(d->objective, m->ws[9].p, (size_t)N * 8, cudaMemcpyDeviceToHost, m->stream));
+    if (grad_bytes) HB_CUDA(cudaMemcpyAsync(d->gradient, m->ws[10].p, grad_bytes, cudaMemcpyDeviceToHost, m->stream));
     if (d->final_states && st_bytes && last_state_slot >= 0)
         HB_CUDA(cudaMemcpyAsync(d->final_states, m->ws[last_state_slot].p, st_bytes, cudaMemcpyDeviceToHost, m->stream));
     if (d->uh_hist_out && uh_bytes && last_uh_slot >= 0)
@@ -829,7 +841,11 @@ int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out)
         if (m->wave_qslots < 2 || m->wave_qslots > 8) { delete m; return fail(HB_ERR_INVALID, "HB_WAVE_QSLOTS must be 2..8"); }
         if (obuf < 2 || obuf > 4) { delete m; return fail(HB_ERR_INVALID, "HB_WAVE_OBUF must be 2..4"); }
         m->dyn_smem = warps * (up128(stages * 32 * spec->n_inputs * 8) + up128(obuf * 32 * spec->n_rows * 8)) + warps * stages * 8;
-        if (m->dyn_smem > 227 * 1024) { delete m; return fail(HB_ERR_INVALID, "wave kernel needs %d bytes of shared memory", m->dyn_smem); }
+        if (m->dyn_smem > 227 * 1024) {
+            const int need = m->dyn_smem;
+            delete m;
+            return fail(HB_ERR_INVALID, "wave kernel needs %d bytes of shared memory", need);
+        }
         int minblocks = (227 * 1024) / (m->dyn_smem + 1024 + 1024);
         const int cap = 2048 / m->block;
         if (minblocks > cap) minblocks = cap;

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #define HB_DEV static inline
+#define HB_MEM inline
 #define HB_CONST static const
 HB_DEV double hb_hiloint2double(int hi, int lo) {
     unsigned long long u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
@@ -34,6 +35,7 @@ HB_DEV double hb_rcp_seed(double x) {   // emulate MUFU.RCP64H: only the upper 3
 }
 #else
 #define HB_DEV __device__ __forceinline__
+#define HB_MEM __device__ __forceinline__
 #define HB_CONST __constant__ const
 HB_DEV double hb_hiloint2double(int hi, int lo) { return __hiloint2double(hi, lo); }
 HB_DEV int hb_double2loint(double x) { return __double2loint(x); }
@@ -282,9 +284,81 @@ HB_DEV double hb_max(double a, double b) { return a > b ? a : b; }
 HB_DEV double hb_leakyrelu(double x) { return hb_max(0.01 * x, x); }
 HB_DEV double hb_clamp(double x, double lo, double hi) { return hb_min(hb_max(x, lo), hi); }
 
+HB_DEV double hb_val(double x) { return x; }   // the value of a quantity (gradient runs overload it for hb_dual)
+
+// ---- forward-mode tangents (HB_TANGENTS = D > 0): value + D directional derivatives -------------------------------------------
+// The gradient run of the stepper (the reference differentiates the same discrete recurrence with Zygote through its
+// ImmutableSolver, /root/reference/README.md:161-187) retypes the generated body's temporaries to `auto` / hb_dual, so the SAME
+// statement list propagates d/dp of every state and flux next to the value: exact derivatives of the arithmetic that is
+// actually executed (min/max/clamp pass the selected branch's tangent, ties to the second argument like `a > b ? a : b`).
+#if defined(HB_TANGENTS) && HB_TANGENTS > 0
+#define HB_DK _Pragma("unroll") for (int k = 0; k < HB_TANGENTS; ++k)
+struct hb_dual {
+    double v;
+    double d[HB_TANGENTS];
+    HB_MEM hb_dual() {}
+    HB_MEM hb_dual(double x) : v(x) { HB_DK d[k] = 0.0; }
+};
+HB_DEV double hb_val(const hb_dual &x) { return x.v; }
+// f(a) with f'(a) = g
+HB_DEV hb_dual hb_chain(const hb_dual &a, double f, double g) { hb_dual r; r.v = f; HB_DK r.d[k] = g * a.d[k]; return r; }
+HB_DEV hb_dual operator-(const hb_dual &a) { hb_dual r; r.v = -a.v; HB_DK r.d[k] = -a.d[k]; return r; }
+HB_DEV hb_dual operator+(const hb_dual &a, const hb_dual &b) { hb_dual r; r.v = a.v + b.v; HB_DK r.d[k] = a.d[k] + b.d[k]; return r; }
+HB_DEV hb_dual operator+(const hb_dual &a, double b) { hb_dual r = a; r.v = a.v + b; return r; }
+HB_DEV hb_dual operator+(double a, const hb_dual &b) { hb_dual r = b; r.v = a + b.v; return r; }
+HB_DEV hb_dual operator-(const hb_dual &a, const hb_dual &b) { hb_dual r; r.v = a.v - b.v; HB_DK r.d[k] = a.d[k] - b.d[k]; return r; }
+HB_DEV hb_dual operator-(const hb_dual &a, double b) { hb_dual r = a; r.v = a.v - b; return r; }
+HB_DEV hb_dual operator-(double a, const hb_dual &b) { hb_dual r; r.v = a - b.v; HB_DK r.d[k] = -b.d[k]; return r; }
+HB_DEV hb_dual operator*(const hb_dual &a, const hb_dual &b) { hb_dual r; r.v = a.v * b.v; HB_DK r.d[k] = fma(a.v, b.d[k], a.d[k] * b.v); return r; }
+HB_DEV hb_dual operator*(const hb_dual &a, double b) { hb_dual r; r.v = a.v * b; HB_DK r.d[k] = a.d[k] * b; return r; }
+HB_DEV hb_dual operator*(double a, const hb_dual &b) { hb_dual r; r.v = a * b.v; HB_DK r.d[k] = a * b.d[k]; return r; }
+HB_DEV hb_dual operator/(const hb_dual &a, const hb_dual &b) {
+    hb_dual r; r.v = a.v / b.v; const double ib = 1.0 / b.v; HB_DK r.d[k] = fma(-r.v, b.d[k], a.d[k]) * ib; return r;
+}
+HB_DEV hb_dual operator/(const hb_dual &a, double b) { hb_dual r; r.v = a.v / b; const double ib = 1.0 / b; HB_DK r.d[k] = a.d[k] * ib; return r; }
+HB_DEV hb_dual operator/(double a, const hb_dual &b) { hb_dual r; r.v = a / b.v; const double g = -r.v / b.v; HB_DK r.d[k] = g * b.d[k]; return r; }
+HB_DEV hb_dual &operator+=(hb_dual &a, const hb_dual &b) { a.v += b.v; HB_DK a.d[k] += b.d[k]; return a; }
+HB_DEV hb_dual &operator*=(hb_dual &a, const hb_dual &b) { a = a * b; return a; }
+#define HB_DUAL_CMP(op) \
+    HB_DEV bool operator op(const hb_dual &a, const hb_dual &b) { return a.v op b.v; } \
+    HB_DEV bool operator op(const hb_dual &a, double b) { return a.v op b; } \
+    HB_DEV bool operator op(double a, const hb_dual &b) { return a op b.v; }
+HB_DUAL_CMP(<) HB_DUAL_CMP(<=) HB_DUAL_CMP(>) HB_DUAL_CMP(>=)
+HB_DEV hb_dual hb_exp(const hb_dual &a) { const double e = hb_exp(a.v); return hb_chain(a, e, e); }
+HB_DEV hb_dual hb_step(const hb_dual &a) { const double s = hb_step(a.v); return hb_chain(a, s, 10.0 * s * (1.0 - s)); }   // (tanh(5x)+1)/2
+HB_DEV hb_dual hb_tanh(const hb_dual &a) { const double t = hb_tanh(a.v); return hb_chain(a, t, fma(-t, t, 1.0)); }
+HB_DEV hb_dual log(const hb_dual &a) { return hb_chain(a, log(a.v), 1.0 / a.v); }
+HB_DEV hb_dual sqrt(const hb_dual &a) { const double s = sqrt(a.v); return hb_chain(a, s, 0.5 / s); }
+HB_DEV hb_dual fabs(const hb_dual &a) { return a.v < 0.0 ? -a : a; }
+HB_DEV hb_dual hb_min(const hb_dual &a, const hb_dual &b) { return a.v < b.v ? a : b; }
+HB_DEV hb_dual hb_min(const hb_dual &a, double b) { return a.v < b ? a : hb_dual(b); }
+HB_DEV hb_dual hb_min(double a, const hb_dual &b) { return a < b.v ? hb_dual(a) : b; }
+HB_DEV hb_dual hb_max(const hb_dual &a, const hb_dual &b) { return a.v > b.v ? a : b; }
+HB_DEV hb_dual hb_max(const hb_dual &a, double b) { return a.v > b ? a : hb_dual(b); }
+HB_DEV hb_dual hb_max(double a, const hb_dual &b) { return a > b.v ? hb_dual(a) : b; }
+// x^y: d = y x^(y-1) dx + x^y log(x) dy (the log term is dropped at x <= 0 where the value is 0 / undefined)
+HB_DEV hb_dual hb_pow(const hb_dual &x, double y) { return hb_chain(x, hb_pow(x.v, y), y * hb_pow(x.v, y - 1.0)); }
+HB_DEV hb_dual hb_pow(double x, const hb_dual &y) {
+    const double r = hb_pow(x, y.v);
+    return hb_chain(y, r, x > 0.0 ? r * log(x) : 0.0);
+}
+HB_DEV hb_dual hb_pow(const hb_dual &x, const hb_dual &y) {
+    hb_dual r; r.v = hb_pow(x.v, y.v);
+    const double gx = y.v * hb_pow(x.v, y.v - 1.0), gy = x.v > 0.0 ? r.v * log(x.v) : 0.0;
+    HB_DK r.d[k] = fma(gx, x.d[k], gy * y.d[k]);
+    return r;
+}
+HB_DEV hb_dual fma(const hb_dual &a, const hb_dual &b, const hb_dual &c) {
+    hb_dual r; r.v = fma(a.v, b.v, c.v); HB_DK r.d[k] = fma(a.v, b.d[k], fma(a.d[k], b.v, c.d[k])); return r;
+}
+HB_DEV hb_dual fma(double a, const hb_dual &b, const hb_dual &c) { hb_dual r; r.v = fma(a, b.v, c.v); HB_DK r.d[k] = fma(a, b.d[k], c.d[k]); return r; }
+HB_DEV hb_dual fma(const hb_dual &a, double b, const hb_dual &c) { return fma(b, a, c); }
+#endif
+
 // ---- opt-in Float32 mode: same functions on float (libdevice expf is ~1-2 ulp; the FP32 pipe is not the
 //      bottleneck, the halved HBM traffic is the point) ---------------------------------------------
 #ifndef HB_HOST_TEST
+HB_DEV double hb_val(float x) { return (double)x; }
 HB_DEV float hb_exp(float x) { return expf(x); }
 HB_DEV float hb_pow(float x, float y) { return powf(x, y); }
 HB_DEV float hb_rcp(float x) { return __frcp_rn(x); }

@@ -51,6 +51,9 @@ typedef float real;
 #else
 typedef double real;
 #endif
+#ifndef HB_TANGENTS
+#define HB_TANGENTS 0 // D > 0: gradient run — parameters carry D unit tangents (HB_TDIR: direction of each parameter slot or -1),
+#endif                //   states / fluxes / the objective propagate them (hb_dual, hb_math.cuh); objective mode only, Float64 only
 #ifndef HB_NPW
 #define HB_NPW 32     // nodes per warp.  16: lanes l and l+16 carry the SAME node — the scalar code runs identically in both halves
 #endif                //   (free under SIMT) while the warp-cooperative tensor-core MLPs spread half as many basins over the 32 lanes:
@@ -128,6 +131,15 @@ __device__ __forceinline__ void hb_fence_proxy_async() { asm volatile("fence.pro
 // ---- math helpers shared by all generated bodies: templates/hb_math.cuh -----------------------
 //@@HB:MATH
 
+// `treal`: what parameters, states and everything derived from them are made of
+#if HB_TANGENTS > 0
+typedef hb_dual treal;
+typedef hb_dual tacc;    // objective accumulators
+#else
+typedef real treal;
+typedef double tacc;
+#endif
+
 // ---- MLP parameters: module-scope constant bank (filled by the host before each launch) so that
 //      every weight is a c[3][imm] operand of its DFMA; shared across all nodes (src/nn.jl:140-165)
 #if HB_NN_WORDS > 0
@@ -190,7 +202,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
 #endif
 
     // ---- per-node constants: parameters (p[htypes], /root/reference/src/utils.jl:174-201) ------
-    real hb_p[HB_ARR(HB_NP)];
+    treal hb_p[HB_ARR(HB_NP)];
 #pragma unroll
     for (int j = 0; j < HB_NP; ++j) {
         const int mode = a.p_mode[j];
@@ -199,24 +211,34 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
         else if (mode >= 2) idx += a.htypes[(i64)(mode - 2) * a.N + nc];
         hb_p[j] = (real)a.params[idx];
     }
+#if HB_TANGENTS > 0
+    {
+        constexpr int tdir[HB_ARR(HB_NP)] = HB_TDIR;   // d p_j / d theta_k = [tdir[j] == k]
+#pragma unroll
+        for (int j = 0; j < HB_NP; ++j)
+#pragma unroll
+            for (int k = 0; k < HB_TANGENTS; ++k) hb_p[j].d[k] = tdir[j] == k ? 1.0 : 0.0;
+    }
+#endif
     // ---- states: initial value is used UNCLAMPED for the first increment (solve.jl:47-49) ------
-    real hb_u[HB_ARR(HB_S)];
+    treal hb_u[HB_ARR(HB_S)];
 #pragma unroll
     for (int s = 0; s < HB_S; ++s) hb_u[s] = a.init ? (real)a.init[(i64)s * a.N + nc] : (real)0.0;
     // ---- unit-hydrograph ordinates and history -----------------------------------------------
-    real hb_uhw[HB_ARR(HB_UHW_TOTAL)];
-    real hb_uhh[HB_ARR(HB_UHH_TOTAL)];
+    treal hb_uhw[HB_ARR(HB_UHW_TOTAL)];
+    treal hb_uhh[HB_ARR(HB_UHH_TOTAL)];
 #pragma unroll
     for (int k = 0; k < HB_UHW_TOTAL; ++k) hb_uhw[k] = (real)a.uhw[(i64)k * a.N + nc];
 #pragma unroll
     for (int k = 0; k < HB_UHH_TOTAL; ++k) hb_uhh[k] = a.uhh_in ? (real)a.uhh_in[(i64)k * a.N + nc] : (real)0.0;
-    real hb_c[HB_ARR(HB_NC)];   // state-only subexpressions carried from one step to the next
+    treal hb_c[HB_ARR(HB_NC)];   // state-only subexpressions carried from one step to the next
     const real hb_minv = (real)a.min_value;
     (void)hb_p; (void)hb_u; (void)hb_uhw; (void)hb_uhh; (void)hb_c; (void)hb_minv;
 
 #if HB_MODE == 1
     // objective accumulators (shifted sums; metrics of …OptimizationExt.jl:34-68)
-    double q_n = 0.0, q_so = 0.0, q_ss = 0.0, q_soo = 0.0, q_sss = 0.0, q_sos = 0.0, q_sse = 0.0, q_shift = 0.0, q_shift_s = 0.0;
+    double q_n = 0.0, q_so = 0.0, q_soo = 0.0, q_shift = 0.0, q_shift_s = 0.0;
+    tacc q_ss = 0.0, q_sss = 0.0, q_sos = 0.0, q_sse = 0.0;   // the sums the simulated series enters
 #endif
 
     //@@HB:PROLOGUE
@@ -284,7 +306,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
         real hb_out[HB_ARR(HB_R)];
         (void)hb_x; (void)hb_out;
 #if HB_MODE == 1
-        real hb_sim = (real)0.0;
+        treal hb_sim = (real)0.0;
 #endif
 
         //@@HB:STEP
@@ -318,15 +340,16 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
 #if HB_MODE == 1
         if (t + 1 >= a.warm_up) {
             double o = a.target_per_node ? a.target[t * a.N + nc] : a.target[t];
-            double s = (double)hb_sim;
+            tacc s = (tacc)hb_sim;
 #if HB_METRIC == 3
             o = log(o + 1e-6);
             s = log(s + 1e-6);
 #endif
             // each series is shifted by its OWN first value: a simulated series many orders of magnitude below the observed
             // one (degenerate parameter sets are routine inside a calibration) keeps its variance and covariance
-            if (q_n == 0.0) { q_shift = o; q_shift_s = s; }
-            const double od = o - q_shift, sd = s - q_shift_s, e = o - s;
+            if (q_n == 0.0) { q_shift = o; q_shift_s = hb_val(s); }   // the shifts are constants of the run (no tangent)
+            const double od = o - q_shift;
+            const auto sd = s - q_shift_s, e = o - s;
             q_n += 1.0; q_so += od; q_ss += sd;
             q_soo = fma(od, od, q_soo); q_sss = fma(sd, sd, q_sss); q_sos = fma(od, sd, q_sos);
             q_sse = fma(e, e, q_sse);
@@ -339,29 +362,37 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     if (!valid) return;
     if (a.final_states) {
 #pragma unroll
-        for (int s = 0; s < HB_S; ++s) a.final_states[(i64)s * a.N + n] = (double)hb_u[s];
+        for (int s = 0; s < HB_S; ++s) a.final_states[(i64)s * a.N + n] = hb_val(hb_u[s]);
     }
     if (a.uhh_out) {
 #pragma unroll
-        for (int k = 0; k < HB_UHH_TOTAL; ++k) a.uhh_out[(i64)k * a.N + n] = (double)hb_uhh[k];
+        for (int k = 0; k < HB_UHH_TOTAL; ++k) a.uhh_out[(i64)k * a.N + n] = hb_val(hb_uhh[k]);
     }
 #if HB_MODE == 1
     {
         const double var_o = q_soo - q_so * q_so / q_n;   // = sum (o - mean o)^2
-        double val;
+        tacc val;
 #if HB_METRIC == 0
         val = q_sse / q_n;                                 // MSE
 #elif HB_METRIC == 1
         val = -(1.0 - q_sse / var_o);                      // -NSE
+#elif HB_METRIC == 4
+        val = q_sse;                                       // sum of squared errors (the loss of README.md:161-187)
 #else
-        const double var_s = q_sss - q_ss * q_ss / q_n;
-        const double cov = q_sos - q_so * q_ss / q_n;
-        const double r = cov / sqrt(var_o * var_s);
-        const double alpha = sqrt(var_s / var_o);          // std(sim)/std(obs), (n-1) cancels
-        const double beta = (q_ss + q_n * q_shift_s) / (q_so + q_n * q_shift);
+        const auto var_s = q_sss - q_ss * q_ss / q_n;
+        const auto cov = q_sos - q_so * q_ss / q_n;
+        const auto r = cov / sqrt(var_o * var_s);
+        const auto alpha = sqrt(var_s / var_o);            // std(sim)/std(obs), (n-1) cancels
+        const auto beta = (q_ss + q_n * q_shift_s) / (q_so + q_n * q_shift);
         val = -(1.0 - sqrt((r - 1.0) * (r - 1.0) + (alpha - 1.0) * (alpha - 1.0) + (beta - 1.0) * (beta - 1.0)));
 #endif
-        a.obj[n] = val;
+        a.obj[n] = hb_val(val);
+#if HB_TANGENTS > 0
+        // gradient rows [D][N] (the `out` slot of the argument block carries the buffer in a gradient run)
+        double *grad = reinterpret_cast<double *>(a.out);
+#pragma unroll
+        for (int k = 0; k < HB_TANGENTS; ++k) grad[(i64)k * a.N + n] = val.d[k];
+#endif
     }
 #endif
     //@@HB:EPILOGUE

@@ -26,7 +26,8 @@ LIB_PATH = os.path.join(_HERE, "libhydrob200.so")
 
 HB_MAX_UH = 8
 HB_OUT_ROWS, HB_OUT_OBJECTIVE = 0, 1
-METRICS = {"mse": 0, "nse": 1, "kge": 2, "logkge": 3}
+METRICS = {"mse": 0, "nse": 1, "kge": 2, "logkge": 3, "sse": 4}
+HB_MAX_TANGENTS = 16
 
 
 class HydroB200Error(RuntimeError):
@@ -42,7 +43,8 @@ class StepperSpec(C.Structure):
                 ("n_params", C.c_int32), ("n_uh", C.c_int32), ("uh_kmax", C.c_int32 * HB_MAX_UH),
                 ("nn_words", C.c_int32), ("output_mode", C.c_int32), ("metric", C.c_int32),
                 ("shared_forcing", C.c_int32), ("block_threads", C.c_int32), ("stages", C.c_int32),
-                ("max_registers", C.c_int32), ("precision", C.c_int32), ("nn_tensor", C.c_int32), ("nodes_per_warp", C.c_int32)]
+                ("max_registers", C.c_int32), ("precision", C.c_int32), ("nn_tensor", C.c_int32), ("nodes_per_warp", C.c_int32),
+                ("n_tangents", C.c_int32)]
 
 
 class RunDesc(C.Structure):
@@ -52,7 +54,8 @@ class RunDesc(C.Structure):
                 ("initstates", C.c_void_p), ("uh_weights", C.c_void_p), ("uh_hist_in", C.c_void_p),
                 ("nn_params", C.c_void_p), ("target", C.c_void_p), ("target_per_node", C.c_int32),
                 ("warm_up", C.c_int32), ("min_value", C.c_double), ("out", C.c_void_p), ("objective", C.c_void_p),
-                ("final_states", C.c_void_p), ("uh_hist_out", C.c_void_p), ("elapsed_ms", C.c_void_p)]
+                ("final_states", C.c_void_p), ("uh_hist_out", C.c_void_p), ("elapsed_ms", C.c_void_p),
+                ("gradient", C.c_void_p)]
 
 
 class KernelInfo(C.Structure):
@@ -195,6 +198,7 @@ class CompiledStepper:
         spec.nn_tensor = 1 if getattr(program, "nn_tensor", False) else 0
         spec.nodes_per_warp = nodes_per_warp if spec.nn_tensor else 0
         spec.precision = 1 if getattr(program, "precision", "f64") == "f32" else 0
+        spec.n_tangents = len(getattr(program, "tangents", ()) or ())
         self.spec = spec
         h = C.c_void_p()
         check(lib().hb_compile_stepper(C.byref(spec), program.body.encode(), C.byref(h)))
@@ -403,21 +407,22 @@ class B200Model:
     # -- compile ------------------------------------------------------------------------------------
     def compiled(self, *, rows=None, objective=False, metric=0, shared_forcing=False,
                  uh_kmax: Sequence[int] = (), uh_on_device: bool = False, n_nodes: int = 0,
-                 component_min: Optional[Sequence[float]] = None) -> CompiledStepper:
+                 component_min: Optional[Sequence[float]] = None, tangents: Sequence[str] = ()) -> CompiledStepper:
         # tensor-path MLP bodies: `nodes_per_warp = 16` doubles the warps of a small run (stepper.cu HB_NPW).  Measured on M50
         # 50 k x 3650: 48.6 ms vs 46.1 ms at 32 — the kernel is FP64-pipe bound (math_pipe_throttle), not short of warps, and
         # the duplicated scalar work costs more than the extra warps hide — so 32 stays the default and 16 is opt-in.
         npw = self.nodes_per_warp or 32
         key = (tuple(rows) if rows is not None else None, objective, metric, shared_forcing, tuple(uh_kmax), bool(uh_on_device), npw,
-               tuple(component_min) if component_min is not None else None)
+               tuple(component_min) if component_min is not None else None, tuple(tangents))
         if key not in self._cache:
             prog = lower_stepper(self._stepper_component(), rows=rows, objective=objective,
                                  uh_kmax=list(uh_kmax) if len(uh_kmax) else None, fast=self.fast,
                                  holes=self._route_rows(), nn_tensor=self.nn_tensor,
                                  precision=self.precision, uh_on_device=uh_on_device,
-                                 component_min_values=component_min)
-            # MLP-fused bodies keep 16+16 activations per net in registers: give them 168 (3 blocks/SM)
-            maxreg = self.max_registers or (168 if prog.nn_words else 0)
+                                 component_min_values=component_min, tangents=list(tangents) or None)
+            # MLP-fused bodies keep 16+16 activations per net in registers: give them 168 (3 blocks/SM);
+            # gradient bodies carry 1 + D doubles per value: all 255
+            maxreg = self.max_registers or (255 if tangents else (168 if prog.nn_words else 0))
             self._cache[key] = CompiledStepper(prog, metric=metric, shared_forcing=shared_forcing,
                                                block_threads=self.block_threads, stages=self.stages,
                                                max_registers=maxreg, nodes_per_warp=npw)
@@ -777,7 +782,8 @@ class B200Model:
 
     # -- calibration ensembles: fused objective --------------------------------------------------------
     def objective(self, input, params, target, *, metric: str = "NSE", warm_up: int = 1, config=None,
-                  initstates=None, n_members: Optional[int] = None, timing: Optional[dict] = None) -> np.ndarray:
+                  initstates=None, n_members: Optional[int] = None, timing: Optional[dict] = None,
+                  _tangents: Sequence[str] = ()) -> np.ndarray:
         """`loss(target[warm_up:end], model(input, p_i, config; initstates)[end, warm_up:end])` for
         every parameter set / node `i` in one launch
         (`/root/reference/ext/HydroModelsOptimizationExt/HydroModelsOptimizationExt.jl:153-175`).
@@ -787,7 +793,9 @@ class B200Model:
         * multi-node model: one objective per node, `target` is `[T]` (shared) or `[N, T]`."""
         m = metric.lower()
         if m not in METRICS:
-            raise ValueError(f"Unknown metric: {metric}. Supported metrics: KGE, NSE, LogKGE, MSE")
+            raise ValueError(f"Unknown metric: {metric}. Supported metrics: KGE, NSE, LogKGE, MSE, SSE")
+        if self.route is not None:
+            raise NotImplementedError("fused objectives are for per-node models (no HydroRoute)")
         cfg = normalize_config(config)
         input = np.asarray(input, dtype=self.dtype)
         ensemble = n_members is not None
@@ -801,7 +809,8 @@ class B200Model:
             kmax = self.prepare(probe, params, N, ensemble=ensemble)[5]
         else:
             kmax = []
-        ck = self.compiled(objective=True, metric=METRICS[m], shared_forcing=ensemble, uh_kmax=kmax)
+        ck = self.compiled(objective=True, metric=METRICS[m], shared_forcing=ensemble, uh_kmax=kmax,
+                           uh_on_device=bool(_tangents) and bool(kmax), tangents=_tangents)
         prog = ck.program
         flat, p_off, p_mode, htypes, uhw, kmax, nn = self.prepare(prog, params, N, ensemble=ensemble)
         uhw_flat = np.ascontiguousarray(np.concatenate(uhw, axis=0)) if uhw else None
@@ -832,11 +841,56 @@ class B200Model:
         d.target, d.target_per_node, d.warm_up = _ptr(tgt), per_node, int(warm_up)
         d.min_value = cfg.min_value
         d.objective = _ptr(obj)
+        grad = np.empty((len(_tangents), N), dtype=np.float64) if _tangents else None
+        d.gradient = _ptr(grad)
         d.elapsed_ms = C.cast(C.byref(elapsed), C.c_void_p)
         check(lib().hb_run(ck.handle, C.byref(d)))
         if timing is not None:
-            timing["kernel_ms"] = elapsed.value
+            timing["kernel_ms"] = timing.get("kernel_ms", 0.0) + elapsed.value if _tangents else elapsed.value
+            timing["kernel"] = ck
+        if _tangents:
+            return obj, grad, prog, p_mode, htypes
         return obj
+
+    # -- gradients: forward-mode tangents through the same fused stepper ------------------------------
+    def gradient(self, input, params, target, *, metric: str = "SSE", warm_up: int = 1, config=None, initstates=None,
+                 wrt: Optional[Sequence[str]] = None, n_members: Optional[int] = None, max_directions: int = 6,
+                 timing: Optional[dict] = None):
+        """`(loss, grads)`: the objective of `objective()` and its derivative w.r.t. the physical parameters — what the
+        reference obtains with `Zygote.gradient` through its ImmutableSolver (`/root/reference/README.md:161-187`; loss
+        `sum((sim - obs).^2)` = metric "SSE").  Forward mode: the stepper body is re-lowered with value + D tangents per
+        quantity (`hb_dual`, hb_math.cuh) and ONE launch returns the objective and D derivative rows per node; more than
+        `max_directions` parameters take several launches.  `grads[name]` has the shape of `params["params"][name]`
+        (scalar, `[ntypes]`, or `[n_members]` for ensembles) and is the derivative of `sum(loss)`: node types shared by
+        several nodes sum their nodes' derivatives.  `loss` is the per-node / per-member objective vector.
+        Models with neural components are not covered (hundreds of weights need the reverse-mode adjoint)."""
+        pdict = _as_componentvector(params)["params"]
+        names = list(wrt) if wrt is not None else [nm for nm in self.component.param_names]
+        if not names:
+            raise ValueError("no parameters to differentiate")
+        D = max(1, min(int(max_directions), HB_MAX_TANGENTS))
+        loss, grads = None, {}
+        for g0 in range(0, len(names), D):
+            group = tuple(names[g0:g0 + D])
+            obj, g, prog, p_mode, htypes = self.objective(input, params, target, metric=metric, warm_up=warm_up, config=config,
+                                                          initstates=initstates, n_members=n_members, timing=timing,
+                                                          _tangents=group)
+            loss = obj if loss is None else loss
+            for k, nm in enumerate(group):
+                modes = {int(p_mode[j]) for j, (pn, _) in enumerate(prog.param_slots) if pn == nm}
+                if len(modes) != 1:
+                    raise NotImplementedError(f"parameter {nm} is used under different htypes vectors")
+                mode = modes.pop()
+                if mode == 0:                                   # one value for every node
+                    val = g[k].sum()
+                    grads[nm] = val if np.ndim(pdict[nm]) == 0 else np.full(np.shape(pdict[nm]), val)
+                elif mode == 1:                                 # one value per node / member
+                    grads[nm] = g[k].copy()
+                else:                                           # gathered through 0-based htypes set (mode - 2)
+                    out = np.zeros(np.size(pdict[nm]), dtype=np.float64)
+                    np.add.at(out, htypes[mode - 2], g[k])
+                    grads[nm] = out
+        return loss, grads
 
 
 def run_component(component: Component, input, params, config=None, *, initstates=None, **kwargs):

@@ -93,6 +93,7 @@ class StepperProgram:
     nn_tensor: bool = False         # some dense chain is lowered to FP64 MMA fragments
     precision: str = "f64"          # "f64" (reference arithmetic) | "f32" (opt-in)
     uh_on_device: bool = False      # the prologue evaluates the unit-hydrograph ordinates (host table ignored)
+    tangents: List[str] = field(default_factory=list)   # gradient run: parameter name of each direction
 
 
 class _Builder:
@@ -252,13 +253,16 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                   uh_kmax: Optional[Sequence[int]] = None, fast: bool = True,
                   holes: Sequence[str] = (), nn_tensor: bool = False, precision: str = "f64",
                   uh_on_device: bool = False,
-                  component_min_values: Optional[Sequence[Optional[float]]] = None) -> StepperProgram:
+                  component_min_values: Optional[Sequence[Optional[float]]] = None,
+                  tangents: Optional[Sequence[str]] = None) -> StepperProgram:
     """Lower a per-node model (buckets, fluxes, neural fluxes, unit hydrographs) to one stepper
     body.  `rows`: subset/order of result rows to write (default: all = the reference result);
     `objective`: emit the last output row as `hb_sim` for the fused metric reduction instead of
     rows; `uh_kmax[u]`: ordinates per unit hydrograph (from the run's parameters);
     `component_min_values[c]`: the state floor of component c when the call carries per-component configs
-    (`/root/reference/src/model.jl:140-152`) — baked in as a literal; None = the run's `min_value` argument."""
+    (`/root/reference/src/model.jl:140-152`) — baked in as a literal; None = the run's `min_value` argument;
+    `tangents`: parameter names to differentiate the objective by (gradient run: the body's temporaries become
+    `auto` / `hb_dual`, see hb_math.cuh; objective mode, Float64, no neural components)."""
     comps, input_names, all_rows = _flatten(component)
     if component_min_values is not None and len(component_min_values) != len(comps):
         raise LoweringError("Component configs length must equal components length")
@@ -542,8 +546,9 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
         K = uh_kmax[u]
         th = [pro_ref(i) for i in thr]
         vnames = [[pro_ref(vi) for vi in row] for row in vals]     # materialise every operand at prologue scope first
-        pro.append(f"{{ const double ulag = {th[0]};")
-        pro.append(f"  const int uK = ulag > 0.0 ? (int)hb_min((double){K}, ceil(ulag)) : 0;")
+        # the ordinate COUNT is piecewise constant in the parameters: taken from the value (hb_val), no tangent
+        pro.append(f"{{ const double ulag = hb_val({th[0]});")
+        pro.append(f"  const int uK = ulag > 0.0 ? (int)hb_min({float(K)}, ceil(ulag)) : 0;")
         pro.append("  double us_prev = 0.0, usum = 0.0;")
         for k in range(1, K + 1):
             pro.append("  { double uval = 1.0, ubest = 1.0e300;")
@@ -607,6 +612,23 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
            "//@@HB:STEP\n" + "\n".join("        " + s for s in step) + "\n"
     if precision == "f32":
         body = _body_to_f32(body)
+    tangents = list(tangents) if tangents else []
+    if tangents:
+        if not objective or precision != "f64" or not fast:
+            raise LoweringError("a gradient run is an objective run in Float64 with the hb_math helpers")
+        if nets:
+            raise LoweringError("forward-mode gradients are for the physical parameters of bucket models; models with neural "
+                                "components have hundreds of weights and need the reverse-mode adjoint (not built)")
+        if uhs and not uh_on_device:
+            raise LoweringError("gradient runs of models with unit hydrographs need the ordinates evaluated on the device")
+        known = [nm for nm, _ in param_slots]
+        for nm in tangents:
+            if nm not in known:
+                raise LoweringError(f"Parameter {nm} does not exist in the model")
+        if len(set(tangents)) != len(tangents):
+            raise LoweringError("duplicate parameter in the gradient directions")
+        tdir = ", ".join(str(tangents.index(nm)) if nm in tangents else "-1" for nm in known) or "-1"
+        body = _body_to_tangent(body).replace("//@@HB:DEFINES\n", f"//@@HB:DEFINES\n#define HB_TDIR {{{tdir}}}\n", 1)
     n_ops = sum(1 for v in b.vals if v.id in live and v.mask != 0 and v.op not in ("const", "in", "param", "state")
                 and v.id not in carried)
     stats = {"step_values": n_ops, "prologue_values": len(pro), "carried": len(carried),
@@ -617,7 +639,25 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                           uh_kmax=list(uh_kmax), uh_htype_set=[htype_set(u) for u in uhs],
                           nn_layout=nn_layout, nn_words=sum(n for _, _, n in nn_layout), n_carry=len(carried),
                           objective=objective, stats=stats, nn_tensor=any(net_mma), precision=precision,
-                          uh_on_device=bool(uh_on_device and uhs))
+                          uh_on_device=bool(uh_on_device and uhs), tangents=tangents)
+
+
+def _body_to_tangent(body: str) -> str:
+    """Gradient run: every temporary takes the type of its initialiser (`auto`: plain double for forcing-only
+    subexpressions, hb_dual for anything downstream of a parameter or a state), accumulators become hb_dual."""
+    import re
+    out = []
+    for line in body.split("\n"):
+        if line.startswith("//@@HB:") or line.startswith("#define"):
+            out.append(line)
+            continue
+        if "ulag" in line:                       # plain-double bookkeeping of the unit-hydrograph prologue
+            out.append(line)
+            continue
+        line = re.sub(r"\bconst double uw\b", "const hb_dual uw", line)   # `cond ? dual : 0.0`
+        line = re.sub(r"\bconst double\b", "const auto", line)
+        out.append(re.sub(r"\bdouble\b", "hb_dual", line))
+    return "\n".join(out)
 
 
 def _expr_with(v: Val, a: List[str], fast: bool) -> str:

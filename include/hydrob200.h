@@ -56,7 +56,8 @@ enum {
 
 /* metrics of ext/HydroModelsOptimizationExt/HydroModelsOptimizationExt.jl:34-68 (value the
  * optimiser minimises: -KGE, -NSE, -LogKGE, MSE) */
-enum { HB_METRIC_MSE = 0, HB_METRIC_NSE = 1, HB_METRIC_KGE = 2, HB_METRIC_LOGKGE = 3 };
+enum { HB_METRIC_MSE = 0, HB_METRIC_NSE = 1, HB_METRIC_KGE = 2, HB_METRIC_LOGKGE = 3,
+       HB_METRIC_SSE = 4 /* sum of squared errors: the loss of the gradient example, README.md:161-187 */ };
 
 /* parameter addressing modes: value of parameter j for node n is
  *   mode 0: params[offset_j]                 scalar (2D single-node call)
@@ -66,6 +67,7 @@ enum { HB_PARAM_SCALAR = 0, HB_PARAM_PER_NODE = 1, HB_PARAM_GATHER = 2 };
 
 #define HB_MAX_PARAMS 96
 #define HB_MAX_UH 8
+#define HB_MAX_TANGENTS 16
 
 typedef struct hb_model_s *hb_model_t;
 
@@ -93,6 +95,10 @@ typedef struct {
                                     parameters are staged in shared memory + 1 KB scratch per warp */
     int32_t nodes_per_warp;      /* 0 / 32: one node per lane.  16: lanes l and l+16 carry the same node, so the warp-cooperative
                                     MLPs spread 16 basins over 32 lanes and a small, MLP-heavy run gets twice the warps */
+    int32_t n_tangents;          /* D > 0: gradient run (HB_OUT_OBJECTIVE, Float64, no MLPs): the body was lowered with D
+                                    parameter directions and the kernel also returns d objective / d direction per node —
+                                    the forward-mode counterpart of the reference's Zygote gradient through its
+                                    ImmutableSolver (README.md:161-187) */
 } hb_stepper_spec;
 
 /* One forward run.  Pointers are HOST pointers for hb_run and DEVICE pointers for
@@ -121,6 +127,7 @@ typedef struct {
     double *final_states;        /* [S][N] or NULL: states after step T (resume / BMI)        */
     double *uh_hist_out;         /* [sum_u (kmax_u-1)][N] or NULL                             */
     float *elapsed_ms;           /* optional HOST pointer: device time of the kernel(s)       */
+    double *gradient;            /* gradient runs (spec.n_tangents = D): [D][N], d objective[n] / d direction k */
 } hb_run_desc;
 
 typedef struct {

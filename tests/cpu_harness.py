@@ -21,7 +21,13 @@ _SRC = r'''
 #include <cstdint>
 typedef long long i64;
 #define HB_HOST_TEST 1
+#define HB_TANGENTS @TANGENTS@
 #include "@MATH_HEADER@"
+#if HB_TANGENTS > 0
+typedef hb_dual treal;
+#else
+typedef double treal;
+#endif
 #define __device__
 #define __forceinline__ inline
 #define __restrict__
@@ -32,15 +38,19 @@ static const double* hb_nn_host = 0;      /* stands in for the kernel's __consta
 @HELPERS@
 extern "C" int run(i64 N, i64 T, int shared, const double* in, const double* params, const int* p_off,
                    const int* p_mode, const int* htypes, const double* init, const double* uhw,
-                   const double* nn, double minv, double* out, double* sim, double* final_states) {
+                   const double* nn, double minv, double* out, double* sim, double* final_states, double* dsim) {
     const double* sNN = nn; (void)sNN; hb_nn_host = nn;
     for (i64 n = 0; n < N; ++n) {
-        double hb_p[HB_ARR(HB_NP)], hb_u[HB_ARR(HB_S)], hb_uhw[HB_ARR(HB_UHW_TOTAL)], hb_uhh[HB_ARR(HB_UHH_TOTAL)], hb_c[HB_ARR(HB_NC)];
+        treal hb_p[HB_ARR(HB_NP)], hb_u[HB_ARR(HB_S)], hb_uhw[HB_ARR(HB_UHW_TOTAL)], hb_uhh[HB_ARR(HB_UHH_TOTAL)], hb_c[HB_ARR(HB_NC)];
         for (int j = 0; j < HB_NP; ++j) {
             i64 idx = p_off[j];
             if (p_mode[j] == 1) idx += n; else if (p_mode[j] >= 2) idx += htypes[(i64)(p_mode[j] - 2) * N + n];
             hb_p[j] = params[idx];
         }
+#if HB_TANGENTS > 0
+        { const int tdir[HB_ARR(HB_NP)] = HB_TDIR;
+          for (int j = 0; j < HB_NP; ++j) for (int k = 0; k < HB_TANGENTS; ++k) hb_p[j].d[k] = tdir[j] == k ? 1.0 : 0.0; }
+#endif
         for (int s = 0; s < HB_S; ++s) hb_u[s] = init ? init[(i64)s * N + n] : 0.0;
         for (int k = 0; k < HB_UHW_TOTAL; ++k) hb_uhw[k] = uhw[(i64)k * N + n];
         for (int k = 0; k < HB_UHH_TOTAL; ++k) hb_uhh[k] = 0.0;
@@ -48,14 +58,18 @@ extern "C" int run(i64 N, i64 T, int shared, const double* in, const double* par
         (void)hb_p; (void)hb_u; (void)hb_uhw; (void)hb_uhh; (void)hb_c; (void)hb_minv;
 @PROLOGUE@
         for (i64 t = 0; t < T; ++t) {
-            double hb_x[HB_ARR(HB_V)], hb_out[HB_ARR(HB_R)], hb_sim = 0.0;
+            double hb_x[HB_ARR(HB_V)], hb_out[HB_ARR(HB_R)];
+            treal hb_sim = 0.0;
             for (int v = 0; v < HB_V; ++v) hb_x[v] = shared ? in[t * HB_V + v] : in[(t * N + n) * HB_V + v];
             (void)hb_out; (void)hb_sim;
 @STEP@
             for (int r = 0; r < HB_R; ++r) out[(t * N + n) * HB_R + r] = hb_out[r];
-            if (sim) sim[t * N + n] = hb_sim;
+            if (sim) sim[t * N + n] = hb_val(hb_sim);
+#if HB_TANGENTS > 0
+            if (dsim) for (int k = 0; k < HB_TANGENTS; ++k) dsim[((i64)k * T + t) * N + n] = hb_sim.d[k];
+#endif
         }
-        if (final_states) for (int s = 0; s < HB_S; ++s) final_states[(i64)s * N + n] = hb_u[s];
+        if (final_states) for (int s = 0; s < HB_S; ++s) final_states[(i64)s * N + n] = hb_val(hb_u[s]);
     }
     return 0;
 }
@@ -74,7 +88,7 @@ def _sections(body: str):
 
 
 def run_body_on_cpu(eng, input, params, config=None, initstates=None, rows=None, objective=False,
-                    ensemble_members=None, return_final_states=False, uh_on_device=False, uh_kmax=None):
+                    ensemble_members=None, return_final_states=False, uh_on_device=False, uh_kmax=None, tangents=None):
     """Mirror of `B200Model.__call__` that executes the generated body with g++ instead of NVRTC."""
     from hydromodels_jl_b200.components import normalize_config
     from hydromodels_jl_b200.lowering import lower_stepper
@@ -92,7 +106,7 @@ def run_body_on_cpu(eng, input, params, config=None, initstates=None, rows=None,
     probe = lower_stepper(eng.component, rows=rows, objective=objective, fast=eng.fast)
     kmax = uh_kmax or eng.prepare(probe, params, N, ensemble=ensemble)[5]
     prog = lower_stepper(eng.component, rows=rows, objective=objective, uh_kmax=kmax or None, fast=eng.fast, uh_on_device=uh_on_device,
-                         component_min_values=cmin)
+                         component_min_values=cmin, tangents=tangents)
     flat, p_off, p_mode, htypes, uhw, _, nn = eng.prepare(prog, params, N, ensemble=ensemble)
     if uh_on_device and uhw:
         uhw = [np.full((k, N), np.nan) for k in kmax]       # the prologue must overwrite every ordinate
@@ -106,7 +120,8 @@ def run_body_on_cpu(eng, input, params, config=None, initstates=None, rows=None,
         f"#define HB_UHH_TOTAL {sum(k - 1 for k in prog.uh_kmax)}", secs.get("DEFINES", "")])
     hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hydromodels.jl_b200", "csrc",
                        "templates", "hb_math.cuh")
-    src = (_SRC.replace("@DEFINES@", defines).replace("@MATH_HEADER@", hdr).replace("@HELPERS@", secs.get("HELPERS", ""))
+    D = len(tangents) if tangents else 0
+    src = (_SRC.replace("@DEFINES@", defines).replace("@TANGENTS@", str(D)).replace("@MATH_HEADER@", hdr).replace("@HELPERS@", secs.get("HELPERS", ""))
            .replace("@PROLOGUE@", secs.get("PROLOGUE", "")).replace("@STEP@", secs.get("STEP", "")))
     tag = hashlib.sha1((src + open(hdr).read()).encode()).hexdigest()[:16]
     d = os.path.join(tempfile.gettempdir(), "hb_cpu_harness")
@@ -123,9 +138,12 @@ def run_body_on_cpu(eng, input, params, config=None, initstates=None, rows=None,
     S = len(prog.state_names)
     final = np.zeros((S, N)) if return_final_states else None
     P = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-    L.run.argtypes = [C.c_int64, C.c_int64, C.c_int] + [C.c_void_p] * 8 + [C.c_double] + [C.c_void_p] * 3
+    dsim = np.zeros((D, T, N)) if D else None
+    L.run.argtypes = [C.c_int64, C.c_int64, C.c_int] + [C.c_void_p] * 8 + [C.c_double] + [C.c_void_p] * 4
     L.run(N, T, 1 if ensemble else 0, P(inp), P(flat), P(p_off), P(p_mode), P(htypes), P(init), P(uhw_flat),
-          P(nn if nn is not None else np.zeros(1)), cfg.min_value, P(out), P(sim), P(final))
+          P(nn if nn is not None else np.zeros(1)), cfg.min_value, P(out), P(sim), P(final), P(dsim))
+    if D:
+        return sim.T.copy(), np.ascontiguousarray(dsim.transpose(0, 2, 1))   # [N, T], [D, N, T]
     if objective:
         return sim.T.copy()          # [N, T] simulated last row
     if return_final_states:

@@ -1,0 +1,91 @@
+"""Gradients (`/root/reference/README.md:161-187`): the complex-step oracle is pinned to the
+forward oracle by finite differences; the tangent (hb_dual) lowering of the stepper body, compiled with g++ through the
+test harness, must reproduce the oracle's derivatives."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import hydromodels_jl_b200 as hm
+from hydromodels_jl_b200 import synthetic as sy
+from hydromodels_jl_b200.lowering import LoweringError, lower_stepper
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+sys.path.insert(0, os.path.dirname(__file__))
+import hydro_oracle as ho  # noqa: E402
+from cpu_harness import run_body_on_cpu  # noqa: E402
+
+
+def _case(name, N, T, ntypes):
+    ht = np.arange(N) % ntypes + 1
+    model = getattr(hm.models, name)(htypes=ht)
+    inp = sy.forcing(name, 0, N, T)
+    p = {"params": sy.parameters(name, 0, ntypes)}
+    init = {k: np.full(N, v) for k, v in sy.INIT[name].items()}
+    target = 5.0 * np.random.default_rng(3).random(T)
+    return model, ht, inp, p, init, target
+
+
+def _sse(model, inp, p, init, target):
+    sim = ho.run_model(model, inp, p, None, init)[-1]
+    return ((sim - target) ** 2).sum()
+
+
+def test_complex_step_oracle_agrees_with_finite_differences_of_the_forward_oracle():
+    model, ht, inp, p, init, target = _case("exphydro", 6, 150, 3)
+    loss, g = ho.loss_gradient(model, inp, p, target, "sse", 1, None, init)
+    sim = ho.run_model(model, inp, p, None, init)[-1]
+    np.testing.assert_allclose(loss, ((sim - target) ** 2).sum(axis=1), rtol=1e-13)
+    for nm in model.param_names:
+        for k in range(3):
+            h = 1e-6 * abs(p["params"][nm][k])
+            pp = {"params": {a: np.array(b, dtype=float) for a, b in p["params"].items()}}
+            pm = {"params": {a: np.array(b, dtype=float) for a, b in p["params"].items()}}
+            pp["params"][nm][k] += h
+            pm["params"][nm][k] -= h
+            fd = (_sse(model, inp, pp, init, target) - _sse(model, inp, pm, init, target)) / (2 * h)
+            assert abs(g[nm][k] - fd) <= 1e-5 * abs(fd) + 1e-6, (nm, k, g[nm][k], fd)
+
+
+@pytest.mark.parametrize("name", ["exphydro", "hbv"])
+def test_tangent_body_matches_the_oracle_gradient(name):
+    model, ht, inp, p, init, target = _case(name, 5, 120, 5)
+    names = list(model.param_names)[:6]
+    sim, dsim = run_body_on_cpu(hm.B200Model(model), inp, p, None, init, objective=True, tangents=names)
+    loss, g = ho.loss_gradient(model, inp, p, target, "sse", 1, None, init, wrt=names)
+    np.testing.assert_allclose(((sim - target) ** 2).sum(axis=1), loss, rtol=1e-10)
+    for k, nm in enumerate(names):
+        got = (2.0 * (sim - target) * dsim[k]).sum(axis=1)           # d SSE_n / d p_n, types are 1:1 with nodes here
+        np.testing.assert_allclose(got, g[nm], rtol=1e-8, atol=1e-9 * np.abs(g[nm]).max())
+
+
+def test_tangent_body_of_gr4j_differentiates_through_the_device_unit_hydrographs():
+    N, T = 3, 150
+    model, ht, inp, p, init, target = _case("gr4j", N, T, N)
+    p["params"]["x4"] = np.array([1.37, 1.82, 2.41])                 # away from the integer breakpoints of the ordinates
+    names = ["x1", "x2", "x3", "x4"]
+    eng = hm.B200Model(model)
+    kmax = eng.prepare(lower_stepper(model, objective=True), p, N)[5]
+    sim, dsim = run_body_on_cpu(eng, inp, p, None, init, objective=True, tangents=names, uh_on_device=True, uh_kmax=kmax)
+    np.testing.assert_allclose(sim, ho.run_model(model, inp, p, None, init)[-1], rtol=1e-10, atol=1e-12)
+    for k, nm in enumerate(names):
+        h = 1e-6 * np.abs(p["params"][nm])
+        pp = {"params": dict(p["params"])}
+        pm = {"params": dict(p["params"])}
+        pp["params"][nm] = p["params"][nm] + h
+        pm["params"][nm] = p["params"][nm] - h
+        fd = (ho.run_model(model, inp, pp, None, init)[-1] - ho.run_model(model, inp, pm, None, init)[-1]) / (2 * h[:, None])
+        np.testing.assert_allclose(dsim[k], fd, rtol=2e-5, atol=2e-6 * np.abs(fd).max())
+
+
+def test_gradient_lowering_rejects_what_it_does_not_cover():
+    et, q = hm.models.m50_chains()
+    with pytest.raises(LoweringError, match="neural"):
+        lower_stepper(hm.models.m50(htypes=[1, 2]), objective=True, tangents=["f"])
+    with pytest.raises(LoweringError, match="does not exist"):
+        lower_stepper(hm.models.exphydro(htypes=[1, 2]), objective=True, tangents=["nope"])
+    with pytest.raises(LoweringError, match="objective run"):
+        lower_stepper(hm.models.exphydro(htypes=[1, 2]), tangents=["f"])
+    with pytest.raises(LoweringError, match="ordinates evaluated on the device"):
+        lower_stepper(hm.models.gr4j(htypes=[1, 2]), objective=True, tangents=["x4"], uh_kmax=[2, 4])
