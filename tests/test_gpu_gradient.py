@@ -57,7 +57,8 @@ def test_hbv_gradient_takes_several_launches_and_per_node_targets():
     for nm in model.param_names:
         _close(g[nm], ref_g[nm])
     sub = eng.gradient(inp, p, target, metric="SSE", initstates=init, wrt=["FC", "BETA"])[1]
-    assert list(sub) == ["FC", "BETA"] and np.array_equal(sub["FC"], g["FC"])
+    assert list(sub) == ["FC", "BETA"]
+    _close(sub["FC"], g["FC"], 1e-11)                # another kernel (2 directions, other FMA contractions): not bitwise
 
 
 def test_ensemble_gradient_equals_the_multinode_gradient():
