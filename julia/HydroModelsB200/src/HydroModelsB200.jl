@@ -20,6 +20,7 @@ struct HbStepperSpec
     struct_size::Int32; n_inputs::Int32; n_rows::Int32; n_states::Int32; n_params::Int32; n_uh::Int32
     uh_kmax::NTuple{8,Int32}; nn_words::Int32; output_mode::Int32; metric::Int32; shared_forcing::Int32
     block_threads::Int32; stages::Int32; max_registers::Int32; precision::Int32; nn_tensor::Int32
+    nodes_per_warp::Int32; n_tangents::Int32
 end
 
 struct HbRunDesc
@@ -29,7 +30,7 @@ struct HbRunDesc
     initstates::Ptr{Float64}; uh_weights::Ptr{Float64}; uh_hist_in::Ptr{Float64}; nn_params::Ptr{Float64}
     target::Ptr{Float64}; target_per_node::Int32; warm_up::Int32; min_value::Float64
     out::Ptr{Cvoid}; objective::Ptr{Float64}; final_states::Ptr{Float64}; uh_hist_out::Ptr{Float64}
-    elapsed_ms::Ptr{Float32}
+    elapsed_ms::Ptr{Float32}; gradient::Ptr{Float64}
 end
 
 function hb_check(rc::Integer)
@@ -163,7 +164,7 @@ get_nn_names(m::B200Model) = get_nn_names(m.model)
 function B200Model(model::HydroModel; fluxes_of, htypes::Vector{Int})
     plan = lower_stepper(model; fluxes_of=fluxes_of)
     spec = Ref(HbStepperSpec(sizeof(HbStepperSpec), length(plan.input_names), length(plan.row_names), length(plan.state_names),
-                             length(plan.param_names), 0, ntuple(_ -> Int32(0), 8), 0, 0, 0, 0, 0, 0, 0, 0, 0))
+                             length(plan.param_names), 0, ntuple(_ -> Int32(0), 8), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     hb_check(ccall((:hb_compile_stepper, LIB), Cint, (Ref{HbStepperSpec}, Cstring, Ref{Ptr{Cvoid}}), spec, plan.body, h))
     B200Model(model, h[], plan, htypes)
@@ -198,7 +199,7 @@ function (m::B200Model)(input::AbstractArray{Float64,3}, params::ComponentVector
     GC.@preserve inp flat offs modes ht0 init out begin
         d = Ref(HbRunDesc(sizeof(HbRunDesc), 1, N, T, pointer(inp), pointer(flat), length(flat), pointer(offs), pointer(modes),
                           pointer(ht0), pointer(init), C_NULL, C_NULL, C_NULL, C_NULL, 0, 1, cfg.min_value,
-                          pointer(out), C_NULL, C_NULL, C_NULL, C_NULL))
+                          pointer(out), C_NULL, C_NULL, C_NULL, C_NULL, C_NULL))
         hb_check(ccall((:hb_run, LIB), Cint, (Ptr{Cvoid}, Ref{HbRunDesc}), m.handle, d))
     end
     return out
