@@ -17,6 +17,12 @@ Unit hydrographs: a normal run reads host-built ordinates, but a search changes 
 generation, so the device loop compiles the stepper with `uh_on_device` — the kernel prologue evaluates the S-curve
 ordinates of each member from its own parameters (`UnitHydrograph.weights`), with the number of ordinates reserved
 from the parameter bounds.
+
+Gradient-based calibration: the reference enables it with `adtype=Optimization.AutoForwardDiff()` and a gradient solver
+(`ext/HydroModelsOptimizationExt/README.md:107-120`, `…OptimizationExt.jl:193-197`).  Here `prob.gradient_batch(P)` returns
+the objective AND its derivatives for a whole set of parameter vectors from one forward-mode launch per 6 parameters
+(`B200Model.gradient`), and `solve(prob, MultiStartAdam(...))` runs projected Adam from many starting points at once — the
+starts are the ensemble members of that launch.
 """
 from __future__ import annotations
 
@@ -35,6 +41,18 @@ class DifferentialEvolution:
     popsize: int = 1024
     F: float = 0.7
     CR: float = 0.9
+    seed: int = 0
+
+
+@dataclass
+class MultiStartAdam:
+    """Projected Adam in box-normalised coordinates (x = (p - lb)/(ub - lb), clipped to [0, 1]) from `n_starts` uniformly
+    drawn starting points, all advanced together: one gradient launch per iteration."""
+    n_starts: int = 256
+    lr: float = 0.02
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
     seed: int = 0
 
 
@@ -104,6 +122,20 @@ class OptimizationProblem:
         return self.engine.objective(self.input, self._params(P), self.target, metric=self.metric, warm_up=self.warm_up,
                                      config=self.config, initstates=init, n_members=n)
 
+    def gradient_batch(self, P):
+        """`(objective[n], d objective / d P [n, D])` for every row of `P[n, D]` — the reference's
+        `OptimizationFunction(objective, AutoForwardDiff())` evaluated for a whole set of vectors at once."""
+        P = np.atleast_2d(np.asarray(P, dtype=np.float64))
+        n = P.shape[0]
+        init = None if self.initstates is None else {k: np.full(n, v) for k, v in self.initstates.items()}
+        obj, g = self.engine.gradient(self.input, self._params(P), self.target, metric=self.metric, warm_up=self.warm_up,
+                                      config=self.config, initstates=init, n_members=n, wrt=self.calibrated)
+        return obj, np.stack([g[nm] for nm in self.calibrated], axis=1)
+
+    def gradient(self, p):
+        obj, g = self.gradient_batch(np.asarray(p, dtype=np.float64)[None, :])
+        return float(obj[0]), g[0]
+
     def objective(self, p) -> float:
         """The reference's closure `(p, c) -> loss(target[warm_up:end], component(input, p, c)[end, warm_up:end])`."""
         return float(self.objective_batch(np.asarray(p, dtype=np.float64)[None, :])[0])
@@ -131,10 +163,53 @@ def _uh_kmax_from_bounds(prob: OptimizationProblem) -> List[int]:
     return out
 
 
-def solve(prob: OptimizationProblem, alg: Optional[DifferentialEvolution] = None, *, maxiters: int = 100) -> Solution:
-    """Differential evolution on the device; returns the best member after `maxiters` generations."""
+def _solve_adam(prob: OptimizationProblem, alg: MultiStartAdam, maxiters: int, grad_fn=None) -> Solution:
+    """`grad_fn(P) -> (objective[n], gradient[n, D])` defaults to the device (`prob.gradient_batch`); the CPU tests pass
+    the oracle's to exercise this loop without a GPU."""
+    import time
+    grad_fn = grad_fn or prob.gradient_batch
+    N, D = int(alg.n_starts), len(prob.calibrated)
+    if N < 1 or D == 0:
+        raise ValueError("need at least one start and one calibrated parameter")
+    span = prob.ub - prob.lb
+    rng = np.random.default_rng(alg.seed)
+    X = rng.random((N, D))
+    m, v = np.zeros((N, D)), np.zeros((N, D))
+    best_f, best_x = np.full(N, np.inf), X.copy()
+    history = np.empty(maxiters + 1)
+    t0 = time.perf_counter()
+    for it in range(maxiters + 1):
+        f, g = grad_fn(prob.lb + X * span)
+        f = np.where(np.isfinite(f), f, np.inf)
+        better = f < best_f
+        best_f = np.where(better, f, best_f)
+        best_x[better] = X[better]
+        history[it] = best_f.min()
+        if it == maxiters:
+            break
+        gx = np.where(np.isfinite(g), g, 0.0) * span                 # chain rule into the normalised coordinates
+        m = alg.beta1 * m + (1 - alg.beta1) * gx
+        v = alg.beta2 * v + (1 - alg.beta2) * gx * gx
+        mh, vh = m / (1 - alg.beta1 ** (it + 1)), v / (1 - alg.beta2 ** (it + 1))
+        X = np.clip(X - alg.lr * mh / (np.sqrt(vh) + alg.eps), 0.0, 1.0)
+    elapsed = time.perf_counter() - t0
+    population = prob.lb + best_x * span
+    best = int(np.argmin(best_f))
+    params = dict(prob.fixed)
+    params.update({nm: float(population[best, j]) for j, nm in enumerate(prob.calibrated)})
+    per_eval = -(-D // 6)
+    return Solution(u=population[best].copy(), params=params, objective=float(best_f[best]), history=history,
+                    n_evaluations=N * (maxiters + 1), population=population, fitness=best_f,
+                    gpu_launches=per_eval * (maxiters + 1), elapsed_s=elapsed)
+
+
+def solve(prob: OptimizationProblem, alg=None, *, maxiters: int = 100) -> Solution:
+    """`solve(prob, alg; maxiters)`: differential evolution on the device (default) — returns the best member after
+    `maxiters` generations — or `MultiStartAdam` on the device gradients."""
     import time
     from .engine import DeviceBuffer, DeviceRun, check, lib
+    if isinstance(alg, MultiStartAdam):
+        return _solve_adam(prob, alg, maxiters)
     alg = alg or DifferentialEvolution()
     N, D = int(alg.popsize), len(prob.calibrated)
     if N < 4:

@@ -135,3 +135,35 @@ def test_device_de_on_a_unit_hydrograph_model():
     host = prob.objective_batch(sol.population)
     assert np.allclose(sol.fitness, host, rtol=1e-9, atol=1e-12)
     assert abs(sol.params["x4"] - truth["x4"]) < 0.1
+
+
+def test_gradient_batch_and_multi_start_adam_recover_planted_parameters():
+    """`adtype=AutoForwardDiff()` + a gradient solver in the reference (`ext/HydroModelsOptimizationExt/README.md:107-120`):
+    here one forward-mode launch differentiates the objective of every start."""
+    T = 730
+    model = hm.models.exphydro()
+    names = list(model.get_param_names())
+    inp = sy.forcing("exphydro", 0, 1, T)[:, 0, :]
+    lb = np.array([-3.0, 0.0, 0.5, 500.0, 5.0, 0.005])
+    ub = np.array([0.0, 3.0, 5.0, 2500.0, 40.0, 0.1])
+    truth = np.array([-2.09, 0.17, 2.674, 1709.46, 18.47, 0.0167])
+    init = dict(snowpack=0.0, soilwater=1303.0)
+    target = model(inp, {"params": dict(zip(names, truth))}, initstates=init)[-1]
+    prob = cal.OptimizationProblem(model, inp, target, metric="NSE", warm_up=61, lb_pas=lb, ub_pas=ub, default_initstates=init,
+                                   fixed_params={"Tmin": -2.09})
+    assert prob.calibrated == names[1:]
+    P = lb[1:] + np.random.default_rng(0).random((50, 5)) * (ub[1:] - lb[1:])
+    f, g = prob.gradient_batch(P)
+    np.testing.assert_allclose(f, prob.objective_batch(P), rtol=1e-11, atol=1e-13)
+    j, h = 2, 1e-4 * (ub[3] - lb[3])                                   # Smax by central differences of the objective kernel
+    Pp, Pm = P.copy(), P.copy()
+    Pp[:, j] += h
+    Pm[:, j] -= h
+    fd = (prob.objective_batch(Pp) - prob.objective_batch(Pm)) / (2 * h)
+    np.testing.assert_allclose(g[:, j], fd, rtol=2e-4, atol=1e-6 * np.abs(fd).max())
+    f1, g1 = prob.gradient(P[3])
+    assert abs(f1 - f[3]) < 1e-12 and np.allclose(g1, g[3], rtol=1e-10)
+    sol = cal.solve(prob, cal.MultiStartAdam(n_starts=256, lr=0.03, seed=2), maxiters=80)
+    assert np.all(np.diff(sol.history) <= 0)
+    assert sol.objective < -0.97, sol.objective                       # NSE > 0.97 from gradients alone
+    assert abs(prob.objective(sol.u) - sol.objective) < 1e-10 and sol.params["Tmin"] == -2.09

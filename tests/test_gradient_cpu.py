@@ -89,3 +89,38 @@ def test_gradient_lowering_rejects_what_it_does_not_cover():
         lower_stepper(hm.models.exphydro(htypes=[1, 2]), tangents=["f"])
     with pytest.raises(LoweringError, match="ordinates evaluated on the device"):
         lower_stepper(hm.models.gr4j(htypes=[1, 2]), objective=True, tangents=["x4"], uh_kmax=[2, 4])
+
+
+def test_multi_start_adam_loop_with_the_oracle_as_the_gradient():
+    """`solve(prob, MultiStartAdam())` host logic (projected Adam in box-normalised coordinates, best-so-far bookkeeping)
+    driven by the oracle's gradient instead of the device's."""
+    from hydromodels_jl_b200 import calibration as cal
+    T, n = 150, 8
+    names = list(hm.models.exphydro().get_param_names())
+    inp = sy.forcing("exphydro", 0, 1, T)[:, 0, :]
+    lb = np.array([-3.0, 0.0, 0.5, 500.0, 5.0, 0.005])
+    ub = np.array([0.0, 3.0, 5.0, 2500.0, 40.0, 0.1])
+    truth = dict(zip(names, [-2.09, 0.17, 2.674, 1709.46, 18.47, 0.0167]))
+    init = dict(snowpack=0.0, soilwater=1303.0)
+    one = hm.models.exphydro(htypes=[1])
+    target = ho.run_model(one, inp[:, None, :], {"params": {k: np.array([v]) for k, v in truth.items()}}, None,
+                          {k: np.array([v]) for k, v in init.items()})[-1, 0]
+    prob = cal.OptimizationProblem.__new__(cal.OptimizationProblem)      # no engine: the loop only needs the box
+    prob.calibrated, prob.fixed, prob.lb, prob.ub = names, {}, lb, ub
+    calls = []
+
+    def grad_fn(P):
+        assert np.all(P >= lb) and np.all(P <= ub)
+        calls.append(len(P))
+        m = hm.models.exphydro(htypes=np.arange(1, len(P) + 1))
+        f, g = ho.loss_gradient(m, np.repeat(inp[:, None, :], len(P), axis=1), {"params": {k: P[:, j].copy() for j, k in enumerate(names)}},
+                                target, "nse", 30, None, {k: np.full(len(P), v) for k, v in init.items()})
+        return f, np.stack([g[k] for k in names], axis=1)
+
+    sol = cal._solve_adam(prob, cal.MultiStartAdam(n_starts=n, lr=0.03, seed=1), 12, grad_fn)
+    assert calls == [n] * 13 and sol.history.shape == (13,)
+    assert np.all(np.diff(sol.history) <= 0) and sol.history[-1] < sol.history[0] - 0.5
+    assert sol.objective == sol.history[-1] == sol.fitness.min()
+    f_check, _ = grad_fn(sol.u[None, :])
+    assert abs(f_check[0] - sol.objective) < 1e-12
+    assert set(sol.params) == set(names) and sol.population.shape == (n, 6)
