@@ -349,6 +349,32 @@ def bench_calibration(args):
     return 0
 
 
+def _fp64_instructions_per_step(ck):
+    """FP64-pipe instructions (DFMA/DMUL/DADD/DSETP) inside the time loop of a compiled stepper, counted in its SASS
+    (static count of the largest backward-branch region; a few belong to rarely taken division slow paths)."""
+    import re, subprocess, tempfile
+    try:
+        with tempfile.NamedTemporaryFile(suffix=".cubin") as f:
+            f.write(ck.cubin()); f.flush()
+            sass = subprocess.run(["cuobjdump", "-sass", f.name], capture_output=True, text=True, timeout=120).stdout
+        rows = []
+        for l in sass.splitlines():
+            m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
+            if m:
+                rows.append((int(m.group(1), 16), m.group(2).strip()))
+        loops = []
+        for a, ins in rows:
+            if "BRA" in ins:
+                t = re.findall(r"0x([0-9a-f]+)", ins)
+                if t and int(t[-1], 16) < a:
+                    loops.append((int(t[-1], 16), a))
+        lo, hi = max(loops, key=lambda x: x[1] - x[0])
+        ops = [re.sub(r"^@!?\w+\s+", "", ins).split()[0].split(".")[0] for a, ins in rows if lo <= a <= hi]
+        return sum(o in ("DFMA", "DMUL", "DADD", "DSETP") for o in ops), len(ops)
+    except Exception:
+        return None, None
+
+
 def bench_gradient(args):
     """SURVEY.md §8f row 3 (second half): d NSE / d parameters of an ExpHydro calibration ensemble, 262 144 members x 10
     years, 6 directions per launch (forward-mode tangents in the fused stepper) beside the plain objective launch."""
@@ -372,12 +398,24 @@ def bench_gradient(args):
             ms_g.append(tg["kernel_ms"]); ms_o.append(to["kernel_ms"])
     info = tg["kernel"].info()
     mg, mo = float(np.mean(ms_g)), float(np.mean(ms_o))
+    import ctypes as C
+    pk = C.c_double()
+    hm.engine.lib().hb_probe_fp64_tflops(C.byref(pk))
+    roof = {}
+    for tag, ck, ms in (("gradient", tg["kernel"], mg), ("objective", to["kernel"], mo)):
+        fp, tot = _fp64_instructions_per_step(ck)
+        if fp:
+            rate = fp * N * T / (ms * 1e-3)                  # FP64-pipe thread-instructions per second
+            roof[tag] = {"fp64_instructions_per_step": fp, "instructions_per_step": tot, "achieved": rate / 1e12,
+                         "peak": pk.value / 2.0, "unit": "T FP64 instr/s", "frac": rate / 1e12 / (pk.value / 2.0)}
     print(json.dumps({"metric": "member-timesteps/sec of a gradient run (objective + 6 derivatives per member)", "value": N * T / (mg * 1e-3),
                       "unit": "member-timesteps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mg,
                       "higher_is_better": True, "dtype": "f64", "data": "synthetic",
                       "config": {"workload": "gradient_exphydro_262144x3650", "members": N, "timesteps": T, "directions": 6, "metric": "NSE"},
                       "objective_only_ms": mo, "gradient_over_objective": mg / mo, "registers": info["registers_per_thread"],
                       "spill_bytes": info["local_bytes_per_thread"], "blocks_per_sm": info["max_blocks_per_sm"],
+                      "roofline": {"bound": "fp64 issue", "kernel": "hb_stepper (HB_TANGENTS 6)", "peak_source": "measured DFMA probe (hb_probe_fp64_tflops) / 2 flop",
+                                   **roof},
                       "max_abs_loss_difference_vs_objective_kernel": float(np.abs(loss - obj).max()), "gpu_launches": 2 * (args.warmup + args.steps),
                       "timing": "CUDA events around each kernel (hb_run elapsed_ms)"}))
     return 0
