@@ -31,6 +31,29 @@ def test_struct_sizes_match_header():
     assert "cp.async.bulk" in ck.source()
 
 
+def test_ctypes_mirrors_have_the_layout_of_the_header(tmp_path):
+    """Every field of every struct: offsetof/sizeof from a C compile of include/hydrob200.h against the ctypes mirrors."""
+    import subprocess
+    pairs = {"hb_stepper_spec": engine.StepperSpec, "hb_run_desc": engine.RunDesc, "hb_kernel_info": engine.KernelInfo,
+             "hb_route_spec": engine.RouteSpec, "hb_route_desc": engine.RouteDesc, "hb_grid_spec": engine.GridSpec,
+             "hb_grid_desc": engine.GridDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hydrob200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for f, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert int(got[f"{cname}.{f}"]) == getattr(cls, f).offset, f"{cname}.{f}"
+
+
 def test_nvrtc_error_is_reported():
     from hydromodels_jl_b200.lowering import lower_stepper
     prog = lower_stepper(hm.models.exphydro())
