@@ -165,13 +165,15 @@ template <int HP>
 __global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in, long long T, int H, long long nnz,
                                                             const int *__restrict__ row_ptr, const int *__restrict__ src,
                                                             const double *__restrict__ w, const double *__restrict__ in,
-                                                            double *__restrict__ out) {
+                                                            const double *__restrict__ xt, long long Tp, double *__restrict__ out) {
     constexpr int TT = HB_IRF_TT;
     constexpr int BT = 8 * TT;                         // time steps per block (8 warps)
     constexpr int WP = BT + HP;                        // staged input window: steps [t_blk - HP, t_blk + BT)
     extern __shared__ __align__(16) double hb_irf_smem[];
-    double(*sx)[WP][32] = reinterpret_cast<double(*)[WP][32]>(hb_irf_smem);                       // [2][WP][32]
-    double(*sw)[HP][32] = reinterpret_cast<double(*)[HP][32]>(hb_irf_smem + 2 * WP * 32);        // [2][HP][32]
+    // pitch 33: the time-major staging below writes a column (32 consecutive steps of ONE source) per warp instruction and
+    // the arithmetic reads a row (32 sources at one step) — both conflict-free with an odd pitch
+    double(*sx)[WP][33] = reinterpret_cast<double(*)[WP][33]>(hb_irf_smem);                       // [2][WP][33]
+    double(*sw)[HP][32] = reinterpret_cast<double(*)[HP][32]>(hb_irf_smem + 2 * WP * 33);        // [2][HP][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = blockIdx.x * 32 + lane;
     const long long t_blk = (long long)blockIdx.y * BT;
@@ -187,11 +189,24 @@ __global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in,
     auto stage = [&](int r, int buf) {                 // this thread's share of row r: window rows / lags warp, warp+8, ...
         const bool has = r < nrows;
         const long long row = (long long)r_begin + r;
-        const double *x = in + (has ? src[row] : 0);
-        for (int m = warp; m < WP; m += 8) {
-            const long long t = t_blk - HP + m;
-            const bool ok = has && t >= 0 && t < T;
-            hb_cp_async8(&sx[buf][m][lane], ok ? x + t * n_in : in, ok);
+        const int my_src = has ? src[row] : -1;
+        if (xt) {
+            // time-contiguous copy of the input (hb_irf_transpose: xt[n][HP + t], zero padded): a warp fetches 32 consecutive
+            // steps of one source per instruction — full 32-byte sectors instead of one 8-byte value per sector
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = warp + 8 * i;            // destination (lane index) whose source this warp stages
+                const int sj = __shfl_sync(0xffffffffu, my_src, j);
+                const double *xrow = xt + (long long)(sj < 0 ? 0 : sj) * Tp + t_blk;   // padded index of step t_blk - HP
+                for (int m = lane; m < WP; m += 32) hb_cp_async8(&sx[buf][m][j], xrow + m, sj >= 0);
+            }
+        } else {
+            const double *x = in + (has ? my_src : 0);
+            for (int m = warp; m < WP; m += 8) {
+                const long long t = t_blk - HP + m;
+                const bool ok = has && t >= 0 && t < T;
+                hb_cp_async8(&sx[buf][m][lane], ok ? x + t * n_in : in, ok);
+            }
         }
         for (int l = warp; l < HP; l += 8) {
             const bool ok = has && l < H;
@@ -243,13 +258,57 @@ __global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in,
     }
 }
 
+// xt[n][lead + t] = in[t][n] for 0 <= t < T, zero elsewhere in [0, Tp): 32 x 32 tiles through shared memory, both sides coalesced
+__global__ void __launch_bounds__(256) hb_irf_transpose(const double *__restrict__ in, int n_in, long long T, int lead, long long Tp,
+                                                        double *__restrict__ xt) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long tp0 = (long long)blockIdx.x * 32;
+    const int n0 = blockIdx.y * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long t = tp0 + ty + 8 * k - lead;
+        const int n = n0 + tx;
+        tile[ty + 8 * k][tx] = (t >= 0 && t < T && n < n_in) ? in[t * n_in + n] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int n = n0 + ty + 8 * k;
+        const long long tp = tp0 + tx;
+        if (n < n_in && tp < Tp) xt[(long long)n * Tp + tp] = tile[tx][ty + 8 * k];
+    }
+}
+
+// workspace of the transposed input (grown on demand, kept for the life of the process; cudaFree waits for kernels using it)
+double *g_irf_ws = nullptr;
+size_t g_irf_cap = 0;
+
 template <int HP>
 int hb_launch_conv_tiled(dim3 grid, cudaStream_t st, int n_out, int n_in, long long T, int H, long long nnz, const int *row_ptr,
                          const int *src, const double *w, const double *in, double *out) {
-    const int smem = (2 * (8 * HB_IRF_TT + HP) * 32 + 2 * HP * 32) * 8;
+    constexpr int BT = 8 * HB_IRF_TT;
+    const int smem = (2 * (BT + HP) * 33 + 2 * HP * 32) * 8;
     // per device and per context: set on every call (a host-side attribute write, negligible next to the launch)
     if (cudaFuncSetAttribute(hb_sparse_conv_tiled<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HB_ERR_CUDA;
-    hb_sparse_conv_tiled<HP><<<grid, 256, smem, st>>>(n_out, n_in, T, H, nnz, row_ptr, src, w, in, out);
+    const double *xt = nullptr;
+    const long long Tp = (long long)grid.y * BT + HP;              // every block's window [t_blk, t_blk + BT + HP) in padded steps
+    if (!getenv("HB_IRF_NO_TRANSPOSE") && (n_in + 31) / 32 <= 65535) {
+        const size_t need = (size_t)n_in * (size_t)Tp * 8;
+        if (need > g_irf_cap) {
+            if (g_irf_ws) cudaFree(g_irf_ws);
+            g_irf_ws = nullptr;
+            g_irf_cap = 0;
+            if (cudaMalloc(&g_irf_ws, need) == cudaSuccess) g_irf_cap = need;
+            else cudaGetLastError();                               // no room for the copy: gather from the [T][n_in] input instead
+        }
+        if (g_irf_cap >= need) {
+            dim3 tg((unsigned)(Tp / 32), (unsigned)((n_in + 31) / 32));
+            hb_irf_transpose<<<tg, 256, 0, st>>>(in, n_in, T, HP, Tp, g_irf_ws);
+            xt = g_irf_ws;
+        }
+    }
+    hb_sparse_conv_tiled<HP><<<grid, 256, smem, st>>>(n_out, n_in, T, H, nnz, row_ptr, src, w, in, xt, Tp, out);
     return HB_OK;
 }
 }  // namespace

@@ -149,8 +149,8 @@ def test_gradient_batch_and_multi_start_adam_recover_planted_parameters():
     truth = np.array([-2.09, 0.17, 2.674, 1709.46, 18.47, 0.0167])
     init = dict(snowpack=0.0, soilwater=1303.0)
     target = model(inp, {"params": dict(zip(names, truth))}, initstates=init)[-1]
-    prob = cal.OptimizationProblem(model, inp, target, metric="NSE", warm_up=61, lb_pas=lb, ub_pas=ub, default_initstates=init,
-                                   fixed_params={"Tmin": -2.09})
+    prob = cal.OptimizationProblem(model, inp, target, metric="NSE", warm_up=61, lb_pas=lb[1:], ub_pas=ub[1:],
+                                   default_initstates=init, fixed_params={"Tmin": -2.09})
     assert prob.calibrated == names[1:]
     P = lb[1:] + np.random.default_rng(0).random((50, 5)) * (ub[1:] - lb[1:])
     f, g = prob.gradient_batch(P)

@@ -418,7 +418,8 @@ def test_sparse_route_convolution_matches_oracle():
     assert_parity(irf.SparseRouteConvolution(K2)(x2), ho.sparse_route_convolution(K2.indices, K2.weights, 3, 2, x2))
 
 
-@pytest.mark.parametrize("n,per,H,T", [(70, 3, 16, 203), (33, 5, 32, 64), (100, 2, 40, 130), (40, 4, 64, 77), (20, 2, 70, 150), (5, 1, 1, 9)])
+@pytest.mark.parametrize("n,per,H,T", [(70, 3, 16, 203), (33, 5, 32, 64), (100, 2, 40, 130), (40, 4, 64, 77), (20, 2, 70, 150), (5, 1, 1, 9),
+                                         (300, 6, 32, 700)])
 def test_sparse_route_convolution_tiled_kernel(n, per, H, T, monkeypatch):
     """The register-tiled kernel (horizon <= 64: ring of 8 inputs per thread, weights staged in shared memory) against the
     oracle and, bit for bit, against the one-thread-per-(destination, step) kernel: ragged time tiles, horizons that are not a
@@ -431,8 +432,10 @@ def test_sparse_route_convolution_tiled_kernel(n, per, H, T, monkeypatch):
     K = irf.SparseRouteKernel(np.array(rows), rng.random((len(rows), H)) / H, n, n)
     x = rng.normal(size=(n, T))
     conv = irf.SparseRouteConvolution(K)
-    got = conv(x)
+    got = conv(x)                                      # input window staged from the time-contiguous copy (hb_irf_transpose)
     assert_parity(got, ho.sparse_route_convolution(K.indices, K.weights, n, n, x))
+    monkeypatch.setenv("HB_IRF_NO_TRANSPOSE", "1")     # window gathered from the [T][n_in] input
+    assert np.array_equal(conv(x), got)
     monkeypatch.setenv("HB_IRF_NAIVE", "1")
     assert np.array_equal(conv(x), got)
 
