@@ -286,35 +286,59 @@ def bench_irf(args):
     from hydromodels_jl_b200.engine import check, lib
     hm.engine.init(0)
     n, per, H, T = 65536, 8, 32, 3650
-    nnz = n * per
     g = torch.Generator(device="cuda"); g.manual_seed(3)
-    row_ptr = (torch.arange(n + 1, device="cuda", dtype=torch.int32) * per).contiguous()
-    # sources: the destination itself and 7 nodes a short way "upstream" of it (river networks are local in node order)
-    src = (torch.arange(n, device="cuda").view(n, 1) - torch.randint(0, 256, (n, per), generator=g, device="cuda")).clamp_(min=0)
-    src[:, 0] = torch.arange(n, device="cuda")
-    src = src.to(torch.int32).reshape(-1).contiguous()
+    ragged = args.workload == "irf_route_ragged"
+    if ragged:
+        # row counts of an aggregated kernel are skewed (headwaters see themselves, outlets see hundreds of upstream nodes):
+        # Pareto-distributed counts, mean ~8, capped at 256
+        cnt = np.minimum(256, 1 + np.floor(3.2 * np.random.default_rng(3).pareto(1.4, n))).astype(np.int64)
+        ptr = np.concatenate([[0], np.cumsum(cnt)])
+        nnz = int(ptr[-1])
+        row_ptr = torch.tensor(ptr, dtype=torch.int32, device="cuda")
+        dest_of = torch.repeat_interleave(torch.arange(n, device="cuda"), torch.tensor(cnt, device="cuda"))
+        src = (dest_of - torch.randint(0, 256, (nnz,), generator=g, device="cuda")).clamp_(min=0).to(torch.int32).contiguous()
+        order = torch.tensor(np.argsort(-cnt, kind="stable").astype(np.int32), device="cuda")
+    else:
+        nnz = n * per
+        row_ptr = (torch.arange(n + 1, device="cuda", dtype=torch.int32) * per).contiguous()
+        # sources: the destination itself and 7 nodes a short way "upstream" of it (river networks are local in node order)
+        src = (torch.arange(n, device="cuda").view(n, 1) - torch.randint(0, 256, (n, per), generator=g, device="cuda")).clamp_(min=0)
+        src[:, 0] = torch.arange(n, device="cuda")
+        src = src.to(torch.int32).reshape(-1).contiguous()
+        order = None
     w = torch.rand(H, nnz, generator=g, device="cuda", dtype=torch.float64) / H
     x = torch.rand(T, n, generator=g, device="cuda", dtype=torch.float64)
     out = torch.empty(T, n, device="cuda", dtype=torch.float64)
     L = lib()
-    L.hb_sparse_route_conv_device.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64] + [C.c_void_p] * 6
-    fn = lambda: check(L.hb_sparse_route_conv_device(n, n, T, H, nnz, row_ptr.data_ptr(), src.data_ptr(), w.data_ptr(), x.data_ptr(), out.data_ptr(), None))
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        fn()
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+    L.hb_sparse_route_conv_ordered_device.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64] + [C.c_void_p] * 7
+
+    def timed(order_ptr):
+        fn = lambda: check(L.hb_sparse_route_conv_ordered_device(n, n, T, H, nnz, row_ptr.data_ptr(), src.data_ptr(), w.data_ptr(), x.data_ptr(),
+                                                                 order_ptr, out.data_ptr(), None))
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps
+
+    ms = timed(order.data_ptr() if order is not None else None)
+    extra = {}
+    if ragged:
+        ref = out.clone()
+        extra = {"unordered_ms": timed(None), "rows_per_destination": {"mean": nnz / n, "max": int(cnt.max())}}
+        extra["bit_identical_to_unordered"] = bool(torch.equal(ref, out))
     flop = 2.0 * nnz * T * H
     v = C.c_double()
     L.hb_probe_fp64_tflops(C.byref(v))
     peak, peak_src = peaks()
     print(json.dumps({"metric": "node-timesteps/sec of the IRF routing convolution", "value": n * T / (ms * 1e-3), "unit": "node-timesteps/s", "n_gpus": 1,
                       "steps": args.steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": "irf_route_65536x3650_h32", "nodes": n, "nnz": nnz, "horizon": H, "timesteps": T},
+                      "config": {"workload": ("irf_route_ragged_65536x3650_h32" if ragged else "irf_route_65536x3650_h32"), "nodes": n, "nnz": nnz,
+                                 "horizon": H, "timesteps": T, **extra},
                       "roofline": {"bound": "fp64", "achieved": flop / ms / 1e9, "peak": v.value, "unit": "TFLOP/s", "frac": flop / ms / 1e9 / v.value,
                                    "peak_source": "measured DFMA probe (hb_probe_fp64_tflops)", "kernel": "hb_sparse_conv", "kernel_ms": ms,
                                    "hbm_GBps_compulsory": (2 * n * T * 8 + nnz * H * 8) / ms / 1e6, "hbm_peak": peak},
@@ -427,7 +451,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096", "calibrate_exphydro", "gradient_exphydro", "irf_route", "exphydro_single_basin_365d"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096", "calibrate_exphydro", "gradient_exphydro", "irf_route", "irf_route_ragged", "exphydro_single_basin_365d"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -464,7 +488,7 @@ def main():
         return bench_calibration(args) if rank == 0 else 0
     if args.workload == "gradient_exphydro":
         return bench_gradient(args) if rank == 0 else 0
-    if args.workload == "irf_route":
+    if args.workload in ("irf_route", "irf_route_ragged"):
         return bench_irf(args) if rank == 0 else 0
     if args.workload == "exphydro_single_basin_365d":
         return bench_single_basin(args) if rank == 0 else 0

@@ -165,7 +165,8 @@ template <int HP>
 __global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in, long long T, int H, long long nnz,
                                                             const int *__restrict__ row_ptr, const int *__restrict__ src,
                                                             const double *__restrict__ w, const double *__restrict__ in,
-                                                            const double *__restrict__ xt, long long Tp, double *__restrict__ out) {
+                                                            const double *__restrict__ xt, long long Tp,
+                                                            const int *__restrict__ order, double *__restrict__ out) {
     constexpr int TT = HB_IRF_TT;
     constexpr int BT = 8 * TT;                         // time steps per block (8 warps)
     constexpr int WP = BT + HP;                        // staged input window: steps [t_blk - HP, t_blk + BT)
@@ -175,7 +176,10 @@ __global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in,
     double(*sx)[WP][33] = reinterpret_cast<double(*)[WP][33]>(hb_irf_smem);                       // [2][WP][33]
     double(*sw)[HP][32] = reinterpret_cast<double(*)[HP][32]>(hb_irf_smem + 2 * WP * 33);        // [2][HP][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int d = blockIdx.x * 32 + lane;
+    // `order`: the destinations in the sequence the blocks take them (e.g. sorted by row count, so that the 32 of a block
+    // finish together — a block runs for as many rows as its longest destination); NULL = natural order
+    const int slot = blockIdx.x * 32 + lane;
+    const int d = slot < n_out ? (order ? order[slot] : slot) : n_out;
     const long long t_blk = (long long)blockIdx.y * BT;
     const long long t0 = t_blk + warp * TT;
     const int r_begin = d < n_out ? row_ptr[d] : 0;
@@ -286,7 +290,7 @@ size_t g_irf_cap = 0;
 
 template <int HP>
 int hb_launch_conv_tiled(dim3 grid, cudaStream_t st, int n_out, int n_in, long long T, int H, long long nnz, const int *row_ptr,
-                         const int *src, const double *w, const double *in, double *out) {
+                         const int *src, const double *w, const double *in, const int *order, double *out) {
     constexpr int BT = 8 * HB_IRF_TT;
     const int smem = (2 * (BT + HP) * 33 + 2 * HP * 32) * 8;
     // per device and per context: set on every call (a host-side attribute write, negligible next to the launch)
@@ -308,7 +312,7 @@ int hb_launch_conv_tiled(dim3 grid, cudaStream_t st, int n_out, int n_in, long l
             xt = g_irf_ws;
         }
     }
-    hb_sparse_conv_tiled<HP><<<grid, 256, smem, st>>>(n_out, n_in, T, H, nnz, row_ptr, src, w, in, xt, Tp, out);
+    hb_sparse_conv_tiled<HP><<<grid, 256, smem, st>>>(n_out, n_in, T, H, nnz, row_ptr, src, w, in, xt, Tp, order, out);
     return HB_OK;
 }
 }  // namespace
@@ -316,6 +320,12 @@ int hb_launch_conv_tiled(dim3 grid, cudaStream_t st, int n_out, int n_in, long l
 extern "C" int hb_sparse_route_conv_device(int n_out, int n_in, int64_t T, int H, int64_t nnz, const int32_t *row_ptr,
                                            const int32_t *src, const double *weights, const double *input, double *out,
                                            void *stream) {
+    return hb_sparse_route_conv_ordered_device(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, nullptr, out, stream);
+}
+
+extern "C" int hb_sparse_route_conv_ordered_device(int n_out, int n_in, int64_t T, int H, int64_t nnz, const int32_t *row_ptr,
+                                                   const int32_t *src, const double *weights, const double *input,
+                                                   const int32_t *dest_order, double *out, void *stream) {
     if (n_out <= 0 || n_in <= 0 || T < 0 || H <= 0 || nnz < 0 || !row_ptr || !out) return HB_ERR_INVALID;
     if (T == 0) return HB_OK;
     const bool naive = H > 64 || getenv("HB_IRF_NAIVE") != nullptr;
@@ -324,8 +334,9 @@ extern "C" int hb_sparse_route_conv_device(int n_out, int n_in, int64_t T, int H
         hb_sparse_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
     } else {
         dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((T + 8 * HB_IRF_TT - 1) / (8 * HB_IRF_TT)));
-        const int rc = H <= 32 ? hb_launch_conv_tiled<32>(grid, (cudaStream_t)stream, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out)
-                               : hb_launch_conv_tiled<64>(grid, (cudaStream_t)stream, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
+        const int32_t *order = getenv("HB_IRF_NO_ORDER") ? nullptr : dest_order;
+        const int rc = H <= 32 ? hb_launch_conv_tiled<32>(grid, (cudaStream_t)stream, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, order, out)
+                               : hb_launch_conv_tiled<64>(grid, (cudaStream_t)stream, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, order, out);
         if (rc) return rc;
     }
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;

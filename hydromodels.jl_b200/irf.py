@@ -5,7 +5,7 @@
 Kernel construction (`aggregate_route_kernel`: topologically ordered composition of truncated node kernels,
 O(nnz·H²), done once per network) stays on the host, exactly like the unit-hydrograph ordinates; the hot
 operator — `SparseRouteConvolution(input)`: nnz × T × H multiply-adds — runs on the GPU
-(`hb_sparse_route_conv_device`, `csrc/aot_kernels.cu`).  No CPU execution of the convolution exists here.
+(`hb_sparse_route_conv_ordered_device`, `csrc/aot_kernels.cu`).  No CPU execution of the convolution exists here.
 """
 from __future__ import annotations
 
@@ -154,6 +154,9 @@ class SparseRouteConvolution:
         np.add.at(ptr, dest + 1, 1)
         self._row_ptr = np.cumsum(ptr).astype(np.int32)
         self._w = np.ascontiguousarray(kernel.weights[order].T)       # [H][nnz]
+        # destinations by decreasing row count: the 32 destinations of a kernel block then finish together
+        counts = np.diff(self._row_ptr)
+        self._dest_order = np.argsort(-counts, kind="stable").astype(np.int32) if counts.size and counts.max() != counts.min() else None
         if kernel.indices.size and (kernel.indices[:, 1].max() > kernel.n_in or kernel.indices.min() < 1 or
                                     kernel.indices[:, 0].max() > kernel.n_out):
             raise ValueError("kernel indices out of range")
@@ -169,14 +172,17 @@ class SparseRouteConvolution:
             raise ValueError(f"Input node count {x.shape[0]} does not match kernel.n_in {k.n_in}.")
         T = x.shape[1]
         L = lib()
-        L.hb_sparse_route_conv_device.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64] + [C.c_void_p] * 6
-        L.hb_sparse_route_conv_device.restype = C.c_int
+        L.hb_sparse_route_conv_ordered_device.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64] + [C.c_void_p] * 7
+        L.hb_sparse_route_conv_ordered_device.restype = C.c_int
         xin = np.asfortranarray(x)                                     # memory [T][n_in]
         bufs = [DeviceBuffer.from_host(self._row_ptr), DeviceBuffer.from_host(self._src if self._src.size else np.zeros(1, np.int32)),
                 DeviceBuffer.from_host(self._w if self._w.size else np.zeros(1)), DeviceBuffer.from_host(xin.ravel(order="K") if xin.size else np.zeros(1))]
         dout = DeviceBuffer(max(1, k.n_out * T) * 8)
-        check(L.hb_sparse_route_conv_device(k.n_out, k.n_in, T, k.horizon, len(self._src) if k.indices.size else 0,
-                                            bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr, dout.ptr, None))
+        if self._dest_order is not None:
+            bufs.append(DeviceBuffer.from_host(self._dest_order))
+        check(L.hb_sparse_route_conv_ordered_device(k.n_out, k.n_in, T, k.horizon, len(self._src) if k.indices.size else 0,
+                                                    bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr,
+                                                    bufs[4].ptr if self._dest_order is not None else None, dout.ptr, None))
         out = dout.to_host((k.n_out, T), order="F")
         for b in bufs + [dout]:
             b.free()

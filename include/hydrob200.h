@@ -279,6 +279,13 @@ int hb_grid_status(hb_model_t m, void *stream, int32_t *steps_per_launch);
  * weights [H][nnz] with rows in CSR order. */
 int hb_sparse_route_conv_device(int n_out, int n_in, int64_t n_steps, int horizon, int64_t nnz, const int32_t *row_ptr,
                                 const int32_t *src, const double *weights, const double *input, double *out, void *stream);
+/* Same, with `dest_order` (DEVICE, a permutation of 0..n_out-1 or NULL): the sequence in which the kernel's blocks take the
+ * destinations, 32 per block.  A block runs for as many rows as its longest destination, so a network whose destinations
+ * have very different row counts (a few outlets with hundreds of upstream sources) wants them sorted by row count; the
+ * result does not depend on the order. */
+int hb_sparse_route_conv_ordered_device(int n_out, int n_in, int64_t n_steps, int horizon, int64_t nnz, const int32_t *row_ptr,
+                                        const int32_t *src, const double *weights, const double *input,
+                                        const int32_t *dest_order, double *out, void *stream);
 
 /* ---- raster ingest (/root/reference/ext/HydroModelsRastersExt) -------------------------------------------------
  * compute_d8_flow_direction (HydroModelsRastersExt.jl:32-109): steepest-descent D8 codes (1 E, 2 SE, 4 S, 8 SW, 16 W,
