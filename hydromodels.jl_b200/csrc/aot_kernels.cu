@@ -190,10 +190,15 @@ __global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in,
         const int other = __shfl_xor_sync(0xffffffffu, maxrows, o);
         maxrows = other > maxrows ? other : maxrows;
     }
+    // the source index of a row is fetched ONE ROW BEFORE its window is staged (the staging addresses depend on it: an
+    // L2 round trip in front of the copies otherwise stalls the warp — 15 % of the stall samples before this)
+    auto src_of = [&](int r) { return r < nrows ? src[(long long)r_begin + r] : -1; };
+    int src_next = src_of(0);
     auto stage = [&](int r, int buf) {                 // this thread's share of row r: window rows / lags warp, warp+8, ...
         const bool has = r < nrows;
         const long long row = (long long)r_begin + r;
-        const int my_src = has ? src[row] : -1;
+        const int my_src = src_next;
+        src_next = src_of(r + 1);
         if (xt) {
             // time-contiguous copy of the input (hb_irf_transpose: xt[n][HP + t], zero padded): a warp fetches 32 consecutive
             // steps of one source per instruction — full 32-byte sectors instead of one 8-byte value per sector
