@@ -297,7 +297,8 @@ def bench_irf(args):
         row_ptr = torch.tensor(ptr, dtype=torch.int32, device="cuda")
         dest_of = torch.repeat_interleave(torch.arange(n, device="cuda"), torch.tensor(cnt, device="cuda"))
         src = (dest_of - torch.randint(0, 256, (nnz,), generator=g, device="cuda")).clamp_(min=0).to(torch.int32).contiguous()
-        order = torch.tensor(np.argsort(-cnt, kind="stable").astype(np.int32), device="cuda")
+        from hydromodels_jl_b200.irf import balanced_destination_order
+        order = torch.tensor(balanced_destination_order(cnt, int(os.environ.get("HB_IRF_ORDER_WINDOW", "4096"))), device="cuda")
     else:
         nnz = n * per
         row_ptr = (torch.arange(n + 1, device="cuda", dtype=torch.int32) * per).contiguous()
