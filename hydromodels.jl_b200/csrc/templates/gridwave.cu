@@ -228,6 +228,21 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
     }
     if (!valid) inmask = 0;
     bool gave_up = false;
+#ifndef HB_PREFETCH_POLL
+#define HB_PREFETCH_POLL 0       // 1: request the first two upstream words and the downstream word of step i-1 BEFORE the bucket
+#endif                           //    part of step i and consume them after it (the L2 round trip of the common first poll round
+                                 //    overlaps the bucket arithmetic; cells with more inflows finish in the normal poll loop)
+#if HB_PREFETCH_POLL
+    int pk0 = -1, pk1 = -1, poff0 = 0, poff1 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if ((inmask >> k) & 1u) {
+            const int off = 2 * (kDr[k] * a.cols + kDc[k]);
+            if (pk0 < 0) { pk0 = k; poff0 = off; }
+            else if (pk1 < 0) { pk1 = k; poff1 = off; }
+        }
+    }
+#endif
 
     //@@HB:PROLOGUE
 
@@ -267,6 +282,19 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
 #pragma unroll 1
     for (int i = 0; i <= ns; ++i) {
         real xr_next[HB_ARR(HB_RV)];
+#if HB_PREFETCH_POLL
+        double pfv0 = 0.0, pfv1 = 0.0, pfvd = 0.0;
+        i64 pft0 = 0, pft1 = 0, pftd = 0;      // tag 0 never matches (tags are step index + 1 >= 1)
+        if (i > 0 && !gave_up) {
+            const i64 t_abs = a.t0 + (i - 1);
+            const double *qb = a.qbuf + 2 * ((t_abs % HB_QSLOTS) * a.N + nc);
+            const i64 bp_step = t_abs + 2 - HB_QSLOTS;
+            if (pk0 >= 0) pft0 = hb_peek(qb - poff0, pfv0);
+            if (pk1 >= 0) pft1 = hb_peek(qb - poff1, pfv1);
+            if ((inmask >> 8) & 1u)
+                pftd = hb_peek(a.qbuf + 2 * ((((bp_step % HB_QSLOTS) + HB_QSLOTS) % HB_QSLOTS) * a.N + nc + down_off), pfvd);
+        }
+#endif
         if (i < ns) {
             real hb_x[HB_ARR(HB_V)];
             if (tma_in) {
@@ -319,6 +347,17 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_grid_wav
 #pragma unroll
             for (int k = 0; k < 8; ++k) qin[k] = 0.0;
             u32 pending = gave_up ? 0u : inmask;
+#if HB_PREFETCH_POLL
+            if (pending) {
+                const bool ok0 = pk0 >= 0 && pft0 == need, ok1 = pk1 >= 0 && pft1 == need;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (ok0 && k == pk0) { qin[k] = pfv0; pending &= ~(1u << k); }
+                    if (ok1 && k == pk1) { qin[k] = pfv1; pending &= ~(1u << k); }
+                }
+                if (((pending >> 8) & 1u) && pftd >= bp_step + 1) pending &= ~(1u << 8);
+            }
+#endif
             int spins = 0;
             while (pending) {
                 // all outstanding words are requested back to back (one L2 round trip per poll round)
