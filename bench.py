@@ -179,6 +179,10 @@ def bench_raster_ingest(args):
             ("pack_forcing_trc", lambda: check(lib().hb_pack_forcing_device(ptrs.data_ptr(), V, T, n * n, n, 1, d_r.data_ptr(), d_c.data_ptr(), n * n, out.data_ptr(), None)),
              T * n * n * V * 16),
             ("pack_forcing_tcr", lambda: check(lib().hb_pack_forcing_device(ptrs.data_ptr(), V, T, n * n, 1, n, d_r.data_ptr(), d_c.data_ptr(), n * n, out.data_ptr(), None)),
+             T * n * n * V * 16),
+            ("pack_forcing_dense_trc", lambda: check(lib().hb_pack_forcing_dense_device(ptrs.data_ptr(), V, T, n * n, n, 1, n, n, out.data_ptr(), None)),
+             T * n * n * V * 16),
+            ("pack_forcing_dense_tcr", lambda: check(lib().hb_pack_forcing_dense_device(ptrs.data_ptr(), V, T, n * n, 1, n, n, n, out.data_ptr(), None)),
              T * n * n * V * 16)]:
         for _ in range(3):
             fn()
@@ -195,7 +199,7 @@ def bench_raster_ingest(args):
                       "dtype": "f64", "data": "synthetic", "config": {"workload": "raster_ingest_4096", "grid": [n, n], "timesteps": T, "variables": V,
                                                                    "l2": "every launch moves > 1 GB, far beyond the 126 MB L2"},
                       "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "kernels": res},
-                      "gpu_launches": 3 * (args.steps + 3)}))
+                      "gpu_launches": 5 * (args.steps + 3)}))
     return 0
 
 

@@ -412,6 +412,45 @@ __global__ void __launch_bounds__(256) hb_pack_kernel(const double *const *__res
     for (int v = 0; v < n_vars; ++v) o[v] = vars[v][off];
 }
 
+// Dense variant: the nodes are ALL cells of the raster in row-major order (n = r * cols + c) — no position arrays to re-read
+// every step, and a 32 x 32 tile per variable goes through shared memory so that BOTH sides are coalesced whatever the
+// raster's memory order: reads run along its fastest axis, writes are runs of 32 * V consecutive doubles of out[t][n][v].
+__global__ void __launch_bounds__(256) hb_pack_dense_kernel(const double *const *__restrict__ vars, int V, long long t_stride,
+                                                            long long row_stride, long long col_stride, int rows, int cols,
+                                                            double *__restrict__ out) {
+    extern __shared__ double hb_pack_smem[];
+    constexpr int VP = 32 * 33 + 1;                    // doubles per variable tile (odd pitches: conflict-free both ways)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const long long t = blockIdx.z;
+    const bool rows_fastest = row_stride < col_stride;
+    for (int v = 0; v < V; ++v) {
+        const double *src = vars[v] + t * t_stride;
+        double *tile = hb_pack_smem + v * VP;          // tile[r_local * 33 + c_local]
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int a = ty + 8 * k;
+            const int rl = rows_fastest ? tx : a, cl = rows_fastest ? a : tx;
+            const int r = r0 + rl, c = c0 + cl;
+            if (r < rows && c < cols) tile[rl * 33 + cl] = src[r * row_stride + c * col_stride];
+        }
+    }
+    __syncthreads();
+    const long long N = (long long)rows * cols;
+    const int ncol = cols - c0 < 32 ? cols - c0 : 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int rl = ty + 8 * k, r = r0 + rl;
+        if (r < rows) {
+            double *o = out + (t * N + (long long)r * cols + c0) * V;
+            for (int j = tx; j < ncol * V; j += 32) {
+                const int cl = j / V, v = j - cl * V;
+                o[j] = hb_pack_smem[v * VP + rl * 33 + cl];
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int hb_d8_flow_direction_device(const double *dem, int rows, int cols, int64_t row_stride, int64_t col_stride,
@@ -433,6 +472,17 @@ extern "C" int hb_pack_forcing_device(const double *const *vars_device_array, in
     dim3 grid((unsigned)((n_nodes + 255) / 256), (unsigned)n_steps);
     hb_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(vars_device_array, n_vars, n_steps, t_stride, row_stride, col_stride, node_row,
                                                           node_col, n_nodes, out);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
+extern "C" int hb_pack_forcing_dense_device(const double *const *vars_device_array, int n_vars, int64_t n_steps, int64_t t_stride,
+                                            int64_t row_stride, int64_t col_stride, int rows, int cols, double *out, void *stream) {
+    if (!vars_device_array || n_vars <= 0 || n_vars > 5 || n_steps < 0 || rows <= 0 || cols <= 0 || !out) return HB_ERR_INVALID;
+    if (n_steps == 0) return HB_OK;
+    if (n_steps > 65535 || (rows + 31) / 32 > 65535) return HB_ERR_INVALID;   // grid.z = steps; callers chunk the time axis
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)n_steps);
+    const int smem = n_vars * (32 * 33 + 1) * 8;       // <= 42 KB for 5 variables: inside the default dynamic limit
+    hb_pack_dense_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(vars_device_array, n_vars, t_stride, row_stride, col_stride, rows, cols, out);
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
 

@@ -145,6 +145,8 @@ def device_forcing(rasters: Sequence, positions: Sequence[Tuple[int, int]], n_st
     N, V = len(pos), len(rasters)
     ptrs = np.array([r.ptr if hasattr(r, "ptr") else int(r) for r in rasters], dtype=np.uint64)
     d_ptrs = DeviceBuffer.from_host(ptrs)
+    # every cell, row-major: the tiled kernel (no position arrays, coalesced on both sides for either memory order)
+    dense = V <= 5 and N == rows * cols and np.array_equal(pos[:, 0] * cols + pos[:, 1], np.arange(N))
     d_r = DeviceBuffer.from_host(np.ascontiguousarray(pos[:, 0], dtype=np.int32))
     d_c = DeviceBuffer.from_host(np.ascontiguousarray(pos[:, 1], dtype=np.int32))
     out = DeviceBuffer(n_steps * N * V * 8)
@@ -153,8 +155,11 @@ def device_forcing(rasters: Sequence, positions: Sequence[Tuple[int, int]], n_st
         nt = min(32768, n_steps - t0)
         sub = np.array([int(p) + t0 * rows * cols * 8 for p in ptrs], dtype=np.uint64)
         d_sub = d_ptrs if t0 == 0 and nt == n_steps else DeviceBuffer.from_host(sub)
-        check(lib().hb_pack_forcing_device(d_sub.ptr, V, nt, rows * cols, rs, cs, d_r.ptr, d_c.ptr, N,
-                                           out.ptr + t0 * N * V * 8, stream))
+        if dense:
+            check(lib().hb_pack_forcing_dense_device(d_sub.ptr, V, nt, rows * cols, rs, cs, rows, cols, out.ptr + t0 * N * V * 8, stream))
+        else:
+            check(lib().hb_pack_forcing_device(d_sub.ptr, V, nt, rows * cols, rs, cs, d_r.ptr, d_c.ptr, N,
+                                               out.ptr + t0 * N * V * 8, stream))
         if d_sub is not d_ptrs:
             check(lib().hb_stream_synchronize(stream))
             d_sub.free()

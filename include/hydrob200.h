@@ -299,6 +299,11 @@ int hb_d8_flow_direction_device(const double *dem, int32_t rows, int32_t cols, i
 int hb_pack_forcing_device(const double *const *vars_device_array, int32_t n_vars, int64_t n_steps, int64_t t_stride,
                            int64_t row_stride, int64_t col_stride, const int32_t *node_row, const int32_t *node_col,
                            int64_t n_nodes, double *out, void *stream);
+/* Same for the dense case — the nodes are all rows x cols cells in row-major order (n = r * cols + c), n_vars <= 5: no
+ * position arrays, 32 x 32 tiles through shared memory so reads follow the raster's fastest axis and writes are whole runs
+ * of out[t][n][v] whatever the raster's memory order. */
+int hb_pack_forcing_dense_device(const double *const *vars_device_array, int n_vars, int64_t n_steps, int64_t t_stride,
+                                 int64_t row_stride, int64_t col_stride, int rows, int cols, double *out, void *stream);
 
 /* ---- on-device calibration: differential evolution around the ensemble objective kernel -----------------------
  * Replaces the host loop `solve(OptimizationProblem(component, input, target; ...), BBO_adaptive_de_rand_1_bin...)`

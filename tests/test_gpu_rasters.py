@@ -60,6 +60,25 @@ def test_pack_forcing_is_an_exact_gather(layout):
         rs.device_forcing(dev, [(R + 1, 1)], T, R, Cc, layout=layout)
 
 
+@pytest.mark.parametrize("layout", ["trc", "tcr"])
+@pytest.mark.parametrize("R,Cc", [(70, 45), (32, 64), (5, 3)])
+def test_pack_forcing_dense_grid_takes_the_tiled_kernel(layout, R, Cc):
+    """Every cell in row-major order -> `hb_pack_forcing_dense_device` (32 x 32 tiles through shared memory); ragged edge
+    tiles, both raster memory orders, and equality with the position-list kernel."""
+    rng = np.random.default_rng(R * Cc)
+    T, V = 9, 3
+    cubes = [rng.normal(size=(R, Cc, T)) for _ in range(V)]
+    pos = [(r + 1, c + 1) for r in range(R) for c in range(Cc)]
+    mem = [np.ascontiguousarray(a.transpose(2, 0, 1)) if layout == "trc" else np.ascontiguousarray(a.transpose(2, 1, 0)) for a in cubes]
+    dev = [DeviceBuffer.from_host(m) for m in mem]
+    got = rs.device_forcing(dev, pos, T, R, Cc, layout=layout).to_host((V, R * Cc, T), order="F")
+    assert np.array_equal(got, ho.gather_forcing(cubes, pos))
+    if R * Cc > 1:                                                   # the same cells in another order: position-list kernel
+        perm = rng.permutation(R * Cc)
+        got2 = rs.device_forcing(dev, [pos[i] for i in perm], T, R, Cc, layout=layout).to_host((V, R * Cc, T), order="F")
+        assert np.array_equal(got2, got[:, perm, :])
+
+
 def test_dem_to_routed_grid_run():
     """DEM -> D8 on the GPU -> `exphydro_grid` on those flow directions: same result as with the oracle's directions,
     and the outlet of the plane collects more flow than the ridge (`test/base/run_spatial_model.jl:140`)."""
