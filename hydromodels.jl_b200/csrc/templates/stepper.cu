@@ -224,6 +224,15 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     treal hb_u[HB_ARR(HB_S)];
 #pragma unroll
     for (int s = 0; s < HB_S; ++s) hb_u[s] = a.init ? (real)a.init[(i64)s * a.N + nc] : (real)0.0;
+#if HB_TANGENTS > 0
+    {
+        constexpr int sdir[HB_ARR(HB_S)] = HB_TSDIR;   // d u_s(0) / d theta_k = [sdir[s] == k]: derivatives w.r.t. initial states
+#pragma unroll
+        for (int s = 0; s < HB_S; ++s)
+#pragma unroll
+            for (int k = 0; k < HB_TANGENTS; ++k) hb_u[s].d[k] = sdir[s] == k ? 1.0 : 0.0;
+    }
+#endif
     // ---- unit-hydrograph ordinates and history -----------------------------------------------
     treal hb_uhw[HB_ARR(HB_UHW_TOTAL)];
     treal hb_uhh[HB_ARR(HB_UHH_TOTAL)];

@@ -862,7 +862,8 @@ class B200Model:
         reference obtains with `Zygote.gradient` through its ImmutableSolver (`/root/reference/README.md:161-187`; loss
         `sum((sim - obs).^2)` = metric "SSE").  Forward mode: the stepper body is re-lowered with value + D tangents per
         quantity (`hb_dual`, hb_math.cuh) and ONE launch returns the objective and D derivative rows per node; more than
-        `max_directions` parameters take several launches.  `grads[name]` has the shape of `params["params"][name]`
+        `max_directions` parameters take several launches.  `wrt` may also name STATES: the derivative w.r.t. that state's
+        initial value (one per node).  `grads[name]` has the shape of `params["params"][name]`
         (scalar, `[ntypes]`, or `[n_members]` for ensembles) and is the derivative of `sum(loss)`: node types shared by
         several nodes sum their nodes' derivatives.  `loss` is the per-node / per-member objective vector.
         Models with neural components are not covered (hundreds of weights need the reverse-mode adjoint)."""
@@ -879,6 +880,9 @@ class B200Model:
                                                           _tangents=group)
             loss = obj if loss is None else loss
             for k, nm in enumerate(group):
+                if nm in prog.state_names and nm not in pdict:          # initial value of a state: one per node
+                    grads[nm] = g[k].copy() if (self.multinode or n_members is not None) else g[k][0]
+                    continue
                 modes = {int(p_mode[j]) for j, (pn, _) in enumerate(prog.param_slots) if pn == nm}
                 if len(modes) != 1:
                     raise NotImplementedError(f"parameter {nm} is used under different htypes vectors")

@@ -622,13 +622,14 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
         if uhs and not uh_on_device:
             raise LoweringError("gradient runs of models with unit hydrographs need the ordinates evaluated on the device")
         known = [nm for nm, _ in param_slots]
-        for nm in tangents:
-            if nm not in known:
+        for nm in tangents:                      # a direction is a parameter name or the INITIAL value of a state
+            if nm not in known and nm not in state_names:
                 raise LoweringError(f"Parameter {nm} does not exist in the model")
         if len(set(tangents)) != len(tangents):
             raise LoweringError("duplicate parameter in the gradient directions")
         tdir = ", ".join(str(tangents.index(nm)) if nm in tangents else "-1" for nm in known) or "-1"
-        body = _body_to_tangent(body).replace("//@@HB:DEFINES\n", f"//@@HB:DEFINES\n#define HB_TDIR {{{tdir}}}\n", 1)
+        sdir = ", ".join(str(tangents.index(nm)) if nm in tangents else "-1" for nm in state_names) or "-1"
+        body = _body_to_tangent(body).replace("//@@HB:DEFINES\n", f"//@@HB:DEFINES\n#define HB_TDIR {{{tdir}}}\n#define HB_TSDIR {{{sdir}}}\n", 1)
     n_ops = sum(1 for v in b.vals if v.id in live and v.mask != 0 and v.op not in ("const", "in", "param", "state")
                 and v.id not in carried)
     stats = {"step_values": n_ops, "prologue_values": len(pro), "carried": len(carried),

@@ -52,6 +52,10 @@ extern "C" int run(i64 N, i64 T, int shared, const double* in, const double* par
           for (int j = 0; j < HB_NP; ++j) for (int k = 0; k < HB_TANGENTS; ++k) hb_p[j].d[k] = tdir[j] == k ? 1.0 : 0.0; }
 #endif
         for (int s = 0; s < HB_S; ++s) hb_u[s] = init ? init[(i64)s * N + n] : 0.0;
+#if HB_TANGENTS > 0
+        { const int sdir[HB_ARR(HB_S)] = HB_TSDIR;
+          for (int s = 0; s < HB_S; ++s) for (int k = 0; k < HB_TANGENTS; ++k) hb_u[s].d[k] = sdir[s] == k ? 1.0 : 0.0; }
+#endif
         for (int k = 0; k < HB_UHW_TOTAL; ++k) hb_uhw[k] = uhw[(i64)k * N + n];
         for (int k = 0; k < HB_UHH_TOTAL; ++k) hb_uhh[k] = 0.0;
         const double hb_minv = minv;

@@ -119,3 +119,17 @@ def test_single_basin_gradient_and_errors():
         et, q = hm.models.m50_chains()
         hm.B200Model(m50).gradient(sy.forcing("m50", 0, 2, 50), {"params": sy.parameters("m50", 0, 2),
                                    "nns": {"etnn": et.init_params(1), "qnn": q.init_params(2)}}, np.ones(50), wrt=["f"])
+
+
+def test_gradient_with_respect_to_initial_states():
+    model, inp, p, init, target = _case("exphydro", 40, 120, 5)
+    init = {"snowpack": np.linspace(0.0, 150.0, 40), "soilwater": np.linspace(300.0, 1600.0, 40)}
+    eng = hm.B200Model(model)
+    wrt = ["soilwater", "Smax", "snowpack", "f"]
+    loss, g = eng.gradient(inp, p, target, metric="NSE", warm_up=10, initstates=init, wrt=wrt)
+    ref_loss, ref_g = ho.loss_gradient(model, inp, p, target, "nse", 10, None, init, wrt=wrt)
+    _close(loss, ref_loss, 1e-10)
+    assert g["soilwater"].shape == (40,) and g["Smax"].shape == (5,)
+    for nm in wrt:
+        _close(g[nm], ref_g[nm])
+    assert np.any(g["snowpack"] != 0) and np.any(g["soilwater"] != 0)
