@@ -356,7 +356,6 @@ def bench_calibration(args):
     generations; every generation is trial kernel + ensemble objective kernel + selection kernel, no host round trip."""
     import hydromodels_jl_b200 as hm
     from hydromodels_jl_b200 import calibration as cal, synthetic as sy
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     hm.engine.init(0)
     T, N, gens = 3650, 65536, max(1, args.steps)
     model = hm.models.exphydro()
