@@ -121,6 +121,117 @@ def device_forcing(torch, model_name, N, T, seed):
     return out
 
 
+class PinnedArray:
+    """A pinned host array owned through the C-ABI (`hb_malloc_host`), viewed as a numpy array."""
+
+    def __init__(self, shape, dtype=np.float64):
+        import ctypes as C
+        from hydromodels_jl_b200.engine import check, lib
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        check(lib().hb_malloc_host(C.byref(p), self.nbytes))
+        self.ptr = p.value
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        from hydromodels_jl_b200.engine import lib
+        if self.ptr:
+            self.array = None
+            lib().hb_free_host(self.ptr)
+            self.ptr = None
+
+
+def mem_available_bytes():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return None
+
+
+def pcie_probe(torch, dist, world, barrier, nbytes=1 << 30, reps=6):
+    """`hb_probe_pcie_gbs` on every rank AT THE SAME TIME (barrier first): per-rank and summed GB/s of plain pinned
+    cudaMemcpyAsync, H2D / D2H alone and both directions at once — the ceiling of the host-buffer path on this box."""
+    import ctypes as C
+    from hydromodels_jl_b200.engine import check, lib
+    g = (C.c_double * 4)()
+    barrier()
+    check(lib().hb_probe_pcie_gbs(nbytes, reps, g))
+    mine = torch.tensor(list(g), device="cuda", dtype=torch.float64)
+    if dist is not None:
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per = torch.stack(allr).cpu().numpy()
+    else:
+        per = mine.cpu().numpy()[None, :]
+    keys = ["h2d_alone", "d2h_alone", "h2d_while_d2h", "d2h_while_h2d"]
+    return {"bytes_per_copy": nbytes, "copies": reps, "concurrent_ranks": world,
+            "sum_GBps": {k: float(per[:, i].sum()) for i, k in enumerate(keys)},
+            "min_rank_GBps": {k: float(per[:, i].min()) for i, k in enumerate(keys)}}
+
+
+def e2e_leg(torch, dist, hm, eng, p, init, d_in, T, N, v_of, rows_of, world, rank, local_rank, args, unit, barrier):
+    in_bytes, out_bytes = T * N * v_of * 8, T * N * rows_of * 8
+    avail = mem_available_bytes()
+    need = world * (in_bytes + out_bytes)
+    if avail is not None and need > 0.9 * avail:
+        raise MemoryError(f"host buffers of {world} ranks need {need / 2**30:.0f} GiB, MemAvailable is {avail / 2**30:.0f} GiB")
+    h_in, h_out = PinnedArray((T, N, v_of)), PinnedArray((T, N, rows_of))
+    torch.from_numpy(h_in.array).copy_(d_in)
+    torch.cuda.synchronize()
+    np_in = h_in.array.transpose(2, 1, 0)      # [V, N, T] Fortran-ordered view, zero copy
+    np_out = h_out.array.transpose(2, 1, 0)
+    assert np_in.flags.f_contiguous and np_out.flags.f_contiguous
+    small = int(sum(np.asarray(v).nbytes for v in p["params"].values()) + 8 * N * len(init))
+
+    def timed(x, y, steps):
+        eng(x, p, initstates=init, out=y)       # warm-up (library workspace; first touch of pageable pages)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            eng(x, p, initstates=init, out=y)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / steps
+
+    s_pinned = timed(np_in, np_out, args.e2e_steps)
+    probe = pcie_probe(torch, dist, world, barrier)
+    # the pipeline moves H2D and D2H at the same time: its floor is the slower of the two streams at the box's concurrent rates
+    floor = max(world * in_bytes / (probe["sum_GBps"]["h2d_while_d2h"] * 1e9), world * out_bytes / (probe["sum_GBps"]["d2h_while_h2d"] * 1e9))
+    e2e = {"value": world * N * T / s_pinned, "unit": unit, "timesteps": T, "h2d_bytes_per_step": in_bytes + small,
+           "d2h_bytes_per_step": out_bytes, "steps": args.e2e_steps, "s_per_step": s_pinned,
+           "api": "B200Model.__call__(input, params, config; initstates) with pinned host arrays (hb_malloc_host)",
+           "aggregate_GBps": {"h2d": world * in_bytes / s_pinned / 1e9, "d2h": world * out_bytes / s_pinned / 1e9},
+           "pcie_probe": probe, "pcie_floor_s_per_step": floor, "pcie_frac": floor / s_pinned,
+           "_launches": (args.e2e_steps + 1) * min(T, -(-out_bytes // (256 << 20)))}
+    if not args.no_pageable:
+        # same call, ordinary (pageable) numpy arrays: the library stages them through its pinned ring with host threads
+        try:
+            if avail is not None and 2 * need > 0.9 * avail:
+                raise MemoryError("not enough host memory for a second, pageable copy of the arrays")
+            pg_in = np.empty((T, N, v_of)); pg_in[...] = h_in.array
+            pg_out = np.empty((T, N, rows_of))
+            s_page = timed(pg_in.transpose(2, 1, 0), pg_out.transpose(2, 1, 0), 1)
+            import ctypes as C
+            nt = C.c_int(0)
+            hm.engine.lib().hb_host_threads(C.byref(nt))
+            same = bool(np.array_equal(pg_out[::37], h_out.array[::37]))
+            e2e["pageable"] = {"value": world * N * T / s_page, "s_per_step": s_page, "host_threads_per_rank": nt.value,
+                               "identical_to_pinned_run": same,
+                               "api": "same call with ordinary numpy arrays (pageable, as a Julia Array): staged through the library's pinned ring"}
+            e2e["_launches"] += 2 * min(T, -(-out_bytes // (64 << 20)))
+            del pg_in, pg_out
+        except Exception as ex:
+            e2e["pageable"] = {"value": None, "error": f"{type(ex).__name__}: {ex}"[:200]}
+    h_in.free(); h_out.free()
+    return e2e
+
+
 def cpu_reference_rate(model_name, T, target_seconds=12.0):
     """Time the CPU oracle on a bounded sample of the workload: the C restatement of the
     reference's two-pass / per-component algorithm (oracle/hydro_oracle.c), OpenMP over node
@@ -458,6 +569,9 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096", "calibrate_exphydro", "gradient_exphydro", "irf_route", "irf_route_ragged", "exphydro_single_basin_365d"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="N > 1: do not bind each rank to its own slice of the host cores")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-array leg of the end-to-end measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="N > 1: skip the config-5 (one 4096 x 4096 grid over all ranks) secondary line")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--block", type=int, default=0, help="tuning: threads per block of the stepper")
     ap.add_argument("--stages", type=int, default=0, help="tuning: forcing pipeline depth (time steps)")
@@ -486,6 +600,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    if local_world > 1 and not args.no_bind and hasattr(os, "sched_setaffinity"):
+        # one contiguous slice of the host cores per rank: the library's host threads (pageable staging) and the
+        # launching thread of a rank stay off the other ranks' cores
+        cores = sorted(os.sched_getaffinity(0))
+        k = len(cores) // local_world
+        if k >= 1:
+            os.sched_setaffinity(0, cores[local_rank * k:(local_rank + 1) * k])
     if args.workload == "raster_ingest_4096":
         return bench_raster_ingest(args) if rank == 0 else 0
     if args.workload == "calibrate_exphydro":
@@ -739,43 +861,23 @@ def main():
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get(args.workload)
+            ent = json.load(open(tr)).get(args.workload)
+            if isinstance(ent, dict):
+                roofline["traffic"] = ent.get("bytes")
+                roofline["traffic_source"] = {"kind": "static_profile (ncu --set full capture, not measured in this run)",
+                                              **{k: v for k, v in ent.items() if k != "bytes"}}
         except Exception:
             pass
 
-    # ---- end to end through the public functor, pinned host buffers --------------------------------
+    # ---- end to end through the public functor, HOST buffers (the headline against the CPU arm) ------------------
+    # Same N and T at every world size.  Each rank pins its own buffers through the C-ABI (hb_malloc_host, after hb_init on
+    # its device); a second leg passes ordinary pageable numpy arrays (what a Julia `Array` is) through the same call.
     e2e = None
     launches = args.steps * launches_per_step
     if not args.no_e2e:
         try:
-            # every rank pins its own host buffers (38 GB at the headline size): from 4 ranks on, the end-to-end leg runs on the
-            # first quarter of the time axis so that 8 ranks pin ~80 GB instead of ~300 GB (a throughput, not a total)
-            Te = T if world < 4 else max(32, T // 4)
-            h_in = torch.empty((Te, N, v_of), dtype=torch.float64, pin_memory=True)
-            h_in.copy_(d_in[:Te])
-            h_out = torch.empty((Te, N, rows_of), dtype=torch.float64, pin_memory=True)
-            torch.cuda.synchronize()
-            np_in = h_in.numpy().transpose(2, 1, 0)      # [V, N, T] Fortran-ordered view, zero copy
-            np_out = h_out.numpy().transpose(2, 1, 0)
-            assert np_in.flags.f_contiguous and np_out.flags.f_contiguous
-            del d_out
-            torch.cuda.empty_cache()
-            eng(np_in, p, initstates=init, out=np_out)   # warm-up (allocates the library workspace)
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                eng(np_in, p, initstates=init, out=np_out)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            if dist is not None:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-            e2e = {"value": world * N * Te * args.e2e_steps / dt, "unit": unit, "timesteps": Te,
-                   "h2d_bytes_per_step": int(h_in.numel() * 8 + sum(np.asarray(v).nbytes for v in p["params"].values()) + 8 * N * len(init)),
-                   "d2h_bytes_per_step": int(h_out.numel() * 8), "steps": args.e2e_steps, "s_per_step": dt / args.e2e_steps,
-                   "api": "B200Model.__call__(input, params, config; initstates) with pinned host arrays"}
-            launches += args.e2e_steps + 1
+            e2e = e2e_leg(torch, dist, hm, eng, p, init, d_in, T, N, v_of, rows_of, world, rank, local_rank, args, unit, barrier)
+            launches += e2e.pop("_launches", 0)
         except Exception as ex:  # e.g. not enough pinnable host memory on the box
             e2e = {"value": None, "unit": unit, "error": f"{type(ex).__name__}: {ex}"[:300]}
 

@@ -282,11 +282,17 @@ class Chain:
 
 
 class NeuralFlux(Component):
-    """`@neuralflux out ~ chain([in1, in2, …])` (`/root/reference/src/nn.jl:32-70,111-132`).
-    `norm` defaults to identity (`:48`) and is not supported otherwise."""
+    """`@neuralflux out ~ chain([in1, in2, …])` / `NeuralFlux(inputs, outputs, chain; norm)`
+    (`/root/reference/src/nn.jl:32-70,111-132`).  Usable inside a `HydroBucket`, as a component of a `HydroModel`, or
+    stand-alone: its functor takes 2D `[inputs, time]` or 3D `[inputs, nodes, time]` arrays (`:140-165` — there is no
+    `htypes`, the chain's parameters are shared by all nodes) and returns `chain(norm(input))`.
+
+    `norm` (`:48`, default identity) normalises the inputs before the chain.  In the reference it is a Julia function of
+    the whole input array; here it is a function of the list of input SYMBOLS returning one expression per input
+    (e.g. `lambda x: [(x[0] - 3.0) / 2.0, x[1], x[2]]`), so it lowers into the same kernel."""
 
     def __init__(self, inputs: Sequence[Sym], outputs: Union[Sym, Sequence[Sym]], chain: Chain, *,
-                 name: Optional[str] = None):
+                 name: Optional[str] = None, norm=None):
         if isinstance(outputs, Sym):
             outputs = [outputs]
         self.chain = chain
@@ -301,6 +307,17 @@ class NeuralFlux(Component):
         self.nn_names = [chain.name]
         self.htypes = None
         self.name = name or f"##neural_flux#{chain.name}"
+        self.norm_exprs: Optional[List[Expr]] = None
+        if norm is not None:
+            from .symbolic import as_expr, free_symbols
+            ex = [as_expr(e) for e in norm([Sym(n) for n in self.input_names])]
+            if len(ex) != len(self.input_names):
+                raise DimensionMismatchError("norm must return one expression per input")
+            for e in ex:
+                extra = [v for group in free_symbols(e) for v in group if v not in self.input_names]
+                if extra:
+                    raise ValueError(f"norm may only use the flux's own inputs, found {extra}")
+            self.norm_exprs = ex
 
 
 class NeuralBucket(Component):
@@ -585,7 +602,7 @@ class HydroModel(Component):
         self.param_names = _uniq(p for c in self.components for p in c.param_names)
         self.nn_names = _uniq(n for c in self.components for n in c.nn_names)
         self.name = name or "##model"
-        multi = [c.is_multinode for c in self.components]
+        multi = [c.is_multinode for c in self.components if not isinstance(c, NeuralFlux)]   # a NeuralFlux takes 2D or 3D
         if any(multi) and not all(multi):
             raise ValueError("mixing single-node and multi-node (htypes) components in one model")
         self.htypes = self.components[0].htypes if all(multi) else None

@@ -9,6 +9,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime_api.h>
+#include <immintrin.h>
 #include <dlfcn.h>
 #include <nvrtc.h>
 #include <sys/stat.h>
@@ -18,8 +19,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <sched.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "templates_embedded.h"   // generated: kStepperTemplate, kRouteTemplate
@@ -231,6 +237,7 @@ struct hb_model_s {
     // workspace for hb_run (host-pointer entry point)
     struct Buf { void *p = nullptr; size_t cap = 0; };
     Buf ws[16];
+    Buf pin_in, pin_out;        // pinned staging rings of hb_run for pageable host arrays
     cudaStream_t stream = nullptr, stream_h2d = nullptr, stream_d2h = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
@@ -319,6 +326,133 @@ int ws_reserve(hb_model_s::Buf &b, size_t bytes) {
     }
     b.cap = bytes;
     return HB_OK;
+}
+
+int pin_reserve(hb_model_s::Buf &b, size_t bytes) {
+    if (bytes <= b.cap) return HB_OK;
+    if (b.p) cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    cudaError_t e = cudaMallocHost(&b.p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HB_ERR_NOMEM, "cudaMallocHost(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.cap = bytes;
+    return HB_OK;
+}
+
+// true when the DMA engines cannot address `p` directly (ordinary malloc'd / Julia GC / numpy memory)
+bool host_is_pageable(const void *p) {
+    if (!p) return false;
+    if (getenv("HB_NO_STAGING")) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Large host copy with streaming (non-temporal) stores: the destination is not read back by this thread, so skipping the
+// read-for-ownership of a plain memcpy saves a third of the DRAM traffic (glibc only switches to NT stores above a
+// threshold of tens of MB per call, larger than the pieces the pool hands out).
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void stream_copy_avx2(char *dst, const char *src, size_t n) {
+    size_t head = (64 - (reinterpret_cast<uintptr_t>(dst) & 63)) & 63;
+    if (head > n) head = n;
+    memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+    size_t blocks = n / 128;
+    for (size_t i = 0; i < blocks; ++i) {
+        __m256i a = _mm256_loadu_si256((const __m256i *)(src + 0)), b = _mm256_loadu_si256((const __m256i *)(src + 32));
+        __m256i c = _mm256_loadu_si256((const __m256i *)(src + 64)), d = _mm256_loadu_si256((const __m256i *)(src + 96));
+        _mm256_stream_si256((__m256i *)(dst + 0), a);
+        _mm256_stream_si256((__m256i *)(dst + 32), b);
+        _mm256_stream_si256((__m256i *)(dst + 64), c);
+        _mm256_stream_si256((__m256i *)(dst + 96), d);
+        src += 128; dst += 128;
+    }
+    _mm_sfence();
+    memcpy(dst, src, n - blocks * 128);
+}
+#endif
+void stream_copy(char *dst, const char *src, size_t n) {
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("HB_NO_NT_COPY");
+    if (avx2 && n >= 4096) { stream_copy_avx2(dst, src, n); return; }
+#endif
+    memcpy(dst, src, n);
+}
+
+// Host threads that move chunks between pageable caller arrays and the pinned staging ring.  One pool per
+// process; size = HB_HOST_THREADS, default min(16, cores this process may run on).
+class HostPool {
+  public:
+    void copy(char *dst, const char *src, size_t bytes) {
+        const size_t piece = (size_t)4 << 20;
+        if (bytes <= piece || n_ <= 1) { stream_copy(dst, src, bytes); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (size_t o = 0; o < bytes; o += piece) q_.push_back({dst + o, src + o, bytes - o < piece ? bytes - o : piece});
+            pending_ += (bytes + piece - 1) / piece;
+        }
+        cv_.notify_all();
+        work(false);                       // the caller copies too
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+    explicit HostPool(int n) : n_(n) {
+        for (int i = 1; i < n_; ++i) th_.emplace_back([this] { work(true); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int threads() const { return n_; }
+
+  private:
+    struct Job { char *dst; const char *src; size_t n; };
+    void work(bool forever) {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                if (forever) cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                j = q_.front();
+                q_.pop_front();
+            }
+            stream_copy(j.dst, j.src, j.n);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::deque<Job> q_;
+    size_t pending_ = 0;
+    bool stop_ = false;
+};
+
+HostPool &host_pool() {
+    static HostPool *pool = [] {
+        int n = 0;
+        if (const char *e = getenv("HB_HOST_THREADS")) n = atoi(e);
+        if (n <= 0) {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            n = sched_getaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+            if (n > 16) n = 16;
+        }
+        if (n < 1) n = 1;
+        if (n > 64) n = 64;
+        return new HostPool(n);            // lives for the process (worker threads are detached from static destruction order)
+    }();
+    return *pool;
 }
 
 int check_desc(const hb_model_s *m, const hb_run_desc *d) {
@@ -576,6 +710,8 @@ int hb_free_model(hb_model_t m) {
     if (!m) return HB_OK;
     for (auto &b : m->ws)
         if (b.p) cudaFree(b.p);
+    if (m->pin_in.p) cudaFreeHost(m->pin_in.p);
+    if (m->pin_out.p) cudaFreeHost(m->pin_out.p);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -650,26 +786,41 @@ int hb_run(hb_model_t m, const hb_run_desc *d) {
     const size_t es = s.precision ? 4 : 8;
     const size_t in_step = (size_t)Nin * s.n_inputs * es;         // forcing bytes per time step
     const size_t out_step = rows_mode ? (size_t)N * s.n_rows * es : 0;
-    if ((rc = ws_reserve(m->ws[0], in_step * T))) return rc;
-    if (rows_mode && (rc = ws_reserve(m->ws[8], out_step * T))) return rc;
-    if (!rows_mode && (rc = ws_reserve(m->ws[9], (size_t)N * 8))) return rc;
-    const size_t grad_bytes = (size_t)s.n_tangents * N * 8;
-    if (grad_bytes && (rc = ws_reserve(m->ws[10], grad_bytes))) return rc;
-    const size_t st_bytes = (size_t)s.n_states * N * 8, uh_bytes = (size_t)m->uhh_total * N * 8;
     // ---- time chunks: H2D(c+1) | kernel(c) | D2H(c-1) overlap on three streams; the bucket states
     //      and UH history are carried between chunk launches in device ping-pong buffers (a chunked
     //      run is bit-identical to a one-shot run: states are clamped values, carried subexpressions
     //      are functions of the state).  Objective mode reduces over the whole series: one chunk.
+    //      The device side is a RING of `nslots` chunk-sized forcing / record slots (not the whole
+    //      series), so a run larger than HBM streams through, and the first call allocates ~1 GB
+    //      instead of the full forcing + result.
+    //      Pageable host arrays (a plain Julia Array / numpy array) cannot be DMA'd directly: their
+    //      chunks go through a pinned staging ring, copied by the library's host threads while the
+    //      DMA engines work on the neighbouring chunks.
+    const bool in_pageable = rows_mode && in_step && T > 0 && host_is_pageable(d->input);
+    const bool out_pageable = rows_mode && out_step && T > 0 && host_is_pageable(d->out);
     int64_t nchunk = 1;
     if (rows_mode && T > 1) {
-        size_t per_chunk = (size_t)256 << 20;                     // ~256 MiB of results per chunk
+        size_t per_chunk = (in_pageable || out_pageable) ? (size_t)64 << 20 : (size_t)256 << 20;   // bytes of results per chunk
         if (const char *e = getenv("HB_CHUNK_BYTES")) { long long v = atoll(e); if (v > 0) per_chunk = (size_t)v; }
         nchunk = (int64_t)((out_step * T + per_chunk - 1) / per_chunk);
         if (nchunk > T) nchunk = T;
-        if (nchunk > 256) nchunk = 256;
         if (nchunk < 1) nchunk = 1;
         if (getenv("HB_NO_PIPELINE")) nchunk = 1;
     }
+    int nslots = 3;
+    if (const char *e = getenv("HB_RING_SLOTS")) { int v = atoi(e); if (v >= 2 && v <= 16) nslots = v; }
+    if (nchunk < nslots) nslots = (int)nchunk;
+    const int64_t cs_max = (T + nchunk - 1) / nchunk;             // longest chunk (chunks are balanced: T*c/nchunk)
+    const size_t in_slot = in_step * (size_t)cs_max, out_slot = out_step * (size_t)cs_max;
+    const bool stage_in = in_pageable && nchunk > 1, stage_out = out_pageable && nchunk > 1;
+    if (in_step && (rc = ws_reserve(m->ws[0], in_slot * nslots))) return rc;
+    if (rows_mode && (rc = ws_reserve(m->ws[8], out_slot * nslots))) return rc;
+    if (stage_in && (rc = pin_reserve(m->pin_in, in_slot * nslots))) return rc;
+    if (stage_out && (rc = pin_reserve(m->pin_out, out_slot * nslots))) return rc;
+    if (!rows_mode && (rc = ws_reserve(m->ws[9], (size_t)N * 8))) return rc;
+    const size_t grad_bytes = (size_t)s.n_tangents * N * 8;
+    if (grad_bytes && (rc = ws_reserve(m->ws[10], grad_bytes))) return rc;
+    const size_t st_bytes = (size_t)s.n_states * N * 8, uh_bytes = (size_t)m->uhh_total * N * 8;
     if (nchunk > 1) {
         if (st_bytes && ((rc = ws_reserve(m->ws[12], st_bytes)) || (rc = ws_reserve(m->ws[13], st_bytes)))) return rc;
         if (uh_bytes && ((rc = ws_reserve(m->ws[14], uh_bytes)) || (rc = ws_reserve(m->ws[15], uh_bytes)))) return rc;
@@ -677,29 +828,56 @@ int hb_run(hb_model_t m, const hb_run_desc *d) {
         if (d->final_states && st_bytes && (rc = ws_reserve(m->ws[12], st_bytes))) return rc;
         if (d->uh_hist_out && uh_bytes && (rc = ws_reserve(m->ws[14], uh_bytes))) return rc;
     }
-    while ((int64_t)m->chunk_ev.size() < 2 * nchunk) {
+    // per ring slot: forcing landed / kernel done (slot's forcing consumed, records complete) / records copied out
+    while ((int)m->chunk_ev.size() < 3 * nslots) {
         cudaEvent_t e;
         HB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         m->chunk_ev.push_back(e);
     }
+    auto ev_h2d = [&](int sl) { return m->chunk_ev[3 * sl]; };
+    auto ev_krn = [&](int sl) { return m->chunk_ev[3 * sl + 1]; };
+    auto ev_d2h = [&](int sl) { return m->chunk_ev[3 * sl + 2]; };
     HB_CUDA(cudaEventRecord(m->ev0, m->stream));
     // the copy streams must not start before the workspace of a previous call is idle
     HB_CUDA(cudaStreamWaitEvent(m->stream_h2d, m->ev0, 0));
+    HB_CUDA(cudaStreamWaitEvent(m->stream_d2h, m->ev0, 0));
     const void *state_in = dd.initstates, *uhh_in = dd.uh_hist_in;
     int last_state_slot = -1, last_uh_slot = -1;
+    auto chunk_t0 = [&](int64_t c) { return T * c / nchunk; };
+    // drain chunk c of a staged (pageable) result: wait for its D2H into the pinned slot, copy it to the caller's array
+    auto drain = [&](int64_t c) -> int {
+        const int sl = (int)(c % nslots);
+        const int64_t t0 = chunk_t0(c), t1 = chunk_t0(c + 1);
+        if (t1 <= t0) return HB_OK;
+        HB_CUDA(cudaEventSynchronize(ev_d2h(sl)));
+        host_pool().copy((char *)d->out + out_step * t0, (const char *)m->pin_out.p + out_slot * sl, out_step * (t1 - t0));
+        return HB_OK;
+    };
     for (int64_t c = 0; c < nchunk; ++c) {
-        const int64_t t0 = T * c / nchunk, t1 = T * (c + 1) / nchunk;
+        const int64_t t0 = chunk_t0(c), t1 = chunk_t0(c + 1);
+        const int sl = (int)(c % nslots);
+        const bool reuse = c >= nslots;
+        char *dev_in = (char *)m->ws[0].p + in_slot * sl;
+        char *dev_out = rows_mode ? (char *)m->ws[8].p + out_slot * sl : nullptr;
         if (t1 > t0 && in_step) {
-            HB_CUDA(cudaMemcpyAsync((char *)m->ws[0].p + in_step * t0, (const char *)d->input + in_step * t0, in_step * (t1 - t0),
-                                    cudaMemcpyHostToDevice, m->stream_h2d));
+            const char *src = (const char *)d->input + in_step * t0;
+            if (stage_in) {
+                if (reuse) HB_CUDA(cudaEventSynchronize(ev_h2d(sl)));      // the pinned slot's previous chunk is on the device
+                char *pin = (char *)m->pin_in.p + in_slot * sl;
+                host_pool().copy(pin, src, in_step * (t1 - t0));
+                src = pin;
+            }
+            if (reuse) HB_CUDA(cudaStreamWaitEvent(m->stream_h2d, ev_krn(sl), 0));   // the device slot's previous chunk is consumed
+            HB_CUDA(cudaMemcpyAsync(dev_in, src, in_step * (t1 - t0), cudaMemcpyHostToDevice, m->stream_h2d));
         }
-        HB_CUDA(cudaEventRecord(m->chunk_ev[2 * c], m->stream_h2d));
-        HB_CUDA(cudaStreamWaitEvent(m->stream, m->chunk_ev[2 * c], 0));
+        HB_CUDA(cudaEventRecord(ev_h2d(sl), m->stream_h2d));
+        HB_CUDA(cudaStreamWaitEvent(m->stream, ev_h2d(sl), 0));
+        if (reuse && rows_mode) HB_CUDA(cudaStreamWaitEvent(m->stream, ev_d2h(sl), 0)); // the record slot's previous chunk left the device
         hb_run_desc dc = dd;
         dc.elapsed_ms = nullptr;
         dc.n_steps = t1 - t0;
-        dc.input = (const char *)m->ws[0].p + in_step * t0;
-        dc.out = rows_mode ? (void *)((char *)m->ws[8].p + out_step * t0) : nullptr;
+        dc.input = dev_in;
+        dc.out = dev_out;
         dc.objective = rows_mode ? nullptr : (double *)m->ws[9].p;
         dc.gradient = grad_bytes ? (double *)m->ws[10].p : nullptr;
         dc.initstates = (const double *)state_in;
@@ -720,11 +898,16 @@ int hb_run(hb_model_t m, const hb_run_desc *d) {
         if ((rc = launch_stepper(m, &dc, m->stream))) return rc;
         state_in = dc.final_states;
         uhh_in = dc.uh_hist_out;
-        if (rows_mode && t1 > t0) {
-            HB_CUDA(cudaEventRecord(m->chunk_ev[2 * c + 1], m->stream));
-            HB_CUDA(cudaStreamWaitEvent(m->stream_d2h, m->chunk_ev[2 * c + 1], 0));
-            HB_CUDA(cudaMemcpyAsync((char *)d->out + out_step * t0, (char *)m->ws[8].p + out_step * t0, out_step * (t1 - t0),
-                                    cudaMemcpyDeviceToHost, m->stream_d2h));
+        HB_CUDA(cudaEventRecord(ev_krn(sl), m->stream));
+        if (rows_mode) {
+            HB_CUDA(cudaStreamWaitEvent(m->stream_d2h, ev_krn(sl), 0));
+            if (t1 > t0) {
+                char *dst = stage_out ? (char *)m->pin_out.p + out_slot * sl : (char *)d->out + out_step * t0;
+                HB_CUDA(cudaMemcpyAsync(dst, dev_out, out_step * (t1 - t0), cudaMemcpyDeviceToHost, m->stream_d2h));
+            }
+            HB_CUDA(cudaEventRecord(ev_d2h(sl), m->stream_d2h));
+            // staged result: the chunk nslots-1 behind has to leave its pinned slot before the next iteration reuses it
+            if (stage_out && c >= nslots - 1 && (rc = drain(c - (nslots - 1)))) return rc;
         }
     }
     HB_CUDA(cudaEventRecord(m->ev1, m->stream));
@@ -734,6 +917,9 @@ int hb_run(hb_model_t m, const hb_run_desc *d) {
         HB_CUDA(cudaMemcpyAsync(d->final_states, m->ws[last_state_slot].p, st_bytes, cudaMemcpyDeviceToHost, m->stream));
     if (d->uh_hist_out && uh_bytes && last_uh_slot >= 0)
         HB_CUDA(cudaMemcpyAsync(d->uh_hist_out, m->ws[last_uh_slot].p, uh_bytes, cudaMemcpyDeviceToHost, m->stream));
+    if (stage_out)
+        for (int64_t c = nchunk - (nslots - 1) > 0 ? nchunk - (nslots - 1) : 0; c < nchunk; ++c)
+            if ((rc = drain(c))) return rc;
     HB_CUDA(cudaStreamSynchronize(m->stream));
     HB_CUDA(cudaStreamSynchronize(m->stream_d2h));
     HB_CUDA(cudaStreamSynchronize(m->stream_h2d));
@@ -1059,6 +1245,86 @@ int hb_grid_status(hb_model_t m, void *stream, int32_t *steps_per_launch) {
         cudaMemset((char *)m->ws[6].p + 4, 0, 4);
         return fail(HB_ERR_CUDA, "hb_grid_wave: a warp gave up waiting for a neighbouring warp's outflows (forward-progress failure); results are invalid");
     }
+    return HB_OK;
+}
+
+
+// ---- host <-> device link probe: the roofline of the end-to-end (host buffer) path ---------------------------
+// Plain cudaMemcpyAsync of `bytes` between pinned host memory and the device: H2D alone, D2H alone, and both
+// directions at once on two streams (what hb_run's pipeline asks of the link).  gbs[0..3] = H2D, D2H, H2D while
+// D2H runs, D2H while H2D runs (GB/s, mean over `reps` copies).  bench.py runs it on all ranks at the same time.
+int hb_probe_pcie_gbs(int64_t bytes, int reps, double *gbs) {
+    if (!gbs || bytes <= 0 || reps <= 0) return fail(HB_ERR_INVALID, "bad argument");
+    int rc = ensure_device();
+    if (rc) return rc;
+    void *h0 = nullptr, *h1 = nullptr, *d0 = nullptr, *d1 = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t a0 = nullptr, a1 = nullptr, b0 = nullptr, b1 = nullptr;
+    auto cleanup = [&] {
+        if (h0) cudaFreeHost(h0);
+        if (h1) cudaFreeHost(h1);
+        if (d0) cudaFree(d0);
+        if (d1) cudaFree(d1);
+        if (s0) cudaStreamDestroy(s0);
+        if (s1) cudaStreamDestroy(s1);
+        for (cudaEvent_t e : {a0, a1, b0, b1}) if (e) cudaEventDestroy(e);
+    };
+#define HB_P(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return fail(HB_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+    HB_P(cudaMallocHost(&h0, (size_t)bytes));
+    HB_P(cudaMallocHost(&h1, (size_t)bytes));
+    HB_P(cudaMalloc(&d0, (size_t)bytes));
+    HB_P(cudaMalloc(&d1, (size_t)bytes));
+    memset(h0, 1, (size_t)bytes);
+    memset(h1, 2, (size_t)bytes);
+    HB_P(cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking));
+    HB_P(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+    HB_P(cudaEventCreate(&a0)); HB_P(cudaEventCreate(&a1)); HB_P(cudaEventCreate(&b0)); HB_P(cudaEventCreate(&b1));
+    HB_P(cudaMemcpyAsync(d0, h0, (size_t)bytes, cudaMemcpyHostToDevice, s0));      // warm-up
+    HB_P(cudaMemcpyAsync(h1, d1, (size_t)bytes, cudaMemcpyDeviceToHost, s1));
+    HB_P(cudaStreamSynchronize(s0)); HB_P(cudaStreamSynchronize(s1));
+    float ms = 0;
+    const double gb = (double)bytes * reps / 1e9;
+    HB_P(cudaEventRecord(a0, s0));
+    for (int i = 0; i < reps; ++i) HB_P(cudaMemcpyAsync(d0, h0, (size_t)bytes, cudaMemcpyHostToDevice, s0));
+    HB_P(cudaEventRecord(a1, s0));
+    HB_P(cudaEventSynchronize(a1));
+    HB_P(cudaEventElapsedTime(&ms, a0, a1));
+    gbs[0] = gb / (ms * 1e-3);
+    HB_P(cudaEventRecord(b0, s1));
+    for (int i = 0; i < reps; ++i) HB_P(cudaMemcpyAsync(h1, d1, (size_t)bytes, cudaMemcpyDeviceToHost, s1));
+    HB_P(cudaEventRecord(b1, s1));
+    HB_P(cudaEventSynchronize(b1));
+    HB_P(cudaEventElapsedTime(&ms, b0, b1));
+    gbs[1] = gb / (ms * 1e-3);
+    HB_P(cudaEventRecord(a0, s0));
+    HB_P(cudaEventRecord(b0, s1));
+    for (int i = 0; i < reps; ++i) {
+        HB_P(cudaMemcpyAsync(d0, h0, (size_t)bytes, cudaMemcpyHostToDevice, s0));
+        HB_P(cudaMemcpyAsync(h1, d1, (size_t)bytes, cudaMemcpyDeviceToHost, s1));
+    }
+    HB_P(cudaEventRecord(a1, s0));
+    HB_P(cudaEventRecord(b1, s1));
+    HB_P(cudaEventSynchronize(a1));
+    HB_P(cudaEventSynchronize(b1));
+    HB_P(cudaEventElapsedTime(&ms, a0, a1));
+    gbs[2] = gb / (ms * 1e-3);
+    HB_P(cudaEventElapsedTime(&ms, b0, b1));
+    gbs[3] = gb / (ms * 1e-3);
+#undef HB_P
+    cleanup();
+    return HB_OK;
+}
+
+int hb_host_copy(void *dst, const void *src, int64_t bytes) {
+    if ((!dst || !src) && bytes > 0) return fail(HB_ERR_INVALID, "NULL argument");
+    if (bytes < 0) return fail(HB_ERR_INVALID, "negative size");
+    host_pool().copy((char *)dst, (const char *)src, (size_t)bytes);
+    return HB_OK;
+}
+
+int hb_host_threads(int *n) {
+    if (!n) return fail(HB_ERR_INVALID, "n is NULL");
+    *n = host_pool().threads();
     return HB_OK;
 }
 

@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from .components import (Component, ConstantInterpolation, D8_CODES, GridAggregation, HydroBucket, HydroConfig, HydroFlux,
-                         HydroModel, HydroRoute, LinearInterpolation, SolverType, UnitHydrograph, normalize_config)
+                         HydroModel, HydroRoute, LinearInterpolation, NeuralFlux, SolverType, UnitHydrograph, normalize_config)
 from .lowering import GridProgram, LoweringError, RouteProgram, StepperProgram, lower_grid, lower_route, lower_stepper
 from .symbolic import evaluate_np
 
@@ -139,6 +139,8 @@ def lib():
         "hb_memset_device": [C.c_void_p, C.c_int, C.c_int64, C.c_void_p], "hb_stream_synchronize": [C.c_void_p],
         "hb_probe_fp64_tflops": [C.POINTER(C.c_double)], "hb_probe_dmma_tflops": [C.POINTER(C.c_double)],
         "hb_fill_device": [C.c_void_p, C.c_int64, C.c_double, C.c_void_p],
+        "hb_probe_pcie_gbs": [C.c_int64, C.c_int, C.POINTER(C.c_double)], "hb_host_threads": [C.POINTER(C.c_int)],
+        "hb_host_copy": [C.c_void_p, C.c_void_p, C.c_int64],
     }.items():
         fn = getattr(L, name)
         fn.argtypes = args
@@ -285,6 +287,8 @@ def upstream_csr(aggr, n_nodes: int):
 # argument preparation (host side of the functor)
 # ---------------------------------------------------------------------------------------------------
 def _as_componentvector(params):
+    if isinstance(params, dict) and "params" not in params and "nns" in params:
+        params = dict(params, params={})      # `ComponentVector(nns=(...))`: what a stand-alone NeuralFlux is called with
     if not isinstance(params, dict) or "params" not in params:
         # the reference has no method for plain vectors either (`src/utils.jl:15,22`)
         raise TypeError("params must be a dict {'params': {...}, 'nns': {...}} (ComponentVector stand-in)")
@@ -388,8 +392,10 @@ class B200Model:
                 # keep the model's own input row order
                 self.lumped = HydroModel(components=comps[:-1], name="##lumped_part", input_names=component.input_names)
             self._route_kernel: Optional[CompiledRoute] = None
-        self.multinode = component.htypes is not None if not isinstance(component, HydroModel) else \
-            all(c.htypes is not None for c in comps)
+        # a NeuralFlux has no htypes (its chain is shared by all nodes): stand-alone it takes 2D or 3D input
+        # (`/root/reference/src/nn.jl:140-165`), inside a model it follows the other components
+        self.any_rank = all(isinstance(c, NeuralFlux) for c in comps)
+        self.multinode = all(c.htypes is not None for c in comps if not isinstance(c, NeuralFlux)) and not self.any_rank
 
     # -- name getters forward to the wrapped component ----------------------------------------------
     @property
@@ -442,6 +448,14 @@ class B200Model:
         comp = self.component
         V = len(comp.input_names)
         kind = type(comp).__name__
+        if self.any_rank:
+            if input.ndim not in (2, 3):
+                raise ValueError(f"{kind} accepts 2D (variables × time) or 3D (variables × nodes × time) input, got shape {input.shape}")
+            if input.shape[0] != V:
+                raise AssertionError("Input variables length mismatch")
+            if shared_forcing:
+                raise ValueError("ensembles are built from single-node models with parameters")
+            return (input.shape[1] if input.ndim == 3 else 1), input.shape[-1]
         if self.multinode:
             if input.ndim != 3:
                 raise ValueError(f"{kind} with htypes only accepts 3D input (variables × nodes × time).\n"
@@ -639,7 +653,7 @@ class B200Model:
         uhw_flat = np.ascontiguousarray(np.concatenate(uhw, axis=0)) if uhw else None
         init = self._initstates(prog, initstates, N)
         R = len(prog.row_names)
-        shape = (R, T) if not self.multinode else (R, N, T)
+        shape = (R, N, T) if (self.multinode or (self.any_rank and input.ndim == 3)) else (R, T)
         if out is None:
             out = np.empty(shape, dtype=self.dtype, order="F")                  # memory = [T][N][R]
         elif out.shape != shape or not out.flags.f_contiguous or out.dtype != self.dtype:

@@ -269,7 +269,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
     for c in comps:
         if isinstance(c, HydroRoute):
             raise LoweringError("HydroRoute is a grid-coupled component; it is lowered by lower_route")
-        if not isinstance(c, (HydroBucket, HydroFlux, UnitHydrograph, NeuralBucket)):
+        if not isinstance(c, (HydroBucket, HydroFlux, UnitHydrograph, NeuralBucket, NeuralFlux)):
             raise LoweringError(f"cannot lower component of type {type(c).__name__}")
     b = _Builder(fast)
 
@@ -348,11 +348,19 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
             out.append(vid)
         return out
 
+    def neural_flux_outputs(f: NeuralFlux, local: Dict[str, int]) -> List[int]:
+        """`chain(norm(inputs))` (`/root/reference/src/nn.jl:56-58,148,161`)."""
+        if f.norm_exprs is not None:
+            ins = tuple(b.lower_expr(e, {i: local[i] for i in f.input_names}, {}) for e in f.norm_exprs)
+        else:
+            ins = tuple(local[i] for i in f.input_names)
+        return nn_outputs(f.chain, ins)
+
     def eval_fluxes(bucket: HydroBucket, local: Dict[str, int], ptab: Dict[str, int]) -> Dict[str, int]:
         outs = {}
         for f in bucket.fluxes:
             if isinstance(f, NeuralFlux):
-                for o, vid in zip(f.output_names, nn_outputs(f.chain, tuple(local[i] for i in f.input_names))):
+                for o, vid in zip(f.output_names, neural_flux_outputs(f, local)):
                     local[o] = outs[o] = vid
             else:
                 for eq in f.eqs:
@@ -410,6 +418,10 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                 env[o] = vid
             for s, si in zip(c.state_names, sidx):
                 env[s] = state_post[si]
+        elif isinstance(c, NeuralFlux):
+            # stand-alone / model-level neural flux (`/root/reference/src/nn.jl:140-165`): stateless, one evaluation per step
+            for o, vid in zip(c.output_names, neural_flux_outputs(c, {i: env[i] for i in c.input_names})):
+                env[o] = vid
         elif isinstance(c, HydroFlux):
             ptab = param_table(c)
             local = {i: env[i] for i in c.input_names}

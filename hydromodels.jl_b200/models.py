@@ -177,6 +177,36 @@ def m50(htypes=None) -> HydroModel:
     return HydroModel(name="m50", components=(snow, soil), input_names=["prcp", "temp", "lday"])
 
 
+def m50_three_components(htypes=None) -> HydroModel:
+    """The M50 of `/root/reference/test/models/m50.jl`: snow bucket, soil bucket whose two neural fluxes give
+    `log(evap / lday)` and `log(flow)` (both exponentiated in the soil balance, `:72`), and a third, stateless component
+    `flow ~ exp(log_flow)` (`:77`).  Inputs `prcp, temp, lday`; chains `epnn` (3-16-16-1) and `qnn` (2-16-16-1)."""
+    s = Symbols("prcp temp lday pet rainfall snowfall snowpack soilwater melt log_evap_div_lday log_flow flow "
+                "norm_snw norm_slw norm_temp norm_prcp",
+                "Tmin Tmax Df snowpack_std snowpack_mean soilwater_std soilwater_mean prcp_std prcp_mean "
+                "temp_std temp_mean")
+    snow = HydroBucket(
+        name="m50_snow",
+        fluxes=[HydroFlux(PET_HAMON, symbols=s),
+                HydroFlux(["snowfall ~ step_func(Tmin - temp) * prcp", "rainfall ~ step_func(temp - Tmin) * prcp"], symbols=s),
+                HydroFlux("melt ~ step_func(temp - Tmax) * min(snowpack, Df * (temp - Tmax))", symbols=s)],
+        dfluxes=[StateFlux("snowpack ~ snowfall - melt", symbols=s)], htypes=htypes)
+    ep_nn = Chain((Dense(3, 16, "tanh"), Dense(16, 16, "leakyrelu"), Dense(16, 1, "leakyrelu")), name="epnn")
+    q_nn = Chain((Dense(2, 16, "tanh"), Dense(16, 16, "leakyrelu"), Dense(16, 1, "leakyrelu")), name="qnn")
+    soil = HydroBucket(
+        name="m50_soil",
+        fluxes=[HydroFlux("norm_snw ~ (snowpack - snowpack_mean) / snowpack_std", symbols=s),
+                HydroFlux("norm_slw ~ (soilwater - soilwater_mean) / soilwater_std", symbols=s),
+                HydroFlux("norm_prcp ~ (prcp - prcp_mean) / prcp_std", symbols=s),
+                HydroFlux("norm_temp ~ (temp - temp_mean) / temp_std", symbols=s),
+                NeuralFlux([s.norm_snw, s.norm_slw, s.norm_temp], s.log_evap_div_lday, ep_nn),
+                NeuralFlux([s.norm_slw, s.norm_prcp], s.log_flow, q_nn)],
+        dfluxes=[StateFlux("soilwater ~ rainfall + melt - step_func(soilwater) * lday * exp(log_evap_div_lday) "
+                           "- step_func(soilwater) * exp(log_flow)", symbols=s)], htypes=htypes)
+    convert = HydroFlux("flow ~ exp(log_flow)", symbols=s, htypes=htypes)
+    return HydroModel(name="m50", components=(snow, soil, convert), input_names=["prcp", "temp", "lday"])
+
+
 def exphydro_grid(flwdir, positions, htypes: Optional[Sequence[int]] = None) -> HydroModel:
     """Distributed ExpHydro + `q ~ flow * area_coef` + D8 grid route
     (`q_routed ~ s_river / (1 + lag) + q`, `s_river ~ q - q_routed`)."""

@@ -159,8 +159,10 @@ int hb_model_info(hb_model_t m, hb_kernel_info *info);   /* needs a device */
 int hb_free_model(hb_model_t m);
 
 /* ---- run --------------------------------------------------------------------------------- */
-/* Host buffers: stages H2D, launches, stages D2H, returns after the stream is idle.  Pinned
- * host buffers (hb_malloc_host / cudaHostRegister) are DMA'd directly. */
+/* Host buffers: stages H2D, launches, stages D2H, returns after the stream is idle.  The run is cut into time
+ * chunks that stream through a 3-slot device ring (H2D | kernel | D2H overlap; the forcing and the result never
+ * have to fit in HBM together).  Pinned host buffers (hb_malloc_host / cudaHostRegister) are DMA'd directly;
+ * pageable ones (a plain Julia Array) go through a pinned staging ring filled / drained by library host threads. */
 int hb_run(hb_model_t m, const hb_run_desc *desc);
 /* Device buffers, asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
 int hb_run_device(hb_model_t m, const hb_run_desc *desc, void *stream);
@@ -336,6 +338,14 @@ int hb_stream_synchronize(void *stream);
 int hb_probe_fp64_tflops(double *tflops);                       /* measured FP64 FMA peak (2 flop/FMA) */
 int hb_probe_dmma_tflops(double *tflops);                       /* measured FP64 tensor (DMMA m8n8k4) peak */
 int hb_fill_device(double *p, int64_t n, double v, void *stream); /* L2 flush / buffer fill           */
+/* Host <-> device link (the roofline of hb_run's host-buffer path): `reps` cudaMemcpyAsync of `bytes` between pinned
+ * host memory and the device; gbs[4] = H2D alone, D2H alone, H2D while D2H runs, D2H while H2D runs (GB/s). */
+int hb_probe_pcie_gbs(int64_t bytes, int reps, double *gbs);
+/* Host threads hb_run uses to move chunks of PAGEABLE caller arrays through its pinned staging ring
+ * ($HB_HOST_THREADS, default min(16, cores of the process's affinity mask)). */
+int hb_host_threads(int *n);
+/* The copy those threads perform (parallel, streaming stores): host to host, no device needed. */
+int hb_host_copy(void *dst, const void *src, int64_t bytes);
 
 #ifdef __cplusplus
 }

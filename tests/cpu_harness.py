@@ -137,7 +137,7 @@ def run_body_on_cpu(eng, input, params, config=None, initstates=None, rows=None,
         # -ffp-contract=off: no FMA contraction beyond the explicit fma() calls; plain IEEE
         subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", cpp, "-o", so], check=True)
     L = C.CDLL(so)
-    out = np.zeros((R, N, T) if eng.multinode or ensemble else (R, T), order="F")
+    out = np.zeros((R, N, T) if eng.multinode or ensemble or (getattr(eng, "any_rank", False) and input.ndim == 3) else (R, T), order="F")
     sim = np.zeros((T, N)) if objective else None
     S = len(prog.state_names)
     final = np.zeros((S, N)) if return_final_states else None

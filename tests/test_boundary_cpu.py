@@ -83,3 +83,17 @@ def test_argument_errors_raise_before_any_device_work():
     with pytest.raises(ValueError, match="reads 'b' before it is defined"):
         s = hm.Symbols("a b c", "")
         hm.HydroBucket(fluxes=[hm.HydroFlux("c ~ b + a", symbols=s), hm.HydroFlux("b ~ a", symbols=s)])
+
+
+def test_host_copy_pool_is_exact_for_any_alignment_and_size():
+    """`hb_host_copy`: the parallel streaming-store copy `hb_run` uses to stage pageable arrays (no device involved)."""
+    L = engine.lib()
+    n = ctypes.c_int(0)
+    assert L.hb_host_threads(ctypes.byref(n)) == 0 and n.value >= 1
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 256, size=(40 << 20) + 977, dtype=np.uint8)
+    for off_s, off_d, size in [(0, 0, 0), (1, 3, 5), (7, 1, 4095), (3, 61, 4096 + 129), (5, 64, (9 << 20) + 13), (0, 32, 40 << 20)]:
+        dst = np.full(size + 256, 0xAB, dtype=np.uint8)
+        assert L.hb_host_copy(dst[off_d:].ctypes.data, src[off_s:].ctypes.data, size) == 0
+        assert np.array_equal(dst[off_d:off_d + size], src[off_s:off_s + size])
+        assert np.all(dst[:off_d] == 0xAB) and np.all(dst[off_d + size:] == 0xAB)

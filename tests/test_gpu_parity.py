@@ -125,17 +125,43 @@ def test_chunked_run_resumes_bit_identically():
 
 
 @pytest.mark.parametrize("name", ["gr4j", "hbv"])
-def test_pipelined_host_run_is_bit_identical(monkeypatch, name):
-    """`hb_run` splits long runs into time chunks (H2D | kernel | D2H overlap) carrying states and UH
-    history on the device: results must not depend on the chunking."""
+@pytest.mark.parametrize("mode", ["staged", "direct", "ring2", "pinned"])
+def test_pipelined_host_run_is_bit_identical(monkeypatch, name, mode):
+    """`hb_run` splits long runs into time chunks (H2D | kernel | D2H overlap) that stream through a ring of device slots,
+    carrying states and UH history on the device: results must not depend on the chunking, on the ring depth, or on
+    whether the host arrays are pageable (staged through the library's pinned ring by its host threads, 20 chunks through
+    3 slots), handed to the driver as they are ("direct"), or pinned (`hb_malloc_host`)."""
+    import ctypes as C
     model, inp, p, init = case(name, 640, 97)
     eng = hm.B200Model(model)
     monkeypatch.setenv("HB_NO_PIPELINE", "1")
     one, fin1 = eng(inp, p, initstates=init, return_final_states=True)
     monkeypatch.delenv("HB_NO_PIPELINE")
     monkeypatch.setenv("HB_CHUNK_BYTES", str(640 * len(model.var_names) * 8 * 5))     # 5 steps per chunk
-    many, fin2 = eng(inp, p, initstates=init, return_final_states=True)
+    if mode == "direct":
+        monkeypatch.setenv("HB_NO_STAGING", "1")
+    if mode == "ring2":
+        monkeypatch.setenv("HB_RING_SLOTS", "2")
+    out = None
+    if mode == "pinned":
+        from hydromodels_jl_b200.engine import check, lib
+        ptrs = []
+        def pinned(shape):
+            n = int(np.prod(shape)) * 8
+            q = C.c_void_p()
+            check(lib().hb_malloc_host(C.byref(q), n))
+            ptrs.append(q)
+            return np.frombuffer((C.c_char * n).from_address(q.value), dtype=np.float64).reshape(shape)
+        V, N, T = inp.shape
+        hin = pinned((T, N, V)); hin[...] = inp.transpose(2, 1, 0)
+        inp = hin.transpose(2, 1, 0)
+        out = pinned((T, N, len(model.var_names))).transpose(2, 1, 0)
+    many, fin2 = eng(inp, p, initstates=init, return_final_states=True, out=out)
     assert np.array_equal(one, many) and np.array_equal(fin1, fin2)
+    if mode == "pinned":
+        many = None
+        for q in ptrs:
+            lib().hb_free_host(q)
 
 
 def test_standalone_flux_uh_bucket_components():
@@ -563,3 +589,48 @@ def test_wave_grid_fuzz_against_the_generic_path():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([_sys.executable, os.path.join(root, "tools", "fuzz_wave.py"), "20", "3"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "FUZZ PASSED" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---- stand-alone NeuralFlux (`/root/reference/src/nn.jl:140-165`) -------------------------------------
+@pytest.mark.parametrize("n_out", [1, 2])
+def test_standalone_neural_flux_2d_and_replicated_3d(n_out):
+    """The reference's own differential test shape (`test/base/run_neural_flux.jl:17-24,41-48`): a 3-16-16-n leakyrelu chain
+    on a 2D input, and the 3D call == the 2D result replicated over 10 nodes; expected values from `oracle.chain_apply`
+    (Lux itself cannot run here).  Called with `nns` only, as the reference's test does."""
+    s = hm.Symbols("a b c d e", "")
+    ch = hm.Chain((hm.Dense(3, 16, "leakyrelu"), hm.Dense(16, 16, "leakyrelu"), hm.Dense(16, n_out, "leakyrelu")), name="testnn")
+    f = hm.NeuralFlux([s.a, s.b, s.c], [s.d, s.e][:n_out], ch)
+    x2 = np.array([[1, 3, 3], [2, 2, 2], [1, 2, 1], [3, 1, 2]], dtype=float).T
+    pas = {"nns": {"testnn": ch.init_params(42) + np.random.default_rng(1).normal(0, 0.05, ch.n_params)}}
+    expected = ho.chain_apply(ch, x2, pas["nns"]["testnn"])
+    got = f(x2, pas)
+    assert_parity(got, expected)
+    x3 = np.asfortranarray(np.repeat(x2[:, None, :], 10, axis=1))
+    got3 = f(x3, pas)
+    assert_parity(got3, np.repeat(expected[:, None, :], 10, axis=1))
+    assert np.array_equal(got3, np.repeat(got[:, None, :], 10, axis=1))          # bit-identical across nodes
+    # a larger ragged batch through both MLP code paths (tensor / per-thread)
+    xb = np.asfortranarray(np.random.default_rng(2).normal(size=(3, 333, 41)))
+    ref = ho.run_component(f, xb, pas)
+    assert_parity(hm.B200Model(f, nn_tensor=True)(xb, pas), ref)
+    assert_parity(hm.B200Model(f, nn_tensor=False)(xb, pas), ref)
+
+
+def test_neural_flux_norm_and_three_component_m50():
+    s = hm.Symbols("a b c d", "")
+    ch = hm.Chain((hm.Dense(3, 16, "tanh"), hm.Dense(16, 1, "identity")), name="n1")
+    f = hm.NeuralFlux([s.a, s.b, s.c], s.d, ch, norm=lambda v: [(v[0] - 2.0) / 3.0, v[1], hm.symbolic.tanh(v[2])])
+    x = np.asfortranarray(np.random.default_rng(5).normal(size=(3, 70, 33)))
+    pas = {"nns": {"n1": ch.init_params(9)}}
+    assert_parity(f(x, pas), ho.run_component(f, x, pas))
+    # test/models/m50.jl: snow bucket, soil bucket with two neural fluxes, `flow ~ exp(log_flow)`
+    N, T = 300, 200
+    model = hm.models.m50_three_components(htypes=np.arange(1, N + 1))
+    inp = sy.forcing("m50", 0, N, T)
+    et, q = hm.models.m50_chains()
+    p = {"params": sy.parameters("m50", 0, N), "nns": {"epnn": et.init_params(1) * 0.3, "qnn": q.init_params(2) * 0.3}}
+    init = {k: np.full(N, v) for k, v in sy.INIT["m50"].items()}
+    ref = ho.run_model(model, inp, p, initstates=init)
+    got = model(inp, p, initstates=init)
+    assert_parity(got, ref)
+    assert got.shape[0] == 13 and model.var_names[-1] == "flow"
