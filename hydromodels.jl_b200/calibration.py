@@ -242,8 +242,8 @@ def solve(prob: OptimizationProblem, alg=None, *, maxiters: int = 100) -> Soluti
     L = lib()
     t0 = time.perf_counter()
     run.launch(d_in.ptr, fit.ptr, None)                                # initial population (the trial buffer holds it)
-    # generation 0 bookkeeping: "select" of the population against itself records the best
-    check(L.hb_de_select_device(pop.ptr, trial.ptr, fit.ptr, fit.ptr, d_off.ptr, D, N, hist.ptr, 0, None))
+    # generation 0 bookkeeping: only the best of the initial population is recorded (no selection)
+    check(L.hb_de_best_device(fit.ptr, N, hist.ptr, 0, None))
     launches = 3
     for g in range(1, maxiters + 1):
         check(L.hb_de_trial_device(pop.ptr, trial.ptr, d_off.ptr, D, N, d_lb.ptr, d_ub.ptr, float(alg.F), float(alg.CR),

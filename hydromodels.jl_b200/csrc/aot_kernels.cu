@@ -1,6 +1,7 @@
 // Ahead-of-time (nvcc, sm_100a) kernels that do not depend on a model: measurement probes used by
 // bench.py (FP64 FMA peak for the compute-bound roofline, L2 flush) and exported through the C-ABI.
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -31,6 +32,19 @@ __global__ void __launch_bounds__(256) hb_dmma_probe(double *out, int iters, dou
     }
     const double s = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1];
     if (s == 123.456) out[0] = s;
+}
+
+// Co-tenant stand-in for tests: every block holds `smem` bytes of shared memory (i.e. a share of an SM) and spins until
+// `ns` nanoseconds have passed on the global timer.
+__global__ void hb_occupy(unsigned long long ns) {
+    extern __shared__ unsigned char hog[];
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    if (threadIdx.x == 0) hog[0] = 1;
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
 }
 
 __global__ void hb_fill(double *p, int64_t n, double v) {
@@ -105,6 +119,16 @@ int hb_probe_dmma_tflops(double *tflops) {
     const double flop = 2.0 * 8 * 8 * 4 * 4.0 * iters * (double)blocks * (threads / 32);   // 4 MMAs of 8x8x4 per warp-iteration
     *tflops = flop / (best * 1e-3) / 1e12;
     return HB_OK;
+}
+
+// Hold `n_blocks` blocks of `smem_bytes` shared memory each busy for `ms` milliseconds on `stream` (asynchronous): the
+// co-tenant the wave grid kernel's forward-progress tests run against.
+int hb_probe_occupy_sms(int n_blocks, int smem_bytes, double ms, void *stream) {
+    if (n_blocks <= 0 || smem_bytes < 0 || smem_bytes > 227 * 1024 || !(ms >= 0)) return HB_ERR_INVALID;
+    if (smem_bytes > 48 * 1024 &&
+        cudaFuncSetAttribute(hb_occupy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return HB_ERR_CUDA;
+    hb_occupy<<<n_blocks, 32, smem_bytes, (cudaStream_t)stream>>>((unsigned long long)(ms * 1e6));
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
 
 // Overwrite `n` doubles (use a buffer larger than the 126 MB L2 to flush it between timed runs).
@@ -292,6 +316,7 @@ __global__ void __launch_bounds__(256) hb_irf_transpose(const double *__restrict
 // workspace of the transposed input (grown on demand, kept for the life of the process; cudaFree waits for kernels using it)
 double *g_irf_ws = nullptr;
 size_t g_irf_cap = 0;
+std::mutex g_irf_mu;      // growth + the launches that use the workspace are one critical section (calls are serialised per process)
 
 template <int HP>
 int hb_launch_conv_tiled(dim3 grid, cudaStream_t st, int n_out, int n_in, long long T, int H, long long nnz, const int *row_ptr,
@@ -301,6 +326,7 @@ int hb_launch_conv_tiled(dim3 grid, cudaStream_t st, int n_out, int n_in, long l
     // per device and per context: set on every call (a host-side attribute write, negligible next to the launch)
     if (cudaFuncSetAttribute(hb_sparse_conv_tiled<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HB_ERR_CUDA;
     const double *xt = nullptr;
+    std::lock_guard<std::mutex> lk(g_irf_mu);
     const long long Tp = (long long)grid.y * BT + HP;              // every block's window [t_blk, t_blk + BT + HP) in padded steps
     if (!getenv("HB_IRF_NO_TRANSPOSE") && (n_in + 31) / 32 <= 65535) {
         const size_t need = (size_t)n_in * (size_t)Tp * 8;
@@ -544,7 +570,10 @@ __global__ void __launch_bounds__(256) hb_de_select_kernel(double *__restrict__ 
                                                            int N) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
-    if (trial_fit[i] <= fit[i]) {          // a NaN objective never replaces a member
+    // a NaN trial never replaces a member; a member whose own objective is NaN (KGE of a constant series, log of a
+    // negative flow at generation 0) is replaced by any trial with a real objective, otherwise it would stay for the whole run
+    const double tf = trial_fit[i], f = fit[i];
+    if (tf <= f || (f != f && tf == tf)) {
         fit[i] = trial_fit[i];
         for (int d = 0; d < D; ++d) pop[dim_off[d] + i] = trial[dim_off[d] + i];
     }
@@ -591,9 +620,16 @@ extern "C" int hb_de_trial_device(const double *pop, double *trial, const int64_
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
 
+extern "C" int hb_de_best_device(const double *fitness, int n_members, double *history, int history_slot, void *stream) {
+    if (!fitness || !history || n_members <= 0 || history_slot < 0) return HB_ERR_INVALID;
+    hb_de_best_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(fitness, n_members, history, history_slot);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
 extern "C" int hb_de_select_device(double *pop, const double *trial, double *fitness, const double *trial_fitness,
                                    const int64_t *dim_offset, int n_dims, int n_members, double *history, int history_slot, void *stream) {
     if (!pop || !trial || !fitness || !trial_fitness || !dim_offset || n_dims <= 0 || n_members <= 0) return HB_ERR_INVALID;
+    if (pop == trial || fitness == trial_fitness) return HB_ERR_INVALID;      // the kernel's arguments are __restrict__
     hb_de_select_kernel<<<(n_members + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pop, trial, fitness, trial_fitness,
                                                                                  (const long long *)dim_offset, n_dims, n_members);
     if (history) hb_de_best_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(fitness, n_members, history, history_slot);

@@ -459,7 +459,7 @@ int check_desc(const hb_model_s *m, const hb_run_desc *d) {
     const hb_stepper_spec &s = m->spec;
     if (!d || d->struct_size != (int32_t)sizeof(hb_run_desc)) return fail(HB_ERR_INVALID, "hb_run_desc.struct_size mismatch");
     if (d->n_nodes <= 0 || d->n_steps < 0) return fail(HB_ERR_INVALID, "n_nodes must be > 0 and n_steps >= 0");
-    if (!(d->min_value > 0)) return fail(HB_ERR_INVALID, "min_value must be positive, got %g", d->min_value);
+    if (d->min_value != d->min_value) return fail(HB_ERR_INVALID, "min_value is NaN");   // any real floor: hydrosolve takes what the config carries (src/solve.jl:40); HydroConfig's own > 0 check is the host mirror's
     if (s.n_inputs > 0 && d->n_steps > 0 && !d->input) return fail(HB_ERR_INVALID, "input is NULL");
     if (s.n_params > 0 && (!d->params || !d->param_offset || !d->param_mode)) return fail(HB_ERR_INVALID, "params / param tables are NULL");
     for (int j = 0; j < s.n_params; ++j) {
@@ -565,7 +565,7 @@ int check_route_desc(const hb_model_s *m, const hb_route_desc *d) {
     if (!d || d->struct_size != (int32_t)sizeof(hb_route_desc)) return fail(HB_ERR_INVALID, "hb_route_desc.struct_size mismatch");
     const hb_route_spec &s = m->rspec;
     if (d->n_nodes <= 0 || d->n_steps < 0 || !d->records || !d->up_ptr || !d->up_idx) return fail(HB_ERR_INVALID, "bad route descriptor");
-    if (!(d->min_value > 0)) return fail(HB_ERR_INVALID, "min_value must be positive, got %g", d->min_value);
+    if (d->min_value != d->min_value) return fail(HB_ERR_INVALID, "min_value is NaN");   // any real floor: hydrosolve takes what the config carries (src/solve.jl:40); HydroConfig's own > 0 check is the host mirror's
     if (d->s_row < 0 || d->s_row >= d->n_rows || d->o_row < 0 || d->o_row >= d->n_rows) return fail(HB_ERR_INVALID, "route rows outside the record");
     for (int v = 0; v < s.n_inputs; ++v)
         if (d->in_row[v] < 0 || d->in_row[v] >= d->n_rows) return fail(HB_ERR_INVALID, "route input row outside the record");
@@ -634,8 +634,10 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
         m->uhh_total += spec->uh_kmax[u] - 1;
     }
     m->dyn_smem = stepper_smem_bytes(*spec, m->block, stages);
-    if (m->dyn_smem > 227 * 1024) {
-        const int need = m->dyn_smem;
+    // static shared memory of the templates: the 256-entry exp table (2 KB) + a few words
+    const int kStaticSmem = 2048 + 64;
+    if (m->dyn_smem + kStaticSmem > 227 * 1024) {
+        const int need = m->dyn_smem + kStaticSmem;
         delete m;
         return fail(HB_ERR_INVALID, "kernel needs %d bytes of shared memory (> 227 KB)", need);
     }
@@ -1027,8 +1029,8 @@ int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out)
         if (m->wave_qslots < 2 || m->wave_qslots > 8) { delete m; return fail(HB_ERR_INVALID, "HB_WAVE_QSLOTS must be 2..8"); }
         if (obuf < 2 || obuf > 4) { delete m; return fail(HB_ERR_INVALID, "HB_WAVE_OBUF must be 2..4"); }
         m->dyn_smem = warps * (up128(stages * 32 * spec->n_inputs * 8) + up128(obuf * 32 * spec->n_rows * 8)) + warps * stages * 8;
-        if (m->dyn_smem > 227 * 1024) {
-            const int need = m->dyn_smem;
+        if (m->dyn_smem + 2048 + 64 > 227 * 1024) {
+            const int need = m->dyn_smem + 2048 + 64;
             delete m;
             return fail(HB_ERR_INVALID, "wave kernel needs %d bytes of shared memory", need);
         }
@@ -1118,7 +1120,7 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
     const int o_c0 = d->out_cols > 0 ? d->out_col0 : 0, o_nc = d->out_cols > 0 ? d->out_cols : d->cols;
     if (window && (s.variant != HB_GRID_WAVE || o_r0 < 0 || o_c0 < 0 || o_r0 + o_nr > d->rows || o_c0 + o_nc > d->cols))
         return fail(HB_ERR_INVALID, "an output window needs the wave kernel and must lie inside the grid");
-    if (!(d->min_value > 0)) return fail(HB_ERR_INVALID, "min_value must be positive, got %g", d->min_value);
+    if (d->min_value != d->min_value) return fail(HB_ERR_INVALID, "min_value is NaN");   // any real floor: hydrosolve takes what the config carries (src/solve.jl:40); HydroConfig's own > 0 check is the host mirror's
     if (s.n_params > 0 && (!d->params || !d->param_offset || !d->param_mode)) return fail(HB_ERR_INVALID, "params / param tables are NULL");
     int rc = load_model(m);
     if (rc) return rc;
@@ -1229,6 +1231,7 @@ int hb_run_grid_device(hb_model_t m, const hb_grid_desc *d, void *stream) {
         HB_CUDA(cudaEventRecord(m->ev1, st));
         HB_CUDA(cudaEventSynchronize(m->ev1));
         HB_CUDA(cudaEventElapsedTime(d->elapsed_ms, m->ev0, m->ev1));
+        if (wave) return hb_grid_status(m, stream, nullptr);     // a timed run is synchronous anyway: report an expired poll here
     }
     return HB_OK;
 }
@@ -1363,6 +1366,19 @@ int hb_memset_device(void *dst, int value, int64_t bytes, void *stream) {
     int rc = ensure_device();
     if (rc) return rc;
     HB_CUDA(cudaMemsetAsync(dst, value, (size_t)bytes, (cudaStream_t)stream));
+    return HB_OK;
+}
+int hb_stream_create(void **stream) {
+    if (!stream) return fail(HB_ERR_INVALID, "stream is NULL");
+    int rc = ensure_device();
+    if (rc) return rc;
+    cudaStream_t s;
+    HB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = s;
+    return HB_OK;
+}
+int hb_stream_destroy(void *stream) {
+    if (stream) HB_CUDA(cudaStreamDestroy((cudaStream_t)stream));
     return HB_OK;
 }
 int hb_stream_synchronize(void *stream) {

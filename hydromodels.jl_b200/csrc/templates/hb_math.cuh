@@ -139,15 +139,17 @@ __device__ __forceinline__ void hb_math_init() {
 }
 #endif
 
-// |x| saturated at (just above) a bound given by the HIGH WORD of its double representation (3 integer
-// instructions, no FP64-pipe work; the NaN-aware fmin/fmax the compiler emits cost ~6 each).
-// A NaN is mapped to +/-bound as well (NaN forcing is not propagated through exp/step_func).
+// |x| saturated at (just above) a bound given by the HIGH WORD of its double representation (integer instructions only,
+// no FP64-pipe work; the NaN-aware fmin/fmax the compiler emits cost ~6 each).  A NaN passes through unchanged (its
+// high word is above the exponent-all-ones pattern of infinity), so NaN forcing propagates through exp / step_func /
+// tanh into the states as it does in the reference; +/-inf saturates like any large value.
 HB_DEV double hb_clamp_abs(double x, int bound_hi) {
     const int hi = hb_double2hiint(x);
     const unsigned ahi = (unsigned)hi & 0x7fffffffu;
-    const unsigned chi = (ahi < (unsigned)bound_hi ? ahi : (unsigned)bound_hi) | ((unsigned)hi & 0x80000000u);
+    const unsigned lim = ahi > 0x7ff00000u ? ahi : (unsigned)bound_hi;     // NaN: no saturation
+    const unsigned chi = (ahi < lim ? ahi : lim) | ((unsigned)hi & 0x80000000u);
     // the low word is kept: a saturated value lies in [bound, bound * (1 + 2^-20)) — still inside the
-    // range the callers need (3 instructions: LOP3, VIMNMX.U32, LOP3)
+    // range the callers need
     return hb_hiloint2double((int)chi, hb_double2loint(x));
 }
 #define HB_HI_700 0x4085e000   // high word of 700.0

@@ -132,11 +132,14 @@ def lib():
                                C.c_uint64, C.c_uint32, C.c_void_p],
         "hb_de_select_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                 C.c_void_p],
+        "hb_de_best_device": [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p],
         "hb_malloc_device": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_device": [C.c_void_p],
         "hb_malloc_host": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_host": [C.c_void_p],
         "hb_memcpy_h2d": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
         "hb_memcpy_d2h": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
         "hb_memset_device": [C.c_void_p, C.c_int, C.c_int64, C.c_void_p], "hb_stream_synchronize": [C.c_void_p],
+        "hb_stream_create": [C.POINTER(C.c_void_p)], "hb_stream_destroy": [C.c_void_p],
+        "hb_probe_occupy_sms": [C.c_int, C.c_int, C.c_double, C.c_void_p],
         "hb_probe_fp64_tflops": [C.POINTER(C.c_double)], "hb_probe_dmma_tflops": [C.POINTER(C.c_double)],
         "hb_fill_device": [C.c_void_p, C.c_int64, C.c_double, C.c_void_p],
         "hb_probe_pcie_gbs": [C.c_int64, C.c_int, C.POINTER(C.c_double)], "hb_host_threads": [C.POINTER(C.c_int)],
@@ -741,9 +744,12 @@ class B200Model:
                 full = rec.to_host((R, N, T), order="F")
             except HydroB200Error as ex:
                 # a grid wider than the co-resident blocks can cover keeps the wave kernel's forward-progress guarantee
-                # from holding: the library refuses it and the generic two-pass path takes over
-                if "too wide for the wave kernel" not in str(ex):
+                # from holding: the library refuses it and the generic two-pass path takes over.  The same happens when a
+                # warp's bounded poll expired (a co-tenant kernel held SMs the dependency cone needed): the records are
+                # invalid, the generic path recomputes them
+                if "too wide for the wave kernel" not in str(ex) and "gave up waiting" not in str(ex):
                     raise
+                self.wave_fallbacks = getattr(self, "wave_fallbacks", 0) + 1
                 full = None
             din.free()
             rec.free()

@@ -121,7 +121,7 @@ typedef struct {
     const double *target;        /* objective mode: observed series [T] or [T][N]             */
     int32_t target_per_node;     /* 0: target[T] shared, 1: target[T][N]                      */
     int32_t warm_up;             /* objective uses steps warm_up..T (1-based, as the reference) */
-    double min_value;            /* state clamp, > 0 (src/config.jl:46, src/solve.jl:50)      */
+    double min_value;            /* state clamp (src/solve.jl:40,50); HydroConfig requires > 0 (src/config.jl:46), a NamedTuple config does not */
     void *out;                   /* HB_OUT_ROWS: [T][N][R]; double, or float in Float32 mode  */
     double *objective;           /* HB_OUT_OBJECTIVE: [N]                                     */
     double *final_states;        /* [S][N] or NULL: states after step T (resume / BMI)        */
@@ -164,7 +164,10 @@ int hb_free_model(hb_model_t m);
  * have to fit in HBM together).  Pinned host buffers (hb_malloc_host / cudaHostRegister) are DMA'd directly;
  * pageable ones (a plain Julia Array) go through a pinned staging ring filled / drained by library host threads. */
 int hb_run(hb_model_t m, const hb_run_desc *desc);
-/* Device buffers, asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
+/* Device buffers, asynchronous on `stream` (a cudaStream_t, NULL = default stream).
+ * Threading contract: a model handle is SINGLE-STREAM — the MLP parameter bank and the route / grid workspaces belong to
+ * the handle, so launches of one handle must be ordered on one stream (or serialised by the caller with events); the
+ * library is re-entrant across handles.  hb_init selects ONE device per process (one process per GPU). */
 int hb_run_device(hb_model_t m, const hb_run_desc *desc, void *stream);
 
 /* ---- grid / graph routing (HydroRoute, /root/reference/src/route.jl:336-404) ------------------- */
@@ -317,11 +320,15 @@ int hb_pack_forcing_dense_device(const double *const *vars_device_array, int n_v
 int hb_de_trial_device(const double *pop, double *trial, const int64_t *dim_offset, int32_t n_dims, int32_t n_members,
                        const double *lower, const double *upper, double F, double CR, uint64_t seed, uint32_t generation,
                        void *stream);
-/* trial replaces member where trial_fitness <= fitness; `history` (optional, DEVICE [2 * slots]) receives the best
- * objective of the population and its index at slot `history_slot`. */
+/* trial replaces member where trial_fitness <= fitness, or where the member's own fitness is NaN and the trial's is not
+ * (a NaN trial never wins); `history` (optional, DEVICE [2 * slots]) receives the best objective of the population and
+ * its index at slot `history_slot`.  `pop`/`trial` and `fitness`/`trial_fitness` must not alias. */
 int hb_de_select_device(double *pop, const double *trial, double *fitness, const double *trial_fitness,
                         const int64_t *dim_offset, int32_t n_dims, int32_t n_members, double *history, int32_t history_slot,
                         void *stream);
+/* Best (lowest, NaN ignored) objective of `fitness[n_members]` and its first index -> history[2*slot], history[2*slot+1]
+ * (generation 0 bookkeeping: no selection). */
+int hb_de_best_device(const double *fitness, int32_t n_members, double *history, int32_t history_slot, void *stream);
 
 /* ---- memory helpers (so a host without a CUDA binding can own device / pinned buffers) ---- */
 int hb_malloc_device(void **ptr, int64_t bytes);
@@ -331,6 +338,8 @@ int hb_free_host(void *ptr);
 int hb_memcpy_h2d(void *dst, const void *src, int64_t bytes, void *stream);
 int hb_memcpy_d2h(void *dst, const void *src, int64_t bytes, void *stream);
 int hb_memset_device(void *dst, int value, int64_t bytes, void *stream);
+int hb_stream_create(void **stream);              /* a non-blocking cudaStream_t for the *_device entry points */
+int hb_stream_destroy(void *stream);
 int hb_stream_synchronize(void *stream);
 
 
@@ -338,6 +347,9 @@ int hb_stream_synchronize(void *stream);
 int hb_probe_fp64_tflops(double *tflops);                       /* measured FP64 FMA peak (2 flop/FMA) */
 int hb_probe_dmma_tflops(double *tflops);                       /* measured FP64 tensor (DMMA m8n8k4) peak */
 int hb_fill_device(double *p, int64_t n, double v, void *stream); /* L2 flush / buffer fill           */
+/* Test aid: `n_blocks` blocks holding `smem_bytes` of shared memory each spin for `ms` milliseconds on `stream`
+ * (asynchronous) — a co-tenant kernel for the wave grid kernel's forward-progress tests. */
+int hb_probe_occupy_sms(int n_blocks, int smem_bytes, double ms, void *stream);
 /* Host <-> device link (the roofline of hb_run's host-buffer path): `reps` cudaMemcpyAsync of `bytes` between pinned
  * host memory and the device; gbs[4] = H2D alone, D2H alone, H2D while D2H runs, D2H while H2D runs (GB/s). */
 int hb_probe_pcie_gbs(int64_t bytes, int reps, double *gbs);

@@ -37,6 +37,13 @@ def test_de_trial_indices_are_distinct_and_trials_stay_in_bounds(N, D):
     keep_pop, keep_fit = ho.de_select(pop, trial, np.zeros(N), np.where(np.arange(N) % 2 == 0, -1.0, np.nan))
     assert np.array_equal(keep_pop[::2], trial[::2]) and np.array_equal(keep_pop[1::2], pop[1::2])   # NaN never wins
     assert np.array_equal(keep_fit, np.where(np.arange(N) % 2 == 0, -1.0, 0.0))
+    # a member whose OWN objective is NaN (KGE of a constant series at generation 0) must not be stuck: any real trial replaces
+    # it, a NaN trial does not
+    fit = np.array([np.nan, np.nan, 0.5, 0.5][:N] + [0.5] * max(0, N - 4))
+    tf = np.array([0.9, np.nan, np.nan, 0.4][:N] + [0.6] * max(0, N - 4))
+    kp, kf = ho.de_select(pop, trial, fit, tf)
+    assert np.array_equal(kp[0], trial[0]) and kf[0] == 0.9 and np.array_equal(kp[1], pop[1]) and np.isnan(kf[1])
+    assert np.array_equal(kp[2], pop[2]) and kf[2] == 0.5 and np.array_equal(kp[3], trial[3]) and kf[3] == 0.4
 
 
 def test_optimization_problem_keywords():

@@ -55,14 +55,20 @@ def test_de_kernels_match_the_numpy_restatement_bit_for_bit(N, D, offs):
         assert np.array_equal(got[mask], flat[mask])
     fit, tfit = rng.random(N), rng.random(N)
     tfit[::7] = np.nan
+    fit[1::5] = np.nan                        # incumbents without a valid objective: replaced by any real-valued trial
     d_fit, d_tfit, d_hist = DeviceBuffer.from_host(fit), DeviceBuffer.from_host(tfit), DeviceBuffer.from_host(np.zeros(4))
     check(lib().hb_de_select_device(d_pop.ptr, d_trial.ptr, d_fit.ptr, d_tfit.ptr, d_off.ptr, D, N, d_hist.ptr, 1, None))
     new_pop, new_fit = ho.de_select(pop, ref, fit, tfit)
     got = d_pop.to_host((n_flat,))
     assert np.array_equal(np.stack([got[o:o + N] for o in offs], axis=1), new_pop)
-    assert np.array_equal(d_fit.to_host((N,)), new_fit)
+    assert np.array_equal(d_fit.to_host((N,)), new_fit, equal_nan=True)
     hist = d_hist.to_host((4,))
-    assert hist[2] == new_fit.min() and int(hist[3]) == int(np.argmin(new_fit))
+    assert hist[2] == np.nanmin(new_fit) and int(hist[3]) == int(np.nanargmin(new_fit))
+    check(lib().hb_de_best_device(d_fit.ptr, N, d_hist.ptr, 0, None))          # generation-0 bookkeeping entry point
+    hist = d_hist.to_host((4,))
+    assert hist[0] == np.nanmin(new_fit) and int(hist[1]) == int(np.nanargmin(new_fit))
+    with pytest.raises(ValueError):                                            # aliased arguments are refused
+        check(lib().hb_de_select_device(d_pop.ptr, d_trial.ptr, d_fit.ptr, d_fit.ptr, d_off.ptr, D, N, d_hist.ptr, 1, None))
 
 
 @pytest.mark.parametrize("metric", ["NSE", "KGE", "LogKGE", "MSE"])

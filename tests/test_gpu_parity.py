@@ -416,6 +416,57 @@ def test_wave_grid_kernel_matches_oracle_and_generic_path(R, Cc, T, tc):
     assert np.array_equal(eng(inp, p, initstates=init), wave)  # step counters / tickets are reset between runs
 
 
+def _grid_case(R, Cc, T, seed=0):
+    rng = np.random.default_rng(R * 1000 + Cc + seed)
+    flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128, 0, 5], size=(R, Cc))
+    rr, cc = np.divmod(np.arange(R * Cc), Cc)
+    N = R * Cc
+    model = hm.models.exphydro_grid(flw, np.stack([rr + 1, cc + 1], axis=1))
+    inp = sy.forcing("exphydro", 0, N, T)
+    p = {"params": dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))}
+    init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 2, N))
+    return model, inp, p, init
+
+
+def test_wave_grid_kernel_expired_poll_falls_back_to_the_generic_path(monkeypatch):
+    """A warp whose bounded poll expires raises the kernel's error word: the records are invalid.  The functor must notice
+    (`hb_grid_status`) and recompute through the generic stepper + route path instead of returning them.  Forced here by
+    compiling the wave kernel with a spin limit of zero (any word that is not there at the first poll counts as expiry)."""
+    model, inp, p, init = _grid_case(96, 256, 24)
+    eng2 = hm.B200Model(model)
+    eng2.grid_kernel = "generic"
+    generic = eng2(inp, p, initstates=init)
+    monkeypatch.setenv("HB_EXTRA_DEFINES", "#define HB_SPIN_LIMIT 0")
+    eng = hm.B200Model(model)
+    got = eng(inp, p, initstates=init)
+    assert getattr(eng, "wave_fallbacks", 0) == 1, "the zero spin limit should have expired at least one poll"
+    assert np.array_equal(got, generic)
+
+
+def test_wave_grid_kernel_with_a_co_tenant_holding_half_the_sms():
+    """The wave kernel's forward-progress argument assumes its dependency cone is co-resident; a foreign kernel on another
+    stream takes SMs away.  With half the SMs held for 40 ms by blocks that fill their SM's shared memory, the run must
+    still return the generic path's records bit for bit — by waiting the co-tenant out or by the automatic fallback."""
+    import ctypes as C
+    from hydromodels_jl_b200.engine import check, lib
+    model, inp, p, init = _grid_case(300, 512, 32, seed=1)
+    eng2 = hm.B200Model(model)
+    eng2.grid_kernel = "generic"
+    generic = eng2(inp, p, initstates=init)
+    eng = hm.B200Model(model)
+    assert np.array_equal(eng(inp, p, initstates=init), generic)            # warm-up: compile, allocate
+    st = C.c_void_p()
+    check(lib().hb_stream_create(C.byref(st)))
+    try:
+        for hold_ms in (40.0, 5.0):
+            check(lib().hb_probe_occupy_sms(74, 200 * 1024, hold_ms, st))
+            got = eng(inp, p, initstates=init)
+            check(lib().hb_stream_synchronize(st))
+            assert np.array_equal(got, generic)
+    finally:
+        check(lib().hb_stream_destroy(st))
+
+
 # ---- IRF river routing: SparseRouteConvolution (SURVEY.md §8f row 1) -----------------------------------------
 def test_sparse_route_convolution_matches_oracle():
     """`/root/reference/src/route.jl:593-610`: the reference has no test or fixture for this operator, so the

@@ -108,3 +108,14 @@ def test_log_and_pow(hbm):
     assert np.all(np.abs((got[ok] - ref[ok]) / ref[ok]).astype(np.float64) <= bound[ok])
     assert hbm.pow([0.0, 0.0, 0.0, 5.0, 1e-320], [2.5, 0.0, 1.0, 0.0, 3.0]).tolist() == [0.0, 1.0, 0.0, 1.0, 0.0]
     assert np.isnan(hbm.pow([-1.0], [2.5])[0]) and np.isinf(hbm.pow([0.0], [-1.0])[0])
+
+
+def test_nan_propagates_and_infinities_saturate(hbm):
+    """NaN forcing must not come out of exp / step_func / tanh as a plausible finite number (Julia propagates it);
+    +/-inf keep their limits."""
+    nan, inf = float("nan"), float("inf")
+    for which in (0, 1, 2):
+        assert np.isnan(hbm(which, [nan, -nan])).all()
+    assert hbm(0, [inf])[0] == inf and hbm(0, [-inf])[0] == 0.0
+    assert hbm(1, [inf])[0] == 1.0 and hbm(1, [-inf])[0] < 1e-300
+    assert hbm(2, [inf])[0] == 1.0 and hbm(2, [-inf])[0] == -1.0
