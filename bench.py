@@ -232,6 +232,91 @@ def e2e_leg(torch, dist, hm, eng, p, init, d_in, T, N, v_of, rows_of, world, ran
     return e2e
 
 
+def bench_grid_total(torch, dist, hm, sy, args, rank, world, steps, barrier, halo_exchange):
+    """BASELINE config 5 proper as a SECONDARY line: ONE 4096 x 4096 D8 grid (ExpHydro buckets + HydroRoute), 60 daily
+    steps, cut into `world` column panels with 32 ghost columns; bucket and river states of the ghost columns are
+    refreshed every 32 steps through the library's halo exchange (`hb_halo_exchange_device`).  Strong scaling: the
+    grid is fixed, `value` = all cells x steps / max-over-ranks device time."""
+    from hydromodels_jl_b200.parallel import LibComm, PanelledGridRun, ShardedPanelRun
+    side, T, V, R = 4096, 60, 3, 13
+    Ng = side * side
+    rng = np.random.default_rng(sy.SEED)
+    flw = rng.choice(np.array([1, 2, 4, 8, 16, 32, 64, 128]), size=(side, side), p=[.3, .2, .3, .05, .03, .02, .05, .05])
+    rr, cc = np.divmod(np.arange(Ng), side)
+    model = hm.models.exphydro_grid(flw, np.stack([rr + 1, cc + 1], axis=1))
+    pp = sy.parameters("exphydro", 0, Ng)
+    pp.update(area_coef=np.full(Ng, 1.0), lag=rng.uniform(0.1, 2.0, Ng))
+    init = dict(snowpack=np.zeros(Ng), soilwater=np.full(Ng, 1303.0), s_river=np.zeros(Ng))
+    eng = hm.B200Model(model)
+    out = {"workload": "exphydro_grid_4096x4096_total_x_60d", "metric": "cell-timesteps/sec", "unit": "cell-timesteps/s",
+           "scaling": "strong", "grid": [side, side], "timesteps": T, "n_gpus": world, "steps": steps}
+    comm = None
+    if world > 1:
+        mode = halo_exchange
+        if mode != "torch":
+            try:
+                comm = LibComm(rank, world, halo_mode=mode)
+                if mode == "peer":
+                    comm.enable_peer(side * 32 * 3 * 8)
+            except Exception as ex:      # no CUDA IPC between the ranks' devices: the NCCL exchange of the library still works
+                out["halo_exchange_fallback"] = f"{type(ex).__name__}: {ex}"[:200]
+                if comm is not None and mode == "peer":
+                    comm.halo_mode = mode = "nccl"
+                else:
+                    comm, mode = None, "torch"
+        run = ShardedPanelRun(eng, side, side, T, {"params": pp}, initstates=init, halo=32, comm=comm)
+        n_local, n_owned = run.plan.n_local, run.N
+        out.update(grid_split=f"{world} column panels, 32 ghost columns, states exchanged every 32 steps",
+                   halo_exchange={"torch": "torch.distributed point-to-point from Python", "nccl": "library: pack kernel + grouped ncclSend/ncclRecv + unpack kernel",
+                                  "peer": "library: pack kernel stores into the neighbours' staging over NVLink (CUDA IPC) + epoch flag, unpack kernel waits"}[mode],
+                   halo_bytes_sent_per_exchange_per_rank=run.halo_bytes_per_exchange(), exchanges_per_pass=(T - 1) // 32)
+    else:
+        run = PanelledGridRun(eng, side, side, T, {"params": pp}, initstates=init, panels=0)
+        n_local = n_owned = Ng
+        out.update(grid_split=f"one GPU: {run.K} column panels run one after the other in place")
+    del flw, rr, cc, pp, init
+    d_in = device_forcing(torch, "exphydro", n_local, T, sy.SEED + 17 * rank)
+    d_out = torch.empty((T, n_owned, R), device="cuda", dtype=torch.float64)
+    stream = torch.cuda.current_stream()
+    for _ in range(2):
+        run.launch(d_in.data_ptr(), d_out.data_ptr())
+    barrier()
+    ex_ms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        run.launch(d_in.data_ptr(), d_out.data_ptr())
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    tc = run.check()
+    if world > 1:
+        # exchange share: one more pass with events around every exchange (kept out of the timed passes)
+        run.exchange_events = []
+        run.launch(d_in.data_ptr(), d_out.data_ptr())
+        torch.cuda.synchronize()
+        ex_ms = [a.elapsed_time(b) for a, b in run.exchange_events]
+        run.exchange_events = None
+    t = torch.tensor([ms, float(sum(ex_ms))], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, ex_max = float(t[0].item()), float(t[1].item())
+    peak, _ = peaks()
+    out.update(value=Ng * T / (ms_max * 1e-3), ms_per_step=ms_max, steps_per_launch=tc,
+               roofline={"bound": "hbm", "kernel": "hb_grid_wave", "algorithmic_bytes_per_cell_timestep": 128,
+                         "achieved_per_gpu": 128 * (Ng / world) * T / (ms_max * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac_per_gpu": 128 * (Ng / world) * T / (ms_max * 1e-3) / 1e9 / peak,
+                         "ghost_work": n_local / n_owned - 1.0},
+               exchange_ms_per_pass=ex_max, exchange_share=(ex_max / ms_max if ms_max > 0 else None),
+               gpu_launches=(steps + 2) * (-(-T // 32)) * (3 if world > 1 else 1))
+    if comm is not None:
+        comm.free()
+    del d_in, d_out
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_reference_rate(model_name, T, target_seconds=12.0):
     """Time the CPU oracle on a bounded sample of the workload: the C restatement of the
     reference's two-pass / per-component algorithm (oracle/hydro_oracle.c), OpenMP over node
@@ -571,6 +656,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bind", action="store_true", help="N > 1: do not bind each rank to its own slice of the host cores")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-array leg of the end-to-end measurement")
+    ap.add_argument("--halo-exchange", default="peer", choices=["peer", "nccl", "torch"],
+                    help="sharded grid runs: how ghost states travel (library peer stores over NVLink | library NCCL | torch.distributed)")
     ap.add_argument("--no-secondary", action="store_true", help="N > 1: skip the config-5 (one 4096 x 4096 grid over all ranks) secondary line")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--block", type=int, default=0, help="tuning: threads per block of the stepper")
@@ -888,13 +975,27 @@ def main():
                "one_thread_value": rate1,
                "reference_published_one_thread": 1.05e6}    # docs/src/get_start_en.md:408 (hardware not stated)
 
+    secondary = None
+    if args.workload == DEFAULT_WORKLOAD and not args.no_secondary:
+        # config 5 (the routed grid over all ranks) next to the headline, so that the driver's 1/2/4/8 runs carry it
+        try:
+            del d_in, d_out
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        try:
+            secondary = bench_grid_total(torch, dist, hm, sy, args, rank, world, max(2, min(args.steps, 5)), barrier, args.halo_exchange)
+        except Exception as ex:
+            secondary = {"workload": "exphydro_grid_4096x4096_total_x_60d", "value": None, "error": f"{type(ex).__name__}: {ex}"[:300]}
+        launches += (secondary or {}).get("gpu_launches", 0) or 0
+
     sampler.stop()
     if rank == 0:
         print(json.dumps({
             "metric": "basin-timesteps/sec", "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong" if total_grid else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "secondary": secondary, "gpu_launches": launches, "clocks": clocks,
             "kernel_ms_each": [round(x, 4) for x in kernel_ms]}))
     if dist is not None:
         dist.destroy_process_group()

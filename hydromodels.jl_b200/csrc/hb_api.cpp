@@ -577,6 +577,8 @@ int check_route_desc(const hb_model_s *m, const hb_route_desc *d) {
 // ================================ C-ABI ==============================================================
 extern "C" {
 
+void hb_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }   // for the other translation units of the library
+
 int hb_version(void) { return HB_ABI_VERSION; }
 const char *hb_last_error(void) { return g_err.c_str(); }
 

@@ -95,6 +95,11 @@ class GridDesc(C.Structure):
                 ("in_col0", C.c_int32), ("out_pitch", C.c_int32), ("out_base", C.c_int32)]
 
 
+class HaloEdge(C.Structure):
+    _fields_ = [("peer", C.c_int32), ("s_row0", C.c_int32), ("s_col0", C.c_int32), ("r_row0", C.c_int32), ("r_col0", C.c_int32),
+                ("nrows", C.c_int32), ("ncols", C.c_int32), ("peer_slot", C.c_int32)]
+
+
 _lib = None
 
 
@@ -132,6 +137,9 @@ def lib():
                                C.c_uint64, C.c_uint32, C.c_void_p],
         "hb_de_select_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                 C.c_void_p],
+        "hb_irf_compose_device": [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_void_p],
+        "hb_irf_gather_rows_device": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
         "hb_de_best_device": [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p],
         "hb_malloc_device": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_device": [C.c_void_p],
         "hb_malloc_host": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_host": [C.c_void_p],
@@ -142,6 +150,15 @@ def lib():
         "hb_probe_occupy_sms": [C.c_int, C.c_int, C.c_double, C.c_void_p],
         "hb_probe_fp64_tflops": [C.POINTER(C.c_double)], "hb_probe_dmma_tflops": [C.POINTER(C.c_double)],
         "hb_fill_device": [C.c_void_p, C.c_int64, C.c_double, C.c_void_p],
+        "hb_comm_unique_id": [C.c_void_p, C.c_int32], "hb_comm_init": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)],
+        "hb_comm_rank": [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)], "hb_comm_free": [C.c_void_p],
+        "hb_comm_all_gather": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
+        "hb_comm_alloc": [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)],
+        "hb_comm_peer_ptr": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)],
+        "hb_halo_enable_peer": [C.c_void_p, C.c_int64],
+        "hb_halo_exchange_device": [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.POINTER(HaloEdge), C.c_int32, C.c_int32,
+                                    C.c_void_p],
+        "hb_halo_status": [C.c_void_p, C.c_void_p],
         "hb_probe_pcie_gbs": [C.c_int64, C.c_int, C.POINTER(C.c_double)], "hb_host_threads": [C.POINTER(C.c_int)],
         "hb_host_copy": [C.c_void_p, C.c_void_p, C.c_int64],
     }.items():

@@ -80,76 +80,227 @@ class SparseRouteKernel:
         self.n_out, self.n_in, self.horizon = int(n_out), int(n_in), int(weights.shape[1])
 
 
-def _truncated_route_convolution(a, b, horizon: int) -> np.ndarray:
-    """`_truncated_route_convolution` (`src/route.jl:506-521`)."""
-    out = np.zeros(horizon)
-    ua, ub = min(len(a), horizon), min(len(b), horizon)
-    for ia in range(ua):
-        av = float(a[ia])
-        if av == 0.0:
-            continue
-        mb = min(ub, horizon - ia)
-        out[ia:ia + mb] += av * np.asarray(b[:mb], dtype=np.float64)
-    return out
+def _edge_list(adjacency, nn: int):
+    """(dest, upstream, weight) arrays, 0-based, of the non-zero entries of `adjacency[dest, upstream]` — a dense array, a
+    scipy.sparse matrix, or an explicit `(dest, upstream[, weight])` tuple of 0-based arrays (networks too large for a dense
+    matrix)."""
+    if isinstance(adjacency, tuple):
+        d, u = np.asarray(adjacency[0], dtype=np.int64), np.asarray(adjacency[1], dtype=np.int64)
+        w = np.asarray(adjacency[2], dtype=np.float64) if len(adjacency) > 2 else np.ones(d.size)
+        if d.size and (min(d.min(), u.min()) < 0 or max(d.max(), u.max()) >= nn):
+            raise ValueError("adjacency and node_kernels size mismatch.")
+    elif hasattr(adjacency, "tocoo"):
+        if adjacency.shape != (nn, nn):
+            raise ValueError("adjacency and node_kernels size mismatch.")
+        coo = adjacency.tocoo()
+        d, u, w = coo.row.astype(np.int64), coo.col.astype(np.int64), coo.data.astype(np.float64)
+    else:
+        A = np.asarray(adjacency, dtype=np.float64)
+        if A.shape != (nn, nn):
+            raise ValueError("adjacency and node_kernels size mismatch.")
+        d, u = np.nonzero(A)
+        w = A[d, u]
+    keep = w != 0.0
+    return d[keep], u[keep], w[keep]
 
 
-def topological_order(adjacency) -> List[int]:
-    """Kahn's algorithm, 1-based node ids (`_topological_order`, `src/route.jl:147-169`); `adjacency[node,
-    upstream] != 0` means `upstream` drains into `node`."""
-    A = np.asarray(adjacency) != 0
-    n = A.shape[0]
-    indeg = A.sum(axis=1).astype(int)
-    order, ready = [], [i for i in range(n) if indeg[i] == 0]
-    while ready:
-        u = ready.pop(0)
-        order.append(u + 1)
-        for v in np.nonzero(A[:, u])[0]:
-            indeg[v] -= 1
-            if indeg[v] == 0:
-                ready.append(int(v))
+def topological_order(adjacency, n_nodes: Optional[int] = None) -> List[int]:
+    """Kahn's algorithm, 1-based node ids, FIFO over the initially free nodes in id order and then in the order their last
+    upstream neighbour was processed (`_topological_order`, `src/route.jl:147-169`); `adjacency[node, upstream] != 0` means
+    `upstream` drains into `node`.  Works on the sparse edge list: O(nodes + edges)."""
+    if n_nodes is None:
+        n_nodes = adjacency.shape[0]
+    d, u, _ = _edge_list(adjacency, n_nodes)
+    n = int(n_nodes)
+    indeg = np.bincount(d, minlength=n).astype(np.int64)
+    by_up = np.argsort(u, kind="stable")
+    dn, ptr = d[by_up], np.concatenate([[0], np.cumsum(np.bincount(u, minlength=n))])
+    order, ready, head = [], [int(i) for i in np.nonzero(indeg == 0)[0]], 0
+    while head < len(ready):
+        v = ready[head]
+        head += 1
+        order.append(v + 1)
+        for t in np.sort(dn[ptr[v]:ptr[v + 1]]):          # the reference scans `downstream in 1:nn`
+            indeg[t] -= 1
+            if indeg[t] == 0:
+                ready.append(int(t))
     if len(order) != n:
-        raise ValueError("river network has a cycle")
+        raise ValueError("adjacency must define an acyclic upstream-to-downstream network.")
     return order
 
 
-def aggregate_route_kernel(adjacency, node_kernels: Sequence, *, topo_order=None, horizon: int) -> SparseRouteKernel:
-    """`aggregate_route_kernel` (`src/route.jl:523-577`): source→destination kernels by composing node kernels
-    down the network in topological order, truncated to `horizon`."""
+class CompositionPlan:
+    """Row structure of `aggregate_route_kernel` for one network: which (destination, source) rows exist, in which LEVEL
+    each is computed, and which finished upstream rows (with which edge weights, in which order) it accumulates."""
+
+    def __init__(self, n_nodes, level_row_ptr, row_dest, row_src, contrib_ptr, contrib_row, contrib_ew, final_perm):
+        self.n_nodes = n_nodes
+        self.level_row_ptr = level_row_ptr          # [levels + 1] offsets into the plan's row order (level by level)
+        self.row_dest, self.row_src = row_dest, row_src
+        self.contrib_ptr, self.contrib_row, self.contrib_ew = contrib_ptr, contrib_row, contrib_ew
+        self.final_perm = final_perm                # final row (dest ascending, source ascending) -> plan row
+
+    @property
+    def nnz(self) -> int:
+        return int(self.row_dest.size)
+
+
+def plan_route_composition(adjacency, n_nodes: int, topo_order=None) -> CompositionPlan:
+    """Symbolic phase of `aggregate_route_kernel` (`/root/reference/src/route.jl:536-560`), vectorised per level.
+
+    The reference visits the nodes in `order` (default `1:nn`) and lets a node see only what its upstream neighbours hold
+    AT THAT TIME: an upstream neighbour that comes later in `order` contributes nothing.  So the edges that count are those
+    whose upstream end precedes the node in `order`; on them, a node's level is one more than its deepest upstream
+    neighbour's.  A row (node, source) accumulates one candidate per upstream neighbour that knows `source`, in ascending
+    upstream id (the reference's `for upstream in 1:nn`)."""
+    nn = int(n_nodes)
+    d, u, w = _edge_list(adjacency, nn)
+    pos = np.arange(nn) if topo_order is None else np.empty(nn, dtype=np.int64)
+    if topo_order is not None:
+        order0 = np.asarray(topo_order, dtype=np.int64) - 1
+        if order0.size != nn or not np.array_equal(np.sort(order0), np.arange(nn)):
+            raise ValueError("topo_order must be a permutation of 1:nn")
+        pos[order0] = np.arange(nn)
+    keep = pos[u] < pos[d]
+    d, u, w = d[keep], u[keep], w[keep]
+    # ---- levels (Kahn, frontier at a time) ----
+    level = np.zeros(nn, dtype=np.int64)
+    indeg = np.bincount(d, minlength=nn)
+    by_up = np.argsort(u, kind="stable")
+    up_ptr = np.concatenate([[0], np.cumsum(np.bincount(u, minlength=nn))])
+    frontier = np.nonzero(indeg == 0)[0]
+    lv = 0
+    done = 0
+    while frontier.size:
+        level[frontier] = lv
+        done += frontier.size
+        cnt = up_ptr[frontier + 1] - up_ptr[frontier]
+        if cnt.sum() == 0:
+            break
+        idx = np.repeat(up_ptr[frontier], cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+        targets = d[by_up[idx]]
+        dec = np.bincount(targets, minlength=nn)
+        indeg = indeg - dec
+        frontier = np.nonzero((indeg == 0) & (dec > 0))[0]
+        lv += 1
+    if done != nn:
+        raise ValueError("adjacency must define an acyclic upstream-to-downstream network.")
+    n_levels = int(level.max()) + 1 if nn else 0
+    # edges grouped by the level of their destination
+    e_order = np.lexsort((u, d, level[d]))
+    d, u, w = d[e_order], u[e_order], w[e_order]
+    e_ptr = np.concatenate([[0], np.cumsum(np.bincount(level[d], minlength=n_levels))]) if d.size else np.zeros(n_levels + 1, dtype=np.int64)
+    nodes_by_level = np.argsort(level, kind="stable")
+    n_ptr = np.concatenate([[0], np.cumsum(np.bincount(level, minlength=n_levels))]) if nn else np.zeros(1, dtype=np.int64)
+    start = np.zeros(nn, dtype=np.int64)            # first plan row of a node
+    count = np.zeros(nn, dtype=np.int64)
+    rows_d, rows_s, c_ptrs, c_rows, c_ews, lvl_ptr = [], [], [], [], [], [0]
+    src_all = np.zeros(0, dtype=np.int64)           # plan row -> source node
+    total_rows, total_contrib = 0, 0
+    for L in range(n_levels):
+        nodes = nodes_by_level[n_ptr[L]:n_ptr[L + 1]]
+        ed, eu, ew = d[e_ptr[L]:e_ptr[L + 1]], u[e_ptr[L]:e_ptr[L + 1]], w[e_ptr[L]:e_ptr[L + 1]]
+        cnt = count[eu]
+        tot = int(cnt.sum())
+        rep = np.repeat(np.arange(eu.size), cnt)
+        within = np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        up_row = start[eu][rep] + within                                   # finished rows of the upstream neighbours
+        cand_dest = np.concatenate([nodes, ed[rep]])
+        cand_src = np.concatenate([nodes, src_all[up_row]])
+        cand_up = np.concatenate([np.full(nodes.size, -1, dtype=np.int64), eu[rep]])
+        cand_row = np.concatenate([np.full(nodes.size, -1, dtype=np.int64), up_row])
+        cand_ew = np.concatenate([np.zeros(nodes.size), ew[rep]])
+        o = np.lexsort((cand_up, cand_src, cand_dest))
+        cand_dest, cand_src, cand_up, cand_row, cand_ew = cand_dest[o], cand_src[o], cand_up[o], cand_row[o], cand_ew[o]
+        first = np.ones(cand_dest.size, dtype=bool)
+        first[1:] = (cand_dest[1:] != cand_dest[:-1]) | (cand_src[1:] != cand_src[:-1])
+        row_of = np.cumsum(first) - 1                                      # level-local row of every candidate
+        n_rows = int(first.sum())
+        rd, rs = cand_dest[first], cand_src[first]
+        real = cand_up >= 0                                                # the node's own entry carries no contribution
+        c_count = np.bincount(row_of[real], minlength=n_rows)
+        rows_d.append(rd)
+        rows_s.append(rs)
+        c_ptrs.append(total_contrib + np.cumsum(c_count) - c_count)
+        c_rows.append(cand_row[real])
+        c_ews.append(cand_ew[real])
+        # rows are sorted by (dest, source): a node's rows are contiguous
+        per_node = np.bincount(rd, minlength=nn)
+        firsts = np.nonzero(np.concatenate([[True], rd[1:] != rd[:-1]]))[0] if n_rows else np.zeros(0, dtype=np.int64)
+        start[rd[firsts]] = total_rows + firsts
+        count[nodes] = per_node[nodes]
+        src_all = np.concatenate([src_all, rs])
+        total_rows += n_rows
+        total_contrib += int(real.sum())
+        lvl_ptr.append(total_rows)
+    row_dest = np.concatenate(rows_d) if rows_d else np.zeros(0, dtype=np.int64)
+    row_src = np.concatenate(rows_s) if rows_s else np.zeros(0, dtype=np.int64)
+    contrib_ptr = np.concatenate(c_ptrs + [np.array([total_contrib])]) if rows_d else np.zeros(1, dtype=np.int64)
+    contrib_row = np.concatenate(c_rows) if c_rows else np.zeros(0, dtype=np.int64)
+    contrib_ew = np.concatenate(c_ews) if c_ews else np.zeros(0)
+    final_perm = np.lexsort((row_src, row_dest))                           # `sort!(collect(keys(pairwise[dest])))`, dest ascending
+    return CompositionPlan(nn, np.asarray(lvl_ptr, dtype=np.int64), row_dest.astype(np.int32), row_src.astype(np.int64),
+                           contrib_ptr.astype(np.int64), contrib_row.astype(np.int64), contrib_ew.astype(np.float64), final_perm.astype(np.int64))
+
+
+class DeviceRouteKernel:
+    """An aggregated kernel whose weights stay on the device: `w_conv` is `[H][nnz]` in CSR-by-destination order (what
+    `hb_sparse_route_conv_device` reads); `.weights` downloads the reference's `[nnz, H]` matrix on demand."""
+
+    def __init__(self, indices, n_out, n_in, horizon, w_rows_buf, w_conv_buf):
+        self.indices, self.n_out, self.n_in, self.horizon = indices, int(n_out), int(n_in), int(horizon)
+        self._w_rows, self.w_conv = w_rows_buf, w_conv_buf
+        self._weights = None
+
+    @property
+    def weights(self) -> np.ndarray:
+        if self._weights is None:
+            self._weights = self._w_rows.to_host((self.indices.shape[0], self.horizon))
+        return self._weights
+
+
+def aggregate_route_kernel(adjacency, node_kernels: Sequence, *, topo_order=None, horizon: int, keep_on_device: bool = False):
+    """`aggregate_route_kernel` (`/root/reference/src/route.jl:523-577`): source -> destination kernels by composing the node
+    kernels down the network, truncated to `horizon`.  The row structure is planned on the host from the sparse edge list
+    (`plan_route_composition`); the arithmetic — one truncated `H x H` convolution per (row, upstream neighbour) — runs on
+    the device level by level (`hb_irf_compose_device`), with the reference's operations in the reference's order: the
+    weights are bit-identical to a literal evaluation of the reference's loops (tests: oracle.aggregate_route_kernel).
+    `adjacency`: dense array, scipy.sparse matrix, or `(dest, upstream[, weight])` 0-based edge arrays; `None` pairs every
+    node with itself (`:533-537`)."""
+    from .engine import DeviceBuffer, check, lib
     nn = len(node_kernels)
     H = int(horizon)
     if H <= 0:
         raise ValueError(f"horizon must be positive, got {horizon}")
+    padded = np.zeros((max(nn, 1), H))
+    for i, k in enumerate(node_kernels):
+        padded[i] = _pad_route_kernel(k, H)
     if adjacency is None:
         idx = np.stack([np.arange(1, nn + 1), np.arange(1, nn + 1)], axis=1)
-        w = np.stack([_pad_route_kernel(k, H) for k in node_kernels]) if nn else np.zeros((0, H))
-        return SparseRouteKernel(idx, w, nn, nn)
-    A = np.asarray(adjacency, dtype=np.float64)
-    if A.shape != (nn, nn):
-        raise ValueError("adjacency and node_kernels size mismatch.")
-    order = list(range(1, nn + 1)) if topo_order is None else [int(i) for i in topo_order]
-    pairwise: List[Dict[int, np.ndarray]] = [dict() for _ in range(nn)]
-    for node in order:
-        i = node - 1
-        selfk = _pad_route_kernel(node_kernels[i], H)
-        pairwise[i][i] = selfk.copy()
-        for up in range(nn):
-            ew = A[i, up]
-            if ew == 0.0:
-                continue
-            for source, upk in pairwise[up].items():
-                cand = _truncated_route_convolution(selfk, upk, H)
-                if ew != 1.0:
-                    cand = cand * ew
-                if source in pairwise[i]:
-                    pairwise[i][source] = pairwise[i][source] + cand
-                else:
-                    pairwise[i][source] = cand
-    rows_i, rows_w = [], []
-    for dest in range(nn):
-        for source in sorted(pairwise[dest]):
-            rows_i.append((dest + 1, source + 1))
-            rows_w.append(pairwise[dest][source])
-    return SparseRouteKernel(np.asarray(rows_i, dtype=np.int64).reshape(-1, 2), np.asarray(rows_w).reshape(-1, H), nn, nn)
+        return SparseRouteKernel(idx, padded[:nn], nn, nn)
+    plan = plan_route_composition(adjacency, nn, topo_order)
+    nnz = plan.nnz
+    indices = np.stack([plan.row_dest[plan.final_perm].astype(np.int64) + 1, plan.row_src[plan.final_perm] + 1], axis=1)
+    if nnz == 0:
+        return SparseRouteKernel(indices.reshape(0, 2), np.zeros((0, H)), nn, nn)
+    bufs = [DeviceBuffer.from_host(a) for a in (plan.row_dest, plan.contrib_ptr, plan.contrib_row if plan.contrib_row.size else np.zeros(1, np.int64),
+                                                plan.contrib_ew if plan.contrib_ew.size else np.zeros(1), padded, plan.final_perm)]
+    w_plan, w_rows = DeviceBuffer(nnz * H * 8), DeviceBuffer(nnz * H * 8)
+    L = lib()
+    check(L.hb_irf_compose_device(len(plan.level_row_ptr) - 1, plan.level_row_ptr.ctypes.data_as(C.c_void_p), bufs[0].ptr, bufs[1].ptr,
+                                  bufs[2].ptr, bufs[3].ptr, bufs[4].ptr, w_plan.ptr, H, None))
+    check(L.hb_irf_gather_rows_device(w_plan.ptr, bufs[5].ptr, nnz, H, 0, w_rows.ptr, None))          # reference row order [nnz][H]
+    if keep_on_device:
+        w_conv = DeviceBuffer(nnz * H * 8)
+        check(L.hb_irf_gather_rows_device(w_rows.ptr, None, nnz, H, 1, w_conv.ptr, None))             # [H][nnz] for the convolution
+        check(L.hb_stream_synchronize(None))
+        for b in bufs + [w_plan]:
+            b.free()
+        return DeviceRouteKernel(indices, nn, nn, H, w_rows, w_conv)
+    weights = w_rows.to_host((nnz, H))
+    for b in bufs + [w_plan, w_rows]:
+        b.free()
+    return SparseRouteKernel(indices, weights, nn, nn)
 
 
 class SparseRouteConvolution:

@@ -76,6 +76,71 @@ def gather_nodes(local: np.ndarray, n_nodes: int, group=None, device: Optional[s
 
 
 # ---------------------------------------------------------------------------------------------------
+# The communicator INSIDE the library (C-ABI `hb_comm_*`, csrc/hb_comm.cu): what a Julia host would use.
+# ---------------------------------------------------------------------------------------------------
+class LibComm:
+    """`hb_comm_t` of this rank.  The 128-byte NCCL id of rank 0 reaches the other ranks through whatever the host has —
+    here `torch.distributed` (any backend); a Julia host would use MPI or a shared file.  `halo_mode`: "nccl" = pack
+    kernel + one grouped ncclSend/ncclRecv per neighbour + unpack kernel, all on the compute stream; "peer" = the pack
+    kernel stores the blocks straight into the neighbours' staging over NVLink (CUDA IPC peer pointers) and publishes an
+    epoch flag the neighbour's unpack kernel waits for."""
+
+    def __init__(self, rank: int, world: int, group=None, halo_mode: str = "nccl"):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from .engine import check, lib
+        if halo_mode not in ("nccl", "peer"):
+            raise ValueError("halo_mode must be 'nccl' or 'peer'")
+        self.rank, self.world, self.halo_mode = int(rank), int(world), halo_mode
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            check(lib().hb_comm_unique_id(buf, 128))
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        h = C.c_void_p()
+        check(lib().hb_comm_init(raw, self.rank, self.world, C.byref(h)))
+        self.handle = h
+        self._peer_bytes = 0
+
+    def enable_peer(self, max_block_bytes: int):
+        from .engine import check, lib
+        if self._peer_bytes == 0:
+            check(lib().hb_halo_enable_peer(self.handle, int(max_block_bytes)))
+            self._peer_bytes = int(max_block_bytes)
+        elif max_block_bytes > self._peer_bytes:
+            raise ValueError("peer staging was reserved for smaller blocks")
+
+    def halo_exchange(self, plane_ptrs: Sequence[int], pitch: int, edges, stream: Optional[int] = None):
+        """`edges`: [(peer, s_row0, s_col0, r_row0, r_col0, nrows, ncols, peer_slot)]; collective, asynchronous on `stream`."""
+        import ctypes as C
+        from .engine import HaloEdge, check, lib
+        n = len(plane_ptrs)
+        planes = (C.c_void_p * n)(*[int(x) for x in plane_ptrs])
+        earr = (HaloEdge * max(1, len(edges)))(*[HaloEdge(*[int(v) for v in e]) for e in edges])
+        mode = 1 if self.halo_mode == "peer" else 0
+        if mode == 1:
+            self.enable_peer(max([n * e[5] * e[6] * 8 for e in edges] or [8]))
+        check(lib().hb_halo_exchange_device(self.handle, planes, n, int(pitch), earr, len(edges), mode, stream))
+
+    def all_gather(self, send_ptr: int, recv_ptr: int, nbytes: int, stream: Optional[int] = None):
+        from .engine import check, lib
+        check(lib().hb_comm_all_gather(self.handle, send_ptr, recv_ptr, int(nbytes), stream))
+
+    def status(self, stream: Optional[int] = None):
+        from .engine import check, lib
+        check(lib().hb_halo_status(self.handle, stream))
+
+    def free(self):
+        from .engine import lib
+        if getattr(self, "handle", None):
+            lib().hb_comm_free(self.handle)
+            self.handle = None
+
+
+# ---------------------------------------------------------------------------------------------------
 # Sharded routing: contiguous node slices + ghost outflows exchanged every step (SURVEY.md §8e)
 # ---------------------------------------------------------------------------------------------------
 class RoutePartition:
@@ -259,6 +324,16 @@ class GridStripPlan:
         return out
 
 
+def strip_halo_edges(plan: GridStripPlan):
+    """The strip's neighbours as `hb_halo_edge` tuples (planes are `[rows_local][cols]`, pitch = cols)."""
+    C_, out = plan.cols, []
+    for peer, (s0, s1), (q0, q1) in plan.exchanges():
+        # the peer lists its lower-rank neighbour first: I am its LAST edge when I am above it, its FIRST when below
+        peer_slot = (1 if peer > 0 else 0) if peer < plan.rank else 0
+        out.append((peer, s0 // C_, 0, q0 // C_, 0, (s1 - s0) // C_, C_, peer_slot))
+    return out
+
+
 def exchange_strip_states(states: Sequence, plan: GridStripPlan, group=None):
     """Refresh the ghost rows of every state array (`[..., n_local]` torch tensors, node axis last and contiguous)
     from the neighbouring ranks (grouped send/recv: NCCL on GPUs, gloo in the CPU tests)."""
@@ -285,12 +360,14 @@ class ShardedGridRun:
     The forcing passed to `launch` covers the rank's COMPUTED rows: `[T][plan.n_local][V]`."""
 
     def __init__(self, eng, rows: int, cols: int, T: int, params, *, config=None, initstates=None, halo: int = 16, group=None,
-                 stages: int = 0, max_registers: int = 0, block_threads: int = 0):
+                 stages: int = 0, max_registers: int = 0, block_threads: int = 0, comm: Optional["LibComm"] = None):
+        """`comm`: a `LibComm` — the ghost states then travel through the library's own exchange (`hb_halo_exchange_device`:
+        NCCL or NVLink peer stores) on the compute stream instead of `torch.distributed` point-to-point calls."""
         import torch
         import torch.distributed as dist
         from .engine import GridDeviceRun
 
-        self.group = group
+        self.group, self.comm = group, comm
         self.rank, self.world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
         self.plan = GridStripPlan(rows, cols, self.rank, self.world, halo)
         pl = self.plan
@@ -331,9 +408,16 @@ class ShardedGridRun:
                                   pl.out_first, pl.out_count, stream)
             cur ^= 1
             if t0 + ns < self.T and self.world > 1:
-                exchange_strip_states([self.bucket[cur], self.river[cur]], pl, self.group)
+                if self.comm is not None:
+                    S = self.run.n_states
+                    planes = [self.bucket[cur].data_ptr() + s * pl.n_local * 8 for s in range(S)] + [self.river[cur].data_ptr()]
+                    self.comm.halo_exchange(planes, pl.cols, strip_halo_edges(pl), stream)
+                else:
+                    exchange_strip_states([self.bucket[cur], self.river[cur]], pl, self.group)
 
     def check(self) -> int:
+        if self.comm is not None:
+            self.comm.status()
         return self.run.check()
 
 
@@ -368,6 +452,17 @@ class GridPanelPlan:
         if self.rank < self.world - 1:
             out.append((self.rank + 1, (self.c1 - H - self.g0, self.c1 - self.g0), (self.c1 - self.g0, self.g1 - self.g0)))
         return out
+
+
+def panel_halo_edges(plan: GridPanelPlan):
+    """The panel's neighbours as `hb_halo_edge` tuples (planes are `[rows][local_cols]`, pitch = local_cols)."""
+    out = []
+    for peer, (s0, s1), (q0, q1) in plan.exchanges():
+        # edge lists are [left neighbour (if any), right neighbour (if any)]: seen from my LEFT neighbour I am its right
+        # edge (slot 1, or 0 when it has no left neighbour); seen from my RIGHT neighbour I am its left edge (slot 0)
+        peer_slot = (1 if peer > 0 else 0) if peer < plan.rank else 0
+        out.append((peer, 0, s0, 0, q0, plan.rows, s1 - s0, peer_slot))
+    return out
 
 
 def exchange_panel_states(states: Sequence, plan: GridPanelPlan, group=None):
@@ -415,12 +510,14 @@ class ShardedPanelRun:
     `[T][rows][owned columns][R]` for the owned cells."""
 
     def __init__(self, eng, rows: int, cols: int, T: int, params, *, config=None, initstates=None, halo: int = 32, group=None,
-                 stages: int = 0, max_registers: int = 0, block_threads: int = 0, steps_per_launch: int = 0):
+                 stages: int = 0, max_registers: int = 0, block_threads: int = 0, steps_per_launch: int = 0,
+                 comm: Optional["LibComm"] = None):
         import torch
         import torch.distributed as dist
         from .engine import B200Model, GridDeviceRun
 
-        self.group = group
+        self.group, self.comm = group, comm
+        self.exchange_events = None          # [(start, end)] CUDA events around the exchanges of the last launch (set by `time_exchange`)
         self.rank, self.world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
         self.plan = pl = GridPanelPlan(rows, cols, self.rank, self.world, halo)
         flw = np.asarray(eng.route.aggr.flwdir)[:, pl.g0:pl.g1]
@@ -457,9 +554,27 @@ class ShardedPanelRun:
                                   out_window=pl.out_window)
             cur ^= 1
             if t0 + ns < self.T and self.world > 1:
-                exchange_panel_states([self.bucket[cur], self.river[cur]], pl, self.group)
+                ev = None
+                if self.exchange_events is not None:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
+                if self.comm is not None:
+                    S = self.run.n_states
+                    planes = [self.bucket[cur].data_ptr() + s * pl.n_local * 8 for s in range(S)] + [self.river[cur].data_ptr()]
+                    self.comm.halo_exchange(planes, pl.local_cols, panel_halo_edges(pl), stream)
+                else:
+                    exchange_panel_states([self.bucket[cur], self.river[cur]], pl, self.group)
+                if ev is not None:
+                    ev[1].record()
+                    self.exchange_events.append(ev)
+
+    def halo_bytes_per_exchange(self) -> int:
+        """Bytes this rank SENDS per exchange (states of `halo` owned columns per neighbour)."""
+        return sum(e[5] * e[6] for e in panel_halo_edges(self.plan)) * (self.run.n_states + 1) * 8
 
     def check(self) -> int:
+        if self.comm is not None:
+            self.comm.status()
         return self.run.check()
 
 

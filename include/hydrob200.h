@@ -292,6 +292,19 @@ int hb_sparse_route_conv_ordered_device(int n_out, int n_in, int64_t n_steps, in
                                         const int32_t *src, const double *weights, const double *input,
                                         const int32_t *dest_order, double *out, void *stream);
 
+/* aggregate_route_kernel (/root/reference/src/route.jl:523-577) on the device: composition of the node kernels down the
+ * network, level by level (level_row_ptr is a HOST array of n_levels + 1 row offsets; everything else DEVICE).  Row r
+ * belongs to node row_dest[r]; its contributions contrib_ptr[r] .. contrib_ptr[r+1] name finished rows of upstream
+ * neighbours (contrib_row) with their edge weights, in the reference's accumulation order; a row without contributions is
+ * the node's own kernel.  weights is [n_rows][horizon].  Bit-identical to the reference's arithmetic. */
+int hb_irf_compose_device(int32_t n_levels, const int64_t *level_row_ptr, const int32_t *row_dest, const int64_t *contrib_ptr,
+                          const int64_t *contrib_row, const double *contrib_ew, const double *node_kernels, double *weights,
+                          int32_t horizon, void *stream);
+/* out row i = w row perm[i] (perm NULL = identity); transpose = 1 writes out[horizon][nnz], the layout
+ * hb_sparse_route_conv_device takes, else out[nnz][horizon] (SparseRouteKernel.weights). */
+int hb_irf_gather_rows_device(const double *w, const int64_t *perm, int64_t nnz, int32_t horizon, int32_t transpose, double *out,
+                              void *stream);
+
 /* ---- raster ingest (/root/reference/ext/HydroModelsRastersExt) -------------------------------------------------
  * compute_d8_flow_direction (HydroModelsRastersExt.jl:32-109): steepest-descent D8 codes (1 E, 2 SE, 4 S, 8 SW, 16 W,
  * 32 NW, 64 N, 128 NE; 0 for NaN cells) from a DEM.  dem[r * row_stride + c * col_stride] (element strides: a Julia
@@ -342,6 +355,44 @@ int hb_stream_create(void **stream);              /* a non-blocking cudaStream_t
 int hb_stream_destroy(void *stream);
 int hb_stream_synchronize(void *stream);
 
+
+/* ---- multi-GPU: one process per GPU (hb_init picks the device), a communicator inside the library -------------------
+ * The reference is single-process and single-threaded (src/config.jl:36 `parallel` is never read); SURVEY.md §8(e) shards the
+ * node axis.  Lumped / ensemble runs need no exchange (every rank calls hb_run on its slice; hb_comm_all_gather collects
+ * objective vectors).  A dense D8 grid (src/route.jl:336-404) is cut into row strips or column panels with `halo` ghost
+ * rows / columns; every `halo` steps the ghost cells' bucket and river STATES are refreshed from the neighbouring ranks with
+ * hb_halo_exchange_device.  NCCL is resolved at run time from libnccl.so.2 ($HB_NCCL_LIB overrides); the 128-byte id of
+ * rank 0 travels to the other ranks by whatever the host has (MPI, a file, torch.distributed). */
+typedef struct hb_comm_s *hb_comm_t;
+int hb_comm_unique_id(void *id, int32_t id_bytes);                 /* rank 0: ncclGetUniqueId into id[128] */
+int hb_comm_init(const void *id, int32_t rank, int32_t world, hb_comm_t *out);      /* collective (ncclCommInitRank) */
+int hb_comm_rank(hb_comm_t c, int32_t *rank, int32_t *world);
+int hb_comm_free(hb_comm_t c);
+int hb_comm_all_gather(hb_comm_t c, const void *send, void *recv, int64_t bytes_per_rank, void *stream);   /* DEVICE buffers */
+/* Collective symmetric allocation: every rank allocates `bytes` (zeroed) and maps the other ranks' copies through CUDA IPC
+ * (NVLink peer access); hb_comm_peer_ptr returns rank `peer`'s copy as an address valid in THIS process. */
+int hb_comm_alloc(hb_comm_t c, int64_t bytes, void **local_ptr, int32_t *segment);
+int hb_comm_peer_ptr(hb_comm_t c, int32_t segment, int32_t peer, void **ptr);
+
+/* One neighbour of a sub-grid.  All planes are [rows][pitch] double arrays (bucket state s of cell (r, c) at
+ * planes[s][r * pitch + c]; the river state is one more plane).  The block I send and the block I receive have the same shape. */
+typedef struct {
+    int32_t peer;               /* rank on the other side */
+    int32_t s_row0, s_col0;     /* first cell of the block of MY owned cells the peer needs */
+    int32_t r_row0, r_col0;     /* first cell of MY ghost block the peer fills */
+    int32_t nrows, ncols;       /* block shape */
+    int32_t peer_slot;          /* index of the matching edge in the PEER's edge list (its staging slot; peer-store mode) */
+} hb_halo_edge;
+#define HB_HALO_NCCL 0          /* pack kernel, one grouped ncclSend/ncclRecv per neighbour on `stream`, unpack kernel */
+#define HB_HALO_PEER 1          /* pack kernel stores into the neighbours' staging over NVLink + epoch flag; unpack kernel waits for it */
+/* Collective, once per communicator before the first HB_HALO_PEER exchange: reserve the symmetric staging
+ * (`max_block_bytes` >= n_planes * nrows * ncols * 8 of the largest block). */
+int hb_halo_enable_peer(hb_comm_t c, int64_t max_block_bytes);
+/* Refresh the ghost blocks of `planes` (HOST array of n_planes DEVICE pointers) from the neighbours, asynchronous on `stream`.
+ * Every rank calls it the same number of times, in the same order, on one stream; at most 8 planes and 8 edges. */
+int hb_halo_exchange_device(hb_comm_t c, double *const *planes, int32_t n_planes, int32_t pitch, const hb_halo_edge *edges,
+                            int32_t n_edges, int32_t mode, void *stream);
+int hb_halo_status(hb_comm_t c, void *stream);    /* synchronises; error if a peer-mode wait expired */
 
 /* ---- measurement probes (bench.py) --------------------------------------------------------- */
 int hb_probe_fp64_tflops(double *tflops);                       /* measured FP64 FMA peak (2 flop/FMA) */

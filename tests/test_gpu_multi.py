@@ -75,7 +75,13 @@ def test_sharded_grid_routing_matches_single_gpu():
     assert np.array_equal(got, single)
 
 
-def _strip_worker(rank, world, port, R, Cc, T, halo, q):
+def _lib_comm(par, rank, world, exchange):
+    """`exchange`: "torch" = torch.distributed point-to-point calls from Python; "nccl" / "peer" = the library's own exchange
+    (`hb_comm_*` + `hb_halo_exchange_device`: grouped NCCL send/recv, or NVLink peer stores with epoch flags)."""
+    return None if exchange == "torch" else par.LibComm(rank, world, halo_mode=exchange)
+
+
+def _strip_worker(rank, world, port, R, Cc, T, halo, q, exchange="torch"):
     import torch
     import torch.distributed as dist
     from hydromodels_jl_b200 import parallel as par
@@ -85,7 +91,8 @@ def _strip_worker(rank, world, port, R, Cc, T, halo, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     model, p, init, N = _grid_problem(R, Cc, T)
     eng = hm.B200Model(model)
-    run = par.ShardedGridRun(eng, R, Cc, T, p, initstates=init, halo=halo)
+    comm = _lib_comm(par, rank, world, exchange)
+    run = par.ShardedGridRun(eng, R, Cc, T, p, initstates=init, halo=halo, comm=comm)
     n_lo, n_hi = run.plan.node_range()
     inp = sy.forcing("exphydro", n_lo, n_hi, T)                     # forcing of the computed rows (ghost rows included)
     d_in = torch.from_numpy(np.ascontiguousarray(inp.transpose(2, 1, 0))).cuda()
@@ -99,16 +106,17 @@ def _strip_worker(rank, world, port, R, Cc, T, halo, q):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("exchange", ["torch", "nccl", "peer"])
 @pytest.mark.parametrize("R,Cc,T,halo", [(40, 33, 50, 4), (96, 64, 40, 16)])
-def test_sharded_wave_grid_matches_single_gpu(R, Cc, T, halo):
+def test_sharded_wave_grid_matches_single_gpu(R, Cc, T, halo, exchange):
     """Row strips + ghost rows, states exchanged every `halo` steps (temporal blocking): bit-identical to one GPU.  Uses
     up to 4 GPUs when the box has them (interior ranks exchange with two neighbours)."""
     import torch.multiprocessing as mp
     world = min(_ngpu(), 4)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 34500 + (os.getpid() % 2000) + halo
-    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, R, Cc, T, halo, q)) for r in range(world)]
+    port = 34500 + (os.getpid() % 2000) + halo + 100 * ["torch", "nccl", "peer"].index(exchange)
+    procs = [ctx.Process(target=_strip_worker, args=(r, world, port, R, Cc, T, halo, q, exchange)) for r in range(world)]
     for pr in procs:
         pr.start()
     model, p, init, N = _grid_problem(R, Cc, T)
@@ -157,7 +165,7 @@ def test_strip_of_a_grid_on_one_gpu_matches_the_whole_grid():
         assert np.array_equal(r1.cpu().numpy()[own], whole[2, pl.r0 * Cc:pl.r1 * Cc, halo - 1])
 
 
-def _panel_worker(rank, world, port, R, Cc, T, halo, q):
+def _panel_worker(rank, world, port, R, Cc, T, halo, q, exchange="torch"):
     import torch
     import torch.distributed as dist
     from hydromodels_jl_b200 import parallel as par
@@ -166,7 +174,7 @@ def _panel_worker(rank, world, port, R, Cc, T, halo, q):
     hm.engine.init(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     model, p, init, N = _grid_problem(R, Cc, T)
-    run = par.ShardedPanelRun(hm.B200Model(model), R, Cc, T, p, initstates=init, halo=halo)
+    run = par.ShardedPanelRun(hm.B200Model(model), R, Cc, T, p, initstates=init, halo=halo, comm=_lib_comm(par, rank, world, exchange))
     inp = sy.forcing("exphydro", 0, N, T)[:, run.plan.idx, :]       # forcing of the computed cells, local row-major order
     d_in = torch.from_numpy(np.ascontiguousarray(inp.transpose(2, 1, 0))).cuda()
     rec = torch.zeros((T, run.N, run.n_rows), dtype=torch.float64, device="cuda")
@@ -179,16 +187,17 @@ def _panel_worker(rank, world, port, R, Cc, T, halo, q):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("exchange", ["torch", "nccl", "peer"])
 @pytest.mark.parametrize("R,Cc,T,halo", [(30, 41, 25, 4), (64, 256, 70, 32)])
-def test_sharded_column_panels_match_single_gpu(R, Cc, T, halo):
+def test_sharded_column_panels_match_single_gpu(R, Cc, T, halo, exchange):
     """Column panels + ghost columns (sub-model restricted to the panel's cells, global parameter vectors gathered through
     htypes), states exchanged every `halo` steps: bit-identical to one GPU."""
     import torch.multiprocessing as mp
     world = min(_ngpu(), 4)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 36500 + (os.getpid() % 2000) + halo
-    procs = [ctx.Process(target=_panel_worker, args=(r, world, port, R, Cc, T, halo, q)) for r in range(world)]
+    port = 36500 + (os.getpid() % 2000) + halo + 100 * ["torch", "nccl", "peer"].index(exchange)
+    procs = [ctx.Process(target=_panel_worker, args=(r, world, port, R, Cc, T, halo, q, exchange)) for r in range(world)]
     for pr in procs:
         pr.start()
     model, p, init, N = _grid_problem(R, Cc, T)

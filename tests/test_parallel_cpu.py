@@ -286,3 +286,23 @@ def test_panel_plan_with_ghost_columns_reproduces_the_whole_grid(world, halo):
     init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 2, N))
     ref = ho.run_model(model, sy.forcing("exphydro", 0, N, T), {"params": pg}, initstates=init)
     assert np.array_equal(got.reshape(13, N, T), ref)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5, 8])
+def test_library_halo_edges_pair_up_between_neighbouring_ranks(world):
+    """`hb_halo_edge` lists of the strips / panels (what `LibComm.halo_exchange` hands to `hb_halo_exchange_device`): every
+    edge's `peer_slot` must name the matching edge of the peer, with the same block shape, and the block I send must be,
+    in GLOBAL cell coordinates, exactly the ghost block the peer receives."""
+    from hydromodels_jl_b200.parallel import GridPanelPlan, GridStripPlan, panel_halo_edges, strip_halo_edges
+    rows, cols, halo = 64 * world + 3, 40 * world + 7, 16
+    panels = [GridPanelPlan(rows, cols, r, world, halo) for r in range(world)]
+    strips = [GridStripPlan(rows, cols, r, world, halo) for r in range(world)]
+    for plans, edges_of, origin in ((panels, panel_halo_edges, lambda pl: (0, pl.g0)), (strips, strip_halo_edges, lambda pl: (pl.g0, 0))):
+        all_edges = [edges_of(pl) for pl in plans]
+        for r, edges in enumerate(all_edges):
+            assert len(edges) == (r > 0) + (r < world - 1)
+            for k, (peer, sr, sc, rr, rc, nr, nc, slot) in enumerate(edges):
+                back = all_edges[peer][slot]
+                assert back[0] == r and back[7] == k and (back[5], back[6]) == (nr, nc)
+                o_me, o_peer = origin(plans[r]), origin(plans[peer])
+                assert (sr + o_me[0], sc + o_me[1]) == (back[3] + o_peer[0], back[4] + o_peer[1])
