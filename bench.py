@@ -478,16 +478,23 @@ def bench_single_basin(args):
 
 
 def bench_irf(args):
-    """SparseRouteConvolution on a synthetic river network — 65 536 nodes, 8 source rows per destination
-    (nnz = 524 288), horizon 32, 3650 steps: 2 * nnz * T * H = 1.2e11 flop per pass, FP64-FMA bound."""
+    """IRF routing of a synthetic RIVER TREE — 65 536 nodes, horizon 32, 3650 steps.  The aggregated
+    kernel (one row per (destination, upstream source) pair, ~1.1 M rows) is built end to end by `aggregate_route_kernel`
+    (host plan from the sparse edge list + level-synchronous composition on the device, timed), and `SparseRouteConvolution`
+    then runs on it: 2 * nnz * T * H flop per pass, FP64-FMA bound.  `--workload irf_route_ragged` keeps the Pareto-count
+    synthetic CSR of round 1 for comparison."""
     import torch
     import ctypes as C
     import hydromodels_jl_b200 as hm
+    from hydromodels_jl_b200 import irf
     from hydromodels_jl_b200.engine import check, lib
     hm.engine.init(0)
-    n, per, H, T = 65536, 8, 32, 3650
+    n, H, T = 65536, 32, 3650
     g = torch.Generator(device="cuda"); g.manual_seed(3)
     ragged = args.workload == "irf_route_ragged"
+    build = None
+    L = lib()
+    L.hb_sparse_route_conv_ordered_device.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64] + [C.c_void_p] * 7
     if ragged:
         # row counts of an aggregated kernel are skewed (headwaters see themselves, outlets see hundreds of upstream nodes):
         # Pareto-distributed counts, mean ~8, capped at 256
@@ -497,53 +504,68 @@ def bench_irf(args):
         row_ptr = torch.tensor(ptr, dtype=torch.int32, device="cuda")
         dest_of = torch.repeat_interleave(torch.arange(n, device="cuda"), torch.tensor(cnt, device="cuda"))
         src = (dest_of - torch.randint(0, 256, (nnz,), generator=g, device="cuda")).clamp_(min=0).to(torch.int32).contiguous()
-        from hydromodels_jl_b200.irf import balanced_destination_order
-        order = torch.tensor(balanced_destination_order(cnt, int(os.environ.get("HB_IRF_ORDER_WINDOW", "4096"))), device="cuda")
+        order = torch.tensor(irf.balanced_destination_order(cnt, int(os.environ.get("HB_IRF_ORDER_WINDOW", "4096"))), device="cuda")
+        w = torch.rand(H, nnz, generator=g, device="cuda", dtype=torch.float64) / H
+        ptrs = (row_ptr.data_ptr(), src.data_ptr(), w.data_ptr(), order.data_ptr())
     else:
-        nnz = n * per
-        row_ptr = (torch.arange(n + 1, device="cuda", dtype=torch.int32) * per).contiguous()
-        # sources: the destination itself and 7 nodes a short way "upstream" of it (river networks are local in node order)
-        src = (torch.arange(n, device="cuda").view(n, 1) - torch.randint(0, 256, (n, per), generator=g, device="cuda")).clamp_(min=0)
-        src[:, 0] = torch.arange(n, device="cuda")
-        src = src.to(torch.int32).reshape(-1).contiguous()
-        order = None
-    w = torch.rand(H, nnz, generator=g, device="cuda", dtype=torch.float64) / H
+        down = irf.synthetic_river_tree(n, seed=3)
+        up = np.nonzero(down >= 0)[0]
+        rng = np.random.default_rng(3)
+        route = irf.RouteIRF(["k"], lambda p, dt, h: (1 - np.exp(-dt / p[0])) * np.exp(-np.arange(h) * dt / p[0]))   # linear reservoir
+        kernels = irf.build_irf_kernels(route, rng.uniform(0.5, 3.0, (n, 1)), horizon=H)
+        irf.aggregate_route_kernel((down[up][:64], up[:64]), kernels[:max(int(down[up][:64].max()) + 1, 65)], horizon=H)   # warm-up: module load
+        t0 = time.perf_counter()
+        K = irf.aggregate_route_kernel((down[up], up), kernels, horizon=H, keep_on_device=True)
+        build_s = time.perf_counter() - t0
+        conv = irf.SparseRouteConvolution(K)                      # destinations longer than 64 rows are split into segments
+        conv_whole = irf.SparseRouteConvolution(K, segment_rows=None)
+        nnz = int(K.indices.shape[0])
+        cnt = np.bincount(K.indices[:, 0] - 1, minlength=n)
+        t0 = time.perf_counter()
+        plan = irf.plan_route_composition((down[up], up), n, None)
+        plan_s = time.perf_counter() - t0
+        build = {"aggregate_route_kernel_s": build_s, "host_plan_s": plan_s, "levels": len(plan.level_row_ptr) - 1, "rows": nnz,
+                 "truncated_convolutions": int(plan.contrib_row.size), "network": "synthetic_river_tree(65536, seed=3): 1-3 tributaries per node"}
     x = torch.rand(T, n, generator=g, device="cuda", dtype=torch.float64)
     out = torch.empty(T, n, device="cuda", dtype=torch.float64)
-    L = lib()
-    L.hb_sparse_route_conv_ordered_device.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64] + [C.c_void_p] * 7
 
-    def timed(order_ptr):
-        fn = lambda: check(L.hb_sparse_route_conv_ordered_device(n, n, T, H, nnz, row_ptr.data_ptr(), src.data_ptr(), w.data_ptr(), x.data_ptr(),
-                                                                 order_ptr, out.data_ptr(), None))
-        for _ in range(3):
+    def timed(fn, steps):
+        for _ in range(min(3, steps)):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             fn()
         e1.record(); torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / args.steps
+        return e0.elapsed_time(e1) / steps
 
-    ms = timed(order.data_ptr() if order is not None else None)
-    extra = {}
     if ragged:
+        call = lambda order_ptr: (lambda: check(L.hb_sparse_route_conv_ordered_device(n, n, T, H, nnz, ptrs[0], ptrs[1], ptrs[2], x.data_ptr(),
+                                                                                       order_ptr, out.data_ptr(), None)))
+        ms = timed(call(ptrs[3]), args.steps)
         ref = out.clone()
-        extra = {"unordered_ms": timed(None), "rows_per_destination": {"mean": nnz / n, "max": int(cnt.max())}}
+        extra = {"unordered_ms": timed(call(None), args.steps), "rows_per_destination": {"mean": nnz / n, "max": int(cnt.max())}}
         extra["bit_identical_to_unordered"] = bool(torch.equal(ref, out))
+    else:
+        ms = timed(lambda: conv.launch(x.data_ptr(), out.data_ptr(), T), args.steps)
+        ref = out.clone()
+        whole_ms = timed(lambda: conv_whole.launch(x.data_ptr(), out.data_ptr(), T), 2)
+        rel = float(((ref - out).abs() / out.abs().clamp_min(1e-300)).max().item())
+        extra = {"rows_per_destination": {"mean": nnz / n, "max": int(cnt.max())}, "segment_rows": 64, "virtual_destinations": conv.n_virtual,
+                 "whole_destinations_ms": whole_ms, "max_relative_difference_vs_whole_destinations": rel, "kernel_build": build}
     flop = 2.0 * nnz * T * H
     v = C.c_double()
     L.hb_probe_fp64_tflops(C.byref(v))
     peak, peak_src = peaks()
     print(json.dumps({"metric": "node-timesteps/sec of the IRF routing convolution", "value": n * T / (ms * 1e-3), "unit": "node-timesteps/s", "n_gpus": 1,
                       "steps": args.steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": ("irf_route_ragged_65536x3650_h32" if ragged else "irf_route_65536x3650_h32"), "nodes": n, "nnz": nnz,
+                      "config": {"workload": ("irf_route_ragged_65536x3650_h32" if ragged else "irf_route_river_tree_65536x3650_h32"), "nodes": n, "nnz": nnz,
                                  "horizon": H, "timesteps": T, **extra},
                       "roofline": {"bound": "fp64", "achieved": flop / ms / 1e9, "peak": v.value, "unit": "TFLOP/s", "frac": flop / ms / 1e9 / v.value,
                                    "peak_source": "measured DFMA probe (hb_probe_fp64_tflops)", "kernel": "hb_sparse_conv", "kernel_ms": ms,
                                    "hbm_GBps_compulsory": (2 * n * T * 8 + nnz * H * 8) / ms / 1e6, "hbm_peak": peak},
-                      "gpu_launches": args.steps + 3}))
+                      "gpu_launches": 3 * (args.steps + 3) + (build["levels"] + 2 if build else 0)}))
     return 0
 
 

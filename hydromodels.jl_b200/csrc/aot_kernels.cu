@@ -449,6 +449,31 @@ __global__ void __launch_bounds__(256) hb_irf_gather_rows_kernel(const double *_
 
 }  // namespace
 
+namespace {
+// out[t][d] = part[t][seg_ptr[d]] + part[t][seg_ptr[d] + 1] + ... in that order (a destination whose kernel rows were split
+// into segments, each convolved as a "virtual destination" by a different block)
+__global__ void __launch_bounds__(256) hb_irf_reduce_segments_kernel(int n_out, long long T, int n_virtual, const int *__restrict__ seg_ptr,
+                                                                     const double *__restrict__ part, double *__restrict__ out) {
+    const int d = blockIdx.x * 32 + (threadIdx.x & 31);
+    const long long t = (long long)blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (d >= n_out || t >= T) return;
+    const double *p = part + t * n_virtual;
+    const int v0 = seg_ptr[d], v1 = seg_ptr[d + 1];
+    double s = v0 < v1 ? p[v0] : 0.0;
+    for (int v = v0 + 1; v < v1; ++v) s += p[v];
+    out[t * n_out + d] = s;
+}
+}  // namespace
+
+extern "C" int hb_irf_reduce_segments_device(int32_t n_out, int64_t n_steps, int32_t n_virtual, const int32_t *seg_ptr, const double *part,
+                                             double *out, void *stream) {
+    if (n_out <= 0 || n_steps < 0 || n_virtual < n_out || !seg_ptr || !part || !out) return HB_ERR_INVALID;
+    if (n_steps == 0) return HB_OK;
+    dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((n_steps + 7) / 8));
+    hb_irf_reduce_segments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_steps, n_virtual, seg_ptr, part, out);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
 extern "C" int hb_irf_compose_device(int32_t n_levels, const int64_t *level_row_ptr, const int32_t *row_dest, const int64_t *contrib_ptr,
                                      const int64_t *contrib_row, const double *contrib_ew, const double *node_kernels, double *weights,
                                      int32_t horizon, void *stream) {

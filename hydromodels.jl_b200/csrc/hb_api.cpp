@@ -304,7 +304,9 @@ int load_model(hb_model_s *m) {
     if (rc) return rc;
     HB_DRV(g_drv.ModuleLoadData(&m->module, m->cubin.data()));
     HB_DRV(g_drv.ModuleGetFunction(&m->func, m->module, m->kernel_name.c_str()));
-    if (m->dyn_smem > 48 * 1024)
+    // the 48 KB default limit counts static + dynamic shared memory (the templates hold a 2 KB exp table statically): opt in
+    // whenever the sum comes near it, not only when the dynamic part alone exceeds it
+    if (m->dyn_smem + 4096 > 48 * 1024)
         HB_DRV(g_drv.FuncSetAttribute(m->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
     if (m->spec.nn_words > 0) {
         size_t bytes = 0;

@@ -139,6 +139,7 @@ def lib():
                                 C.c_void_p],
         "hb_irf_compose_device": [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                   C.c_void_p],
+        "hb_irf_reduce_segments_device": [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
         "hb_irf_gather_rows_device": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
         "hb_de_best_device": [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p],
         "hb_malloc_device": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_device": [C.c_void_p],

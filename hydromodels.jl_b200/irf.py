@@ -28,6 +28,23 @@ def balanced_destination_order(counts, window: int = 4096) -> np.ndarray:
     return out
 
 
+def synthetic_river_tree(n_nodes: int, seed: int = 0, p_children=(0.3, 0.45, 0.25)) -> np.ndarray:
+    """A river-like tree for benchmarks and tests: `down[i]` = the node that node `i` drains into (-1 for the outlet, node
+    `n_nodes - 1`).  Built breadth-first from the outlet, every node receiving 1, 2 or 3 tributaries (reaches, confluences)
+    with probabilities `p_children`, and numbered so that every node's id is smaller than its downstream neighbour's
+    (ids are a topological order, headwaters first).  Mean depth ~ log2(n): 65 536 nodes give ~1 M (destination, source)
+    kernel rows."""
+    n = int(n_nodes)
+    rng = np.random.default_rng(seed)
+    c = rng.choice(np.array([1, 2, 3]), size=n, p=np.asarray(p_children, dtype=float))
+    first_child = 1 + np.cumsum(c) - c                       # breadth-first index of a node's first tributary
+    j = np.arange(1, n)
+    parent = np.searchsorted(first_child, j, side="right") - 1
+    down = np.full(n, -1, dtype=np.int64)
+    down[n - 1 - j] = n - 1 - parent
+    return down
+
+
 class RouteIRF:
     """`RouteIRF(params, kernel_func)` (`src/route.jl:417-432`): `kernel_func(params, delta_t, horizon)`
     returns the node's impulse response; the call pads / truncates it to `horizon`."""
@@ -307,23 +324,84 @@ class SparseRouteConvolution:
     """`SparseRouteConvolution(kernel)` functor (`src/route.jl:482-495,593-610`): `out[n_out, T] = conv(input[n_in, T])`
     on the GPU."""
 
-    def __init__(self, kernel: SparseRouteKernel, *, name: Optional[str] = None, inputs=(), outputs=(), params=()):
+    def __init__(self, kernel, *, name: Optional[str] = None, inputs=(), outputs=(), params=(), segment_rows: Optional[int] = 64):
+        """`kernel`: a `SparseRouteKernel` (host weights) or a `DeviceRouteKernel` (weights already on the device, as
+        `aggregate_route_kernel(..., keep_on_device=True)` leaves them).  `segment_rows`: destinations with more kernel rows
+        than this are split into segments convolved by different blocks and added up in order afterwards (river networks:
+        the outlet has one row per node); `None` keeps every destination whole (the reference's single running sum)."""
         self.kernel = kernel
         self.name = name or "##sparse_route"
         self.input_names, self.output_names, self.param_names = list(inputs), list(outputs), list(params)
-        dest = kernel.indices[:, 0] - 1
-        order = np.argsort(dest, kind="stable")                       # CSR by destination, row order kept
-        self._src = np.ascontiguousarray((kernel.indices[order, 1] - 1).astype(np.int32))
-        ptr = np.zeros(kernel.n_out + 1, dtype=np.int64)
-        np.add.at(ptr, dest + 1, 1)
-        self._row_ptr = np.cumsum(ptr).astype(np.int32)
-        self._w = np.ascontiguousarray(kernel.weights[order].T)       # [H][nnz]
-        # destinations by decreasing row count: the 32 destinations of a kernel block then finish together
-        counts = np.diff(self._row_ptr)
-        self._dest_order = balanced_destination_order(counts) if counts.size and counts.max() != counts.min() else None
         if kernel.indices.size and (kernel.indices[:, 1].max() > kernel.n_in or kernel.indices.min() < 1 or
                                     kernel.indices[:, 0].max() > kernel.n_out):
             raise ValueError("kernel indices out of range")
+        dest = kernel.indices[:, 0] - 1
+        sorted_rows = bool(np.all(np.diff(dest) >= 0))
+        order = np.arange(dest.size) if sorted_rows else np.argsort(dest, kind="stable")   # CSR by destination, row order kept
+        self._src = np.ascontiguousarray((kernel.indices[order, 1] - 1).astype(np.int32))
+        ptr = np.zeros(kernel.n_out + 1, dtype=np.int64)
+        np.add.at(ptr, dest + 1, 1)
+        row_ptr = np.cumsum(ptr)
+        self._w_dev = None
+        if isinstance(kernel, DeviceRouteKernel):
+            if not sorted_rows:
+                raise ValueError("a device-resident kernel must list its rows by destination")
+            self._w, self._w_dev = None, kernel.w_conv
+        else:
+            self._w = np.ascontiguousarray(kernel.weights[order].T)   # [H][nnz]
+        # long destinations -> segments ("virtual destinations"): same CSR rows, more row pointers
+        counts = np.diff(row_ptr)
+        self._seg_ptr = None
+        self.n_virtual = kernel.n_out
+        if segment_rows is not None and counts.size and counts.max() > int(segment_rows):
+            S = int(segment_rows)
+            nseg = np.maximum(1, -(-counts // S))
+            seg_ptr = np.concatenate([[0], np.cumsum(nseg)])
+            self.n_virtual = int(seg_ptr[-1])
+            which = np.repeat(np.arange(kernel.n_out), nseg)                   # virtual -> real destination
+            k_in = np.arange(self.n_virtual) - seg_ptr[which]                  # segment number inside its destination
+            v_start = row_ptr[which] + k_in * S
+            v_end = np.minimum(v_start + S, row_ptr[which + 1])
+            row_ptr = np.concatenate([v_start, [v_end[-1]]])
+            assert np.array_equal(row_ptr[1:], v_end)
+            self._seg_ptr = seg_ptr.astype(np.int32)
+            counts = np.diff(row_ptr)
+        self._row_ptr = row_ptr.astype(np.int32)
+        # destinations by decreasing row count: the 32 destinations of a kernel block then finish together
+        self._dest_order = balanced_destination_order(counts) if counts.size and counts.max() != counts.min() else None
+        self._static = None                                           # device copies of the CSR structure (first call)
+        self._part = None                                             # [T][n_virtual] partial results (split destinations)
+
+    def _device_structure(self):
+        from .engine import DeviceBuffer
+        if self._static is None:
+            w = self._w_dev if self._w_dev is not None else DeviceBuffer.from_host(self._w if self._w.size else np.zeros(1))
+            self._static = (DeviceBuffer.from_host(self._row_ptr), DeviceBuffer.from_host(self._src if self._src.size else np.zeros(1, np.int32)), w,
+                            DeviceBuffer.from_host(self._dest_order) if self._dest_order is not None else None,
+                            DeviceBuffer.from_host(self._seg_ptr) if self._seg_ptr is not None else None)
+        return self._static
+
+    def launch(self, in_ptr: int, out_ptr: int, T: int, stream: Optional[int] = None):
+        """Device-resident call: `in_ptr` `[T][n_in]`, `out_ptr` `[T][n_out]` (asynchronous on `stream`)."""
+        from .engine import DeviceBuffer, check, lib
+        k = self.kernel
+        L = lib()
+        L.hb_sparse_route_conv_ordered_device.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64] + [C.c_void_p] * 7
+        L.hb_sparse_route_conv_ordered_device.restype = C.c_int
+        rp, src, w, order, seg = self._device_structure()
+        nnz = len(self._src) if k.indices.size else 0
+        if seg is None:
+            check(L.hb_sparse_route_conv_ordered_device(k.n_out, k.n_in, int(T), k.horizon, nnz, rp.ptr, src.ptr, w.ptr, in_ptr,
+                                                        order.ptr if order is not None else None, out_ptr, stream))
+            return
+        need = int(T) * self.n_virtual * 8
+        if self._part is None or self._part.nbytes < need:
+            if self._part is not None:
+                self._part.free()
+            self._part = DeviceBuffer(need)
+        check(L.hb_sparse_route_conv_ordered_device(self.n_virtual, k.n_in, int(T), k.horizon, nnz, rp.ptr, src.ptr, w.ptr, in_ptr,
+                                                    order.ptr if order is not None else None, self._part.ptr, stream))
+        check(L.hb_irf_reduce_segments_device(k.n_out, int(T), self.n_virtual, seg.ptr, self._part.ptr, out_ptr, stream))
 
     def __call__(self, input, timing: Optional[dict] = None) -> np.ndarray:
         from .engine import DeviceBuffer, check, lib
@@ -335,19 +413,11 @@ class SparseRouteConvolution:
         if x.shape[0] != k.n_in:
             raise ValueError(f"Input node count {x.shape[0]} does not match kernel.n_in {k.n_in}.")
         T = x.shape[1]
-        L = lib()
-        L.hb_sparse_route_conv_ordered_device.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64] + [C.c_void_p] * 7
-        L.hb_sparse_route_conv_ordered_device.restype = C.c_int
         xin = np.asfortranarray(x)                                     # memory [T][n_in]
-        bufs = [DeviceBuffer.from_host(self._row_ptr), DeviceBuffer.from_host(self._src if self._src.size else np.zeros(1, np.int32)),
-                DeviceBuffer.from_host(self._w if self._w.size else np.zeros(1)), DeviceBuffer.from_host(xin.ravel(order="K") if xin.size else np.zeros(1))]
+        din = DeviceBuffer.from_host(xin.ravel(order="K") if xin.size else np.zeros(1))
         dout = DeviceBuffer(max(1, k.n_out * T) * 8)
-        if self._dest_order is not None:
-            bufs.append(DeviceBuffer.from_host(self._dest_order))
-        check(L.hb_sparse_route_conv_ordered_device(k.n_out, k.n_in, T, k.horizon, len(self._src) if k.indices.size else 0,
-                                                    bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr,
-                                                    bufs[4].ptr if self._dest_order is not None else None, dout.ptr, None))
+        self.launch(din.ptr, dout.ptr, T, None)
         out = dout.to_host((k.n_out, T), order="F")
-        for b in bufs + [dout]:
-            b.free()
+        din.free()
+        dout.free()
         return out[0] if vec else out

@@ -292,6 +292,13 @@ int hb_sparse_route_conv_ordered_device(int n_out, int n_in, int64_t n_steps, in
                                         const int32_t *src, const double *weights, const double *input,
                                         const int32_t *dest_order, double *out, void *stream);
 
+/* River networks are skewed: the outlet's kernel has one row per node of the basin, and a convolution block runs for as
+ * many rows as its longest destination.  The host therefore splits long destinations into segments of rows, convolves
+ * every segment as a "virtual destination" (hb_sparse_route_conv_ordered_device with n_out = n_virtual into
+ * part[T][n_virtual]) and this kernel adds a destination's segments in order: out[t][d] = sum part[t][seg_ptr[d] ..
+ * seg_ptr[d+1]).  Deterministic; differs from the reference's single running sum by rounding only (<= 1e-13 relative). */
+int hb_irf_reduce_segments_device(int32_t n_out, int64_t n_steps, int32_t n_virtual, const int32_t *seg_ptr, const double *part,
+                                  double *out, void *stream);
 /* aggregate_route_kernel (/root/reference/src/route.jl:523-577) on the device: composition of the node kernels down the
  * network, level by level (level_row_ptr is a HOST array of n_levels + 1 row offsets; everything else DEVICE).  Row r
  * belongs to node row_dest[r]; its contributions contrib_ptr[r] .. contrib_ptr[r+1] name finished rows of upstream

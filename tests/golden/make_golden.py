@@ -12,7 +12,8 @@ Only *data columns* of the reference's sample files are extracted (no source cod
 * m50_01013500.npz — first 2 000 rows of `/root/reference/data/m50/01013500.csv`
   (`Prcp, Temp, Lday, SnowWater, SoilWater`): forcing for the M50 test of
   `test/base/run_single_lumped.jl:192-203`.
-* hbv_sample.npz — `/root/reference/data/hbv_edu/hbv_sample.csv` (`prec, temp, pet`, first 2000).
+* hbv_sample.npz — `/root/reference/data/hbv_edu/hbv_sample.csv` (`prec, temp, pet` and, for plausibility only, the
+  third-party simulation's `qsim, snow, soil, s1, s2`; all 3652 rows).
 """
 import csv
 import os
@@ -43,7 +44,7 @@ def main():
     np.savez_compressed(f"{OUT}/gr4j_sample.npz", **d)
     d = read(f"{REF}/m50/01013500.csv", ["Prcp", "Temp", "Lday", "SnowWater", "SoilWater"], 2000)
     np.savez_compressed(f"{OUT}/m50_01013500.npz", **d)
-    d = read(f"{REF}/hbv_edu/hbv_sample.csv", ["prec", "temp", "pet"], 2000)
+    d = read(f"{REF}/hbv_edu/hbv_sample.csv", ["prec", "temp", "pet", "qsim", "snow", "soil", "s1", "s2"])
     np.savez_compressed(f"{OUT}/hbv_sample.npz", **d)
 
 

@@ -416,6 +416,89 @@ def test_wave_grid_kernel_matches_oracle_and_generic_path(R, Cc, T, tc):
     assert np.array_equal(eng(inp, p, initstates=init), wave)  # step counters / tickets are reset between runs
 
 
+@pytest.mark.parametrize("n,H,dag", [(300, 32, True), (1200, 16, False), (64, 70, True)])
+def test_route_kernel_composition_on_the_device_is_bit_identical_to_the_reference_loops(n, H, dag):
+    """`aggregate_route_kernel` (`/root/reference/src/route.jl:523-577`): host plan + level-synchronous device sweep against
+    the oracle's literal restatement of the reference loops — same rows, same weights to the last bit — for weighted
+    trees, DAGs whose branches re-join (several candidates accumulate into one row), the default node order, a
+    topological order and an arbitrary one, and with the kernel kept on the device for the convolution."""
+    from hydromodels_jl_b200 import irf
+    rng = np.random.default_rng(n + H)
+    A = np.zeros((n, n))
+    for i in range(n - 1):
+        A[min(n - 1, i + 1 + int(rng.geometric(0.25))), i] = rng.choice([1.0, 1.0, 0.5, 1.75])
+    if dag:
+        for i in range(0, n - 9, 5):
+            A[min(n - 1, i + 2 + int(rng.geometric(0.3))), i] = 0.125
+    kernels = [rng.random(rng.integers(2, H + 5)) for _ in range(n)]
+    kernels[1][0] = 0.0
+    for order in (None, irf.topological_order(A), list(rng.permutation(n) + 1)):
+        ref_idx, ref_w = ho.aggregate_route_kernel(A, kernels, H, order)
+        K = irf.aggregate_route_kernel(A, kernels, topo_order=order, horizon=H)
+        assert np.array_equal(K.indices, ref_idx)
+        assert np.array_equal(K.weights, ref_w)
+    Kd = irf.aggregate_route_kernel(A, kernels, horizon=H, keep_on_device=True)
+    K0 = irf.aggregate_route_kernel(A, kernels, horizon=H)
+    assert np.array_equal(Kd.weights, K0.weights)
+    x = np.abs(rng.normal(size=(n, 90)))
+    assert np.array_equal(irf.SparseRouteConvolution(Kd)(x), irf.SparseRouteConvolution(K0)(x))
+
+
+def test_long_destinations_are_split_into_segments_and_summed_in_order():
+    """A river outlet has one kernel row per node of its basin; `SparseRouteConvolution` splits destinations longer than
+    `segment_rows` into segments handled by different blocks and adds them in order.  Against the oracle (the reference's
+    single running sum) the result may differ by rounding only (tolerance 1e-12 relative, stated here); destinations that
+    were not split stay bit-identical to the unsplit run."""
+    from hydromodels_jl_b200 import irf
+    rng = np.random.default_rng(11)
+    n, H, T = 700, 16, 150
+    down = irf.synthetic_river_tree(n, seed=5)
+    up = np.nonzero(down >= 0)[0]
+    kernels = [np.exp(-np.arange(H) / k) * (1 - np.exp(-1 / k)) for k in rng.uniform(0.5, 3.0, n)]
+    K = irf.aggregate_route_kernel((down[up], up), kernels, horizon=H)
+    counts = np.bincount(K.indices[:, 0] - 1, minlength=n)
+    assert counts.max() == n and (counts > 40).sum() >= 3
+    x = np.abs(rng.normal(size=(n, T)))
+    ref = ho.sparse_route_convolution(K.indices, K.weights, n, n, x)
+    whole = irf.SparseRouteConvolution(K, segment_rows=None)(x)
+    assert_parity(whole, ref)
+    for S in (40, 7):
+        conv = irf.SparseRouteConvolution(K, segment_rows=S)
+        assert conv.n_virtual > n
+        got = conv(x)
+        assert_parity(got, ref, rtol=1e-12, atol=1e-300)
+        short = counts <= S
+        assert np.array_equal(got[short], whole[short])
+        assert np.array_equal(conv(x), got)                      # deterministic
+
+
+def test_river_tree_of_65536_nodes_is_aggregated_in_under_a_second():
+    import time
+    from hydromodels_jl_b200 import irf
+    n, H = 65536, 32
+    down = irf.synthetic_river_tree(n, seed=3)
+    up = np.nonzero(down >= 0)[0]
+    rng = np.random.default_rng(3)
+    kernels = [np.exp(-np.arange(H) / k) * (1 - np.exp(-1 / k)) for k in rng.uniform(0.5, 3.0, n)]
+    irf.aggregate_route_kernel((down[up][:8], up[:8]), kernels[:int(down[up][:8].max()) + 1], horizon=H)     # warm-up
+    t0 = time.perf_counter()
+    K = irf.aggregate_route_kernel((down[up], up), kernels, horizon=H, keep_on_device=True)
+    dt = time.perf_counter() - t0
+    assert K.indices.shape[0] > 1_000_000 and dt < 1.0, (K.indices.shape, dt)
+    # spot-check rows against first principles: the kernel of (dest, source) is the convolution along the path
+    w = K.weights
+    for row in rng.integers(0, K.indices.shape[0], 40):
+        d1, s1 = K.indices[row] - 1
+        ref = np.zeros(H); ref[0] = 1.0
+        cur = s1
+        while True:
+            ref = np.convolve(ref, kernels[cur])[:H]
+            if cur == d1:
+                break
+            cur = down[cur]
+        assert np.allclose(w[row], ref, rtol=1e-11, atol=1e-300)
+
+
 def _grid_case(R, Cc, T, seed=0):
     rng = np.random.default_rng(R * 1000 + Cc + seed)
     flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128, 0, 5], size=(R, Cc))
@@ -480,6 +563,8 @@ def test_sparse_route_convolution_matches_oracle():
     route = irf.RouteIRF(["k"], lambda p, dt, h: (1 - np.exp(-dt / p[0])) * np.exp(-np.arange(h) * dt / p[0]))
     kernels = irf.build_irf_kernels(route, rng.uniform(0.5, 3.0, (n, 1)), horizon=H)
     K = irf.aggregate_route_kernel(A, kernels, topo_order=irf.topological_order(A), horizon=H)
+    ref_idx, ref_w = ho.aggregate_route_kernel(A, kernels, H, irf.topological_order(A))
+    assert np.array_equal(K.indices, ref_idx) and np.array_equal(K.weights, ref_w)      # composed on the device, bit for bit
     conv = irf.SparseRouteConvolution(K)
     x = np.abs(rng.normal(size=(n, T)))
     got = conv(x)

@@ -243,6 +243,26 @@ def test_gr4j_runs(golden):
     assert abs(out[0, 50] - d["prob"][50]) / d["prob"][50] < 0.05
 
 
+def test_gr4j_transcription_is_plausible_against_the_reference_fixture(golden):
+    """`models.gr4j` (the equations both the oracle and the GPU path evaluate) against the third-party GR4J simulation the
+    reference ships (`data/gr4j/sample.csv`, ten years; parameters and initial states of `test/test_helpers.jl:172-185`).
+    Different numerics (the fixture's model is a continuous-time GR4J), so no equality — but a transcription error in the
+    production store, the routing store or the flow equation would break these bounds: measured here r = 0.9998 / 0.996 /
+    0.940 and biases of 0.7 % / -2.1 % / 0.8 %."""
+    d = golden("gr4j_sample.npz")
+    g = hm.models.gr4j()
+    out = ho.run_model(g, np.stack([d["prec"], d["pet"]]), {"params": dict(x1=320.11, x2=2.42, x3=69.63, x4=1.39)},
+                       initstates=dict(soilwater=235.97, routingstore=45.47))
+    names = g.var_names
+    for row, col, rmin, bias_max, nse_min in (("soilwater", "prob", 0.999, 0.015, 0.995), ("routingstore", "rout", 0.99, 0.04, 0.94),
+                                              ("flow", "qsim", 0.92, 0.03, 0.80)):
+        a, b = out[names.index(row)], d[col]
+        r = np.corrcoef(a, b)[0, 1]
+        bias = (a.mean() - b.mean()) / b.mean()
+        nse = 1 - np.sum((a - b) ** 2) / np.sum((b - b.mean()) ** 2)
+        assert r > rmin and abs(bias) < bias_max and nse > nse_min, (row, r, bias, nse)
+
+
 def test_m50_and_hbv_run(golden):
     d = golden("m50_01013500.npz")
     T = 200
@@ -264,6 +284,28 @@ def test_m50_and_hbv_run(golden):
     out = ho.run_model(hb, np.stack([h["prec"][:T], h["temp"][:T], h["pet"][:T]]), {"params": hp},
                        initstates=dict(snowpack=0.0, meltwater=0.0, soilwater=100.0, suz=3.0, slz=10.0))
     assert out.shape == (18, T) and np.all(np.isfinite(out)) and np.all(out[:5] >= 1e-6)
+
+
+def test_hbv_transcription_is_plausible_against_the_reference_fixture(golden):
+    """`models.hbv` against the third-party HBV-edu simulation the reference ships (`data/hbv_edu/hbv_sample.csv`, ten years;
+    its first row gives the initial stores 0 / 100 / 3 / 10).  The reference holds no parameter set for this file, so the
+    parameters below were CALIBRATED once against the fixture's `qsim` (scipy differential evolution on the first 1500 days,
+    run in the build container) — what is pinned is that such a set exists: flow NSE 0.956 and r = 0.984 over all 3652
+    days, snow store r = 0.999, soil store r = 0.981.  The fixture's two response stores are formulated differently
+    (r = 0.54 / 0.74) and are not pinned.  A transcription error in the snow, soil or flow equations breaks these bounds."""
+    h = golden("hbv_sample.npz")
+    hb = hm.models.hbv()
+    p = dict(TT=-0.055177629778313704, CFMAX=4.28013053201527, CFR=5.343514950281117e-05, CWH=2.746183659363226e-05,
+             FC=226.45380568371377, BETA=0.2037500238445265, LP=0.4778656230153751, PPERC=0.9596688716757769,
+             UZL=19.047451446030152, k0=0.2880885391111444, k1=0.04033089084168639, k2=0.07419436194865836)
+    out = ho.run_model(hb, np.stack([h["prec"], h["temp"], h["pet"]]), {"params": p},
+                       initstates=dict(snowpack=0.0, meltwater=0.0, soilwater=100.0, suz=3.0, slz=10.0))
+    n = hb.var_names
+    q = out[n.index("q")]
+    nse = 1 - np.sum((q - h["qsim"]) ** 2) / np.sum((h["qsim"] - h["qsim"].mean()) ** 2)
+    assert nse > 0.94 and np.corrcoef(q, h["qsim"])[0, 1] > 0.975, nse
+    assert np.corrcoef(out[n.index("snowpack")], h["snow"])[0, 1] > 0.995
+    assert np.corrcoef(out[n.index("soilwater")], h["soil"])[0, 1] > 0.97
 
 
 # -- 8. objectives -----------------------------------------------------------------------------
