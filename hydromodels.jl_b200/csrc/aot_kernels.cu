@@ -6,8 +6,51 @@
 #include <stdlib.h>
 
 #include "../../include/hydrob200.h"
+#include "templates/hb_tc.cuh"
 
 namespace {
+
+// Stand-alone check of the tcgen05 dense-layer path (templates/hb_tc.cuh): one CTA of 128 rows, D = A * W^T, `reps` rounds
+// through the same TMEM columns and mbarrier (phase flips), the last round's result is stored.
+template <int K, int N>
+__global__ void __launch_bounds__(128) hb_tc_probe_kernel(const float *__restrict__ A, const double *__restrict__ W, float *__restrict__ D, int reps) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned long long bar;
+    __shared__ unsigned tmem_base;
+    constexpr int kAFloats = (K / 8) * 1024;
+    float *sA = reinterpret_cast<float *>(smem);
+    float *sB = sA + 2 * kAFloats;
+    hb_tc_stage_b<K, N>(sB, W, threadIdx.x, 128);
+    if (threadIdx.x < 32) hb_tc_alloc((unsigned)__cvta_generic_to_shared(&tmem_base), N < 32 ? 32 : N);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    hb_tc_fence_before();
+    __syncthreads();
+    hb_tc_fence_after();
+    HbTc tc;
+    tc.sA = sA;
+    tc.sA_u32 = (unsigned)__cvta_generic_to_shared(sA);
+    tc.sB_u32 = (unsigned)__cvta_generic_to_shared(sB);
+    tc.bar_u32 = (unsigned)__cvta_generic_to_shared(&bar);
+    tc.tmem = tmem_base;
+    tc.phase = 0;
+    tc.a_lo_floats = kAFloats;
+    float x[K], z[N];
+    for (int k = 0; k < K; ++k) x[k] = A[threadIdx.x * K + k];
+    for (int rep = 0; rep < reps; ++rep) {
+        float xs[K];
+        const float s = (rep == reps - 1) ? 1.0f : 0.5f + rep;          // earlier rounds leave different values behind
+        for (int k = 0; k < K; ++k) xs[k] = x[k] * s;
+        hb_tc_layer<K, N>(tc, xs, 0, z);
+    }
+    for (int n = 0; n < N; ++n) D[threadIdx.x * N + n] = z[n];
+    hb_tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) hb_tc_dealloc(tc.tmem, N < 32 ? 32 : N);
+}
 
 // Dependent-chain FP64 FMA probe: 8 independent accumulators per thread, ITERS x 8 DFMA each.
 __global__ void __launch_bounds__(256) hb_fp64_probe(double *out, int iters, double a, double b) {
@@ -128,6 +171,21 @@ int hb_probe_occupy_sms(int n_blocks, int smem_bytes, double ms, void *stream) {
     if (smem_bytes > 48 * 1024 &&
         cudaFuncSetAttribute(hb_occupy, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return HB_ERR_CUDA;
     hb_occupy<<<n_blocks, 32, smem_bytes, (cudaStream_t)stream>>>((unsigned long long)(ms * 1e6));
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
+// D[128][N] = A[128][K] * W^T (W[n + N*k] doubles, rounded to float) through the tcgen05 path of templates/hb_tc.cuh;
+// (K, N) in {(16, 16), (24, 32), (64, 64)}.  DEVICE pointers; test / measurement aid.
+int hb_probe_tc_layer(int k, int n, const float *A, const double *W, float *D, int reps, void *stream) {
+    if (!A || !W || !D || reps < 1) return HB_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem = (2 * (k / 8) * 1024 + 2 * k * n) * 4;
+    if (k == 16 && n == 16) hb_tc_probe_kernel<16, 16><<<1, 128, smem, st>>>(A, W, D, reps);
+    else if (k == 24 && n == 32) hb_tc_probe_kernel<24, 32><<<1, 128, smem, st>>>(A, W, D, reps);
+    else if (k == 64 && n == 64) {
+        if (cudaFuncSetAttribute(hb_tc_probe_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HB_ERR_CUDA;
+        hb_tc_probe_kernel<64, 64><<<1, 128, smem, st>>>(A, W, D, reps);
+    } else return HB_ERR_INVALID;
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
 

@@ -148,6 +148,7 @@ def lib():
         "hb_memcpy_d2h": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
         "hb_memset_device": [C.c_void_p, C.c_int, C.c_int64, C.c_void_p], "hb_stream_synchronize": [C.c_void_p],
         "hb_stream_create": [C.POINTER(C.c_void_p)], "hb_stream_destroy": [C.c_void_p],
+        "hb_probe_tc_layer": [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p],
         "hb_probe_occupy_sms": [C.c_int, C.c_int, C.c_double, C.c_void_p],
         "hb_probe_fp64_tflops": [C.POINTER(C.c_double)], "hb_probe_dmma_tflops": [C.POINTER(C.c_double)],
         "hb_fill_device": [C.c_void_p, C.c_int64, C.c_double, C.c_void_p],

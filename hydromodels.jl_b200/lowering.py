@@ -94,6 +94,7 @@ class StepperProgram:
     precision: str = "f64"          # "f64" (reference arithmetic) | "f32" (opt-in)
     uh_on_device: bool = False      # the prologue evaluates the unit-hydrograph ordinates (host table ignored)
     tangents: List[str] = field(default_factory=list)   # gradient run: parameter name of each direction
+    nn_tc_bytes: int = 0            # Float32 tensor path (tcgen05): shared-memory bytes of the A and B tiles (0 = not used)
 
 
 class _Builder:
@@ -505,9 +506,12 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
     if precision not in ("f64", "f32"):
         raise LoweringError("precision must be 'f64' or 'f32'")
     net_mma = [bool(nn_tensor and fast and precision == "f64" and _mma_eligible(ch)) for ch in nets]
+    # Float32 mode: dense layers of tensor-core shape go through tcgen05.mma (kind::tf32, accumulator in TMEM), the CTA's
+    # 128 basins being the M dimension (templates/hb_tc.cuh)
+    net_tc = [bool(nn_tensor and fast and precision == "f32" and _tc_layers(ch)) for ch in nets]
 
     def nn_call(ni: int, args: List[str], arr: str) -> str:
-        pre = "sNN, hb_scr, lane, " if net_mma[ni] else "sNN, "
+        pre = "sNN, hb_scr, lane, " if net_mma[ni] else ("hb_tc, " if net_tc[ni] else "sNN, ")
         return f"hb_mlp_{ni}({pre}{', '.join(args)}, {arr});"
 
     def nn_var(ni: int, ins: Tuple[int, ...], tag: str) -> str:
@@ -616,9 +620,26 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
         if K >= 2:
             step.append(f"hb_uhh[{uh_h_off[u]}] = {step_ref(x)};")
 
-    helpers = [(_mlp_helper_mma if net_mma[i] else _mlp_helper)(i, ch, off, fast)
-               for i, (ch, (_, off, _)) in enumerate(zip(nets, nn_layout))]
-    body = "//@@HB:DEFINES\n" + f"#define HB_NC {len(carried)}\n" + \
+    tc_defs, tc_bytes = "", 0
+    if any(net_tc):
+        helpers, b_off, stage, kmax, nmax = [], 0, [], 8, 16
+        for i, (ch, (_, off, _)) in enumerate(zip(nets, nn_layout)):
+            if not net_tc[i]:
+                helpers.append(_mlp_helper(i, ch, off, fast))
+                continue
+            text, b_off, st, km, nm = _mlp_helper_tc(i, ch, off, b_off)
+            helpers.append(text)
+            stage += st
+            kmax, nmax = max(kmax, km), max(nmax, nm)
+        a_floats = (kmax // 8) * 1024                          # one [128 x kmax] tile (hi); the lo tile follows
+        tc_bytes = (2 * a_floats + b_off) * 4
+        tc_defs = (f"#define HB_NN_TC 1\n#define HB_TC_A_FLOATS {a_floats}\n#define HB_TC_B_FLOATS {b_off}\n"
+                   f"#define HB_TC_COLS {32 if nmax <= 32 else 64}\n"
+                   f"#define HB_TC_STAGE(sB, nn, tid, nthr) {' '.join(stage)}\n")
+    else:
+        helpers = [(_mlp_helper_mma if net_mma[i] else _mlp_helper)(i, ch, off, fast)
+                   for i, (ch, (_, off, _)) in enumerate(zip(nets, nn_layout))]
+    body = "//@@HB:DEFINES\n" + f"#define HB_NC {len(carried)}\n" + tc_defs + \
            "//@@HB:HELPERS\n" + "\n".join(helpers) + "\n" + \
            "//@@HB:PROLOGUE\n" + "\n".join("    " + s for s in pro) + "\n" + \
            "//@@HB:STEP\n" + "\n".join("        " + s for s in step) + "\n"
@@ -651,8 +672,8 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                           state_names=state_names, param_slots=param_slots, htype_sets=htype_sets, uh=uhs,
                           uh_kmax=list(uh_kmax), uh_htype_set=[htype_set(u) for u in uhs],
                           nn_layout=nn_layout, nn_words=sum(n for _, _, n in nn_layout), n_carry=len(carried),
-                          objective=objective, stats=stats, nn_tensor=any(net_mma), precision=precision,
-                          uh_on_device=bool(uh_on_device and uhs), tangents=tangents)
+                          objective=objective, stats=stats, nn_tensor=any(net_mma) or any(net_tc), precision=precision,
+                          uh_on_device=bool(uh_on_device and uhs), tangents=tangents, nn_tc_bytes=tc_bytes)
 
 
 def _body_to_tangent(body: str) -> str:
@@ -798,6 +819,52 @@ def lower_route(route: HydroRoute, *, fast: bool = True) -> RouteProgram:
     body = "//@@HB:HELPERS\n" + f1 + "\n" + f2 + "\n"
     return RouteProgram(body=body, input_names=list(route.input_names), state_name=sname, output_name=oname,
                         param_slots=param_slots, htype_sets=htype_sets)
+
+
+def _tc_layers(chain) -> List[int]:
+    """Layers of `chain` that go through tcgen05.mma in Float32 mode: K = n_in a multiple of 8, N = n_out a multiple of 16,
+    both at most 64 (M50's 16 -> 16 hidden layers, `test/base/run_single_lumped.jl:216-229`).  The other layers (3 -> 16,
+    16 -> 1) are too thin for an MMA and stay per-thread FFMA."""
+    return [i for i, l in enumerate(chain.layers) if l.n_in % 8 == 0 and l.n_out % 16 == 0 and l.n_in <= 64 and l.n_out <= 64]
+
+
+def _mlp_helper_tc(idx: int, chain, offset: int, b_off: int):
+    """Float32 tensor path of one chain: thin layers as per-thread FFMA straight-line code, tensor-shaped layers through
+    `hb_tc_layer<K, N>` (all 128 threads of the CTA call it at the same point).  Returns (text, next B offset in floats,
+    staging statements, max K, max N)."""
+    acts = _ACT_C
+    tcl = set(_tc_layers(chain))
+    args = ", ".join(f"const double x{i}" for i in range(chain.n_in))
+    lines = [f"__device__ __forceinline__ void hb_mlp_{idx}(HbTc& hb_tc, {args}, double* __restrict__ y) {{"]
+    prev = [f"x{i}" for i in range(chain.n_in)]
+    off, stage, kmax, nmax = offset, [], 8, 16
+    for li, l in enumerate(chain.layers):
+        bias = off + l.n_out * l.n_in
+        cur = [f"a{li + 1}_{o}" for o in range(l.n_out)]
+        if li in tcl:
+            K, N = l.n_in, l.n_out
+            lines.append(f"    double t{li + 1}[{N}];")
+            lines.append(f"    {{ const double xin[{K}] = {{{', '.join(prev)}}}; hb_tc_layer<{K}, {N}>(hb_tc, xin, {b_off}, t{li + 1}); }}")
+            for o in range(N):
+                lines.append(f"    double {cur[o]} = t{li + 1}[{o}] + HB_NNW({bias + o});")
+            stage.append(f"hb_tc_stage_b<{K}, {N}>((sB) + {b_off}, (nn) + {off}, tid, nthr);")
+            b_off += 2 * K * N
+            kmax, nmax = max(kmax, K), max(nmax, N)
+        else:
+            for o in range(l.n_out):
+                lines.append(f"    double {cur[o]} = HB_NNW({bias + o});")
+            for i in range(l.n_in):
+                for o in range(l.n_out):
+                    lines.append(f"    {cur[o]} = fma(HB_NNW({off + i * l.n_out + o}), {prev[i]}, {cur[o]});")
+        for o in range(l.n_out):
+            if l.activation != "identity":
+                lines.append(f"    {cur[o]} = {acts[l.activation].format(cur[o])};")
+        off += l.n_params
+        prev = cur
+    for o in range(chain.n_out):
+        lines.append(f"    y[{o}] = {prev[o]};")
+    lines.append("}")
+    return "\n".join(lines), b_off, stage, kmax, nmax
 
 
 def _mma_eligible(chain) -> bool:

@@ -405,6 +405,10 @@ int hb_halo_status(hb_comm_t c, void *stream);    /* synchronises; error if a pe
 int hb_probe_fp64_tflops(double *tflops);                       /* measured FP64 FMA peak (2 flop/FMA) */
 int hb_probe_dmma_tflops(double *tflops);                       /* measured FP64 tensor (DMMA m8n8k4) peak */
 int hb_fill_device(double *p, int64_t n, double v, void *stream); /* L2 flush / buffer fill           */
+/* Test aid for the Float32 tensor path (tcgen05.mma kind::tf32, 3xTF32 split, accumulator in TMEM; templates/hb_tc.cuh):
+ * D[128][n] = A[128][k] * W^T with W[n_idx + n * k_idx] (the Lux Dense weight layout), DEVICE pointers,
+ * (k, n) in {(16, 16), (24, 32), (64, 64)}; `reps` rounds through the same TMEM columns. */
+int hb_probe_tc_layer(int k, int n, const float *A, const double *W, float *D, int reps, void *stream);
 /* Test aid: `n_blocks` blocks holding `smem_bytes` of shared memory each spin for `ms` milliseconds on `stream`
  * (asynchronous) — a co-tenant kernel for the wave grid kernel's forward-progress tests. */
 int hb_probe_occupy_sms(int n_blocks, int smem_bytes, double ms, void *stream);
