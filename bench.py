@@ -34,6 +34,7 @@ WORKLOADS = {
     "gr4j_uh_100k_basins_x_3650d": ("gr4j", 100_000, 3650),
     "hbv_100k_basins_x_730d": ("hbv", 100_000, 730),
     "m50_50k_basins_x_3650d": ("m50", 50_000, 3650),
+    # the opt-in Float32 mode of the same workload: --precision f32 [--nn-tensor 0|1] (per-thread FFMA | tcgen05 3xTF32)
     "exphydro_64k_basins_x_365d": ("exphydro", 65_536, 365),
     # BASELINE config 3: calibration ensemble, shared forcing, fused objective (no rows written)
     "hbv_ensemble_1M_members_x_7305d": ("hbv_ensemble", 1_000_000, 7305),
@@ -676,6 +677,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096", "calibrate_exphydro", "gradient_exphydro", "irf_route", "irf_route_ragged", "exphydro_single_basin_365d"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="opt-in Float32 mode (per-node workloads; device-resident value only)")
+    ap.add_argument("--nn-tensor", type=int, default=-1, help="neural fluxes on the tensor cores: 1 / 0 / -1 = the engine's default for the precision")
     ap.add_argument("--no-bind", action="store_true", help="N > 1: do not bind each rank to its own slice of the host cores")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-array leg of the end-to-end measurement")
     ap.add_argument("--halo-exchange", default="peer", choices=["peer", "nccl", "torch"],
@@ -904,11 +907,17 @@ def main():
         d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
     else:
         model, p, init = build_problem(hm, sy, model_name, n0, N, T)
-        eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg)
+        eng = hm.B200Model(model, block_threads=args.block, stages=args.stages, max_registers=args.maxreg, precision=args.precision,
+                           nn_tensor=None if args.nn_tensor < 0 else bool(args.nn_tensor))
         eng.nodes_per_warp = args.npw
         run = DeviceRun(eng, N, T, p, initstates=init)
         d_in = device_forcing(torch, model_name, N, T, sy.SEED + 17 * rank)
         d_out = torch.empty((T, N, rows_of), device="cuda", dtype=torch.float64)
+        if args.precision == "f32":
+            args.no_e2e = True
+            d_in, d_out = d_in.float().contiguous(), d_out.float()
+            config.update(precision="f32 (opt-in mode: forcing, arithmetic and records in Float32)",
+                          nn_path=("tcgen05.mma kind::tf32, 3xTF32 split" if run.ck.spec.nn_tc_bytes else "per-thread FFMA") if model_name == "m50" else None)
     stream = torch.cuda.current_stream()
     info = eng.last_kernel.info()
 
@@ -949,7 +958,7 @@ def main():
 
     # roofline of the dominant (only) kernel: algorithmic bytes per launch / mean launch time
     peak, peak_src = peaks()
-    bytes_per_unit = 8 * (v_of + rows_of)
+    bytes_per_unit = (4 if args.precision == "f32" else 8) * (v_of + rows_of)
     launches_per_step = 1
     if model_name == "exphydro_grid":
         generic = args.grid_kernel == "generic" or (world > 1 and args.grid_kernel != "wave")
@@ -998,7 +1007,7 @@ def main():
                "reference_published_one_thread": 1.05e6}    # docs/src/get_start_en.md:408 (hardware not stated)
 
     secondary = None
-    if args.workload == DEFAULT_WORKLOAD and not args.no_secondary:
+    if args.workload == DEFAULT_WORKLOAD and not args.no_secondary and args.precision == "f64":
         # config 5 (the routed grid over all ranks) next to the headline, so that the driver's 1/2/4/8 runs carry it
         try:
             del d_in, d_out
@@ -1016,7 +1025,7 @@ def main():
         print(json.dumps({
             "metric": "basin-timesteps/sec", "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "strong" if total_grid else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "scaling": "strong" if total_grid else "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": config,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "secondary": secondary, "gpu_launches": launches, "clocks": clocks,
             "kernel_ms_each": [round(x, 4) for x in kernel_ms]}))
     if dist is not None:

@@ -90,6 +90,11 @@ __global__ void hb_occupy(unsigned long long ns) {
     } while (t - t0 < ns);
 }
 
+__global__ void hb_cvt_f64_f32(const double *__restrict__ src, float *__restrict__ dst, int64_t n) {
+    const int64_t i = blockIdx.x * 256ll + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+
 __global__ void hb_fill(double *p, int64_t n, double v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -186,6 +191,14 @@ int hb_probe_tc_layer(int k, int n, const float *A, const double *W, float *D, i
         if (cudaFuncSetAttribute(hb_tc_probe_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HB_ERR_CUDA;
         hb_tc_probe_kernel<64, 64><<<1, 128, smem, st>>>(A, W, D, reps);
     } else return HB_ERR_INVALID;
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
+// dst[i] = (float)src[i] (MLP parameters of a Float32 run -> the kernel's float constant bank)
+int hb_convert_f64_f32_device(const double *src, float *dst, int64_t n, void *stream) {
+    if (!src || !dst || n < 0) return HB_ERR_INVALID;
+    if (n == 0) return HB_OK;
+    hb_cvt_f64_f32<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
 }
 

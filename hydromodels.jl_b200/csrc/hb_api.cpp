@@ -291,9 +291,9 @@ int stepper_smem_bytes(const hb_stepper_spec &s, int block, int stages) {
     int warps = block / 32;
     const int npw = s.nodes_per_warp == 16 ? 16 : 32;
     // per-thread MLP path: parameters in the module's constant bank; tensor path: staged in shared memory + scratch
-    int nn = s.nn_tensor ? up128(s.nn_words * 8) + warps * 1024 : 0;
+    int nn = s.nn_tensor ? (s.precision ? up128(s.nn_tc_bytes) : up128(s.nn_words * 8) + warps * 1024) : 0;
     const int es = s.precision ? 4 : 8;
-    int in_b = up128(stages * npw * s.n_inputs * es);
+    int in_b = up128(stages * npw * s.n_inputs * es) + up128(stages * npw * s.n_aux_inputs * es);
     int out_b = s.output_mode == HB_OUT_ROWS ? up128(2 * npw * s.n_rows * es) : 0;
     return nn + warps * (in_b + out_b) + warps * stages * 8;
 }
@@ -311,7 +311,8 @@ int load_model(hb_model_s *m) {
     if (m->spec.nn_words > 0) {
         size_t bytes = 0;
         HB_DRV(g_drv.ModuleGetGlobal(&m->nn_const, &bytes, m->module, "hb_nn_const"));
-        if (bytes != (size_t)m->spec.nn_words * 8) return fail(HB_ERR_CUDA, "hb_nn_const has %zu bytes, expected %d", bytes, m->spec.nn_words * 8);
+        const size_t want = (size_t)m->spec.nn_words * (m->spec.precision ? 4 : 8);
+        if (bytes != want) return fail(HB_ERR_CUDA, "hb_nn_const has %zu bytes, expected %zu", bytes, want);
     }
     return HB_OK;
 }
@@ -473,6 +474,7 @@ int check_desc(const hb_model_s *m, const hb_run_desc *d) {
         if (off < 0 || off + span > d->n_param_values) return fail(HB_ERR_INVALID, "parameter %d addresses outside params (offset %lld)", j, (long long)off);
     }
     if (m->uhw_total > 0 && !d->uh_weights) return fail(HB_ERR_INVALID, "uh_weights is NULL");
+    if (s.n_aux_inputs > 0 && d->n_steps > 0 && !d->aux_input) return fail(HB_ERR_INVALID, "aux_input is NULL");
     if (s.nn_words > 0 && !d->nn_params) return fail(HB_ERR_INVALID, "nn_params is NULL");
     if (s.output_mode == HB_OUT_ROWS) {
         if (s.n_rows > 0 && d->n_steps > 0 && !d->out) return fail(HB_ERR_INVALID, "out is NULL");
@@ -487,15 +489,15 @@ int check_desc(const hb_model_s *m, const hb_run_desc *d) {
 // Launch with DEVICE pointers in `d` (param tables are host pointers).
 int launch_stepper(hb_model_s *m, const hb_run_desc *d, cudaStream_t stream) {
     const hb_stepper_spec &s = m->spec;
-    // HbArgs mirror (templates/stepper.cu): 12 pointers, 2 i64, 1 double, 4 int, then int tables
-    unsigned char buf[160 + 8 * HB_MAX_PARAMS + 16];
+    // HbArgs mirror (templates/stepper.cu): 13 pointers, 2 i64, 1 double, 4 int, then int tables
+    unsigned char buf[168 + 8 * HB_MAX_PARAMS + 16];
     memset(buf, 0, sizeof buf);
     size_t o = 0;
     auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
     // gradient runs have no record stream: the `out` slot carries the [D][N] gradient buffer
-    const void *ptrs[12] = {d->input, d->params, d->htypes, d->initstates, d->uh_weights, d->uh_hist_in,
+    const void *ptrs[13] = {d->input, d->params, d->htypes, d->initstates, d->uh_weights, d->uh_hist_in,
                             d->nn_params, d->target, s.n_tangents > 0 ? (void *)d->gradient : d->out, d->objective, d->final_states,
-                            d->uh_hist_out};
+                            d->uh_hist_out, d->aux_input};
     put(ptrs, sizeof ptrs);
     int64_t N = d->n_nodes, T = d->n_steps;
     put(&N, 8);
@@ -506,6 +508,7 @@ int launch_stepper(hb_model_s *m, const hb_run_desc *d, cudaStream_t stream) {
     // TMA bulk copies need 16-byte aligned global addresses: base pointer and per-step stride
     const int es = s.precision ? 4 : 8;
     int tma_in = ((reinterpret_cast<uintptr_t>(d->input) & 15) == 0) && ((N * s.n_inputs * es) % 16 == 0);
+    if (s.n_aux_inputs > 0 && (((reinterpret_cast<uintptr_t>(d->aux_input) & 15) != 0) || ((N * s.n_aux_inputs * es) % 16 != 0))) tma_in = 0;
     int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((N * s.n_rows * es) % 16 == 0);
     if (getenv("HB_DISABLE_TMA")) tma_in = tma_out = 0;
     put(&warm, 4);
@@ -522,8 +525,16 @@ int launch_stepper(hb_model_s *m, const hb_run_desc *d, cudaStream_t stream) {
     const int64_t nodes_per_block = (int64_t)(m->block / 32) * (s.nodes_per_warp == 16 ? 16 : 32);
     unsigned grid = (unsigned)((N + nodes_per_block - 1) / nodes_per_block);
     if (T == 0 && s.output_mode == HB_OUT_ROWS && !d->final_states) return HB_OK;
-    if (s.nn_words > 0)   // MLP parameters -> constant bank (stream-ordered before the launch)
-        HB_DRV(g_drv.MemcpyDtoDAsync(m->nn_const, (CUdeviceptr)(uintptr_t)d->nn_params, (size_t)s.nn_words * 8, (CUstream)stream));
+    if (s.nn_words > 0) {   // MLP parameters -> constant bank (stream-ordered before the launch), in the run's arithmetic type
+        if (s.precision) {
+            int rc = ws_reserve(m->ws[11], (size_t)s.nn_words * 4);
+            if (rc) return rc;
+            if ((rc = hb_convert_f64_f32_device(d->nn_params, (float *)m->ws[11].p, s.nn_words, stream))) return fail(rc, "hb_convert_f64_f32_device failed");
+            HB_DRV(g_drv.MemcpyDtoDAsync(m->nn_const, (CUdeviceptr)(uintptr_t)m->ws[11].p, (size_t)s.nn_words * 4, (CUstream)stream));
+        } else {
+            HB_DRV(g_drv.MemcpyDtoDAsync(m->nn_const, (CUdeviceptr)(uintptr_t)d->nn_params, (size_t)s.nn_words * 8, (CUstream)stream));
+        }
+    }
     HB_DRV(g_drv.LaunchKernel(m->func, grid, 1, 1, m->block, 1, 1, m->dyn_smem, (CUstream)stream, params, nullptr));
     return HB_OK;
 }
@@ -615,11 +626,16 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
     if (!spec || !body || !out) return fail(HB_ERR_INVALID, "NULL argument");
     if (spec->struct_size != (int32_t)sizeof(hb_stepper_spec)) return fail(HB_ERR_INVALID, "hb_stepper_spec.struct_size mismatch");
     if (spec->n_inputs < 0 || spec->n_rows < 0 || spec->n_states < 0 || spec->n_params < 0 || spec->n_params > HB_MAX_PARAMS ||
-        spec->n_uh < 0 || spec->n_uh > HB_MAX_UH || spec->nn_words < 0)
+        spec->n_uh < 0 || spec->n_uh > HB_MAX_UH || spec->nn_words < 0 || spec->n_aux_inputs < 0 || spec->n_aux_inputs > 16 ||
+        (spec->n_aux_inputs > 0 && (spec->shared_forcing || spec->output_mode != HB_OUT_ROWS)))
         return fail(HB_ERR_INVALID, "hb_stepper_spec out of range");
     if (spec->output_mode != HB_OUT_ROWS && spec->output_mode != HB_OUT_OBJECTIVE) return fail(HB_ERR_INVALID, "bad output_mode");
     if (spec->precision != 0 && spec->precision != 1) return fail(HB_ERR_INVALID, "precision must be 0 (Float64) or 1 (Float32)");
-    if (spec->precision && spec->nn_tensor) return fail(HB_ERR_INVALID, "the FP64 tensor path is not available in Float32 mode");
+    // Float32 + nn_tensor = the tcgen05 path (templates/hb_tc.cuh): the CTA's 128 threads are the M dimension of the MMA
+    if (spec->precision && spec->nn_tensor && (spec->nn_tc_bytes <= 0 || (spec->block_threads != 0 && spec->block_threads != 128) ||
+                                                 spec->nodes_per_warp == 16))
+        return fail(HB_ERR_INVALID, "the Float32 tensor path needs nn_tc_bytes > 0, 128 threads per block and 32 nodes per warp");
+    if (!spec->precision && spec->nn_tc_bytes != 0) return fail(HB_ERR_INVALID, "nn_tc_bytes is for the Float32 tensor path");
     if (spec->nodes_per_warp != 0 && spec->nodes_per_warp != 32 && spec->nodes_per_warp != 16)
         return fail(HB_ERR_INVALID, "nodes_per_warp must be 0, 16 or 32");
     if (spec->nodes_per_warp == 16 && !spec->nn_tensor) return fail(HB_ERR_INVALID, "nodes_per_warp = 16 is meant for tensor-path MLP bodies");
@@ -662,11 +678,13 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
              "//@@HB:DEFINES\n#define HB_V %d\n#define HB_R %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_UHW_TOTAL %d\n"
              "#define HB_UHH_TOTAL %d\n#define HB_NN_WORDS %d\n#define HB_MODE %d\n#define HB_METRIC %d\n#define HB_SHARED_FORCING %d\n"
              "#define HB_BLOCK %d\n#define HB_STAGES %d\n#define HB_MINBLOCKS %d\n#define HB_NN_MMA %d\n#define HB_F32 %d\n#define HB_NPW %d\n"
-             "#define HB_TANGENTS %d\n",
+             "#define HB_TANGENTS %d\n#define HB_V2 %d\n",
              spec->n_inputs, spec->output_mode == HB_OUT_ROWS ? spec->n_rows : 0, spec->n_states, spec->n_params, m->uhw_total,
              m->uhh_total, spec->nn_words, spec->output_mode, spec->metric, spec->shared_forcing ? 1 : 0, m->block, stages, minblocks,
-             spec->nn_tensor ? 1 : 0, spec->precision ? 1 : 0, spec->nodes_per_warp == 16 ? 16 : 32, spec->n_tangents);
+             (spec->nn_tensor && !spec->precision) ? 1 : 0, spec->precision ? 1 : 0, spec->nodes_per_warp == 16 ? 16 : 32, spec->n_tangents,
+             spec->n_aux_inputs);
     std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";   // body may append to DEFINES (e.g. HB_NC)
+    if (spec->nn_tensor && spec->precision) full_body += std::string("//@@HB:TC\n") + kTcHeader + "\n";
     if (const char *x = getenv("HB_EXTRA_DEFINES")) full_body = std::string("//@@HB:DEFINES\n") + x + "\n" + full_body;   // tuning experiments
     m->source = splice(kStepperTemplate, full_body.c_str());
     m->kernel_name = "hb_stepper";
@@ -754,6 +772,7 @@ int hb_run_device(hb_model_t m, const hb_run_desc *d, void *stream) {
 int hb_run(hb_model_t m, const hb_run_desc *d) {
     if (!m) return fail(HB_ERR_INVALID, "model is NULL");
     if (m->kind != 0) return fail(HB_ERR_INVALID, "not a stepper model");
+    if (m->spec.n_aux_inputs > 0) return fail(HB_ERR_INVALID, "auxiliary inputs are a device-resident feature (hb_run_device)");
     int rc = check_desc(m, d);
     if (rc) return rc;
     rc = load_model(m);

@@ -40,6 +40,13 @@ typedef unsigned int u32;
 #ifndef HB_NN_MMA
 #define HB_NN_MMA 0
 #endif
+#ifndef HB_V2
+#define HB_V2 0       // auxiliary per-node inputs (a second [T][N][V2] stream riding the same TMA ring): rows another kernel
+#endif                //   produced for this model — the route state and outflow the generic routed path computes between two
+                      //   stepper passes (hb_route_step in planes mode) — which the body copies into the records (hb_aux[k])
+#ifndef HB_NN_TC
+#define HB_NN_TC 0    // 1: Float32 mode, tensor-shaped dense layers through tcgen05.mma (templates/hb_tc.cuh): the CTA's 128
+#endif                //    threads / basins are the M dimension, so the CTA meets at a barrier in every neural-flux evaluation
 #ifndef HB_F32
 #define HB_F32 0
 #endif
@@ -75,6 +82,7 @@ struct HbArgs {
     double *obj;
     double *final_states;
     double *uhh_out;
+    const real *in2;          // [T][N][HB_V2] auxiliary inputs (HB_V2 > 0)
     i64 N;
     i64 T;
     double min_value;
@@ -143,14 +151,20 @@ typedef double tacc;
 // ---- MLP parameters: module-scope constant bank (filled by the host before each launch) so that
 //      every weight is a c[3][imm] operand of its DFMA; shared across all nodes (src/nn.jl:140-165)
 #if HB_NN_WORDS > 0
-__constant__ double hb_nn_const[HB_NN_WORDS];
-#define HB_NNW(i) ((real)hb_nn_const[i])
+// in the arithmetic type of the run: a Float32 body must not pay a double -> float conversion per weight use (the host
+// converts the parameters once per launch, hb_api.cpp launch_stepper)
+__constant__ real hb_nn_const[HB_NN_WORDS];
+#define HB_NNW(i) (hb_nn_const[i])
 #endif
 // D(8x8) += A(8x4) * B(4x8) on the FP64 tensor pipe (SASS DMMA).  Fragments: A lane l -> A[l/4][l%4],
 // B lane l -> B[l%4][l/4], C/D lane l -> C[l/4][2*(l%4) + {0,1}].
 __device__ __forceinline__ void hb_dmma(double &d0, double &d1, const double a, const double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+
+#if HB_NN_TC
+//@@HB:TC
+#endif
 
 //@@HB:HELPERS
 
@@ -169,24 +183,58 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     // shared-memory carve-up: [MLP params + per-warp MMA scratch][per-warp forcing ring][per-warp result tiles][mbarriers]
 #if HB_NN_MMA
     constexpr int kNNBytes = ((HB_NN_WORDS * 8 + 127) / 128) * 128 + HB_WARPS * 1024;
+#elif HB_NN_TC
+    constexpr int kNNBytes = (((2 * HB_TC_A_FLOATS + HB_TC_B_FLOATS) * 4 + 127) / 128) * 128;   // A tiles (hi, lo) + B tiles of every tensor layer
 #else
     constexpr int kNNBytes = 0;   // per-thread MLP path: parameters live in the constant bank (hb_nn_const)
 #endif
     constexpr int kInStage = HB_NPW * HB_V * (int)sizeof(real);                      // bytes of one warp-step of forcing
-    constexpr int kInBytes = ((HB_STAGES * kInStage + 127) / 128) * 128;
+    constexpr int kIn2Stage = HB_NPW * HB_V2 * (int)sizeof(real);                    // ... of auxiliary inputs
+    constexpr int kIn1Bytes = ((HB_STAGES * kInStage + 127) / 128) * 128;
+    constexpr int kInBytes = kIn1Bytes + ((HB_STAGES * kIn2Stage + 127) / 128) * 128;
     constexpr int kOutTile = HB_NPW * HB_R * (int)sizeof(real);                      // bytes of one warp-step of results
     constexpr int kOutBytes = ((HB_OBUF * kOutTile + 127) / 128) * 128;
     real *sNN = reinterpret_cast<real *>(hb_smem);   // tensor path only (Float64): staged MLP parameters
     double *hb_scr = reinterpret_cast<double *>(hb_smem + ((HB_NN_WORDS * 8 + 127) / 128) * 128) + warp * 128;   // 1 KB per warp
     unsigned char *warp_base = hb_smem + kNNBytes + (size_t)warp * (kInBytes + kOutBytes);
     real *sIn = reinterpret_cast<real *>(warp_base);
+    real *sIn2 = reinterpret_cast<real *>(warp_base + kIn1Bytes);
     real *sOut = reinterpret_cast<real *>(warp_base + kInBytes);
+    (void)sIn2;
     u64 *bars = reinterpret_cast<u64 *>(hb_smem + kNNBytes + (size_t)HB_WARPS * (kInBytes + kOutBytes)) + warp * HB_STAGES;
     (void)sNN; (void)hb_scr; (void)sIn; (void)sOut; (void)bars;
 #if HB_NN_MMA
     // tensor-core MLP path: dense-layer weights are read as MMA fragments (lane-dependent addresses)
     for (int i = threadIdx.x; i < HB_NN_WORDS; i += HB_BLOCK) sNN[i] = a.nn[i];
     __syncthreads();
+#endif
+#if HB_NN_TC
+    // tcgen05 path: weights -> canonical K-major B tiles (hi / lo halves of the 3xTF32 split), TMEM columns for the
+    // accumulator, one mbarrier for the MMA completions
+    __shared__ u64 hb_tc_bar;
+    __shared__ u32 hb_tc_tmem_base;
+    HbTc hb_tc;
+    {
+        float *sTcA = reinterpret_cast<float *>(hb_smem);
+        float *sTcB = sTcA + 2 * HB_TC_A_FLOATS;
+        HB_TC_STAGE(sTcB, a.nn, (int)threadIdx.x, HB_BLOCK)
+        if (warp == 0) hb_tc_alloc(hb_smem_u32(&hb_tc_tmem_base), HB_TC_COLS);
+        if (threadIdx.x == 0) {
+            hb_mbar_init(hb_smem_u32(&hb_tc_bar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        hb_fence_proxy_async();
+        hb_tc_fence_before();
+        __syncthreads();
+        hb_tc_fence_after();
+        hb_tc.sA = sTcA;
+        hb_tc.sA_u32 = hb_smem_u32(sTcA);
+        hb_tc.sB_u32 = hb_smem_u32(sTcB);
+        hb_tc.bar_u32 = hb_smem_u32(&hb_tc_bar);
+        hb_tc.tmem = hb_tc_tmem_base;
+        hb_tc.phase = 0;
+        hb_tc.a_lo_floats = HB_TC_A_FLOATS;
+    }
 #endif
 
     // warp-uniform choice of the I/O path
@@ -197,7 +245,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     // ragged warp is on the per-thread path, which has no warp syncs) — measurably faster code
     // (GR4J 100k x 3650: 8.4 vs 9.4 ms).
     const i64 nc = valid ? n : a.N - 1;
-#if !HB_NN_MMA
+#if !HB_NN_MMA && !HB_NN_TC
     if (!valid) return;
 #endif
 
@@ -259,6 +307,12 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     real *out_warp = a.out + n0w * HB_R;
     real *out_lane = a.out + n * HB_R;
     (void)in_warp; (void)out_warp; (void)out_lane; (void)in_lane;
+#if HB_V2 > 0
+    const i64 in2_step = a.N * (i64)HB_V2;
+    const real *in2_warp = a.in2 + n0w * HB_V2;
+    const real *gx2 = a.in2 + nc * HB_V2;
+    const real *pf2_ptr = in2_warp + (i64)HB_STAGES * in2_step;
+#endif
 
     if (tma_in) {
         if (lane == 0) {
@@ -269,8 +323,11 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
 #pragma unroll
             for (int s = 0; s < HB_STAGES; ++s) {
                 if (s < T) {
-                    hb_mbar_expect_tx(hb_smem_u32(&bars[s]), kInStage);
+                    hb_mbar_expect_tx(hb_smem_u32(&bars[s]), kInStage + kIn2Stage);
                     hb_bulk_g2s(hb_smem_u32(sIn + s * HB_NPW * HB_V), in_warp + (i64)s * in_step, kInStage, hb_smem_u32(&bars[s]));
+#if HB_V2 > 0
+                    hb_bulk_g2s(hb_smem_u32(sIn2 + s * HB_NPW * HB_V2), in2_warp + (i64)s * in2_step, kIn2Stage, hb_smem_u32(&bars[s]));
+#endif
                 }
             }
         }
@@ -291,26 +348,43 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     for (i64 t = 0; t < T; ++t) {
         // ---- forcing of this step -------------------------------------------------------------
         real hb_x[HB_ARR(HB_V)];
+        real hb_aux[HB_ARR(HB_V2)];
+        (void)hb_aux;
         if (tma_in) {
             hb_mbar_wait(hb_smem_u32(&bars[slot]), parity);
             const real *sx = sIn + slot * HB_NPW * HB_V + ln * HB_V;
 #pragma unroll
             for (int v = 0; v < HB_V; ++v) hb_x[v] = sx[v];
+#if HB_V2 > 0
+#pragma unroll
+            for (int v = 0; v < HB_V2; ++v) hb_aux[v] = sIn2[slot * HB_NPW * HB_V2 + ln * HB_V2 + v];
+#endif
             // cross-proxy write-after-read: the lanes' generic-proxy loads of the slot must be ordered before the
             // async-proxy (TMA) refill of the same slot; __syncwarp orders the generic proxy only (the wave grid
             // kernel, which shares this ring, showed overtaken loads on cold launches without the fence)
             hb_fence_proxy_async();
             __syncwarp();   // every lane has consumed the slot -> refill it HB_STAGES steps ahead
             if (lane == 0 && t + HB_STAGES < T) {
-                hb_mbar_expect_tx(hb_smem_u32(&bars[slot]), kInStage);
+                hb_mbar_expect_tx(hb_smem_u32(&bars[slot]), kInStage + kIn2Stage);
                 hb_bulk_g2s(hb_smem_u32(sIn + slot * HB_NPW * HB_V), pf_ptr, kInStage, hb_smem_u32(&bars[slot]));
+#if HB_V2 > 0
+                hb_bulk_g2s(hb_smem_u32(sIn2 + slot * HB_NPW * HB_V2), pf2_ptr, kIn2Stage, hb_smem_u32(&bars[slot]));
+#endif
             }
             pf_ptr += in_step;
+#if HB_V2 > 0
+            pf2_ptr += in2_step;
+#endif
             if (++slot == HB_STAGES) { slot = 0; parity ^= 1; }
         } else {
 #pragma unroll
             for (int v = 0; v < HB_V; ++v) hb_x[v] = gx[v];
             gx += in_step;
+#if HB_V2 > 0
+#pragma unroll
+            for (int v = 0; v < HB_V2; ++v) hb_aux[v] = gx2[v];
+            gx2 += in2_step;
+#endif
         }
         real hb_out[HB_ARR(HB_R)];
         (void)hb_x; (void)hb_out;
@@ -368,6 +442,12 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     if (tma_out && lane == 0) hb_bulk_wait<0>();   // shared tiles must outlive the last bulk stores
 
     // ---- epilogue: final states / UH history for chunked-T runs, objective ---------------------
+#if HB_NN_TC
+    // the TMEM columns go back before the CTA ends; every thread (also the shadows past the last node) reaches this point
+    hb_tc_fence_before();
+    __syncthreads();
+    if (warp == 0) hb_tc_dealloc(hb_tc.tmem, HB_TC_COLS);
+#endif
     if (!valid) return;
     if (a.final_states) {
 #pragma unroll

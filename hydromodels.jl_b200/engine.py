@@ -44,7 +44,7 @@ class StepperSpec(C.Structure):
                 ("nn_words", C.c_int32), ("output_mode", C.c_int32), ("metric", C.c_int32),
                 ("shared_forcing", C.c_int32), ("block_threads", C.c_int32), ("stages", C.c_int32),
                 ("max_registers", C.c_int32), ("precision", C.c_int32), ("nn_tensor", C.c_int32), ("nodes_per_warp", C.c_int32),
-                ("n_tangents", C.c_int32)]
+                ("n_tangents", C.c_int32), ("n_aux_inputs", C.c_int32), ("nn_tc_bytes", C.c_int32)]
 
 
 class RunDesc(C.Structure):
@@ -55,7 +55,7 @@ class RunDesc(C.Structure):
                 ("nn_params", C.c_void_p), ("target", C.c_void_p), ("target_per_node", C.c_int32),
                 ("warm_up", C.c_int32), ("min_value", C.c_double), ("out", C.c_void_p), ("objective", C.c_void_p),
                 ("final_states", C.c_void_p), ("uh_hist_out", C.c_void_p), ("elapsed_ms", C.c_void_p),
-                ("gradient", C.c_void_p)]
+                ("gradient", C.c_void_p), ("aux_input", C.c_void_p)]
 
 
 class KernelInfo(C.Structure):
@@ -147,6 +147,7 @@ def lib():
         "hb_memcpy_h2d": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
         "hb_memcpy_d2h": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
         "hb_memset_device": [C.c_void_p, C.c_int, C.c_int64, C.c_void_p], "hb_stream_synchronize": [C.c_void_p],
+        "hb_convert_f64_f32_device": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
         "hb_stream_create": [C.POINTER(C.c_void_p)], "hb_stream_destroy": [C.c_void_p],
         "hb_probe_tc_layer": [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p],
         "hb_probe_occupy_sms": [C.c_int, C.c_int, C.c_double, C.c_void_p],
@@ -225,6 +226,8 @@ class CompiledStepper:
         spec.nodes_per_warp = nodes_per_warp if spec.nn_tensor else 0
         spec.precision = 1 if getattr(program, "precision", "f64") == "f32" else 0
         spec.n_tangents = len(getattr(program, "tangents", ()) or ())
+        spec.nn_tc_bytes = int(getattr(program, "nn_tc_bytes", 0)) if spec.precision else 0
+        spec.n_aux_inputs = len(getattr(program, "aux_names", ()) or ())
         self.spec = spec
         h = C.c_void_p()
         check(lib().hb_compile_stepper(C.byref(spec), program.body.encode(), C.byref(h)))
@@ -376,7 +379,7 @@ class B200Model:
     """Wrapper component: `B200Model(model)(input, params, config; initstates)`."""
 
     def __init__(self, component: Component, *, fast: bool = True, block_threads: int = 0, stages: int = 0,
-                 max_registers: int = 0, nn_tensor: bool = True, precision: str = "f64"):
+                 max_registers: int = 0, nn_tensor: Optional[bool] = None, precision: str = "f64"):
         """`precision="f32"` is the opt-in Float32 mode: forcing and results are float32 arrays, the body
         computes in float (stated tolerance: DESIGN.md §5, `tests/test_gpu_parity.py::test_float32_mode`)."""
         if precision not in ("f64", "f32"):
@@ -385,7 +388,10 @@ class B200Model:
         self.precision = precision
         self.dtype = np.float64 if precision == "f64" else np.float32
         self.fast = fast
-        self.nn_tensor = nn_tensor        # dense chains on the FP64 tensor pipe (DMMA) where their shape fits
+        # dense chains on the tensor cores where their shape fits: Float64 -> FP64 MMA (DMMA) fragments per warp; Float32 ->
+        # tcgen05.mma kind::tf32 with the CTA's 128 basins as M (templates/hb_tc.cuh).  None = on: both tensor paths measured faster
+        # than their per-thread twins (M50 50 k x 3650: Float64 50.9 -> 41 ms round 1; Float32 33.5 -> 32.9 ms, +8 % at >= 4 CTAs/SM)
+        self.nn_tensor = True if nn_tensor is None else bool(nn_tensor)
         # [buckets…, HydroRoute] on a dense row-major D8 grid: "wave" = single-pass kernel whose warps exchange
         # outflows through L2 (templates/gridwave.cu, default); "tile" = tile + halo kernel (templates/grid.cu);
         # "generic" = stepper over all T, then one routing launch per step (any node list / graph)

@@ -91,14 +91,21 @@ typedef struct {
     int32_t max_registers;       /* 0 = default (128); register budget per thread -> __launch_bounds__ min blocks */
     int32_t precision;           /* 0 = Float64 (reference arithmetic), 1 = opt-in Float32: `input` and `out` are float
                                     arrays and the body computes in float; everything else stays double */
-    int32_t nn_tensor;           /* 1: the body contracts its dense layers with FP64 MMA (DMMA) fragments: MLP
-                                    parameters are staged in shared memory + 1 KB scratch per warp */
+    int32_t nn_tensor;           /* 1: the body contracts its dense layers on the tensor cores.  Float64: FP64 MMA (DMMA)
+                                    fragments, MLP parameters staged in shared memory + 1 KB scratch per warp.  Float32: the
+                                    tcgen05 path, see nn_tc_bytes */
     int32_t nodes_per_warp;      /* 0 / 32: one node per lane.  16: lanes l and l+16 carry the same node, so the warp-cooperative
                                     MLPs spread 16 basins over 32 lanes and a small, MLP-heavy run gets twice the warps */
     int32_t n_tangents;          /* D > 0: gradient run (HB_OUT_OBJECTIVE, Float64, no MLPs): the body was lowered with D
                                     parameter directions and the kernel also returns d objective / d direction per node —
                                     the forward-mode counterpart of the reference's Zygote gradient through its
                                     ImmutableSolver (README.md:161-187) */
+    int32_t n_aux_inputs;        /* V2 > 0: a second per-node input stream aux_input[T][N][V2] (hb_run_device only): rows another
+                                    kernel produced for this model, which the body copies into its records (hb_aux[k]) — the
+                                    route state / outflow between the two stepper passes of the generic routed path */
+    int32_t nn_tc_bytes;         /* precision = 1 and nn_tensor = 1: the body's tensor-shaped dense layers run on tcgen05.mma
+                                    (kind::tf32, 3xTF32 operand split, accumulator in TMEM; templates/hb_tc.cuh) and need this
+                                    many bytes of shared memory for their A / B tiles.  128 threads per block. */
 } hb_stepper_spec;
 
 /* One forward run.  Pointers are HOST pointers for hb_run and DEVICE pointers for
@@ -128,6 +135,7 @@ typedef struct {
     double *uh_hist_out;         /* [sum_u (kmax_u-1)][N] or NULL                             */
     float *elapsed_ms;           /* optional HOST pointer: device time of the kernel(s)       */
     double *gradient;            /* gradient runs (spec.n_tangents = D): [D][N], d objective[n] / d direction k */
+    const void *aux_input;       /* spec.n_aux_inputs = V2 > 0: DEVICE [T][N][V2] (hb_run_device) */
 } hb_run_desc;
 
 typedef struct {
@@ -361,6 +369,7 @@ int hb_memset_device(void *dst, int value, int64_t bytes, void *stream);
 int hb_stream_create(void **stream);              /* a non-blocking cudaStream_t for the *_device entry points */
 int hb_stream_destroy(void *stream);
 int hb_stream_synchronize(void *stream);
+int hb_convert_f64_f32_device(const double *src, float *dst, int64_t n, void *stream);   /* DEVICE arrays */
 
 
 /* ---- multi-GPU: one process per GPU (hb_init picks the device), a communicator inside the library -------------------
