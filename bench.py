@@ -695,6 +695,9 @@ def main():
     ap.add_argument("--grid-kernel", default="wave", choices=["wave", "tile", "generic"],
                     help="grid workload: wave = single-pass L2-dataflow kernel (gridwave.cu, default); tile = tile + halo "
                          "(grid.cu); generic = stepper over all T, then one routing launch per step")
+    ap.add_argument("--route-passes", type=int, default=3, choices=[2, 3],
+                    help="--grid-kernel generic: 3 = stepper / route on compact planes / stepper (records written once); 2 = round 1's "
+                         "stepper + in-place route patches")
     ap.add_argument("--fused-grid", action="store_true", help="(round-1 flag) same as --grid-kernel tile")
     ap.add_argument("--grid-panels", type=int, default=-1,
                     help="single-GPU grid workload, wave kernel: run the grid as this many column panels one after the other "
@@ -852,7 +855,8 @@ def main():
                     sharded.launch(ip, op)
             run = _Run()
         elif args.grid_kernel == "generic":
-            run = RoutedDeviceRun(eng, N, T, p, initstates=init)
+            run = RoutedDeviceRun(eng, N, T, p, initstates=init, legacy=(args.route_passes == 2))
+            config["generic_route_passes"] = 2 if run.legacy else 3
         else:
             from hydromodels_jl_b200.engine import GridDeviceRun
             n_panels = args.grid_panels if args.grid_panels >= 0 else (0 if g_cols > 3000 else 1)
@@ -965,10 +969,11 @@ def main():
         if not generic:
             args.grid_tc = grid_run.check()          # raises if a warp of the wave kernel gave up waiting
             config["grid_kernel"], config["steps_per_launch"] = args.grid_kernel, args.grid_tc
-        launches_per_step = (T + 2) if generic else -(-T // args.grid_tc)
+        launches_per_step = (T + 2 + (0 if (world > 1 or args.route_passes == 2) else 1)) if generic else -(-T // args.grid_tc)
     k_ms = float(np.mean(kernel_ms))
     achieved = bytes_per_unit * N * T / (k_ms * 1e-3) / 1e9
-    kname = {"exphydro_grid": "hb_stepper + T x hb_route_step" if (args.grid_kernel == "generic" or (world > 1 and args.grid_kernel != "wave")) else
+    kname = {"exphydro_grid": ("hb_stepper + T x hb_route_step (in-place patches)" if (world > 1 or args.route_passes == 2) else
+                               "hb_stepper (route inputs) + T x hb_route_step (planes) + hb_stepper (records)") if (args.grid_kernel == "generic" or (world > 1 and args.grid_kernel != "wave")) else
              ("hb_grid_wave" if args.grid_kernel == "wave" else "hb_grid_chunk"),
              "hbv_ensemble": "hb_stepper (objective mode)"}.get(model_name, "hb_stepper")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",

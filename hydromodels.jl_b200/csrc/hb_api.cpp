@@ -474,7 +474,10 @@ int check_desc(const hb_model_s *m, const hb_run_desc *d) {
         if (off < 0 || off + span > d->n_param_values) return fail(HB_ERR_INVALID, "parameter %d addresses outside params (offset %lld)", j, (long long)off);
     }
     if (m->uhw_total > 0 && !d->uh_weights) return fail(HB_ERR_INVALID, "uh_weights is NULL");
-    if (s.n_aux_inputs > 0 && d->n_steps > 0 && !d->aux_input) return fail(HB_ERR_INVALID, "aux_input is NULL");
+    if (d->n_compact_rows < 0 || d->n_compact_rows > 4 || (d->n_compact_rows > 0 && s.output_mode != HB_OUT_ROWS))
+        return fail(HB_ERR_INVALID, "n_compact_rows must be 0..4 (rows mode)");
+    for (int k = 0; k < d->n_compact_rows; ++k)
+        if (d->compact_rows[k] < 0 || d->compact_rows[k] >= s.n_rows) return fail(HB_ERR_INVALID, "compact row outside the record");
     if (s.nn_words > 0 && !d->nn_params) return fail(HB_ERR_INVALID, "nn_params is NULL");
     if (s.output_mode == HB_OUT_ROWS) {
         if (s.n_rows > 0 && d->n_steps > 0 && !d->out) return fail(HB_ERR_INVALID, "out is NULL");
@@ -489,8 +492,8 @@ int check_desc(const hb_model_s *m, const hb_run_desc *d) {
 // Launch with DEVICE pointers in `d` (param tables are host pointers).
 int launch_stepper(hb_model_s *m, const hb_run_desc *d, cudaStream_t stream) {
     const hb_stepper_spec &s = m->spec;
-    // HbArgs mirror (templates/stepper.cu): 13 pointers, 2 i64, 1 double, 4 int, then int tables
-    unsigned char buf[168 + 8 * HB_MAX_PARAMS + 16];
+    // HbArgs mirror (templates/stepper.cu): 13 pointers, 2 i64, 1 double, 4 + 5 int, then int tables
+    unsigned char buf[188 + 8 * HB_MAX_PARAMS + 16];
     memset(buf, 0, sizeof buf);
     size_t o = 0;
     auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
@@ -508,13 +511,17 @@ int launch_stepper(hb_model_s *m, const hb_run_desc *d, cudaStream_t stream) {
     // TMA bulk copies need 16-byte aligned global addresses: base pointer and per-step stride
     const int es = s.precision ? 4 : 8;
     int tma_in = ((reinterpret_cast<uintptr_t>(d->input) & 15) == 0) && ((N * s.n_inputs * es) % 16 == 0);
-    if (s.n_aux_inputs > 0 && (((reinterpret_cast<uintptr_t>(d->aux_input) & 15) != 0) || ((N * s.n_aux_inputs * es) % 16 != 0))) tma_in = 0;
+    if (s.n_aux_inputs > 0 && d->aux_input && (((reinterpret_cast<uintptr_t>(d->aux_input) & 15) != 0) || ((N * s.n_aux_inputs * es) % 16 != 0))) tma_in = 0;
     int tma_out = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((N * s.n_rows * es) % 16 == 0);
     if (getenv("HB_DISABLE_TMA")) tma_in = tma_out = 0;
     put(&warm, 4);
     put(&tpn, 4);
+    if (d->n_compact_rows > 0) tma_out = 0;
     put(&tma_in, 4);
     put(&tma_out, 4);
+    int cn = d->n_compact_rows, crow[4] = {d->compact_rows[0], d->compact_rows[1], d->compact_rows[2], d->compact_rows[3]};
+    put(&cn, 4);
+    put(crow, 16);
     int np = s.n_params > 0 ? s.n_params : 1;
     std::vector<int> tmp(np, 0);
     for (int j = 0; j < s.n_params; ++j) tmp[j] = d->param_offset[j];
@@ -544,12 +551,12 @@ int launch_route_step(hb_model_s *m, const hb_route_desc *d, int64_t t, const do
     const hb_route_spec &s = m->rspec;
     const int64_t N = d->n_nodes, T = d->n_steps;
     const int nv = s.n_inputs > 0 ? s.n_inputs : 1, np = s.n_params > 0 ? s.n_params : 1;
-    // HbRouteArgs mirror (templates/route.cu): 9 pointers, 3 i64, 1 double, 3 int, int tables
-    unsigned char buf[9 * 8 + 3 * 8 + 8 + 3 * 4 + 4 * (16 + 2 * HB_MAX_PARAMS) + 16];
+    // HbRouteArgs mirror (templates/route.cu): 11 pointers, 3 i64, 1 double, 3 int, int tables
+    unsigned char buf[11 * 8 + 3 * 8 + 8 + 3 * 4 + 4 * (16 + 2 * HB_MAX_PARAMS) + 16];
     memset(buf, 0, sizeof buf);
     size_t o = 0;
     auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
-    const void *ptrs[9] = {d->records, d->params, d->htypes, s_prev, s_next, q_cur, q_next, d->up_ptr, d->up_idx};
+    const void *ptrs[11] = {d->records, d->params, d->htypes, s_prev, s_next, q_cur, q_next, d->up_ptr, d->up_idx, d->route_inputs, d->route_out};
     put(ptrs, sizeof ptrs);
     put(&N, 8);
     put(&t, 8);
@@ -577,7 +584,10 @@ int check_route_desc(const hb_model_s *m, const hb_route_desc *d) {
     if (!m || m->kind != 1) return fail(HB_ERR_INVALID, "not a route model");
     if (!d || d->struct_size != (int32_t)sizeof(hb_route_desc)) return fail(HB_ERR_INVALID, "hb_route_desc.struct_size mismatch");
     const hb_route_spec &s = m->rspec;
-    if (d->n_nodes <= 0 || d->n_steps < 0 || !d->records || !d->up_ptr || !d->up_idx) return fail(HB_ERR_INVALID, "bad route descriptor");
+    const bool planes = d->route_inputs || d->route_out;
+    if (planes && (!d->route_inputs || !d->route_out)) return fail(HB_ERR_INVALID, "planes mode needs both route_inputs and route_out");
+    if (d->n_nodes <= 0 || d->n_steps < 0 || (!d->records && !planes) || !d->up_ptr || !d->up_idx) return fail(HB_ERR_INVALID, "bad route descriptor");
+    if (planes) return HB_OK;
     if (d->min_value != d->min_value) return fail(HB_ERR_INVALID, "min_value is NaN");   // any real floor: hydrosolve takes what the config carries (src/solve.jl:40); HydroConfig's own > 0 check is the host mirror's
     if (d->s_row < 0 || d->s_row >= d->n_rows || d->o_row < 0 || d->o_row >= d->n_rows) return fail(HB_ERR_INVALID, "route rows outside the record");
     for (int v = 0; v < s.n_inputs; ++v)
@@ -772,7 +782,8 @@ int hb_run_device(hb_model_t m, const hb_run_desc *d, void *stream) {
 int hb_run(hb_model_t m, const hb_run_desc *d) {
     if (!m) return fail(HB_ERR_INVALID, "model is NULL");
     if (m->kind != 0) return fail(HB_ERR_INVALID, "not a stepper model");
-    if (m->spec.n_aux_inputs > 0) return fail(HB_ERR_INVALID, "auxiliary inputs are a device-resident feature (hb_run_device)");
+    if (m->spec.n_aux_inputs > 0 || d->n_compact_rows > 0)
+        return fail(HB_ERR_INVALID, "auxiliary inputs / compact rows are device-resident features (hb_run_device)");
     int rc = check_desc(m, d);
     if (rc) return rc;
     rc = load_model(m);

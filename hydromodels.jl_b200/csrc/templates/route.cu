@@ -37,6 +37,10 @@ struct HbRouteArgs {
     double *q_next;         // [N] outflows of the next step
     const int *up_ptr;      // [N+1] CSR of upstream nodes
     const int *up_idx;
+    const double *xin;      // planes mode (non-NULL): route inputs as a compact [T][N][HB_RV] array instead of record rows
+    double *out2;           // planes mode (non-NULL): [T][N][2] = {state, outflow} instead of the two record rows — both fully
+                            //   coalesced; the records are then written ONCE by a second stepper pass that takes out2 as its
+                            //   auxiliary input (no 8-byte patches into 104-byte records: ncu r01 saw 312 B per cell-step there)
     i64 N;
     i64 t;                  // 0-based step; t == -1: prologue launch (only q_next for step 0)
     i64 T;
@@ -72,24 +76,39 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK) hb_route_step(const __gri
     double s_new;
     if (a.t >= 0) {
         double *rec = a.rec + (a.t * a.N + n) * a.R;
+        if (a.xin) {
 #pragma unroll
-        for (int v = 0; v < HB_RV; ++v) hb_x[v] = rec[a.in_row[v]];
+            for (int v = 0; v < HB_RV; ++v) hb_x[v] = a.xin[(a.t * a.N + n) * HB_RV + v];
+        } else {
+#pragma unroll
+            for (int v = 0; v < HB_RV; ++v) hb_x[v] = rec[a.in_row[v]];
+        }
         const double s_prev = a.s_prev[n];
         const double q_own = a.q_cur[n];
         const double ds = hb_rds(hb_x, s_prev, q_own, hb_p);
         double inflow = 0.0;
         for (int e = a.up_ptr[n]; e < a.up_ptr[n + 1]; ++e) inflow += a.q_cur[a.up_idx[e]];
         s_new = hb_max(a.min_value, s_prev + (ds + inflow));      // tmp_states .+ tmp_inflow_arr, then the clamp
-        rec[a.s_row] = s_new;                                      // saved after the update (solve.jl:51)
-        rec[a.o_row] = hb_rflux(hb_x, s_new, hb_p);                // flux_func over post-update states
+        const double o_new = hb_rflux(hb_x, s_new, hb_p);          // flux_func over post-update states
+        if (a.out2) {
+            *reinterpret_cast<double2 *>(a.out2 + (a.t * a.N + n) * 2) = make_double2(s_new, o_new);
+        } else {
+            rec[a.s_row] = s_new;                                  // saved after the update (solve.jl:51)
+            rec[a.o_row] = o_new;
+        }
         a.s_next[n] = s_new;
     } else {
         s_new = a.s_prev[n];                                       // initial state, used unclamped (solve.jl:47-49)
     }
     if (a.t + 1 < a.T) {
         const double *recn = a.rec + ((a.t + 1) * a.N + n) * a.R;
+        if (a.xin) {
 #pragma unroll
-        for (int v = 0; v < HB_RV; ++v) hb_x[v] = recn[a.in_row[v]];
+            for (int v = 0; v < HB_RV; ++v) hb_x[v] = a.xin[((a.t + 1) * a.N + n) * HB_RV + v];
+        } else {
+#pragma unroll
+            for (int v = 0; v < HB_RV; ++v) hb_x[v] = recn[a.in_row[v]];
+        }
         a.q_next[n] = hb_rflux(hb_x, s_new, hb_p);
     }
 }

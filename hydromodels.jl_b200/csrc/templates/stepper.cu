@@ -90,6 +90,8 @@ struct HbArgs {
     int target_per_node;
     int tma_in_ok;
     int tma_out_ok;
+    int compact_n;            // > 0: store only rows compact_rows[0..compact_n) of every step, as out[T][N][compact_n] — the SAME
+    int compact_rows[4];      //   cubin (hence bit-identical values) then serves as the first pass of the generic routed path
     int p_off[HB_ARR(HB_NP)];
     int p_mode[HB_ARR(HB_NP)];
 };
@@ -308,10 +310,15 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
     real *out_lane = a.out + n * HB_R;
     (void)in_warp; (void)out_warp; (void)out_lane; (void)in_lane;
 #if HB_V2 > 0
+    // the auxiliary stream is optional at run time (NULL: hb_aux reads as 0 — the first pass of the generic routed path runs
+    // this same kernel before the route rows exist)
+    const int in2_bytes = a.in2 ? kIn2Stage : 0;
     const i64 in2_step = a.N * (i64)HB_V2;
     const real *in2_warp = a.in2 + n0w * HB_V2;
     const real *gx2 = a.in2 + nc * HB_V2;
     const real *pf2_ptr = in2_warp + (i64)HB_STAGES * in2_step;
+#else
+    constexpr int in2_bytes = 0;
 #endif
 
     if (tma_in) {
@@ -323,10 +330,10 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
 #pragma unroll
             for (int s = 0; s < HB_STAGES; ++s) {
                 if (s < T) {
-                    hb_mbar_expect_tx(hb_smem_u32(&bars[s]), kInStage + kIn2Stage);
+                    hb_mbar_expect_tx(hb_smem_u32(&bars[s]), kInStage + in2_bytes);
                     hb_bulk_g2s(hb_smem_u32(sIn + s * HB_NPW * HB_V), in_warp + (i64)s * in_step, kInStage, hb_smem_u32(&bars[s]));
 #if HB_V2 > 0
-                    hb_bulk_g2s(hb_smem_u32(sIn2 + s * HB_NPW * HB_V2), in2_warp + (i64)s * in2_step, kIn2Stage, hb_smem_u32(&bars[s]));
+                    if (in2_bytes) hb_bulk_g2s(hb_smem_u32(sIn2 + s * HB_NPW * HB_V2), in2_warp + (i64)s * in2_step, kIn2Stage, hb_smem_u32(&bars[s]));
 #endif
                 }
             }
@@ -357,7 +364,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
             for (int v = 0; v < HB_V; ++v) hb_x[v] = sx[v];
 #if HB_V2 > 0
 #pragma unroll
-            for (int v = 0; v < HB_V2; ++v) hb_aux[v] = sIn2[slot * HB_NPW * HB_V2 + ln * HB_V2 + v];
+            for (int v = 0; v < HB_V2; ++v) hb_aux[v] = in2_bytes ? sIn2[slot * HB_NPW * HB_V2 + ln * HB_V2 + v] : (real)0.0;
 #endif
             // cross-proxy write-after-read: the lanes' generic-proxy loads of the slot must be ordered before the
             // async-proxy (TMA) refill of the same slot; __syncwarp orders the generic proxy only (the wave grid
@@ -365,10 +372,10 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
             hb_fence_proxy_async();
             __syncwarp();   // every lane has consumed the slot -> refill it HB_STAGES steps ahead
             if (lane == 0 && t + HB_STAGES < T) {
-                hb_mbar_expect_tx(hb_smem_u32(&bars[slot]), kInStage + kIn2Stage);
+                hb_mbar_expect_tx(hb_smem_u32(&bars[slot]), kInStage + in2_bytes);
                 hb_bulk_g2s(hb_smem_u32(sIn + slot * HB_NPW * HB_V), pf_ptr, kInStage, hb_smem_u32(&bars[slot]));
 #if HB_V2 > 0
-                hb_bulk_g2s(hb_smem_u32(sIn2 + slot * HB_NPW * HB_V2), pf2_ptr, kIn2Stage, hb_smem_u32(&bars[slot]));
+                if (in2_bytes) hb_bulk_g2s(hb_smem_u32(sIn2 + slot * HB_NPW * HB_V2), pf2_ptr, kIn2Stage, hb_smem_u32(&bars[slot]));
 #endif
             }
             pf_ptr += in_step;
@@ -382,7 +389,7 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
             gx += in_step;
 #if HB_V2 > 0
 #pragma unroll
-            for (int v = 0; v < HB_V2; ++v) hb_aux[v] = gx2[v];
+            for (int v = 0; v < HB_V2; ++v) hb_aux[v] = in2_bytes ? gx2[v] : (real)0.0;
             gx2 += in2_step;
 #endif
         }
@@ -396,7 +403,18 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_MINBLOCKS) hb_stepper(
 
         // ---- results of this step -------------------------------------------------------------
 #if HB_MODE == 0 && HB_R > 0
-        if (tma_out) {
+        if (a.compact_n > 0) {
+            // selected rows only, as out[T][N][compact_n]: through the warp's shared tile (a run-time row index into the
+            // register array hb_out would spill it), then one coalesced store per selected row
+            real *so = sOut;
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < HB_R; ++r) so[ln * HB_R + r] = hb_out[r];
+            __syncwarp();
+            if (valid) {
+                for (int k = 0; k < a.compact_n; ++k) a.out[(t * a.N + n) * a.compact_n + k] = so[ln * HB_R + a.compact_rows[k]];
+            }
+        } else if (tma_out) {
             real *so = sOut + ob * HB_NPW * HB_R;
             if (t >= HB_OBUF) {   // the bulk store that last read this tile must have drained it
                 if (lane == 0) hb_bulk_wait_read<HB_OBUF - 1>();

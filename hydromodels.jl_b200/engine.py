@@ -55,7 +55,7 @@ class RunDesc(C.Structure):
                 ("nn_params", C.c_void_p), ("target", C.c_void_p), ("target_per_node", C.c_int32),
                 ("warm_up", C.c_int32), ("min_value", C.c_double), ("out", C.c_void_p), ("objective", C.c_void_p),
                 ("final_states", C.c_void_p), ("uh_hist_out", C.c_void_p), ("elapsed_ms", C.c_void_p),
-                ("gradient", C.c_void_p), ("aux_input", C.c_void_p)]
+                ("gradient", C.c_void_p), ("aux_input", C.c_void_p), ("n_compact_rows", C.c_int32), ("compact_rows", C.c_int32 * 4)]
 
 
 class KernelInfo(C.Structure):
@@ -74,7 +74,7 @@ class RouteDesc(C.Structure):
                 ("in_row", C.c_void_p), ("params", C.c_void_p), ("n_param_values", C.c_int64),
                 ("param_offset", C.c_void_p), ("param_mode", C.c_void_p), ("htypes", C.c_void_p),
                 ("initstates", C.c_void_p), ("up_ptr", C.c_void_p), ("up_idx", C.c_void_p), ("min_value", C.c_double),
-                ("final_states", C.c_void_p), ("elapsed_ms", C.c_void_p)]
+                ("final_states", C.c_void_p), ("elapsed_ms", C.c_void_p), ("route_inputs", C.c_void_p), ("route_out", C.c_void_p)]
 
 
 class GridSpec(C.Structure):
@@ -397,6 +397,8 @@ class B200Model:
         # "generic" = stepper over all T, then one routing launch per step (any node list / graph)
         self.nodes_per_warp = 0           # tensor-path MLP bodies: 0 = default (32), 16 = two lanes per node (stepper.cu HB_NPW)
         self.grid_kernel = "wave"
+        self.generic_route_passes = 3        # generic routed path: 3 = stepper / route on compact planes / stepper (default);
+                                             #   2 = round 1's stepper + in-place route patches into the records
         self.grid_steps_per_launch = 0       # wave kernel: steps per launch (0 = chosen by the library from the grid width)
         self.grid_panel_min_cols = 3072      # wave kernel: grids at least this wide run as column panels (parallel.PanelledGridRun)
         self.block_threads, self.stages, self.max_registers = block_threads, stages, max_registers
@@ -443,19 +445,20 @@ class B200Model:
     # -- compile ------------------------------------------------------------------------------------
     def compiled(self, *, rows=None, objective=False, metric=0, shared_forcing=False,
                  uh_kmax: Sequence[int] = (), uh_on_device: bool = False, n_nodes: int = 0,
-                 component_min: Optional[Sequence[float]] = None, tangents: Sequence[str] = ()) -> CompiledStepper:
+                 component_min: Optional[Sequence[float]] = None, tangents: Sequence[str] = (),
+                 aux_rows: Sequence[str] = ()) -> CompiledStepper:
         # tensor-path MLP bodies: `nodes_per_warp = 16` doubles the warps of a small run (stepper.cu HB_NPW).  Measured on M50
         # 50 k x 3650: 48.6 ms vs 46.1 ms at 32 — the kernel is FP64-pipe bound (math_pipe_throttle), not short of warps, and
         # the duplicated scalar work costs more than the extra warps hide — so 32 stays the default and 16 is opt-in.
         npw = self.nodes_per_warp or 32
         key = (tuple(rows) if rows is not None else None, objective, metric, shared_forcing, tuple(uh_kmax), bool(uh_on_device), npw,
-               tuple(component_min) if component_min is not None else None, tuple(tangents))
+               tuple(component_min) if component_min is not None else None, tuple(tangents), tuple(aux_rows))
         if key not in self._cache:
             prog = lower_stepper(self._stepper_component(), rows=rows, objective=objective,
                                  uh_kmax=list(uh_kmax) if len(uh_kmax) else None, fast=self.fast,
                                  holes=self._route_rows(), nn_tensor=self.nn_tensor,
                                  precision=self.precision, uh_on_device=uh_on_device,
-                                 component_min_values=component_min, tangents=list(tangents) or None)
+                                 component_min_values=component_min, tangents=list(tangents) or None, aux_rows=list(aux_rows))
             # MLP-fused bodies keep 16+16 activations per net in registers: give them 168 (3 blocks/SM);
             # gradient bodies carry 1 + D doubles per value: all 255
             maxreg = self.max_registers or (255 if tangents else (168 if prog.nn_words else 0))
@@ -784,6 +787,23 @@ class B200Model:
                 if return_final_states:
                     return full, np.ascontiguousarray(full[:len(state_names), :, -1])
                 return full
+        if self.lumped is not None and not extra and self.generic_route_passes == 3:
+            # generic path for any node list / graph: stepper (route inputs only) -> route on compact planes -> stepper
+            # (all rows, route rows from the auxiliary stream): every record written once (RoutedDeviceRun)
+            inp = input if input.flags.f_contiguous else np.asfortranarray(input)
+            run3 = RoutedDeviceRun(self, N, T, params, config=cfg, initstates=init_all)
+            din = DeviceBuffer.from_host(inp.ravel(order="K"))
+            rec = DeviceBuffer(T * N * R * 8)
+            ms = run3.launch(din.ptr, rec.ptr, None, timed=True)
+            full = rec.to_host((R, N, T), order="F")
+            for bfr in (din, rec):
+                bfr.free()
+            run3.free()
+            if timing is not None:
+                timing["kernel_ms"] = ms
+            if return_final_states:
+                return full, np.ascontiguousarray(full[:len(state_names), :, -1])
+            return full
         rec = DeviceBuffer(T * N * Rr * 8)
         kernel_ms = 0.0
         if self.lumped is not None:
@@ -998,7 +1018,7 @@ class DeviceRun:
     def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None,
                  rows: Optional[Sequence[str]] = None, objective: Optional[str] = None, target=None,
                  warm_up: int = 1, ensemble: bool = False, _kmax=None, node_range: Optional[Tuple[int, int]] = None,
-                 uh_on_device: bool = False):
+                 uh_on_device: bool = False, aux_rows: Sequence[str] = ()):
         """`uh_on_device`: unit-hydrograph ordinates are evaluated in the kernel prologue from the parameters in the device
         buffer (`_kmax` then gives the ordinates to reserve per unit hydrograph) — the host table is only a placeholder."""
         self.eng, self.N, self.T = eng, int(N), int(T)
@@ -1015,7 +1035,7 @@ class DeviceRun:
         else:
             kmax = []
         self.ck = eng.compiled(rows=rows, objective=obj, metric=metric, shared_forcing=ensemble, uh_kmax=kmax,
-                               uh_on_device=uh_on_device, n_nodes=N)
+                               uh_on_device=uh_on_device, n_nodes=N, aux_rows=aux_rows)
         prog = self.ck.program
         flat, p_off, p_mode, htypes, uhw, kmax_host, nn = eng.prepare(prog, params, N, ensemble=ensemble, node_range=node_range)
         if uh_on_device and uhw:
@@ -1053,8 +1073,13 @@ class DeviceRun:
         return self.N * 8 if self.objective else self.T * self.N * self.n_rows * (4 if self.ck.spec.precision else 8)
 
     def launch(self, input_ptr: int, out_ptr: int, stream: Optional[int] = None, final_states_ptr: Optional[int] = None,
-               timed: bool = False) -> Optional[float]:
+               timed: bool = False, aux_ptr: Optional[int] = None, compact_rows: Sequence[int] = ()) -> Optional[float]:
+        """`compact_rows`: store only these record rows, `out_ptr` is then `[T][N][len(compact_rows)]` (same kernel)."""
         d = RunDesc()
+        d.aux_input = aux_ptr
+        d.n_compact_rows = len(compact_rows)
+        for k, r in enumerate(compact_rows):
+            d.compact_rows[k] = int(r)
         d.struct_size = C.sizeof(RunDesc)
         d.n_htype_sets = self.n_sets
         d.n_nodes, d.n_steps = self.N, self.T
@@ -1133,9 +1158,13 @@ class RouteStage:
         self.s_row = list(rec_rows).index(route.state_names[0])
         self.o_row = list(rec_rows).index(route.output_names[0])
 
-    def launch(self, rec_ptr: int, stream: Optional[int] = None, timed: bool = False) -> Optional[float]:
+    def launch(self, rec_ptr: Optional[int], stream: Optional[int] = None, timed: bool = False,
+               planes: Optional[Tuple[int, int]] = None) -> Optional[float]:
+        """`planes = (route_inputs_ptr, route_out_ptr)`: compact `[T][N][n_inputs]` in, `[T][N][2]` out instead of record rows."""
         el = C.c_float(0.0)
         d = RouteDesc()
+        if planes is not None:
+            d.route_inputs, d.route_out = planes
         d.struct_size = C.sizeof(RouteDesc)
         d.n_htype_sets = 1
         d.n_nodes, d.n_steps = self.N, self.T
@@ -1180,24 +1209,59 @@ class RouteStage:
 
 
 class RoutedDeviceRun:
-    """Device-resident run of a model that ends in a HydroRoute: the per-node stepper over all T steps
-    into the [T][N][R] records, then T+1 routing launches filling the route's two rows in place."""
+    """Device-resident run of a model that ends in a HydroRoute on ANY node list / graph, in three passes that touch every
+    byte once:
 
-    def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None):
+      1. the per-node stepper storing the route's input rows only -> compact plane `[T][N][RV]` (24 B in, 8 B out per cell-step);
+      2. T+1 routing launches on compact planes: route inputs in, `{state, outflow}` out (`hb_route_step`, planes mode);
+      3. the per-node stepper again with ALL rows, the route's two rows arriving through its auxiliary input stream — every
+         record is written once by a TMA bulk store.
+
+    Round 1 wrote the records first and patched the route's two 8-byte rows into the 104-byte records afterwards: 312 B of
+    DRAM traffic per cell-step for the route alone (read-modify-write at sector granularity).  The bucket algebra is now
+    evaluated twice (cheap: both stepper passes are HBM-bound) and the whole model moves ~1.6x its algorithmic bytes.
+    `legacy=True` keeps the in-place path (used by the per-step sharded run, `parallel.ShardedRoutedRun`)."""
+
+    def __init__(self, eng: B200Model, N: int, T: int, params, *, config=None, initstates=None, legacy: bool = False):
         if eng.route is None or eng.lumped is None:
             raise ValueError("RoutedDeviceRun needs a model with per-node components followed by a HydroRoute")
         self.cfg = normalize_config(config)
         rows = eng.component.var_names
-        s_name = eng.route.state_names[0]
+        route = eng.route
+        s_name, o_name = route.state_names[0], route.output_names[0]
         init = None if initstates is None else {k: v for k, v in initstates.items() if k != s_name}
-        self.stepper = DeviceRun(eng, N, T, params, config=self.cfg, initstates=init, rows=rows)
-        self.stage = RouteStage(eng, N, T, params, self.cfg, rows, None if initstates is None else initstates.get(s_name))
+        self.legacy = bool(legacy) or any(nm not in rows for nm in route.input_names)
         self.N, self.T, self.n_rows = int(N), int(T), len(rows)
+        self.stage = RouteStage(eng, N, T, params, self.cfg, rows, None if initstates is None else initstates.get(s_name))
+        if self.legacy:
+            self.stepper = DeviceRun(eng, N, T, params, config=self.cfg, initstates=init, rows=rows)
+        else:
+            self.stepper = DeviceRun(eng, N, T, params, config=self.cfg, initstates=init, rows=rows, aux_rows=[s_name, o_name])
+            self.route_in_rows = [list(rows).index(nm) for nm in route.input_names]
+            if len(self.route_in_rows) > 4:
+                raise NotImplementedError("at most 4 route inputs")
+            self.xin = DeviceBuffer(max(1, T * N * len(route.input_names)) * 8)
+            self.out2 = DeviceBuffer(max(1, T * N * 2) * 8)
         self.in_bytes, self.out_bytes = self.stepper.in_bytes, T * N * len(rows) * 8
 
-    def launch(self, input_ptr: int, rec_ptr: int, stream: Optional[int] = None):
-        self.stepper.launch(input_ptr, rec_ptr, stream)
-        self.stage.launch(rec_ptr, stream)
+    def launch(self, input_ptr: int, rec_ptr: int, stream: Optional[int] = None, timed: bool = False) -> Optional[float]:
+        if self.legacy:
+            ms = self.stepper.launch(input_ptr, rec_ptr, stream, timed=timed)
+            ms2 = self.stage.launch(rec_ptr, stream, timed=timed)
+            return (ms + ms2) if timed else None
+        # pass 1 is the SAME kernel as pass 3 (no auxiliary stream yet, only the route's input rows stored): its values are
+        # bit-identical to the rows pass 3 writes — a separately compiled "route inputs only" kernel differs in the last bit
+        # where the compiler contracts multiplies and adds differently
+        ms1 = self.stepper.launch(input_ptr, self.xin.ptr, stream, timed=timed, compact_rows=self.route_in_rows)
+        ms2 = self.stage.launch(None, stream, timed=timed, planes=(self.xin.ptr, self.out2.ptr))
+        ms3 = self.stepper.launch(input_ptr, rec_ptr, stream, timed=timed, aux_ptr=self.out2.ptr)
+        return (ms1 + ms2 + ms3) if timed else None
+
+    def free(self):
+        self.stage.free()
+        if not self.legacy:
+            self.xin.free()
+            self.out2.free()
 
 
 # ---------------------------------------------------------------------------------------------------

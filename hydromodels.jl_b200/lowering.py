@@ -95,6 +95,7 @@ class StepperProgram:
     uh_on_device: bool = False      # the prologue evaluates the unit-hydrograph ordinates (host table ignored)
     tangents: List[str] = field(default_factory=list)   # gradient run: parameter name of each direction
     nn_tc_bytes: int = 0            # Float32 tensor path (tcgen05): shared-memory bytes of the A and B tiles (0 = not used)
+    aux_names: List[str] = field(default_factory=list)   # rows copied from the auxiliary input stream (hb_aux[k])
 
 
 class _Builder:
@@ -255,7 +256,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                   holes: Sequence[str] = (), nn_tensor: bool = False, precision: str = "f64",
                   uh_on_device: bool = False,
                   component_min_values: Optional[Sequence[Optional[float]]] = None,
-                  tangents: Optional[Sequence[str]] = None) -> StepperProgram:
+                  tangents: Optional[Sequence[str]] = None, aux_rows: Sequence[str] = ()) -> StepperProgram:
     """Lower a per-node model (buckets, fluxes, neural fluxes, unit hydrographs) to one stepper
     body.  `rows`: subset/order of result rows to write (default: all = the reference result);
     `objective`: emit the last output row as `hb_sim` for the fused metric reduction instead of
@@ -263,8 +264,13 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
     `component_min_values[c]`: the state floor of component c when the call carries per-component configs
     (`/root/reference/src/model.jl:140-152`) — baked in as a literal; None = the run's `min_value` argument;
     `tangents`: parameter names to differentiate the objective by (gradient run: the body's temporaries become
-    `auto` / `hb_dual`, see hb_math.cuh; objective mode, Float64, no neural components)."""
+    `auto` / `hb_dual`, see hb_math.cuh; objective mode, Float64, no neural components);
+    `aux_rows`: rows (a subset of `holes`) whose values arrive through the kernel's auxiliary input stream
+    (`aux_input[T][N][len(aux_rows)]`, in this order) and are copied into the records instead of 0.0."""
     comps, input_names, all_rows = _flatten(component)
+    aux_rows = list(aux_rows)
+    if any(r not in holes for r in aux_rows):
+        raise LoweringError("aux_rows must be rows another kernel fills (holes)")
     if component_min_values is not None and len(component_min_values) != len(comps):
         raise LoweringError("Component configs length must equal components length")
     for c in comps:
@@ -608,7 +614,10 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
         step.append(f"hb_sim = {step_ref(out_vals[0])};")
     else:
         for r, vid in enumerate(out_vals):
-            step.append(f"hb_out[{r}] = {step_ref(vid)};")
+            if row_names[r] in aux_rows and row_names[r] not in env:
+                step.append(f"hb_out[{r}] = hb_aux[{aux_rows.index(row_names[r])}];")
+            else:
+                step.append(f"hb_out[{r}] = {step_ref(vid)};")
     for pre, (slot, post) in sorted(carried.items(), key=lambda kv: kv[1][0]):
         step.append(f"hb_c[{slot}] = {step_ref(post)};")
     for si in sorted(state_post):
@@ -673,7 +682,8 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                           uh_kmax=list(uh_kmax), uh_htype_set=[htype_set(u) for u in uhs],
                           nn_layout=nn_layout, nn_words=sum(n for _, _, n in nn_layout), n_carry=len(carried),
                           objective=objective, stats=stats, nn_tensor=any(net_mma) or any(net_tc), precision=precision,
-                          uh_on_device=bool(uh_on_device and uhs), tangents=tangents, nn_tc_bytes=tc_bytes)
+                          uh_on_device=bool(uh_on_device and uhs), tangents=tangents, nn_tc_bytes=tc_bytes,
+                          aux_names=[r for r in aux_rows if r in row_names] if not objective else [])
 
 
 def _body_to_tangent(body: str) -> str:

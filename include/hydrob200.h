@@ -135,7 +135,10 @@ typedef struct {
     double *uh_hist_out;         /* [sum_u (kmax_u-1)][N] or NULL                             */
     float *elapsed_ms;           /* optional HOST pointer: device time of the kernel(s)       */
     double *gradient;            /* gradient runs (spec.n_tangents = D): [D][N], d objective[n] / d direction k */
-    const void *aux_input;       /* spec.n_aux_inputs = V2 > 0: DEVICE [T][N][V2] (hb_run_device) */
+    const void *aux_input;       /* spec.n_aux_inputs = V2 > 0: DEVICE [T][N][V2] (hb_run_device); NULL = the body reads zeros */
+    int32_t n_compact_rows;      /* > 0 (hb_run_device, <= 4): store only rows compact_rows[] of every step, `out` is then */
+    int32_t compact_rows[4];     /*   [T][N][n_compact_rows].  Same kernel, same arithmetic: the selected rows are bit-identical
+                                      to those of a full run (first pass of the generic routed path) */
 } hb_run_desc;
 
 typedef struct {
@@ -210,6 +213,12 @@ typedef struct {
     double min_value;
     double *final_states;       /* DEVICE [N] or NULL */
     float *elapsed_ms;          /* optional HOST pointer */
+    /* planes mode (both non-NULL; `records` may then be NULL): the route inputs come from a compact DEVICE array
+     * route_inputs[T][N][n_inputs] and the state / outflow go to route_out[T][N][2] — every access coalesced.  The generic
+     * routed path is then three passes: stepper (rows = route inputs) -> this -> stepper (all rows, route_out as its
+     * auxiliary input), each record written once. */
+    const double *route_inputs;
+    double *route_out;
 } hb_route_desc;
 
 int hb_compile_route(const hb_route_spec *spec, const char *body, hb_model_t *out);

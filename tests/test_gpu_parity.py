@@ -332,6 +332,53 @@ def test_graph_route_equals_grid_route():
     assert_parity(b, ho.run_route(graph, x, p))
 
 
+@pytest.mark.parametrize("kind", ["irregular_grid", "graph", "gr4j_grid"])
+def test_generic_routed_path_three_passes_equal_the_in_place_path(kind):
+    """The generic routed path (any node list / graph, unit hydrographs in the per-node part) is three passes — stepper with
+    the route's inputs only, `hb_route_step` on compact planes, stepper with all rows and the route's rows from its
+    auxiliary input stream — so that every record is written once.  Bit-identical to round 1's two-pass path (stepper, then
+    route rows patched into the records) and within tolerance of the oracle."""
+    rng = np.random.default_rng(17)
+    R, Cc, T = 23, 31, 45
+    flw = rng.choice([1, 2, 4, 8, 16, 32, 64, 128, 0, 3], size=(R, Cc))
+    pos = [(r + 1, c + 1) for r in range(R) for c in range(Cc) if rng.random() < 0.85]
+    N = len(pos)
+    if kind == "gr4j_grid":
+        ht = np.arange(1, N + 1)
+        g = hm.models.gr4j(htypes=ht)
+        s = hm.Symbols("flow q q_routed s_river", "area_coef lag")
+        model = hm.HydroModel(name="gr4j_grid", components=tuple(g.components) + (
+            hm.HydroFlux("q ~ flow * area_coef", symbols=s, htypes=ht),
+            hm.HydroRoute(rfluxes=[hm.HydroFlux("q_routed ~ s_river / (1 + lag) + q", symbols=s)],
+                          dfluxes=[hm.StateFlux("s_river ~ q - q_routed", symbols=s)],
+                          aggr_func=hm.build_aggr_func(flw, pos), htypes=ht, name="grid_route")), input_names=["prcp", "ep"])
+        inp = sy.forcing("gr4j", 0, N, T)
+        p = {"params": dict(sy.parameters("gr4j", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))}
+        init = {k: np.full(N, v) for k, v in sy.INIT["gr4j"].items()}
+        init["s_river"] = rng.uniform(0, 2, N)
+    else:
+        model = hm.models.exphydro_grid(flw, pos)
+        if kind == "graph":                                      # the same topology as an explicit graph (adjacency' * q)
+            down = model.components[-1].aggr.downstream()
+            edges = [(n + 1, d + 1) for n, d in enumerate(down) if d >= 0]
+            comps = list(model.components)
+            s = hm.Symbols("q q_routed s_river", "lag")
+            comps[-1] = hm.HydroRoute(rfluxes=[hm.HydroFlux("q_routed ~ s_river / (1 + lag) + q", symbols=s)],
+                                      dfluxes=[hm.StateFlux("s_river ~ q - q_routed", symbols=s)],
+                                      aggr_func=hm.build_aggr_func(N, edges), htypes=np.arange(1, N + 1), name="graph_route")
+            model = hm.HydroModel(name="exphydro_graph", components=tuple(comps), input_names=model.input_names)
+        inp = sy.forcing("exphydro", 0, N, T)
+        p = {"params": dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))}
+        init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 2, N))
+    e3, e2 = hm.B200Model(model), hm.B200Model(model)
+    e3.grid_kernel = e2.grid_kernel = "generic"
+    e2.generic_route_passes = 2
+    got3, got2 = e3(inp, p, initstates=init), e2(inp, p, initstates=init)
+    assert np.array_equal(got3, got2)
+    assert_parity(got3, ho.run_model(model, inp, p, initstates=init))
+    assert np.array_equal(e3(inp, p), e2(inp, p))                # default (zero) initial states
+
+
 # ---- opt-in Float32 mode (north star: "an opt-in Float32 mode has a stated NSE/flow tolerance") ---------
 @pytest.mark.parametrize("name,T", [("exphydro", 1460), ("gr4j", 1460), ("hbv", 730), ("m50", 365)])
 def test_float32_mode(name, T):
