@@ -668,13 +668,51 @@ def bench_gradient(args):
     return 0
 
 
+def bench_adjoint(args):
+    """SURVEY.md §8f row 3 (reverse mode): d SSE / d (690 MLP weights, 11 physical parameters, 2 initial states) of M50 on
+    50 000 basins x 3650 steps in ONE backward sweep over the stored state trajectory (templates/adjoint.cu), next to the
+    forward run that stores the trajectory.  What the reference does with Zygote through its ImmutableSolver
+    (/root/reference/README.md:161-187)."""
+    import hydromodels_jl_b200 as hm
+    from hydromodels_jl_b200 import synthetic as sy
+    hm.engine.init(0)
+    N, T = 50_000, 3650
+    model = hm.models.m50(htypes=np.arange(1, N + 1))
+    et, q = hm.models.m50_chains()
+    p = {"params": sy.parameters("m50", 0, N), "nns": {"etnn": et.init_params(1) * 0.5, "qnn": q.init_params(2) * 0.5}}
+    init = {k: np.full(N, v) for k, v in sy.INIT["m50"].items()}
+    inp = sy.forcing("m50", 0, N, T)
+    target = np.abs(0.3 * inp[0, 0] + 0.5)                 # one observed series shared by all basins
+    eng = hm.B200Model(model)
+    ms_a, ms_f = [], []
+    for i in range(max(1, args.warmup // 2) + args.steps):
+        tm = {}
+        loss, g = eng.gradient(inp, p, target, metric="SSE", warm_up=366, initstates=init, timing=tm)
+        if i >= max(1, args.warmup // 2):
+            ms_a.append(tm["kernel_ms"]); ms_f.append(tm["forward_ms"])
+    info = tm["kernel"].info()
+    ma, mf = float(np.mean(ms_a)), float(np.mean(ms_f))
+    gn = np.concatenate([g["nns"]["etnn"], g["nns"]["qnn"]])
+    print(json.dumps({"metric": "basin-timesteps/sec of a reverse-mode gradient run (backward sweep)", "value": N * T / (ma * 1e-3),
+                      "unit": "basin-timesteps/s", "n_gpus": 1, "steps": args.steps, "warmup": max(1, args.warmup // 2), "ms_per_step": ma,
+                      "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "gradient_m50_adjoint_50k_basins_x_3650d", "basins": N, "timesteps": T, "metric": "SSE",
+                                 "gradient_entries": {"mlp_weights": int(gn.size), "physical_parameters_per_basin": len(model.param_names),
+                                                      "initial_states_per_basin": len(model.state_names)}},
+                      "forward_trajectory_ms": mf, "adjoint_over_forward": ma / mf if mf else None,
+                      "registers": info["registers_per_thread"], "spill_bytes": info["local_bytes_per_thread"], "blocks_per_sm": info["max_blocks_per_sm"],
+                      "finite": bool(np.all(np.isfinite(gn)) and np.all(np.isfinite(loss))), "weight_gradient_norm": float(np.linalg.norm(gn)),
+                      "gpu_launches": 2 * (args.steps + max(1, args.warmup // 2)), "timing": "CUDA events around each kernel"}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096", "calibrate_exphydro", "gradient_exphydro", "irf_route", "irf_route_ragged", "exphydro_single_basin_365d"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096", "calibrate_exphydro", "gradient_exphydro", "gradient_m50_adjoint", "irf_route", "irf_route_ragged", "exphydro_single_basin_365d"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="opt-in Float32 mode (per-node workloads; device-resident value only)")
@@ -729,6 +767,8 @@ def main():
         return bench_calibration(args) if rank == 0 else 0
     if args.workload == "gradient_exphydro":
         return bench_gradient(args) if rank == 0 else 0
+    if args.workload == "gradient_m50_adjoint":
+        return bench_adjoint(args) if rank == 0 else 0
     if args.workload in ("irf_route", "irf_route_ragged"):
         return bench_irf(args) if rank == 0 else 0
     if args.workload == "exphydro_single_basin_365d":

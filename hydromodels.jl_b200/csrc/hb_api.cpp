@@ -216,7 +216,8 @@ std::string splice(const char *tmpl, const char *body) {
 
 // ---- model object ----------------------------------------------------------------------------------
 struct hb_model_s {
-    int kind = 0;   // 0 stepper, 1 route, 2 fused grid
+    int kind = 0;   // 0 stepper, 1 route, 2 fused grid, 3 adjoint
+    hb_adjoint_spec aspec{};
     hb_stepper_spec spec{};
     hb_route_spec rspec{};
     hb_grid_spec gspec{};
@@ -308,7 +309,12 @@ int load_model(hb_model_s *m) {
     // whenever the sum comes near it, not only when the dynamic part alone exceeds it
     if (m->dyn_smem + 4096 > 48 * 1024)
         HB_DRV(g_drv.FuncSetAttribute(m->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
-    if (m->spec.nn_words > 0) {
+    if (m->kind == 3 && m->aspec.nn_words > 0) {
+        size_t bytes = 0;
+        HB_DRV(g_drv.ModuleGetGlobal(&m->nn_const, &bytes, m->module, "hb_nn_const"));
+        if (bytes != (size_t)m->aspec.nn_words * 8) return fail(HB_ERR_CUDA, "hb_nn_const has %zu bytes, expected %d", bytes, m->aspec.nn_words * 8);
+    }
+    if (m->kind == 0 && m->spec.nn_words > 0) {
         size_t bytes = 0;
         HB_DRV(g_drv.ModuleGetGlobal(&m->nn_const, &bytes, m->module, "hb_nn_const"));
         const size_t want = (size_t)m->spec.nn_words * (m->spec.precision ? 4 : 8);
@@ -1034,6 +1040,86 @@ int hb_route_step_device(hb_model_t m, const hb_route_desc *d, int64_t t, const 
     if ((rc = load_model(m))) return rc;
     HB_CUDA(cudaSetDevice(g_device));
     return launch_route_step(m, d, t, s_prev, s_next, q_cur, q_next, (cudaStream_t)stream);
+}
+
+// ---- reverse-mode gradient (templates/adjoint.cu) ----------------------------------------------------------------
+int hb_compile_adjoint(const hb_adjoint_spec *spec, const char *body, hb_model_t *out) {
+    if (!spec || !body || !out) return fail(HB_ERR_INVALID, "NULL argument");
+    if (spec->struct_size != (int32_t)sizeof(hb_adjoint_spec)) return fail(HB_ERR_INVALID, "hb_adjoint_spec.struct_size mismatch");
+    if (spec->n_inputs < 0 || spec->n_states < 0 || spec->n_params < 0 || spec->n_params > HB_MAX_PARAMS || spec->nn_words < 0)
+        return fail(HB_ERR_INVALID, "hb_adjoint_spec out of range");
+    hb_model_s *m = new hb_model_s();
+    m->kind = 3;
+    m->aspec = *spec;
+    m->block = spec->block_threads > 0 ? spec->block_threads : 128;
+    if (m->block % 32 || m->block > 1024) { delete m; return fail(HB_ERR_INVALID, "block_threads must be a multiple of 32 <= 1024"); }
+    m->dyn_smem = 0;
+    char defs[512];
+    snprintf(defs, sizeof defs, "//@@HB:DEFINES\n#define HB_V %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_NN_WORDS %d\n#define HB_BLOCK %d\n"
+             "#define HB_UHW_TOTAL 0\n#define HB_UHH_TOTAL 0\n",
+             spec->n_inputs, spec->n_states, spec->n_params, spec->nn_words, m->block);
+    std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";
+    m->source = splice(kAdjointTemplate, full_body.c_str());
+    m->kernel_name = "hb_adjoint";
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--fmad=true"};
+    int rc = nvrtc_compile(m->source, opts, m->cubin, m->from_cache);
+    if (rc) { delete m; return rc; }
+    *out = m;
+    return HB_OK;
+}
+
+int hb_run_adjoint_device(hb_model_t m, const hb_adjoint_desc *d, void *stream) {
+    if (!m || m->kind != 3) return fail(HB_ERR_INVALID, "not an adjoint model");
+    if (!d || d->struct_size != (int32_t)sizeof(hb_adjoint_desc)) return fail(HB_ERR_INVALID, "hb_adjoint_desc.struct_size mismatch");
+    const hb_adjoint_spec &s = m->aspec;
+    if (d->n_nodes <= 0 || d->n_steps < 0 || !d->target || !d->scale || !d->grad_params || !d->grad_init || !d->loss ||
+        (s.n_inputs > 0 && !d->input) || (s.n_states > 0 && d->n_steps > 1 && !d->trajectory) || (s.nn_words > 0 && (!d->nn_params || !d->grad_nn)))
+        return fail(HB_ERR_INVALID, "bad adjoint descriptor");
+    if (d->warm_up < 1) return fail(HB_ERR_INVALID, "warm_up must be >= 1");
+    if (s.n_params > 0 && (!d->params || !d->param_offset || !d->param_mode)) return fail(HB_ERR_INVALID, "params / param tables are NULL");
+    int rc = load_model(m);
+    if (rc) return rc;
+    HB_CUDA(cudaSetDevice(g_device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // HbAdjArgs mirror (templates/adjoint.cu): 11 pointers, 2 i64, 1 double, 2 int, int tables
+    unsigned char buf[11 * 8 + 16 + 8 + 8 + 8 * HB_MAX_PARAMS + 16];
+    memset(buf, 0, sizeof buf);
+    size_t o = 0;
+    auto put = [&](const void *p, size_t n) { memcpy(buf + o, p, n); o += n; };
+    const void *ptrs[11] = {d->input, d->trajectory, d->params, d->htypes, d->initstates, d->target, d->scale,
+                            d->grad_params, d->grad_init, d->grad_nn, d->loss};
+    put(ptrs, sizeof ptrs);
+    int64_t N = d->n_nodes, T = d->n_steps;
+    put(&N, 8);
+    put(&T, 8);
+    double minv = d->min_value;
+    put(&minv, 8);
+    int warm = d->warm_up, tpn = d->target_per_node;
+    put(&warm, 4);
+    put(&tpn, 4);
+    const int np = s.n_params > 0 ? s.n_params : 1;
+    std::vector<int> tmp(np, 0);
+    for (int j = 0; j < s.n_params; ++j) tmp[j] = d->param_offset[j];
+    put(tmp.data(), 4 * np);
+    for (int j = 0; j < s.n_params; ++j) tmp[j] = d->param_mode[j];
+    put(tmp.data(), 4 * np);
+    void *params[1] = {buf};
+    if (d->elapsed_ms) {
+        if (!m->ev0) { HB_CUDA(cudaEventCreate(&m->ev0)); HB_CUDA(cudaEventCreate(&m->ev1)); }
+        HB_CUDA(cudaEventRecord(m->ev0, st));
+    }
+    if (s.nn_words > 0) {
+        HB_CUDA(cudaMemsetAsync(d->grad_nn, 0, (size_t)s.nn_words * 8, st));
+        HB_DRV(g_drv.MemcpyDtoDAsync(m->nn_const, (CUdeviceptr)(uintptr_t)d->nn_params, (size_t)s.nn_words * 8, (CUstream)st));
+    }
+    const unsigned grid = (unsigned)((N + m->block - 1) / m->block);
+    HB_DRV(g_drv.LaunchKernel(m->func, grid, 1, 1, m->block, 1, 1, 0, (CUstream)st, params, nullptr));
+    if (d->elapsed_ms) {
+        HB_CUDA(cudaEventRecord(m->ev1, st));
+        HB_CUDA(cudaEventSynchronize(m->ev1));
+        HB_CUDA(cudaEventElapsedTime(d->elapsed_ms, m->ev0, m->ev1));
+    }
+    return HB_OK;
 }
 
 // ---- fused dense-grid model -------------------------------------------------------------------------------

@@ -95,6 +95,20 @@ class GridDesc(C.Structure):
                 ("in_col0", C.c_int32), ("out_pitch", C.c_int32), ("out_base", C.c_int32)]
 
 
+class AdjointSpec(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_inputs", C.c_int32), ("n_states", C.c_int32), ("n_params", C.c_int32),
+                ("nn_words", C.c_int32), ("block_threads", C.c_int32)]
+
+
+class AdjointDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_htype_sets", C.c_int32), ("n_nodes", C.c_int64), ("n_steps", C.c_int64),
+                ("input", C.c_void_p), ("trajectory", C.c_void_p), ("params", C.c_void_p), ("n_param_values", C.c_int64),
+                ("param_offset", C.c_void_p), ("param_mode", C.c_void_p), ("htypes", C.c_void_p), ("initstates", C.c_void_p),
+                ("nn_params", C.c_void_p), ("target", C.c_void_p), ("target_per_node", C.c_int32), ("warm_up", C.c_int32),
+                ("min_value", C.c_double), ("scale", C.c_void_p), ("grad_params", C.c_void_p), ("grad_init", C.c_void_p),
+                ("grad_nn", C.c_void_p), ("loss", C.c_void_p), ("elapsed_ms", C.c_void_p)]
+
+
 class HaloEdge(C.Structure):
     _fields_ = [("peer", C.c_int32), ("s_row0", C.c_int32), ("s_col0", C.c_int32), ("r_row0", C.c_int32), ("r_col0", C.c_int32),
                 ("nrows", C.c_int32), ("ncols", C.c_int32), ("peer_slot", C.c_int32)]
@@ -122,6 +136,8 @@ def lib():
         "hb_model_info": [C.c_void_p, C.POINTER(KernelInfo)], "hb_free_model": [C.c_void_p],
         "hb_run": [C.c_void_p, C.POINTER(RunDesc)], "hb_run_device": [C.c_void_p, C.POINTER(RunDesc), C.c_void_p],
         "hb_compile_route": [C.POINTER(RouteSpec), C.c_char_p, C.POINTER(C.c_void_p)],
+        "hb_compile_adjoint": [C.POINTER(AdjointSpec), C.c_char_p, C.POINTER(C.c_void_p)],
+        "hb_run_adjoint_device": [C.c_void_p, C.POINTER(AdjointDesc), C.c_void_p],
         "hb_compile_grid": [C.POINTER(GridSpec), C.c_char_p, C.POINTER(C.c_void_p)],
         "hb_run_grid_device": [C.c_void_p, C.POINTER(GridDesc), C.c_void_p],
         "hb_grid_status": [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)],
@@ -231,6 +247,44 @@ class CompiledStepper:
         self.spec = spec
         h = C.c_void_p()
         check(lib().hb_compile_stepper(C.byref(spec), program.body.encode(), C.byref(h)))
+        self.handle = h
+
+    def source(self) -> str:
+        s = C.c_char_p()
+        n = C.c_int64()
+        check(lib().hb_model_source(self.handle, C.byref(s), C.byref(n)))
+        return s.value.decode()
+
+    def cubin(self) -> bytes:
+        p = C.c_void_p()
+        n = C.c_int64()
+        check(lib().hb_model_cubin(self.handle, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value)
+
+    def info(self) -> Dict[str, int]:
+        k = KernelInfo()
+        check(lib().hb_model_info(self.handle, C.byref(k)))
+        return {f: getattr(k, f) for f, _ in KernelInfo._fields_}
+
+    def __del__(self):
+        try:
+            if self.handle and _lib is not None:
+                _lib.hb_free_model(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class CompiledAdjoint:
+    """The reverse-mode kernel of a per-node model (`lowering.lower_stepper(adjoint=True)` spliced into templates/adjoint.cu)."""
+
+    def __init__(self, program, block_threads: int = 0):
+        self.program = program
+        spec = AdjointSpec(C.sizeof(AdjointSpec), len(program.input_names), len(program.state_names), len(program.param_slots),
+                           program.nn_words, block_threads)
+        self.spec = spec
+        h = C.c_void_p()
+        check(lib().hb_compile_adjoint(C.byref(spec), program.body.encode(), C.byref(h)))
         self.handle = h
 
     def source(self) -> str:
@@ -922,7 +976,7 @@ class B200Model:
     # -- gradients: forward-mode tangents through the same fused stepper ------------------------------
     def gradient(self, input, params, target, *, metric: str = "SSE", warm_up: int = 1, config=None, initstates=None,
                  wrt: Optional[Sequence[str]] = None, n_members: Optional[int] = None, max_directions: int = 6,
-                 timing: Optional[dict] = None):
+                 timing: Optional[dict] = None, mode: Optional[str] = None):
         """`(loss, grads)`: the objective of `objective()` and its derivative w.r.t. the physical parameters — what the
         reference obtains with `Zygote.gradient` through its ImmutableSolver (`/root/reference/README.md:161-187`; loss
         `sum((sim - obs).^2)` = metric "SSE").  Forward mode: the stepper body is re-lowered with value + D tangents per
@@ -932,6 +986,13 @@ class B200Model:
         (scalar, `[ntypes]`, or `[n_members]` for ensembles) and is the derivative of `sum(loss)`: node types shared by
         several nodes sum their nodes' derivatives.  `loss` is the per-node / per-member objective vector.
         Models with neural components are not covered (hundreds of weights need the reverse-mode adjoint)."""
+        if mode is None:                    # models with neural fluxes: hundreds of weights -> the reverse-mode adjoint
+            mode = "reverse" if self.component.nn_names else "forward"
+        if mode == "reverse":
+            return self.gradient_reverse(input, params, target, metric=metric, warm_up=warm_up, config=config, initstates=initstates,
+                                         timing=timing)
+        if mode != "forward":
+            raise ValueError("mode must be 'forward' or 'reverse'")
         pdict = _as_componentvector(params)["params"]
         names = list(wrt) if wrt is not None else [nm for nm in self.component.param_names]
         if not names:
@@ -961,6 +1022,115 @@ class B200Model:
                     out = np.zeros(np.size(pdict[nm]), dtype=np.float64)
                     np.add.at(out, htypes[mode - 2], g[k])
                     grads[nm] = out
+        return loss, grads
+
+
+    # -- gradients: the reverse-mode adjoint of the stepper (neural-network weights) -------------------
+    def gradient_reverse(self, input, params, target, *, metric: str = "SSE", warm_up: int = 1, config=None, initstates=None,
+                         timing: Optional[dict] = None):
+        """`(loss, grads)` like `gradient`, by ONE backward sweep over the stored state trajectory (templates/adjoint.cu) —
+        the reverse-mode counterpart of the reference's `Zygote.gradient` through its ImmutableSolver
+        (`/root/reference/README.md:161-187`, `docs/src/tutorials/neuralnetwork_embeding.md`): what training the neural fluxes
+        of a hybrid model (M50: 690 weights) needs.  `grads` holds every physical parameter (shape of `params["params"][name]`),
+        every state's initial value (per node) and `grads["nns"][chain]` (flat, the layout of `params["nns"][chain]`, summed
+        over all nodes).  Metrics that are linear in the squared errors: SSE, MSE, NSE.  Multi-node models (3D input)."""
+        m = metric.lower()
+        if m not in ("sse", "mse", "nse"):
+            raise NotImplementedError("the adjoint run covers SSE / MSE / NSE (metrics linear in the squared errors)")
+        if self.route is not None or self.precision != "f64":
+            raise NotImplementedError("the adjoint run is for per-node models in Float64")
+        if not self.multinode:
+            raise NotImplementedError("the adjoint run takes multi-node models (give the components htypes; one node is N = 1)")
+        cfg = normalize_config(config)
+        input = np.asarray(input, dtype=np.float64)
+        N, T = self._dims(input, False, None)
+        _check_config(cfg, T)
+        key = ("adjoint",)
+        if key not in self._cache:
+            self._cache[key] = CompiledAdjoint(lower_stepper(self.component, objective=True, fast=True, adjoint=True), self.block_threads)
+        ck = self._cache[key]
+        prog = ck.program
+        flat, p_off, p_mode, htypes, _, _, nn = self.prepare(prog, params, N)
+        pdict = _as_componentvector(params)["params"]
+        init = self._initstates(prog, initstates, N)
+        S, NP = len(prog.state_names), len(prog.param_slots)
+        tgt = np.asarray(target, dtype=np.float64)
+        per_node = 0
+        if tgt.ndim == 2:
+            if tgt.shape != (N, T):
+                raise ValueError("target must be [T] or [N, T]")
+            tgt2 = tgt
+            tgt, per_node = np.ascontiguousarray(tgt.T), 1
+        elif tgt.shape != (T,):
+            raise ValueError("target must be [T] or [N, T]")
+        else:
+            tgt2 = np.broadcast_to(tgt, (N, T))
+        w = tgt2[:, warm_up - 1:]
+        if m == "sse":
+            scale = np.ones(N)
+        elif m == "mse":
+            scale = np.full(N, 1.0 / w.shape[1])
+        else:
+            scale = 1.0 / np.sum((w - w.mean(axis=1, keepdims=True)) ** 2, axis=1)
+        inp = input if input.flags.f_contiguous else np.asfortranarray(input)
+        # forward: the state trajectory [T][N][S]
+        fwd = DeviceRun(self, N, T, params, config=cfg, initstates=initstates, rows=list(prog.state_names))
+        bufs = {"in": DeviceBuffer.from_host(inp.ravel(order="K")), "traj": DeviceBuffer(max(1, T * N * S) * 8),
+                "params": DeviceBuffer.from_host(flat), "tgt": DeviceBuffer.from_host(np.ascontiguousarray(tgt)),
+                "scale": DeviceBuffer.from_host(np.ascontiguousarray(scale)), "gp": DeviceBuffer(max(1, NP * N) * 8),
+                "gi": DeviceBuffer(max(1, S * N) * 8), "gn": DeviceBuffer(max(1, prog.nn_words) * 8), "loss": DeviceBuffer(N * 8)}
+        if htypes is not None:
+            bufs["ht"] = DeviceBuffer.from_host(htypes)
+        if init is not None:
+            bufs["init"] = DeviceBuffer.from_host(init)
+        if nn is not None:
+            bufs["nn"] = DeviceBuffer.from_host(nn)
+        ms_f = fwd.launch(bufs["in"].ptr, bufs["traj"].ptr, None, timed=True) if S else 0.0
+        d = AdjointDesc()
+        d.struct_size = C.sizeof(AdjointDesc)
+        d.n_htype_sets = 0 if htypes is None else htypes.shape[0]
+        d.n_nodes, d.n_steps = N, T
+        d.input, d.trajectory = bufs["in"].ptr, bufs["traj"].ptr
+        d.params, d.n_param_values = bufs["params"].ptr, flat.size
+        d.param_offset, d.param_mode = _ptr(p_off), _ptr(p_mode)
+        d.htypes = bufs["ht"].ptr if "ht" in bufs else None
+        d.initstates = bufs["init"].ptr if "init" in bufs else None
+        d.nn_params = bufs["nn"].ptr if "nn" in bufs else None
+        d.target, d.target_per_node, d.warm_up = bufs["tgt"].ptr, per_node, int(warm_up)
+        d.min_value = cfg.min_value
+        d.scale, d.grad_params, d.grad_init = bufs["scale"].ptr, bufs["gp"].ptr, bufs["gi"].ptr
+        d.grad_nn, d.loss = bufs["gn"].ptr, bufs["loss"].ptr
+        el = C.c_float(0.0)
+        d.elapsed_ms = C.cast(C.byref(el), C.c_void_p)
+        check(lib().hb_run_adjoint_device(ck.handle, C.byref(d), None))
+        gp = bufs["gp"].to_host((max(1, NP), N))
+        gi = bufs["gi"].to_host((max(1, S), N))
+        gn = bufs["gn"].to_host((max(1, prog.nn_words),))
+        loss = bufs["loss"].to_host((N,))
+        for b_ in bufs.values():
+            b_.free()
+        if m == "nse":
+            loss = loss - 1.0                                   # -NSE = -1 + SSE / var(obs): what `objective(metric="NSE")` returns
+        if timing is not None:
+            timing.update(kernel_ms=el.value, forward_ms=ms_f, kernel=ck)
+        grads: Dict[str, object] = {}
+        for nm in dict.fromkeys(pn for pn, _ in prog.param_slots):
+            out = np.zeros(np.size(pdict[nm]), dtype=np.float64)
+            for j, (pn, hs) in enumerate(prog.param_slots):
+                if pn != nm:
+                    continue
+                mode_j = int(p_mode[j])
+                if mode_j == 0:
+                    out[0] += gp[j].sum()
+                elif mode_j == 1:
+                    out += gp[j]
+                else:
+                    np.add.at(out, htypes[mode_j - 2], gp[j])
+            grads[nm] = out if np.ndim(pdict[nm]) else float(out[0])
+        for si, sn in enumerate(prog.state_names):
+            grads[sn] = gi[si].copy()
+        if prog.nn_layout:
+            grads["nns"] = {name: gn[off:off + n].copy() for name, off, n in prog.nn_layout}
         return loss, grads
 
 

@@ -256,7 +256,7 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                   holes: Sequence[str] = (), nn_tensor: bool = False, precision: str = "f64",
                   uh_on_device: bool = False,
                   component_min_values: Optional[Sequence[Optional[float]]] = None,
-                  tangents: Optional[Sequence[str]] = None, aux_rows: Sequence[str] = ()) -> StepperProgram:
+                  tangents: Optional[Sequence[str]] = None, aux_rows: Sequence[str] = (), adjoint: bool = False):
     """Lower a per-node model (buckets, fluxes, neural fluxes, unit hydrographs) to one stepper
     body.  `rows`: subset/order of result rows to write (default: all = the reference result);
     `objective`: emit the last output row as `hb_sim` for the fused metric reduction instead of
@@ -460,6 +460,15 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
             raise LoweringError(f"row {r} is not produced by the model")
     # `holes`: rows another kernel fills in later (the route's state / outflow rows) — written as 0.0
     out_vals = [env[r] if r in env else zero for r in row_names]
+
+    if adjoint:
+        # reverse-mode program of the same step DAG (templates/adjoint.cu): see _emit_adjoint
+        if not objective or precision != "f64" or not fast:
+            raise LoweringError("the adjoint run differentiates the objective row, in Float64, with the hb_math helpers")
+        if uhs or any(isinstance(c, NeuralBucket) for c in comps):
+            raise LoweringError("the adjoint run covers HydroBucket / HydroFlux / NeuralFlux components (no unit hydrographs, no NeuralBucket)")
+        return _emit_adjoint(b, out_vals[0], statements, param_slots, nets, nn_layout, raw_states, state_floor, input_names,
+                             state_names, htype_sets)
 
     # ---- carry detection (class S) --------------------------------------------------------------------
     by_erased: Dict[object, Dict[int, int]] = {}
@@ -684,6 +693,305 @@ def lower_stepper(component: Component, *, rows: Optional[Sequence[str]] = None,
                           objective=objective, stats=stats, nn_tensor=any(net_mma) or any(net_tc), precision=precision,
                           uh_on_device=bool(uh_on_device and uhs), tangents=tangents, nn_tc_bytes=tc_bytes,
                           aux_names=[r for r in aux_rows if r in row_names] if not objective else [])
+
+
+# ---------------------------------------------------------------------------------------------
+# reverse mode: the adjoint of one step (templates/adjoint.cu) — what Zygote does through the reference's
+# ImmutableSolver (/root/reference/README.md:161-187, src/solve.jl:62-79), here generated from the same step DAG
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class AdjointProgram:
+    body: str
+    input_names: List[str]
+    state_names: List[str]
+    param_slots: List[Tuple[str, Optional[int]]]
+    htype_sets: List[np.ndarray]
+    nn_layout: List[Tuple[str, int, int]]
+    nn_words: int
+    nn_group_offset: List[int]      # first 32-weight accumulator group of every chain
+    n_groups: int
+    uh: List = field(default_factory=list)            # (no unit hydrographs in an adjoint run: what B200Model.prepare expects)
+    uh_kmax: List[int] = field(default_factory=list)
+    uh_htype_set: List = field(default_factory=list)
+
+
+def _act_derivative(act: str, z: str, a: str) -> str:
+    """d act / d z given the pre-activation `z` and the activation value `a` (selects mirror hb_max: ties take the identity branch)."""
+    if act == "identity": return "1.0"
+    if act == "tanh": return f"fma(-{a}, {a}, 1.0)"
+    if act == "leakyrelu": return f"((0.01 * {z} > {z}) ? 0.01 : 1.0)"
+    if act == "relu": return f"((0.0 > {z}) ? 0.0 : 1.0)"
+    if act == "sigmoid": return f"({a} * (1.0 - {a}))"
+    raise LoweringError(f"no derivative for activation {act}")
+
+
+def _mlp_helper_bwd(idx: int, chain, offset: int) -> str:
+    """Forward recomputation + backward pass of one chain for ONE node, and the accumulation of the weight gradient over the
+    32 nodes of the warp: the products `delta_o * a_i` of 32 consecutive flat parameters at a time go through a butterfly
+    (hb_transpose_reduce32) that leaves lane l with the warp total of parameter 32 g + l, added to this lane's accumulator
+    `gw[g]`.  Flat parameter order = the chain's own (`weight[out, in]` column-major, then bias)."""
+    acts = _ACT_C
+    args = ", ".join(f"const double x{i}" for i in range(chain.n_in))
+    dys = ", ".join(f"const double dy{o}" for o in range(chain.n_out))
+    L = [f"__device__ __forceinline__ void hb_mlp_bwd_{idx}(const int lane, {args}, {dys}, double* __restrict__ dx, double* __restrict__ gw) {{"]
+    prev = [f"x{i}" for i in range(chain.n_in)]
+    acts_in = [prev]
+    zs, off, offs = [], offset, []
+    for li, l in enumerate(chain.layers):
+        bias = off + l.n_out * l.n_in
+        z = [f"z{li + 1}_{o}" for o in range(l.n_out)]
+        a = [f"a{li + 1}_{o}" for o in range(l.n_out)]
+        for o in range(l.n_out):
+            L.append(f"    double {z[o]} = HB_NNW({bias + o});")
+        for i in range(l.n_in):
+            for o in range(l.n_out):
+                L.append(f"    {z[o]} = fma(HB_NNW({off + i * l.n_out + o}), {prev[i]}, {z[o]});")
+        for o in range(l.n_out):
+            L.append(f"    const double {a[o]} = {acts[l.activation].format(z[o])};")
+        zs.append(z)
+        offs.append(off)
+        off += l.n_params
+        prev = a
+        acts_in.append(a)
+    # backward: delta of the last layer from dy, then down
+    g_out = [f"dy{o}" for o in range(chain.n_out)]
+    deltas = [None] * len(chain.layers)
+    for li in range(len(chain.layers) - 1, -1, -1):
+        l = chain.layers[li]
+        d = [f"d{li + 1}_{o}" for o in range(l.n_out)]
+        for o in range(l.n_out):
+            L.append(f"    const double {d[o]} = {g_out[o]} * {_act_derivative(l.activation, zs[li][o], acts_in[li + 1][o])};")
+        deltas[li] = d
+        g_in = [f"g{li}_{i}" for i in range(l.n_in)]
+        for i in range(l.n_in):
+            terms = [f"HB_NNW({offs[li] + i * l.n_out + o}) * {d[o]}" for o in range(l.n_out)]
+            L.append(f"    double {g_in[i]} = {terms[0]};")
+            for o in range(1, l.n_out):
+                L.append(f"    {g_in[i]} = fma(HB_NNW({offs[li] + i * l.n_out + o}), {d[o]}, {g_in[i]});")
+        g_out = g_in
+    for i in range(chain.n_in):
+        L.append(f"    dx[{i}] = {g_out[i]};")
+    # weight gradient: flat local index -> product expression
+    prods: List[str] = []
+    for li, l in enumerate(chain.layers):
+        for i in range(l.n_in):
+            for o in range(l.n_out):
+                prods.append(f"{deltas[li][o]} * {acts_in[li][i]}")
+        for o in range(l.n_out):
+            prods.append(deltas[li][o])
+    assert len(prods) == chain.n_params
+    for g in range((len(prods) + 31) // 32):
+        chunk = prods[32 * g:32 * g + 32] + ["0.0"] * (32 - len(prods[32 * g:32 * g + 32]))
+        L.append("    { double pp[32] = {" + ", ".join(chunk) + "};")
+        L.append(f"      gw[{g}] += hb_transpose_reduce32(pp, lane); }}")
+    L.append("}")
+    return "\n".join(L)
+
+
+def _emit_adjoint(b: "_Builder", sim: int, statements, param_slots, nets, nn_layout, raw_states, state_floor, input_names,
+                  state_names, htype_sets) -> AdjointProgram:
+    """Body of templates/adjoint.cu for one time step, walked backwards in time by the kernel:
+
+        forward   recompute every value of the step from the PRE-update states hb_u[] (read from the stored trajectory),
+                  the forcing hb_x[] and the parameters (parameter-only values hoisted to the prologue as in the forward body);
+        seed      adjoint of the simulated value += hb_seed (d loss / d sim_t), adjoint of the post-update states = hb_lam[]
+                  (what the later steps passed back);
+        backward  the vector-Jacobian product of every value in reverse order: adjoints of the pre-update states -> hb_lam[]
+                  for step t-1, of the parameters -> hb_gp[], of parameter-only values -> persistent accumulators swept once
+                  in the epilogue, of neural-flux inputs / weights through hb_mlp_bwd_k.
+    Selects (min / max / the state floor) pass the adjoint to the branch the forward pass took — the same convention as the
+    forward-mode duals in hb_math.cuh."""
+    updates = {p[0]: p for k, p in statements if k == "update"}       # state index -> (si, pre leaf, du val)
+    vals = b.vals
+    live = set()
+    stack = [sim]
+    while stack:
+        j = stack.pop()
+        if j in live:
+            continue
+        live.add(j)
+        v = vals[j]
+        stack.extend(v.args)
+        if v.op == "state" and v.payload[1] == 1:
+            stack.append(updates[v.payload[0]][2])
+    for si in range(len(state_names)):                               # every state is stepped, whether the objective sees it or not
+        for j in (b.leaf_state(si, 0), b.leaf_state(si, 1), updates[si][2]) if si in updates else ():
+            stack.append(j)
+    while stack:
+        j = stack.pop()
+        if j in live:
+            continue
+        live.add(j)
+        stack.extend(vals[j].args)
+        if vals[j].op == "state" and vals[j].payload[1] == 1:
+            stack.append(updates[vals[j].payload[0]][2])
+    vals = b.vals                                                     # leaf_state above may have appended leaves
+    pclass = lambda i: vals[i].mask == 0 and vals[i].op not in ("const", "param")
+    # values that depend on something differentiable (a parameter, a state, a neural flux): forcing-only subexpressions
+    # (ExpHydro's whole PET chain) carry no adjoint
+    diff = set()
+    for v in vals:
+        if v.op in ("param", "state", "nn") or any(k in diff for k in v.args):
+            diff.add(v.id)
+
+    def ref(i: int) -> str:
+        v = vals[i]
+        if v.op == "const": return _c_double(v.payload)
+        if v.op == "in": return f"hb_x[{v.payload}]"
+        if v.op == "param": return f"hb_p[{v.payload}]"
+        if v.op == "state": return f"hb_u[{v.payload[0]}]" if v.payload[1] == 0 else f"hb_un{v.payload[0]}"
+        return f"h{i}" if v.mask == 0 else f"v{i}"
+
+    def adj(i: int) -> Optional[str]:
+        v = vals[i]
+        if v.op in ("const", "in") or i not in diff: return None
+        if v.op == "param": return f"hb_gp[{v.payload}]"
+        if v.op == "state": return f"as{v.payload[0]}" if v.payload[1] == 0 else f"an{v.payload[0]}"
+        return f"ah{i}" if v.mask == 0 else f"a{i}"
+
+    def vjp(v: Val, g: str) -> List[str]:
+        """statements adding the contributions of `g` = adjoint of v to the adjoints of its arguments"""
+        a = [ref(k) for k in v.args]
+        t = [adj(k) for k in v.args]
+        me = ref(v.id)
+        out: List[str] = []
+
+        def add(k, expr):
+            if t[k] is not None:
+                out.append(f"{t[k]} += {expr};")
+        op = v.op
+        if op == "add": add(0, g); add(1, g)
+        elif op == "sub": add(0, g); add(1, f"-{g}")
+        elif op == "mul": add(0, f"{g} * {a[1]}"); add(1, f"{g} * {a[0]}")
+        elif op == "div": add(0, f"{g} / {a[1]}"); add(1, f"-{g} * {me} / {a[1]}")
+        elif op == "rcp": add(0, f"-{g} * {me} * {me}")
+        elif op == "neg": add(0, f"-{g}")
+        elif op == "exp": add(0, f"{g} * {me}")
+        elif op == "log": add(0, f"{g} / {a[0]}")
+        elif op == "sqrt": add(0, f"{g} * 0.5 / {me}")
+        elif op == "abs": add(0, f"({a[0]} < 0.0 ? -{g} : {g})")
+        elif op == "tanh": add(0, f"{g} * fma(-{me}, {me}, 1.0)")
+        elif op == "step": add(0, f"{g} * 10.0 * {me} * (1.0 - {me})")
+        elif op == "min":
+            add(0, f"({a[0]} < {a[1]} ? {g} : 0.0)"); add(1, f"({a[0]} < {a[1]} ? 0.0 : {g})")
+        elif op == "max":
+            add(0, f"({a[0]} > {a[1]} ? {g} : 0.0)"); add(1, f"({a[0]} > {a[1]} ? 0.0 : {g})")
+        elif op == "pow":
+            add(0, f"{g} * {a[1]} * hb_pow({a[0]}, {a[1]} - 1.0)")
+            add(1, f"({a[0]} > 0.0 ? {g} * {me} * log({a[0]}) : 0.0)")
+        else:
+            raise LoweringError(f"no adjoint rule for {op}")
+        return out
+
+    pro: List[str] = []
+    step: List[str] = []
+    epi: List[str] = []
+    # ---- prologue: parameter-only values and their persistent adjoints ----
+    for v in vals:
+        if v.id in live and pclass(v.id):
+            if v.op == "nn":
+                raise LoweringError("a neural flux whose inputs are parameters only is not covered by the adjoint run")
+            pro.append(f"const double h{v.id} = {_expr_with(v, [ref(k) for k in v.args], True)};")
+            if v.id in diff:
+                pro.append(f"double ah{v.id} = 0.0;")
+    # ---- step, forward ----
+    nn_groups: Dict[Tuple[int, Tuple[int, ...]], List[int]] = {}
+    for v in vals:
+        i = v.id
+        if v.op == "state" and v.payload[1] == 1 and i in live:
+            si = v.payload[0]
+            step.append(f"const double hb_raw{si} = hb_u[{si}] + {ref(updates[si][2])};")
+            if si in raw_states:
+                step.append(f"const double hb_un{si} = hb_raw{si};")
+            else:
+                floor = _c_double(state_floor[si]) if si in state_floor else "hb_minv"
+                step.append(f"const double hb_un{si} = hb_max({floor}, hb_raw{si});")
+            continue
+        if i not in live or v.mask == 0 or v.op in ("const", "in", "param", "state"):
+            continue
+        if v.op == "nn":
+            ni, ins, j = v.payload
+            key = (ni, ins)
+            if key not in nn_groups:
+                nn_groups[key] = [None] * nets[ni].n_out
+                arr = f"nnf{ni}_" + "_".join(str(k) for k in ins)
+                step.append(f"double {arr}[{nets[ni].n_out}]; hb_mlp_{ni}(sNN, {', '.join(ref(k) for k in ins)}, {arr});")
+            nn_groups[key][j] = i
+            arr = f"nnf{ni}_" + "_".join(str(k) for k in ins)
+            step.append(f"const double v{i} = {arr}[{j}];")
+        else:
+            step.append(f"const double v{i} = {_expr_with(v, [ref(k) for k in v.args], True)};")
+    step.append(f"hb_sim = {ref(sim)};")
+    step.append("HB_SEED_STMT")                                       # template macro: hb_seed = d loss / d sim_t, loss accumulation
+    # ---- step, adjoint declarations and seeds ----
+    for v in vals:
+        if v.id in live and v.id in diff and v.mask != 0 and v.op not in ("const", "in", "param", "state"):
+            step.append(f"double a{v.id} = 0.0;")
+    for si in range(len(state_names)):
+        step.append(f"double as{si} = 0.0, an{si} = hb_lam[{si}];")
+    t_sim = adj(sim)
+    if t_sim is not None:
+        step.append(f"{t_sim} += hb_seed;")
+    # ---- step, backward ----
+    done_groups = set()
+    for v in reversed(vals):
+        i = v.id
+        if i not in live or v.op in ("const", "in", "param"):
+            continue
+        if v.op == "state":
+            si, ver = v.payload
+            if ver == 1:
+                du_t = adj(updates[si][2])
+                body = f"as{si} += an{si};" + (f" {du_t} += an{si};" if du_t is not None else "")
+                if si in raw_states:
+                    step.append(body)
+                else:
+                    floor = _c_double(state_floor[si]) if si in state_floor else "hb_minv"
+                    step.append(f"if (!({floor} > hb_raw{si})) {{ {body} }}")
+            continue
+        if v.mask == 0 or i not in diff:
+            continue                                                   # parameter-only: swept once in the epilogue; forcing-only: no adjoint
+        if v.op == "nn":
+            ni, ins, j = v.payload
+            key = (ni, ins)
+            if key in done_groups:
+                continue
+            done_groups.add(key)
+            dys = [f"a{vid}" if vid is not None else "0.0" for vid in nn_groups[key]]
+            arr = f"nnb{ni}_" + "_".join(str(k) for k in ins)
+            step.append(f"double {arr}[{nets[ni].n_in}]; hb_mlp_bwd_{ni}(lane, {', '.join(ref(k) for k in ins)}, {', '.join(dys)}, {arr}, "
+                        f"hb_gw + HB_GOFF_{ni});")
+            for k, src in enumerate(ins):
+                t = adj(src)
+                if t is not None:
+                    step.append(f"{t} += {arr}[{k}];")
+            continue
+        step.extend(vjp(v, f"a{i}"))
+    for si in range(len(state_names)):
+        step.append(f"hb_lam[{si}] = as{si};")
+    # ---- epilogue: parameter-only values, once ----
+    for v in reversed(vals):
+        if v.id in live and pclass(v.id) and v.id in diff:
+            epi.extend(vjp(v, f"ah{v.id}"))
+    goffs, ng = [], 0
+    for _, _, n in nn_layout:
+        goffs.append(ng)
+        ng += (n + 31) // 32
+    helpers = [_mlp_helper(i, ch, off, True) + "\n" + _mlp_helper_bwd(i, ch, off) for i, (ch, (_, off, _)) in enumerate(zip(nets, nn_layout))]
+    # flat index of the weight lane l holds for accumulator group g (or -1): chains own disjoint group ranges
+    gw = "-1"
+    for (name, off, n), g0 in reversed(list(zip(nn_layout, goffs))):
+        g1 = g0 + (n + 31) // 32
+        gw = f"(((g) >= {g0} && (g) < {g1}) ? ((32 * ((g) - {g0}) + (l)) < {n} ? {off} + 32 * ((g) - {g0}) + (l) : -1) : {gw})"
+    defs = f"#define HB_NG {ng}\n" + "".join(f"#define HB_GOFF_{i} {g}\n" for i, g in enumerate(goffs)) + \
+           f"#define HB_GROUP_WEIGHT(g, l) {gw}\n"
+    body = "//@@HB:DEFINES\n" + defs + "//@@HB:HELPERS\n" + "\n".join(helpers) + "\n" + \
+           "//@@HB:PROLOGUE\n" + "\n".join("    " + x for x in pro) + "\n" + \
+           "//@@HB:STEP\n" + "\n".join("        " + x for x in step) + "\n" + \
+           "//@@HB:EPILOGUE\n" + "\n".join("    " + x for x in epi) + "\n"
+    return AdjointProgram(body=body, input_names=list(input_names), state_names=list(state_names), param_slots=list(param_slots),
+                          htype_sets=list(htype_sets), nn_layout=list(nn_layout), nn_words=sum(n for _, _, n in nn_layout),
+                          nn_group_offset=goffs, n_groups=ng)
 
 
 def _body_to_tangent(body: str) -> str:

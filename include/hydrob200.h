@@ -232,6 +232,44 @@ int hb_run_route_device(hb_model_t m, const hb_route_desc *desc, void *stream);
 int hb_route_step_device(hb_model_t m, const hb_route_desc *desc, int64_t t, const double *s_prev, double *s_next,
                          const double *q_cur, double *q_next, void *stream);
 
+/* ---- reverse-mode gradient: the adjoint of the stepper --------------------------------------------------------------
+ * What the reference computes with Zygote through its ImmutableSolver (/root/reference/README.md:161-187, src/solve.jl:62-79;
+ * hybrid training, docs/src/tutorials/neuralnetwork_embeding.md): d loss / d (parameters, initial states, neural-network
+ * weights) of   loss_n = scale[n] * sum_{t >= warm_up} (sim_n(t) - target(t))^2   for per-node models of buckets, fluxes and
+ * neural fluxes.  The host lowers the SAME step expressions to a reverse-mode body (PROLOGUE / STEP / EPILOGUE); the kernel
+ * walks the stored state trajectory backwards (templates/adjoint.cu).  All pointers DEVICE unless noted. */
+typedef struct {
+    int32_t struct_size;         /* sizeof(hb_adjoint_spec) */
+    int32_t n_inputs, n_states, n_params;
+    int32_t nn_words;            /* MLP parameters (all chains) */
+    int32_t block_threads;       /* 0 = 128 */
+} hb_adjoint_spec;
+typedef struct {
+    int32_t struct_size;         /* sizeof(hb_adjoint_desc) */
+    int32_t n_htype_sets;
+    int64_t n_nodes, n_steps;
+    const double *input;         /* [T][N][V] */
+    const double *trajectory;    /* [T][N][S]: post-update states of every step (forward run with rows = the states) */
+    const double *params;
+    int64_t n_param_values;
+    const int32_t *param_offset; /* HOST [n_params] */
+    const int32_t *param_mode;   /* HOST [n_params] */
+    const int32_t *htypes;
+    const double *initstates;    /* [S][N] or NULL */
+    const double *nn_params;     /* [nn_words] */
+    const double *target;        /* [T] or [T][N] */
+    int32_t target_per_node, warm_up;
+    double min_value;
+    const double *scale;         /* [N]: 1 (SSE), 1/count (MSE), 1/sum (obs - mean obs)^2 (NSE) */
+    double *grad_params;         /* [n_params][N]: d loss_n / d (parameter slot j of node n) */
+    double *grad_init;           /* [S][N] */
+    double *grad_nn;             /* [nn_words]: summed over all nodes (zeroed by the call) */
+    double *loss;                /* [N] */
+    float *elapsed_ms;           /* optional HOST pointer */
+} hb_adjoint_desc;
+int hb_compile_adjoint(const hb_adjoint_spec *spec, const char *body, hb_model_t *out);
+int hb_run_adjoint_device(hb_model_t m, const hb_adjoint_desc *desc, void *stream);
+
 /* ---- fused dense-grid model: per-cell buckets + D8 HydroRoute in one pass ----------------------------
  * Replaces, for `[buckets..., HydroRoute]` models whose node list is the complete row-major grid, the two-pass
  * generic path above (/root/reference/src/model.jl:273-309 sequencing + src/route.jl:336-404).  Two kernel

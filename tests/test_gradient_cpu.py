@@ -143,3 +143,25 @@ def test_tangent_body_differentiates_with_respect_to_initial_states():
     dn["soilwater"] -= h
     sse = lambda st: ((ho.run_model(model, inp, p, None, st)[-1] - target) ** 2).sum(axis=1)
     np.testing.assert_allclose(g["soilwater"], (sse(up) - sse(dn)) / (2 * h), rtol=1e-5, atol=1e-8)   # exact zeros: a soil store above Smax spills its excess in one step
+
+
+def test_adjoint_bodies_lower_and_compile_without_a_device():
+    """`lower_stepper(adjoint=True)` + NVRTC for sm_100a (no GPU needed to compile): bucket models with and without neural
+    fluxes; unit hydrographs and gradient-unfriendly settings are refused with the reference-style error text."""
+    import numpy as np
+    import hydromodels_jl_b200 as hm
+    from hydromodels_jl_b200.engine import CompiledAdjoint
+    from hydromodels_jl_b200.lowering import LoweringError, lower_stepper
+    for name in ("exphydro", "hbv", "m50"):
+        model = getattr(hm.models, name)(htypes=np.arange(1, 5))
+        prog = lower_stepper(model, objective=True, adjoint=True)
+        assert prog.state_names == model.state_names and "HB_SEED_STMT" in prog.body and "hb_lam[" in prog.body
+        assert prog.n_groups == sum((n + 31) // 32 for _, _, n in prog.nn_layout)
+        ck = CompiledAdjoint(prog)
+        assert "hb_adjoint" in ck.source() and len(ck.cubin()) > 1000
+    m50 = lower_stepper(hm.models.m50(htypes=np.arange(1, 5)), objective=True, adjoint=True)
+    assert m50.nn_words == 690 and "hb_mlp_bwd_0" in m50.body and "hb_transpose_reduce32" in m50.body
+    with pytest.raises(LoweringError, match="unit hydrographs"):
+        lower_stepper(hm.models.gr4j(htypes=np.arange(1, 5)), objective=True, adjoint=True, uh_kmax=[3, 6])
+    with pytest.raises(LoweringError, match="objective row"):
+        lower_stepper(hm.models.exphydro(htypes=np.arange(1, 5)), objective=False, adjoint=True)
