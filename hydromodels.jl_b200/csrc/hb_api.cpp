@@ -1046,14 +1046,17 @@ int hb_route_step_device(hb_model_t m, const hb_route_desc *d, int64_t t, const 
 int hb_compile_adjoint(const hb_adjoint_spec *spec, const char *body, hb_model_t *out) {
     if (!spec || !body || !out) return fail(HB_ERR_INVALID, "NULL argument");
     if (spec->struct_size != (int32_t)sizeof(hb_adjoint_spec)) return fail(HB_ERR_INVALID, "hb_adjoint_spec.struct_size mismatch");
-    if (spec->n_inputs < 0 || spec->n_states < 0 || spec->n_params < 0 || spec->n_params > HB_MAX_PARAMS || spec->nn_words < 0)
+    if (spec->n_inputs < 0 || spec->n_states < 0 || spec->n_params < 0 || spec->n_params > HB_MAX_PARAMS || spec->nn_words < 0 ||
+        spec->acc_doubles_per_warp < 0)
         return fail(HB_ERR_INVALID, "hb_adjoint_spec out of range");
     hb_model_s *m = new hb_model_s();
     m->kind = 3;
     m->aspec = *spec;
     m->block = spec->block_threads > 0 ? spec->block_threads : 128;
     if (m->block % 32 || m->block > 1024) { delete m; return fail(HB_ERR_INVALID, "block_threads must be a multiple of 32 <= 1024"); }
-    m->dyn_smem = 0;
+    // per warp: transposition scratch (2 x 32 x 20 doubles) + the accumulator fragments of every dense layer
+    m->dyn_smem = (m->block / 32) * (2 * 32 * 20 + spec->acc_doubles_per_warp) * 8;
+    if (m->dyn_smem + 4096 > 227 * 1024) { delete m; return fail(HB_ERR_INVALID, "adjoint kernel needs too much shared memory; use a smaller block"); }
     char defs[512];
     snprintf(defs, sizeof defs, "//@@HB:DEFINES\n#define HB_V %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_NN_WORDS %d\n#define HB_BLOCK %d\n"
              "#define HB_UHW_TOTAL 0\n#define HB_UHH_TOTAL 0\n",
@@ -1113,7 +1116,7 @@ int hb_run_adjoint_device(hb_model_t m, const hb_adjoint_desc *d, void *stream) 
         HB_DRV(g_drv.MemcpyDtoDAsync(m->nn_const, (CUdeviceptr)(uintptr_t)d->nn_params, (size_t)s.nn_words * 8, (CUstream)st));
     }
     const unsigned grid = (unsigned)((N + m->block - 1) / m->block);
-    HB_DRV(g_drv.LaunchKernel(m->func, grid, 1, 1, m->block, 1, 1, 0, (CUstream)st, params, nullptr));
+    HB_DRV(g_drv.LaunchKernel(m->func, grid, 1, 1, m->block, 1, 1, m->dyn_smem, (CUstream)st, params, nullptr));
     if (d->elapsed_ms) {
         HB_CUDA(cudaEventRecord(m->ev1, st));
         HB_CUDA(cudaEventSynchronize(m->ev1));

@@ -97,7 +97,7 @@ class GridDesc(C.Structure):
 
 class AdjointSpec(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("n_inputs", C.c_int32), ("n_states", C.c_int32), ("n_params", C.c_int32),
-                ("nn_words", C.c_int32), ("block_threads", C.c_int32)]
+                ("nn_words", C.c_int32), ("block_threads", C.c_int32), ("acc_doubles_per_warp", C.c_int32)]
 
 
 class AdjointDesc(C.Structure):
@@ -281,7 +281,7 @@ class CompiledAdjoint:
     def __init__(self, program, block_threads: int = 0):
         self.program = program
         spec = AdjointSpec(C.sizeof(AdjointSpec), len(program.input_names), len(program.state_names), len(program.param_slots),
-                           program.nn_words, block_threads)
+                           program.nn_words, block_threads, program.n_groups)
         self.spec = spec
         h = C.c_void_p()
         check(lib().hb_compile_adjoint(C.byref(spec), program.body.encode(), C.byref(h)))

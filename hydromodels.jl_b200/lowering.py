@@ -708,8 +708,8 @@ class AdjointProgram:
     htype_sets: List[np.ndarray]
     nn_layout: List[Tuple[str, int, int]]
     nn_words: int
-    nn_group_offset: List[int]      # first 32-weight accumulator group of every chain
-    n_groups: int
+    nn_group_offset: List[int]      # offset (doubles) of every chain's accumulator fragments in the per-warp shared block
+    n_groups: int                   # accumulator doubles per warp (all chains)
     uh: List = field(default_factory=list)            # (no unit hydrographs in an adjoint run: what B200Model.prepare expects)
     uh_kmax: List[int] = field(default_factory=list)
     uh_htype_set: List = field(default_factory=list)
@@ -727,13 +727,13 @@ def _act_derivative(act: str, z: str, a: str) -> str:
 
 def _mlp_helper_bwd(idx: int, chain, offset: int) -> str:
     """Forward recomputation + backward pass of one chain for ONE node, and the accumulation of the weight gradient over the
-    32 nodes of the warp: the products `delta_o * a_i` of 32 consecutive flat parameters at a time go through a butterfly
-    (hb_transpose_reduce32) that leaves lane l with the warp total of parameter 32 g + l, added to this lane's accumulator
-    `gw[g]`.  Flat parameter order = the chain's own (`weight[out, in]` column-major, then bias)."""
+    32 nodes of the warp: per layer `dW += delta (x) input`, summed over the nodes, as FP64 tensor-core MMAs with the nodes as
+    the K dimension (hb_outer_acc; accumulator fragments in shared memory at `gw`, transposition scratch `scr`)."""
     acts = _ACT_C
     args = ", ".join(f"const double x{i}" for i in range(chain.n_in))
     dys = ", ".join(f"const double dy{o}" for o in range(chain.n_out))
-    L = [f"__device__ __forceinline__ void hb_mlp_bwd_{idx}(const int lane, {args}, {dys}, double* __restrict__ dx, double* __restrict__ gw) {{"]
+    L = [f"__device__ __forceinline__ void hb_mlp_bwd_{idx}(const int lane, {args}, {dys}, double* __restrict__ dx, double* __restrict__ scr, "
+         f"double* __restrict__ gw) {{"]
     prev = [f"x{i}" for i in range(chain.n_in)]
     acts_in = [prev]
     zs, off, offs = [], offset, []
@@ -771,21 +771,31 @@ def _mlp_helper_bwd(idx: int, chain, offset: int) -> str:
         g_out = g_in
     for i in range(chain.n_in):
         L.append(f"    dx[{i}] = {g_out[i]};")
-    # weight gradient: flat local index -> product expression
-    prods: List[str] = []
+    # weight gradient: per layer one warp-wide outer-product accumulation on the FP64 tensor pipe (templates/adjoint.cu:
+    # hb_outer_acc), delta and input vectors zero-padded to multiples of 8
+    acc_off = 0
     for li, l in enumerate(chain.layers):
-        for i in range(l.n_in):
-            for o in range(l.n_out):
-                prods.append(f"{deltas[li][o]} * {acts_in[li][i]}")
-        for o in range(l.n_out):
-            prods.append(deltas[li][o])
-    assert len(prods) == chain.n_params
-    for g in range((len(prods) + 31) // 32):
-        chunk = prods[32 * g:32 * g + 32] + ["0.0"] * (32 - len(prods[32 * g:32 * g + 32]))
-        L.append("    { double pp[32] = {" + ", ".join(chunk) + "};")
-        L.append(f"      gw[{g}] += hb_transpose_reduce32(pp, lane); }}")
+        NO, NI = -(-l.n_out // 8) * 8, -(-l.n_in // 8) * 8
+        if NO > 16 or NI > 16:
+            raise LoweringError("the adjoint run handles dense layers up to 16 x 16 (scratch pitch)")
+        dd = deltas[li] + ["0.0"] * (NO - l.n_out)
+        aa = acts_in[li] + ["0.0"] * (NI - l.n_in)
+        L.append(f"    {{ const double dd[{NO}] = {{{', '.join(dd)}}}; const double aa[{NI}] = {{{', '.join(aa)}}};")
+        L.append(f"      hb_outer_acc<{NO}, {NI}>(scr, gw + {acc_off}, lane, dd, aa); }}")
+        acc_off += (NO // 8) * (NI // 8 + 1) * 64
     L.append("}")
     return "\n".join(L)
+
+
+def _adjoint_acc_layout(chain, offset: int):
+    """[(acc offset in doubles, NO, NI, flat parameter offset, n_out, n_in)] per layer, and the chain's accumulator doubles."""
+    out, acc_off, off = [], 0, offset
+    for l in chain.layers:
+        NO, NI = -(-l.n_out // 8) * 8, -(-l.n_in // 8) * 8
+        out.append((acc_off, NO, NI, off, l.n_out, l.n_in))
+        acc_off += (NO // 8) * (NI // 8 + 1) * 64
+        off += l.n_params
+    return out, acc_off
 
 
 def _emit_adjoint(b: "_Builder", sim: int, statements, param_slots, nets, nn_layout, raw_states, state_floor, input_names,
@@ -960,7 +970,7 @@ def _emit_adjoint(b: "_Builder", sim: int, statements, param_slots, nets, nn_lay
             dys = [f"a{vid}" if vid is not None else "0.0" for vid in nn_groups[key]]
             arr = f"nnb{ni}_" + "_".join(str(k) for k in ins)
             step.append(f"double {arr}[{nets[ni].n_in}]; hb_mlp_bwd_{ni}(lane, {', '.join(ref(k) for k in ins)}, {', '.join(dys)}, {arr}, "
-                        f"hb_gw + HB_GOFF_{ni});")
+                        f"hb_scr, hb_gw + HB_GOFF_{ni});")
             for k, src in enumerate(ins):
                 t = adj(src)
                 if t is not None:
@@ -973,22 +983,21 @@ def _emit_adjoint(b: "_Builder", sim: int, statements, param_slots, nets, nn_lay
     for v in reversed(vals):
         if v.id in live and pclass(v.id) and v.id in diff:
             epi.extend(vjp(v, f"ah{v.id}"))
-    goffs, ng = [], 0
-    for _, _, n in nn_layout:
-        goffs.append(ng)
-        ng += (n + 31) // 32
+    goffs, acc_total, flush = [], 0, []
+    for ch, (_, off, _) in zip(nets, nn_layout):
+        layers, n_acc = _adjoint_acc_layout(ch, off)
+        goffs.append(acc_total)
+        for a_off, NO, NI, p_off, n_out, n_in in layers:
+            flush.append(f"hb_outer_flush<{NO}, {NI}>(hb_gw + {acc_total + a_off}, lane, a.grad_nn + {p_off}, {n_out}, {n_in});")
+        acc_total += n_acc
     helpers = [_mlp_helper(i, ch, off, True) + "\n" + _mlp_helper_bwd(i, ch, off) for i, (ch, (_, off, _)) in enumerate(zip(nets, nn_layout))]
-    # flat index of the weight lane l holds for accumulator group g (or -1): chains own disjoint group ranges
-    gw = "-1"
-    for (name, off, n), g0 in reversed(list(zip(nn_layout, goffs))):
-        g1 = g0 + (n + 31) // 32
-        gw = f"(((g) >= {g0} && (g) < {g1}) ? ((32 * ((g) - {g0}) + (l)) < {n} ? {off} + 32 * ((g) - {g0}) + (l) : -1) : {gw})"
-    defs = f"#define HB_NG {ng}\n" + "".join(f"#define HB_GOFF_{i} {g}\n" for i, g in enumerate(goffs)) + \
-           f"#define HB_GROUP_WEIGHT(g, l) {gw}\n"
+    defs = f"#define HB_ACC_DOUBLES {acc_total}\n" + "".join(f"#define HB_GOFF_{i} {g}\n" for i, g in enumerate(goffs))
     body = "//@@HB:DEFINES\n" + defs + "//@@HB:HELPERS\n" + "\n".join(helpers) + "\n" + \
            "//@@HB:PROLOGUE\n" + "\n".join("    " + x for x in pro) + "\n" + \
            "//@@HB:STEP\n" + "\n".join("        " + x for x in step) + "\n" + \
-           "//@@HB:EPILOGUE\n" + "\n".join("    " + x for x in epi) + "\n"
+           "//@@HB:EPILOGUE\n" + "\n".join("    " + x for x in epi) + "\n" + \
+           "//@@HB:FLUSH\n" + "\n".join("    " + x for x in flush) + "\n"
+    ng = acc_total
     return AdjointProgram(body=body, input_names=list(input_names), state_names=list(state_names), param_slots=list(param_slots),
                           htype_sets=list(htype_sets), nn_layout=list(nn_layout), nn_words=sum(n for _, _, n in nn_layout),
                           nn_group_offset=goffs, n_groups=ng)

@@ -243,6 +243,7 @@ typedef struct {
     int32_t n_inputs, n_states, n_params;
     int32_t nn_words;            /* MLP parameters (all chains) */
     int32_t block_threads;       /* 0 = 128 */
+    int32_t acc_doubles_per_warp;/* shared-memory accumulator fragments of the dense layers' weight gradients (from the lowering) */
 } hb_adjoint_spec;
 typedef struct {
     int32_t struct_size;         /* sizeof(hb_adjoint_desc) */
