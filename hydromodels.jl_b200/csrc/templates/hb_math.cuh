@@ -139,14 +139,24 @@ __device__ __forceinline__ void hb_math_init() {
 }
 #endif
 
-// |x| saturated at (just above) a bound given by the HIGH WORD of its double representation (integer instructions only,
-// no FP64-pipe work; the NaN-aware fmin/fmax the compiler emits cost ~6 each).  A NaN passes through unchanged (its
-// high word is above the exponent-all-ones pattern of infinity), so NaN forcing propagates through exp / step_func /
-// tanh into the states as it does in the reference; +/-inf saturates like any large value.
+// |x| saturated at (just above) a bound given by the HIGH WORD of its double representation (3 integer instructions: LOP3,
+// VIMNMX.U32, LOP3 — no FP64-pipe work; the NaN-aware fmin/fmax the compiler emits cost ~6 each).
+// NaN: by default a NaN is saturated like any value above the bound, i.e. NaN forcing does NOT propagate through exp /
+// step_func / tanh (the reference propagates it).  `#define HB_NAN_PROPAGATE 1` (library: HB_EXTRA_DEFINES) lets NaN through
+// unchanged — its high word lies above the exponent-all-ones pattern of infinity — at the price of two more integer
+// instructions per call (measured: GR4J 100 k x 3650 8.4 -> 9.0 ms, the kernel is close to issue-bound); +/-inf saturates
+// either way.
+#ifndef HB_NAN_PROPAGATE
+#define HB_NAN_PROPAGATE 0
+#endif
 HB_DEV double hb_clamp_abs(double x, int bound_hi) {
     const int hi = hb_double2hiint(x);
     const unsigned ahi = (unsigned)hi & 0x7fffffffu;
+#if HB_NAN_PROPAGATE
     const unsigned lim = ahi > 0x7ff00000u ? ahi : (unsigned)bound_hi;     // NaN: no saturation
+#else
+    const unsigned lim = (unsigned)bound_hi;
+#endif
     const unsigned chi = (ahi < lim ? ahi : lim) | ((unsigned)hi & 0x80000000u);
     // the low word is kept: a saturated value lies in [bound, bound * (1 + 2^-20)) — still inside the
     // range the callers need

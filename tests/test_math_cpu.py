@@ -12,11 +12,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HDR = os.path.join(ROOT, "hydromodels.jl_b200", "csrc", "templates", "hb_math.cuh")
 
 
-@pytest.fixture(scope="module")
-def hbm():
+def _build(extra_define=""):
     d = tempfile.mkdtemp(prefix="hb_math_")
     src = os.path.join(d, "m.cpp")
     open(src, "w").write(f'''#define HB_HOST_TEST 1
+{extra_define}
 #include "{HDR}"
 extern "C" void apply(int which, long n, const double* x, double* y) {{
     for (long i = 0; i < n; ++i) {{
@@ -51,6 +51,16 @@ extern "C" void apply2(long n, const double* x, const double* y, double* z) {{
         return z
     f.pow = pw
     return f
+
+
+@pytest.fixture(scope="module")
+def hbm():
+    return _build()
+
+
+@pytest.fixture(scope="module")
+def hbm_nan():
+    return _build("#define HB_NAN_PROPAGATE 1")
 
 
 def test_exp_full_range(hbm):
@@ -110,9 +120,10 @@ def test_log_and_pow(hbm):
     assert np.isnan(hbm.pow([-1.0], [2.5])[0]) and np.isinf(hbm.pow([0.0], [-1.0])[0])
 
 
-def test_nan_propagates_and_infinities_saturate(hbm):
-    """NaN forcing must not come out of exp / step_func / tanh as a plausible finite number (Julia propagates it);
-    +/-inf keep their limits."""
+def test_nan_propagates_and_infinities_saturate(hbm_nan):
+    """With `HB_NAN_PROPAGATE 1` NaN forcing does not come out of exp / step_func / tanh as a plausible finite number (Julia
+    propagates it); +/-inf keep their limits either way."""
+    hbm = hbm_nan
     nan, inf = float("nan"), float("inf")
     for which in (0, 1, 2):
         assert np.isnan(hbm(which, [nan, -nan])).all()
