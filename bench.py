@@ -222,12 +222,16 @@ def e2e_leg(torch, dist, hm, eng, p, init, d_in, T, N, v_of, rows_of, world, ran
     probe = pcie_probe(torch, dist, world, barrier)
     # the pipeline moves H2D and D2H at the same time: its floor is the slower of the two streams at the box's concurrent rates
     floor = max(world * in_bytes / (probe["sum_GBps"]["h2d_while_d2h"] * 1e9), world * out_bytes / (probe["sum_GBps"]["d2h_while_h2d"] * 1e9))
+    floor_min = max(in_bytes / (probe["min_rank_GBps"]["h2d_while_d2h"] * 1e9), out_bytes / (probe["min_rank_GBps"]["d2h_while_h2d"] * 1e9))
     e2e = {"value": world * N * T / s_pinned, "unit": unit, "timesteps": T, "h2d_bytes_per_step": in_bytes + small,
            "d2h_bytes_per_step": out_bytes, "steps": args.e2e_steps, "s_per_step": s_pinned,
            "api": "B200Model.__call__(input, params, config; initstates) with pinned host arrays (hb_malloc_host)",
            "host_windows": n_win, "host_memory": {"MemAvailable_GiB": None if avail is None else avail / 2**30, "needed_GiB": need / 2**30},
            "aggregate_GBps": {"h2d": world * in_bytes / s_pinned / 1e9, "d2h": world * out_bytes / s_pinned / 1e9},
            "pcie_probe": probe, "pcie_floor_s_per_step": floor, "pcie_frac": floor / s_pinned,
+           # the timed region ends when the SLOWEST rank is done, and the box does not share its PCIe bandwidth evenly between
+           # the ranks: the same floor from the slowest rank's measured rates
+           "pcie_floor_slowest_rank_s_per_step": floor_min, "pcie_frac_slowest_rank": floor_min / s_pinned,
            "_launches": (args.e2e_steps + 1) * min(T, -(-out_bytes // (256 << 20)))}
     if not args.no_pageable:
         # same call, ordinary (pageable) numpy arrays: the library stages them through its pinned ring with host threads
