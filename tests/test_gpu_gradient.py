@@ -114,11 +114,13 @@ def test_single_basin_gradient_and_errors():
     for nm, v in g.items():
         assert np.ndim(v) == 0
         _close(np.array([v]), ref_g[nm])
+    # forward-mode tangents do not cover neural components (their hundreds of weights are what the reverse-mode adjoint is
+    # for: `gradient()` picks it by default for such models, tests/test_gpu_adjoint.py)
     with pytest.raises(hm.lowering.LoweringError, match="neural"):
         m50 = hm.models.m50(htypes=[1, 2])
         et, q = hm.models.m50_chains()
         hm.B200Model(m50).gradient(sy.forcing("m50", 0, 2, 50), {"params": sy.parameters("m50", 0, 2),
-                                   "nns": {"etnn": et.init_params(1), "qnn": q.init_params(2)}}, np.ones(50), wrt=["f"])
+                                   "nns": {"etnn": et.init_params(1), "qnn": q.init_params(2)}}, np.ones(50), wrt=["Tmin"], mode="forward")
 
 
 def test_gradient_with_respect_to_initial_states():
