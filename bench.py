@@ -736,6 +736,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["raster_ingest_4096", "calibrate_exphydro", "gradient_exphydro", "gradient_m50_adjoint", "irf_route", "irf_route_ragged", "exphydro_single_basin_365d"])
+    ap.add_argument("--basins", type=int, default=0, help="tuning experiments: override the workload's basin count")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"], help="opt-in Float32 mode (per-node workloads; device-resident value only)")
@@ -797,6 +798,8 @@ def main():
     if args.workload == "exphydro_single_basin_365d":
         return bench_single_basin(args) if rank == 0 else 0
     model_name, N, T = WORKLOADS[args.workload]
+    if args.basins:          # tuning experiments only (the config key `basins_per_gpu` reports what ran)
+        N = int(args.basins)
     total_grid = "_total_" in args.workload
     if total_grid:
         N //= int(os.environ.get("WORLD_SIZE", "1"))          # cells owned per rank

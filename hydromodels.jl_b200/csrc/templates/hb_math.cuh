@@ -231,23 +231,38 @@ HB_DEV double hb_step(double x) {
     const double tk = hb_hiloint2double(hb_double2hiint(tj) + (k << 20), hb_double2loint(tj));   // 2^k T_j, a normal double for |z| <= 700
     return hb_rcp(fma(tk, q, 1.0));                         // 1 + exp(z) in one fma
 }
-// tanh(x) = 1 - 2/(1+exp(2x)), same saturated logistic (absolute error < 4.5e-16).  The factor 2 is folded into the
-// argument reduction (t = round(x * 512/ln2), r = x - t ln2/512, exp(2x) = 2^(t/256) e^(2r) with the polynomial in r
-// carrying the powers of two) and the table product is fused with the `1 +`, so a tanh costs 13 FP64 operations: M50 evaluates 64 of them per basin-step and is bound
-// by the FP64 pipe.
+// tanh(x) = 1 - 2/(1+exp(2x)), same saturated logistic.  The factor 2 is folded into the argument reduction
+// (t = round(x * 512/ln2), r = x - t ln2/512, exp(2x) = 2^(t/256) e^(2r) with the polynomial in r carrying the powers of two)
+// and the table product is fused with the `1 +`.  M50 evaluates 128 of them per basin-step and is bound by the FP64 pipe, so
+// the default form spends as few FP64-pipe operations as the 1e-10 parity bar allows — TEN:
+//   * r comes out of ONE fma with the full double ln2/512 (the product is exact inside the fma; what is lost against the
+//     two-constant Cody-Waite form is t * 2^-63 <= 2e-15 wherever tanh has not saturated);
+//   * e^(2r) = (1 + 2r) + [2r^2 + 4/3 r^3 + 2/3 r^4], and the bracket (<= 9.2e-7) is evaluated in FLOAT on the FP32 pipe
+//     (two conversions on the XU pipe): its 2e-7 relative rounding is 2e-13 absolute in e^(2r), at most 1e-13 in tanh.
+// `#define HB_TANH_EXACT 1` (library: HB_EXTRA_DEFINES) selects the 13-operation all-FP64 form (< 4.5e-16 absolute).
 #define HB_HI_350 0x4075e000   // high word of 350.0
+#ifndef HB_TANH_EXACT
+#define HB_TANH_EXACT 0
+#endif
 HB_DEV double hb_tanh(double x) {
     const double MAGIC = 6755399441055744.0;
     const double xc = hb_clamp_abs(x, HB_HI_350);
     double t = fma(xc, 738.6598609351493, MAGIC);           // x * 512/ln2
     const int ti = hb_double2loint(t);
     t -= MAGIC;
+#if HB_TANH_EXACT
     double r = fma(t, -0.0013538030834752135, xc);           // ln2/512 high part (an eighth of the ln2/64 split: exact)
     r = fma(t, -3.5559296845784106e-12, r);                  // ln2/512 low part
     double q = fma(r, 6.66666666666666666667e-01, 1.33333333333333333333e+00);   // e^(2r) = sum (2r)^n / n!, |2r| <= ln2/512
     q = fma(q, r, 2.0);
     q = fma(q, r, 2.0);
     q = fma(q, r, 1.0);
+#else
+    const double r = fma(t, -0.0013538030870311431, xc);     // |r| <= ln2/1024
+    const float rf = (float)r;
+    const float tail = (rf * rf) * fmaf(rf, fmaf(rf, 0.66666669f, 1.33333337f), 2.0f);
+    const double q = fma(2.0, r, 1.0) + (double)tail;
+#endif
     // 1 + exp(2x) = 1 + (2^k T_j) q in ONE fma: 2^k goes onto the table entry by an integer add to its exponent field
     // (|2x| <= 700: the scaled entry stays a normal double)
     const double tj = hb_exp2t[ti & 255];
@@ -293,7 +308,10 @@ HB_DEV double hb_pow(double x, double y) {
 // handling differs from Julia's min/max (which propagate NaN) exactly as fmin/fmax would.
 HB_DEV double hb_min(double a, double b) { return a < b ? a : b; }
 HB_DEV double hb_max(double a, double b) { return a > b ? a : b; }
-HB_DEV double hb_leakyrelu(double x) { return hb_max(0.01 * x, x); }
+// NNlib.leakyrelu = max(0.01 x, x): the larger one is x exactly when x's sign bit is clear, so the choice is an integer test of
+// the high word (ISETP + 2 SEL) instead of an FP64 compare (DSETP holds the issue port for two cycles) — same bits for every
+// non-NaN x, -0.0 included (0.01 * -0.0 = -0.0).
+HB_DEV double hb_leakyrelu(double x) { const double m = 0.01 * x; return hb_double2hiint(x) < 0 ? m : x; }
 HB_DEV double hb_clamp(double x, double lo, double hi) { return hb_min(hb_max(x, lo), hi); }
 
 HB_DEV double hb_val(double x) { return x; }   // the value of a quantity (gradient runs overload it for hb_dual)

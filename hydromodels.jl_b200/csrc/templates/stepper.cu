@@ -163,6 +163,10 @@ __constant__ real hb_nn_const[HB_NN_WORDS];
 __device__ __forceinline__ void hb_dmma(double &d0, double &d1, const double a, const double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+// the first product of an accumulation reads its addend (the bias pair, shared by all M tiles) from other registers: no copies
+__device__ __forceinline__ void hb_dmma_c(double &d0, double &d1, const double a, const double b, const double c0, const double c1) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};" : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
 
 #if HB_NN_TC
 //@@HB:TC

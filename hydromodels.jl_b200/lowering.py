@@ -1235,7 +1235,7 @@ def _mlp_helper_mma(idx: int, chain, offset: int, fast: bool) -> str:
     o.append(f"        const double b = (j < {l0.n_in}) ? sW[{off} + j * {l0.n_out} + nt * 8 + q] : 0.0;")
     o.append(f"        const double c0 = sW[{bias} + nt * 8 + 2 * j], c1 = sW[{bias} + nt * 8 + 2 * j + 1];")
     o.append("#pragma unroll")
-    o.append("        for (int mt = 0; mt < HB_MT; ++mt) { h0[mt][nt][0] = c0; h0[mt][nt][1] = c1; hb_dmma(h0[mt][nt][0], h0[mt][nt][1], afr[mt], b); }")
+    o.append("        for (int mt = 0; mt < HB_MT; ++mt) hb_dmma_c(h0[mt][nt][0], h0[mt][nt][1], afr[mt], b, c0, c1);")
     o.append("    }")
     if l0.activation != "identity":
         o.append("#pragma unroll")
@@ -1252,12 +1252,13 @@ def _mlp_helper_mma(idx: int, chain, offset: int, fast: bool) -> str:
         o.append(f"    for (int nt = 0; nt < {ntl}; ++nt) {{")
         o.append(f"        const double c0 = sW[{bias} + nt * 8 + 2 * j], c1 = sW[{bias} + nt * 8 + 2 * j + 1];")
         o.append("#pragma unroll")
-        o.append(f"        for (int mt = 0; mt < HB_MT; ++mt) {{ {cur}[mt][nt][0] = c0; {cur}[mt][nt][1] = c1; }}")
-        o.append("#pragma unroll")
         o.append(f"        for (int c = 0; c < {l.n_in // 4}; ++c) {{")
         o.append(f"            const double b = sW[{off} + ((c >> 1) * 8 + 2 * j + (c & 1)) * {l.n_out} + nt * 8 + q];")
         o.append("#pragma unroll")
-        o.append(f"            for (int mt = 0; mt < HB_MT; ++mt) hb_dmma({cur}[mt][nt][0], {cur}[mt][nt][1], {prev}[mt][c >> 1][c & 1], b);")
+        o.append(f"            for (int mt = 0; mt < HB_MT; ++mt) {{")
+        o.append(f"                if (c == 0) hb_dmma_c({cur}[mt][nt][0], {cur}[mt][nt][1], {prev}[mt][0][0], b, c0, c1);")
+        o.append(f"                else hb_dmma({cur}[mt][nt][0], {cur}[mt][nt][1], {prev}[mt][c >> 1][c & 1], b);")
+        o.append("            }")
         o.append("        }")
         o.append("    }")
         if l.activation != "identity":

@@ -487,6 +487,34 @@ def test_wave_grid_kernel_matches_oracle_and_generic_path(R, Cc, T, tc):
     assert np.array_equal(eng(inp, p, initstates=init), wave)  # step counters / tickets are reset between runs
 
 
+def test_wave_grid_kernel_cells_with_up_to_eight_inflows():
+    """The wave kernel polls a cell's first four inflows through its slot list and any further ones one by one
+    (`HB_USLOTS`, templates/gridwave.cu): a field of 3 x 3 blocks that all drain into their centre cell (8 inflows, the
+    centres chained eastwards) must come out bit-identical to the generic path — same words, same summation order."""
+    R, Cc, T = 30, 66, 25
+    kdr, kdc, code = [0, 1, 1, 1, 0, -1, -1, -1], [1, 1, 0, -1, -1, -1, 0, 1], [1, 2, 4, 8, 16, 32, 64, 128]
+    flw = np.zeros((R, Cc), dtype=np.int64)
+    for r in range(R):
+        for c in range(Cc):
+            a, b = r % 3 - 1, c % 3 - 1
+            flw[r, c] = 1 if (a, b) == (0, 0) else code[[k for k in range(8) if (kdr[k], kdc[k]) == (-a, -b)][0]]
+    rr, cc = np.divmod(np.arange(R * Cc), Cc)
+    N = R * Cc
+    model = hm.models.exphydro_grid(flw, np.stack([rr + 1, cc + 1], axis=1))
+    rng = np.random.default_rng(8)
+    inp = sy.forcing("exphydro", 0, N, T)
+    p = {"params": dict(sy.parameters("exphydro", 0, N), area_coef=rng.uniform(0.5, 2.0, N), lag=rng.uniform(0.1, 3.0, N))}
+    init = dict(snowpack=np.zeros(N), soilwater=np.full(N, 1303.0), s_river=rng.uniform(0, 2, N))
+    eng = hm.B200Model(model)
+    eng.grid_steps_per_launch = 6
+    wave = eng(inp, p, initstates=init)
+    assert any(isinstance(k, tuple) and k[:2] == ("grid", "wave") for k in eng._cache)
+    assert_parity(wave, ho.run_model(model, inp, p, initstates=init))
+    eng2 = hm.B200Model(model)
+    eng2.grid_kernel = "generic"
+    assert np.array_equal(wave, eng2(inp, p, initstates=init))
+
+
 @pytest.mark.parametrize("n,H,dag", [(300, 32, True), (1200, 16, False), (64, 70, True)])
 def test_route_kernel_composition_on_the_device_is_bit_identical_to_the_reference_loops(n, H, dag):
     """`aggregate_route_kernel` (`/root/reference/src/route.jl:523-577`): host plan + level-synchronous device sweep against
