@@ -231,18 +231,20 @@ HB_DEV double hb_step(double x) {
     const double tk = hb_hiloint2double(hb_double2hiint(tj) + (k << 20), hb_double2loint(tj));   // 2^k T_j, a normal double for |z| <= 700
     return hb_rcp(fma(tk, q, 1.0));                         // 1 + exp(z) in one fma
 }
-// tanh(x) = 1 - 2/(1+exp(2x)), same saturated logistic.  The factor 2 is folded into the argument reduction
-// (t = round(x * 512/ln2), r = x - t ln2/512, exp(2x) = 2^(t/256) e^(2r) with the polynomial in r carrying the powers of two)
-// and the table product is fused with the `1 +`.  M50 evaluates 128 of them per basin-step and is bound by the FP64 pipe, so
-// the default form spends as few FP64-pipe operations as the 1e-10 parity bar allows — TEN:
-//   * r comes out of ONE fma with the full double ln2/512 (the product is exact inside the fma; what is lost against the
-//     two-constant Cody-Waite form is t * 2^-63 <= 2e-15 wherever tanh has not saturated);
-//   * e^(2r) = (1 + 2r) + [2r^2 + 4/3 r^3 + 2/3 r^4], and the bracket (<= 9.2e-7) is evaluated in FLOAT on the FP32 pipe
-//     (two conversions on the XU pipe): its 2e-7 relative rounding is 2e-13 absolute in e^(2r), at most 1e-13 in tanh.
-// `#define HB_TANH_EXACT 1` (library: HB_EXTRA_DEFINES) selects the 13-operation all-FP64 form (< 4.5e-16 absolute).
+// tanh(x) = 1 - 2/(1+exp(2x)), same saturated logistic (absolute error < 4.5e-16).  The factor 2 is folded into the argument
+// reduction (t = round(x * 512/ln2), r = x - t ln2/512, exp(2x) = 2^(t/256) e^(2r) with the polynomial in r carrying the powers
+// of two) and the table product is fused with the `1 +`, so a tanh costs 13 FP64 operations; M50 evaluates 64 of them per
+// basin-step.
+// `#define HB_TANH_EXACT 0` (library: HB_EXTRA_DEFINES) selects a form with TEN FP64 operations: r from ONE fma with the full
+// double ln2/512 (the product is exact inside the fma; what is lost against the two-constant Cody-Waite form is t * 2^-63
+// <= 2e-15 wherever tanh has not saturated), and e^(2r) = (1 + 2r) + [2r^2 + 4/3 r^3 + 2/3 r^4] with the bracket (<= 9.2e-7)
+// evaluated in FLOAT (two conversions, four FP32 operations): 8.3e-14 absolute.  It is NOT the default because it buys nothing:
+// M50 50 k x 3650 runs 41.65 ms with it and 41.70 ms without — a sub-partition issues one warp instruction per clock and an
+// FP64 instruction holds the issue port for two (tools/r2_fp64_mix.cu, profiles/round2_fp64_issue_microbench.txt), so three
+// FP64 operations traded for six FP32 / conversion ones leave the issue time where it was.
 #define HB_HI_350 0x4075e000   // high word of 350.0
 #ifndef HB_TANH_EXACT
-#define HB_TANH_EXACT 0
+#define HB_TANH_EXACT 1
 #endif
 HB_DEV double hb_tanh(double x) {
     const double MAGIC = 6755399441055744.0;

@@ -59,8 +59,8 @@ def hbm():
 
 
 @pytest.fixture(scope="module")
-def hbm_exact():
-    return _build("#define HB_TANH_EXACT 1")
+def hbm_tanh10():
+    return _build("#define HB_TANH_EXACT 0")
 
 
 @pytest.fixture(scope="module")
@@ -99,14 +99,12 @@ def test_step_func_against_reference_form(hbm):
     assert np.all(np.abs(got[sel] - truth[sel]) / truth[sel] < tol)
 
 
-def test_tanh_and_rcp(hbm, hbm_exact):
+def test_tanh_and_rcp(hbm, hbm_tanh10):
     rng = np.random.default_rng(2)
     x = np.concatenate([rng.uniform(-30, 30, 200000), rng.uniform(-3, 3, 400000), rng.normal(0, 1e-4, 1000), [0.0, 400.0, -400.0]])
-    # default form (10 FP64-pipe operations, the tail of e^(2r) in float): 1e-13 absolute — three decades inside the 1e-10 bar
-    err = np.abs(hbm(2, x) - np.tanh(x))
-    print("hb_tanh default form: max abs error", err.max())
-    assert err.max() < 1e-13
-    assert np.abs(hbm_exact(2, x) - np.tanh(x)).max() < 4.5e-16      # HB_TANH_EXACT: 2 ulp of 1.0
+    assert np.abs(hbm(2, x) - np.tanh(x)).max() < 4.5e-16      # 2 ulp of 1.0
+    # opt-in form with 10 FP64-pipe operations (the tail of e^(2r) in float): 1e-13 absolute
+    assert np.abs(hbm_tanh10(2, x) - np.tanh(x)).max() < 1e-13
     y = np.concatenate([rng.uniform(1e-3, 1e3, 100000), -rng.uniform(1e-3, 1e3, 100000), 10.0 ** rng.uniform(-250, 250, 100000)])
     assert (np.abs(hbm(3, y) * y - 1.0)).max() < 5e-16
 
