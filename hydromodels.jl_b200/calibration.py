@@ -8,7 +8,8 @@ The reference's objective evaluates ONE parameter vector per call on the host an
 * `OptimizationProblem(...)` keeps the reference's keywords (`metric`, `loss`-less, `warm_up`, `lb_pas`, `ub_pas`,
   `fixed_params`, `default_initstates`) and offers `prob.objective(p)` — same value the reference's closure returns —
   and `prob.objective_batch(P)` for a whole population in one launch (`B200Model.objective`, ensemble mode);
-* `solve(prob, DifferentialEvolution(...), maxiters=…)` runs DE/rand/1/bin entirely on the GPU: per generation
+* `solve(prob, DifferentialEvolution(...) | AdaptiveDifferentialEvolution(...), maxiters=…)` runs DE/rand/1/bin (fixed F and
+  CR, or BlackBoxOptim's self-adapting, radius-limited variant) entirely on the GPU: per generation
   `hb_de_trial_device` (mutation + crossover + bounds) writes the trial population straight into the stepper's
   parameter buffer, `hb_run_device` in objective mode scores it, `hb_de_select_device` keeps the better member and
   records the generation's best — three kernels on one stream, nothing crosses PCIe until the end.
@@ -41,6 +42,18 @@ class DifferentialEvolution:
     popsize: int = 1024
     F: float = 0.7
     CR: float = 0.9
+    seed: int = 0
+
+
+@dataclass
+class AdaptiveDifferentialEvolution:
+    """BlackBoxOptim.jl's `adaptive_de_rand_1_bin_radiuslimited` — what every example of the reference passes to `solve`
+    (`/root/reference/ext/HydroModelsOptimizationExt/examples.jl:28`, `docs/src/tutorials/optimimal_parameters.md:189-195`) —
+    run generation-synchronously on the device: per-member F and CR redrawn from bimodal Cauchy mixtures whenever a member's
+    trial fails, parents from a window of `radius` neighbouring members, random re-entry at the bounds
+    (`hb_ade_*_device`, csrc/aot_kernels.cu).  BlackBoxOptim's own defaults: popsize 50, radius 8."""
+    popsize: int = 1024
+    radius: int = 8
     seed: int = 0
 
 
@@ -211,9 +224,12 @@ def solve(prob: OptimizationProblem, alg=None, *, maxiters: int = 100) -> Soluti
     if isinstance(alg, MultiStartAdam):
         return _solve_adam(prob, alg, maxiters)
     alg = alg or DifferentialEvolution()
+    adaptive = isinstance(alg, AdaptiveDifferentialEvolution)
     N, D = int(alg.popsize), len(prob.calibrated)
     if N < 4:
         raise ValueError("differential evolution needs at least 4 members")
+    if adaptive and (alg.radius < 4 or N < alg.radius):
+        raise ValueError("adaptive differential evolution needs radius >= 4 and at least `radius` members")
     if D == 0:
         raise ValueError("nothing to calibrate: every parameter is fixed")
     eng = prob.engine
@@ -245,11 +261,25 @@ def solve(prob: OptimizationProblem, alg=None, *, maxiters: int = 100) -> Soluti
     # generation 0 bookkeeping: only the best of the initial population is recorded (no selection)
     check(L.hb_de_best_device(fit.ptr, N, hist.ptr, 0, None))
     launches = 3
+    extra = []
+    if adaptive:
+        d_f, d_cr = DeviceBuffer(N * 8), DeviceBuffer(N * 8)
+        extra = [d_f, d_cr]
+        check(L.hb_ade_init_device(d_f.ptr, d_cr.ptr, N, C.c_uint64(alg.seed), None))
+        launches += 1
     for g in range(1, maxiters + 1):
-        check(L.hb_de_trial_device(pop.ptr, trial.ptr, d_off.ptr, D, N, d_lb.ptr, d_ub.ptr, float(alg.F), float(alg.CR),
-                                   C.c_uint64(alg.seed), g, None))
+        if adaptive:
+            check(L.hb_ade_trial_device(pop.ptr, trial.ptr, d_off.ptr, D, N, d_lb.ptr, d_ub.ptr, d_f.ptr, d_cr.ptr, int(alg.radius),
+                                        C.c_uint64(alg.seed), g, None))
+        else:
+            check(L.hb_de_trial_device(pop.ptr, trial.ptr, d_off.ptr, D, N, d_lb.ptr, d_ub.ptr, float(alg.F), float(alg.CR),
+                                       C.c_uint64(alg.seed), g, None))
         run.launch(d_in.ptr, tfit.ptr, None)
-        check(L.hb_de_select_device(pop.ptr, trial.ptr, fit.ptr, tfit.ptr, d_off.ptr, D, N, hist.ptr, g, None))
+        if adaptive:
+            check(L.hb_ade_select_device(pop.ptr, trial.ptr, fit.ptr, tfit.ptr, d_off.ptr, D, N, d_f.ptr, d_cr.ptr, C.c_uint64(alg.seed), g,
+                                         hist.ptr, g, None))
+        else:
+            check(L.hb_de_select_device(pop.ptr, trial.ptr, fit.ptr, tfit.ptr, d_off.ptr, D, N, hist.ptr, g, None))
         launches += 4
     check(L.hb_stream_synchronize(None))
     elapsed = time.perf_counter() - t0
@@ -260,7 +290,7 @@ def solve(prob: OptimizationProblem, alg=None, *, maxiters: int = 100) -> Soluti
     best = int(np.argmin(fitness))
     params = dict(prob.fixed)
     params.update({nm: float(population[best, j]) for j, nm in enumerate(prob.calibrated)})
-    for b in (pop, d_off, d_lb, d_ub, fit, tfit, hist, d_in):
+    for b in [pop, d_off, d_lb, d_ub, fit, tfit, hist, d_in] + extra:
         b.free()
     return Solution(u=population[best].copy(), params=params, objective=float(fitness[best]), history=history[:, 0].copy(),
                     n_evaluations=N * (maxiters + 1), population=population, fitness=fitness, gpu_launches=launches,

@@ -808,6 +808,136 @@ __global__ void __launch_bounds__(1024) hb_de_best_kernel(const double *__restri
 
 }  // namespace
 
+// ---- adaptive DE: BlackBoxOptim.jl's `adaptive_de_rand_1_bin_radiuslimited` (the optimiser of every example of the
+// reference: ext/HydroModelsOptimizationExt/examples.jl:28, docs/src/tutorials/optimimal_parameters.md:189-195; the package
+// itself is a dependency that is not vendored under /root/reference — its published operators are restated here),
+// made generation-synchronous: all members are targets once per generation instead of one per step.
+//   * every member carries its own F and CR; a member whose trial did not improve it draws new ones from the bimodal Cauchy
+//     mixtures  F ~ {C(0.65, 0.1) | C(1.0, 0.1)},  CR ~ {C(0.1, 0.1) | C(0.95, 0.1)}  (above 1 -> 1, below 0 -> redrawn);
+//   * the three parents come from a window of `radius` consecutive members (ring order) that contains the target;
+//   * a mutant component outside its bounds lands at a random point between the target's value and the bound.
+// A standard Cauchy variate is X / Y of a point uniform in the unit disk (rejection from the square): only IEEE + - * /, so
+// the numpy restatement reproduces every draw bit for bit (a tangent would not).
+namespace {
+
+constexpr unsigned kAdeDrawParam = 1u << 20;     // draw indices of the parameter redraws (trial draws stay below)
+
+__device__ double hb_ade_cauchy01(unsigned long long seed, unsigned gen, unsigned member, unsigned k0, double loc1, double loc2, double scale) {
+    // up to 8 attempts of (mixture pick, disk point); 16 draws each
+    for (unsigned a = 0; a < 8; ++a) {
+        const unsigned k = k0 + 64u * a;
+        const double loc = hb_de_uniform(seed, gen, member, k) < 0.5 ? loc1 : loc2;
+        double c = 0.0;
+        bool ok = false;
+        for (unsigned r = 0; r < 16 && !ok; ++r) {
+            const double x = __dsub_rn(__dmul_rn(2.0, hb_de_uniform(seed, gen, member, k + 1 + 2 * r)), 1.0);
+            const double y = __dsub_rn(__dmul_rn(2.0, hb_de_uniform(seed, gen, member, k + 2 + 2 * r)), 1.0);
+            if (__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)) <= 1.0 && y != 0.0) { c = __ddiv_rn(x, y); ok = true; }
+        }
+        const double v = __dadd_rn(loc, __dmul_rn(scale, c));
+        if (ok && v >= 0.0) return v > 1.0 ? 1.0 : v;
+    }
+    return loc1;
+}
+
+__global__ void __launch_bounds__(256) hb_ade_params_kernel(double *__restrict__ f, double *__restrict__ cr, const unsigned char *__restrict__ redraw,
+                                                            int N, unsigned long long seed, unsigned gen) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N || (redraw && !redraw[i])) return;
+    f[i] = hb_ade_cauchy01(seed, gen, i, kAdeDrawParam, 0.65, 1.0, 0.1);
+    cr[i] = hb_ade_cauchy01(seed, gen, i, kAdeDrawParam + 1024u, 0.1, 0.95, 0.1);
+}
+
+__global__ void __launch_bounds__(256) hb_ade_trial_kernel(const double *__restrict__ pop, double *__restrict__ trial,
+                                                           const long long *__restrict__ dim_off, int D, int N,
+                                                           const double *__restrict__ lb, const double *__restrict__ ub,
+                                                           const double *__restrict__ f, const double *__restrict__ cr, int radius,
+                                                           unsigned long long seed, unsigned gen) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    // the window [i - w, i - w + radius) holds the target at position w; three distinct other positions
+    int w = (int)(hb_de_uniform(seed, gen, i, 0) * radius);
+    if (w > radius - 1) w = radius - 1;
+    const int M = radius - 1;
+    int o1 = (int)(hb_de_uniform(seed, gen, i, 1) * M);
+    int o2 = (int)(hb_de_uniform(seed, gen, i, 2) * (M - 1));
+    int o3 = (int)(hb_de_uniform(seed, gen, i, 3) * (M - 2));
+    if (o1 > M - 1) o1 = M - 1;
+    if (o2 > M - 2) o2 = M - 2;
+    if (o3 > M - 3) o3 = M - 3;
+    if (o2 >= o1) ++o2;
+    const int lo = o1 < o2 ? o1 : o2, hi = o1 < o2 ? o2 : o1;
+    if (o3 >= lo) ++o3;
+    if (o3 >= hi) ++o3;
+    o1 += o1 >= w;
+    o2 += o2 >= w;
+    o3 += o3 >= w;
+    const int base = i - w + N;
+    const int r1 = (base + o1) % N, r2 = (base + o2) % N, r3 = (base + o3) % N;
+    int jrand = (int)(hb_de_uniform(seed, gen, i, 4) * D);
+    if (jrand > D - 1) jrand = D - 1;
+    const double F = f[i], CR = cr[i];
+    for (int d = 0; d < D; ++d) {
+        const double *p = pop + dim_off[d];
+        const double own = p[i];
+        double v = own;
+        if (hb_de_uniform(seed, gen, i, 8 + 2 * d) < CR || d == jrand) {
+            v = __dadd_rn(p[r1], __dmul_rn(F, __dsub_rn(p[r2], p[r3])));
+            const double u = hb_de_uniform(seed, gen, i, 9 + 2 * d);
+            if (v < lb[d]) v = __dadd_rn(own, __dmul_rn(u, __dsub_rn(lb[d], own)));
+            else if (v > ub[d]) v = __dadd_rn(own, __dmul_rn(u, __dsub_rn(ub[d], own)));
+        }
+        trial[dim_off[d] + i] = v;
+    }
+}
+
+// strict improvement (or a real-valued trial against a NaN incumbent) replaces the member; everyone else redraws F and CR
+__global__ void __launch_bounds__(256) hb_ade_select_kernel(double *__restrict__ pop, const double *__restrict__ trial, double *__restrict__ fit,
+                                                            const double *__restrict__ trial_fit, const long long *__restrict__ dim_off, int D,
+                                                            int N, double *__restrict__ f, double *__restrict__ cr, unsigned long long seed,
+                                                            unsigned gen) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const double tf = trial_fit[i], fi = fit[i];
+    if (tf < fi || (fi != fi && tf == tf)) {
+        fit[i] = tf;
+        for (int d = 0; d < D; ++d) pop[dim_off[d] + i] = trial[dim_off[d] + i];
+    } else {
+        f[i] = hb_ade_cauchy01(seed, gen, i, kAdeDrawParam, 0.65, 1.0, 0.1);
+        cr[i] = hb_ade_cauchy01(seed, gen, i, kAdeDrawParam + 1024u, 0.1, 0.95, 0.1);
+    }
+}
+
+}  // namespace
+
+extern "C" int hb_ade_init_device(double *f, double *cr, int n_members, uint64_t seed, void *stream) {
+    if (!f || !cr || n_members <= 0) return HB_ERR_INVALID;
+    hb_ade_params_kernel<<<(n_members + 255) / 256, 256, 0, (cudaStream_t)stream>>>(f, cr, nullptr, n_members, seed, 0u);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
+extern "C" int hb_ade_trial_device(const double *pop, double *trial, const int64_t *dim_offset, int n_dims, int n_members,
+                                   const double *lower, const double *upper, const double *f, const double *cr, int radius, uint64_t seed,
+                                   uint32_t generation, void *stream) {
+    if (!pop || !trial || !dim_offset || !lower || !upper || !f || !cr || n_dims <= 0 || radius < 4 || n_members < radius || n_dims > (1 << 18))
+        return HB_ERR_INVALID;
+    hb_ade_trial_kernel<<<(n_members + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pop, trial, (const long long *)dim_offset, n_dims, n_members,
+                                                                                 lower, upper, f, cr, radius, seed, generation);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
+extern "C" int hb_ade_select_device(double *pop, const double *trial, double *fitness, const double *trial_fitness,
+                                    const int64_t *dim_offset, int n_dims, int n_members, double *f, double *cr, uint64_t seed,
+                                    uint32_t generation, double *history, int history_slot, void *stream) {
+    if (!pop || !trial || !fitness || !trial_fitness || !dim_offset || !f || !cr || n_dims <= 0 || n_members <= 0) return HB_ERR_INVALID;
+    if (pop == trial || fitness == trial_fitness) return HB_ERR_INVALID;
+    hb_ade_select_kernel<<<(n_members + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pop, trial, fitness, trial_fitness,
+                                                                                  (const long long *)dim_offset, n_dims, n_members, f, cr, seed,
+                                                                                  generation);
+    if (history) hb_de_best_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(fitness, n_members, history, history_slot);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
 extern "C" int hb_de_trial_device(const double *pop, double *trial, const int64_t *dim_offset, int n_dims, int n_members,
                                   const double *lower, const double *upper, double F, double CR, uint64_t seed, uint32_t generation,
                                   void *stream) {

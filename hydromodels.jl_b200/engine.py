@@ -158,6 +158,11 @@ def lib():
         "hb_irf_reduce_segments_device": [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
         "hb_irf_gather_rows_device": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
         "hb_de_best_device": [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p],
+        "hb_ade_init_device": [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p],
+        "hb_ade_trial_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p],
+        "hb_ade_select_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_uint64, C.c_uint32, C.c_void_p, C.c_int32, C.c_void_p],
         "hb_malloc_device": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_device": [C.c_void_p],
         "hb_malloc_host": [C.POINTER(C.c_void_p), C.c_int64], "hb_free_host": [C.c_void_p],
         "hb_memcpy_h2d": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],

@@ -406,6 +406,21 @@ int hb_de_select_device(double *pop, const double *trial, double *fitness, const
  * (generation 0 bookkeeping: no selection). */
 int hb_de_best_device(const double *fitness, int32_t n_members, double *history, int32_t history_slot, void *stream);
 
+/* Adaptive DE — BlackBoxOptim.jl's `adaptive_de_rand_1_bin_radiuslimited`, the optimiser the reference's examples pass to
+ * `solve` (ext/HydroModelsOptimizationExt/examples.jl:28, docs/src/tutorials/optimimal_parameters.md:189-195), generation-
+ * synchronous: per-member F and CR (`f`, `cr`: DEVICE [n_members], drawn by hb_ade_init_device; a member whose trial did not
+ * strictly improve it redraws both from the bimodal Cauchy mixtures F ~ {C(0.65,0.1) | C(1,0.1)}, CR ~ {C(0.1,0.1) |
+ * C(0.95,0.1)}, above 1 -> 1, below 0 -> redrawn), parents from a window of `radius` (>= 4, BlackBoxOptim: 8) consecutive members
+ * around the target, out-of-bounds components placed at random between the target's value and the bound.  Same buffers,
+ * aliasing rule and history as the plain DE entry points; `generation` >= 1 keys the draws. */
+int hb_ade_init_device(double *f, double *cr, int32_t n_members, uint64_t seed, void *stream);
+int hb_ade_trial_device(const double *pop, double *trial, const int64_t *dim_offset, int32_t n_dims, int32_t n_members,
+                        const double *lower, const double *upper, const double *f, const double *cr, int32_t radius, uint64_t seed,
+                        uint32_t generation, void *stream);
+int hb_ade_select_device(double *pop, const double *trial, double *fitness, const double *trial_fitness,
+                         const int64_t *dim_offset, int32_t n_dims, int32_t n_members, double *f, double *cr, uint64_t seed,
+                         uint32_t generation, double *history, int32_t history_slot, void *stream);
+
 /* ---- memory helpers (so a host without a CUDA binding can own device / pinned buffers) ---- */
 int hb_malloc_device(void **ptr, int64_t bytes);
 int hb_free_device(void *ptr);

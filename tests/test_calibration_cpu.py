@@ -46,6 +46,36 @@ def test_de_trial_indices_are_distinct_and_trials_stay_in_bounds(N, D):
     assert np.array_equal(kp[2], pop[2]) and kf[2] == 0.5 and np.array_equal(kp[3], trial[3]) and kf[3] == 0.4
 
 
+def test_adaptive_de_restatement_has_blackboxoptims_operators():
+    """`ade_params` / `ade_trial` / `ade_select` (oracle): the bimodal Cauchy mixtures BlackBoxOptim's adaptive DE draws F and
+    CR from (modes at 0.65 | 1.0 and 0.1 | 0.95, scale 0.1, truncated to [0, 1] with mass piling up at 1), parents that are
+    distinct, differ from the target and lie within the radius window, re-entry inside the box, strict selection."""
+    N = 4000
+    f, cr = ho.ade_params(N, 11, 0)
+    assert f.min() >= 0 and f.max() <= 1 and cr.min() >= 0 and cr.max() <= 1
+    # mixture modes: about half of F within 0.1 of 0.65 (a Cauchy has half its mass within one scale), a quarter+ exactly 1
+    assert 0.18 < np.mean(np.abs(f - 0.65) < 0.1) < 0.32 and 0.2 < np.mean(f == 1.0) < 0.4
+    assert 0.18 < np.mean(np.abs(cr - 0.1) < 0.1) < 0.36 and 0.18 < np.mean(np.abs(cr - 0.95) <= 0.1) < 0.45
+    rng = np.random.default_rng(0)
+    D, radius = 5, 8
+    lb, ub = -rng.random(D), 1 + rng.random(D)
+    pop = lb + rng.random((N, D)) * (ub - lb)
+    trial, (r1, r2, r3, w) = ho.ade_trial(pop, lb, ub, f, cr, radius, 11, 1)
+    i = np.arange(N)
+    for r in (r1, r2, r3):
+        assert np.all(r != i) and np.all(((r - (i - w)) % N) < radius)
+    assert np.all(r1 != r2) and np.all(r1 != r3) and np.all(r2 != r3)
+    assert np.all(trial >= lb) and np.all(trial <= ub) and np.any(trial != pop)
+    assert np.all(np.any(trial != pop, axis=1))                               # jrand: every trial differs from its target
+    fit, tfit = rng.random(N), rng.random(N)
+    tfit[:10] = fit[:10]                                                      # ties: the member stays and redraws
+    pop2, fit2, f2, cr2 = ho.ade_select(pop, trial, fit, tfit, f, cr, 11, 1)
+    better = tfit < fit
+    assert np.array_equal(pop2[better], trial[better]) and np.array_equal(pop2[~better], pop[~better])
+    assert np.array_equal(f2[better], f[better]) and np.mean(f2[~better] != f[~better]) > 0.6
+    assert np.array_equal(fit2, np.minimum(fit, tfit))
+
+
 def test_optimization_problem_keywords():
     model = hm.models.exphydro()
     inp, tgt = np.zeros((3, 10)), np.zeros(10)

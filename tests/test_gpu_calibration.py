@@ -112,6 +112,68 @@ def test_device_de_recovers_planted_parameters_and_follows_the_oracle_loop():
     assert np.array_equal(np.array(hist), sol.history[:6])
 
 
+@pytest.mark.parametrize("N,D,offs,radius", [(8, 1, [0], 8), (37, 3, [0, 37, 74], 4), (1000, 6, [0, 1000, 2001, 3001, 4001, 5002], 8)])
+def test_adaptive_de_kernels_match_the_numpy_restatement_bit_for_bit(N, D, offs, radius):
+    """`hb_ade_*_device` (BlackBoxOptim's adaptive, radius-limited DE made generation-synchronous) against the oracle's
+    restatement: per-member F / CR draws, windows, trials with random re-entry at the bounds, strict selection and the
+    redraws of the members that failed — every value identical."""
+    rng = np.random.default_rng(N + D)
+    lb, ub = -rng.random(D), 1 + rng.random(D)
+    pop = lb + rng.random((N, D)) * (ub - lb)
+    n_flat = offs[-1] + N + 3
+    flat = rng.random(n_flat)
+    for d in range(D):
+        flat[offs[d]:offs[d] + N] = pop[:, d]
+    d_pop, d_trial = DeviceBuffer.from_host(flat), DeviceBuffer.from_host(flat)
+    d_off = DeviceBuffer.from_host(np.array(offs, dtype=np.int64))
+    d_lb, d_ub = DeviceBuffer.from_host(lb), DeviceBuffer.from_host(ub)
+    d_f, d_cr = DeviceBuffer(N * 8), DeviceBuffer(N * 8)
+    check(lib().hb_ade_init_device(d_f.ptr, d_cr.ptr, N, 777, None))
+    f, cr = ho.ade_params(N, 777, 0)
+    assert np.array_equal(d_f.to_host((N,)), f) and np.array_equal(d_cr.to_host((N,)), cr)
+    assert f.min() >= 0.0 and f.max() <= 1.0 and cr.min() >= 0.0 and cr.max() <= 1.0
+    for gen in (1, 2, 3):
+        check(lib().hb_ade_trial_device(d_pop.ptr, d_trial.ptr, d_off.ptr, D, N, d_lb.ptr, d_ub.ptr, d_f.ptr, d_cr.ptr, radius, 777, gen, None))
+        got = d_trial.to_host((n_flat,))
+        ref, _ = ho.ade_trial(pop, lb, ub, f, cr, radius, 777, gen)
+        assert np.array_equal(np.stack([got[o:o + N] for o in offs], axis=1), ref)
+        assert np.all(ref >= lb) and np.all(ref <= ub)
+        mask = np.ones(n_flat, bool)
+        for o in offs:
+            mask[o:o + N] = False
+        assert np.array_equal(got[mask], flat[mask])
+        fit, tfit = rng.random(N), rng.random(N)
+        tfit[::7] = np.nan
+        fit[1::5] = np.nan
+        tfit[2::9] = fit[2::9]                                                 # ties keep the member (strict improvement)
+        d_fit, d_tfit, d_hist = DeviceBuffer.from_host(fit), DeviceBuffer.from_host(tfit), DeviceBuffer.from_host(np.zeros(8))
+        check(lib().hb_ade_select_device(d_pop.ptr, d_trial.ptr, d_fit.ptr, d_tfit.ptr, d_off.ptr, D, N, d_f.ptr, d_cr.ptr, 777, gen,
+                                         d_hist.ptr, gen, None))
+        pop, new_fit, f, cr = ho.ade_select(pop, ref, fit, tfit, f, cr, 777, gen)
+        got = d_pop.to_host((n_flat,))
+        assert np.array_equal(np.stack([got[o:o + N] for o in offs], axis=1), pop)
+        assert np.array_equal(d_fit.to_host((N,)), new_fit, equal_nan=True)
+        assert np.array_equal(d_f.to_host((N,)), f) and np.array_equal(d_cr.to_host((N,)), cr)
+        hist = d_hist.to_host((8,))
+        assert hist[2 * gen] == np.nanmin(new_fit) and int(hist[2 * gen + 1]) == int(np.nanargmin(new_fit))
+    with pytest.raises(ValueError):
+        check(lib().hb_ade_trial_device(d_pop.ptr, d_trial.ptr, d_off.ptr, D, N, d_lb.ptr, d_ub.ptr, d_f.ptr, d_cr.ptr, 3, 777, 1, None))
+
+
+def test_adaptive_de_recovers_planted_parameters():
+    """The optimiser of the reference's examples (`BBO_adaptive_de_rand_1_bin_radiuslimited`) on the device: planted ExpHydro
+    parameters recovered, monotone history, population inside the box, and at least as good as plain DE on the same budget."""
+    model, inp, target, prob = _problem()
+    sol = cal.solve(prob, cal.AdaptiveDifferentialEvolution(popsize=512, radius=8, seed=3), maxiters=150)
+    assert sol.objective < -0.999 and sol.n_evaluations == 512 * 151 and sol.gpu_launches == 4 + 4 * 150
+    assert np.all(np.diff(sol.history) <= 0) and sol.history[-1] == sol.objective == sol.fitness.min()
+    assert np.all(sol.population >= LB) and np.all(sol.population <= UB)
+    assert prob.objective(sol.u) == pytest.approx(sol.objective, rel=1e-12)
+    assert abs(sol.params["Smax"] - TRUE[3]) / TRUE[3] < 0.1 and abs(sol.params["f"] - TRUE[5]) / TRUE[5] < 0.1
+    with pytest.raises(ValueError, match="radius"):
+        cal.solve(prob, cal.AdaptiveDifferentialEvolution(popsize=6, radius=8), maxiters=1)
+
+
 def test_fixed_parameters_and_unsupported_models():
     model, inp, target, _ = _problem(T=365)
     prob = cal.OptimizationProblem(model, inp, target, warm_up=30, lb_pas=LB[[0, 1, 2, 3]], ub_pas=UB[[0, 1, 2, 3]],
