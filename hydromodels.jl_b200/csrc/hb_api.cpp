@@ -1441,6 +1441,106 @@ int hb_probe_pcie_gbs(int64_t bytes, int reps, double *gbs) {
     return HB_OK;
 }
 
+// ---- raster ingest: HOST rasters -> the stepper's [T][N][V] forcing on the device, streamed ------------------------
+// (/root/reference/ext/HydroModelsRastersExt/netcdf_loader.jl:29-62, :119-136 build the same array
+// on the host with a Julia loop per position.)  The rasters never sit on the device as a whole: time chunks of every
+// variable go host -> (pinned staging slot, filled by the library's host threads when the source is pageable) -> device
+// scratch slot -> pack kernel -> out, with two slots so that the copy of chunk c+1 runs under the pack of chunk c.
+namespace {
+struct IngestState {
+    std::mutex mu;
+    hb_model_s::Buf dev[2], pin[2], ptrs[2];
+    cudaStream_t copy = nullptr;
+    cudaEvent_t landed[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr};
+};
+IngestState g_ingest;
+}  // namespace
+
+extern "C" int hb_pack_forcing_device(const double *const *, int, int64_t, int64_t, int64_t, int64_t, const int32_t *, const int32_t *, int64_t,
+                                      double *, void *);
+extern "C" int hb_pack_forcing_dense_device(const double *const *, int, int64_t, int64_t, int64_t, int64_t, int, int, double *, void *);
+
+int hb_ingest_forcing(const double *const *vars_host, int32_t n_vars, int64_t n_steps, int64_t t_stride, int64_t row_stride,
+                      int64_t col_stride, int32_t rows, int32_t cols, const int32_t *node_row, const int32_t *node_col, int64_t n_nodes,
+                      double *out, void *stream) {
+    if (!vars_host || n_vars <= 0 || n_vars > 64 || n_steps < 0 || rows <= 0 || cols <= 0 || !out) return fail(HB_ERR_INVALID, "bad ingest arguments");
+    const int64_t plane = (int64_t)rows * cols;
+    if (t_stride != plane) return fail(HB_ERR_INVALID, "ingest needs rasters whose time axis is the slowest (t_stride == rows * cols)");
+    const bool dense = !node_row && !node_col;
+    if (!dense && (!node_row || !node_col || n_nodes <= 0)) return fail(HB_ERR_INVALID, "node_row / node_col / n_nodes");
+    if (dense && n_vars > 5) return fail(HB_ERR_INVALID, "the dense gather takes at most 5 variables");
+    for (int v = 0; v < n_vars; ++v)
+        if (!vars_host[v]) return fail(HB_ERR_INVALID, "raster %d is NULL", v);
+    if (n_steps == 0) return HB_OK;
+    int rc = ensure_device();
+    if (rc) return rc;
+    HB_CUDA(cudaSetDevice(g_device));
+    std::lock_guard<std::mutex> lk(g_ingest.mu);
+    IngestState &g = g_ingest;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!g.copy) {
+        HB_CUDA(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            HB_CUDA(cudaEventCreateWithFlags(&g.landed[k], cudaEventDisableTiming));
+            HB_CUDA(cudaEventCreateWithFlags(&g.packed[k], cudaEventDisableTiming));
+        }
+    }
+    // steps per chunk: ~64 MiB of raster data per slot (all variables), at most the pack kernels' 65535 steps per launch
+    size_t per_slot = (size_t)64 << 20;
+    if (const char *e = getenv("HB_INGEST_CHUNK_BYTES")) { long long v = atoll(e); if (v > 0) per_slot = (size_t)v; }
+    const size_t step_bytes = (size_t)plane * 8 * n_vars;
+    int64_t cs = (int64_t)(per_slot / step_bytes);
+    if (cs < 1) cs = 1;
+    if (cs > 32768) cs = 32768;
+    if (cs > n_steps) cs = n_steps;
+    const int64_t nchunk = (n_steps + cs - 1) / cs;
+    const int nslots = nchunk > 1 ? 2 : 1;
+    const size_t slot_bytes = step_bytes * (size_t)cs;
+    bool pageable = false;
+    for (int v = 0; v < n_vars; ++v) pageable = pageable || host_is_pageable(vars_host[v]);
+    for (int k = 0; k < nslots; ++k) {
+        if ((rc = ws_reserve(g.dev[k], slot_bytes)) || (rc = ws_reserve(g.ptrs[k], 64 * sizeof(void *)))) return rc;
+        if (pageable && (rc = pin_reserve(g.pin[k], slot_bytes))) return rc;
+        // the slot's pointer table: variable v of the chunk starts at dev + v * cs * plane doubles
+        const double *tab[64];
+        for (int v = 0; v < n_vars; ++v) tab[v] = (const double *)g.dev[k].p + (size_t)v * cs * plane;
+        HB_CUDA(cudaMemcpyAsync(g.ptrs[k].p, tab, n_vars * sizeof(void *), cudaMemcpyHostToDevice, st));
+    }
+    HB_CUDA(cudaStreamSynchronize(st));         // tables are in place (and `tab` may go out of scope)
+    // the copy stream must not overwrite a slot the caller's stream may still be reading from a previous call
+    HB_CUDA(cudaEventRecord(g.packed[0], st));
+    HB_CUDA(cudaStreamWaitEvent(g.copy, g.packed[0], 0));
+    for (int64_t c = 0; c < nchunk; ++c) {
+        const int sl = (int)(c % nslots);
+        const int64_t t0 = c * cs, nt = (n_steps - t0) < cs ? (n_steps - t0) : cs;
+        const size_t var_bytes = (size_t)nt * plane * 8;
+        if (c >= nslots) {
+            HB_CUDA(cudaStreamWaitEvent(g.copy, g.packed[sl], 0));              // device slot consumed by its pack kernel
+            if (pageable) HB_CUDA(cudaEventSynchronize(g.landed[sl]));          // pinned slot's previous chunk is on the device
+        }
+        for (int v = 0; v < n_vars; ++v) {
+            const char *src = (const char *)(vars_host[v] + t0 * plane);
+            char *dst = (char *)g.dev[sl].p + (size_t)v * cs * plane * 8;
+            if (pageable) {
+                char *pin = (char *)g.pin[sl].p + (size_t)v * cs * plane * 8;
+                host_pool().copy(pin, src, var_bytes);
+                src = pin;
+            }
+            HB_CUDA(cudaMemcpyAsync(dst, src, var_bytes, cudaMemcpyHostToDevice, g.copy));
+        }
+        HB_CUDA(cudaEventRecord(g.landed[sl], g.copy));
+        HB_CUDA(cudaStreamWaitEvent(st, g.landed[sl], 0));
+        double *dst_out = out + (size_t)t0 * (dense ? plane : n_nodes) * n_vars;
+        rc = dense ? hb_pack_forcing_dense_device((const double *const *)g.ptrs[sl].p, n_vars, nt, plane, row_stride, col_stride, rows, cols, dst_out, st)
+                   : hb_pack_forcing_device((const double *const *)g.ptrs[sl].p, n_vars, nt, plane, row_stride, col_stride, node_row, node_col,
+                                            n_nodes, dst_out, st);
+        if (rc) return fail(rc, "pack kernel launch failed in hb_ingest_forcing");
+        HB_CUDA(cudaEventRecord(g.packed[sl], st));
+    }
+    HB_CUDA(cudaStreamSynchronize(st));          // the caller's rasters and the staging slots are free again
+    return HB_OK;
+}
+
 int hb_host_copy(void *dst, const void *src, int64_t bytes) {
     if ((!dst || !src) && bytes > 0) return fail(HB_ERR_INVALID, "NULL argument");
     if (bytes < 0) return fail(HB_ERR_INVALID, "negative size");

@@ -149,6 +149,8 @@ def lib():
                                    C.c_void_p, C.c_void_p],
         "hb_pack_forcing_dense_device": [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p],
+        "hb_ingest_forcing": [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                              C.c_int64, C.c_void_p, C.c_void_p],
         "hb_de_trial_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                C.c_uint64, C.c_uint32, C.c_void_p],
         "hb_de_select_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,

@@ -9,7 +9,8 @@ Same names and argument meaning as the reference: `compute_d8_flow_direction(dem
 What runs on the GPU: the D8 steepest-descent stencil (`hb_d8_flow_direction_device`) and the gather of the variable
 rasters at the node positions into the stepper's forcing layout `[T][N][V]` (`hb_pack_forcing_device`,
 `device_forcing`) — so a gridded run goes NetCDF -> pinned host -> HBM -> packed forcing -> `GridDeviceRun` /
-`DeviceRun` without a host-side transpose.  Neither has a CPU path here; position lists (one integer pair per
+`DeviceRun` without a host-side transpose; `ingest_forcing` does the upload and the gather in one streamed call
+(`hb_ingest_forcing`: two chunk slots, host rasters never whole on the device).  Neither has a CPU path here; position lists (one integer pair per
 valid cell, computed once per grid) are plain numpy.
 """
 from __future__ import annotations
@@ -166,4 +167,62 @@ def device_forcing(rasters: Sequence, positions: Sequence[Tuple[int, int]], n_st
     check(lib().hb_stream_synchronize(stream))
     for b in (d_ptrs, d_r, d_c):
         b.free()
+    return out
+
+
+def ingest_forcing(rasters: Sequence[np.ndarray], positions: Optional[Sequence[Tuple[int, int]]] = None, *, layout: str = "trc",
+                   stream: Optional[int] = None, out=None):
+    """HOST rasters -> a device buffer laid out `[T][N][V]`, streamed through the library (`hb_ingest_forcing`): what
+    `load_netcdf_data` + `prepare_netcdf_forcing` (`netcdf_loader.jl:29-62, :119-136`) and an upload would do, without ever
+    holding the rasters on the device — time chunks are copied (pinned staging by the library's host threads for ordinary
+    numpy / memory-mapped arrays) while the previous chunk is being gathered.
+
+    `rasters`: one array per variable, each `[time, rows, cols]` C-ordered ("trc", NetCDF's usual order) or `[rows, cols, time]`
+    Fortran-ordered ("tcr", the arrays the reference indexes) — the time axis is the slowest in memory either way.
+    `positions`: 1-based `(row, col)` pairs, or None for every cell in row-major order.  `out`: an existing `DeviceBuffer` of
+    `T * N * V * 8` bytes to fill (a loop over files reuses one), else a new one is allocated."""
+    from .engine import DeviceBuffer, check, lib
+    if layout not in ("trc", "tcr"):
+        raise ValueError("layout must be 'trc' or 'tcr'")
+    arrs = []
+    for a in rasters:
+        a = np.asarray(a)
+        if a.dtype != np.float64 or a.ndim != 3:
+            raise TypeError("rasters must be 3-dimensional float64 arrays")
+        if layout == "trc" and not a.flags.c_contiguous:
+            raise ValueError("layout 'trc' takes C-contiguous [time, rows, cols] arrays")
+        if layout == "tcr" and not a.flags.f_contiguous:
+            raise ValueError("layout 'tcr' takes Fortran-contiguous [rows, cols, time] arrays")
+        arrs.append(a)
+    if not arrs or any(a.shape != arrs[0].shape for a in arrs):
+        raise ValueError("rasters must be a non-empty list of equally shaped arrays")
+    if layout == "trc":
+        T, rows, cols = arrs[0].shape
+        rs, cs = cols, 1
+    else:
+        rows, cols, T = arrs[0].shape
+        rs, cs = 1, rows
+    V = len(arrs)
+    ptrs = (C.c_void_p * V)(*[a.ctypes.data for a in arrs])
+    bufs = []
+    if positions is None:
+        N, d_r, d_c = rows * cols, None, None
+    else:
+        pos = np.asarray(positions, dtype=np.int64).reshape(-1, 2) - 1
+        if pos.size and (pos.min() < 0 or pos[:, 0].max() >= rows or pos[:, 1].max() >= cols):
+            raise IndexError("position outside the raster")
+        N = len(pos)
+        d_r = DeviceBuffer.from_host(np.ascontiguousarray(pos[:, 0], dtype=np.int32))
+        d_c = DeviceBuffer.from_host(np.ascontiguousarray(pos[:, 1], dtype=np.int32))
+        bufs = [d_r, d_c]
+    if out is None:
+        out = DeviceBuffer(T * N * V * 8)
+    elif out.nbytes < T * N * V * 8:
+        raise ValueError(f"out holds {out.nbytes} bytes, the forcing needs {T * N * V * 8}")
+    try:
+        check(lib().hb_ingest_forcing(ptrs, V, T, rows * cols, rs, cs, rows, cols, d_r.ptr if d_r else None, d_c.ptr if d_c else None, N,
+                                      out.ptr, stream))
+    finally:
+        for b in bufs:
+            b.free()
     return out

@@ -386,6 +386,17 @@ int hb_pack_forcing_device(const double *const *vars_device_array, int32_t n_var
 int hb_pack_forcing_dense_device(const double *const *vars_device_array, int n_vars, int64_t n_steps, int64_t t_stride,
                                  int64_t row_stride, int64_t col_stride, int rows, int cols, double *out, void *stream);
 
+/* The same gather from HOST rasters, streamed (netcdf_loader.jl:29-62, :119-136 + the upload): `vars_host[v]` is raster v in
+ * host memory (pinned or ordinary pageable memory — a Julia Array, a numpy array, an mmap'd file), time axis slowest
+ * (t_stride == rows * cols; element (t, r, c) at t * t_stride + r * row_stride + c * col_stride).  Time chunks go through two
+ * device scratch slots (and two pinned staging slots when the source is pageable, filled by the library's host threads), so the
+ * copy of chunk c + 1 runs under the pack kernel of chunk c and the rasters never sit on the device as a whole.
+ * node_row / node_col: DEVICE arrays of 0-based positions, or both NULL for the dense case (all cells row-major, n_vars <= 5).
+ * `out`: DEVICE [n_steps][n_nodes][n_vars].  Synchronous: returns when `out` is complete on `stream`. */
+int hb_ingest_forcing(const double *const *vars_host, int32_t n_vars, int64_t n_steps, int64_t t_stride, int64_t row_stride,
+                      int64_t col_stride, int32_t rows, int32_t cols, const int32_t *node_row, const int32_t *node_col,
+                      int64_t n_nodes, double *out, void *stream);
+
 /* ---- on-device calibration: differential evolution around the ensemble objective kernel -----------------------
  * Replaces the host loop `solve(OptimizationProblem(component, input, target; ...), BBO_adaptive_de_rand_1_bin...)`
  * (/root/reference/ext/HydroModelsOptimizationExt/HydroModelsOptimizationExt.jl:72-199, docs/src/tutorials/

@@ -79,6 +79,50 @@ def test_pack_forcing_dense_grid_takes_the_tiled_kernel(layout, R, Cc):
         assert np.array_equal(got2, got[:, perm, :])
 
 
+@pytest.mark.parametrize("layout", ["trc", "tcr"])
+@pytest.mark.parametrize("dense", [True, False])
+def test_streamed_ingest_from_host_rasters(layout, dense, monkeypatch):
+    """`hb_ingest_forcing`: host rasters -> `[T][N][V]` on the device through two chunk slots (copy of chunk c + 1 under the
+    gather of chunk c).  Ordinary numpy arrays (pageable: pinned staging by the library's threads) and pinned ones, a chunk
+    size that cuts T into many ragged chunks and the one-chunk default — all equal to the exact gather."""
+    from hydromodels_jl_b200.engine import check, lib
+    rng = np.random.default_rng(11)
+    R, Cc, T, V = 37, 50, 23, 3
+    cubes = [rng.normal(size=(R, Cc, T)) for _ in range(V)]                                  # reference indexing [row, col, time]
+    pos = [(r + 1, c + 1) for r in range(R) for c in range(Cc) if dense or rng.random() < 0.6]
+    mem = [np.ascontiguousarray(a.transpose(2, 0, 1)) if layout == "trc" else np.asfortranarray(a) for a in cubes]
+    ref = ho.gather_forcing(cubes, pos)
+    for chunk in (None, str(V * R * Cc * 8 * 4), str(1)):                                    # default | 4 steps per chunk | 1 step
+        if chunk is None:
+            monkeypatch.delenv("HB_INGEST_CHUNK_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("HB_INGEST_CHUNK_BYTES", chunk)
+        out = rs.ingest_forcing(mem, None if dense else pos, layout=layout)
+        assert np.array_equal(out.to_host((V, len(pos), T), order="F"), ref)
+        out.free()
+    # pinned sources take the direct path (no staging)
+    import ctypes as C
+    n_bytes = mem[0].nbytes
+    pinned, keep = [], []
+    for m in mem:
+        ptr = C.c_void_p()
+        check(lib().hb_malloc_host(C.byref(ptr), n_bytes))
+        keep.append(ptr)
+        a = np.ctypeslib.as_array((C.c_double * m.size).from_address(ptr.value)).reshape(m.shape, order="C" if layout == "trc" else "F")
+        a[...] = m
+        pinned.append(a)
+    monkeypatch.setenv("HB_INGEST_CHUNK_BYTES", str(V * R * Cc * 8 * 5))
+    out = rs.ingest_forcing(pinned, None if dense else pos, layout=layout)
+    assert np.array_equal(out.to_host((V, len(pos), T), order="F"), ref)
+    out.free()
+    for ptr in keep:
+        check(lib().hb_free_host(ptr))
+    with pytest.raises(ValueError):
+        rs.ingest_forcing([m.transpose(0, 2, 1) for m in mem], layout=layout)                # not contiguous in the stated order
+    with pytest.raises(IndexError):
+        rs.ingest_forcing(mem, [(R + 1, 1)], layout=layout)
+
+
 def test_dem_to_routed_grid_run():
     """DEM -> D8 on the GPU -> `exphydro_grid` on those flow directions: same result as with the oracle's directions,
     and the outlet of the plane collects more flow than the ridge (`test/base/run_spatial_model.jl:140`)."""
