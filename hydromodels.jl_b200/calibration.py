@@ -70,6 +70,19 @@ class MultiStartAdam:
 
 
 @dataclass
+class Adam:
+    """`Optimization.solve(prob, Adam(lr); maxiters)` on the reverse-mode gradient — the reference trains the neural fluxes of
+    a hybrid model this way (`adtype=AutoZygote()` through its ImmutableSolver, `/root/reference/README.md:161-187`,
+    `src/solve.jl:62-79`).  One forward run (state trajectory) + one adjoint sweep per iteration (`B200Model.gradient_reverse`);
+    the optimisation vector is [calibrated physical parameters, all network weights], as in the reference's
+    `OptimizationProblem` (`…OptimizationExt.jl:94-104`).  Physical parameters with bounds are projected onto them."""
+    lr: float = 0.01
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+
+
+@dataclass
 class Solution:
     u: np.ndarray                      # best calibrated vector (order = prob.calibrated)
     params: Dict[str, float]           # all parameters, fixed ones included
@@ -81,6 +94,7 @@ class Solution:
     gpu_launches: int = 0
     elapsed_s: float = 0.0
     extras: dict = field(default_factory=dict)
+    nns: dict = field(default_factory=dict)   # trained network weights by chain name (hybrid models)
 
 
 class OptimizationProblem:
@@ -89,10 +103,28 @@ class OptimizationProblem:
     are calibrated within `[lb_pas, ub_pas]` (sequences in the order of `calibrated`, or mappings by name)."""
 
     def __init__(self, component: Component, input, target, *, metric: str = "NSE", warm_up: int = 1, lb_pas=None, ub_pas=None,
-                 fixed_params: Optional[Mapping] = None, default_initstates: Optional[Mapping] = None, config=None):
+                 fixed_params: Optional[Mapping] = None, default_initstates: Optional[Mapping] = None, config=None,
+                 initial_params: Optional[Mapping] = None):
         from .engine import METRICS, B200Model
         if metric.lower() not in METRICS:
             raise ValueError(f"Unknown metric: {metric}. Supported metrics: KGE, NSE, LogKGE, MSE")
+        # hybrid models: the network weights are part of the optimisation vector (`default_pas = get_initial_params(component)`
+        # or the caller's `initial_params`, `…OptimizationExt.jl:99-104`); `fixed_params` may also fix them (`nns=…`)
+        self.nn_names = list(component.get_nn_names())
+        ip = dict(initial_params) if initial_params else {}
+        nested = bool(fixed_params) and ("params" in fixed_params or "nns" in fixed_params)
+        fixed_nns = dict(fixed_params.get("nns", {})) if nested else {}
+        self.nns0 = {}
+        if self.nn_names:
+            chains = _chains_of(component)
+            given = dict(ip.get("nns", {}))
+            for nm in self.nn_names:
+                w = fixed_nns.get(nm, given.get(nm))
+                self.nns0[nm] = np.array(chains[nm].init_params() if w is None else w, dtype=np.float64)
+        self.fixed_nns = set(fixed_nns)
+        self.initial = {k: float(v) for k, v in dict(ip.get("params", {})).items()}
+        if nested:
+            fixed_params = fixed_params.get("params", {})
         self.component, self.metric, self.warm_up, self.config = component, metric, int(warm_up), config
         self.input = np.asarray(input, dtype=np.float64)
         self.target = np.asarray(target, dtype=np.float64)
@@ -107,6 +139,9 @@ class OptimizationProblem:
         self.calibrated: List[str] = [nm for nm in names if nm not in self.fixed]
 
         def bounds(b, what):
+            if b is None and (not self.calibrated or self.nn_names):
+                # nothing physical to calibrate, or a gradient run from `initial_params`: bounds are optional
+                return np.full(len(self.calibrated), -np.inf if what == "lb_pas" else np.inf)
             if b is None:
                 raise ValueError(f"{what} is required: the device optimiser samples inside the bounds")
             if isinstance(b, Mapping):
@@ -125,7 +160,10 @@ class OptimizationProblem:
         P = np.atleast_2d(np.asarray(P, dtype=np.float64))
         d = {nm: np.ascontiguousarray(P[:, j]) for j, nm in enumerate(self.calibrated)}
         d.update({k: np.array([v]) for k, v in self.fixed.items()})
-        return {"params": d}
+        out = {"params": d}
+        if self.nns0:
+            out["nns"] = self.nns0
+        return out
 
     def objective_batch(self, P) -> np.ndarray:
         """Objective of every row of `P[n, D]` (minimised: -NSE, -KGE, -LogKGE or MSE), one ensemble launch."""
@@ -216,6 +254,79 @@ def _solve_adam(prob: OptimizationProblem, alg: MultiStartAdam, maxiters: int, g
                     gpu_launches=per_eval * (maxiters + 1), elapsed_s=elapsed)
 
 
+def _chains_of(component) -> Dict[str, object]:
+    """Every Lux-style chain of a component tree by name (`NeuralFlux.chain`, the three networks of a `NeuralBucket`)."""
+    out: Dict[str, object] = {}
+
+    def walk(c):
+        for attr in ("chain", "flux_network", "state_network", "output_network"):
+            ch = getattr(c, attr, None)
+            if ch is not None and hasattr(ch, "init_params"):
+                out[ch.name] = ch
+        for attr in ("components", "fluxes", "dfluxes"):
+            for sub in getattr(c, attr, None) or ():
+                walk(sub)
+    walk(component)
+    return out
+
+
+def _solve_hybrid_adam(prob: OptimizationProblem, alg: Adam, maxiters: int) -> Solution:
+    """Adam over [calibrated physical parameters, network weights] of a hybrid model, gradients from the adjoint stepper."""
+    import time
+    m = prob.metric.lower()
+    if m not in ("sse", "mse", "nse"):
+        raise NotImplementedError("hybrid training uses the adjoint run: metric SSE, MSE or NSE")
+    trained = [nm for nm in prob.nn_names if nm not in prob.fixed_nns]
+    D = len(prob.calibrated)
+    missing = [nm for nm in prob.calibrated if nm not in prob.initial]
+    if missing:
+        raise ValueError(f"initial_params is missing the calibrated parameters {missing} (a gradient run starts from a point)")
+    x = np.concatenate([np.array([prob.initial[nm] for nm in prob.calibrated], dtype=np.float64)] + [prob.nns0[nm].copy() for nm in trained])
+    sizes = [prob.nns0[nm].size for nm in trained]
+    lb = np.concatenate([prob.lb, np.full(sum(sizes), -np.inf)])
+    ub = np.concatenate([prob.ub, np.full(sum(sizes), np.inf)])
+    init = prob.initstates
+    eng = prob.engine
+
+    def unpack(v):
+        pd = {nm: float(v[j]) for j, nm in enumerate(prob.calibrated)}
+        pd.update(prob.fixed)
+        nns, o = dict(prob.nns0), D
+        for nm, n in zip(trained, sizes):
+            nns[nm] = v[o:o + n]
+            o += n
+        return {"params": pd, "nns": nns}
+
+    def value_and_grad(v):
+        loss, g = eng.gradient_reverse(prob.input, unpack(v), prob.target, metric=prob.metric, warm_up=prob.warm_up, config=prob.config,
+                                       initstates=init)
+        gv = np.concatenate([np.array([np.sum(g[nm]) for nm in prob.calibrated], dtype=np.float64)] + [g["nns"][nm] for nm in trained])
+        return float(np.sum(loss)), gv
+
+    mom, vel = np.zeros_like(x), np.zeros_like(x)
+    hist, best_x, best = [], x.copy(), np.inf
+    t0 = time.perf_counter()
+    for it in range(1, maxiters + 1):
+        f, g = value_and_grad(x)
+        hist.append(f)
+        if f < best:
+            best, best_x = f, x.copy()
+        mom = alg.beta1 * mom + (1 - alg.beta1) * g
+        vel = alg.beta2 * vel + (1 - alg.beta2) * g * g
+        x = x - alg.lr * (mom / (1 - alg.beta1 ** it)) / (np.sqrt(vel / (1 - alg.beta2 ** it)) + alg.eps)
+        x = np.minimum(np.maximum(x, lb), ub)
+    f, _ = value_and_grad(x)
+    hist.append(f)
+    if f < best:
+        best, best_x = f, x.copy()
+    full = unpack(best_x)
+    sol = Solution(u=best_x, params=dict(full["params"]), objective=best, history=np.array(hist), n_evaluations=maxiters + 1,
+                   population=best_x[None, :], fitness=np.array([best]), gpu_launches=2 * (maxiters + 1),
+                   elapsed_s=time.perf_counter() - t0)
+    sol.nns = {k: np.array(v) for k, v in full["nns"].items()}
+    return sol
+
+
 def solve(prob: OptimizationProblem, alg=None, *, maxiters: int = 100) -> Solution:
     """`solve(prob, alg; maxiters)`: differential evolution on the device (default) — returns the best member after
     `maxiters` generations — or `MultiStartAdam` on the device gradients."""
@@ -223,6 +334,8 @@ def solve(prob: OptimizationProblem, alg=None, *, maxiters: int = 100) -> Soluti
     from .engine import DeviceBuffer, DeviceRun, check, lib
     if isinstance(alg, MultiStartAdam):
         return _solve_adam(prob, alg, maxiters)
+    if isinstance(alg, Adam):
+        return _solve_hybrid_adam(prob, alg, maxiters)
     alg = alg or DifferentialEvolution()
     adaptive = isinstance(alg, AdaptiveDifferentialEvolution)
     N, D = int(alg.popsize), len(prob.calibrated)

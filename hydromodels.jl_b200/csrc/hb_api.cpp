@@ -1075,7 +1075,7 @@ int hb_run_adjoint_device(hb_model_t m, const hb_adjoint_desc *d, void *stream) 
     if (!m || m->kind != 3) return fail(HB_ERR_INVALID, "not an adjoint model");
     if (!d || d->struct_size != (int32_t)sizeof(hb_adjoint_desc)) return fail(HB_ERR_INVALID, "hb_adjoint_desc.struct_size mismatch");
     const hb_adjoint_spec &s = m->aspec;
-    if (d->n_nodes <= 0 || d->n_steps < 0 || !d->target || !d->scale || !d->grad_params || !d->grad_init || !d->loss ||
+    if (d->n_nodes <= 0 || d->n_steps < 0 || !d->scale || !d->grad_params || !d->grad_init || !d->loss ||
         (s.n_inputs > 0 && !d->input) || (s.n_states > 0 && d->n_steps > 1 && !d->trajectory) || (s.nn_words > 0 && (!d->nn_params || !d->grad_nn)))
         return fail(HB_ERR_INVALID, "bad adjoint descriptor");
     if (d->warm_up < 1) return fail(HB_ERR_INVALID, "warm_up must be >= 1");

@@ -39,7 +39,7 @@ struct HbAdjArgs {
     const double *params;
     const int *htypes;
     const double *init;       // [S][N] initial states or NULL (zeros)
-    const double *target;     // [T] or [T][N]
+    const double *target;     // [T] or [T][N]; NULL: loss_n = scale_n * sum of the simulated values (no observations)
     const double *scale;      // [N] weight of the squared errors of node n (1: SSE, 1/n: MSE, 1/sum (obs - mean obs)^2: NSE)
     double *grad_params;      // [NP][N]   d loss_n / d p_j(n)
     double *grad_init;        // [S][N]    d loss_n / d u_s(0)
@@ -171,12 +171,15 @@ extern "C" __global__ void __launch_bounds__(HB_BLOCK) hb_adjoint(const __grid_c
 #pragma unroll
         for (int s = 0; s < HB_S; ++s)
             hb_u[s] = t > 0 ? a.traj[((t - 1) * a.N + nc) * HB_S + s] : (a.init ? a.init[(i64)s * a.N + nc] : 0.0);
-        const double obs = a.target_per_node ? a.target[t * a.N + nc] : a.target[t];
+        const double obs = !a.target ? 0.0 : (a.target_per_node ? a.target[t * a.N + nc] : a.target[t]);
         const bool counts = (t + 1 >= a.warm_up);
         double hb_sim = 0.0, hb_seed = 0.0;
         (void)hb_x; (void)hb_u;
 
-#define HB_SEED_STMT { const double e = hb_sim - obs; if (counts) { hb_seed = 2.0 * scale * e; loss = fma(scale * e, e, loss); } }
+        // target == NULL: the loss is the linear functional scale_n * sum_t sim_n(t) (the reference's own gradient tests
+        // differentiate `output[end, :] |> sum`, test/gradient/run_hybrid_gradient.jl:39-44)
+#define HB_SEED_STMT { const double e = hb_sim - obs; if (counts) { if (a.target) { hb_seed = 2.0 * scale * e; loss = fma(scale * e, e, loss); } \
+                                                                     else { hb_seed = scale; loss = fma(scale, hb_sim, loss); } } }
         //@@HB:STEP
 #undef HB_SEED_STMT
     }

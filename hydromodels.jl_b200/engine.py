@@ -943,7 +943,7 @@ class B200Model:
         flat, p_off, p_mode, htypes, uhw, kmax, nn = self.prepare(prog, params, N, ensemble=ensemble)
         uhw_flat = np.ascontiguousarray(np.concatenate(uhw, axis=0)) if uhw else None
         init = self._initstates(prog, initstates, N)
-        tgt = np.asarray(target, dtype=np.float64)
+        tgt = np.zeros(T) if (target is None and m == "sum") else np.asarray(target, dtype=np.float64)
         per_node = 0
         if tgt.ndim == 2:
             if tgt.shape != (N, T):
@@ -1040,14 +1040,14 @@ class B200Model:
         (`/root/reference/README.md:161-187`, `docs/src/tutorials/neuralnetwork_embeding.md`): what training the neural fluxes
         of a hybrid model (M50: 690 weights) needs.  `grads` holds every physical parameter (shape of `params["params"][name]`),
         every state's initial value (per node) and `grads["nns"][chain]` (flat, the layout of `params["nns"][chain]`, summed
-        over all nodes).  Metrics that are linear in the squared errors: SSE, MSE, NSE.  Multi-node models (3D input)."""
+        over all nodes).  Metrics that are linear in the squared errors: SSE, MSE, NSE — and SUM, the plain sum of the simulated
+        row from `warm_up` on (`target` may be None), which is what the reference's own gradient tests differentiate
+        (`test/gradient/run_hybrid_gradient.jl:39-44`: `output[end, :] |> sum`).  Single-node (2D input) and multi-node models."""
         m = metric.lower()
-        if m not in ("sse", "mse", "nse"):
-            raise NotImplementedError("the adjoint run covers SSE / MSE / NSE (metrics linear in the squared errors)")
+        if m not in ("sse", "mse", "nse", "sum"):
+            raise NotImplementedError("the adjoint run covers SSE / MSE / NSE (metrics linear in the squared errors) and SUM")
         if self.route is not None or self.precision != "f64":
             raise NotImplementedError("the adjoint run is for per-node models in Float64")
-        if not self.multinode:
-            raise NotImplementedError("the adjoint run takes multi-node models (give the components htypes; one node is N = 1)")
         cfg = normalize_config(config)
         input = np.asarray(input, dtype=np.float64)
         N, T = self._dims(input, False, None)
@@ -1061,7 +1061,7 @@ class B200Model:
         pdict = _as_componentvector(params)["params"]
         init = self._initstates(prog, initstates, N)
         S, NP = len(prog.state_names), len(prog.param_slots)
-        tgt = np.asarray(target, dtype=np.float64)
+        tgt = np.zeros(T) if (target is None and m == "sum") else np.asarray(target, dtype=np.float64)
         per_node = 0
         if tgt.ndim == 2:
             if tgt.shape != (N, T):
@@ -1073,7 +1073,7 @@ class B200Model:
         else:
             tgt2 = np.broadcast_to(tgt, (N, T))
         w = tgt2[:, warm_up - 1:]
-        if m == "sse":
+        if m in ("sse", "sum"):
             scale = np.ones(N)
         elif m == "mse":
             scale = np.full(N, 1.0 / w.shape[1])
@@ -1103,7 +1103,7 @@ class B200Model:
         d.htypes = bufs["ht"].ptr if "ht" in bufs else None
         d.initstates = bufs["init"].ptr if "init" in bufs else None
         d.nn_params = bufs["nn"].ptr if "nn" in bufs else None
-        d.target, d.target_per_node, d.warm_up = bufs["tgt"].ptr, per_node, int(warm_up)
+        d.target, d.target_per_node, d.warm_up = (None if m == "sum" else bufs["tgt"].ptr), per_node, int(warm_up)
         d.min_value = cfg.min_value
         d.scale, d.grad_params, d.grad_init = bufs["scale"].ptr, bufs["gp"].ptr, bufs["gi"].ptr
         d.grad_nn, d.loss = bufs["gn"].ptr, bufs["loss"].ptr

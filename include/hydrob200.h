@@ -258,7 +258,8 @@ typedef struct {
     const int32_t *htypes;
     const double *initstates;    /* [S][N] or NULL */
     const double *nn_params;     /* [nn_words] */
-    const double *target;        /* [T] or [T][N] */
+    const double *target;        /* [T] or [T][N]; NULL: loss_n = scale[n] * sum_{t >= warm_up} sim_n(t) — the linear functional the
+                                    reference's gradient tests differentiate (test/gradient/run_hybrid_gradient.jl:39-44) */
     int32_t target_per_node, warm_up;
     double min_value;
     const double *scale;         /* [N]: 1 (SSE), 1/count (MSE), 1/sum (obs - mean obs)^2 (NSE) */

@@ -95,3 +95,24 @@ def test_optimization_problem_keywords():
         cal.OptimizationProblem(model, inp, tgt, lb_pas=lb, ub_pas=ub, fixed_params=dict(nope=1.0))
     with pytest.raises(ValueError, match="entries"):
         cal.OptimizationProblem(model, inp, tgt, lb_pas=lb[:3], ub_pas=ub)
+
+
+def test_optimization_problem_of_a_hybrid_model_carries_the_network_weights():
+    """`default_pas = get_initial_params(component)` / `initial_params` and `fixed_params=ComponentVector(params=…)` of the
+    reference (`…OptimizationExt.jl:94-131`): with every physical parameter fixed the optimisation vector is the weights."""
+    model = hm.models.m50()
+    et, q = hm.models.m50_chains()
+    inp, tgt = np.zeros((3, 10)), np.zeros(10)
+    phys = {nm: 1.0 for nm in model.get_param_names()}
+    w = {"etnn": et.init_params(1), "qnn": q.init_params(2)}
+    prob = cal.OptimizationProblem(model, inp, tgt, metric="MSE", fixed_params={"params": phys}, initial_params={"nns": w})
+    assert prob.calibrated == [] and prob.nn_names == ["etnn", "qnn"] and prob.lb.size == 0
+    assert np.array_equal(prob.nns0["etnn"], w["etnn"]) and prob.nns0["qnn"].size == q.n_params
+    assert set(prob._params(np.zeros((1, 0)))) == {"params", "nns"}
+    # without `initial_params` the chains' own initialisers are used (Lux's default in the reference)
+    prob = cal.OptimizationProblem(model, inp, tgt, metric="MSE", fixed_params={"params": phys})
+    assert prob.nns0["etnn"].shape == (et.n_params,) and np.any(prob.nns0["etnn"] != 0)
+    # fixed networks stay out of the trained set
+    prob = cal.OptimizationProblem(model, inp, tgt, metric="MSE", fixed_params={"params": phys, "nns": {"qnn": w["qnn"]}})
+    assert prob.fixed_nns == {"qnn"} and np.array_equal(prob.nns0["qnn"], w["qnn"])
+    assert cal._chains_of(model).keys() == {"etnn", "qnn"}

@@ -96,3 +96,33 @@ def test_m50_weight_gradient_64_basins_120_steps(metric, shared):
         assert _rel(g["nns"][cname][ii], g_o["nns"][cname][ii]) < 1e-8, (cname, _rel(g["nns"][cname][ii], g_o["nns"][cname][ii]))
     for nm in model.param_names + ["soilwater"]:
         assert _rel(g[nm], g_o[nm]) < 1e-8, (nm, _rel(g[nm], g_o[nm]))
+
+
+def test_reference_hybrid_gradient_shape_single_basin_sum_of_flow():
+    """The reference's own hybrid gradient test (`/root/reference/test/gradient/run_hybrid_gradient.jl:1-45`): ONE basin of M50,
+    100 steps, `Zygote.gradient(pas) do p; m50_model(input, p; initstates)[end, :] |> sum; end` — the gradient of the summed
+    flow with respect to every physical parameter and all MLP weights.  Same call shape here (2D input, scalar parameters,
+    metric "SUM", no target), checked against the oracle's complex-step derivatives of the one-node model."""
+    T = 100
+    model = hm.models.m50()
+    et, q = hm.models.m50_chains()
+    p = {"params": {k: float(np.atleast_1d(v)[0]) for k, v in sy.parameters("m50", 0, 1).items()},
+         "nns": {"etnn": et.init_params(42) * 0.5, "qnn": q.init_params(42) * 0.5}}
+    inp = sy.forcing("m50", 0, 1, T)[:, 0, :]
+    init = {k: float(v) for k, v in sy.INIT["m50"].items()}
+    loss, g = hm.B200Model(model).gradient(inp, p, None, metric="SUM", initstates=init)
+    out = ho.run_model(model, inp, p, initstates=init)
+    assert np.allclose(loss, out[-1].sum(), rtol=1e-10)
+    model1 = hm.models.m50(htypes=[1])
+    p1 = {"params": {k: np.array([v]) for k, v in p["params"].items()}, "nns": p["nns"]}
+    names = list(model.param_names) + list(model.state_names) + ["nns"]
+    _, g_o = ho.loss_gradient(model1, inp[:, None, :], p1, np.zeros(T), metric="sum", initstates={k: np.array([v]) for k, v in init.items()},
+                              wrt=names)
+    for cname in ("etnn", "qnn"):
+        assert _rel(g["nns"][cname], g_o["nns"][cname]) < 1e-8, (cname, _rel(g["nns"][cname], g_o["nns"][cname]))
+    for nm in model.param_names + model.state_names:
+        assert _rel(g[nm], g_o[nm]) < 1e-8, (nm, _rel(g[nm], g_o[nm]))
+    assert isinstance(g["Tmin"], float)                       # scalar parameter -> scalar derivative
+    # warm_up: only the steps from warm_up on are summed
+    loss20, _ = hm.B200Model(model).gradient(inp, p, None, metric="SUM", warm_up=21, initstates=init)
+    assert np.allclose(loss20, out[-1][20:].sum(), rtol=1e-10)

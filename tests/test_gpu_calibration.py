@@ -235,3 +235,32 @@ def test_gradient_batch_and_multi_start_adam_recover_planted_parameters():
     assert np.all(np.diff(sol.history) <= 0)
     assert sol.objective < -0.97, sol.objective                       # NSE > 0.97 from gradients alone
     assert abs(prob.objective(sol.u) - sol.objective) < 1e-10 and sol.params["Tmin"] == -2.09
+
+
+def test_hybrid_training_with_adam_on_the_adjoint():
+    """The reference's hybrid-model workflow: physical parameters fixed, the two MLPs of M50 trained by Adam on reverse-mode
+    gradients (`OptimizationProblem(...; fixed_params=ComponentVector(params=…), adtype=AutoZygote())` + `solve(prob, Adam(lr))`).
+    Target = the flow of planted weights; start = those weights perturbed."""
+    T = 400
+    model = hm.models.m50()
+    et, q = hm.models.m50_chains()
+    phys = {k: float(np.atleast_1d(v)[0]) for k, v in sy.parameters("m50", 0, 1).items()}
+    truth = {"etnn": et.init_params(1) * 0.5, "qnn": q.init_params(2) * 0.5}
+    inp = sy.forcing("m50", 0, 1, T)[:, 0, :]
+    init = {k: float(v) for k, v in sy.INIT["m50"].items()}
+    target = ho.run_model(model, inp, {"params": phys, "nns": truth}, initstates=init)[-1]
+    rng = np.random.default_rng(0)
+    start = {k: v + rng.normal(0, 0.05, v.size) for k, v in truth.items()}
+    prob = cal.OptimizationProblem(model, inp, target, metric="MSE", warm_up=30, fixed_params={"params": phys},
+                                   initial_params={"nns": start}, default_initstates=init)
+    sol = cal.solve(prob, cal.Adam(lr=0.005), maxiters=120)
+    assert sol.history[0] > 0 and sol.objective < 0.05 * sol.history[0]          # the loss falls by more than 20x
+    assert sol.u.size == et.n_params + q.n_params and set(sol.nns) == {"etnn", "qnn"}
+    # the returned weights reproduce the returned objective through the forward engine
+    sim = hm.B200Model(model)(inp, {"params": phys, "nns": sol.nns}, initstates=init)[-1]
+    assert np.mean((sim[29:] - target[29:]) ** 2) == pytest.approx(sol.objective, rel=1e-9)
+    # one network fixed: only the other one moves
+    prob2 = cal.OptimizationProblem(model, inp, target, metric="MSE", warm_up=30, fixed_params={"params": phys, "nns": {"qnn": truth["qnn"]}},
+                                    initial_params={"nns": start}, default_initstates=init)
+    sol2 = cal.solve(prob2, cal.Adam(lr=0.005), maxiters=20)
+    assert sol2.u.size == et.n_params and np.array_equal(sol2.nns["qnn"], truth["qnn"]) and sol2.objective < sol2.history[0]
