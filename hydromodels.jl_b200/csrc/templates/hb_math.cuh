@@ -310,6 +310,7 @@ HB_DEV double hb_pow(double x, double y) {
 // handling differs from Julia's min/max (which propagate NaN) exactly as fmin/fmax would.
 HB_DEV double hb_min(double a, double b) { return a < b ? a : b; }
 HB_DEV double hb_max(double a, double b) { return a > b ? a : b; }
+HB_DEV double hb_relu(double x) { return hb_double2hiint(x) < 0 ? 0.0 : x; }          // max(0, x) by the sign bit (NaN with a clear sign bit stays NaN)
 // NNlib.leakyrelu = max(0.01 x, x): the larger one is x exactly when x's sign bit is clear, so the choice is an integer test of
 // the high word (ISETP + 2 SEL) instead of an FP64 compare (DSETP holds the issue port for two cycles) — same bits for every
 // non-NaN x, -0.0 included (0.01 * -0.0 = -0.0).
@@ -368,6 +369,7 @@ HB_DEV hb_dual hb_min(double a, const hb_dual &b) { return a < b.v ? hb_dual(a) 
 HB_DEV hb_dual hb_max(const hb_dual &a, const hb_dual &b) { return a.v > b.v ? a : b; }
 HB_DEV hb_dual hb_max(const hb_dual &a, double b) { return a.v > b ? a : hb_dual(b); }
 HB_DEV hb_dual hb_max(double a, const hb_dual &b) { return a > b.v ? hb_dual(a) : b; }
+HB_DEV hb_dual hb_relu(const hb_dual &a) { return hb_double2hiint(a.v) < 0 ? hb_dual(0.0) : a; }
 // x^y: d = y x^(y-1) dx + x^y log(x) dy (the log term is dropped at x <= 0 where the value is 0 / undefined)
 HB_DEV hb_dual hb_pow(const hb_dual &x, double y) { return hb_chain(x, hb_pow(x.v, y), y * hb_pow(x.v, y - 1.0)); }
 HB_DEV hb_dual hb_pow(double x, const hb_dual &y) {
@@ -398,5 +400,6 @@ HB_DEV float hb_step(float x) { return __frcp_rn(1.0f + expf(fminf(fmaxf(-10.0f 
 HB_DEV float hb_tanh(float x) { return fmaf(-2.0f, __frcp_rn(1.0f + expf(fminf(fmaxf(2.0f * x, -80.0f), 80.0f))), 1.0f); }
 HB_DEV float hb_min(float a, float b) { return a < b ? a : b; }
 HB_DEV float hb_max(float a, float b) { return a > b ? a : b; }
+HB_DEV float hb_relu(float x) { return fmaxf(x, 0.0f); }
 HB_DEV float hb_leakyrelu(float x) { return hb_max(0.01f * x, x); }
 #endif
