@@ -126,6 +126,37 @@ HB_DEV int hb_double2hiint(double x) {
     1.9360617934922943, 1.9413109895286405, 1.9465744175792332, 1.9518521162309783, \
     1.9571441241754002, 1.9624504802089273, 1.9677712232331759, 1.9731063922552343, \
     1.978456026387951, 1.9838201648502194, 1.9891988469672663, 1.9945921121709402
+// Polynomial / reduction constants whose double representation has a non-zero low word cannot be instruction immediates: as
+// literals the compiler re-materialises each of them with two UMOV / IMAD.MOV per use INSIDE the time loop (22 + ~10 of the
+// 246 instructions of an HBV step, 81 of ExpHydro's 451 — issue slots, and the issue port is what bounds these kernels).  Read
+// from a (non-const, so not foldable) __constant__ array they are c[bank][offset] operands of the DFMA itself: no instruction.
+#ifdef HB_HOST_TEST
+#define HB_KBANK static const double
+#else
+#define HB_KBANK __constant__ double
+#endif
+HB_KBANK hb_k[] = {
+    369.32993046757463,          //  0  256/ln2
+    -0.002707606166950427,       //  1  -ln2/256 high part
+    -7.111859369156821e-12,      //  2  -ln2/256 low part
+    4.16666666666666666667e-02,  //  3  1/24
+    1.66666666666666666667e-01,  //  4  1/6
+    738.6598609351493,           //  5  512/ln2
+    -0.0013538030834752135,      //  6  -ln2/512 high part
+    -3.5559296845784106e-12,     //  7  -ln2/512 low part
+    6.66666666666666666667e-01,  //  8  2/3
+    1.33333333333333333333e+00,  //  9  4/3
+    1.479819860511658591e-01,    // 10  log: Lg7
+    1.531383769920937332e-01,    // 11  Lg6
+    1.818357216161805012e-01,    // 12  Lg5
+    2.222219843214978396e-01,    // 13  Lg4
+    2.857142874366239149e-01,    // 14  Lg3
+    3.999999999940941908e-01,    // 15  Lg2
+    6.666666666666735130e-01,    // 16  Lg1
+    6.93147180369123816490e-01,  // 17  ln2 high part
+    1.90821492927058770002e-10,  // 18  ln2 low part
+    -0.0013538030870311431,      // 19  -ln2/512 in one double (HB_TANH_EXACT 0)
+};
 #ifdef HB_HOST_TEST
 static const double hb_exp2t[256] = {HB_EXP2_TABLE};
 static inline void hb_math_init() {}
@@ -168,13 +199,13 @@ HB_DEV double hb_clamp_abs(double x, int bound_hi) {
 // m = 2^(j/256) * exp(r) in [1, 2), k such that exp(x) = m * 2^k
 HB_DEV double hb_exp_reduce(double x, int &k) {
     const double MAGIC = 6755399441055744.0;               // 1.5 * 2^52: round-to-nearest-integer trick
-    double t = fma(x, 369.32993046757463, MAGIC);           // x * 256/ln2
+    double t = fma(x, hb_k[0], MAGIC);                      // x * 256/ln2
     const int ti = hb_double2loint(t);
     t -= MAGIC;
-    double r = fma(t, -0.002707606166950427, x);            // ln2/256 high part (a quarter of the ln2/64 split: t*hi exact)
-    r = fma(t, -7.111859369156821e-12, r);                  // ln2/256 low part
+    double r = fma(t, hb_k[1], x);                          // ln2/256 high part (a quarter of the ln2/64 split: t*hi exact)
+    r = fma(t, hb_k[2], r);                                 // ln2/256 low part
     k = ti >> 8;
-    double q = fma(r, 4.16666666666666666667e-02, 1.66666666666666666667e-01);   // |r| <= ln2/512: r^5/120 < 3.8e-17
+    double q = fma(r, hb_k[3], hb_k[4]);                    // 1/24, 1/6; |r| <= ln2/512: r^5/120 < 3.8e-17
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     q = fma(q, r, 1.0);                                      // exp(r)
@@ -217,13 +248,13 @@ HB_DEV double hb_step(double x) {
     int k;
     const double MAGIC = 6755399441055744.0;
     const double z = hb_clamp_abs(-10.0 * x, HB_HI_700);
-    double t = fma(z, 369.32993046757463, MAGIC);
+    double t = fma(z, hb_k[0], MAGIC);
     const int ti = hb_double2loint(t);
     t -= MAGIC;
-    double r = fma(t, -0.002707606166950427, z);
-    r = fma(t, -7.111859369156821e-12, r);
+    double r = fma(t, hb_k[1], z);
+    r = fma(t, hb_k[2], r);
     k = ti >> 8;
-    double q = fma(r, 4.16666666666666666667e-02, 1.66666666666666666667e-01);
+    double q = fma(r, hb_k[3], hb_k[4]);
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     q = fma(q, r, 1.0);
@@ -249,18 +280,18 @@ HB_DEV double hb_step(double x) {
 HB_DEV double hb_tanh(double x) {
     const double MAGIC = 6755399441055744.0;
     const double xc = hb_clamp_abs(x, HB_HI_350);
-    double t = fma(xc, 738.6598609351493, MAGIC);           // x * 512/ln2
+    double t = fma(xc, hb_k[5], MAGIC);                     // x * 512/ln2
     const int ti = hb_double2loint(t);
     t -= MAGIC;
 #if HB_TANH_EXACT
-    double r = fma(t, -0.0013538030834752135, xc);           // ln2/512 high part (an eighth of the ln2/64 split: exact)
-    r = fma(t, -3.5559296845784106e-12, r);                  // ln2/512 low part
-    double q = fma(r, 6.66666666666666666667e-01, 1.33333333333333333333e+00);   // e^(2r) = sum (2r)^n / n!, |2r| <= ln2/512
+    double r = fma(t, hb_k[6], xc);                          // ln2/512 high part (an eighth of the ln2/64 split: exact)
+    r = fma(t, hb_k[7], r);                                  // ln2/512 low part
+    double q = fma(r, hb_k[8], hb_k[9]);                     // 2/3, 4/3: e^(2r) = sum (2r)^n / n!, |2r| <= ln2/512
     q = fma(q, r, 2.0);
     q = fma(q, r, 2.0);
     q = fma(q, r, 1.0);
 #else
-    const double r = fma(t, -0.0013538030870311431, xc);     // |r| <= ln2/1024
+    const double r = fma(t, hb_k[19], xc);                   // |r| <= ln2/1024
     const float rf = (float)r;
     const float tail = (rf * rf) * fmaf(rf, fmaf(rf, 0.66666669f, 1.33333337f), 2.0f);
     const double q = fma(2.0, r, 1.0) + (double)tail;
@@ -285,16 +316,16 @@ HB_DEV double hb_log_pos(double x) {
     const double f = m - 1.0;
     const double s = f * hb_rcp(2.0 + f);
     const double z = s * s;
-    double R = fma(z, 1.479819860511658591e-01, 1.531383769920937332e-01);
-    R = fma(R, z, 1.818357216161805012e-01);
-    R = fma(R, z, 2.222219843214978396e-01);
-    R = fma(R, z, 2.857142874366239149e-01);
-    R = fma(R, z, 3.999999999940941908e-01);
-    R = fma(R, z, 6.666666666666735130e-01);
+    double R = fma(z, hb_k[10], hb_k[11]);
+    R = fma(R, z, hb_k[12]);
+    R = fma(R, z, hb_k[13]);
+    R = fma(R, z, hb_k[14]);
+    R = fma(R, z, hb_k[15]);
+    R = fma(R, z, hb_k[16]);
     R *= z;
     const double hfsq = 0.5 * f * f;
     const double dk = (double)k;
-    return fma(dk, 6.93147180369123816490e-01, f - (hfsq - fma(s, hfsq + R, dk * 1.90821492927058770002e-10)));
+    return fma(dk, hb_k[17], f - (hfsq - fma(s, hfsq + R, dk * hb_k[18])));
 }
 // pow(x, y) for x >= 0 (the models raise clamped, non-negative ratios to parameter exponents): exp(y log x), 0^y = 0 for y > 0,
 // x^0 = 1.  Relative error ~|y log x| * 1.2e-16 (the product is rounded once) — far inside the 1e-10 parity budget — at a
