@@ -327,9 +327,80 @@ def _solve_hybrid_adam(prob: OptimizationProblem, alg: Adam, maxiters: int) -> S
     return sol
 
 
-def solve(prob: OptimizationProblem, alg=None, *, maxiters: int = 100) -> Solution:
+def _solve_de_sharded(prob: OptimizationProblem, alg: DifferentialEvolution, maxiters: int, comm) -> Solution:
+    """DE/rand/1/bin with the population sharded over the ranks of `comm` (`parallel.LibComm`, one process per GPU): every rank
+    scores `popsize / world` members; one all-gather of the population per generation is the only communication
+    (`hb_de_trial_sharded_device`).  Same seed -> the single-GPU trajectory, bit for bit; every rank returns the same Solution."""
+    import time
+    from .engine import DeviceBuffer, DeviceRun, check, lib
+    world, rank = comm.world, comm.rank
+    N, D = int(alg.popsize), len(prob.calibrated)
+    if N % world or N // world < 1 or N < 4:
+        raise ValueError("the sharded search needs popsize to be a multiple of the number of ranks (and >= 4)")
+    if D == 0:
+        raise ValueError("nothing to calibrate: every parameter is fixed")
+    nl, m0 = N // world, rank * (N // world)
+    eng = prob.engine
+    uh_dev = eng._has_uh()
+    kmax = _uh_kmax_from_bounds(prob) if uh_dev else None
+    T = prob.input.shape[1]
+    rng = np.random.default_rng(alg.seed)
+    P0 = prob.lb + rng.random((N, D)) * (prob.ub - prob.lb)                     # the whole initial population, same on every rank
+    mine = P0[m0:m0 + nl]
+    init = None if prob.initstates is None else {k: np.full(nl, v) for k, v in prob.initstates.items()}
+    run = DeviceRun(eng, nl, T, prob._params(mine), config=prob.config, initstates=init, objective=prob.metric,
+                    target=prob.target, warm_up=prob.warm_up, ensemble=True, _kmax=kmax, uh_on_device=uh_dev)
+    slots = run.ck.program.param_slots
+    off_of = {nm: int(run._host[0][j]) for j, (nm, _) in enumerate(slots)}
+    missing = [nm for nm in prob.calibrated if nm not in off_of]
+    if missing:
+        raise KeyError(f"calibrated parameters {missing} are not used by the model's kernels")
+    dim_off = np.array([off_of[nm] for nm in prob.calibrated], dtype=np.int64)
+    trial = run.bufs["params"]
+    # pop_all[world][D][nl]: rank r's block = its members, parameter-major
+    blocks = np.ascontiguousarray(P0.reshape(world, nl, D).transpose(0, 2, 1))
+    pop_all = DeviceBuffer.from_host(blocks.ravel())
+    blk_bytes = D * nl * 8
+    my_block = pop_all.ptr + rank * blk_bytes
+    d_off, d_lb, d_ub = DeviceBuffer.from_host(dim_off), DeviceBuffer.from_host(prob.lb), DeviceBuffer.from_host(prob.ub)
+    fit, tfit = DeviceBuffer(nl * 8), DeviceBuffer(nl * 8)
+    hist, hist_all = DeviceBuffer((maxiters + 1) * 16), DeviceBuffer(world * (maxiters + 1) * 16)
+    fit_all = DeviceBuffer(N * 8)
+    inp = prob.input if prob.input.flags.f_contiguous else np.asfortranarray(prob.input)
+    d_in = DeviceBuffer.from_host(inp.ravel(order="K"))
+    L = lib()
+    t0 = time.perf_counter()
+    run.launch(d_in.ptr, fit.ptr, None)
+    check(L.hb_de_best_device(fit.ptr, nl, hist.ptr, 0, None))
+    launches = 3
+    for g in range(1, maxiters + 1):
+        check(L.hb_de_trial_sharded_device(pop_all.ptr, trial.ptr, d_off.ptr, D, nl, N, m0, d_lb.ptr, d_ub.ptr, float(alg.F), float(alg.CR),
+                                           C.c_uint64(alg.seed), g, None))
+        run.launch(d_in.ptr, tfit.ptr, None)
+        check(L.hb_de_select_sharded_device(my_block, trial.ptr, fit.ptr, tfit.ptr, d_off.ptr, D, nl, hist.ptr, g, None))
+        comm.all_gather(my_block, pop_all.ptr, blk_bytes, None)
+        launches += 5
+    comm.all_gather(fit.ptr, fit_all.ptr, nl * 8, None)
+    comm.all_gather(hist.ptr, hist_all.ptr, (maxiters + 1) * 16, None)
+    check(L.hb_stream_synchronize(None))
+    elapsed = time.perf_counter() - t0
+    fitness = fit_all.to_host((N,))
+    population = pop_all.to_host((world, D, nl)).transpose(0, 2, 1).reshape(N, D)
+    history = hist_all.to_host((world, maxiters + 1, 2))[:, :, 0].min(axis=0)
+    best = int(np.argmin(fitness))
+    params = dict(prob.fixed)
+    params.update({nm: float(population[best, j]) for j, nm in enumerate(prob.calibrated)})
+    for b in (pop_all, d_off, d_lb, d_ub, fit, tfit, hist, hist_all, fit_all, d_in):
+        b.free()
+    return Solution(u=population[best].copy(), params=params, objective=float(fitness[best]), history=history.copy(),
+                    n_evaluations=N * (maxiters + 1), population=population, fitness=fitness, gpu_launches=launches, elapsed_s=elapsed,
+                    extras={"world": world, "members_per_rank": nl, "all_gather_bytes_per_generation": blk_bytes * world})
+
+
+def solve(prob: OptimizationProblem, alg=None, *, maxiters: int = 100, comm=None) -> Solution:
     """`solve(prob, alg; maxiters)`: differential evolution on the device (default) — returns the best member after
-    `maxiters` generations — or `MultiStartAdam` on the device gradients."""
+    `maxiters` generations — or `MultiStartAdam` on the device gradients.  `comm` (`parallel.LibComm` of a multi-GPU job):
+    the population of a `DifferentialEvolution` search is sharded over its ranks."""
     import time
     from .engine import DeviceBuffer, DeviceRun, check, lib
     if isinstance(alg, MultiStartAdam):
@@ -337,6 +408,10 @@ def solve(prob: OptimizationProblem, alg=None, *, maxiters: int = 100) -> Soluti
     if isinstance(alg, Adam):
         return _solve_hybrid_adam(prob, alg, maxiters)
     alg = alg or DifferentialEvolution()
+    if comm is not None and getattr(comm, "world", 1) > 1:
+        if type(alg) is not DifferentialEvolution:
+            raise NotImplementedError("the sharded search covers DifferentialEvolution")
+        return _solve_de_sharded(prob, alg, maxiters, comm)
     adaptive = isinstance(alg, AdaptiveDifferentialEvolution)
     N, D = int(alg.popsize), len(prob.calibrated)
     if N < 4:

@@ -808,6 +808,82 @@ __global__ void __launch_bounds__(1024) hb_de_best_kernel(const double *__restri
 
 }  // namespace
 
+// ---- population sharded over the ranks of a communicator ("parameter sets sharded; no communication beyond an
+// NCCL gather") --------------------------------------------------------------------------------------------------------
+// Global member g lives on rank g / n_local at local index g % n_local.  Every rank holds the WHOLE population as
+// pop_all[world][D][n_local] — the ranks' blocks, refreshed by one all-gather per generation (hb_comm_all_gather, D * N * 8
+// bytes: 3 MB for 65 536 members x 6 parameters) — because DE/rand/1 draws its parents from all members; trials, objectives
+// and the selection stay local.  Draws are keyed by the GLOBAL member index, so the trajectory is the single-GPU one, bit for bit.
+namespace {
+
+__global__ void __launch_bounds__(256) hb_de_trial_sharded_kernel(const double *__restrict__ pop_all, double *__restrict__ trial,
+                                                                  const long long *__restrict__ dim_off, int D, int n_local, int N, int member0,
+                                                                  const double *__restrict__ lb, const double *__restrict__ ub, double F,
+                                                                  double CR, unsigned long long seed, unsigned gen) {
+    const int il = blockIdx.x * 256 + threadIdx.x;
+    if (il >= n_local) return;
+    const int i = member0 + il;
+    int o1 = 1 + (int)(hb_de_uniform(seed, gen, i, 0) * (N - 1));
+    int o2 = 1 + (int)(hb_de_uniform(seed, gen, i, 1) * (N - 2));
+    int o3 = 1 + (int)(hb_de_uniform(seed, gen, i, 2) * (N - 3));
+    if (o1 > N - 1) o1 = N - 1;
+    if (o2 > N - 2) o2 = N - 2;
+    if (o3 > N - 3) o3 = N - 3;
+    if (o2 >= o1) ++o2;
+    const int lo = o1 < o2 ? o1 : o2, hi = o1 < o2 ? o2 : o1;
+    if (o3 >= lo) ++o3;
+    if (o3 >= hi) ++o3;
+    const int r1 = (i + o1) % N, r2 = (i + o2) % N, r3 = (i + o3) % N;
+    int jrand = (int)(hb_de_uniform(seed, gen, i, 3) * D);
+    if (jrand > D - 1) jrand = D - 1;
+    const size_t blk = (size_t)D * n_local;
+    auto at = [&](int g, int d) { return pop_all[(size_t)(g / n_local) * blk + (size_t)d * n_local + (g % n_local)]; };
+    for (int d = 0; d < D; ++d) {
+        double v = at(i, d);
+        if (hb_de_uniform(seed, gen, i, 4 + d) < CR || d == jrand) v = __dadd_rn(at(r1, d), __dmul_rn(F, __dsub_rn(at(r2, d), at(r3, d))));
+        v = v < lb[d] ? lb[d] : v;
+        v = v > ub[d] ? ub[d] : v;
+        trial[dim_off[d] + il] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) hb_de_select_sharded_kernel(double *__restrict__ pop_block, const double *__restrict__ trial,
+                                                                   double *__restrict__ fit, const double *__restrict__ trial_fit,
+                                                                   const long long *__restrict__ dim_off, int D, int n_local) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_local) return;
+    const double tf = trial_fit[i], f = fit[i];
+    if (tf <= f || (f != f && tf == tf)) {
+        fit[i] = tf;
+        for (int d = 0; d < D; ++d) pop_block[(size_t)d * n_local + i] = trial[dim_off[d] + i];
+    }
+}
+
+}  // namespace
+
+extern "C" int hb_de_trial_sharded_device(const double *pop_all, double *trial, const int64_t *dim_offset, int n_dims, int n_local, int n_total,
+                                          int member0, const double *lower, const double *upper, double F, double CR, uint64_t seed,
+                                          uint32_t generation, void *stream) {
+    if (!pop_all || !trial || !dim_offset || !lower || !upper || n_dims <= 0 || n_local <= 0 || n_total < 4 || n_total % n_local ||
+        member0 < 0 || member0 % n_local || member0 + n_local > n_total)
+        return HB_ERR_INVALID;
+    hb_de_trial_sharded_kernel<<<(n_local + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pop_all, trial, (const long long *)dim_offset, n_dims,
+                                                                                      n_local, n_total, member0, lower, upper, F, CR, seed,
+                                                                                      generation);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
+extern "C" int hb_de_select_sharded_device(double *pop_block, const double *trial, double *fitness, const double *trial_fitness,
+                                           const int64_t *dim_offset, int n_dims, int n_local, double *history, int history_slot,
+                                           void *stream) {
+    if (!pop_block || !trial || !fitness || !trial_fitness || !dim_offset || n_dims <= 0 || n_local <= 0 || fitness == trial_fitness)
+        return HB_ERR_INVALID;
+    hb_de_select_sharded_kernel<<<(n_local + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pop_block, trial, fitness, trial_fitness,
+                                                                                       (const long long *)dim_offset, n_dims, n_local);
+    if (history) hb_de_best_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(fitness, n_local, history, history_slot);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
 // ---- adaptive DE: BlackBoxOptim.jl's `adaptive_de_rand_1_bin_radiuslimited` (the optimiser of every example of the
 // reference: ext/HydroModelsOptimizationExt/examples.jl:28, docs/src/tutorials/optimimal_parameters.md:189-195; the package
 // itself is a dependency that is not vendored under /root/reference — its published operators are restated here),

@@ -160,6 +160,10 @@ def lib():
         "hb_irf_reduce_segments_device": [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
         "hb_irf_gather_rows_device": [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p],
         "hb_de_best_device": [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p],
+        "hb_de_trial_sharded_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_double, C.c_double, C.c_uint64, C.c_uint32, C.c_void_p],
+        "hb_de_select_sharded_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_int32, C.c_void_p],
         "hb_ade_init_device": [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p],
         "hb_ade_trial_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p],

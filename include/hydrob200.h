@@ -418,6 +418,19 @@ int hb_de_select_device(double *pop, const double *trial, double *fitness, const
  * (generation 0 bookkeeping: no selection). */
 int hb_de_best_device(const double *fitness, int32_t n_members, double *history, int32_t history_slot, void *stream);
 
+/* The same DE with the population SHARDED over the ranks of a communicator (one process per GPU): global member g lives on rank
+ * g / n_local at local index g % n_local; every rank holds the whole population as pop_all[world][n_dims][n_local] (the ranks'
+ * blocks, refreshed by ONE hb_comm_all_gather per generation — the only communication) because the parents come from all
+ * members; trials are written where the local stepper reads its parameters, objectives and selection stay local
+ * (`pop_block` = pop_all + rank * n_dims * n_local; `history`: this rank's best).  Draws are keyed by the global member index,
+ * so the search follows the single-GPU trajectory bit for bit.  n_total % n_local == 0, member0 = rank * n_local. */
+int hb_de_trial_sharded_device(const double *pop_all, double *trial, const int64_t *dim_offset, int32_t n_dims, int32_t n_local,
+                               int32_t n_total, int32_t member0, const double *lower, const double *upper, double F, double CR,
+                               uint64_t seed, uint32_t generation, void *stream);
+int hb_de_select_sharded_device(double *pop_block, const double *trial, double *fitness, const double *trial_fitness,
+                                const int64_t *dim_offset, int32_t n_dims, int32_t n_local, double *history, int32_t history_slot,
+                                void *stream);
+
 /* Adaptive DE — BlackBoxOptim.jl's `adaptive_de_rand_1_bin_radiuslimited`, the optimiser the reference's examples pass to
  * `solve` (ext/HydroModelsOptimizationExt/examples.jl:28, docs/src/tutorials/optimimal_parameters.md:189-195), generation-
  * synchronous: per-member F and CR (`f`, `cr`: DEVICE [n_members], drawn by hb_ade_init_device; a member whose trial did not

@@ -263,3 +263,60 @@ def test_panelled_run_on_one_gpu_matches_the_single_kernel(R, Cc, T, K, halo):
             cells = np.unique(bad[:, 1])
             raise AssertionError(f"rep {rep}: {len(bad)} values differ; rows {np.unique(bad[:, 0])}, steps {np.unique(bad[:, 2])[:10]}, grid columns "
                                  f"{np.unique(cells % Cc)[:20]}, grid rows {np.unique(cells // Cc)[:10]}, first {bad[0]}: {got[tuple(bad[0])]!r} vs {whole[tuple(bad[0])]!r}")
+
+
+def _de_problem():
+    from hydromodels_jl_b200 import calibration as cal
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import hydro_oracle as ho
+    T = 500
+    model = hm.models.exphydro()
+    inp = sy.forcing("exphydro", 0, 1, T)[:, 0, :]
+    truth = np.array([-2.1, 0.2, 2.7, 1500.0, 18.0, 0.017])
+    lb, ub = np.array([-3.0, 0.0, 0.5, 500.0, 5.0, 0.005]), np.array([0.0, 3.0, 5.0, 2500.0, 40.0, 0.05])
+    init = dict(snowpack=0.0, soilwater=1303.0)
+    target = ho.run_model(model, inp, {"params": dict(zip(model.get_param_names(), truth))}, initstates=init)[-1]
+    return cal, cal.OptimizationProblem(model, inp, target, metric="NSE", warm_up=30, lb_pas=lb, ub_pas=ub, default_initstates=init)
+
+
+def _de_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from hydromodels_jl_b200 import parallel as par
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    hm.engine.init(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    comm = par.LibComm(rank, world)
+    cal, prob = _de_problem()
+    sol = cal.solve(prob, cal.DifferentialEvolution(popsize=512, seed=9), maxiters=25, comm=comm)
+    q.put((rank, sol.history, sol.population, sol.fitness, sol.extras))
+    dist.barrier()
+    comm.free()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_sharded_differential_evolution_follows_the_single_gpu_trajectory():
+    """Population sharded over the ranks (`hb_de_trial_sharded_device` + one all-gather per generation): the history, the final
+    population and the objectives equal the single-GPU search with the same seed bit for bit, on every rank."""
+    import torch.multiprocessing as mp
+    world = min(_ngpu(), 4)
+    while 512 % world:
+        world -= 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 34500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_de_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    got = [q.get(timeout=600) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    cal, prob = _de_problem()
+    single = cal.solve(prob, cal.DifferentialEvolution(popsize=512, seed=9), maxiters=25)
+    for rank, hist, pop, fit, extras in got:
+        assert np.array_equal(hist, single.history), rank
+        assert np.array_equal(pop, single.population) and np.array_equal(fit, single.fitness)
+        assert extras["world"] == world and extras["all_gather_bytes_per_generation"] == 512 * 6 * 8
