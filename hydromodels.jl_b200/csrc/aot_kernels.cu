@@ -254,15 +254,14 @@ __device__ __forceinline__ void hb_cp_async8(void *smem_dst, const void *gsrc, b
 }
 
 #ifndef HB_IRF_TT
-#define HB_IRF_TT 16                                   // time steps per thread
+#define HB_IRF_TT 32                                   // time steps per thread (default; 8 | 16 | 32 through the environment variable HB_IRF_TT)
 #endif
-template <int HP>
+template <int HP, int TT>
 __global__ void __launch_bounds__(256) hb_sparse_conv_tiled(int n_out, int n_in, long long T, int H, long long nnz,
                                                             const int *__restrict__ row_ptr, const int *__restrict__ src,
                                                             const double *__restrict__ w, const double *__restrict__ in,
                                                             const double *__restrict__ xt, long long Tp,
                                                             const int *__restrict__ order, double *__restrict__ out) {
-    constexpr int TT = HB_IRF_TT;
     constexpr int BT = 8 * TT;                         // time steps per block (8 warps)
     constexpr int WP = BT + HP;                        // staged input window: steps [t_blk - HP, t_blk + BT)
     extern __shared__ __align__(16) double hb_irf_smem[];
@@ -389,13 +388,14 @@ double *g_irf_ws = nullptr;
 size_t g_irf_cap = 0;
 std::mutex g_irf_mu;      // growth + the launches that use the workspace are one critical section (calls are serialised per process)
 
-template <int HP>
-int hb_launch_conv_tiled(dim3 grid, cudaStream_t st, int n_out, int n_in, long long T, int H, long long nnz, const int *row_ptr,
+template <int HP, int TT>
+int hb_launch_conv_tiled(cudaStream_t st, int n_out, int n_in, long long T, int H, long long nnz, const int *row_ptr,
                          const int *src, const double *w, const double *in, const int *order, double *out) {
-    constexpr int BT = 8 * HB_IRF_TT;
+    constexpr int BT = 8 * TT;
+    const dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((T + BT - 1) / BT));
     const int smem = (2 * (BT + HP) * 33 + 2 * HP * 32) * 8;
     // per device and per context: set on every call (a host-side attribute write, negligible next to the launch)
-    if (cudaFuncSetAttribute(hb_sparse_conv_tiled<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HB_ERR_CUDA;
+    if (cudaFuncSetAttribute(hb_sparse_conv_tiled<HP, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HB_ERR_CUDA;
     const double *xt = nullptr;
     std::lock_guard<std::mutex> lk(g_irf_mu);
     const long long Tp = (long long)grid.y * BT + HP;              // every block's window [t_blk, t_blk + BT + HP) in padded steps
@@ -414,7 +414,7 @@ int hb_launch_conv_tiled(dim3 grid, cudaStream_t st, int n_out, int n_in, long l
             xt = g_irf_ws;
         }
     }
-    hb_sparse_conv_tiled<HP><<<grid, 256, smem, st>>>(n_out, n_in, T, H, nnz, row_ptr, src, w, in, xt, Tp, order, out);
+    hb_sparse_conv_tiled<HP, TT><<<grid, 256, smem, st>>>(n_out, n_in, T, H, nnz, row_ptr, src, w, in, xt, Tp, order, out);
     return HB_OK;
 }
 }  // namespace
@@ -435,10 +435,18 @@ extern "C" int hb_sparse_route_conv_ordered_device(int n_out, int n_in, int64_t 
         dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((T + 7) / 8));
         hb_sparse_conv_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_out, n_in, T, H, nnz, row_ptr, src, weights, input, out);
     } else {
-        dim3 grid((unsigned)((n_out + 31) / 32), (unsigned)((T + 8 * HB_IRF_TT - 1) / (8 * HB_IRF_TT)));
         const int32_t *order = getenv("HB_IRF_NO_ORDER") ? nullptr : dest_order;
-        const int rc = H <= 32 ? hb_launch_conv_tiled<32>(grid, (cudaStream_t)stream, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, order, out)
-                               : hb_launch_conv_tiled<64>(grid, (cudaStream_t)stream, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, order, out);
+        // time steps per thread: 16 (128-step tiles, 100 / 134 KB of shared memory: 2 / 1 blocks per SM) or 8 (64-step tiles, 67 / 100 KB:
+        // 3 / 2 blocks per SM) — HB_IRF_TT overrides the default
+        const int tt = getenv("HB_IRF_TT") ? atoi(getenv("HB_IRF_TT")) : HB_IRF_TT;
+        cudaStream_t st = (cudaStream_t)stream;
+        int rc;
+        if (H <= 32) rc = tt == 8 ? hb_launch_conv_tiled<32, 8>(st, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, order, out)
+                        : tt == 32 ? hb_launch_conv_tiled<32, 32>(st, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, order, out)
+                                   : hb_launch_conv_tiled<32, 16>(st, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, order, out);
+        else rc = tt == 8 ? hb_launch_conv_tiled<64, 8>(st, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, order, out)
+                : tt == 32 ? hb_launch_conv_tiled<64, 32>(st, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, order, out)
+                           : hb_launch_conv_tiled<64, 16>(st, n_out, n_in, T, H, nnz, row_ptr, src, weights, input, order, out);
         if (rc) return rc;
     }
     return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
