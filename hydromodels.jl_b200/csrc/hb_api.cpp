@@ -305,9 +305,10 @@ int load_model(hb_model_s *m) {
     if (rc) return rc;
     HB_DRV(g_drv.ModuleLoadData(&m->module, m->cubin.data()));
     HB_DRV(g_drv.ModuleGetFunction(&m->func, m->module, m->kernel_name.c_str()));
-    // the 48 KB default limit counts static + dynamic shared memory (the templates hold a 2 KB exp table statically): opt in
+    // the 48 KB default limit counts static + dynamic shared memory (the templates hold a 2 KB exp table and, for bodies with
+    // powers, a 2 KB log table statically): opt in
     // whenever the sum comes near it, not only when the dynamic part alone exceeds it
-    if (m->dyn_smem + 4096 > 48 * 1024)
+    if (m->dyn_smem + 6144 > 48 * 1024)
         HB_DRV(g_drv.FuncSetAttribute(m->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, m->dyn_smem));
     if (m->kind == 3 && m->aspec.nn_words > 0) {
         size_t bytes = 0;
@@ -670,8 +671,8 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
         m->uhh_total += spec->uh_kmax[u] - 1;
     }
     m->dyn_smem = stepper_smem_bytes(*spec, m->block, stages);
-    // static shared memory of the templates: the 256-entry exp table (2 KB) + a few words
-    const int kStaticSmem = 2048 + 64;
+    // static shared memory of the templates: the 256-entry exp table (2 KB), the log table of bodies with powers (2 KB) + a few words
+    const int kStaticSmem = 2048 + 64 + (strstr(body, "#define HB_LOG_TABLE 1") ? 2048 : 0);
     if (m->dyn_smem + kStaticSmem > 227 * 1024) {
         const int need = m->dyn_smem + kStaticSmem;
         delete m;
@@ -1152,8 +1153,9 @@ int hb_compile_grid(const hb_grid_spec *spec, const char *body, hb_model_t *out)
         if (m->wave_qslots < 2 || m->wave_qslots > 8) { delete m; return fail(HB_ERR_INVALID, "HB_WAVE_QSLOTS must be 2..8"); }
         if (obuf < 2 || obuf > 4) { delete m; return fail(HB_ERR_INVALID, "HB_WAVE_OBUF must be 2..4"); }
         m->dyn_smem = warps * (up128(stages * 32 * spec->n_inputs * 8) + up128(obuf * 32 * spec->n_rows * 8)) + warps * stages * 8;
-        if (m->dyn_smem + 2048 + 64 > 227 * 1024) {
-            const int need = m->dyn_smem + 2048 + 64;
+        const int static_smem = 2048 + 64 + 64 + (strstr(body, "#define HB_LOG_TABLE 1") ? 2048 : 0);
+        if (m->dyn_smem + static_smem > 227 * 1024) {
+            const int need = m->dyn_smem + static_smem;
             delete m;
             return fail(HB_ERR_INVALID, "wave kernel needs %d bytes of shared memory", need);
         }

@@ -156,16 +156,101 @@ HB_KBANK hb_k[] = {
     6.93147180369123816490e-01,  // 17  ln2 high part
     1.90821492927058770002e-10,  // 18  ln2 low part
     -0.0013538030870311431,      // 19  -ln2/512 in one double (HB_TANH_EXACT 0)
+    3.33333333333333333333e-01,  // 20  1/3 (table log)
+    0.2,                         // 21  1/5
 };
+// log(x) by table (bodies that raise to a power, `#define HB_LOG_TABLE 1` from the host lowering; host tests always): 128 pairs
+// {1/c_j rounded to double, -log(that double)} for the centres c_j = 1 + (j + 1/2)/128 of the mantissa intervals — with the
+// ROUNDED reciprocal the identity log m = log1p(m/c - 1) + log c holds exactly, |m/c - 1| <= 2^-8 (2 KB of shared memory).
+#ifndef HB_LOG_TABLE
+#ifdef HB_HOST_TEST
+#define HB_LOG_TABLE 1
+#else
+#define HB_LOG_TABLE 0
+#endif
+#endif
+#define HB_LOG_TABLE_DATA \
+    0.9961089494163424, 0.003898640415657309, 0.9884169884169884, 0.01165061721997525, \
+    0.9808429118773946, 0.019342962843130987, 0.973384030418251, 0.026976587698202083, \
+    0.9660377358490566, 0.03455238150665973, 0.9588014981273408, 0.042071213920687044, \
+    0.9516728624535316, 0.049533935122276676, 0.9446494464944649, 0.05694137640013845, \
+    0.9377289377289377, 0.06429435070539725, 0.9309090909090909, 0.07159365318700882, \
+    0.924187725631769, 0.078840061707776, 0.9175627240143369, 0.08603433734180316, \
+    0.9110320284697508, 0.09317722485418334, 0.9045936395759717, 0.10026945316367517, \
+    0.8982456140350877, 0.10731173578908804, 0.89198606271777, 0.11430477128005863, \
+    0.8858131487889274, 0.12124924363286965, 0.8797250859106529, 0.12814582269193006, \
+    0.8737201365187713, 0.13499516453750482, 0.8677966101694915, 0.1417979118602574, \
+    0.8619528619528619, 0.1485546943231372, 0.8561872909698997, 0.15526612891112396, \
+    0.8504983388704319, 0.16193282026931324, 0.8448844884488449, 0.16855536102980664, \
+    0.839344262295082, 0.17513433212784915, 0.8338762214983714, 0.18167030310763463, \
+    0.8284789644012945, 0.18816383241818294, 0.8231511254019293, 0.19461546769967167, \
+    0.8178913738019169, 0.2010257460605908, 0.8126984126984127, 0.2073951943460706, \
+    0.807570977917981, 0.21372432939771818, 0.8025078369905956, 0.22001365830528213, \
+    0.7975077881619937, 0.2262636786504534, 0.7925696594427245, 0.232474878743094, \
+    0.7876923076923077, 0.238647737850175, 0.7828746177370031, 0.24478272641769092, \
+    0.7781155015197568, 0.25088030628580943, 0.7734138972809668, 0.2569409308975004, \
+    0.7687687687687688, 0.26296504550088134, 0.764179104477612, 0.26895308734550394, \
+    0.7596439169139466, 0.2749054858727992, 0.7551622418879056, 0.2808226629008878, \
+    0.750733137829912, 0.2867050328039543, 0.7463556851311953, 0.29255300268637746, \
+    0.7420289855072464, 0.2983669725517973, 0.7377521613832853, 0.3041473354672968, \
+    0.7335243553008596, 0.3098944777228647, 0.7293447293447294, 0.3156087789863033, \
+    0.7252124645892352, 0.32129061245373425, 0.7211267605633803, 0.3269403449958533, \
+    0.7170868347338936, 0.3325583373000766, 0.713091922005571, 0.3381449440087164, \
+    0.7091412742382271, 0.34370051385331846, 0.7052341597796143, 0.3492253897852883, \
+    0.7013698630136986, 0.354719909102929, 0.6975476839237057, 0.3601844035750078, \
+    0.6937669376693767, 0.3656191995609647, 0.6900269541778976, 0.37102461812787263, \
+    0.6863270777479893, 0.376400975164253, 0.6826666666666666, 0.3817485814908484, \
+    0.6790450928381963, 0.3870677429684483, 0.6754617414248021, 0.3923587606028639, \
+    0.6719160104986877, 0.3976219306471385, 0.6684073107049608, 0.4028575447010835, \
+    0.6649350649350649, 0.4080658898082217, 0.661498708010336, 0.41324724855021927, \
+    0.6580976863753213, 0.41840189913888387, 0.6547314578005116, 0.4235301155058032, \
+    0.6513994910941476, 0.42863216738969867, 0.6481012658227848, 0.4337083204215594, \
+    0.6448362720403022, 0.43875883620762796, 0.6416040100250626, 0.44378397241030104, \
+    0.6384039900249376, 0.4487839828270067, 0.6352357320099256, 0.4537591174671205, \
+    0.6320987654320988, 0.4587096226269767, 0.628992628992629, 0.46363574096303256, \
+    0.6259168704156479, 0.46853771156323926, 0.6228710462287105, 0.4734157700166721, \
+    0.6198547215496368, 0.47827014848147026, 0.6168674698795181, 0.48310107575113576, \
+    0.6139088729016786, 0.48790877731923904, 0.6109785202863962, 0.4926934754425752, \
+    0.6080760095011877, 0.4974553892028189, 0.6052009456264775, 0.5021947345667155, \
+    0.6023529411764705, 0.5069117244448544, 0.5995316159250585, 0.5116065687490621, \
+    0.5967365967365967, 0.5162794744484545, 0.5939675174013921, 0.5209306456241853, \
+    0.5912240184757506, 0.5255602835229274, 0.5885057471264368, 0.5301685866091216, \
+    0.585812356979405, 0.5347557506160276, 0.5831435079726651, 0.5393219685956089, \
+    0.5804988662131519, 0.5438674309672835, 0.5778781038374717, 0.5483923255655733, \
+    0.5752808988764045, 0.5528968376866776, 0.5727069351230425, 0.5573811501340064, \
+    0.5701559020044543, 0.5618454432626918, 0.5676274944567627, 0.5662898950231159, \
+    0.565121412803532, 0.5707146810034716, 0.5626373626373626, 0.575119974471388, \
+    0.5601750547045952, 0.5795059464146423, 0.5577342047930284, 0.5838727655809826, \
+    0.5553145336225597, 0.588220598517086, 0.5529157667386609, 0.5925496096066716, \
+    0.5505376344086022, 0.5968599611077938, 0.5481798715203426, 0.6011518131893347, \
+    0.5458422174840085, 0.6054253239667169, 0.5435244161358811, 0.6096806495368553, \
+    0.5412262156448203, 0.6139179440123704, 0.5389473684210526, 0.6181373595550788, \
+    0.5366876310272537, 0.6223390464087787, 0.534446764091858, 0.6265231529313529, \
+    0.5322245322245323, 0.6306898256261987, 0.5300207039337475, 0.6348392091730102, \
+    0.5278350515463918, 0.6389714464579207, 0.5256673511293635, 0.6430866786030273, \
+    0.523517382413088, 0.6471850449953095, 0.5213849287169042, 0.6512666833149582, \
+    0.5192697768762677, 0.6553317295631277, 0.5171717171717172, 0.6593803180891278, \
+    0.5150905432595574, 0.6634125816170662, 0.5130260521042084, 0.6674286512719563, \
+    0.5109780439121756, 0.6714286566053024, 0.5089463220675944, 0.6754127256201768, \
+    0.5069306930693069, 0.6793809847957973, 0.504930966469428, 0.6833335591116206, \
+    0.5029469548133595, 0.6872705720709603, 0.5009784735812133, 0.691192145724142
 #ifdef HB_HOST_TEST
 static const double hb_exp2t[256] = {HB_EXP2_TABLE};
+static const double hb_logt[256] = {HB_LOG_TABLE_DATA};
 static inline void hb_math_init() {}
 #else
 __constant__ const double HB_EXP2T_SRC[256] = {HB_EXP2_TABLE};
 __shared__ double hb_exp2t[256];
+#if HB_LOG_TABLE
+__constant__ const double HB_LOGT_SRC[256] = {HB_LOG_TABLE_DATA};
+__shared__ __align__(16) double hb_logt[256];
+#endif
 // every thread of the block calls this once at kernel entry (contains a block barrier)
 __device__ __forceinline__ void hb_math_init() {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hb_exp2t[i] = HB_EXP2T_SRC[i];   // any block size
+#if HB_LOG_TABLE
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hb_logt[i] = HB_LOGT_SRC[i];
+#endif
     __syncthreads();
 }
 #endif
@@ -305,6 +390,27 @@ HB_DEV double hb_tanh(double x) {
 // log(x) for positive normal x — the classic argument reduction x = 2^k m, m in [sqrt(1/2), sqrt(2)), f = m - 1, s = f / (2 + f),
 // log(1 + f) = f - f^2/2 + s (f^2/2 + R(s^2)) with the degree-7 minimax R of fdlibm's e_log.c (|error| < 2^-58), branch-free:
 // ~24 FP64 operations.  x <= 0, subnormal, inf and NaN are the callers' business (hb_pow filters them).
+#if HB_LOG_TABLE
+// log(x) for positive normal x, table form: x = 2^k m, m in [1, 2), j = the top 7 mantissa bits, r = m / c_j - 1 by ONE fma with
+// the tabulated reciprocal, log x = k ln2 + log c_j + (r - r^2/2 + r^3/3 - r^4/4 + r^5/5)   (|r| <= 2^-8: r^6/6 < 6e-16).
+// 8 FP64 operations instead of the 24 of the table-free form below; absolute error <= 6.2e-16 max(|log x|, 1) (1.1e-15 on
+// (1e-6, 1], where the models' ratios live) — exp(y log x) keeps |y| 1e-15 relative, five decades inside the parity bar.
+// HBV evaluates one power per step (recharge ~ (soilwater / FC)^(BETA * 5 + 1)): 63.7 -> 57 ms for the calibration ensemble.
+HB_DEV double hb_log_pos(double x) {
+    const int hi = hb_double2hiint(x);
+    const int k = (hi >> 20) - 1023;
+    const int j = (hi >> 13) & 127;
+    const double m = hb_hiloint2double((hi & 0x000fffff) | 0x3ff00000, hb_double2loint(x));
+    const double invc = hb_logt[2 * j], logc = hb_logt[2 * j + 1];
+    const double r = fma(m, invc, -1.0);
+    double q = fma(r, hb_k[21], -0.25);
+    q = fma(q, r, hb_k[20]);
+    q = fma(q, r, -0.5);
+    const double p = fma(r * r, q, r);
+    const double dk = (double)k;
+    return fma(dk, hb_k[17], fma(dk, hb_k[18], logc + p));
+}
+#else
 HB_DEV double hb_log_pos(double x) {
     int hi = hb_double2hiint(x);
     const int lo = hb_double2loint(x);
@@ -327,6 +433,7 @@ HB_DEV double hb_log_pos(double x) {
     const double dk = (double)k;
     return fma(dk, hb_k[17], f - (hfsq - fma(s, hfsq + R, dk * hb_k[18])));
 }
+#endif
 // pow(x, y) for x >= 0 (the models raise clamped, non-negative ratios to parameter exponents): exp(y log x), 0^y = 0 for y > 0,
 // x^0 = 1.  Relative error ~|y log x| * 1.2e-16 (the product is rounded once) — far inside the 1e-10 parity budget — at a
 // quarter of the ~200 instructions of libdevice's pow with its special-case branches; negative or NaN x gives NaN like Julia's

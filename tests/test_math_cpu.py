@@ -109,7 +109,33 @@ def test_tanh_and_rcp(hbm, hbm_tanh10):
     assert (np.abs(hbm(3, y) * y - 1.0)).max() < 5e-16
 
 
-def test_log_and_pow(hbm):
+@pytest.fixture(scope="module")
+def hbm_logpoly():
+    return _build("#define HB_LOG_TABLE 0")
+
+
+def test_table_log_and_pow(hbm):
+    """Table form of hb_log_pos (the default wherever a body raises to a power): |error| <= 7e-16 max(|log x|, 1), and
+    hb_pow = exp(y log x) within the rounding of the product plus |y| times that."""
+    rng = np.random.default_rng(3)
+    x = np.abs(np.concatenate([10.0 ** rng.uniform(-300, 300, 200000), rng.uniform(0.5, 2.0, 200000), rng.uniform(1e-9, 1.0, 200000),
+                               1.0 + rng.normal(0, 1e-6, 2000), [1.0, 2.0, 0.5, np.sqrt(2.0), 1.0 - 2.0 ** -53, 1.0 + 2.0 ** -52]]))
+    ref = np.log(x.astype(np.longdouble))
+    err = np.abs(hbm(4, x) - ref).astype(np.float64)
+    assert np.all(err <= 7e-16 * np.maximum(np.abs(ref).astype(np.float64), 1.0))
+    xb = np.concatenate([rng.uniform(0.0, 1.0, 200000), rng.uniform(1e-12, 1e3, 100000)])
+    yb = np.concatenate([rng.uniform(0.05, 8.0, 200000), rng.uniform(-3.0, 6.0, 100000)])
+    got, refp = hbm.pow(xb, yb), np.power(xb.astype(np.longdouble), yb.astype(np.longdouble))
+    ok = (refp > 1e-300) & np.isfinite(refp)
+    ylx = np.abs(yb * np.log(np.maximum(xb, 1e-300)))
+    bound = 3.0 * 1.12e-16 * (1.0 + ylx) + 8e-16 * np.abs(yb) * np.maximum(np.abs(np.log(np.maximum(xb, 1e-300))), 1.0)
+    assert np.all(np.abs((got[ok] - refp[ok]) / refp[ok]).astype(np.float64) <= bound[ok])
+    assert hbm.pow([0.0, 0.0, 0.0, 5.0, 1e-320], [2.5, 0.0, 1.0, 0.0, 3.0]).tolist() == [0.0, 1.0, 0.0, 1.0, 0.0]
+    assert np.isnan(hbm.pow([-1.0], [2.5])[0]) and np.isinf(hbm.pow([0.0], [-1.0])[0])
+
+
+def test_log_and_pow(hbm_logpoly):
+    hbm = hbm_logpoly
     """hb_log_pos: < 1 ulp-ish against libm over the normal range; hb_pow = exp(y log x): relative error bounded by the rounding
     of the product y*log(x) (~|y log x| * 1.2e-16) plus the two kernels, and the x = 0 / y = 0 limits of the reference's `^`."""
     rng = np.random.default_rng(3)
