@@ -662,9 +662,13 @@ int hb_compile_stepper(const hb_stepper_spec *spec, const char *body, hb_model_t
     if (spec->metric < 0 || spec->metric > HB_METRIC_SSE) return fail(HB_ERR_INVALID, "unknown metric %d", spec->metric);
     hb_model_s *m = new hb_model_s();
     m->spec = *spec;
-    m->block = spec->block_threads > 0 ? spec->block_threads : 128;
+    // defaults (tools/r2_tune2.sh, profiles/round2_block_stages_sweep.txt): record-writing Float64 bodies without MLPs are HBM-bound and
+    // run best as many small blocks with a deep forcing ring — 64 threads x 8 steps: ExpHydro 0.947, GR4J + UH 0.93 (128 x 4: 0.87), HBV
+    // 0.93 (0.85); MLP bodies (tensor tiles of 128 basins per CTA) and objective runs keep 128 x 4
+    const bool plain_rows = spec->output_mode != HB_OUT_OBJECTIVE && spec->nn_words == 0 && !spec->precision;
+    m->block = spec->block_threads > 0 ? spec->block_threads : (plain_rows ? 64 : 128);
     if (m->block % 32 || m->block > 1024) { delete m; return fail(HB_ERR_INVALID, "block_threads must be a multiple of 32 <= 1024"); }
-    int stages = spec->stages > 0 ? spec->stages : 4;
+    int stages = spec->stages > 0 ? spec->stages : (plain_rows ? 8 : 4);
     for (int u = 0; u < spec->n_uh; ++u) {
         if (spec->uh_kmax[u] < 1) { delete m; return fail(HB_ERR_INVALID, "uh_kmax must be >= 1"); }
         m->uhw_total += spec->uh_kmax[u];
