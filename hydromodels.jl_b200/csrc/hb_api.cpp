@@ -1060,12 +1060,18 @@ int hb_compile_adjoint(const hb_adjoint_spec *spec, const char *body, hb_model_t
     m->block = spec->block_threads > 0 ? spec->block_threads : 128;
     if (m->block % 32 || m->block > 1024) { delete m; return fail(HB_ERR_INVALID, "block_threads must be a multiple of 32 <= 1024"); }
     // per warp: transposition scratch (2 x 32 x 20 doubles) + the accumulator fragments of every dense layer
-    m->dyn_smem = (m->block / 32) * (2 * 32 * 20 + spec->acc_doubles_per_warp) * 8;
+    m->dyn_smem = (m->block / 32) * (2 * 32 * 17 + spec->acc_doubles_per_warp) * 8;      // scratch pitch: HB_OP in templates/adjoint.cu
     if (m->dyn_smem + 4096 > 227 * 1024) { delete m; return fail(HB_ERR_INVALID, "adjoint kernel needs too much shared memory; use a smaller block"); }
+    // resident blocks per SM the shared memory allows (2 KB exp table, 2 KB log table, 1 KB system per block), at most 3: the
+    // kernel is latency-bound, so three blocks of 168 registers beat two of 255 (M50 50 k nodes: one wave instead of 1.32)
+    int minblocks = (227 * 1024) / (m->dyn_smem + 5 * 1024);
+    if (minblocks > 3) minblocks = 3;
+    if (minblocks < 1) minblocks = 1;
+    if (const char *e = getenv("HB_ADJ_MINBLOCKS")) { int v = atoi(e); if (v >= 1 && v <= 4) minblocks = v; }
     char defs[512];
     snprintf(defs, sizeof defs, "//@@HB:DEFINES\n#define HB_V %d\n#define HB_S %d\n#define HB_NP %d\n#define HB_NN_WORDS %d\n#define HB_BLOCK %d\n"
-             "#define HB_UHW_TOTAL 0\n#define HB_UHH_TOTAL 0\n",
-             spec->n_inputs, spec->n_states, spec->n_params, spec->nn_words, m->block);
+             "#define HB_UHW_TOTAL 0\n#define HB_UHH_TOTAL 0\n#define HB_ADJ_MINBLOCKS %d\n",
+             spec->n_inputs, spec->n_states, spec->n_params, spec->nn_words, m->block, minblocks);
     std::string full_body = std::string(defs) + body + "\n//@@HB:MATH\n" + kMathHeader + "\n";
     m->source = splice(kAdjointTemplate, full_body.c_str());
     m->kernel_name = "hb_adjoint";

@@ -64,16 +64,21 @@ __constant__ double hb_nn_const[HB_NN_WORDS];
 // ---- weight gradients on the FP64 tensor pipe ---------------------------------------------------------------------
 // dW[o][i] += sum over the warp's 32 nodes of delta_o(node) * a_i(node) is a [NO x 32] x [32 x NI] contraction with the NODES
 // as the K dimension: mma.sync.m8n8k4.f64 (SASS DMMA), 8 instructions per 8 x 8 tile.  Every lane writes its delta / activation
-// vectors into a per-warp scratch (pitch 20 doubles: conflict-free for the fragment reads below), the fragments are read back
-// as   A[m = lane/4][k = lane%4] = delta_{8 ot + lane/4}(node 4 s + lane%4),   B[k = lane%4][n = lane/4] = a_{8 it + lane/4}(same node),
+// vectors into a per-warp scratch, the fragments are read back as
+//   A[m = lane/4][k = lane%4] = delta_{8 ot + lane/4}(node 4 s + lane%4),   B[k = lane%4][n = lane/4] = a_{8 it + lane/4}(same node),
 // and the accumulator fragments (lane holds dW[8 ot + lane/4][8 it + 2 (lane%4) + {0, 1}]) live in shared memory between calls:
-// tile t, element e of this lane at acc[(2 t + e) * 32 + lane].  Bias gradients (sum of delta) use B = 1: one more tile per ot.
-#define HB_OP 20
+// tile t, element e of this lane at acc[(2 t + e) * 32 + lane].
+// Bias gradients (sum of delta over the nodes) of ALL layers of a network share ONE tile: the B operand of output tile `ot` of
+// a layer is the one-hot selector of column slot + ot, so that column collects the row sums of that delta tile (round 2: one
+// bias tile per output tile cost 4 KB of shared memory per warp, which — with the scratch — kept the kernel at two blocks per SM
+// and 1.32 waves for 50 000 nodes; scratch pitch 17 instead of 20: conflict-free writes, 4-way reads instead of the reverse).
+#define HB_OP 17
 __device__ __forceinline__ void hb_dmma(double &d0, double &d1, const double a, const double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 template <int NO, int NI>
-__device__ __forceinline__ void hb_outer_acc(double *__restrict__ scr, double *__restrict__ acc, const int lane, const double *d, const double *a) {
+__device__ __forceinline__ void hb_outer_acc(double *__restrict__ scr, double *__restrict__ acc, double *__restrict__ bacc, const int slot,
+                                             const int lane, const double *d, const double *a) {
     constexpr int OT = NO / 8, IT = NI / 8;
     double *sD = scr, *sA = scr + 32 * HB_OP;
     __syncwarp();
@@ -83,9 +88,14 @@ __device__ __forceinline__ void hb_outer_acc(double *__restrict__ scr, double *_
     for (int i = 0; i < NI; ++i) sA[lane * HB_OP + i] = a[i];
     __syncwarp();
     const int q = lane >> 2, j = lane & 3;
-    double c[OT * (IT + 1)][2];
+    double c[OT * IT][2], cb[2];
 #pragma unroll
-    for (int t = 0; t < OT * (IT + 1); ++t) { c[t][0] = acc[(2 * t) * 32 + lane]; c[t][1] = acc[(2 * t + 1) * 32 + lane]; }
+    for (int t = 0; t < OT * IT; ++t) { c[t][0] = acc[(2 * t) * 32 + lane]; c[t][1] = acc[(2 * t + 1) * 32 + lane]; }
+    cb[0] = bacc[lane];
+    cb[1] = bacc[32 + lane];
+    double sel[OT];
+#pragma unroll
+    for (int ot = 0; ot < OT; ++ot) sel[ot] = (q == slot + ot) ? 1.0 : 0.0;
 #pragma unroll
     for (int s8 = 0; s8 < 8; ++s8) {
         const int node = 4 * s8 + j;
@@ -98,15 +108,18 @@ __device__ __forceinline__ void hb_outer_acc(double *__restrict__ scr, double *_
         for (int ot = 0; ot < OT; ++ot) {
 #pragma unroll
             for (int it = 0; it < IT; ++it) hb_dmma(c[ot * IT + it][0], c[ot * IT + it][1], af[ot], bf[it]);
-            hb_dmma(c[OT * IT + ot][0], c[OT * IT + ot][1], af[ot], 1.0);
+            hb_dmma(cb[0], cb[1], af[ot], sel[ot]);
         }
     }
 #pragma unroll
-    for (int t = 0; t < OT * (IT + 1); ++t) { acc[(2 * t) * 32 + lane] = c[t][0]; acc[(2 * t + 1) * 32 + lane] = c[t][1]; }
+    for (int t = 0; t < OT * IT; ++t) { acc[(2 * t) * 32 + lane] = c[t][0]; acc[(2 * t + 1) * 32 + lane] = c[t][1]; }
+    bacc[lane] = cb[0];
+    bacc[32 + lane] = cb[1];
 }
 // add this warp's fragments of one layer to the global gradient: weight[out, in] column-major at g[i * n_out + o], bias at g[n_in * n_out + o]
 template <int NO, int NI>
-__device__ __forceinline__ void hb_outer_flush(const double *__restrict__ acc, const int lane, double *g, const int n_out, const int n_in) {
+__device__ __forceinline__ void hb_outer_flush(const double *__restrict__ acc, const double *__restrict__ bacc, const int slot, const int lane,
+                                               double *g, const int n_out, const int n_in) {
     constexpr int OT = NO / 8, IT = NI / 8;
     const int q = lane >> 2, j = lane & 3;
 #pragma unroll
@@ -119,13 +132,18 @@ __device__ __forceinline__ void hb_outer_flush(const double *__restrict__ acc, c
                 const int i = 8 * it + 2 * j + e;
                 if (o < n_out && i < n_in) atomicAdd(g + i * n_out + o, acc[(2 * (ot * IT + it) + e) * 32 + lane]);
             }
-        if (j == 0 && o < n_out) atomicAdd(g + n_in * n_out + o, acc[(2 * (OT * IT + ot)) * 32 + lane]);   // every column of a bias tile holds the sum
+        // column slot + ot of the bias tile: held by the lanes with 2 j + e == slot + ot
+        const int col = slot + ot;
+        if (j == (col >> 1) && o < n_out) atomicAdd(g + n_in * n_out + o, bacc[(col & 1) * 32 + lane]);
     }
 }
 
 //@@HB:HELPERS
 
-extern "C" __global__ void __launch_bounds__(HB_BLOCK) hb_adjoint(const __grid_constant__ HbAdjArgs a) {
+#ifndef HB_ADJ_MINBLOCKS
+#define HB_ADJ_MINBLOCKS 1
+#endif
+extern "C" __global__ void __launch_bounds__(HB_BLOCK, HB_ADJ_MINBLOCKS) hb_adjoint(const __grid_constant__ HbAdjArgs a) {
     const int lane = threadIdx.x & 31;
     const i64 n = (i64)blockIdx.x * HB_BLOCK + threadIdx.x;
     hb_math_init();   // exp table -> shared memory (block barrier inside)

@@ -777,29 +777,34 @@ def _mlp_helper_bwd(idx: int, chain, offset: int) -> str:
         L.append(f"    dx[{i}] = {g_out[i]};")
     # weight gradient: per layer one warp-wide outer-product accumulation on the FP64 tensor pipe (templates/adjoint.cu:
     # hb_outer_acc), delta and input vectors zero-padded to multiples of 8
-    acc_off = 0
+    layers, bias_off, _ = _adjoint_acc_layout(chain, offset)
     for li, l in enumerate(chain.layers):
-        NO, NI = -(-l.n_out // 8) * 8, -(-l.n_in // 8) * 8
+        acc_off, NO, NI, _, _, _, slot = layers[li]
         if NO > 16 or NI > 16:
             raise LoweringError("the adjoint run handles dense layers up to 16 x 16 (scratch pitch)")
         dd = deltas[li] + ["0.0"] * (NO - l.n_out)
         aa = acts_in[li] + ["0.0"] * (NI - l.n_in)
         L.append(f"    {{ const double dd[{NO}] = {{{', '.join(dd)}}}; const double aa[{NI}] = {{{', '.join(aa)}}};")
-        L.append(f"      hb_outer_acc<{NO}, {NI}>(scr, gw + {acc_off}, lane, dd, aa); }}")
-        acc_off += (NO // 8) * (NI // 8 + 1) * 64
+        L.append(f"      hb_outer_acc<{NO}, {NI}>(scr, gw + {acc_off}, gw + {bias_off}, {slot}, lane, dd, aa); }}")
     L.append("}")
     return "\n".join(L)
 
 
 def _adjoint_acc_layout(chain, offset: int):
-    """[(acc offset in doubles, NO, NI, flat parameter offset, n_out, n_in)] per layer, and the chain's accumulator doubles."""
-    out, acc_off, off = [], 0, offset
+    """[(acc offset in doubles, NO, NI, flat parameter offset, n_out, n_in, bias slot)] per layer, the offset of the chain's shared
+    bias tile and the chain's accumulator doubles.  The bias gradients of all layers share one 8 x 8 tile: output tile `ot` of a
+    layer owns column `slot + ot` (templates/adjoint.cu: hb_outer_acc)."""
+    out, acc_off, off, slot = [], 0, offset, 0
     for l in chain.layers:
         NO, NI = -(-l.n_out // 8) * 8, -(-l.n_in // 8) * 8
-        out.append((acc_off, NO, NI, off, l.n_out, l.n_in))
-        acc_off += (NO // 8) * (NI // 8 + 1) * 64
+        out.append((acc_off, NO, NI, off, l.n_out, l.n_in, slot))
+        acc_off += (NO // 8) * (NI // 8) * 64
+        slot += NO // 8
         off += l.n_params
-    return out, acc_off
+    if slot > 8:
+        raise LoweringError("the adjoint run packs the bias gradients of a network into one 8-column tile: at most 8 output tiles per chain")
+    bias_off = acc_off
+    return out, bias_off, acc_off + 64
 
 
 def _emit_adjoint(b: "_Builder", sim: int, statements, param_slots, nets, nn_layout, raw_states, state_floor, input_names,
@@ -989,10 +994,11 @@ def _emit_adjoint(b: "_Builder", sim: int, statements, param_slots, nets, nn_lay
             epi.extend(vjp(v, f"ah{v.id}"))
     goffs, acc_total, flush = [], 0, []
     for ch, (_, off, _) in zip(nets, nn_layout):
-        layers, n_acc = _adjoint_acc_layout(ch, off)
+        layers, bias_off, n_acc = _adjoint_acc_layout(ch, off)
         goffs.append(acc_total)
-        for a_off, NO, NI, p_off, n_out, n_in in layers:
-            flush.append(f"hb_outer_flush<{NO}, {NI}>(hb_gw + {acc_total + a_off}, lane, a.grad_nn + {p_off}, {n_out}, {n_in});")
+        for a_off, NO, NI, p_off, n_out, n_in, slot in layers:
+            flush.append(f"hb_outer_flush<{NO}, {NI}>(hb_gw + {acc_total + a_off}, hb_gw + {acc_total + bias_off}, {slot}, lane, "
+                         f"a.grad_nn + {p_off}, {n_out}, {n_in});")
         acc_total += n_acc
     helpers = [_mlp_helper(i, ch, off, True) + "\n" + _mlp_helper_bwd(i, ch, off) for i, (ch, (_, off, _)) in enumerate(zip(nets, nn_layout))]
     defs = f"#define HB_ACC_DOUBLES {acc_total}\n" + "".join(f"#define HB_GOFF_{i} {g}\n" for i, g in enumerate(goffs))
