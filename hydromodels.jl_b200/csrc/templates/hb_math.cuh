@@ -129,7 +129,8 @@ HB_DEV int hb_double2hiint(double x) {
 // Polynomial / reduction constants whose double representation has a non-zero low word cannot be instruction immediates: as
 // literals the compiler re-materialises each of them with two UMOV / IMAD.MOV per use INSIDE the time loop (22 + ~10 of the
 // 246 instructions of an HBV step, 81 of ExpHydro's 451 — issue slots, and the issue port is what bounds these kernels).  Read
-// from a (non-const, so not foldable) __constant__ array they are c[bank][offset] operands of the DFMA itself: no instruction.
+// from a (non-const, so not foldable) __constant__ array they are loaded ONCE per kernel (LDC / LDCU into registers or uniform
+// registers — sm_100 FP64 instructions take uniform-register operands — hoisted out of the time loop): no instruction per use.
 #ifdef HB_HOST_TEST
 #define HB_KBANK static const double
 #else
