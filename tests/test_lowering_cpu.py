@@ -158,3 +158,15 @@ def test_per_component_configs_bake_their_state_floors():
     assert np.array_equal(same, ref)
     with pytest.raises(ValueError, match="Component configs length"):
         ho.run_model(model, inp, p, cfgs[:1], init)
+
+
+def test_issue_slot_lowerings_fire():
+    """Round-2 lowerings that trim issue slots of the compute-bound kernels: `max(0, x)` becomes the sign-bit test `hb_relu`, and a
+    body that raises to a power asks for the table logarithm (`HB_LOG_TABLE`, 2 KB of shared memory) — others do not pay for it."""
+    hbv = hm.lower_stepper(hm.models.hbv(htypes=[1, 2]))
+    assert "hb_relu(" in hbv.body and "hb_max(0.0" not in hbv.body and "hb_max(hb_minv" in hbv.body
+    assert "#define HB_LOG_TABLE 1" in hbv.body and "hb_pow(" in hbv.body
+    exp = hm.lower_stepper(hm.models.exphydro(htypes=[1]))
+    assert "HB_LOG_TABLE" not in exp.body and "hb_relu(" in exp.body
+    f32 = hm.lower_stepper(hm.models.hbv(htypes=[1]), precision="f32")
+    assert "HB_LOG_TABLE" not in f32.body
