@@ -82,6 +82,7 @@ function lower(b::Builder, ex, env::Dict{Symbol,String}, params::Set{Symbol})
     args = [lower(b, a, env, params) for a in SymbolicUtils.arguments(ex)]
     ponly = all(a -> occursin(r"^[-0-9.]", a) || startswith(a, "hb_p[") || get(b.isparam, a, false), args)
     fold(f) = foldl((x, y) -> "($x $f $y)", args)
+    is_zero(s) = s in ("0.0", "0", "0.0e0")      # max(0, x) lowers to the sign-bit test hb_relu like lowering._expr_with (Python host)
     text = if op === (+);  fold("+")
     elseif op === (*);     fold("*")
     elseif op === (-);     length(args) == 1 ? "(-$(args[1]))" : "($(args[1]) - $(args[2]))"
@@ -93,8 +94,8 @@ function lower(b::Builder, ex, env::Dict{Symbol,String}, params::Set{Symbol})
     elseif op === abs;     "fabs($(args[1]))"
     elseif op === tanh;    "hb_tanh($(args[1]))"       # step_func traces to 0.5*(1+tanh(5x)) (src/HydroModels.jl:204)
     elseif op === min;     "hb_min($(args[1]), $(args[2]))"
-    elseif op === max;     "hb_max($(args[1]), $(args[2]))"
-    elseif op === clamp;   "hb_min(hb_max($(args[1]), $(args[2])), $(args[3]))"
+    elseif op === max;     is_zero(args[1]) ? "hb_relu($(args[2]))" : is_zero(args[2]) ? "hb_relu($(args[1]))" : "hb_max($(args[1]), $(args[2]))"
+    elseif op === clamp;   "hb_min(" * (is_zero(args[2]) ? "hb_relu($(args[1]))" : "hb_max($(args[1]), $(args[2]))") * ", $(args[3]))"
     else error("Unknown function: $op")
     end
     return emit!(b, (op, args...), text, ponly)
@@ -198,8 +199,10 @@ function lower_stepper(model::HydroModel; fluxes_of, uh_kmax::Vector{Int}=Int[])
     for (r, nm) in enumerate(rows); push!(b.lines_step, "hb_out[$(r - 1)] = $(env[nm]);"); end
     for si in 0:length(states)-1; push!(b.lines_step, "hb_u[$si] = hb_un$si;"); end
     append!(b.lines_step, uh_tail)
-    body = "//@@HB:DEFINES\n#define HB_NC 0\n//@@HB:HELPERS\n//@@HB:PROLOGUE\n" * join(b.lines_pro, "\n") *
-           "\n//@@HB:STEP\n" * join(b.lines_step, "\n") * "\n"
+    # bodies that raise to a power get the table logarithm of hb_math.cuh (2 KB more shared memory), as the Python host decides
+    uses_pow = any(occursin("hb_pow(", l) for l in vcat(b.lines_pro, b.lines_step))
+    body = "//@@HB:DEFINES\n" * (uses_pow ? "#define HB_LOG_TABLE 1\n" : "") * "#define HB_NC 0\n//@@HB:HELPERS\n//@@HB:PROLOGUE\n" *
+           join(b.lines_pro, "\n") * "\n//@@HB:STEP\n" * join(b.lines_step, "\n") * "\n"
     return Plan(body, uh_kmax, uhs, inputs, rows, states, pnames)
 end
 
